@@ -1,0 +1,277 @@
+/*
+ * sosfront.h — C-ABI of libsosfront.so, the B200 (sm_100a) SOS visual-odometry front-end.
+ *
+ * This is the drop-in boundary for the per-frame hot path of ubuntuslave/vo_single_camera_sos.
+ * The reference is pure Python and has no FFI of its own; every entry point below replaces one
+ * call the reference makes into NumPy / OpenCV / OpenGV on that path.  The "replaces:" line of
+ * each function cites the reference call site (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns an int status: SOS_OK (0) or a negative SOS_ERR_* code; the message
+ *     of the last failure on the calling thread is returned by sos_last_error().  Nothing throws,
+ *     nothing calls exit().
+ *   - all array arguments are plain pointers to C-contiguous (row-major) memory.  Unless a
+ *     function name ends in _host, array pointers are DEVICE pointers and the call is asynchronous
+ *     on the context's stream.  *_host functions take HOST pointers, stage through the context's
+ *     device buffers (H2D, kernels, D2H) and return after the results are in host memory.
+ *   - scalar / small struct parameters (sizes, thresholds, GUM parameter vectors, foci) are always
+ *     passed by value or as HOST pointers.
+ *   - the caller owns every input and output buffer.  Scratch memory lives in the context and only
+ *     grows (sos_ctx_reserve pre-sizes it, which is required before CUDA-graph capture).
+ *   - a sos_ctx is bound to one device and one stream and must be used by one thread at a time
+ *     (the reference calls arrive on its VO thread, pose_est_tools.py:1725-1727).
+ */
+#ifndef SOSFRONT_H_
+#define SOSFRONT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOS_OK 0
+#define SOS_ERR_INVALID (-1)     /* bad argument */
+#define SOS_ERR_CUDA (-2)        /* CUDA runtime / launch failure */
+#define SOS_ERR_NOMEM (-3)       /* allocation failure */
+#define SOS_ERR_UNSUPPORTED (-4) /* valid request this build cannot serve */
+#define SOS_ERR_CAPTURE (-5)     /* would have to allocate while the stream is being captured */
+
+#define SOS_ABI_VERSION 1
+
+typedef struct sos_ctx sos_ctx;
+
+/* ------------------------------------------------------------------------------------------------
+ * Context, stream and memory plumbing
+ * ---------------------------------------------------------------------------------------------- */
+int sos_abi_version(void);
+const char* sos_last_error(void);
+int sos_device_count(int* count);
+int sos_ctx_create(int device, sos_ctx** out);
+int sos_ctx_destroy(sos_ctx* ctx);
+/* Borrow an externally owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) instead of the stream the
+ * context created for itself; NULL selects the legacy default stream. */
+int sos_ctx_set_stream(sos_ctx* ctx, void* cuda_stream);
+void* sos_ctx_get_stream(sos_ctx* ctx);
+int sos_ctx_sync(sos_ctx* ctx);
+/* Make sure the context scratch arena holds at least `bytes`. */
+int sos_ctx_reserve(sos_ctx* ctx, size_t bytes);
+/* Number of kernel launches issued through this context since creation (for bench.py's gpu_launches). */
+int64_t sos_ctx_launch_count(sos_ctx* ctx);
+
+int sos_malloc(sos_ctx* ctx, size_t bytes, void** dptr);
+int sos_free(sos_ctx* ctx, void* dptr);
+int sos_malloc_host(size_t bytes, void** hptr); /* pinned */
+int sos_free_host(void* hptr);
+int sos_memcpy_h2d(sos_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes); /* async on ctx stream */
+int sos_memcpy_d2h(sos_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes); /* async on ctx stream */
+int sos_memset(sos_ctx* ctx, void* dst_dev, int value, size_t bytes);
+
+/* ------------------------------------------------------------------------------------------------
+ * Step 1 — panoramic remap
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Packed fixed-point LUT entry (one uint64 per panorama pixel), the device form of what
+ * cv2.convertMaps(CV_16SC2) produces (panorama.py:482) plus the folded mirror mask:
+ *   bits  0..15  x0  (int16)  = sat_s16(cvRound(32*map_x) >> 5)
+ *   bits 16..31  y0  (int16)  = sat_s16(cvRound(32*map_y) >> 5)
+ *   bits 32..36  ax  = cvRound(32*map_x) & 31        bits 37..41  ay = cvRound(32*map_y) & 31
+ *   bits 48..51  tap i lies inside the source image  (i = 0:(y0,x0) 1:(y0,x0+1) 2:(y0+1,x0) 3:(y0+1,x0+1))
+ *   bits 52..55  tap i is inside AND its mask byte is non-zero (mask == NULL: same as inside)
+ * NaN / |32*x| >= 2^31 map to INT_MIN exactly as cvtps2dq does inside cv::remap. */
+typedef uint64_t sos_lut_entry;
+
+/* replaces: the per-frame float64->float32 cast + the float->fixed conversion inside cv2.remap
+ * (panorama.py:291-298) and the mirror mask of get_fully_masked_images (camera_models.py:2932-3010).
+ * map_x/map_y: [rows*cols]; mask: [src_h*src_w] uint8 or NULL; lut: [rows*cols]. */
+int sos_lut_pack_f32(sos_ctx* ctx, const float* map_x, const float* map_y, int rows, int cols,
+                     const uint8_t* mask, int src_h, int src_w, sos_lut_entry* lut);
+int sos_lut_pack_f64(sos_ctx* ctx, const double* map_x, const double* map_y, int rows, int cols,
+                     const uint8_t* mask, int src_h, int src_w, sos_lut_entry* lut);
+
+/* replaces: cv2.remap(src, map_x32, map_y32, INTER_LINEAR, dst, BORDER_CONSTANT, border) in
+ * Panorama.get_panoramic_image (panorama.py:293-298), for `views` LUTs at once (top and bottom
+ * mirror, camera_models.py:3119-3120), with `dst = mask ? src : background` of
+ * get_fully_masked_images applied at tap fetch.  Bit-exact with cv2.remap (Q5 coords, Q15 weights).
+ *   src  [batch, src_h, src_w, channels] uint8      lut [views, rows, cols]
+ *   dst  [batch, views, rows, cols, channels] uint8  border/background: HOST pointers to `channels` bytes
+ * channels in {1,3,4}. */
+int sos_remap_u8(sos_ctx* ctx, const uint8_t* src, int batch, int src_h, int src_w, int channels,
+                 const sos_lut_entry* lut, int views, int rows, int cols, const uint8_t* border,
+                 const uint8_t* background, uint8_t* dst);
+
+/* GUM parameter vector (HOST doubles), gum.py:48-140 Parameters + gum.py:361-383 set_model_params. */
+enum {
+  SOS_GUM_XI1 = 0, SOS_GUM_XI2, SOS_GUM_XI3, /* Cp_wrt_M */
+  SOS_GUM_K1, SOS_GUM_K2, SOS_GUM_K3,        /* forward radial distortion */
+  SOS_GUM_GAMMA1, SOS_GUM_GAMMA2, SOS_GUM_ALPHA_C, SOS_GUM_U0, SOS_GUM_V0,
+  SOS_GUM_L1, SOS_GUM_L2, SOS_GUM_L3,        /* inverse radial model (gum.py:2689-2694) */
+  SOS_GUM_P1, SOS_GUM_P2,                    /* tangential terms of the Heikkila inverse (gum.py:2713-2725) */
+  SOS_GUM_PLANE_K,                           /* z of the normalised projection plane wrt [M] (gum.py:379-382) */
+  SOS_GUM_USE_DISTORTION,                    /* 0/1 */
+  SOS_GUM_NPARAMS
+};
+
+/* replaces: GUM.get_pixel_from_3D_point_wrt_M (gum.py:2512-2551): points wrt [M] -> pixels.
+ * pts [n,3] float64 -> uv [n,2] float64. */
+int sos_gum_project(sos_ctx* ctx, const double* gum, const double* pts, int n, double* uv);
+
+/* replaces: Panorama._generate_LUTs (panorama.py:414-492): forward-project the cylinder grid.
+ * psi(c) = reversed linspace(0,2pi,cols,endpoint=False) and theta(r) = atan2(linspace(h_max,h_min,rows,
+ * endpoint=False), 1) are rounded to float32 as the reference does (panorama.py:431,441); rows whose
+ * theta lies outside [elev_lo, elev_hi] get NaN.  map_x/map_y: [rows*cols] float64. */
+int sos_lut_build(sos_ctx* ctx, const double* gum, int rows, int cols, double cyl_height_max,
+                  double cyl_height_min, double elev_lo, double elev_hi, double* map_x, double* map_y);
+
+/* ------------------------------------------------------------------------------------------------
+ * Step 2 — brute-force Hamming matching of 256-bit descriptors
+ * ---------------------------------------------------------------------------------------------- */
+
+/* replaces: cv2.BFMatcher(NORM_HAMMING).match / .knnMatch(k=2) (camera_models.py:402,421,442), for S
+ * independent (query, train) segment pairs in one launch (azimuthal buckets camera_models.py:3038,
+ * views, frame pairs).
+ *   q [sum Nq, 8] uint32, t [sum Nt, 8] uint32 (row = one 32-byte ORB descriptor)
+ *   seg_q, seg_t [S+1] int32 DEVICE prefix offsets; max_nq / max_nt: HOST upper bounds of any segment length
+ *   idx0, idx1 [sum Nq] int32: best / second-best train row RELATIVE to its segment (-1: none)
+ *   d0, d1     [sum Nq] int32: their Hamming distances (-1: none)
+ * Order is (distance, train index): ties go to the lowest train index, as OpenCV does.
+ * idx1/d1 may be NULL (1-NN only). */
+int sos_hamming_top2(sos_ctx* ctx, const uint32_t* q, const uint32_t* t, const int32_t* seg_q,
+                     const int32_t* seg_t, int n_seg, int max_nq, int max_nt, int32_t* idx0,
+                     int32_t* d0, int32_t* idx1, int32_t* d1);
+
+#define SOS_MATCH_NN 0    /* 1-NN, the reference default (k_best = 1, pose_est_tools.py:686) */
+#define SOS_MATCH_RATIO 1 /* keep m0 iff d0 < ratio * d1 (camera_models.py:421-436) */
+#define SOS_MATCH_CROSS 2 /* mutual nearest neighbours (BFMatcher crossCheck, camera_models.py:401) */
+
+/* replaces: the tail of FeatureMatcher.match — sorted(matches, key=distance) (camera_models.py:444) —
+ * followed by filter_pixel_correspondences (common_cv.py:167-188) as applied by
+ * match_features_panoramic_top_bottom (camera_models.py:3086) and match_features_frame_to_frame
+ * (pose_est_tools.py:245-247).  Per segment: select by `mode`, order stably by (distance, query index),
+ * then keep pairs with |u_t - u_q| <= max_du (if max_du > 0) and v_t - v_q >= min_dv (if min_dv >= 0),
+ * evaluated in float64 on the float32 pixel coordinates.
+ *   rev_idx0 [sum Nt]: best query row per train row (SOS_MATCH_CROSS only, else NULL)
+ *   px_q [sum Nq,2], px_t [sum Nt,2] float32 (u,v) or NULL when no gate is requested
+ *   out_q, out_t, out_d [sum Nq]: segment s writes its pairs from seg_q[s] on; out_q/out_t are GLOBAL rows
+ *   out_count [S]: pairs kept per segment. */
+int sos_match_select(sos_ctx* ctx, int mode, double ratio, const int32_t* idx0, const int32_t* d0,
+                     const int32_t* d1, const int32_t* rev_idx0, const int32_t* seg_q,
+                     const int32_t* seg_t, int n_seg, int max_nq, const float* px_q,
+                     const float* px_t, double max_du, double min_dv, int32_t* out_q,
+                     int32_t* out_t, int32_t* out_d, int32_t* out_count);
+
+/* ------------------------------------------------------------------------------------------------
+ * Steps 3+4 — lifting and midpoint triangulation, RGB-D back-projection (F12)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Panorama geometry (HOST doubles): cols, rows, pixel_size, cyl_height_max, cyl_circumference, cyl_radius */
+enum { SOS_PANO_COLS = 0, SOS_PANO_ROWS, SOS_PANO_PIXEL_SIZE, SOS_PANO_HEIGHT_MAX, SOS_PANO_CIRCUMFERENCE,
+       SOS_PANO_RADIUS, SOS_PANO_NPARAMS };
+
+/* replaces: Panorama.get_direction_angles_from_pixel_pano(use_LUTs=False) (panorama.py:616-666) +
+ * GUM.get_3D_point_from_angles_wrt_focus (gum.py:2564 -> camera_models.py:1031-1065).
+ * uv [n,2] float32 -> az, el [n] float32, bearing [n,3] float32 (NaN outside the panorama). Any output may be NULL. */
+int sos_lift_pano(sos_ctx* ctx, const double* pano, const float* uv, int n, float* az, float* el, float* bearing);
+
+/* replaces: GUM.lift_pixel_to_unit_sphere_wrt_focus (gum.py:2673-2940, new_method branch) and
+ * OmniCamModel.get_direction_angles_from_pixel (camera_models.py:1183-1194).
+ * uv [n,2] float64 omni-image pixels -> sphere [n,3] float64, az/el [n] float64 (may be NULL). */
+int sos_lift_gum(sos_ctx* ctx, const double* gum, const double* uv, int n, double* sphere, double* az, double* el);
+
+/* replaces: OmniStereoModel.get_triangulated_point_from_direction_angles(use_midpoint_triangulation=True)
+ * (camera_models.py:3323-3364 -> 2420-2490) + filter_panoramic_points_due_to_range (camera_models.py:3299-3321).
+ * az/el of the top (1) and bottom (2) rays [n] float32; f1, f2: HOST foci [3] in frame [C].
+ * xyz [n,3] float32; valid [n] uint8 (may be NULL) = (rmin <= norm <= rmax), rmin/rmax <= 0 disabling that bound.
+ * homogeneous_norm != 0 reproduces the reference's frame code, which hands the N x 4 HOMOGENEOUS array to the range
+ * filter (pose_est_tools.py:365-372) so that norm = sqrt(x^2 + y^2 + z^2 + 1). */
+int sos_triangulate_midpoint(sos_ctx* ctx, const float* az1, const float* el1, const float* az2,
+                             const float* el2, int n, const double* f1, const double* f2, double rmin,
+                             double rmax, int homogeneous_norm, float* xyz, uint8_t* valid);
+
+/* Fused steps 3+4 over matched pairs, driven by DEVICE-side counts (no host sync), as
+ * StereoPanoramicFrame.establish_stereo_correspondences does after matching (pose_est_tools.py:344-397).
+ * Frame f owns segments [f*segs_per_frame, (f+1)*segs_per_frame) (its azimuthal buckets, in order).  For segment s
+ * and k < pair_count[s], pair (q,t) = (pair_q[seg_off[s]+k], pair_t[seg_off[s]+k]) with q a bottom-view feature
+ * row and t a top-view feature row (both GLOBAL rows into px_bot / px_top [*,2] float32): lift both pixels (F7,F8),
+ * triangulate (F10), range-gate (F11) and append the survivors, in order, to the compacted per-frame
+ * correspondence store (T1, camera_models.py:291-362), rows [f*cap_per_frame, f*cap_per_frame + out_n[f]):
+ *   out_uv_top/out_uv_bot [*,2], out_b_top/out_b_bot [*,3] (unit bearings), out_xyz [*,3] float32,
+ *   out_src_top/out_src_bot [*] int32 (feature rows, for descriptor gathers), out_n [n_frames] int32. */
+int sos_stereo_lift_triangulate(sos_ctx* ctx, const double* pano_top, const double* pano_bot, const float* px_top,
+                                const float* px_bot, const int32_t* pair_q, const int32_t* pair_t,
+                                const int32_t* pair_count, const int32_t* seg_off, int n_frames, int segs_per_frame,
+                                const double* f1, const double* f2, double rmin, double rmax, int homogeneous_norm,
+                                int cap_per_frame, float* out_uv_top, float* out_uv_bot, float* out_b_top,
+                                float* out_b_bot, float* out_xyz, int32_t* out_src_top, int32_t* out_src_bot,
+                                int32_t* out_n);
+
+/* RGB-D intrinsics (HOST doubles): fx, fy, cx, cy, focal_length_m, depth_is_Z(0/1) — camera_models.py:752-779 */
+enum { SOS_RGBD_FX = 0, SOS_RGBD_FY, SOS_RGBD_CX, SOS_RGBD_CY, SOS_RGBD_FOCAL_M, SOS_RGBD_DEPTH_IS_Z, SOS_RGBD_NPARAMS };
+
+/* replaces: RGBDCamModel.get_depth_Z over the whole map (camera_models.py:781-799). depth/z [h,w] float32. */
+int sos_rgbd_depth_to_z(sos_ctx* ctx, const double* cam, const float* depth, int batch, int h, int w, float* z);
+
+/* replaces: RGBDCamModel.get_XYZ at keypoints (camera_models.py:835-860), get_normalized_points
+ * (camera_models.py:203-212) and the NaN / Z-range gate of RGBDFrame.establish_keypoints
+ * (pose_est_tools.py:612-620).  depth [batch,h,w] float32; u,v [batch,n] int32 pixel indices;
+ * xyz, bearing [batch,n,3] float32 (NaN where depth == 0); valid [batch,n] uint8 = !NaN && zmin <= Z <= zmax. */
+int sos_rgbd_backproject(sos_ctx* ctx, const double* cam, const float* depth, int batch, int h, int w,
+                         const int32_t* u, const int32_t* v, int n, double zmin, double zmax, float* xyz,
+                         float* bearing, uint8_t* valid);
+
+/* ------------------------------------------------------------------------------------------------
+ * Step 5 — batched RANSAC for rigid 3D-3D registration
+ * ---------------------------------------------------------------------------------------------- */
+
+#define SOS_SCORE_EUCLID 0  /* |p_ref - (R p_cur + t)| < thr */
+#define SOS_SCORE_BEARING 1 /* 1 - f . normalize(Rc^T (R^T (p_ref - t) - tc)) < thr  (pose_est_tools.py:150-203, 181-185) */
+
+/* replaces: transformations.superimposition_matrix(v0, v1, scale=False, usesvd=True)
+ * (transformations.py:982-1030 -> 874-980) for n_sets independent point sets of k points each.
+ * v0, v1 [n_sets, k, 3] float64 -> M [n_sets, 12] float64 (row-major 3x4 [R|t], v1 ~ R v0 + t);
+ * ok [n_sets] uint8 = 0 for degenerate (rank < 2) sets. */
+int sos_arun_batch(sos_ctx* ctx, const double* v0, const double* v1, int n_sets, int k, double* M, uint8_t* ok);
+
+/* One RANSAC problem per `problem` (frame pair).  The correspondences of problem b are rows
+ * [b*cap, b*cap + n[b]) of the arrays below, n DEVICE int32 [n_problems].
+ *   p_ref [*,3] float32  3D points in the reference frame (pose_est_tools.py:753-756)
+ *   p_cur [*,3] float32  3D points of the same landmarks in the current frame (Arun hypotheses; EUCLID score)
+ *   f_cur [*,3] float32  unit bearings in the current frame (BEARING score; may be NULL for EUCLID)
+ *   cam   [*]   uint8    camera index of each bearing (0 top, 1 bottom; NULL = central)
+ *   rig   HOST doubles [n_cams*12]: per camera row-major 3x4 [Rc|tc] (pose_est_tools.py:852-859), NULL = identity
+ * Hypotheses: hyp [n_hyp,3] uint32 DEVICE, shared by all problems; sample j of hypothesis h is row
+ * floor(hyp[h][j] * n / 2^32) (size-independent, so the oracle draws the same triples); a hypothesis with a
+ * repeated row or a degenerate (collinear) triple scores -1.  Best = highest inlier count, lowest h on ties
+ * (OpenGV's strict '>' update).
+ * Outputs: best_pose [n_problems,12] float32 (row-major [R|t] of the current frame wrt the reference frame,
+ * p_ref ~ R p_cur + t, what pyopengv.absolute_pose_*_ransac returns, pose_est_tools.py:785,915),
+ * best_hyp, best_count [n_problems] int32, inlier_mask [n_problems*cap] uint8,
+ * best_key [n_problems] uint64 = (count+1) << 32 | (0xFFFFFFFF - (hyp_offset + h)) for cross-GPU max-reduce. */
+int sos_ransac_p3d(sos_ctx* ctx, const float* p_ref, const float* p_cur, const float* f_cur, const uint8_t* cam,
+                   const int32_t* n, int n_problems, int cap, const double* rig, int n_cams, const uint32_t* hyp,
+                   int n_hyp, int hyp_offset, int score_mode, double threshold, float* best_pose,
+                   int32_t* best_hyp, int32_t* best_count, uint8_t* inlier_mask, uint64_t* best_key);
+
+/* Re-derive pose and inlier mask of hypothesis `hyp_index[b]` (DEVICE int32, GLOBAL index, i.e. the winner
+ * of the cross-GPU reduce) without scoring the others. */
+int sos_ransac_p3d_eval(sos_ctx* ctx, const float* p_ref, const float* p_cur, const float* f_cur, const uint8_t* cam,
+                        const int32_t* n, int n_problems, int cap, const double* rig, int n_cams,
+                        const uint32_t* hyp_row /* [n_problems,3] uint32: the winning triples */, int score_mode,
+                        double threshold, float* pose, int32_t* count, uint8_t* inlier_mask);
+
+/* Arun refit on the inlier set (stands in for pyopengv.*_optimize_nonlinear, pose_est_tools.py:830,937; an
+ * approximation — see DESIGN.md).  pose [n_problems,12] float32. */
+int sos_refit_inliers(sos_ctx* ctx, const float* p_ref, const float* p_cur, const uint8_t* inlier_mask,
+                      const int32_t* n, int n_problems, int cap, float* pose, int32_t* n_used);
+
+/* ------------------------------------------------------------------------------------------------
+ * Roofline denominators measured in-process (integer POPC pipe, FP32 FMA pipe) — bench.py only.
+ * ---------------------------------------------------------------------------------------------- */
+int sos_peak_popc(sos_ctx* ctx, double* tera_popc_per_s);
+int sos_peak_ffma(sos_ctx* ctx, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOSFRONT_H_ */

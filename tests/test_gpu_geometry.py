@@ -1,0 +1,165 @@
+"""GPU parity: lifting / triangulation / GUM / RGB-D kernels vs the reference-generated goldens and the oracle.
+Tolerance: 1e-4 relative on float32 outputs (north_star); float64 outputs (GUM paths) to 1e-9."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, sub
+from oracle import geometry
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def rel_close(got, ref, rtol=RTOL, atol=0.0):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    err = np.abs(got[ok] - ref[ok])
+    assert np.all(err <= atol + rtol * np.abs(ref[ok])), float(np.max(err / (np.abs(ref[ok]) + 1e-30)))
+
+
+def test_lift_pano_golden(ctx):
+    g = load_golden("lifting.npz")
+    pano = geometry.pano_vector(sub(g, "pano_top_"))
+    uv = dev(g["pano_px"][:, :2], torch.float32)
+    az, el, b = ctx.lift_pano(pano, uv)
+    rel_close(az.cpu().numpy(), g["pano_az"], atol=1e-6)
+    rel_close(el.cpu().numpy(), g["pano_el"], atol=1e-6)
+    rel_close(b.cpu().numpy(), g["pano_bearing"], atol=1e-6)
+    assert np.isnan(g["pano_az"]).any() and np.isnan(g["pano_el"]).any()  # out-of-panorama pixels are in the fixture
+
+
+def test_triangulation_golden(ctx):
+    g = load_golden("lifting.npz")
+    a = [dev(g[k], torch.float32) for k in ("tri_az1", "tri_el1", "tri_az2", "tri_el2")]
+    ref = g["tri_xyz_homo"][:, :3]
+    for homo, key in ((True, "tri_valid_homo"), (False, "tri_valid_xyz")):
+        xyz, valid = ctx.triangulate_midpoint(*a, g["tri_f1"], g["tri_f2"], 0.5, 7.0, homogeneous_norm=homo)
+        xyz, valid = xyz.cpu().numpy(), valid.cpu().numpy().astype(bool)
+        # norm-wise 1e-4 relative: a component near zero cannot be held to a relative bound of its own
+        err = np.linalg.norm(xyz - ref, axis=1) / np.linalg.norm(ref, axis=1)
+        assert err.max() < RTOL, err.max()
+        nrm = np.linalg.norm(np.hstack([ref, np.ones((len(ref), 1))]) if homo else ref, axis=1)
+        clear = (np.abs(nrm - 0.5) > 1e-3) & (np.abs(nrm - 7.0) > 1e-3)  # float32 output cannot decide exact ties
+        assert np.array_equal(valid[clear], g[key][clear])
+        assert clear.mean() > 0.99
+
+
+def test_stereo_fused_matches_unfused_oracle(ctx):
+    g = load_golden("lifting.npz")
+    rng = np.random.default_rng(3)
+    pano_t, pano_b = sub(g, "pano_top_"), sub(g, "pano_bot_")
+    cols, rows = int(pano_t["cols"]), int(pano_t["rows"])
+    n_frames, segs = 3, 4
+    n_top, n_bot = 500, 450
+    px_top = np.stack([rng.uniform(0, cols, n_top), rng.uniform(0, rows, n_top)], 1).astype(np.float32)
+    px_bot = np.stack([rng.uniform(0, cols, n_bot), rng.uniform(0, rows, n_bot)], 1).astype(np.float32)
+    seg_sizes = rng.integers(0, 60, n_frames * segs)
+    seg_sizes[5] = 0
+    seg_off = np.concatenate([[0], np.cumsum(seg_sizes + 3)])[:-1].astype(np.int32)  # slack between segments
+    total = int(seg_off[-1] + seg_sizes[-1] + 3)
+    pair_q = rng.integers(0, n_bot, total).astype(np.int32)
+    pair_t = rng.integers(0, n_top, total).astype(np.int32)
+    # make most pairs plausible stereo pairs: same column, top row below bottom row
+    px_top[pair_t] = px_bot[pair_q] + np.stack([rng.uniform(-2, 2, total), rng.uniform(1, 25, total)], 1).astype(np.float32)
+    f1, f2 = g["tri_f1"], g["tri_f2"]
+    cap = 128
+    out = ctx.stereo_lift_triangulate(geometry.pano_vector(pano_t), geometry.pano_vector(pano_b), dev(px_top), dev(px_bot),
+                                      dev(pair_q), dev(pair_t), dev(seg_sizes.astype(np.int32)), dev(seg_off), n_frames, segs,
+                                      f1, f2, 0.5, 7.0, cap, homogeneous_norm=True)
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    for f in range(n_frames):
+        rq = np.concatenate([pair_q[seg_off[s]:seg_off[s] + seg_sizes[s]] for s in range(f * segs, (f + 1) * segs)])
+        rt = np.concatenate([pair_t[seg_off[s]:seg_off[s] + seg_sizes[s]] for s in range(f * segs, (f + 1) * segs)])
+        az1, el1 = geometry.pano_pixel_to_angles(pano_t, px_top[rt])
+        az2, el2 = geometry.pano_pixel_to_angles(pano_b, px_bot[rq])
+        xyz = geometry.triangulate_midpoint(az1, el1, az2, el2, f1, f2)
+        homo = np.hstack([xyz, np.ones((len(xyz), 1))])
+        keep = geometry.range_filter(homo, 0.5, 7.0)
+        nrm = np.linalg.norm(homo, axis=1)
+        assert np.all((np.abs(nrm - 0.5) > 1e-6) & (np.abs(nrm - 7.0) > 1e-6) | np.isnan(nrm))  # margin asserted
+        n = int(out["n"][f])
+        assert n == min(int(keep.sum()), cap)
+        sl = slice(f * cap, f * cap + n)
+        assert np.array_equal(out["src_top"][sl], rt[keep][:n]) and np.array_equal(out["src_bot"][sl], rq[keep][:n])
+        assert np.array_equal(out["uv_top"][sl], px_top[rt[keep][:n]])
+        err = np.linalg.norm(out["xyz"][sl] - xyz[keep][:n], axis=1) / np.linalg.norm(xyz[keep][:n], axis=1)
+        assert err.max() < RTOL
+        rel_close(out["b_top"][sl], geometry.angles_to_sphere(az1, el1)[keep][:n], atol=1e-6)
+        rel_close(out["b_bot"][sl], geometry.angles_to_sphere(az2, el2)[keep][:n], atol=1e-6)
+
+
+def test_gum_lift_and_project_golden(ctx):
+    g = load_golden("lifting.npz")
+    for tag in ("heik", "poly"):
+        for name in ("top", "bot"):
+            pre = f"{tag}_{name}_"
+            p = geometry.gum_vector(sub(g, pre + "gum_"))
+            sphere, az, el = ctx.lift_gum(p, dev(g[pre + "omni_uv"]))
+            rel_close(sphere.cpu().numpy(), g[pre + "sphere"], rtol=1e-9, atol=1e-12)
+            rel_close(az.cpu().numpy(), g[pre + "omni_az"], rtol=1e-9, atol=1e-12)
+            rel_close(el.cpu().numpy(), g[pre + "omni_el"], rtol=1e-9, atol=1e-12)
+            uv = ctx.gum_project(p, dev(g[pre + "proj_pts"])).cpu().numpy()
+            rel_close(uv[:, 0], g[pre + "proj_u"], rtol=1e-9)
+            rel_close(uv[:, 1], g[pre + "proj_v"], rtol=1e-9)
+            # round trip: lift then project lands on the pixel again when there is no distortion mismatch
+    p = sub(g, "heik_top_gum_")
+    p.update(k1=0.0, k2=0.0, k3=0.0, p1=0.0, p2=0.0)
+    uv0 = g["heik_top_omni_uv"]
+    sphere, _, _ = ctx.lift_gum(geometry.gum_vector(p), dev(uv0))
+    back = ctx.gum_project(geometry.gum_vector(p), sphere).cpu().numpy()
+    assert np.allclose(back, uv0, atol=1e-8)
+
+
+def test_lut_build_golden(ctx):
+    g = load_golden("remap.npz")
+    for name in ("top", "bot"):
+        p = sub(g, f"gum_{name}_")
+        pano = sub(g, f"pano_{name}_")
+        lo, hi = g[f"elev_{name}"]
+        mx, my = ctx.lut_build(geometry.gum_vector(p), int(pano["rows"]), int(pano["cols"]), pano["cyl_height_max"],
+                               pano["cyl_height_min"], lo, hi)
+        su, sv = mx.cpu().numpy()[::5, ::7], my.cpu().numpy()[::5, ::7]
+        ru, rv = g[f"map_x64_sub_{name}"], g[f"map_y64_sub_{name}"]
+        assert np.array_equal(np.isnan(su), np.isnan(ru))
+        ok = ~np.isnan(ru)
+        assert np.max(np.abs(su[ok] - ru[ok])) < 1 / 64 and np.max(np.abs(sv[ok] - rv[ok])) < 1 / 64
+
+
+def test_rgbd_golden(ctx):
+    g = load_golden("rgbd.npz")
+    for tag in ("z", "radial"):
+        cam = g[f"{tag}_cam"]
+        z = ctx.rgbd_depth_to_z(cam, dev(g["depth"])).cpu().numpy()
+        rel_close(z, g[f"{tag}_depth_z"], atol=1e-9)
+        xyz, bearing, valid = ctx.rgbd_backproject(cam, dev(g["depth"]), dev(g["u"]), dev(g["v"]), 0.8, 7.0)
+        rel_close(xyz.cpu().numpy(), g[f"{tag}_xyz"], atol=1e-7)
+        rel_close(bearing.cpu().numpy(), g[f"{tag}_bearing"], atol=1e-6)
+        camd = dict(zip(geometry.RGBD_FIELDS, cam))
+        _, _, ov = geometry.rgbd_backproject(camd, g["depth"], g["u"], g["v"], 0.8, 7.0)
+        zz = g[f"{tag}_xyz"][:, 2]
+        clear = np.isnan(zz) | ((np.abs(np.abs(zz) - 0.8) > 1e-4) & (np.abs(np.abs(zz) - 7.0) > 1e-4))
+        assert np.array_equal(valid.cpu().numpy().astype(bool)[clear], ov[clear])
+
+
+def test_rgbd_full_frame_640x480(ctx):
+    rng = np.random.default_rng(8)
+    h, w, n = 480, 640, 2000
+    depth = rng.uniform(0.3, 9.0, (2, h, w)).astype(np.float32)
+    depth[rng.random(depth.shape) < 0.05] = 0
+    u = rng.integers(0, w, (2, n)).astype(np.int32)
+    v = rng.integers(0, h, (2, n)).astype(np.int32)
+    cam = dict(fx=554.256258, fy=554.256258, center_x=319.5, center_y=239.5, focal_length_m=1e-3, depth_is_Z=0.0)
+    xyz, bearing, valid = ctx.rgbd_backproject(geometry.rgbd_vector(cam), dev(depth), dev(u), dev(v), 0.8, 7.0)
+    for b in range(2):
+        oxyz, ob, ov = geometry.rgbd_backproject(cam, depth[b], u[b], v[b], 0.8, 7.0)
+        rel_close(xyz[b].cpu().numpy(), oxyz, atol=1e-7)
+        rel_close(bearing[b].cpu().numpy(), ob, atol=1e-6)

@@ -1,0 +1,146 @@
+"""CPU: the oracle restatements against the golden vectors produced by the reference itself (oracle/gen_golden.py)."""
+import numpy as np
+
+from conftest import load_golden, sub
+from oracle import geometry, hamming, ransac, remap
+
+
+def test_remap_spec_matches_reference_panoramas():
+    g = load_golden("remap.npz")
+    for name in ("top", "bot"):
+        mx, my, mask = g[f"map_x32_{name}"], g[f"map_y32_{name}"], g[f"mask_{name}"]
+        # black mask background + black border (demo_vo_sos.py path: mask_RGB=(0,0,0))
+        out = remap.remap_spec(g["img"], mx, my, border=(0, 0, 0), mask=mask, background=(0, 0, 0))
+        assert np.array_equal(out, g[f"pano_{name}"])
+        # same through OpenCV on the materialised masked image (what the reference literally does)
+        ref = remap.remap_reference(remap.masked_image(g["img"], mask), mx, my)
+        assert np.array_equal(ref, g[f"pano_{name}"])
+        # coloured background (RGB (10,200,90) -> BGR) and coloured border (RGB (30,60,250) -> BGR)
+        out = remap.remap_spec(g["img"], mx, my, border=(250, 60, 30), mask=mask, background=(90, 200, 10))
+        assert np.array_equal(out, g[f"pano_colour_{name}"])
+        # single-channel: the mirror mask itself remapped (panorama.py:534)
+        out = remap.remap_spec(mask, mx, my, border=(0,))
+        assert np.array_equal(out, g[f"pano_of_mask_{name}"])
+
+
+def test_remap_spec_matches_cv2_on_adversarial_maps():
+    rng = np.random.default_rng(0)
+    H, W = 97, 131
+    src = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    R, C = 120, 203
+    mx = rng.uniform(-3, W + 3, (R, C)).astype(np.float32)
+    my = rng.uniform(-3, H + 3, (R, C)).astype(np.float32)
+    mx[rng.random((R, C)) < 0.05] = np.nan
+    my[rng.random((R, C)) < 0.05] = np.nan
+    mx[0, :10] = [0, 0.5 / 32, 1.5 / 32, 2.5 / 32, W - 1, W - 1 + 0.5 / 32, W - 0.5, -1, -0.999, 1e20]
+    my[0, :10] = [0, 0.5 / 32, 1.5 / 32, 2.5 / 32, H - 1, H - 1, H - 0.5, -1, -0.5, 3]
+    ref = remap.remap_reference(src, mx, my, border=(7, 9, 11))
+    assert np.array_equal(remap.remap_spec(src, mx, my, border=(7, 9, 11)), ref)
+
+
+def test_lut_build_matches_reference_lut():
+    g = load_golden("remap.npz")
+    for name in ("top", "bot"):
+        p = sub(g, f"gum_{name}_")
+        pano = sub(g, f"pano_{name}_")
+        lo, hi = g[f"elev_{name}"]
+        u, v = geometry.lut_build(p, int(pano["rows"]), int(pano["cols"]), pano["cyl_height_max"], pano["cyl_height_min"], lo, hi)
+        ru, rv = g[f"map_x64_sub_{name}"], g[f"map_y64_sub_{name}"]
+        su, sv = u[::5, ::7], v[::5, ::7]
+        assert np.array_equal(np.isnan(su), np.isnan(ru))
+        ok = ~np.isnan(ru)
+        # the reference evaluates parts of the chain in float32 (panorama.py:431,441); 1/64 px is the SURVEY bar
+        assert np.max(np.abs(su[ok] - ru[ok])) < 1.0 / 64 and np.max(np.abs(sv[ok] - rv[ok])) < 1.0 / 64
+        assert np.allclose(su[ok].astype("float32"), g[f"map_x32_{name}"][::5, ::7][ok], atol=1 / 64)
+
+
+def test_hamming_oracle_matches_bfmatcher():
+    g = load_golden("hamming.npz")
+    q, t = g["q"], g["t"]
+    qi, ti, dd = hamming.match_select(q, t, "nn")
+    assert np.array_equal(qi, g["nn_q"]) and np.array_equal(ti, g["nn_t"]) and np.array_equal(dd, g["nn_d"].astype(np.int32))
+    i0, d0, i1, d1 = hamming.knn2(q, t)
+    assert np.array_equal(np.stack([i0, i1], 1), g["knn_t"])
+    assert np.array_equal(np.stack([d0, d1], 1), g["knn_d"].astype(np.int32))
+    # crossCheck: OpenCV returns mutual matches in query order
+    cq, ct, cd = hamming.match_select(q, t, "cross")
+    order = np.argsort(cq, kind="stable")
+    assert np.array_equal(cq[order], g["cross_q"]) and np.array_equal(ct[order], g["cross_t"])
+    assert np.array_equal(cd[order], g["cross_d"].astype(np.int32))
+    # and against live OpenCV
+    rq, rt, rd = hamming.bf_match_reference(q, t)
+    assert np.array_equal(i0, rt) and np.array_equal(d0, rd.astype(np.int32))
+
+
+def test_stereo_and_temporal_matching_oracle():
+    g = load_golden("matching_frames.npz")
+    m_top, m_bot = [], []
+    for b in range(int(g["n_buckets"])):
+        q, t = g[f"b{b}_d_bot"], g[f"b{b}_d_top"]
+        if len(q) == 0 or len(t) == 0:
+            continue
+        qi, ti, _ = hamming.match_select(q, t, "nn")
+        m_top.append(g[f"b{b}_pt_top"][ti])
+        m_bot.append(g[f"b{b}_pt_bot"][qi])
+    m_top, m_bot = np.concatenate(m_top).astype(np.float64), np.concatenate(m_bot).astype(np.float64)
+    ok = hamming.filter_pixel_correspondences(m_top, m_bot, 1, 2.5)
+    assert np.array_equal(m_top[ok], g["stereo_m_top"][:, :2]) and np.array_equal(m_bot[ok], g["stereo_m_bot"][:, :2])
+    assert 0 < ok.sum() < len(ok)
+    qi, ti, _ = hamming.match_select(g["f2f_q"], g["f2f_t"], "nn", px_q=g["f2f_pq"][:, :2], px_t=g["f2f_pt"][:, :2],
+                                     max_du=float(g["f2f_max_du"]), min_dv=-1)
+    assert np.array_equal(qi, g["f2f_query_idx"]) and np.array_equal(ti, g["f2f_train_idx"])
+
+
+def test_lifting_and_triangulation_oracle():
+    g = load_golden("lifting.npz")
+    pano = sub(g, "pano_top_")
+    az, el = geometry.pano_pixel_to_angles(pano, g["pano_px"])
+    assert np.array_equal(np.isnan(az), np.isnan(g["pano_az"])) and np.array_equal(np.isnan(el), np.isnan(g["pano_el"]))
+    assert np.allclose(az, g["pano_az"], rtol=0, atol=1e-15, equal_nan=True)
+    assert np.allclose(el, g["pano_el"], rtol=0, atol=1e-15, equal_nan=True)
+    assert np.allclose(geometry.angles_to_sphere(az, el), g["pano_bearing"], atol=1e-15, equal_nan=True)
+    xyz = geometry.triangulate_midpoint(g["tri_az1"], g["tri_el1"], g["tri_az2"], g["tri_el2"], g["tri_f1"], g["tri_f2"])
+    ref = g["tri_xyz_homo"][:, :3]
+    assert np.allclose(xyz, ref, rtol=1e-9, atol=1e-12)
+    homo = np.hstack([xyz, np.ones((len(xyz), 1))])
+    assert np.array_equal(geometry.range_filter(homo, 0.5, 7.0), g["tri_valid_homo"])
+    assert np.array_equal(geometry.range_filter(xyz, 0.5, 7.0), g["tri_valid_xyz"])
+    assert not np.array_equal(g["tri_valid_homo"], g["tri_valid_xyz"])  # the homogeneous-norm quirk is observable
+    for tag in ("heik", "poly"):
+        for name in ("top", "bot"):
+            pre = f"{tag}_{name}_"
+            p = sub(g, pre + "gum_")
+            Ps, a, e = geometry.gum_lift(p, g[pre + "omni_uv"])
+            assert np.allclose(Ps, g[pre + "sphere"], rtol=1e-12, atol=1e-14, equal_nan=True)
+            assert np.allclose(a, g[pre + "omni_az"], atol=1e-13, equal_nan=True)
+            assert np.allclose(e, g[pre + "omni_el"], atol=1e-13, equal_nan=True)
+            u, v = geometry.gum_project(p, g[pre + "proj_pts"])
+            assert np.allclose(u, g[pre + "proj_u"], rtol=1e-12) and np.allclose(v, g[pre + "proj_v"], rtol=1e-12)
+
+
+def test_rgbd_oracle():
+    g = load_golden("rgbd.npz")
+    for tag in ("z", "radial"):
+        cam = dict(zip(geometry.RGBD_FIELDS, g[f"{tag}_cam"]))
+        z = geometry.rgbd_depth_to_z(cam, g["depth"])
+        assert np.allclose(z, g[f"{tag}_depth_z"], rtol=1e-6)  # reference mixes float32/float64 here
+        xyz, bearing, valid = geometry.rgbd_backproject(cam, g["depth"], g["u"], g["v"], 0.8, 7.0)
+        assert np.allclose(xyz, g[f"{tag}_xyz"], rtol=1e-6, equal_nan=True)
+        assert np.allclose(bearing, g[f"{tag}_bearing"], rtol=1e-6, atol=1e-9, equal_nan=True)
+        assert np.array_equal(np.isnan(xyz[:, 2]), np.isnan(g[f"{tag}_xyz"][:, 2]))
+        assert 0 < valid.sum() < len(valid)
+
+
+def test_arun_and_score_oracle():
+    g = load_golden("arun.npz")
+    for k in (3, 4, 100):
+        v0, v1, M = g[f"k{k}_v0"], g[f"k{k}_v1"], g[f"k{k}_M"]
+        got = ransac.arun_batch(v0, v1)
+        assert np.allclose(got, M, rtol=0, atol=1e-9)
+        one = ransac.superimposition(v0[0].T, v1[0].T)[:3]
+        assert np.allclose(one, M[0], atol=1e-12)
+        assert np.allclose(np.linalg.det(got[:, :, :3]), 1.0)
+    sc = ransac.score_bearing(g["score_M"], g["score_p_ref"], g["score_f"])
+    assert np.allclose(sc, g["score_values"], rtol=0, atol=1e-14)
+    assert np.array_equal(np.nonzero(sc < float(g["score_thr"]))[0], g["score_inliers"])
+    assert ransac.num_iterations() == int(g["ransac_iters_default"]) == 210

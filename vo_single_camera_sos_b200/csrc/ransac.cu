@@ -1,0 +1,681 @@
+// Step 5 of the SOS front-end: batched RANSAC for rigid 3D-3D registration.
+//
+// Hypotheses are Arun/Kabsch fits on 3 correspondences, restating transformations.superimposition_matrix(v0, v1,
+// scale=False, usesvd=True) (reference omnistereo/transformations.py:874-1030); the inlier score is either the
+// Euclidean residual or the bearing-angle score of get_selected_distances_to_model (pose_est_tools.py:150-203, with
+// the non-central correction of its comment at :181-185), i.e. what OpenGV's AbsolutePoseSacProblem evaluates.
+//
+// Four kernels per call, all on one stream:
+//   hypothesize  one thread per (problem, hypothesis): sample rows, 3-point Kabsch in float64 (Jacobi on H^T H),
+//                emit [R|t] and, per camera, the scoring transform  x = A p_ref + b  with A = Rc^T R^T,
+//                b = -Rc^T (R^T t + tc)   (float32);
+//   score        FP32-FMA bound: a thread keeps RS_HPT hypotheses (A, b) in registers and walks the block's chunk of
+//                correspondences staged in shared memory (every lane reads the SAME point: broadcast LDS.128);
+//                per pair 9 FMA (x) + 3 ADD + 3 FMA (|x - p_cur|^2) + compare; counts go to global with one
+//                atomicAdd per (hypothesis, chunk);
+//   argmax       one block per problem: packed key (count+1) << 32 | (0xFFFFFFFF - global hypothesis index), so
+//                max() prefers the lowest index on ties (and reduces across GPUs with a plain 64-bit MAX);
+//   mask         re-evaluates the winner with the very same float32 instruction sequence -> inlier mask.
+#include <math_constants.h>
+#include <stddef.h>
+
+#include "sos_common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// float64 3x3 helpers (row-major)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void jacobi_rotate(double* S, double* V, int p, int q) {
+  const double apq = S[p * 3 + q];
+  if (apq == 0.0) return;
+  const double app = S[p * 3 + p], aqq = S[q * 3 + q];
+  const double tau = (aqq - app) / (2.0 * apq);
+  const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+  const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
+  // S <- J^T S J
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double skp = S[k * 3 + p], skq = S[k * 3 + q];
+    S[k * 3 + p] = c * skp - s * skq;
+    S[k * 3 + q] = s * skp + c * skq;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double spk = S[p * 3 + k], sqk = S[q * 3 + k];
+    S[p * 3 + k] = c * spk - s * sqk;
+    S[q * 3 + k] = s * spk + c * sqk;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double vkp = V[k * 3 + p], vkq = V[k * 3 + q];
+    V[k * 3 + p] = c * vkp - s * vkq;
+    V[k * 3 + q] = s * vkp + c * vkq;
+  }
+}
+
+// Rotation R (det +1) maximising trace(R^T ... ) for covariance Hm = sum v1_i v0_i^T, i.e. U diag(1,1,det(U V^T)) V^T of
+// Hm = U S V^T (transformations.py:942-953).  Returns false when the second singular value vanishes (rank < 2).
+__device__ bool kabsch_rotation(const double* Hm, double* R) {
+  double S[9], V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) S[i * 3 + j] = Hm[0 * 3 + i] * Hm[0 * 3 + j] + Hm[1 * 3 + i] * Hm[1 * 3 + j] + Hm[2 * 3 + i] * Hm[2 * 3 + j];
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    const double off = fabs(S[1]) + fabs(S[2]) + fabs(S[5]);
+    const double diag = fabs(S[0]) + fabs(S[4]) + fabs(S[8]);
+    if (off <= 1e-300 || off <= 1e-22 * diag) break;
+    jacobi_rotate(S, V, 0, 1);
+    jacobi_rotate(S, V, 0, 2);
+    jacobi_rotate(S, V, 1, 2);
+  }
+  // pick the two largest eigenvalues
+  double lam[3] = {S[0], S[4], S[8]};
+  int i0 = 0;
+  if (lam[1] > lam[i0]) i0 = 1;
+  if (lam[2] > lam[i0]) i0 = 2;
+  int i1 = (i0 + 1) % 3, i2 = (i0 + 2) % 3;
+  if (lam[i2] > lam[i1]) { const int tmp = i1; i1 = i2; i2 = tmp; }
+  if (!(lam[i0] > 0.0) || !(lam[i1] > 1e-24 * lam[i0])) return false;
+  double v1[3] = {V[0 * 3 + i0], V[1 * 3 + i0], V[2 * 3 + i0]};
+  double v2[3] = {V[0 * 3 + i1], V[1 * 3 + i1], V[2 * 3 + i1]};
+  double u1[3], u2[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    u1[i] = Hm[i * 3 + 0] * v1[0] + Hm[i * 3 + 1] * v1[1] + Hm[i * 3 + 2] * v1[2];
+    u2[i] = Hm[i * 3 + 0] * v2[0] + Hm[i * 3 + 1] * v2[1] + Hm[i * 3 + 2] * v2[2];
+  }
+  double n1 = sqrt(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+  if (!(n1 > 0.0)) return false;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) u1[i] /= n1;
+  const double d12 = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) u2[i] -= d12 * u1[i];
+  double n2 = sqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
+  if (!(n2 > 0.0)) return false;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) u2[i] /= n2;
+  const double u3[3] = {u1[1] * u2[2] - u1[2] * u2[1], u1[2] * u2[0] - u1[0] * u2[2], u1[0] * u2[1] - u1[1] * u2[0]};
+  const double v3[3] = {v1[1] * v2[2] - v1[2] * v2[1], v1[2] * v2[0] - v1[0] * v2[2], v1[0] * v2[1] - v1[1] * v2[0]};
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) R[i * 3 + j] = u1[i] * v1[j] + u2[i] * v2[j] + u3[i] * v3[j];
+  return true;
+}
+
+// Arun on k points held in local arrays (v0 -> v1): M = [R|t] row-major 3x4 with v1 ~ R v0 + t.
+__device__ bool arun_fit(const double* v0, const double* v1, int k, double* M) {
+  double c0[3] = {0, 0, 0}, c1[3] = {0, 0, 0};
+  for (int i = 0; i < k; ++i)
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { c0[d] += v0[3 * i + d]; c1[d] += v1[3 * i + d]; }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { c0[d] /= (double)k; c1[d] /= (double)k; }
+  double Hm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < k; ++i) {
+    const double a[3] = {v0[3 * i] - c0[0], v0[3 * i + 1] - c0[1], v0[3 * i + 2] - c0[2]};
+    const double b[3] = {v1[3 * i] - c1[0], v1[3 * i + 1] - c1[1], v1[3 * i + 2] - c1[2]};
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) Hm[r * 3 + c] += b[r] * a[c];  // dot(v1, v0.T), transformations.py:944
+  }
+  double R[9];
+  if (!kabsch_rotation(Hm, R)) return false;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    M[r * 4 + 0] = R[r * 3 + 0]; M[r * 4 + 1] = R[r * 3 + 1]; M[r * 4 + 2] = R[r * 3 + 2];
+    M[r * 4 + 3] = c1[r] - (R[r * 3 + 0] * c0[0] + R[r * 3 + 1] * c0[1] + R[r * 3 + 2] * c0[2]);
+  }
+  return true;
+}
+
+// sin^2 of the angle at vertex 0 of a triangle; collinear / coincident samples give ~0
+__device__ __forceinline__ bool triangle_degenerate(const double* p) {
+  const double e1[3] = {p[3] - p[0], p[4] - p[1], p[5] - p[2]}, e2[3] = {p[6] - p[0], p[7] - p[1], p[8] - p[2]};
+  const double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+  const double a2 = cx * cx + cy * cy + cz * cz;
+  const double l1 = e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2], l2 = e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2];
+  return !(a2 > 1e-12 * l1 * l2);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Per-hypothesis record in the scratch arena
+// ------------------------------------------------------------------------------------------------------------
+constexpr int RS_MAX_CAMS = 2;
+struct Rig {
+  double Rt[RS_MAX_CAMS][12];  // per camera row-major [Rc|tc]
+  int n_cams;
+};
+
+struct HypRec {
+  double pose64[12];              // [R|t] in float64: the exact (slow) path of the inlier test
+  float pose[12];                 // [R|t], p_ref ~ R p_cur + t
+  float xf[RS_MAX_CAMS][12];      // per camera: A (9, row-major) then b (3):  x = A p_ref + b
+};
+
+__device__ void make_scoring_transforms(const double* M, const Rig& rig, HypRec& rec) {
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    rec.pose64[i] = M[i];
+    rec.pose[i] = (float)M[i];
+  }
+  // body frame: y = R^T (p - t)
+  double Rt_[9], bt[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Rt_[i * 3 + j] = M[j * 4 + i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) bt[i] = -(Rt_[i * 3] * M[3] + Rt_[i * 3 + 1] * M[7] + Rt_[i * 3 + 2] * M[11]);
+  for (int c = 0; c < RS_MAX_CAMS; ++c) {
+    if (c >= rig.n_cams) {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) rec.xf[c][i] = 0.f;
+      continue;
+    }
+    const double* C = rig.Rt[c];  // x = Rc^T (y - tc)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        rec.xf[c][i * 3 + j] = (float)(C[0 * 4 + i] * Rt_[0 * 3 + j] + C[1 * 4 + i] * Rt_[1 * 3 + j] + C[2 * 4 + i] * Rt_[2 * 3 + j]);
+      rec.xf[c][9 + i] = (float)(C[0 * 4 + i] * (bt[0] - C[3]) + C[1 * 4 + i] * (bt[1] - C[7]) + C[2 * 4 + i] * (bt[2] - C[11]));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+hypothesize_kernel(const float* __restrict__ p_ref, const float* __restrict__ p_cur, const int32_t* __restrict__ n_arr,
+                   int cap, const uint32_t* __restrict__ hyp, int hyp_stride_problem, int n_hyp, Rig rig,
+                   HypRec* __restrict__ recs, int32_t* __restrict__ counts) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (h >= n_hyp) return;
+  const int n = n_arr[b];
+  const uint32_t* hr = hyp + (size_t)b * hyp_stride_problem + (size_t)h * 3;
+  bool ok = n >= 3;
+  int rows[3] = {0, 0, 0};
+  if (ok) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) rows[j] = (int)(((uint64_t)hr[j] * (uint64_t)n) >> 32);
+    ok = rows[0] != rows[1] && rows[0] != rows[2] && rows[1] != rows[2];
+  }
+  double v0[9], v1[9], M[12];
+  if (ok) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const size_t o = ((size_t)b * cap + rows[j]) * 3;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        v0[3 * j + d] = (double)p_cur[o + d];
+        v1[3 * j + d] = (double)p_ref[o + d];
+      }
+    }
+    ok = !triangle_degenerate(v0) && !triangle_degenerate(v1);
+  }
+  if (ok) ok = arun_fit(v0, v1, 3, M);
+  HypRec rec;
+  if (ok) {
+    make_scoring_transforms(M, rig, rec);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      rec.pose[i] = CUDART_NAN_F;
+      rec.pose64[i] = CUDART_NAN;
+    }
+    for (int c = 0; c < RS_MAX_CAMS; ++c)
+#pragma unroll
+      for (int i = 0; i < 12; ++i) rec.xf[c][i] = CUDART_NAN_F;  // NaN never passes the inlier test
+  }
+  recs[(size_t)b * n_hyp + h] = rec;
+  counts[(size_t)b * n_hyp + h] = ok ? 0 : -(1 << 30);  // failed model: stays negative whatever is added
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// The inlier test.
+//
+// Fast path: float32 FMAs on the per-hypothesis transform.  It also produces a rigorous bound `guard` on its own
+// rounding error; when the decision variable D lies inside the guard band the pair is re-evaluated by
+// inlier_exact() in float64 with the reference's own formula.  The decision therefore equals the float64 decision
+// (up to ~1e-15 relative), which is what makes inlier SETS bit-exact against the NumPy oracle, while >99.9 % of the
+// pairs never leave the FP32 pipe.
+//
+// Error model (p, q are exact float32 inputs, A and b are float32 roundings of float64 values, u = 2^-24):
+//   each component of x = A p + b:   |err| <= E = 4u (|p|_1 + |b|_inf),  and  |b|_inf <= |x|_2 + |p|_2
+//   EUCLID : D = |x - q|^2 - thr^2;  within the band |x|_2 <= |q|_2 + 2 thr, |x - q|_1 <= 2 sqrt(3) thr, hence
+//            |err D| <= u (28 thr (2|p|_1 + |q|_1 + 2 thr) + 18 thr^2) =: guard_j   (per correspondence, staged in .w)
+//   BEARING: D = s^2 - c^2 |x|^2, s = f.x, c = 1 - thr;  |err D| <= u (80 |x|^2 + 32 |p|_1^2) = k |x|^2 + guard_j
+// ------------------------------------------------------------------------------------------------------------
+struct ScoreConst {
+  float thr_sq;       // EUCLID: thr^2
+  float cos_min_sq;   // BEARING: (1 - thr)^2
+  float guard_rel;    // BEARING: 80 u
+  double thr;         // the threshold itself, for the exact path
+};
+
+__device__ __noinline__ bool inlier_exact(int mode, const double* __restrict__ M, const Rig& rig, int cam, float4 p,
+                                          float4 q, double thr) {
+  const double px = p.x, py = p.y, pz = p.z;
+  if (mode == SOS_SCORE_EUCLID) {
+    // |p_ref - (R p_cur + t)| < thr
+    const double cx = q.x, cy = q.y, cz = q.z;
+    const double dx = px - (M[0] * cx + M[1] * cy + M[2] * cz + M[3]);
+    const double dy = py - (M[4] * cx + M[5] * cy + M[6] * cz + M[7]);
+    const double dz = pz - (M[8] * cx + M[9] * cy + M[10] * cz + M[11]);
+    return sqrt(dx * dx + dy * dy + dz * dz) < thr;
+  }
+  // 1 - f . normalize(Rc^T (R^T (p - t) - tc)) < thr   (pose_est_tools.py:150-203, 181-185)
+  const double ex = px - M[3], ey = py - M[7], ez = pz - M[11];
+  double bx = M[0] * ex + M[4] * ey + M[8] * ez;
+  double by = M[1] * ex + M[5] * ey + M[9] * ez;
+  double bz = M[2] * ex + M[6] * ey + M[10] * ez;
+  const double* C = rig.Rt[cam];
+  bx -= C[3]; by -= C[7]; bz -= C[11];
+  const double x = C[0] * bx + C[4] * by + C[8] * bz;
+  const double y = C[1] * bx + C[5] * by + C[9] * bz;
+  const double z = C[2] * bx + C[6] * by + C[10] * bz;
+  const double nrm = sqrt(x * x + y * y + z * z);
+  return 1.0 - ((double)q.x * (x / nrm) + (double)q.y * (y / nrm) + (double)q.z * (z / nrm)) < thr;
+}
+
+// Returns the fast decision in `in` and whether it is uncertain.
+template <int MODE>
+__device__ __forceinline__ bool classify(const float* __restrict__ A, const float4& p, const float4& q, float guard_j,
+                                         const ScoreConst& k, bool& in) {
+  const float x = __fmaf_rn(A[2], p.z, __fmaf_rn(A[1], p.y, __fmaf_rn(A[0], p.x, A[9])));
+  const float y = __fmaf_rn(A[5], p.z, __fmaf_rn(A[4], p.y, __fmaf_rn(A[3], p.x, A[10])));
+  const float z = __fmaf_rn(A[8], p.z, __fmaf_rn(A[7], p.y, __fmaf_rn(A[6], p.x, A[11])));
+  if (MODE == SOS_SCORE_EUCLID) {
+    const float dx = __fsub_rn(x, q.x), dy = __fsub_rn(y, q.y), dz = __fsub_rn(z, q.z);
+    const float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    const float D = __fsub_rn(r2, k.thr_sq);
+    in = D < 0.f;
+    return fabsf(D) < guard_j;
+  } else {
+    const float s = __fmaf_rn(q.z, z, __fmaf_rn(q.y, y, __fmul_rn(q.x, x)));
+    const float n2 = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+    const float D = __fmaf_rn(s, s, -__fmul_rn(k.cos_min_sq, n2));
+    in = (s > 0.f) && (D > 0.f);
+    return fabsf(D) < __fmaf_rn(k.guard_rel, n2, guard_j);
+  }
+}
+
+__device__ __forceinline__ float guard_of(int mode, float px, float py, float pz, float qx, float qy, float qz, double thr) {
+  const double u = 5.9604644775390625e-08;  // 2^-24
+  const double p1 = fabs((double)px) + fabs((double)py) + fabs((double)pz);
+  if (mode == SOS_SCORE_EUCLID) {
+    const double q1 = fabs((double)qx) + fabs((double)qy) + fabs((double)qz);
+    return (float)(u * (28.0 * thr * (2.0 * p1 + q1 + 2.0 * thr) + 18.0 * thr * thr) * 1.0001);
+  }
+  return (float)(u * 32.0 * p1 * p1 * 1.0001);
+}
+
+constexpr int RS_THREADS = 128;
+constexpr int RS_HPT = 4;                       // hypotheses per thread
+constexpr int RS_TILE_H = RS_THREADS * RS_HPT;  // hypotheses per block
+constexpr int RS_CHUNK = 1024;                  // correspondences per block (2 x float4 each = 32 KB)
+
+template <int MODE, int NCAMS>
+__global__ void __launch_bounds__(RS_THREADS)
+score_kernel(const float* __restrict__ p_ref, const float* __restrict__ q_arr, const uint8_t* __restrict__ cam,
+             const int32_t* __restrict__ n_arr, int cap, const HypRec* __restrict__ recs, int n_hyp, ScoreConst k, Rig rig,
+             int32_t* __restrict__ counts) {
+  __shared__ float4 sp[RS_CHUNK];  // p_ref.xyz, guard (sign bit = camera index)
+  __shared__ float4 sq[RS_CHUNK];  // p_cur.xyz (EUCLID) or f_cur.xyz (BEARING)
+  const int b = blockIdx.z;
+  const int n = n_arr[b];
+  const int j0 = blockIdx.y * RS_CHUNK;
+  if (j0 >= n) return;
+  const int nj = min(RS_CHUNK, n - j0);
+  for (int j = threadIdx.x; j < nj; j += RS_THREADS) {
+    const size_t o = ((size_t)b * cap + j0 + j) * 3;
+    const int c = (NCAMS > 1 && cam) ? (cam[(size_t)b * cap + j0 + j] ? 1 : 0) : 0;
+    const float px = p_ref[o], py = p_ref[o + 1], pz = p_ref[o + 2];
+    const float qx = q_arr[o], qy = q_arr[o + 1], qz = q_arr[o + 2];
+    const float g = guard_of(MODE, px, py, pz, qx, qy, qz, k.thr);
+    sp[j] = make_float4(px, py, pz, c ? -g : g);
+    sq[j] = make_float4(qx, qy, qz, 0.f);
+  }
+  float A[RS_HPT][NCAMS][12];
+  int cnt[RS_HPT];
+  int hyp_of[RS_HPT];
+#pragma unroll
+  for (int r = 0; r < RS_HPT; ++r) {
+    int h = blockIdx.x * RS_TILE_H + r * RS_THREADS + threadIdx.x;
+    if (h >= n_hyp) h = n_hyp - 1;  // duplicate work, never stored
+    hyp_of[r] = h;
+    const HypRec* rec = recs + (size_t)b * n_hyp + h;
+#pragma unroll
+    for (int c = 0; c < NCAMS; ++c)
+#pragma unroll
+      for (int i = 0; i < 12; ++i) A[r][c][i] = rec->xf[c][i];
+    cnt[r] = 0;
+  }
+  __syncthreads();
+#pragma unroll 2
+  for (int j = 0; j < nj; ++j) {
+    const float4 p = sp[j];
+    const float4 q = sq[j];
+    const float g = fabsf(p.w);
+    const int c = (NCAMS > 1) ? (int)(__float_as_uint(p.w) >> 31) : 0;  // block-uniform: every lane sees the same point
+#pragma unroll
+    for (int r = 0; r < RS_HPT; ++r) {
+      bool in;
+      bool unsure;
+      if (NCAMS == 1 || c == 0) unsure = classify<MODE>(A[r][0], p, q, g, k, in);
+      else unsure = classify<MODE>(A[r][NCAMS - 1], p, q, g, k, in);
+      if (unsure) in = inlier_exact(MODE, recs[(size_t)b * n_hyp + hyp_of[r]].pose64, rig, c, p, q, k.thr);
+      cnt[r] += in ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RS_HPT; ++r) {
+    const int h = blockIdx.x * RS_TILE_H + r * RS_THREADS + threadIdx.x;
+    if (h < n_hyp && cnt[r] != 0) atomicAdd(&counts[(size_t)b * n_hyp + h], cnt[r]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+argmax_kernel(const int32_t* __restrict__ counts, const HypRec* __restrict__ recs, int n_hyp, int hyp_offset,
+              float* __restrict__ best_pose, int32_t* __restrict__ best_hyp, int32_t* __restrict__ best_count,
+              uint64_t* __restrict__ best_key, HypRec* __restrict__ best_rec) {
+  __shared__ unsigned long long warp_best[8];
+  const int b = blockIdx.x;
+  unsigned long long best = 0ull;
+  for (int h = threadIdx.x; h < n_hyp; h += blockDim.x) {
+    const int c = counts[(size_t)b * n_hyp + h];
+    if (c >= 0) {
+      const unsigned long long key = ((unsigned long long)(c + 1) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(hyp_offset + h));
+      best = max(best, key);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) best = max(best, __shfl_xor_sync(0xFFFFFFFFu, best, off));
+  if ((threadIdx.x & 31) == 0) warp_best[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) best = max(best, warp_best[w]);
+    if (best_key) best_key[b] = best;
+    const bool any = best != 0ull;
+    const int h = any ? (int)((0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull)) - (uint32_t)hyp_offset) : -1;
+    best_hyp[b] = any ? hyp_offset + h : -1;
+    best_count[b] = any ? (int)(best >> 32) - 1 : -1;
+    HypRec rec;
+    if (any) {
+      rec = recs[(size_t)b * n_hyp + h];
+    } else {
+      for (int i = 0; i < 12; ++i) {
+        rec.pose[i] = CUDART_NAN_F;
+        rec.pose64[i] = CUDART_NAN;
+      }
+      for (int c = 0; c < RS_MAX_CAMS; ++c)
+        for (int i = 0; i < 12; ++i) rec.xf[c][i] = CUDART_NAN_F;
+    }
+    best_rec[b] = rec;
+    for (int i = 0; i < 12; ++i) best_pose[(size_t)b * 12 + i] = rec.pose[i];
+  }
+}
+
+// Inlier mask of one hypothesis per problem: evaluated entirely by the exact path (n evaluations, negligible),
+// which by construction agrees with every decision the scoring kernel took.
+__global__ void __launch_bounds__(256)
+mask_kernel(int mode, const float* __restrict__ p_ref, const float* __restrict__ q_arr, const uint8_t* __restrict__ cam,
+            const int32_t* __restrict__ n_arr, int cap, const HypRec* __restrict__ best_rec, Rig rig, double thr,
+            uint8_t* __restrict__ mask, int32_t* __restrict__ count_out) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = n_arr[b];
+  bool in = false;
+  if (j < cap) {
+    if (j < n) {
+      const size_t o = ((size_t)b * cap + j) * 3;
+      const int c = (rig.n_cams > 1 && cam) ? (cam[(size_t)b * cap + j] ? 1 : 0) : 0;
+      const float4 p = make_float4(p_ref[o], p_ref[o + 1], p_ref[o + 2], 0.f);
+      const float4 q = make_float4(q_arr[o], q_arr[o + 1], q_arr[o + 2], 0.f);
+      in = inlier_exact(mode, best_rec[b].pose64, rig, c, p, q, thr);
+    }
+    if (mask) mask[(size_t)b * cap + j] = in ? 1 : 0;
+  }
+  if (count_out) {
+    const unsigned vote = __ballot_sync(0xFFFFFFFFu, in);
+    if ((threadIdx.x & 31) == 0 && vote) atomicAdd(&count_out[b], __popc(vote));
+  }
+}
+
+// generic k-point Arun, one thread per set (parity with transformations.superimposition_matrix)
+__global__ void arun_batch_kernel(const double* __restrict__ v0, const double* __restrict__ v1, int n_sets, int k,
+                                  double* __restrict__ M, uint8_t* __restrict__ ok) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_sets) return;
+  const double* a = v0 + (size_t)s * k * 3;
+  const double* b = v1 + (size_t)s * k * 3;
+  double out[12];
+  const bool good = arun_fit(a, b, k, out);
+  for (int i = 0; i < 12; ++i) M[(size_t)s * 12 + i] = good ? out[i] : CUDART_NAN;
+  if (ok) ok[s] = good ? 1 : 0;
+}
+
+// Arun refit over the inlier set: one block per problem, float64 accumulation, two passes (centroids, covariance).
+__global__ void __launch_bounds__(256)
+refit_kernel(const float* __restrict__ p_ref, const float* __restrict__ p_cur, const uint8_t* __restrict__ mask,
+             const int32_t* __restrict__ n_arr, int cap, float* __restrict__ pose, int32_t* __restrict__ n_used) {
+  __shared__ double red[8][16];
+  __shared__ double cen[6];
+  __shared__ int cnt_sh;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = n_arr[b];
+  double acc[16];
+  // pass 1: centroids
+  for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+  for (int j = tid; j < n; j += blockDim.x) {
+    if (!mask[(size_t)b * cap + j]) continue;
+    const size_t o = ((size_t)b * cap + j) * 3;
+    for (int d = 0; d < 3; ++d) { acc[d] += (double)p_cur[o + d]; acc[3 + d] += (double)p_ref[o + d]; }
+    acc[6] += 1.0;
+  }
+  for (int i = 0; i < 7; ++i) {
+    double v = acc[i];
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, off);
+    if (lane == 0) red[warp][i] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double tot[7];
+    for (int i = 0; i < 7; ++i) { tot[i] = 0; for (int w = 0; w < 8; ++w) tot[i] += red[w][i]; }
+    cnt_sh = (int)tot[6];
+    for (int i = 0; i < 6; ++i) cen[i] = tot[6] > 0 ? tot[i] / tot[6] : 0.0;
+  }
+  __syncthreads();
+  // pass 2: covariance of centred points
+  for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+  for (int j = tid; j < n; j += blockDim.x) {
+    if (!mask[(size_t)b * cap + j]) continue;
+    const size_t o = ((size_t)b * cap + j) * 3;
+    const double a[3] = {(double)p_cur[o] - cen[0], (double)p_cur[o + 1] - cen[1], (double)p_cur[o + 2] - cen[2]};
+    const double c[3] = {(double)p_ref[o] - cen[3], (double)p_ref[o + 1] - cen[4], (double)p_ref[o + 2] - cen[5]};
+    for (int r = 0; r < 3; ++r)
+      for (int s = 0; s < 3; ++s) acc[r * 3 + s] += c[r] * a[s];
+  }
+  __syncthreads();
+  for (int i = 0; i < 9; ++i) {
+    double v = acc[i];
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, off);
+    if (lane == 0) red[warp][i] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double Hm[9], R[9];
+    for (int i = 0; i < 9; ++i) { Hm[i] = 0; for (int w = 0; w < 8; ++w) Hm[i] += red[w][i]; }
+    const bool ok = cnt_sh >= 3 && kabsch_rotation(Hm, R);
+    if (n_used) n_used[b] = ok ? cnt_sh : -1;
+    for (int r = 0; r < 3; ++r) {
+      for (int s = 0; s < 3; ++s) pose[(size_t)b * 12 + r * 4 + s] = ok ? (float)R[r * 3 + s] : CUDART_NAN_F;
+      pose[(size_t)b * 12 + r * 4 + 3] =
+          ok ? (float)(cen[3 + r] - (R[r * 3] * cen[0] + R[r * 3 + 1] * cen[1] + R[r * 3 + 2] * cen[2])) : CUDART_NAN_F;
+    }
+  }
+}
+
+int fill_rig(const double* rig, int n_cams, Rig& out) {
+  out.n_cams = n_cams < 1 ? 1 : n_cams;
+  for (int c = 0; c < RS_MAX_CAMS; ++c)
+    for (int i = 0; i < 12; ++i) out.Rt[c][i] = (i == 0 || i == 5 || i == 10) ? 1.0 : 0.0;
+  if (rig)
+    for (int c = 0; c < n_cams; ++c)
+      for (int i = 0; i < 12; ++i) out.Rt[c][i] = rig[c * 12 + i];
+  return 0;
+}
+
+ScoreConst make_const(int mode, double thr) {
+  ScoreConst k;
+  k.thr_sq = (float)(thr * thr);
+  k.cos_min_sq = (float)((1.0 - thr) * (1.0 - thr));
+  k.guard_rel = (float)(80.0 * 5.9604644775390625e-08 * 1.0001);
+  k.thr = thr;
+  (void)mode;
+  return k;
+}
+
+struct RansacScratch {
+  HypRec* recs;
+  int32_t* counts;
+  HypRec* best_rec;
+};
+
+int ransac_scratch(sos_ctx* ctx, int n_problems, int n_hyp, RansacScratch& s) {
+  const size_t rec_bytes = sos_align_up((size_t)n_problems * n_hyp * sizeof(HypRec), 256);
+  const size_t cnt_bytes = sos_align_up((size_t)n_problems * n_hyp * sizeof(int32_t), 256);
+  const size_t best_bytes = sos_align_up((size_t)n_problems * sizeof(HypRec), 256);
+  void* base = nullptr;
+  const int rc = sos_arena_get(ctx, rec_bytes + cnt_bytes + best_bytes, &base);
+  if (rc != SOS_OK) return rc;
+  s.recs = (HypRec*)base;
+  s.counts = (int32_t*)((char*)base + rec_bytes);
+  s.best_rec = (HypRec*)((char*)base + rec_bytes + cnt_bytes);
+  return SOS_OK;
+}
+
+template <int MODE>
+int launch_score(sos_ctx* ctx, const Rig& rig, dim3 grid, const float* p_ref, const float* q, const uint8_t* cam,
+                 const int32_t* n, int cap, const HypRec* recs, int n_hyp, ScoreConst k, int32_t* counts) {
+  if (rig.n_cams <= 1 || cam == nullptr)
+    score_kernel<MODE, 1><<<grid, RS_THREADS, 0, ctx->stream>>>(p_ref, q, cam, n, cap, recs, n_hyp, k, rig, counts);
+  else
+    score_kernel<MODE, 2><<<grid, RS_THREADS, 0, ctx->stream>>>(p_ref, q, cam, n, cap, recs, n_hyp, k, rig, counts);
+  SOS_LAUNCHED(ctx);
+  return SOS_OK;
+}
+
+}  // namespace
+
+extern "C" int sos_arun_batch(sos_ctx* ctx, const double* v0, const double* v1, int n_sets, int k, double* M,
+                              uint8_t* ok) {
+  SOS_CHECK_ARG(ctx, "ctx is NULL");
+  SOS_CHECK_ARG(n_sets >= 0 && k >= 3, "need k >= 3 points per set");
+  if (n_sets == 0) return SOS_OK;
+  SOS_CHECK_ARG(v0 && v1 && M, "NULL array");
+  SOS_CUDA(cudaSetDevice(ctx->device));
+  arun_batch_kernel<<<sos_div_up(n_sets, 128), 128, 0, ctx->stream>>>(v0, v1, n_sets, k, M, ok);
+  SOS_LAUNCHED(ctx);
+  return SOS_OK;
+}
+
+extern "C" int sos_ransac_p3d(sos_ctx* ctx, const float* p_ref, const float* p_cur, const float* f_cur,
+                              const uint8_t* cam, const int32_t* n, int n_problems, int cap, const double* rig,
+                              int n_cams, const uint32_t* hyp, int n_hyp, int hyp_offset, int score_mode,
+                              double threshold, float* best_pose, int32_t* best_hyp, int32_t* best_count,
+                              uint8_t* inlier_mask, uint64_t* best_key) {
+  SOS_CHECK_ARG(ctx, "ctx is NULL");
+  SOS_CHECK_ARG(n_problems >= 0 && cap >= 0 && n_hyp >= 0, "negative size");
+  SOS_CHECK_ARG(score_mode == SOS_SCORE_EUCLID || score_mode == SOS_SCORE_BEARING, "unknown score mode");
+  SOS_CHECK_ARG(n_cams >= 0 && n_cams <= RS_MAX_CAMS, "at most 2 cameras in the rig");
+  SOS_CHECK_ARG(n_problems <= 65535, "at most 65535 problems per call");
+  if (n_problems == 0) return SOS_OK;
+  SOS_CHECK_ARG(p_ref && p_cur && n && best_pose && best_hyp && best_count, "NULL array");
+  SOS_CHECK_ARG(n_hyp == 0 || hyp, "hyp is NULL");
+  SOS_CHECK_ARG(score_mode != SOS_SCORE_BEARING || f_cur, "bearing score needs f_cur");
+  SOS_CHECK_ARG(score_mode != SOS_SCORE_BEARING || (threshold > 0.0 && threshold < 1.0), "bearing threshold must be in (0,1)");
+  SOS_CUDA(cudaSetDevice(ctx->device));
+  Rig r;
+  fill_rig(score_mode == SOS_SCORE_BEARING ? rig : nullptr, score_mode == SOS_SCORE_BEARING ? n_cams : 1, r);
+  const ScoreConst k = make_const(score_mode, threshold);
+  RansacScratch s;
+  const int n_hyp_alloc = n_hyp > 0 ? n_hyp : 1;
+  int rc = ransac_scratch(ctx, n_problems, n_hyp_alloc, s);
+  if (rc != SOS_OK) return rc;
+  if (n_hyp > 0) {
+    dim3 hgrid(sos_div_up(n_hyp, 128), n_problems);
+    hypothesize_kernel<<<hgrid, 128, 0, ctx->stream>>>(p_ref, p_cur, n, cap, hyp, 0, n_hyp, r, s.recs, s.counts);
+    SOS_LAUNCHED(ctx);
+    if (cap > 0) {
+      dim3 sgrid(sos_div_up(n_hyp, RS_TILE_H), sos_div_up(cap, RS_CHUNK), n_problems);
+      const float* q = score_mode == SOS_SCORE_EUCLID ? p_cur : f_cur;
+      rc = score_mode == SOS_SCORE_EUCLID
+               ? launch_score<SOS_SCORE_EUCLID>(ctx, r, sgrid, p_ref, q, cam, n, cap, s.recs, n_hyp, k, s.counts)
+               : launch_score<SOS_SCORE_BEARING>(ctx, r, sgrid, p_ref, q, cam, n, cap, s.recs, n_hyp, k, s.counts);
+      if (rc != SOS_OK) return rc;
+    }
+  }
+  argmax_kernel<<<n_problems, 256, 0, ctx->stream>>>(s.counts, s.recs, n_hyp, hyp_offset, best_pose, best_hyp,
+                                                     best_count, best_key, s.best_rec);
+  SOS_LAUNCHED(ctx);
+  if (inlier_mask && cap > 0) {
+    dim3 mgrid(sos_div_up(cap, 256), n_problems);
+    const float* q = score_mode == SOS_SCORE_EUCLID ? p_cur : f_cur;
+    mask_kernel<<<mgrid, 256, 0, ctx->stream>>>(score_mode, p_ref, q, cam, n, cap, s.best_rec, r, threshold, inlier_mask, nullptr);
+    SOS_LAUNCHED(ctx);
+  }
+  return SOS_OK;
+}
+
+extern "C" int sos_ransac_p3d_eval(sos_ctx* ctx, const float* p_ref, const float* p_cur, const float* f_cur,
+                                   const uint8_t* cam, const int32_t* n, int n_problems, int cap, const double* rig,
+                                   int n_cams, const uint32_t* hyp_row, int score_mode, double threshold, float* pose,
+                                   int32_t* count, uint8_t* inlier_mask) {
+  SOS_CHECK_ARG(ctx, "ctx is NULL");
+  SOS_CHECK_ARG(n_problems >= 0 && cap >= 0, "negative size");
+  SOS_CHECK_ARG(score_mode == SOS_SCORE_EUCLID || score_mode == SOS_SCORE_BEARING, "unknown score mode");
+  SOS_CHECK_ARG(n_cams >= 0 && n_cams <= RS_MAX_CAMS, "at most 2 cameras in the rig");
+  SOS_CHECK_ARG(n_problems <= 65535, "at most 65535 problems per call");
+  if (n_problems == 0) return SOS_OK;
+  SOS_CHECK_ARG(p_ref && p_cur && n && hyp_row && pose && count, "NULL array");
+  SOS_CHECK_ARG(score_mode != SOS_SCORE_BEARING || f_cur, "bearing score needs f_cur");
+  SOS_CUDA(cudaSetDevice(ctx->device));
+  Rig r;
+  fill_rig(score_mode == SOS_SCORE_BEARING ? rig : nullptr, score_mode == SOS_SCORE_BEARING ? n_cams : 1, r);
+  const ScoreConst k = make_const(score_mode, threshold);
+  RansacScratch s;
+  int rc = ransac_scratch(ctx, n_problems, 1, s);
+  if (rc != SOS_OK) return rc;
+  dim3 hgrid(1, n_problems);
+  // one hypothesis per problem, each with its own row of sample numbers (stride 3 per problem)
+  hypothesize_kernel<<<hgrid, 128, 0, ctx->stream>>>(p_ref, p_cur, n, cap, hyp_row, 3, 1, r, s.recs, s.counts);
+  SOS_LAUNCHED(ctx);
+  // counts[b] is 0 for a valid model and hugely negative otherwise: the mask kernel adds the inliers on top
+  SOS_CUDA(cudaMemcpyAsync(count, s.counts, (size_t)n_problems * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  SOS_CUDA(cudaMemcpy2DAsync(pose, 12 * sizeof(float), (const char*)s.recs + offsetof(HypRec, pose), sizeof(HypRec), 12 * sizeof(float), n_problems,
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+  if (cap > 0) {
+    dim3 mgrid(sos_div_up(cap, 256), n_problems);
+    const float* q = score_mode == SOS_SCORE_EUCLID ? p_cur : f_cur;
+    mask_kernel<<<mgrid, 256, 0, ctx->stream>>>(score_mode, p_ref, q, cam, n, cap, s.recs, r, threshold, inlier_mask, count);
+    SOS_LAUNCHED(ctx);
+  }
+  return SOS_OK;
+}
+
+extern "C" int sos_refit_inliers(sos_ctx* ctx, const float* p_ref, const float* p_cur, const uint8_t* inlier_mask,
+                                 const int32_t* n, int n_problems, int cap, float* pose, int32_t* n_used) {
+  SOS_CHECK_ARG(ctx, "ctx is NULL");
+  SOS_CHECK_ARG(n_problems >= 0 && cap >= 0, "negative size");
+  if (n_problems == 0) return SOS_OK;
+  SOS_CHECK_ARG(p_ref && p_cur && inlier_mask && n && pose, "NULL array");
+  SOS_CUDA(cudaSetDevice(ctx->device));
+  refit_kernel<<<n_problems, 256, 0, ctx->stream>>>(p_ref, p_cur, inlier_mask, n, cap, pose, n_used);
+  SOS_LAUNCHED(ctx);
+  return SOS_OK;
+}

@@ -1,0 +1,217 @@
+// Step 1 of the SOS front-end: LUT panoramic remap of the two mirror views.
+//
+// Replaces cv2.remap(INTER_LINEAR, BORDER_CONSTANT) as called by Panorama.get_panoramic_image (reference
+// omnistereo/panorama.py:258-321) on the masked omni images of OmniStereoModel.get_fully_masked_images
+// (camera_models.py:2932-3025).  The arithmetic is OpenCV's fixed-point bilinear path, restated:
+//   sx = cvRound(32*x) (round-half-even; NaN / overflow -> INT_MIN), x0 = sat_s16(sx >> 5), ax = sx & 31
+//   weights  w = {(32-ay)(32-ax), (32-ay)ax, ay(32-ax), ay*ax} * 32   (Q15, sum == 32768 exactly)
+//   dst = (w00*p00 + w01*p01 + w10*p10 + w11*p11 + 16384) >> 15,  taps outside the image = border value.
+// The mirror mask is folded into the packed LUT (one validity bit per tap): a masked-out source pixel reads
+// as the background colour, so the masked omni images are never materialised.
+//
+// HBM-bound: per panorama pixel 8 B of LUT in, `ch` bytes out, and the source annulus is read about once.
+// Layout: block = 8 warps = 8 panorama rows x 128 columns, a thread owns 4 consecutive pixels, so LUT reads
+// are 2 x LDG.128 per thread, stores are 4*ch contiguous bytes per thread, and neighbouring rows/columns of
+// the tile hit the same source cache lines in L1.
+#include "sos_common.cuh"
+
+namespace {
+
+constexpr int RM_PX = 4;              // pixels per thread
+constexpr int RM_TILE_COLS = 32 * RM_PX;
+constexpr int RM_TILE_ROWS = 8;
+
+__device__ __forceinline__ int cv_round_q5(float x) {
+  // cv::remap: cvRound(x * INTER_TAB_SIZE) via cvtps2dq: round-half-even, "integer indefinite" otherwise
+  const float xs = x * 32.0f;
+  if (!(fabsf(xs) < 2147483648.0f)) return INT_MIN;
+  return __float2int_rn(xs);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+lut_pack_kernel(const T* __restrict__ map_x, const T* __restrict__ map_y, int n, const uint8_t* __restrict__ mask,
+                int src_h, int src_w, uint64_t* __restrict__ lut) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int sx = cv_round_q5((float)map_x[i]);  // float64 -> float32 cast of panorama.py:291-292
+  const int sy = cv_round_q5((float)map_y[i]);
+  const int x0 = max(-32768, min(32767, sx >> 5));
+  const int y0 = max(-32768, min(32767, sy >> 5));
+  const uint32_t ax = (uint32_t)sx & 31u, ay = (uint32_t)sy & 31u;
+  uint32_t inside = 0, live = 0;
+#pragma unroll
+  for (int tap = 0; tap < 4; ++tap) {
+    const int x = x0 + (tap & 1), y = y0 + (tap >> 1);
+    if (x >= 0 && x < src_w && y >= 0 && y < src_h) {
+      inside |= 1u << tap;
+      if (mask == nullptr || mask[(size_t)y * src_w + x] != 0) live |= 1u << tap;
+    }
+  }
+  const uint64_t lo = (uint32_t)(x0 & 0xFFFF) | ((uint32_t)(y0 & 0xFFFF) << 16);
+  const uint64_t hi = ax | (ay << 5) | (inside << 16) | (live << 20);
+  lut[i] = lo | (hi << 32);
+}
+
+struct Px4 {
+  uint32_t acc[4];
+};
+
+template <int CH>
+__device__ __forceinline__ void load_tap(const uint8_t* __restrict__ p, uint32_t w, uint32_t* acc) {
+#pragma unroll
+  for (int c = 0; c < CH; ++c) acc[c] += w * (uint32_t)__ldg(p + c);
+}
+
+// One output pixel: returns CH bytes in out[].
+template <int CH>
+__device__ __forceinline__ void remap_pixel(const uint8_t* __restrict__ src, int src_w, uint64_t e,
+                                            const uint32_t* border, const uint32_t* bg, uint32_t* out) {
+  const int x0 = (int)(int16_t)(e & 0xFFFF);
+  const int y0 = (int)(int16_t)((e >> 16) & 0xFFFF);
+  const uint32_t hi = (uint32_t)(e >> 32);
+  const uint32_t ax = hi & 31u, ay = (hi >> 5) & 31u;
+  const uint32_t inside = (hi >> 16) & 15u, live = (hi >> 20) & 15u;
+  if (inside == 0) {  // all four taps outside: Q15 weights sum to 32768, so the result is the border value
+#pragma unroll
+    for (int c = 0; c < CH; ++c) out[c] = border[c];
+    return;
+  }
+  const uint32_t w[4] = {(32u - ay) * (32u - ax) * 32u, (32u - ay) * ax * 32u, ay * (32u - ax) * 32u, ay * ax * 32u};
+  uint32_t acc[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) acc[c] = 16384u;
+  const uint8_t* p = src + ((size_t)y0 * src_w + x0) * CH;
+  if (live == 15u) {
+    load_tap<CH>(p, w[0], acc);
+    load_tap<CH>(p + CH, w[1], acc);
+    load_tap<CH>(p + (size_t)src_w * CH, w[2], acc);
+    load_tap<CH>(p + (size_t)src_w * CH + CH, w[3], acc);
+  } else {
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) {
+      if (w[tap] == 0) continue;
+      if (live & (1u << tap)) {
+        load_tap<CH>(p + ((size_t)(tap >> 1) * src_w + (tap & 1)) * CH, w[tap], acc);
+      } else {
+        const uint32_t* v = (inside & (1u << tap)) ? bg : border;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) acc[c] += w[tap] * v[c];
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CH; ++c) out[c] = acc[c] >> 15;
+}
+
+struct RemapConst {
+  uint32_t border[4];
+  uint32_t bg[4];
+};
+
+template <int CH>
+__global__ void __launch_bounds__(256)
+remap_kernel(const uint8_t* __restrict__ src, int src_h, int src_w, const uint64_t* __restrict__ lut, int views,
+             int rows, int cols, RemapConst k, uint8_t* __restrict__ dst) {
+  const int lane_col = blockIdx.x * RM_TILE_COLS + (threadIdx.x & 31) * RM_PX;
+  const int row = blockIdx.y * RM_TILE_ROWS + (threadIdx.x >> 5);
+  if (row >= rows || lane_col >= cols) return;
+  const int img = blockIdx.z;  // batch * views + view
+  const int view = img % views, b = img / views;
+  const uint8_t* s = src + (size_t)b * src_h * src_w * CH;
+  const size_t px0 = (size_t)row * cols + lane_col;
+  const uint64_t* l = lut + (size_t)view * rows * cols + px0;
+  uint8_t* d = dst + ((size_t)img * rows * cols + px0) * CH;
+
+  const int n = min(RM_PX, cols - lane_col);
+  uint64_t e[RM_PX];
+  if (n == RM_PX && (((uintptr_t)l) & 15) == 0) {
+    const ulonglong2 a = __ldg((const ulonglong2*)l), c = __ldg((const ulonglong2*)l + 1);
+    e[0] = a.x; e[1] = a.y; e[2] = c.x; e[3] = c.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < RM_PX; ++i) e[i] = (i < n) ? __ldg(l + i) : 0ull;
+  }
+  uint32_t o[RM_PX][CH];
+#pragma unroll
+  for (int i = 0; i < RM_PX; ++i) {
+    if (i < n) remap_pixel<CH>(s, src_w, e[i], k.border, k.bg, o[i]);
+  }
+  if (n == RM_PX && (((uintptr_t)d) & 3) == 0) {
+    // RM_PX * CH bytes = CH 32-bit words
+    uint32_t words[CH];
+#pragma unroll
+    for (int wd = 0; wd < CH; ++wd) {
+      uint32_t v = 0;
+#pragma unroll
+      for (int bt = 0; bt < 4; ++bt) {
+        const int flat = wd * 4 + bt;
+        v |= o[flat / CH][flat % CH] << (8 * bt);
+      }
+      words[wd] = v;
+    }
+    if (CH == 4 && (((uintptr_t)d) & 15) == 0) {
+      *(uint4*)d = make_uint4(words[0], words[1], words[2 % CH], words[3 % CH]);
+    } else {
+#pragma unroll
+      for (int wd = 0; wd < CH; ++wd) ((uint32_t*)d)[wd] = words[wd];
+    }
+  } else {
+    for (int i = 0; i < n; ++i)
+#pragma unroll
+      for (int c = 0; c < CH; ++c) d[i * CH + c] = (uint8_t)o[i][c];
+  }
+}
+
+}  // namespace
+
+template <typename T>
+static int lut_pack_impl(sos_ctx* ctx, const T* map_x, const T* map_y, int rows, int cols, const uint8_t* mask,
+                         int src_h, int src_w, sos_lut_entry* lut) {
+  SOS_CHECK_ARG(ctx, "ctx is NULL");
+  SOS_CHECK_ARG(rows >= 0 && cols >= 0 && src_h > 0 && src_w > 0, "bad size");
+  SOS_CHECK_ARG(src_h <= 32767 && src_w <= 32767, "source image larger than 32767 (int16 coordinates)");
+  const long long n = (long long)rows * cols;
+  if (n == 0) return SOS_OK;
+  SOS_CHECK_ARG(n < (1ll << 31), "panorama too large");
+  SOS_CHECK_ARG(map_x && map_y && lut, "NULL array");
+  SOS_CUDA(cudaSetDevice(ctx->device));
+  lut_pack_kernel<T><<<sos_div_up((int)n, 256), 256, 0, ctx->stream>>>(map_x, map_y, (int)n, mask, src_h, src_w, lut);
+  SOS_LAUNCHED(ctx);
+  return SOS_OK;
+}
+
+extern "C" int sos_lut_pack_f32(sos_ctx* ctx, const float* map_x, const float* map_y, int rows, int cols,
+                                const uint8_t* mask, int src_h, int src_w, sos_lut_entry* lut) {
+  return lut_pack_impl<float>(ctx, map_x, map_y, rows, cols, mask, src_h, src_w, lut);
+}
+
+extern "C" int sos_lut_pack_f64(sos_ctx* ctx, const double* map_x, const double* map_y, int rows, int cols,
+                                const uint8_t* mask, int src_h, int src_w, sos_lut_entry* lut) {
+  return lut_pack_impl<double>(ctx, map_x, map_y, rows, cols, mask, src_h, src_w, lut);
+}
+
+extern "C" int sos_remap_u8(sos_ctx* ctx, const uint8_t* src, int batch, int src_h, int src_w, int channels,
+                            const sos_lut_entry* lut, int views, int rows, int cols, const uint8_t* border,
+                            const uint8_t* background, uint8_t* dst) {
+  SOS_CHECK_ARG(ctx, "ctx is NULL");
+  SOS_CHECK_ARG(channels == 1 || channels == 3 || channels == 4, "channels must be 1, 3 or 4");
+  SOS_CHECK_ARG(batch >= 0 && views >= 0 && rows >= 0 && cols >= 0 && src_h > 0 && src_w > 0, "bad size");
+  if (batch == 0 || views == 0 || rows == 0 || cols == 0) return SOS_OK;
+  SOS_CHECK_ARG((long long)batch * views <= 65535, "batch*views exceeds 65535");
+  SOS_CHECK_ARG(src && lut && dst, "NULL array");
+  SOS_CUDA(cudaSetDevice(ctx->device));
+  RemapConst k;
+  for (int c = 0; c < 4; ++c) {
+    k.border[c] = (border && c < channels) ? border[c] : 0;
+    k.bg[c] = (background && c < channels) ? background[c] : 0;
+  }
+  dim3 grid(sos_div_up(cols, RM_TILE_COLS), sos_div_up(rows, RM_TILE_ROWS), batch * views);
+  switch (channels) {
+    case 1: remap_kernel<1><<<grid, 256, 0, ctx->stream>>>(src, src_h, src_w, lut, views, rows, cols, k, dst); break;
+    case 3: remap_kernel<3><<<grid, 256, 0, ctx->stream>>>(src, src_h, src_w, lut, views, rows, cols, k, dst); break;
+    default: remap_kernel<4><<<grid, 256, 0, ctx->stream>>>(src, src_h, src_w, lut, views, rows, cols, k, dst); break;
+  }
+  SOS_LAUNCHED(ctx);
+  return SOS_OK;
+}

@@ -1,0 +1,55 @@
+// Shared plumbing of libsosfront.so: the context object, error reporting and launch helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "sosfront.h"
+
+struct sos_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  void* arena = nullptr;  // grow-only scratch
+  size_t arena_bytes = 0;
+  int64_t launches = 0;
+  int sm_count = 148;
+};
+
+void sos_set_error(const char* fmt, ...);
+
+#define SOS_CHECK_ARG(cond, msg)                                  \
+  do {                                                            \
+    if (!(cond)) {                                                \
+      sos_set_error("%s: invalid argument: %s", __func__, msg);   \
+      return SOS_ERR_INVALID;                                     \
+    }                                                             \
+  } while (0)
+
+#define SOS_CUDA(call)                                                                     \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      sos_set_error("%s: %s failed: %s", __func__, #call, cudaGetErrorString(e__));        \
+      return SOS_ERR_CUDA;                                                                 \
+    }                                                                                      \
+  } while (0)
+
+// Call after every kernel launch: counts it and surfaces launch-configuration errors.
+#define SOS_LAUNCHED(ctx)                                                                  \
+  do {                                                                                     \
+    (ctx)->launches++;                                                                     \
+    cudaError_t e__ = cudaPeekAtLastError();                                               \
+    if (e__ != cudaSuccess) {                                                              \
+      (void)cudaGetLastError();                                                            \
+      sos_set_error("%s: kernel launch failed: %s", __func__, cudaGetErrorString(e__));    \
+      return SOS_ERR_CUDA;                                                                 \
+    }                                                                                      \
+  } while (0)
+
+// Scratch arena: returns a pointer to at least `bytes` of device memory (256-byte aligned).
+int sos_arena_get(sos_ctx* ctx, size_t bytes, void** out);
+
+static inline int sos_div_up(int a, int b) { return (a + b - 1) / b; }
+static inline size_t sos_align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
