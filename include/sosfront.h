@@ -128,18 +128,19 @@ int sos_lut_build(sos_ctx* ctx, const double* gum, int rows, int cols, double cy
  * Step 2 — brute-force Hamming matching of 256-bit descriptors
  * ---------------------------------------------------------------------------------------------- */
 
-/* replaces: cv2.BFMatcher(NORM_HAMMING).match / .knnMatch(k=2) (camera_models.py:402,421,442), for S
- * independent (query, train) segment pairs in one launch (azimuthal buckets camera_models.py:3038,
- * views, frame pairs).
- *   q [sum Nq, 8] uint32, t [sum Nt, 8] uint32 (row = one 32-byte ORB descriptor)
- *   seg_q, seg_t [S+1] int32 DEVICE prefix offsets; max_nq / max_nt: HOST upper bounds of any segment length
- *   idx0, idx1 [sum Nq] int32: best / second-best train row RELATIVE to its segment (-1: none)
- *   d0, d1     [sum Nq] int32: their Hamming distances (-1: none)
+/* replaces: cv2.BFMatcher(NORM_HAMMING).match / .knnMatch(k=2) (camera_models.py:402,421,442), for n_seg
+ * independent (query, train) segment pairs in one launch (azimuthal buckets camera_models.py:3038, views, frames).
+ *   q, t [*, 8] uint32 (row = one 32-byte ORB descriptor), 16-byte aligned
+ *   segment s compares query rows [q_start[s], q_start[s]+q_len[s]) with train rows [t_start[s], t_start[s]+t_len[s]);
+ *   q_start, q_len, t_start, t_len [n_seg] int32 live on the DEVICE (lengths may be produced by earlier kernels);
+ *   max_nq / max_nt: HOST upper bounds of any q_len / t_len (they size the grid; longer segments are truncated)
+ *   idx0, idx1 [*] int32, indexed like q: best / second-best train row RELATIVE to t_start[s] (-1: none)
+ *   d0, d1     [*] int32: their Hamming distances (-1: none)
  * Order is (distance, train index): ties go to the lowest train index, as OpenCV does.
  * idx1/d1 may be NULL (1-NN only). */
-int sos_hamming_top2(sos_ctx* ctx, const uint32_t* q, const uint32_t* t, const int32_t* seg_q,
-                     const int32_t* seg_t, int n_seg, int max_nq, int max_nt, int32_t* idx0,
-                     int32_t* d0, int32_t* idx1, int32_t* d1);
+int sos_hamming_top2(sos_ctx* ctx, const uint32_t* q, const uint32_t* t, const int32_t* q_start,
+                     const int32_t* q_len, const int32_t* t_start, const int32_t* t_len, int n_seg, int max_nq,
+                     int max_nt, int32_t* idx0, int32_t* d0, int32_t* idx1, int32_t* d1);
 
 #define SOS_MATCH_NN 0    /* 1-NN, the reference default (k_best = 1, pose_est_tools.py:686) */
 #define SOS_MATCH_RATIO 1 /* keep m0 iff d0 < ratio * d1 (camera_models.py:421-436) */
@@ -151,13 +152,13 @@ int sos_hamming_top2(sos_ctx* ctx, const uint32_t* q, const uint32_t* t, const i
  * (pose_est_tools.py:245-247).  Per segment: select by `mode`, order stably by (distance, query index),
  * then keep pairs with |u_t - u_q| <= max_du (if max_du > 0) and v_t - v_q >= min_dv (if min_dv >= 0),
  * evaluated in float64 on the float32 pixel coordinates.
- *   rev_idx0 [sum Nt]: best query row per train row (SOS_MATCH_CROSS only, else NULL)
- *   px_q [sum Nq,2], px_t [sum Nt,2] float32 (u,v) or NULL when no gate is requested
- *   out_q, out_t, out_d [sum Nq]: segment s writes its pairs from seg_q[s] on; out_q/out_t are GLOBAL rows
- *   out_count [S]: pairs kept per segment. */
+ *   rev_idx0: best query row (relative to q_start[s]) per train row, indexed like t (SOS_MATCH_CROSS only, else NULL)
+ *   px_q, px_t [*,2] float32 (u,v), indexed like q / t, or NULL when no gate is requested
+ *   out_q, out_t, out_d: segment s writes its pairs to rows q_start[s] + k, k < out_count[s]; out_q / out_t hold
+ *   ABSOLUTE rows (q_start[s] + query, t_start[s] + train);  out_count [n_seg]: pairs kept per segment. */
 int sos_match_select(sos_ctx* ctx, int mode, double ratio, const int32_t* idx0, const int32_t* d0,
-                     const int32_t* d1, const int32_t* rev_idx0, const int32_t* seg_q,
-                     const int32_t* seg_t, int n_seg, int max_nq, const float* px_q,
+                     const int32_t* d1, const int32_t* rev_idx0, const int32_t* q_start,
+                     const int32_t* q_len, const int32_t* t_start, int n_seg, const float* px_q,
                      const float* px_t, double max_du, double min_dv, int32_t* out_q,
                      int32_t* out_t, int32_t* out_d, int32_t* out_count);
 
@@ -247,11 +248,16 @@ int sos_arun_batch(sos_ctx* ctx, const double* v0, const double* v1, int n_sets,
  * Outputs: best_pose [n_problems,12] float32 (row-major [R|t] of the current frame wrt the reference frame,
  * p_ref ~ R p_cur + t, what pyopengv.absolute_pose_*_ransac returns, pose_est_tools.py:785,915),
  * best_hyp, best_count [n_problems] int32, inlier_mask [n_problems*cap] uint8,
- * best_key [n_problems] uint64 = (count+1) << 32 | (0xFFFFFFFF - (hyp_offset + h)) for cross-GPU max-reduce. */
+ * best_key [n_problems] uint64 = (count+1) << 32 | (0xFFFFFFFF - (hyp_offset + h)) for cross-GPU max-reduce
+ * (may be NULL), all_counts [n_problems, n_hyp] int32 (may be NULL): every hypothesis' inlier count, negative for a
+ * rejected sample.
+ * Scoring runs in float32 with a rigorous rounding-error guard band; pairs inside the band are re-decided in float64
+ * with the reference's formula, so counts and inlier sets equal the float64 result. */
 int sos_ransac_p3d(sos_ctx* ctx, const float* p_ref, const float* p_cur, const float* f_cur, const uint8_t* cam,
                    const int32_t* n, int n_problems, int cap, const double* rig, int n_cams, const uint32_t* hyp,
                    int n_hyp, int hyp_offset, int score_mode, double threshold, float* best_pose,
-                   int32_t* best_hyp, int32_t* best_count, uint8_t* inlier_mask, uint64_t* best_key);
+                   int32_t* best_hyp, int32_t* best_count, uint8_t* inlier_mask, uint64_t* best_key,
+                   int32_t* all_counts);
 
 /* Re-derive pose and inlier mask of hypothesis `hyp_index[b]` (DEVICE int32, GLOBAL index, i.e. the winner
  * of the cross-GPU reduce) without scoring the others. */
@@ -264,6 +270,91 @@ int sos_ransac_p3d_eval(sos_ctx* ctx, const float* p_ref, const float* p_cur, co
  * approximation — see DESIGN.md).  pose [n_problems,12] float32. */
 int sos_refit_inliers(sos_ctx* ctx, const float* p_ref, const float* p_cur, const uint8_t* inlier_mask,
                       const int32_t* n, int n_problems, int cap, float* pose, int32_t* n_used);
+
+/* ------------------------------------------------------------------------------------------------
+ * The batched, GPU-resident front-end: B new frames in, B frame-pair poses out
+ * ---------------------------------------------------------------------------------------------- */
+
+/* One step chains the five hot-path steps for a batch of frames exactly as
+ * StereoPanoramicFrame.establish_stereo_correspondences (pose_est_tools.py:320-402) and
+ * TrackerStereoSE3.track_frame (pose_est_tools.py:736-847) do for one frame; defaults in pose_est_tools.py:284-308,
+ * 672-707, 862-878.  Feature detection is upstream of the hot path: features arrive as input. */
+typedef struct sos_frontend_config {
+  int32_t batch;               /* frames per step; pair i = (frame i-1, frame i), frame -1 = last frame of the previous step */
+  int32_t src_h, src_w, channels;
+  int32_t pano_rows, pano_cols;
+  int32_t n_buckets;           /* azimuthal buckets per view (12, pose_est_tools.py:871) */
+  int32_t max_feat_per_view;   /* rows reserved per frame and view in the feature arrays */
+  int32_t max_feat_per_bucket; /* upper bound of any bucket's feature count */
+  int32_t cap;                 /* capacity of triangulated stereo correspondences per frame */
+  int32_t n_hyp;               /* RANSAC hypotheses (210 in the reference, pose_est_tools.py:709-720) */
+  int32_t score_mode;          /* SOS_SCORE_* */
+  int32_t homogeneous_norm;    /* 1 = range gate on the homogeneous norm as the reference does (pose_est_tools.py:365-372) */
+  int32_t refit;               /* 1 = Arun refit on the inliers after RANSAC */
+  double ransac_threshold;     /* 1 - cos(5 deg) for SOS_SCORE_BEARING (pose_est_tools.py:675-676) */
+  double stereo_max_du, stereo_min_dv; /* 2.5, 1 (pose_est_tools.py:298-304) */
+  double temporal_max_du;      /* 0.125 * 0.5 * cols (pose_est_tools.py:866) */
+  double min_range, max_range; /* 0.5 m, 7 m in model units (pose_est_tools.py:306-308) */
+  double pano_top[SOS_PANO_NPARAMS], pano_bot[SOS_PANO_NPARAMS];
+  double f_top[3], f_bot[3];   /* mirror foci in [C] */
+  double rig[24];              /* 2 x row-major 3x4 [Rc|tc] (pose_est_tools.py:852-859) */
+  uint8_t border[4], background[4];
+} sos_frontend_config;
+
+/* Device buffers of the front-end, exposed for parity tests and for consumers that keep working on the device.
+ * "store" arrays hold batch+1 slots of `cap` rows: slot 0 = carried reference frame, slot i+1 = frame i of the step. */
+typedef struct sos_frontend_buffers {
+  uint8_t* pano;                                   /* [batch, 2, rows, cols, ch] */
+  int32_t *st_q_start, *st_q_len, *st_t_start, *st_t_len; /* stereo segments [batch*n_buckets] */
+  int32_t *st_idx0, *st_d0;                        /* [batch*max_feat] indexed like the bottom-view features */
+  int32_t *st_pair_q, *st_pair_t, *st_pair_d, *st_pair_count;
+  float *uv_c, *uv_top, *uv_bot;                   /* store [2][slots*cap][2]; uv_top / uv_bot alias its halves */
+  float *b_top, *b_bot, *xyz;                      /* store [slots*cap][3] */
+  int32_t *src_top, *src_bot, *n;                  /* store [slots*cap], n [slots] */
+  uint32_t* desc_c;                                /* store [2][slots*cap][8] */
+  int32_t *tm_q_start, *tm_q_len, *tm_t_start, *tm_t_len; /* temporal segments [2*batch]: view-major */
+  int32_t *tm_idx0, *tm_d0, *tm_pair_q, *tm_pair_t, *tm_pair_d, *tm_pair_count;
+  float *p_ref, *p_cur, *f_cur;                    /* [batch, 2*cap, 3] */
+  uint8_t* cam;                                    /* [batch, 2*cap] */
+  int32_t *n_corr, *n_corr_top;                    /* [batch] */
+  float *ransac_pose, *pose;                       /* [batch, 12]; pose = refit (or a copy of ransac_pose) */
+  int32_t *best_hyp, *best_count, *n_refit;        /* [batch] */
+  uint8_t* inlier_mask;                            /* [batch, 2*cap] */
+  int32_t* stats;                                  /* [batch, 4]: n_stereo, n_correspondences, n_inliers, best_hyp */
+  int32_t batch, cap, launches_per_step;
+} sos_frontend_buffers;
+
+typedef struct sos_frontend sos_frontend;
+
+/* lut [2, pano_rows, pano_cols] (top, bottom) and hyp [n_hyp, 3] are DEVICE arrays that must outlive the front-end.
+ * The front-end binds to the context's CURRENT stream. */
+int sos_frontend_create(sos_ctx* ctx, const sos_frontend_config* cfg, const sos_lut_entry* lut, const uint32_t* hyp,
+                        sos_frontend** out);
+int sos_frontend_destroy(sos_frontend* fe);
+int sos_frontend_reset(sos_frontend* fe);                /* forget the carried reference frame */
+int sos_frontend_set_graph(sos_frontend* fe, int enabled); /* CUDA-graph replay (default) or eager launches */
+int sos_frontend_get_buffers(sos_frontend* fe, sos_frontend_buffers* out);
+
+/* One step on DEVICE-resident inputs (asynchronous):
+ *   omni [batch, src_h, src_w, channels] uint8
+ *   px_top, px_bot [batch, max_feat_per_view, 2] float32 panorama pixel coordinates of the features of each view
+ *   desc_top, desc_bot [batch, max_feat_per_view, 8] uint32
+ *   bucket_off_top, bucket_off_bot [batch, n_buckets+1] int32: bucket k of frame b holds feature rows
+ *   [off[b][k], off[b][k+1]) of that frame. */
+int sos_frontend_step(sos_frontend* fe, const uint8_t* omni, const float* px_top, const uint32_t* desc_top,
+                      const int32_t* bucket_off_top, const float* px_bot, const uint32_t* desc_bot,
+                      const int32_t* bucket_off_bot);
+
+/* The same step on HOST buffers (pinned for full copy bandwidth): H2D on a copy stream, kernels, D2H of
+ * poses [batch,12] float32 and stats [batch,4] int32.  submit/wait overlap the copies of step k+1 with the kernels of
+ * step k (two staging slots); step_host = submit + wait. */
+int sos_frontend_submit_host(sos_frontend* fe, const uint8_t* omni, const float* px_top, const uint32_t* desc_top,
+                             const int32_t* bucket_off_top, const float* px_bot, const uint32_t* desc_bot,
+                             const int32_t* bucket_off_bot, int* ticket);
+int sos_frontend_wait_host(sos_frontend* fe, int ticket, float* poses, int32_t* stats);
+int sos_frontend_step_host(sos_frontend* fe, const uint8_t* omni, const float* px_top, const uint32_t* desc_top,
+                           const int32_t* bucket_off_top, const float* px_bot, const uint32_t* desc_bot,
+                           const int32_t* bucket_off_bot, float* poses, int32_t* stats);
 
 /* ------------------------------------------------------------------------------------------------
  * Roofline denominators measured in-process (integer POPC pipe, FP32 FMA pipe) — bench.py only.

@@ -25,7 +25,8 @@ def run_top2(ctx, qs, ts):
     t = np.concatenate(ts) if seg_t[-1] else np.zeros((0, 32), np.uint8)
     qd = dev(q) if len(q) else torch.zeros((0, 32), dtype=torch.uint8, device="cuda")
     td = dev(t) if len(t) else torch.zeros((1, 32), dtype=torch.uint8, device="cuda")
-    out = ctx.hamming_top2(qd, td, dev(seg_q), dev(seg_t), max(len(x) for x in qs), max(len(x) for x in ts))
+    out = ctx.hamming_top2(qd, td, dev(seg_q[:-1]), dev(np.diff(seg_q)), dev(seg_t[:-1]), dev(np.diff(seg_t)),
+                           max(len(x) for x in qs), max(len(x) for x in ts))
     return [o.cpu().numpy() for o in out], seg_q, seg_t, qd, td
 
 
@@ -124,7 +125,7 @@ def test_match_select_modes_and_gate(ctx, mode):
     px_q = dev(np.concatenate(pqs)); px_t = dev(np.concatenate(pts))
     code = {"nn": 0, "ratio": 1, "cross": 2}[mode]
     for gate in (False, True):
-        oq, ot, od, oc = ctx.match_select(code, i0, d0, d1, dev(seg_q), dev(seg_t), max(s[0] for s in sizes), rev_idx0=rev,
+        oq, ot, od, oc = ctx.match_select(code, i0, d0, d1, dev(seg_q[:-1]), dev(np.diff(seg_q)), dev(seg_t[:-1]), rev_idx0=rev,
                                           px_q=px_q if gate else None, px_t=px_t if gate else None,
                                           max_du=2.5 if gate else -1, min_dv=1.0 if gate else -1, ratio=0.75)
         oq, ot, od, oc = (x.cpu().numpy() for x in (oq, ot, od, oc))
@@ -148,7 +149,7 @@ def test_reference_frame_matching_goldens(ctx):
     pt = np.concatenate([g[f"b{b}_pt_top"] for b in range(nb)])
     res, seg_q, seg_t, _, _ = run_top2(ctx, qs, ts)
     i0, d0, i1, d1 = [dev(x) for x in res]
-    oq, ot, od, oc = ctx.match_select(0, i0, d0, d1, dev(seg_q), dev(seg_t), max(len(x) for x in qs), px_q=dev(pq), px_t=dev(pt),
+    oq, ot, od, oc = ctx.match_select(0, i0, d0, d1, dev(seg_q[:-1]), dev(np.diff(seg_q)), dev(seg_t[:-1]), px_q=dev(pq), px_t=dev(pt),
                                       max_du=2.5, min_dv=1.0)
     oq, ot, oc = oq.cpu().numpy(), ot.cpu().numpy(), oc.cpu().numpy()
     m_top = np.concatenate([pt[ot[seg_q[s]:seg_q[s] + oc[s]]] for s in range(nb)])
@@ -159,7 +160,7 @@ def test_reference_frame_matching_goldens(ctx):
     q, t = g["f2f_q"], g["f2f_t"]
     res, seg_q, seg_t, _, _ = run_top2(ctx, [q], [t])
     i0, d0, i1, d1 = [dev(x) for x in res]
-    oq, ot, od, oc = ctx.match_select(0, i0, d0, d1, dev(seg_q), dev(seg_t), len(q), px_q=dev(g["f2f_pq"][:, :2], torch.float32),
+    oq, ot, od, oc = ctx.match_select(0, i0, d0, d1, dev(seg_q[:-1]), dev(np.diff(seg_q)), dev(seg_t[:-1]), px_q=dev(g["f2f_pq"][:, :2], torch.float32),
                                       px_t=dev(g["f2f_pt"][:, :2], torch.float32), max_du=float(g["f2f_max_du"]), min_dv=-1.0)
     n = int(oc[0])
     assert np.array_equal(oq[:n].cpu().numpy(), g["f2f_query_idx"]) and np.array_equal(ot[:n].cpu().numpy(), g["f2f_train_idx"])

@@ -38,8 +38,8 @@ PROTOTYPES = {
     "sos_remap_u8": (I, [c_ctx, P, I, I, I, I, P, I, I, I, P, P, P]),
     "sos_gum_project": (I, [c_ctx, P, P, I, P]),
     "sos_lut_build": (I, [c_ctx, P, I, I, D, D, D, D, P, P]),
-    "sos_hamming_top2": (I, [c_ctx, P, P, P, P, I, I, I, P, P, P, P]),
-    "sos_match_select": (I, [c_ctx, I, D, P, P, P, P, P, P, I, I, P, P, D, D, P, P, P, P]),
+    "sos_hamming_top2": (I, [c_ctx, P, P, P, P, P, P, I, I, I, P, P, P, P]),
+    "sos_match_select": (I, [c_ctx, I, D, P, P, P, P, P, P, P, I, P, P, D, D, P, P, P, P]),
     "sos_lift_pano": (I, [c_ctx, P, P, I, P, P, P]),
     "sos_lift_gum": (I, [c_ctx, P, P, I, P, P, P]),
     "sos_triangulate_midpoint": (I, [c_ctx, P, P, P, P, I, P, P, D, D, I, P, P]),
@@ -47,9 +47,18 @@ PROTOTYPES = {
     "sos_rgbd_depth_to_z": (I, [c_ctx, P, P, I, I, I, P]),
     "sos_rgbd_backproject": (I, [c_ctx, P, P, I, I, I, P, P, I, D, D, P, P, P]),
     "sos_arun_batch": (I, [c_ctx, P, P, I, I, P, P]),
-    "sos_ransac_p3d": (I, [c_ctx, P, P, P, P, P, I, I, P, I, P, I, I, I, D, P, P, P, P, P]),
+    "sos_ransac_p3d": (I, [c_ctx, P, P, P, P, P, I, I, P, I, P, I, I, I, D, P, P, P, P, P, P]),
     "sos_ransac_p3d_eval": (I, [c_ctx, P, P, P, P, P, I, I, P, I, P, I, D, P, P, P]),
     "sos_refit_inliers": (I, [c_ctx, P, P, P, P, I, I, P, P]),
+    "sos_frontend_create": (I, [c_ctx, P, P, P, C.POINTER(C.c_void_p)]),
+    "sos_frontend_destroy": (I, [C.c_void_p]),
+    "sos_frontend_reset": (I, [C.c_void_p]),
+    "sos_frontend_set_graph": (I, [C.c_void_p, I]),
+    "sos_frontend_get_buffers": (I, [C.c_void_p, P]),
+    "sos_frontend_step": (I, [C.c_void_p, P, P, P, P, P, P, P]),
+    "sos_frontend_submit_host": (I, [C.c_void_p, P, P, P, P, P, P, P, C.POINTER(I)]),
+    "sos_frontend_wait_host": (I, [C.c_void_p, I, P, P]),
+    "sos_frontend_step_host": (I, [C.c_void_p, P, P, P, P, P, P, P, P, P]),
     "sos_peak_popc": (I, [c_ctx, C.POINTER(D)]),
     "sos_peak_ffma": (I, [c_ctx, C.POINTER(D)]),
 }

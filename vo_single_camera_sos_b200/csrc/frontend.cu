@@ -1,0 +1,503 @@
+// The batched, GPU-resident SOS front-end: one "step" takes B new frames (omni image + per-view ORB features) and
+// produces B frame-pair poses (frame i-1 -> frame i; the last frame of a step is carried over as the reference of the
+// next step).  It chains the five hot-path steps exactly as StereoPanoramicFrame.establish_stereo_correspondences
+// (reference omnistereo/pose_est_tools.py:320-402) and TrackerStereoSE3.track_frame (pose_est_tools.py:736-847) do,
+// but for all frames of the batch at once and without ever returning to the host: every data-dependent size (matches
+// per bucket, triangulated points per frame, correspondences per pair) stays in device memory and is read by the next
+// kernel.  The kernel chain is captured once into a CUDA graph and replayed per step.
+//
+//   remap (2 views)                                           panorama.py:258-321, camera_models.py:3107-3120
+//   stereo Hamming match per azimuthal bucket, bottom = query  camera_models.py:3027-3101
+//   sort by distance + pixel gate (|du| <= 2.5, dv >= 1)        camera_models.py:444, common_cv.py:167-188
+//   lift + midpoint triangulation + range gate + compaction    pose_est_tools.py:344-397
+//   temporal Hamming match top<->top, bottom<->bottom           pose_est_tools.py:741-749, 211-269
+//   stack correspondences (top first, then bottom)             pose_est_tools.py:752-778
+//   RANSAC over seeded Arun hypotheses (+ inlier refit)        pose_est_tools.py:785, 830
+#include <string.h>
+
+#include <vector>
+
+#include "sos_common.cuh"
+
+namespace {
+
+struct Buf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+__global__ void stereo_segments_kernel(const int32_t* __restrict__ boff_top, const int32_t* __restrict__ boff_bot, int B,
+                                       int nb, int F, int32_t* __restrict__ q_start, int32_t* __restrict__ q_len,
+                                       int32_t* __restrict__ t_start, int32_t* __restrict__ t_len) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= B * nb) return;
+  const int b = s / nb, k = s % nb;
+  const int32_t* ot = boff_top + (size_t)b * (nb + 1);
+  const int32_t* ob = boff_bot + (size_t)b * (nb + 1);
+  q_start[s] = b * F + ob[k];  // bottom view = query (camera_models.py:3042)
+  q_len[s] = max(0, ob[k + 1] - ob[k]);
+  t_start[s] = b * F + ot[k];  // top view = train
+  t_len[s] = max(0, ot[k + 1] - ot[k]);
+}
+
+// desc_c[(view*(B+1) + slot)*cap + k] = desc_view[src_view[slot*cap + k]] for the B new slots (1..B)
+__global__ void gather_desc_kernel(const uint4* __restrict__ desc_top, const uint4* __restrict__ desc_bot,
+                                   const int32_t* __restrict__ src_top, const int32_t* __restrict__ src_bot,
+                                   const int32_t* __restrict__ n, int B, int cap, uint4* __restrict__ desc_c) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int slot = blockIdx.y + 1;
+  const int view = blockIdx.z;
+  if (k >= n[slot]) return;
+  const size_t row = (size_t)slot * cap + k;
+  const int src = view == 0 ? src_top[row] : src_bot[row];
+  const uint4* d = (view == 0 ? desc_top : desc_bot) + (size_t)src * 2;
+  uint4* o = desc_c + ((size_t)(view * (B + 1) + slot) * cap + k) * 2;
+  o[0] = __ldg(d);
+  o[1] = __ldg(d + 1);
+}
+
+__global__ void temporal_segments_kernel(const int32_t* __restrict__ n, int B, int cap, int32_t* __restrict__ q_start,
+                                         int32_t* __restrict__ q_len, int32_t* __restrict__ t_start,
+                                         int32_t* __restrict__ t_len) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= 2 * B) return;
+  const int view = s / B, i = s % B;  // pair i: reference = slot i, current = slot i + 1
+  q_start[s] = (view * (B + 1) + i + 1) * cap;  // query = current frame (pose_est_tools.py:215)
+  q_len[s] = n[i + 1];
+  t_start[s] = (view * (B + 1) + i) * cap;      // train = reference frame
+  t_len[s] = n[i];
+}
+
+// Stack the temporal matches of both views into one correspondence list per frame pair (pose_est_tools.py:752-778).
+__global__ void __launch_bounds__(256)
+assemble_kernel(const int32_t* __restrict__ m_q, const int32_t* __restrict__ m_t, const int32_t* __restrict__ m_count,
+                const int32_t* __restrict__ q_start, int B, int cap, const float* __restrict__ xyz,
+                const float* __restrict__ b_top, const float* __restrict__ b_bot, float* __restrict__ p_ref,
+                float* __restrict__ p_cur, float* __restrict__ f_cur, uint8_t* __restrict__ cam,
+                int32_t* __restrict__ n_corr, int32_t* __restrict__ n_corr_top) {
+  const int i = blockIdx.x;  // frame pair
+  const int c_top = m_count[i], c_bot = m_count[B + i];
+  const int total = c_top + c_bot;
+  if (threadIdx.x == 0) {
+    n_corr[i] = total;
+    n_corr_top[i] = c_top;
+  }
+  const int cap2 = 2 * cap;
+  for (int k = threadIdx.x; k < total; k += blockDim.x) {
+    const int view = k < c_top ? 0 : 1;
+    const int s = view * B + i;
+    const int kk = view == 0 ? k : k - c_top;
+    const int base = view * (B + 1) * cap;        // descriptor-store rows of this view start here
+    const int rq = m_q[q_start[s] + kk] - base;   // store row of the current-frame correspondence
+    const int rt = m_t[q_start[s] + kk] - base;   // store row of the reference-frame correspondence
+    const size_t o = ((size_t)i * cap2 + k) * 3;
+    const float* bq = (view == 0 ? b_top : b_bot) + (size_t)rq * 3;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      p_ref[o + d] = xyz[(size_t)rt * 3 + d];
+      p_cur[o + d] = xyz[(size_t)rq * 3 + d];
+      f_cur[o + d] = bq[d];
+    }
+    cam[(size_t)i * cap2 + k] = (uint8_t)view;
+  }
+}
+
+__global__ void stats_kernel(const int32_t* __restrict__ n, const int32_t* __restrict__ n_corr,
+                             const int32_t* __restrict__ best_count, const int32_t* __restrict__ best_hyp, int B,
+                             int32_t* __restrict__ stats) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  stats[4 * i + 0] = n[i + 1];       // triangulated stereo correspondences of the new frame
+  stats[4 * i + 1] = n_corr[i];      // temporal correspondences handed to RANSAC
+  stats[4 * i + 2] = best_count[i];  // RANSAC inliers
+  stats[4 * i + 3] = best_hyp[i];
+}
+
+}  // namespace
+
+struct sos_frontend {
+  sos_ctx* ctx = nullptr;     // private (own scratch arena)
+  sos_ctx* parent = nullptr;  // the caller's context (launch accounting)
+  sos_frontend_config cfg;
+  const sos_lut_entry* lut = nullptr;
+  const uint32_t* hyp = nullptr;
+  // device state
+  sos_frontend_buffers d;
+  std::vector<void*> owned;
+  // staging for the host API (double buffered)
+  static constexpr int DEPTH = 2;
+  struct Stage {
+    uint8_t* omni = nullptr;
+    float *px_top = nullptr, *px_bot = nullptr;
+    uint32_t *desc_top = nullptr, *desc_bot = nullptr;
+    int32_t *boff_top = nullptr, *boff_bot = nullptr;
+    float* h_poses = nullptr;     // pinned
+    int32_t* h_stats = nullptr;   // pinned
+    cudaEvent_t copied = nullptr, done = nullptr;
+    bool in_flight = false;
+  } stage[DEPTH];
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;  // fences against the caller's stream
+  int next_stage = 0;
+  // graph cache keyed on the input pointers
+  struct GraphKey {
+    const void* p[7];
+  };
+  struct GraphEntry {
+    GraphKey key;
+    cudaGraphExec_t exec = nullptr;
+  };
+  std::vector<GraphEntry> graphs;
+  bool use_graph = true;
+};
+
+namespace {
+
+template <typename T>
+int fe_alloc(sos_frontend* fe, T** out, size_t count) {
+  void* p = nullptr;
+  const size_t bytes = sos_align_up(count * sizeof(T) + 256, 256);
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    sos_set_error("sos_frontend: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return SOS_ERR_NOMEM;
+  }
+  cudaMemsetAsync(p, 0, bytes, fe->ctx->stream);
+  fe->owned.push_back(p);
+  *out = (T*)p;
+  return SOS_OK;
+}
+
+// The kernel chain of one step, enqueued on ctx->stream.
+int enqueue_step(sos_frontend* fe, const uint8_t* omni, const float* px_top, const uint32_t* desc_top,
+                 const int32_t* boff_top, const float* px_bot, const uint32_t* desc_bot, const int32_t* boff_bot) {
+  sos_ctx* ctx = fe->ctx;
+  const sos_frontend_config& c = fe->cfg;
+  sos_frontend_buffers& d = fe->d;
+  const int B = c.batch, nb = c.n_buckets, F = c.max_feat_per_view, cap = c.cap;
+  int rc;
+  // step 1
+  rc = sos_remap_u8(ctx, omni, B, c.src_h, c.src_w, c.channels, fe->lut, 2, c.pano_rows, c.pano_cols, c.border,
+                    c.background, d.pano);
+  if (rc) return rc;
+  // step 2a: stereo matching per bucket
+  const int S = B * nb;
+  stereo_segments_kernel<<<sos_div_up(S, 128), 128, 0, ctx->stream>>>(boff_top, boff_bot, B, nb, F, d.st_q_start, d.st_q_len,
+                                                                       d.st_t_start, d.st_t_len);
+  SOS_LAUNCHED(ctx);
+  rc = sos_hamming_top2(ctx, desc_bot, desc_top, d.st_q_start, d.st_q_len, d.st_t_start, d.st_t_len, S,
+                        c.max_feat_per_bucket, c.max_feat_per_bucket, d.st_idx0, d.st_d0, nullptr, nullptr);
+  if (rc) return rc;
+  rc = sos_match_select(ctx, SOS_MATCH_NN, 0.75, d.st_idx0, d.st_d0, nullptr, nullptr, d.st_q_start, d.st_q_len,
+                        d.st_t_start, S, px_bot, px_top, c.stereo_max_du, c.stereo_min_dv, d.st_pair_q, d.st_pair_t,
+                        d.st_pair_d, d.st_pair_count);
+  if (rc) return rc;
+  // steps 3+4 into store slots 1..B
+  rc = sos_stereo_lift_triangulate(ctx, c.pano_top, c.pano_bot, px_top, px_bot, d.st_pair_q, d.st_pair_t, d.st_pair_count,
+                                   d.st_q_start, B, nb, c.f_top, c.f_bot, c.min_range, c.max_range, c.homogeneous_norm, cap,
+                                   d.uv_top + (size_t)cap * 2, d.uv_bot + (size_t)cap * 2, d.b_top + (size_t)cap * 3,
+                                   d.b_bot + (size_t)cap * 3, d.xyz + (size_t)cap * 3, d.src_top + cap, d.src_bot + cap,
+                                   d.n + 1);
+  if (rc) return rc;
+  {
+    dim3 grid(sos_div_up(cap, 128), B, 2);
+    gather_desc_kernel<<<grid, 128, 0, ctx->stream>>>((const uint4*)desc_top, (const uint4*)desc_bot, d.src_top, d.src_bot,
+                                                      d.n, B, cap, (uint4*)d.desc_c);
+    SOS_LAUNCHED(ctx);
+  }
+  // step 2b: temporal matching, 2 views x B pairs
+  temporal_segments_kernel<<<sos_div_up(2 * B, 128), 128, 0, ctx->stream>>>(d.n, B, cap, d.tm_q_start, d.tm_q_len,
+                                                                            d.tm_t_start, d.tm_t_len);
+  SOS_LAUNCHED(ctx);
+  rc = sos_hamming_top2(ctx, d.desc_c, d.desc_c, d.tm_q_start, d.tm_q_len, d.tm_t_start, d.tm_t_len, 2 * B, cap, cap,
+                        d.tm_idx0, d.tm_d0, nullptr, nullptr);
+  if (rc) return rc;
+  // pixel gate on u only (pose_est_tools.py:245-247): coordinates of the compacted store, both views in one array
+  rc = sos_match_select(ctx, SOS_MATCH_NN, 0.75, d.tm_idx0, d.tm_d0, nullptr, nullptr, d.tm_q_start, d.tm_q_len,
+                        d.tm_t_start, 2 * B, d.uv_c, d.uv_c, c.temporal_max_du, -1.0, d.tm_pair_q, d.tm_pair_t, d.tm_pair_d,
+                        d.tm_pair_count);
+  if (rc) return rc;
+  assemble_kernel<<<B, 256, 0, ctx->stream>>>(d.tm_pair_q, d.tm_pair_t, d.tm_pair_count, d.tm_q_start, B, cap, d.xyz, d.b_top,
+                                              d.b_bot, d.p_ref, d.p_cur, d.f_cur, d.cam, d.n_corr, d.n_corr_top);
+  SOS_LAUNCHED(ctx);
+  // step 5
+  rc = sos_ransac_p3d(ctx, d.p_ref, d.p_cur, d.f_cur, d.cam, d.n_corr, B, 2 * cap, c.rig, 2, fe->hyp, c.n_hyp, 0,
+                      c.score_mode, c.ransac_threshold, d.ransac_pose, d.best_hyp, d.best_count, d.inlier_mask, nullptr,
+                      nullptr);
+  if (rc) return rc;
+  if (c.refit) {
+    rc = sos_refit_inliers(ctx, d.p_ref, d.p_cur, d.inlier_mask, d.n_corr, B, 2 * cap, d.pose, d.n_refit);
+    if (rc) return rc;
+  } else {
+    SOS_CUDA(cudaMemcpyAsync(d.pose, d.ransac_pose, (size_t)B * 12 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  stats_kernel<<<sos_div_up(B, 128), 128, 0, ctx->stream>>>(d.n, d.n_corr, d.best_count, d.best_hyp, B, d.stats);
+  SOS_LAUNCHED(ctx);
+  // carry the last frame over as the reference of the next step: slot B -> slot 0
+  const size_t last = (size_t)B * cap;
+  SOS_CUDA(cudaMemcpyAsync(d.uv_top, d.uv_top + last * 2, (size_t)cap * 2 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  SOS_CUDA(cudaMemcpyAsync(d.uv_bot, d.uv_bot + last * 2, (size_t)cap * 2 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  SOS_CUDA(cudaMemcpyAsync(d.b_top, d.b_top + last * 3, (size_t)cap * 3 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  SOS_CUDA(cudaMemcpyAsync(d.b_bot, d.b_bot + last * 3, (size_t)cap * 3 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  SOS_CUDA(cudaMemcpyAsync(d.xyz, d.xyz + last * 3, (size_t)cap * 3 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  for (int view = 0; view < 2; ++view) {
+    uint32_t* base = d.desc_c + (size_t)view * (B + 1) * cap * 8;
+    SOS_CUDA(cudaMemcpyAsync(base, base + last * 8, (size_t)cap * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  SOS_CUDA(cudaMemcpyAsync(d.n, d.n + B, sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  return SOS_OK;
+}
+
+int run_step(sos_frontend* fe, const uint8_t* omni, const float* px_top, const uint32_t* desc_top, const int32_t* boff_top,
+             const float* px_bot, const uint32_t* desc_bot, const int32_t* boff_bot) {
+  sos_ctx* ctx = fe->ctx;
+  if (!fe->use_graph) return enqueue_step(fe, omni, px_top, desc_top, boff_top, px_bot, desc_bot, boff_bot);
+  sos_frontend::GraphKey key = {{omni, px_top, desc_top, boff_top, px_bot, desc_bot, boff_bot}};
+  for (auto& g : fe->graphs) {
+    if (memcmp(&g.key, &key, sizeof(key)) == 0) {
+      SOS_CUDA(cudaGraphLaunch(g.exec, ctx->stream));
+      ctx->launches += fe->d.launches_per_step;
+      return SOS_OK;
+    }
+  }
+  // first time with these buffers: run once eagerly (sizes the scratch arena), then capture
+  const int64_t before = ctx->launches;
+  int rc = enqueue_step(fe, omni, px_top, desc_top, boff_top, px_bot, desc_bot, boff_bot);
+  if (rc) return rc;
+  fe->d.launches_per_step = (int)(ctx->launches - before);
+  SOS_CUDA(cudaStreamSynchronize(ctx->stream));
+  // the eager run advanced the carried state; capturing does not execute anything
+  cudaGraph_t graph = nullptr;
+  SOS_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  const int64_t l0 = ctx->launches;
+  rc = enqueue_step(fe, omni, px_top, desc_top, boff_top, px_bot, desc_bot, boff_bot);
+  ctx->launches = l0;
+  cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+  if (rc) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) {
+    sos_set_error("sos_frontend: graph capture failed: %s", cudaGetErrorString(e));
+    return SOS_ERR_CUDA;
+  }
+  sos_frontend::GraphEntry ge;
+  ge.key = key;
+  SOS_CUDA(cudaGraphInstantiate(&ge.exec, graph, 0));
+  cudaGraphDestroy(graph);
+  if (fe->graphs.size() >= 8) {
+    cudaGraphExecDestroy(fe->graphs.front().exec);
+    fe->graphs.erase(fe->graphs.begin());
+  }
+  fe->graphs.push_back(ge);
+  return SOS_OK;
+}
+
+}  // namespace
+
+extern "C" int sos_frontend_create(sos_ctx* ctx, const sos_frontend_config* cfg, const sos_lut_entry* lut,
+                                   const uint32_t* hyp, sos_frontend** out) {
+  SOS_CHECK_ARG(ctx && cfg && lut && hyp && out, "NULL argument");
+  SOS_CHECK_ARG(cfg->batch > 0 && cfg->batch <= 4096, "batch out of range");
+  SOS_CHECK_ARG(cfg->channels == 1 || cfg->channels == 3 || cfg->channels == 4, "channels must be 1, 3 or 4");
+  SOS_CHECK_ARG(cfg->n_buckets > 0 && cfg->max_feat_per_view > 0 && cfg->max_feat_per_bucket > 0 && cfg->cap > 0, "bad capacity");
+  SOS_CHECK_ARG(cfg->n_hyp >= 0, "negative n_hyp");
+  SOS_CUDA(cudaSetDevice(ctx->device));
+  sos_frontend* fe = new sos_frontend();
+  // private context: same device and stream, but its own scratch arena — the arena address is baked into the captured
+  // graphs, so no other caller may regrow it
+  fe->ctx = new sos_ctx();
+  fe->ctx->device = ctx->device;
+  // ... and its own compute stream (the caller's may be the legacy default stream, which cannot be captured); every
+  // step is fenced against the caller's current stream with events, so the caller sees ordinary stream semantics
+  SOS_CUDA(cudaStreamCreateWithFlags(&fe->ctx->stream, cudaStreamNonBlocking));
+  fe->ctx->own_stream = true;
+  SOS_CUDA(cudaEventCreateWithFlags(&fe->ev_in, cudaEventDisableTiming));
+  SOS_CUDA(cudaEventCreateWithFlags(&fe->ev_out, cudaEventDisableTiming));
+  fe->ctx->sm_count = ctx->sm_count;
+  fe->parent = ctx;
+  fe->cfg = *cfg;
+  fe->lut = lut;
+  fe->hyp = hyp;
+  memset(&fe->d, 0, sizeof(fe->d));
+  const sos_frontend_config& c = fe->cfg;
+  const size_t B = c.batch, F = c.max_feat_per_view, cap = c.cap, S = B * c.n_buckets, slots = B + 1;
+  sos_frontend_buffers& d = fe->d;
+  int rc = SOS_OK;
+#define FE_ALLOC(field, count) \
+  if (rc == SOS_OK) rc = fe_alloc(fe, &d.field, (count))
+  FE_ALLOC(pano, B * 2 * c.pano_rows * c.pano_cols * c.channels);
+  FE_ALLOC(st_q_start, S); FE_ALLOC(st_q_len, S); FE_ALLOC(st_t_start, S); FE_ALLOC(st_t_len, S);
+  FE_ALLOC(st_idx0, B * F); FE_ALLOC(st_d0, B * F);
+  FE_ALLOC(st_pair_q, B * F); FE_ALLOC(st_pair_t, B * F); FE_ALLOC(st_pair_d, B * F); FE_ALLOC(st_pair_count, S);
+  // compacted per-frame store: uv_c holds both views back to back so that descriptor-store rows index it directly
+  FE_ALLOC(uv_c, 2 * slots * cap * 2);
+  d.uv_top = d.uv_c;
+  d.uv_bot = d.uv_c + slots * cap * 2;
+  FE_ALLOC(b_top, slots * cap * 3); FE_ALLOC(b_bot, slots * cap * 3); FE_ALLOC(xyz, slots * cap * 3);
+  FE_ALLOC(src_top, slots * cap); FE_ALLOC(src_bot, slots * cap); FE_ALLOC(n, slots);
+  FE_ALLOC(desc_c, 2 * slots * cap * 8);
+  FE_ALLOC(tm_q_start, 2 * B); FE_ALLOC(tm_q_len, 2 * B); FE_ALLOC(tm_t_start, 2 * B); FE_ALLOC(tm_t_len, 2 * B);
+  FE_ALLOC(tm_idx0, 2 * slots * cap); FE_ALLOC(tm_d0, 2 * slots * cap);
+  FE_ALLOC(tm_pair_q, 2 * slots * cap); FE_ALLOC(tm_pair_t, 2 * slots * cap); FE_ALLOC(tm_pair_d, 2 * slots * cap);
+  FE_ALLOC(tm_pair_count, 2 * B);
+  FE_ALLOC(p_ref, B * 2 * cap * 3); FE_ALLOC(p_cur, B * 2 * cap * 3); FE_ALLOC(f_cur, B * 2 * cap * 3);
+  FE_ALLOC(cam, B * 2 * cap); FE_ALLOC(n_corr, B); FE_ALLOC(n_corr_top, B);
+  FE_ALLOC(ransac_pose, B * 12); FE_ALLOC(pose, B * 12); FE_ALLOC(best_hyp, B); FE_ALLOC(best_count, B);
+  FE_ALLOC(n_refit, B); FE_ALLOC(inlier_mask, B * 2 * cap); FE_ALLOC(stats, B * 4);
+#undef FE_ALLOC
+  if (rc != SOS_OK) {
+    sos_frontend_destroy(fe);
+    return rc;
+  }
+  d.batch = c.batch;
+  d.cap = c.cap;
+  SOS_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = fe;
+  return SOS_OK;
+}
+
+extern "C" int sos_frontend_destroy(sos_frontend* fe) {
+  if (!fe) return SOS_OK;
+  cudaSetDevice(fe->ctx->device);
+  cudaStreamSynchronize(fe->ctx->stream);
+  if (fe->copy_stream) cudaStreamSynchronize(fe->copy_stream);
+  for (auto& g : fe->graphs) cudaGraphExecDestroy(g.exec);
+  for (void* p : fe->owned) cudaFree(p);
+  for (auto& s : fe->stage) {
+    if (s.h_poses) cudaFreeHost(s.h_poses);
+    if (s.h_stats) cudaFreeHost(s.h_stats);
+    if (s.copied) cudaEventDestroy(s.copied);
+    if (s.done) cudaEventDestroy(s.done);
+  }
+  if (fe->copy_stream) cudaStreamDestroy(fe->copy_stream);
+  if (fe->ev_in) cudaEventDestroy(fe->ev_in);
+  if (fe->ev_out) cudaEventDestroy(fe->ev_out);
+  if (fe->ctx->own_stream && fe->ctx->stream) cudaStreamDestroy(fe->ctx->stream);
+  if (fe->ctx->arena) cudaFree(fe->ctx->arena);
+  delete fe->ctx;
+  delete fe;
+  return SOS_OK;
+}
+
+extern "C" int sos_frontend_reset(sos_frontend* fe) {
+  SOS_CHECK_ARG(fe, "fe is NULL");
+  SOS_CUDA(cudaMemsetAsync(fe->d.n, 0, sizeof(int32_t) * (fe->cfg.batch + 1), fe->ctx->stream));
+  SOS_CUDA(cudaStreamSynchronize(fe->ctx->stream));
+  return SOS_OK;
+}
+
+extern "C" int sos_frontend_set_graph(sos_frontend* fe, int enabled) {
+  SOS_CHECK_ARG(fe, "fe is NULL");
+  fe->use_graph = enabled != 0;
+  return SOS_OK;
+}
+
+extern "C" int sos_frontend_get_buffers(sos_frontend* fe, sos_frontend_buffers* out) {
+  SOS_CHECK_ARG(fe && out, "NULL argument");
+  *out = fe->d;
+  return SOS_OK;
+}
+
+extern "C" int sos_frontend_step(sos_frontend* fe, const uint8_t* omni, const float* px_top, const uint32_t* desc_top,
+                                 const int32_t* bucket_off_top, const float* px_bot, const uint32_t* desc_bot,
+                                 const int32_t* bucket_off_bot) {
+  SOS_CHECK_ARG(fe, "fe is NULL");
+  SOS_CHECK_ARG(omni && px_top && desc_top && bucket_off_top && px_bot && desc_bot && bucket_off_bot, "NULL input");
+  SOS_CUDA(cudaSetDevice(fe->ctx->device));
+  // inputs were produced on the caller's stream; results must be visible to it afterwards
+  SOS_CUDA(cudaEventRecord(fe->ev_in, fe->parent->stream));
+  SOS_CUDA(cudaStreamWaitEvent(fe->ctx->stream, fe->ev_in, 0));
+  const int64_t before = fe->ctx->launches;
+  const int rc = run_step(fe, omni, px_top, desc_top, bucket_off_top, px_bot, desc_bot, bucket_off_bot);
+  fe->parent->launches += fe->ctx->launches - before;
+  if (rc) return rc;
+  SOS_CUDA(cudaEventRecord(fe->ev_out, fe->ctx->stream));
+  SOS_CUDA(cudaStreamWaitEvent(fe->parent->stream, fe->ev_out, 0));
+  return SOS_OK;
+}
+
+static int ensure_staging(sos_frontend* fe) {
+  if (fe->copy_stream) return SOS_OK;
+  const sos_frontend_config& c = fe->cfg;
+  const size_t B = c.batch, F = c.max_feat_per_view;
+  SOS_CUDA(cudaStreamCreateWithFlags(&fe->copy_stream, cudaStreamNonBlocking));
+  for (auto& s : fe->stage) {
+    int rc = fe_alloc(fe, &s.omni, B * c.src_h * c.src_w * c.channels);
+    if (!rc) rc = fe_alloc(fe, &s.px_top, B * F * 2);
+    if (!rc) rc = fe_alloc(fe, &s.px_bot, B * F * 2);
+    if (!rc) rc = fe_alloc(fe, &s.desc_top, B * F * 8);
+    if (!rc) rc = fe_alloc(fe, &s.desc_bot, B * F * 8);
+    if (!rc) rc = fe_alloc(fe, &s.boff_top, B * (c.n_buckets + 1));
+    if (!rc) rc = fe_alloc(fe, &s.boff_bot, B * (c.n_buckets + 1));
+    if (rc) return rc;
+    SOS_CUDA(cudaMallocHost((void**)&s.h_poses, B * 12 * sizeof(float)));
+    SOS_CUDA(cudaMallocHost((void**)&s.h_stats, B * 4 * sizeof(int32_t)));
+    SOS_CUDA(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+    SOS_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+  }
+  SOS_CUDA(cudaStreamSynchronize(fe->ctx->stream));
+  return SOS_OK;
+}
+
+extern "C" int sos_frontend_submit_host(sos_frontend* fe, const uint8_t* omni, const float* px_top,
+                                        const uint32_t* desc_top, const int32_t* bucket_off_top, const float* px_bot,
+                                        const uint32_t* desc_bot, const int32_t* bucket_off_bot, int* ticket) {
+  SOS_CHECK_ARG(fe && ticket, "NULL argument");
+  SOS_CHECK_ARG(omni && px_top && desc_top && bucket_off_top && px_bot && desc_bot && bucket_off_bot, "NULL input");
+  SOS_CUDA(cudaSetDevice(fe->ctx->device));
+  int rc = ensure_staging(fe);
+  if (rc) return rc;
+  const int k = fe->next_stage;
+  sos_frontend::Stage& s = fe->stage[k];
+  if (s.in_flight) {
+    sos_set_error("sos_frontend_submit_host: both staging slots are in flight; call sos_frontend_wait_host first");
+    return SOS_ERR_INVALID;
+  }
+  const sos_frontend_config& c = fe->cfg;
+  const size_t B = c.batch, F = c.max_feat_per_view;
+  cudaStream_t cs = fe->copy_stream;
+  // H2D on the copy stream so that it overlaps the kernels of the previous step
+  SOS_CUDA(cudaMemcpyAsync(s.omni, omni, B * c.src_h * c.src_w * c.channels, cudaMemcpyHostToDevice, cs));
+  SOS_CUDA(cudaMemcpyAsync(s.px_top, px_top, B * F * 2 * sizeof(float), cudaMemcpyHostToDevice, cs));
+  SOS_CUDA(cudaMemcpyAsync(s.px_bot, px_bot, B * F * 2 * sizeof(float), cudaMemcpyHostToDevice, cs));
+  SOS_CUDA(cudaMemcpyAsync(s.desc_top, desc_top, B * F * 32, cudaMemcpyHostToDevice, cs));
+  SOS_CUDA(cudaMemcpyAsync(s.desc_bot, desc_bot, B * F * 32, cudaMemcpyHostToDevice, cs));
+  SOS_CUDA(cudaMemcpyAsync(s.boff_top, bucket_off_top, B * (c.n_buckets + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+  SOS_CUDA(cudaMemcpyAsync(s.boff_bot, bucket_off_bot, B * (c.n_buckets + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, cs));
+  SOS_CUDA(cudaEventRecord(s.copied, cs));
+  SOS_CUDA(cudaStreamWaitEvent(fe->ctx->stream, s.copied, 0));
+  const int64_t before = fe->ctx->launches;
+  rc = run_step(fe, s.omni, s.px_top, s.desc_top, s.boff_top, s.px_bot, s.desc_bot, s.boff_bot);
+  fe->parent->launches += fe->ctx->launches - before;
+  if (rc) return rc;
+  SOS_CUDA(cudaMemcpyAsync(s.h_poses, fe->d.pose, B * 12 * sizeof(float), cudaMemcpyDeviceToHost, fe->ctx->stream));
+  SOS_CUDA(cudaMemcpyAsync(s.h_stats, fe->d.stats, B * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, fe->ctx->stream));
+  SOS_CUDA(cudaEventRecord(s.done, fe->ctx->stream));
+  // slot reuse is safe: sos_frontend_wait_host(ticket) must return before this slot is submitted to again
+  s.in_flight = true;
+  *ticket = k;
+  fe->next_stage = (k + 1) % sos_frontend::DEPTH;
+  return SOS_OK;
+}
+
+extern "C" int sos_frontend_wait_host(sos_frontend* fe, int ticket, float* poses, int32_t* stats) {
+  SOS_CHECK_ARG(fe, "fe is NULL");
+  SOS_CHECK_ARG(ticket >= 0 && ticket < sos_frontend::DEPTH && fe->stage[ticket].in_flight, "unknown ticket");
+  sos_frontend::Stage& s = fe->stage[ticket];
+  SOS_CUDA(cudaEventSynchronize(s.done));
+  const size_t B = fe->cfg.batch;
+  if (poses) memcpy(poses, s.h_poses, B * 12 * sizeof(float));
+  if (stats) memcpy(stats, s.h_stats, B * 4 * sizeof(int32_t));
+  s.in_flight = false;
+  return SOS_OK;
+}
+
+extern "C" int sos_frontend_step_host(sos_frontend* fe, const uint8_t* omni, const float* px_top, const uint32_t* desc_top,
+                                      const int32_t* bucket_off_top, const float* px_bot, const uint32_t* desc_bot,
+                                      const int32_t* bucket_off_bot, float* poses, int32_t* stats) {
+  int ticket = -1;
+  int rc = sos_frontend_submit_host(fe, omni, px_top, desc_top, bucket_off_top, px_bot, desc_bot, bucket_off_bot, &ticket);
+  if (rc) return rc;
+  return sos_frontend_wait_host(fe, ticket, poses, stats);
+}

@@ -31,15 +31,16 @@ __device__ __forceinline__ uint32_t hamming256(const uint4& qa, const uint4& qb,
 }
 
 __global__ void __launch_bounds__(HB_THREADS)
-hamming_partial_kernel(const uint4* __restrict__ q, const uint4* __restrict__ t, const int32_t* __restrict__ seg_q,
-                       const int32_t* __restrict__ seg_t, int splits, uint2* __restrict__ partial) {
+hamming_partial_kernel(const uint4* __restrict__ q, const uint4* __restrict__ t, const int32_t* __restrict__ q_start,
+                       const int32_t* __restrict__ q_len, const int32_t* __restrict__ t_start,
+                       const int32_t* __restrict__ t_len, int max_nq, int splits, uint2* __restrict__ partial) {
   __shared__ uint4 tile[HB_TILE_T * 2];
 
   const int seg = blockIdx.z;
-  const int q0 = seg_q[seg], nq = seg_q[seg + 1] - q0;
+  const int q0 = q_start[seg], nq = min(q_len[seg], max_nq);
   const int q_tile = blockIdx.x * HB_TILE_Q;
   if (q_tile >= nq) return;
-  const int t0 = seg_t[seg], nt = seg_t[seg + 1] - t0;
+  const int t0 = t_start[seg], nt = t_len[seg];
   const int split = blockIdx.y;
   const int chunk = (nt + splits - 1) / splits;
   const int t_begin = min(nt, split * chunk);
@@ -94,19 +95,19 @@ hamming_partial_kernel(const uint4* __restrict__ q, const uint4* __restrict__ t,
 #pragma unroll
   for (int r = 0; r < HB_QPT; ++r) {
     const int row = q_tile + r * HB_THREADS + threadIdx.x;
-    if (row < nq) partial[(size_t)(q0 + row) * splits + split] = make_uint2(k0[r], k1[r]);
+    if (row < nq) partial[((size_t)seg * max_nq + row) * splits + split] = make_uint2(k0[r], k1[r]);
   }
 }
 
 __global__ void __launch_bounds__(256)
-hamming_merge_kernel(const uint2* __restrict__ partial, const int32_t* __restrict__ seg_q, int splits,
-                     int32_t* __restrict__ idx0, int32_t* __restrict__ d0, int32_t* __restrict__ idx1,
-                     int32_t* __restrict__ d1) {
+hamming_merge_kernel(const uint2* __restrict__ partial, const int32_t* __restrict__ q_start,
+                     const int32_t* __restrict__ q_len, int max_nq, int splits, int32_t* __restrict__ idx0,
+                     int32_t* __restrict__ d0, int32_t* __restrict__ idx1, int32_t* __restrict__ d1) {
   const int seg = blockIdx.y;
-  const int q0 = seg_q[seg], nq = seg_q[seg + 1] - q0;
+  const int q0 = q_start[seg], nq = min(q_len[seg], max_nq);
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= nq) return;
-  const uint2* p = partial + (size_t)(q0 + row) * splits;
+  const uint2* p = partial + ((size_t)seg * max_nq + row) * splits;
   uint32_t k0 = KEY_NONE, k1 = KEY_NONE;
   for (int s = 0; s < splits; ++s) {
     const uint2 v = p[s];
@@ -133,7 +134,7 @@ constexpr int MS_BINS = 257;
 struct SelectArgs {
   int mode;
   double ratio;
-  const int32_t *idx0, *d0, *d1, *rev_idx0, *seg_q, *seg_t;
+  const int32_t *idx0, *d0, *d1, *rev_idx0, *q_start, *q_len, *t_start;
   const float2 *px_q, *px_t;
   double max_du, min_dv;
   int32_t *out_q, *out_t, *out_d, *out_count;
@@ -165,8 +166,8 @@ __global__ void __launch_bounds__(MS_THREADS) match_select_kernel(SelectArgs a) 
   __shared__ unsigned char warpcnt[MS_WARPS][MS_BINS + 3];
 
   const int seg = blockIdx.x;
-  const int q0 = a.seg_q[seg], nq = a.seg_q[seg + 1] - q0;
-  const int t0 = a.seg_t[seg];
+  const int q0 = a.q_start[seg], nq = a.q_len[seg];
+  const int t0 = a.t_start[seg];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   for (int i = tid; i <= MS_BINS; i += MS_THREADS) hist[i] = 0;
@@ -237,15 +238,15 @@ __global__ void __launch_bounds__(MS_THREADS) match_select_kernel(SelectArgs a) 
 
 }  // namespace
 
-extern "C" int sos_hamming_top2(sos_ctx* ctx, const uint32_t* q, const uint32_t* t, const int32_t* seg_q,
-                                const int32_t* seg_t, int n_seg, int max_nq, int max_nt, int32_t* idx0,
-                                int32_t* d0, int32_t* idx1, int32_t* d1) {
+extern "C" int sos_hamming_top2(sos_ctx* ctx, const uint32_t* q, const uint32_t* t, const int32_t* q_start,
+                                const int32_t* q_len, const int32_t* t_start, const int32_t* t_len, int n_seg,
+                                int max_nq, int max_nt, int32_t* idx0, int32_t* d0, int32_t* idx1, int32_t* d1) {
   SOS_CHECK_ARG(ctx, "ctx is NULL");
   SOS_CHECK_ARG(n_seg >= 0 && max_nq >= 0 && max_nt >= 0, "negative size");
   SOS_CHECK_ARG(n_seg <= 65535, "at most 65535 segments per call");
   SOS_CHECK_ARG(max_nt < (1 << KEY_IDX_BITS), "segment has too many train rows (limit 4194303)");
   if (n_seg == 0 || max_nq == 0) return SOS_OK;
-  SOS_CHECK_ARG(q && t && seg_q && seg_t && idx0 && d0, "NULL array");
+  SOS_CHECK_ARG(q && t && q_start && q_len && t_start && t_len && idx0 && d0, "NULL array");
   SOS_CHECK_ARG(((uintptr_t)q & 15) == 0 && ((uintptr_t)t & 15) == 0, "descriptor arrays must be 16-byte aligned");
   SOS_CUDA(cudaSetDevice(ctx->device));
 
@@ -263,25 +264,25 @@ extern "C" int sos_hamming_top2(sos_ctx* ctx, const uint32_t* q, const uint32_t*
   if (rc != SOS_OK) return rc;
 
   dim3 grid(q_tiles, splits, n_seg);
-  hamming_partial_kernel<<<grid, HB_THREADS, 0, ctx->stream>>>((const uint4*)q, (const uint4*)t, seg_q, seg_t, splits,
-                                                               (uint2*)ws);
+  hamming_partial_kernel<<<grid, HB_THREADS, 0, ctx->stream>>>((const uint4*)q, (const uint4*)t, q_start, q_len, t_start,
+                                                               t_len, max_nq, splits, (uint2*)ws);
   SOS_LAUNCHED(ctx);
   dim3 mgrid(sos_div_up(max_nq, 256), n_seg);
-  hamming_merge_kernel<<<mgrid, 256, 0, ctx->stream>>>((const uint2*)ws, seg_q, splits, idx0, d0, idx1, d1);
+  hamming_merge_kernel<<<mgrid, 256, 0, ctx->stream>>>((const uint2*)ws, q_start, q_len, max_nq, splits, idx0, d0, idx1, d1);
   SOS_LAUNCHED(ctx);
   return SOS_OK;
 }
 
 extern "C" int sos_match_select(sos_ctx* ctx, int mode, double ratio, const int32_t* idx0, const int32_t* d0,
-                                const int32_t* d1, const int32_t* rev_idx0, const int32_t* seg_q,
-                                const int32_t* seg_t, int n_seg, int max_nq, const float* px_q,
+                                const int32_t* d1, const int32_t* rev_idx0, const int32_t* q_start,
+                                const int32_t* q_len, const int32_t* t_start, int n_seg, const float* px_q,
                                 const float* px_t, double max_du, double min_dv, int32_t* out_q,
                                 int32_t* out_t, int32_t* out_d, int32_t* out_count) {
   SOS_CHECK_ARG(ctx, "ctx is NULL");
   SOS_CHECK_ARG(mode == SOS_MATCH_NN || mode == SOS_MATCH_RATIO || mode == SOS_MATCH_CROSS, "unknown mode");
-  SOS_CHECK_ARG(n_seg >= 0 && max_nq >= 0, "negative size");
+  SOS_CHECK_ARG(n_seg >= 0, "negative size");
   if (n_seg == 0) return SOS_OK;
-  SOS_CHECK_ARG(idx0 && d0 && seg_q && seg_t && out_q && out_t && out_d && out_count, "NULL array");
+  SOS_CHECK_ARG(idx0 && d0 && q_start && q_len && t_start && out_q && out_t && out_d && out_count, "NULL array");
   SOS_CHECK_ARG(mode != SOS_MATCH_RATIO || d1, "ratio mode needs d1");
   SOS_CHECK_ARG(mode != SOS_MATCH_CROSS || rev_idx0, "cross mode needs rev_idx0");
   SOS_CHECK_ARG((px_q == nullptr) == (px_t == nullptr), "px_q and px_t must be given together");
@@ -289,11 +290,10 @@ extern "C" int sos_match_select(sos_ctx* ctx, int mode, double ratio, const int3
   SelectArgs a;
   a.mode = mode;
   a.ratio = ratio;
-  a.idx0 = idx0; a.d0 = d0; a.d1 = d1; a.rev_idx0 = rev_idx0; a.seg_q = seg_q; a.seg_t = seg_t;
+  a.idx0 = idx0; a.d0 = d0; a.d1 = d1; a.rev_idx0 = rev_idx0; a.q_start = q_start; a.q_len = q_len; a.t_start = t_start;
   a.px_q = (const float2*)px_q; a.px_t = (const float2*)px_t;
   a.max_du = max_du; a.min_dv = min_dv;
   a.out_q = out_q; a.out_t = out_t; a.out_d = out_d; a.out_count = out_count;
-  (void)max_nq;
   match_select_kernel<<<n_seg, MS_THREADS, 0, ctx->stream>>>(a);
   SOS_LAUNCHED(ctx);
   return SOS_OK;

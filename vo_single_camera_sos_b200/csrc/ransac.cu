@@ -588,7 +588,7 @@ extern "C" int sos_ransac_p3d(sos_ctx* ctx, const float* p_ref, const float* p_c
                               const uint8_t* cam, const int32_t* n, int n_problems, int cap, const double* rig,
                               int n_cams, const uint32_t* hyp, int n_hyp, int hyp_offset, int score_mode,
                               double threshold, float* best_pose, int32_t* best_hyp, int32_t* best_count,
-                              uint8_t* inlier_mask, uint64_t* best_key) {
+                              uint8_t* inlier_mask, uint64_t* best_key, int32_t* all_counts) {
   SOS_CHECK_ARG(ctx, "ctx is NULL");
   SOS_CHECK_ARG(n_problems >= 0 && cap >= 0 && n_hyp >= 0, "negative size");
   SOS_CHECK_ARG(score_mode == SOS_SCORE_EUCLID || score_mode == SOS_SCORE_BEARING, "unknown score mode");
@@ -623,6 +623,9 @@ extern "C" int sos_ransac_p3d(sos_ctx* ctx, const float* p_ref, const float* p_c
   argmax_kernel<<<n_problems, 256, 0, ctx->stream>>>(s.counts, s.recs, n_hyp, hyp_offset, best_pose, best_hyp,
                                                      best_count, best_key, s.best_rec);
   SOS_LAUNCHED(ctx);
+  if (all_counts && n_hyp > 0)
+    SOS_CUDA(cudaMemcpyAsync(all_counts, s.counts, (size_t)n_problems * n_hyp * sizeof(int32_t), cudaMemcpyDeviceToDevice,
+                             ctx->stream));
   if (inlier_mask && cap > 0) {
     dim3 mgrid(sos_div_up(cap, 256), n_problems);
     const float* q = score_mode == SOS_SCORE_EUCLID ? p_cur : f_cur;

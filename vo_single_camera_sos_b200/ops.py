@@ -154,23 +154,27 @@ class Context:
         return mx, my
 
     # -- step 2: Hamming ----------------------------------------------------------------------------------------
-    def hamming_top2(self, q: torch.Tensor, t: torch.Tensor, seg_q: torch.Tensor, seg_t: torch.Tensor, max_nq: int,
-                     max_nt: int, want_second: bool = True):
-        """q [Nq,32] uint8 (or [Nq,8] int32), t likewise; seg_* [S+1] int32 device prefix offsets."""
+    def hamming_top2(self, q: torch.Tensor, t: torch.Tensor, q_start, q_len, t_start, t_len, max_nq: int, max_nt: int,
+                     want_second: bool = True, out=None):
+        """q [Nq,32] uint8 (or [Nq,8] int32), t likewise; q_start/q_len/t_start/t_len [S] int32 DEVICE tensors."""
         self._sync_stream()
         nq = q.shape[0]
-        n_seg = seg_q.numel() - 1
+        n_seg = q_start.numel()
         qp = self._desc(q, "q")
         tp = self._desc(t, "t")
-        idx0 = self.empty((nq,), torch.int32)
-        d0 = self.empty((nq,), torch.int32)
-        idx1 = self.empty((nq,), torch.int32) if want_second else None
-        d1 = self.empty((nq,), torch.int32) if want_second else None
-        check(self.lib.sos_hamming_top2(self._h, qp, tp, self._t(seg_q, torch.int32, "seg_q"),
-                                        self._t(seg_t, torch.int32, "seg_t"), n_seg, int(max_nq), int(max_nt),
+        if out is None:
+            idx0 = torch.full((nq,), -1, dtype=torch.int32, device=self.device)
+            d0 = torch.full((nq,), -1, dtype=torch.int32, device=self.device)
+            idx1 = torch.full((nq,), -1, dtype=torch.int32, device=self.device) if want_second else None
+            d1 = torch.full((nq,), -1, dtype=torch.int32, device=self.device) if want_second else None
+        else:
+            idx0, d0, idx1, d1 = out
+        check(self.lib.sos_hamming_top2(self._h, qp, tp, self._t(q_start, torch.int32, "q_start"),
+                                        self._t(q_len, torch.int32, "q_len"), self._t(t_start, torch.int32, "t_start"),
+                                        self._t(t_len, torch.int32, "t_len"), n_seg, int(max_nq), int(max_nt),
                                         idx0.data_ptr(), d0.data_ptr(),
-                                        idx1.data_ptr() if want_second else None,
-                                        d1.data_ptr() if want_second else None))
+                                        idx1.data_ptr() if idx1 is not None else None,
+                                        d1.data_ptr() if d1 is not None else None))
         return idx0, d0, idx1, d1
 
     def _desc(self, d: torch.Tensor, what: str):
@@ -182,19 +186,23 @@ class Context:
             raise ValueError(f"{what}: int32 descriptors must be [N,8]")
         return self._t(d, torch.int32, what)
 
-    def match_select(self, mode: int, idx0, d0, d1, seg_q, seg_t, max_nq: int, rev_idx0=None, px_q=None, px_t=None,
-                     max_du: float = -1.0, min_dv: float = -1.0, ratio: float = 0.75):
+    def match_select(self, mode: int, idx0, d0, d1, q_start, q_len, t_start, rev_idx0=None, px_q=None, px_t=None,
+                     max_du: float = -1.0, min_dv: float = -1.0, ratio: float = 0.75, out=None):
         self._sync_stream()
         nq = idx0.shape[0]
-        n_seg = seg_q.numel() - 1
-        out_q = self.empty((nq,), torch.int32)
-        out_t = self.empty((nq,), torch.int32)
-        out_d = self.empty((nq,), torch.int32)
-        out_count = self.empty((n_seg,), torch.int32)
+        n_seg = q_start.numel()
+        if out is None:
+            out_q = self.empty((nq,), torch.int32)
+            out_t = self.empty((nq,), torch.int32)
+            out_d = self.empty((nq,), torch.int32)
+            out_count = self.empty((n_seg,), torch.int32)
+        else:
+            out_q, out_t, out_d, out_count = out
         check(self.lib.sos_match_select(
             self._h, int(mode), float(ratio), self._t(idx0, torch.int32, "idx0"), self._t(d0, torch.int32, "d0"),
             self._t(d1, torch.int32, "d1", optional=True), self._t(rev_idx0, torch.int32, "rev_idx0", optional=True),
-            self._t(seg_q, torch.int32, "seg_q"), self._t(seg_t, torch.int32, "seg_t"), n_seg, int(max_nq),
+            self._t(q_start, torch.int32, "q_start"), self._t(q_len, torch.int32, "q_len"),
+            self._t(t_start, torch.int32, "t_start"), n_seg,
             self._t(px_q, torch.float32, "px_q", optional=True), self._t(px_t, torch.float32, "px_t", optional=True),
             float(max_du), float(min_dv), out_q.data_ptr(), out_t.data_ptr(), out_d.data_ptr(), out_count.data_ptr()))
         return out_q, out_t, out_d, out_count
@@ -312,7 +320,7 @@ class Context:
         return r, n_cams
 
     def ransac_p3d(self, p_ref, p_cur, n, hyp, score_mode: int, threshold: float, f_cur=None, cam=None, rig=None,
-                   n_cams: int = 0, hyp_offset: int = 0, want_mask: bool = True):
+                   n_cams: int = 0, hyp_offset: int = 0, want_mask: bool = True, all_counts=None):
         """p_ref, p_cur, f_cur [B, cap, 3] float32; cam [B, cap] uint8; n [B] int32; hyp [H,3] int64/uint32 bits."""
         self._sync_stream()
         B, cap, _ = p_ref.shape
@@ -328,7 +336,8 @@ class Context:
             self._t(f_cur, torch.float32, "f_cur", optional=True), self._t(cam, torch.uint8, "cam", optional=True),
             self._t(n, torch.int32, "n"), B, cap, _ptr(r), n_cams, self._t(hyp, torch.int32, "hyp"), H, int(hyp_offset),
             int(score_mode), float(threshold), pose.data_ptr(), best_hyp.data_ptr(), best_count.data_ptr(),
-            mask.data_ptr() if want_mask else None, key.data_ptr()))
+            mask.data_ptr() if want_mask else None, key.data_ptr(),
+            self._t(all_counts, torch.int32, "all_counts", optional=True)))
         return pose, best_hyp, best_count, mask, key
 
     def ransac_p3d_eval(self, p_ref, p_cur, n, hyp_row, score_mode: int, threshold: float, f_cur=None, cam=None,
