@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""bench.py — SOS front-end frame-pairs/s on B200 (BASELINE.json metric), with per-kernel roofline fractions and the
+CPU reference path timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|tiny] [--batch B]
+    python bench.py --impl reference ...          # the reference's CPU path (OpenCV + NumPy) on this box's host cores
+
+A "step" is one pass of the hot path over one batch of B new synthetic frames = B frame pairs (frame i-1 -> frame i):
+2 remaps, 12 stereo bucket matches, lifting + triangulation, 2 temporal matches and one RANSAC per pair.
+One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sos_frame_pairs_per_s"
+UNIT = "frame-pairs/s"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU path (oracle) on a bounded sample
+# ---------------------------------------------------------------------------------------------------------------------
+def host_workload(name: str, seed: int):
+    """Rig, scene, LUT maps and masks built WITHOUT the GPU (NumPy), for the CPU arm."""
+    from oracle import geometry
+    from vo_single_camera_sos_b200 import synth, workload
+    c = workload.CONFIGS[name]
+    rig = synth.make_rig(c["width"], c["height"], c["pano_cols"], seed=seed)
+    scene = synth.make_scene(int(c["feat"] * 2.0), seed=seed)
+    p = rig.pano
+    maps, masks = {}, {}
+    for which in ("top", "bot"):
+        lo, hi = rig.elev_top if which == "top" else rig.elev_bot
+        g = dict(zip(synth.GUM_FIELDS, rig.gum_vector(which)))
+        maps[which] = geometry.lut_build(g, p["rows"], p["cols"], p["cyl_height_max"], p["cyl_height_min"], lo, hi)
+        masks[which] = rig.mask(which)
+    hyp = np.random.default_rng(seed + 7).integers(0, 2 ** 32, (c["n_hyp"], 3), dtype=np.uint64).astype(np.uint32)
+    return rig, scene, maps, masks, hyp, c
+
+
+class CpuPath:
+    """One frame pair per call through oracle.pipeline (OpenCV with all its threads + NumPy)."""
+
+    def __init__(self, name: str, seed: int, n_frames: int, score_mode: str):
+        import cv2
+        from vo_single_camera_sos_b200 import synth
+        self.rig, self.scene, self.maps, self.masks, self.hyp, self.c = host_workload(name, seed)
+        self.mode = score_mode
+        self.thr = 1.0 - math.cos(math.radians(5.0)) if score_mode == "bearing" else 0.05
+        self.traj = synth.make_trajectory(n_frames, seed=seed)
+        self.threads = cv2.getNumThreads()
+        self.pano_g = dict(self.rig.pano)
+        base = synth.render_omni(self.rig, self.scene, self.traj[0])
+        rng = np.random.default_rng(seed)
+        self.frames = []
+        for i in range(n_frames):
+            f = synth.make_frame_features(self.rig, self.scene, self.traj[i], self.c["feat"], 12, seed=1000 * i + 17,
+                                          cap=self.c["cap"])
+            # one rendered view of the scene + a per-frame noise variant (content does not change the work done)
+            omni = base if i == 0 else np.bitwise_xor(base, rng.integers(0, 8, base.shape, dtype=np.uint8))
+            self.frames.append((omni, f))
+        self.rigm = np.zeros((2, 3, 4)); self.rigm[:, :, :3] = np.eye(3)
+        self.rigm[0, :, 3] = self.rig.f_top; self.rigm[1, :, 3] = self.rig.f_bot
+        self.state = None
+        self.cursor = 0
+
+    def _frame(self, i):
+        from oracle import pipeline
+        omni, f = self.frames[i % len(self.frames)]
+        panos = pipeline.remap_views(omni, self.maps, self.masks)
+        n_t, n_b = f["top"]["bucket_off"][-1], f["bot"]["bucket_off"][-1]
+        st = pipeline.stereo_frame(self.pano_g, self.rig.f_top, self.rig.f_bot, f["top"]["px"][:n_t], f["top"]["desc"][:n_t],
+                                   f["top"]["bucket_off"], f["bot"]["px"][:n_b], f["bot"]["desc"][:n_b],
+                                   f["bot"]["bucket_off"], cap=self.c["cap"])
+        st["panos"] = panos
+        return st
+
+    def prime(self):
+        self.state = self._frame(0)
+        self.cursor = 1
+
+    def pair(self):
+        from oracle import pipeline
+        cur = self._frame(self.cursor)
+        out = pipeline.track_pair(self.state, cur, self.hyp, self.mode, self.thr, self.rigm,
+                                  0.125 * 0.5 * self.rig.pano["cols"])
+        self.state = cur
+        self.cursor += 1
+        return out
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    t_build = time.perf_counter()
+    cpu = CpuPath(args.workload, seed=0, n_frames=min(args.steps + args.warmup + 1, 6), score_mode=args.score)
+    cpu.prime()
+    for _ in range(args.warmup):
+        cpu.pair()
+    t0 = time.perf_counter()
+    inl = []
+    for _ in range(args.steps):
+        o = cpu.pair()
+        inl.append(o["best_count"] if o else -1)
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    c = cpu.c
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/f64", "data": "synthetic",
+        "config": workload_config(args, c, batch=1, note="reference arm: one frame pair per step (bounded sample)"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.threads, "kind": "port",
+                         "sample": f"{args.steps} frame pairs of {args.workload}; OpenCV calls as the reference makes them "
+                                   f"({cpu.threads} threads) + NumPy float64; RANSAC = NumPy restatement (OpenGV absent)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "setup_s": t0 - t_build, "ransac_inliers": inl,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, c, batch, note=""):
+    return {"workload": f"{args.workload}: {c['width']}x{c['height']} omni -> 2 x {c['pano_cols']}-wide panoramas, "
+                        f"{c['feat']} ORB features/view in 12 azimuth buckets, {c['n_hyp']} RANSAC hypotheses, score={args.score}",
+            "frames_per_step": batch, "note": note}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_gpu(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from vo_single_camera_sos_b200 import ops, workload
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = ops.Context(local_rank)
+    B, K, W = args.batch, args.steps, args.warmup
+    n_sets = 2
+    score = ops.SCORE_BEARING if args.score == "bearing" else ops.SCORE_EUCLID
+    w = workload.build(ctx, args.workload, batch=B, n_frames=n_sets * B + 1, seed=rank, score_mode=score)
+    c = workload.CONFIGS[args.workload]
+    renderer = workload.DeviceRenderer(ctx, w)
+    sets = [workload.make_frames(w, s * B, B, renderer=renderer) for s in range(n_sets)]
+    dev_sets = [workload.to_device(ctx, fr) for fr in sets]
+    pin_sets = [workload.to_pinned(fr) for fr in sets]
+    in_bytes = sum(int(t.numel() * t.element_size()) for t in dev_sets[0])
+    fe = w.frontend(ctx)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ---------------------------------------------------------------------------------
+    for i in range(max(W, n_sets)):
+        fe.step(*dev_sets[i % n_sets])
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        fe.step(*dev_sets[i % n_sets])
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop()
+    stats = fe.buffers()["stats"].cpu().numpy()
+
+    # ---- end to end: pinned host buffers in, poses out, copies overlapped with the previous step's kernels -----------
+    fe2 = w.frontend(ctx)
+    for i in range(max(W, n_sets)):
+        fe2.step_host(*pin_sets[i % n_sets])
+    barrier()
+    t0 = time.perf_counter()
+    prev = None
+    for i in range(K):
+        tk = fe2.submit_host(*pin_sets[i % n_sets])
+        if prev is not None:
+            fe2.wait_host(prev)
+        prev = tk
+    poses, st2 = fe2.wait_host(prev)
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+    barrier()
+    d2h_bytes = int(poses.nbytes + st2.nbytes)
+
+    # ---- per-kernel times (CUDA events after every launch, eager replays of the same steps) --------------------------
+    fe.profile_begin()
+    for i in range(K):
+        fe.step(*dev_sets[i % n_sets])
+    marks = fe.profile_end(max_n=64 * K + 64)
+    torch.cuda.synchronize()
+    buf = fe.buffers()
+    per_step = buf["launches_per_step"]
+    kernels = summarize_kernels(marks, K)
+    # work actually done per step (device-side sizes)
+    st_pairs = int((buf["st_q_len"].long() * buf["st_t_len"].long()).sum())
+    tm_pairs = int((buf["tm_q_len"].long() * buf["tm_t_len"].long()).sum())
+    n_corr = buf["n_corr"].cpu().numpy().astype(np.int64)
+    rows, cols = w.cfg.pano_rows, w.cfg.pano_cols
+    remap_bytes = B * (2 * rows * cols * (8 + 3) + c["height"] * c["width"] * 3)
+    flop_pair = 30.0 if args.score == "euclid" else 45.0
+    popc_peak = ctx.peak_popc()   # T POPC/s, measured on this GPU just now
+    ffma_peak = ctx.peak_ffma()   # TFLOP/s, measured
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json (sustained copy)" if peaks else "fallback 6650 GB/s"
+
+    def k_ms(name):
+        return kernels.get(name, {}).get("ms", float("nan"))
+
+    roof = {}
+    t = k_ms("sos_remap_u8#0")
+    roof["remap"] = {"kernel": "remap_kernel<3>", "bound": "hbm", "achieved": remap_bytes / (t * 1e-3) / 1e9, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": remap_bytes / (t * 1e-3) / 1e9 / hbm_peak, "ms": t, "peak_source": hbm_src,
+                     "algorithmic_bytes": remap_bytes, "traffic": None}
+    t = k_ms("sos_hamming_top2#0:temporal")
+    ops_t = 8.0 * tm_pairs
+    roof["hamming_temporal"] = {"kernel": "hamming_partial_kernel", "bound": "int-pipe (POPC)", "achieved": ops_t / (t * 1e-3) / 1e12,
+                                "peak": popc_peak, "unit": "TPOPC/s", "frac": ops_t / (t * 1e-3) / 1e12 / popc_peak, "ms": t,
+                                "peak_source": "POPC microbenchmark run in this process", "descriptor_pairs": tm_pairs,
+                                "matches_per_s": tm_pairs / (t * 1e-3), "traffic": None}
+    t = k_ms("sos_hamming_top2#0:stereo")
+    ops_s = 8.0 * st_pairs
+    roof["hamming_stereo"] = {"kernel": "hamming_partial_kernel", "bound": "int-pipe (POPC)", "achieved": ops_s / (t * 1e-3) / 1e12,
+                              "peak": popc_peak, "unit": "TPOPC/s", "frac": ops_s / (t * 1e-3) / 1e12 / popc_peak, "ms": t,
+                              "descriptor_pairs": st_pairs, "matches_per_s": st_pairs / (t * 1e-3), "traffic": None}
+    t = k_ms("sos_ransac_p3d#1")
+    fl = float(w.cfg.n_hyp) * float(n_corr.sum()) * flop_pair
+    roof["ransac_score"] = {"kernel": "score_kernel", "bound": "fp32-fma", "achieved": fl / (t * 1e-3) / 1e12, "peak": ffma_peak,
+                            "unit": "TFLOP/s", "frac": fl / (t * 1e-3) / 1e12 / ffma_peak, "ms": t,
+                            "peak_source": "FFMA microbenchmark run in this process",
+                            "hypothesis_point_pairs": float(w.cfg.n_hyp) * float(n_corr.sum()), "traffic": None}
+    t = k_ms("sos_stereo_lift_triangulate#0")
+    lt_bytes = 53.0 * float(buf["st_pair_count"].sum())
+    roof["lift_triangulate"] = {"kernel": "stereo_lift_triangulate_kernel", "bound": "hbm", "achieved": lt_bytes / (t * 1e-3) / 1e9,
+                                "peak": hbm_peak, "unit": "GB/s", "frac": lt_bytes / (t * 1e-3) / 1e9 / hbm_peak, "ms": t,
+                                "traffic": None}
+    dominant = max((k for k in roof if not math.isnan(roof[k]["ms"])), key=lambda k: roof[k]["ms"])
+
+    # ---- reduce over ranks -------------------------------------------------------------------------------------------
+    if world > 1:
+        tt = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = float(tt[0]), float(tt[1])
+        ll = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(ll, op=dist.ReduceOp.SUM)
+        launches = int(ll[0])
+    value = world * B * K / (ms_dev * 1e-3)
+    e2e = world * B * K / (ms_e2e * 1e-3)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu_base = cpu_baseline(args)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8 (remap, Hamming) / f32 (RANSAC scoring, f64 guard path) / f64 (lifting, 3-point Arun)",
+            "data": "synthetic",
+            "config": dict(workload_config(args, c, B, note=f"inputs resident in HBM; {n_sets} input sets of {in_bytes / 1e6:.0f} MB "
+                                                           f"rotated (each larger than the 126 MB L2: no L2 flush needed); "
+                                                           f"CUDA-graph replay of {per_step} launches per step"),
+                           input_bytes_per_step=in_bytes, parallelism=f"frame batches sharded over {world} GPU(s), no collective"),
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": in_bytes,
+                    "d2h_bytes_per_step": d2h_bytes,
+                    "note": "sos_frontend_submit_host/wait_host on pinned host buffers, 2 staging slots (copies overlap kernels)"},
+            "gpu_launches": launches,
+            "roofline": dict(roof[dominant], name=dominant),
+            "roofline_hbm": dict(roof["remap"], name="remap"),
+            "kernels": roof,
+            "kernel_ms_per_step": {k: round(v["ms"], 4) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1]["ms"])},
+            "hamming_matches_per_s": (st_pairs + tm_pairs) / ((k_ms("sos_hamming_top2#0:stereo") + k_ms("sos_hamming_top2#0:temporal")) * 1e-3),
+            "cpu_baseline": cpu_base,
+            "clocks": clocks,
+            "stats_last_step": {"stereo_correspondences": stats[:, 0].tolist(), "temporal_correspondences": stats[:, 1].tolist(),
+                                "ransac_inliers": stats[:, 2].tolist()},
+            "peaks": {"hbm_gbs": hbm_peak, "popc_tera_per_s": popc_peak, "ffma_tflops": ffma_peak},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def summarize_kernels(marks, steps):
+    """marks: (entry point, ms) per launch over `steps` eager steps -> average ms per step for each launch slot."""
+    per = len(marks) // steps
+    out = {}
+    for s in range(steps):
+        seen = {}
+        hamming_calls = 0
+        for name, ms in marks[s * per:(s + 1) * per]:
+            k = seen.get(name, 0)
+            seen[name] = k + 1
+            key = f"{name}#{k}"
+            if name == "sos_hamming_top2":
+                # two calls per step: stereo first, temporal second; each launches partial (#0) then merge (#1)
+                which = "stereo" if hamming_calls < 2 else "temporal"
+                key = f"{name}#{k % 2}:{which}"
+                hamming_calls += 1
+            elif name == "sos_match_select":
+                key = f"{name}#0:{'stereo' if k == 0 else 'temporal'}"
+            out.setdefault(key, []).append(ms)
+    return {k: {"ms": sum(v) / len(v), "n": len(v)} for k, v in out.items()}
+
+
+def cpu_baseline(args):
+    n_pairs = 3 if args.workload == "c2" else 6
+    cpu = CpuPath(args.workload, seed=0, n_frames=n_pairs + 2, score_mode=args.score)
+    cpu.prime()
+    cpu.pair()  # warm-up (OpenCV thread pool, NumPy caches)
+    t0 = time.perf_counter()
+    for _ in range(n_pairs):
+        cpu.pair()
+    dt = time.perf_counter() - t0
+    return {"value": n_pairs / dt, "unit": UNIT, "cores": cpu.threads, "kind": "port", "seconds": dt,
+            "sample": f"{n_pairs} frame pairs of {args.workload} through oracle.pipeline: OpenCV calls as the reference makes "
+                      f"them (cv2.getNumThreads()={cpu.threads}, os.cpu_count()={os.cpu_count()}) + NumPy float64 lifting / "
+                      f"triangulation; RANSAC = NumPy float64 restatement over the same {cpu.c['n_hyp']} hypotheses (OpenGV absent)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "tiny"])
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--score", default="bearing", choices=["bearing", "euclid"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    if args.steps is None:
+        args.steps = 20 if args.impl == "ours" else 5
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        os.execv(sys.executable, cmd)
+    run_gpu(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

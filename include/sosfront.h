@@ -59,6 +59,11 @@ int sos_ctx_sync(sos_ctx* ctx);
 int sos_ctx_reserve(sos_ctx* ctx, size_t bytes);
 /* Number of kernel launches issued through this context since creation (for bench.py's gpu_launches). */
 int64_t sos_ctx_launch_count(sos_ctx* ctx);
+/* Per-launch device timing for bench.py's roofline numbers: between begin and end every kernel launched through the
+ * context is followed by a CUDA event on the context's stream.  end() synchronises and returns, for launch k, the
+ * elapsed time since the previous launch's event in ms[k] and the launching entry point's name (one per line) in names. */
+int sos_ctx_profile_begin(sos_ctx* ctx);
+int sos_ctx_profile_end(sos_ctx* ctx, char* names, size_t names_cap, float* ms, int max_n, int* n_out);
 
 int sos_malloc(sos_ctx* ctx, size_t bytes, void** dptr);
 int sos_free(sos_ctx* ctx, void* dptr);
@@ -334,6 +339,9 @@ int sos_frontend_destroy(sos_frontend* fe);
 int sos_frontend_reset(sos_frontend* fe);                /* forget the carried reference frame */
 int sos_frontend_set_graph(sos_frontend* fe, int enabled); /* CUDA-graph replay (default) or eager launches */
 int sos_frontend_get_buffers(sos_frontend* fe, sos_frontend_buffers* out);
+/* Same as sos_ctx_profile_begin/_end for the front-end's own launches (steps run eagerly while profiling). */
+int sos_frontend_profile_begin(sos_frontend* fe);
+int sos_frontend_profile_end(sos_frontend* fe, char* names, size_t names_cap, float* ms, int max_n, int* n_out);
 
 /* One step on DEVICE-resident inputs (asynchronous):
  *   omni [batch, src_h, src_w, channels] uint8

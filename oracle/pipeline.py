@@ -1,0 +1,82 @@
+"""CPU restatement of one SOS front-end frame / frame pair, chaining the oracle stages the way the reference's
+StereoPanoramicFrame.establish_stereo_correspondences (pose_est_tools.py:320-402) and TrackerStereoSE3.track_frame
+(pose_est_tools.py:736-847) chain them.  TEST INFRASTRUCTURE ONLY: used as the checker in tests and as the timed CPU
+baseline of bench.py (`cpu_baseline`, `--impl reference`).  It makes the same OpenCV calls the reference makes
+(cv2.bitwise_and, cv2.remap, cv2.BFMatcher.match + sorted) and NumPy float64 everywhere else; RANSAC is the float64
+restatement of oracle/ransac.py because OpenGV is not available (parity unpinned, see oracle/__init__.py)."""
+from __future__ import annotations
+
+import cv2
+import numpy as np
+
+from . import geometry, hamming, ransac
+
+
+def remap_views(omni, maps, masks):
+    """set_current_omni_image(apply_mask=True, mask_RGB=(0,0,0)): per view bitwise_and with the mirror mask
+    (camera_models.py:2990-2995) then Panorama.get_panoramic_image: float64 -> float32 cast of both maps every frame and
+    cv2.remap (panorama.py:291-298)."""
+    out = []
+    for which in ("top", "bot"):
+        masked = cv2.bitwise_and(omni, omni, mask=masks[which])
+        mx, my = maps[which]
+        out.append(cv2.remap(masked, mx.astype("float32"), my.astype("float32"), cv2.INTER_LINEAR, None,
+                             cv2.BORDER_CONSTANT, (0, 0, 0)))
+    return out
+
+
+def _bf_sorted(q, t):
+    """FeatureMatcher.match, k_best = 1 (camera_models.py:404-446): BFMatcher.match then Python sorted by distance."""
+    m = cv2.BFMatcher(normType=cv2.NORM_HAMMING).match(queryDescriptors=q, trainDescriptors=t)
+    m = sorted(m, key=lambda x: x.distance)
+    return (np.fromiter((x.queryIdx for x in m), np.int64, len(m)), np.fromiter((x.trainIdx for x in m), np.int64, len(m)))
+
+
+def stereo_frame(pano_g, f_top, f_bot, px_top, desc_top, boff_top, px_bot, desc_bot, boff_bot, max_du=2.5, min_dv=1.0,
+                 min_range=0.5, max_range=7.0, cap=None):
+    """match_features_panoramic_top_bottom (camera_models.py:3027-3101) per bucket, then lifting, midpoint triangulation
+    and the (homogeneous-norm) range gate of establish_stereo_correspondences (pose_est_tools.py:344-397)."""
+    rq, rt = [], []
+    for k in range(len(boff_top) - 1):
+        q0, q1, t0, t1 = boff_bot[k], boff_bot[k + 1], boff_top[k], boff_top[k + 1]
+        if q1 <= q0 or t1 <= t0:
+            continue
+        qi, ti = _bf_sorted(desc_bot[q0:q1], desc_top[t0:t1])
+        rq.append(q0 + qi)
+        rt.append(t0 + ti)
+    rq = np.concatenate(rq) if rq else np.zeros(0, np.int64)
+    rt = np.concatenate(rt) if rt else np.zeros(0, np.int64)
+    ok = hamming.filter_pixel_correspondences(px_top[rt], px_bot[rq], min_dv, max_du)
+    rq, rt = rq[ok], rt[ok]
+    az1, el1 = geometry.pano_pixel_to_angles(pano_g, px_top[rt])
+    az2, el2 = geometry.pano_pixel_to_angles(pano_g, px_bot[rq])
+    b_top = geometry.angles_to_sphere(az1, el1)
+    b_bot = geometry.angles_to_sphere(az2, el2)
+    xyz = geometry.triangulate_midpoint(az1, el1, az2, el2, f_top, f_bot)
+    keep = geometry.range_filter(np.hstack([xyz, np.ones((len(xyz), 1))]), min_range, max_range)
+    if cap is not None:
+        keep &= np.cumsum(keep) <= cap
+    return dict(uv_top=px_top[rt][keep], uv_bot=px_bot[rq][keep], b_top=b_top[keep], b_bot=b_bot[keep], xyz=xyz[keep],
+                desc_top=desc_top[rt][keep], desc_bot=desc_bot[rq][keep])
+
+
+def track_pair(ref, cur, hyp, mode, threshold, rig, max_du, hyp_limit=None):
+    """match_features_frame_to_frame for both views (pose_est_tools.py:741-749), stacking (:752-778), RANSAC + refit."""
+    parts = []
+    for view, (uvk, dk, bk) in enumerate((("uv_top", "desc_top", "b_top"), ("uv_bot", "desc_bot", "b_bot"))):
+        if len(cur[dk]) == 0 or len(ref[dk]) == 0:
+            continue
+        qi, ti = _bf_sorted(cur[dk], ref[dk])
+        ok = hamming.filter_pixel_correspondences(ref[uvk][ti], cur[uvk][qi], -1, max_du)
+        qi, ti = qi[ok], ti[ok]
+        parts.append((ref["xyz"][ti], cur["xyz"][qi], cur[bk][qi], np.full(len(qi), view, np.uint8)))
+    if not parts:
+        return None
+    p_ref, p_cur, f_cur, cam = (np.concatenate(x) for x in zip(*parts))
+    f32 = lambda a: a.astype(np.float32)
+    h = hyp if hyp_limit is None else hyp[:hyp_limit]
+    o = ransac.ransac_p3d(f32(p_ref), f32(p_cur), h, mode, threshold, f_cur=f32(f_cur), cam=cam, rig=rig)
+    if o["best_hyp"] >= 0:
+        o["refit"] = ransac.refit(p_ref, p_cur, o["mask"])
+    o["n_corr"] = len(p_ref)
+    return o

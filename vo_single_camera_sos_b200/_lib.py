@@ -50,6 +50,10 @@ PROTOTYPES = {
     "sos_ransac_p3d": (I, [c_ctx, P, P, P, P, P, I, I, P, I, P, I, I, I, D, P, P, P, P, P, P]),
     "sos_ransac_p3d_eval": (I, [c_ctx, P, P, P, P, P, I, I, P, I, P, I, D, P, P, P]),
     "sos_refit_inliers": (I, [c_ctx, P, P, P, P, I, I, P, P]),
+    "sos_ctx_profile_begin": (I, [c_ctx]),
+    "sos_ctx_profile_end": (I, [c_ctx, C.c_char_p, C.c_size_t, P, I, C.POINTER(I)]),
+    "sos_frontend_profile_begin": (I, [C.c_void_p]),
+    "sos_frontend_profile_end": (I, [C.c_void_p, C.c_char_p, C.c_size_t, P, I, C.POINTER(I)]),
     "sos_frontend_create": (I, [c_ctx, P, P, P, C.POINTER(C.c_void_p)]),
     "sos_frontend_destroy": (I, [C.c_void_p]),
     "sos_frontend_reset": (I, [C.c_void_p]),

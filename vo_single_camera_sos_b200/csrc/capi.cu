@@ -37,7 +37,46 @@ int sos_arena_get(sos_ctx* ctx, size_t bytes, void** out) {
   return SOS_OK;
 }
 
+void sos_prof_mark_launch(sos_ctx* ctx, const char* name) {
+  sos_prof_mark m;
+  m.name = name;
+  if (cudaEventCreate(&m.ev) != cudaSuccess) return;
+  cudaEventRecord(m.ev, ctx->stream);
+  ctx->marks.push_back(m);
+}
+
 extern "C" {
+
+int sos_ctx_profile_begin(sos_ctx* ctx) {
+  SOS_CHECK_ARG(ctx, "ctx is NULL");
+  for (auto& m : ctx->marks) cudaEventDestroy(m.ev);
+  ctx->marks.clear();
+  ctx->prof = true;
+  sos_prof_mark_launch(ctx, "begin");
+  return SOS_OK;
+}
+
+int sos_ctx_profile_end(sos_ctx* ctx, char* names, size_t names_cap, float* ms, int max_n, int* n_out) {
+  SOS_CHECK_ARG(ctx && n_out, "NULL argument");
+  ctx->prof = false;
+  SOS_CUDA(cudaStreamSynchronize(ctx->stream));
+  int n = 0;
+  size_t used = 0;
+  if (names && names_cap) names[0] = 0;
+  for (size_t i = 1; i < ctx->marks.size() && n < max_n; ++i, ++n) {
+    float t = 0.f;
+    SOS_CUDA(cudaEventElapsedTime(&t, ctx->marks[i - 1].ev, ctx->marks[i].ev));
+    if (ms) ms[n] = t;
+    if (names) {
+      const int w = snprintf(names + used, used < names_cap ? names_cap - used : 0, "%s\n", ctx->marks[i].name);
+      if (w > 0 && used + (size_t)w < names_cap) used += (size_t)w;
+    }
+  }
+  for (auto& m : ctx->marks) cudaEventDestroy(m.ev);
+  ctx->marks.clear();
+  *n_out = n;
+  return SOS_OK;
+}
 
 int sos_abi_version(void) { return SOS_ABI_VERSION; }
 const char* sos_last_error(void) { return g_err; }

@@ -245,13 +245,14 @@ int enqueue_step(sos_frontend* fe, const uint8_t* omni, const float* px_top, con
     SOS_CUDA(cudaMemcpyAsync(base, base + last * 8, (size_t)cap * 32, cudaMemcpyDeviceToDevice, ctx->stream));
   }
   SOS_CUDA(cudaMemcpyAsync(d.n, d.n + B, sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (ctx->prof) sos_prof_mark_launch(ctx, "carry_over_copies");  // keeps the copies out of the next kernel's interval
   return SOS_OK;
 }
 
 int run_step(sos_frontend* fe, const uint8_t* omni, const float* px_top, const uint32_t* desc_top, const int32_t* boff_top,
              const float* px_bot, const uint32_t* desc_bot, const int32_t* boff_bot) {
   sos_ctx* ctx = fe->ctx;
-  if (!fe->use_graph) return enqueue_step(fe, omni, px_top, desc_top, boff_top, px_bot, desc_bot, boff_bot);
+  if (!fe->use_graph || ctx->prof) return enqueue_step(fe, omni, px_top, desc_top, boff_top, px_bot, desc_bot, boff_bot);
   sos_frontend::GraphKey key = {{omni, px_top, desc_top, boff_top, px_bot, desc_bot, boff_bot}};
   for (auto& g : fe->graphs) {
     if (memcmp(&g.key, &key, sizeof(key)) == 0) {
@@ -391,6 +392,16 @@ extern "C" int sos_frontend_set_graph(sos_frontend* fe, int enabled) {
   SOS_CHECK_ARG(fe, "fe is NULL");
   fe->use_graph = enabled != 0;
   return SOS_OK;
+}
+
+extern "C" int sos_frontend_profile_begin(sos_frontend* fe) {
+  SOS_CHECK_ARG(fe, "fe is NULL");
+  return sos_ctx_profile_begin(fe->ctx);  // run_step launches eagerly while profiling: events cannot be captured
+}
+
+extern "C" int sos_frontend_profile_end(sos_frontend* fe, char* names, size_t names_cap, float* ms, int max_n, int* n_out) {
+  SOS_CHECK_ARG(fe, "fe is NULL");
+  return sos_ctx_profile_end(fe->ctx, names, names_cap, ms, max_n, n_out);
 }
 
 extern "C" int sos_frontend_get_buffers(sos_frontend* fe, sos_frontend_buffers* out) {

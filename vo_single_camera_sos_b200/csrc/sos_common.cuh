@@ -4,8 +4,14 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 #include "sosfront.h"
+
+struct sos_prof_mark {
+  const char* name;  // __func__ of the C-ABI entry point that launched the kernel (static storage)
+  cudaEvent_t ev;    // recorded right after the launch
+};
 
 struct sos_ctx {
   int device = 0;
@@ -15,9 +21,12 @@ struct sos_ctx {
   size_t arena_bytes = 0;
   int64_t launches = 0;
   int sm_count = 148;
+  bool prof = false;      // per-launch CUDA-event timing (sos_ctx_profile_begin / _end)
+  std::vector<sos_prof_mark> marks;
 };
 
 void sos_set_error(const char* fmt, ...);
+void sos_prof_mark_launch(sos_ctx* ctx, const char* name);
 
 #define SOS_CHECK_ARG(cond, msg)                                  \
   do {                                                            \
@@ -40,6 +49,7 @@ void sos_set_error(const char* fmt, ...);
 #define SOS_LAUNCHED(ctx)                                                                  \
   do {                                                                                     \
     (ctx)->launches++;                                                                     \
+    if ((ctx)->prof) sos_prof_mark_launch((ctx), __func__);                                \
     cudaError_t e__ = cudaPeekAtLastError();                                               \
     if (e__ != cudaSuccess) {                                                              \
       (void)cudaGetLastError();                                                            \

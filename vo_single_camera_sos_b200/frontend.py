@@ -153,6 +153,19 @@ class Frontend:
     def set_graph(self, enabled: bool):
         check(self.ctx.lib.sos_frontend_set_graph(self._h, int(enabled)))
 
+    def profile_begin(self):
+        """Per-launch CUDA-event timing of the following steps (they run eagerly, not from the graph)."""
+        check(self.ctx.lib.sos_frontend_profile_begin(self._h))
+
+    def profile_end(self, max_n: int = 4096):
+        """-> list of (entry point name, milliseconds) in launch order."""
+        names = C.create_string_buffer(64 * max_n)
+        ms = (C.c_float * max_n)()
+        n = C.c_int()
+        check(self.ctx.lib.sos_frontend_profile_end(self._h, names, len(names), ms, max_n, C.byref(n)))
+        nm = names.value.decode().split("\n")[: n.value]
+        return [(nm[i], float(ms[i])) for i in range(n.value)]
+
     def _check_inputs(self, omni, px_top, desc_top, boff_top, px_bot, desc_bot, boff_bot, on_device: bool):
         c = self.cfg
         shapes = {

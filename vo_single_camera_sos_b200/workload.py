@@ -68,8 +68,9 @@ def build(ctx: ops.Context, name: str, batch: int, n_frames: int, seed: int = 0,
     return Workload(name, rig, scene, cfg, lut, hyp, hyp_host, masks, maps, traj)
 
 
-def make_frames(w: Workload, first: int, count: int, render: bool = True, lift=None):
-    """Host input arrays for frames [first, first+count): dict of omni [n,H,W,3], px/desc/boff per view, landmark ids."""
+def make_frames(w: Workload, first: int, count: int, render: bool = True, lift=None, renderer: "DeviceRenderer" = None):
+    """Host input arrays for frames [first, first+count): dict of omni [n,H,W,3], px/desc/boff per view, landmark ids.
+    With `renderer` the omni images are rendered on the device (same scene, same geometry, much faster)."""
     c = CONFIGS[w.name]
     cfg = w.cfg
     n = count
@@ -88,7 +89,9 @@ def make_frames(w: Workload, first: int, count: int, render: bool = True, lift=N
             out[f"desc_{which}"][i] = f[which]["desc"]
             out[f"boff_{which}"][i] = f[which]["bucket_off"]
             out[f"lid_{which}"][i] = f[which]["landmark"]
-        if render:
+        if renderer is not None:
+            out["omni"][i] = renderer.render(T).cpu().numpy()
+        elif render:
             out["omni"][i] = synth.render_omni(w.rig, w.scene, T, lift=lift)
     return out
 
@@ -99,6 +102,44 @@ def device_lift(ctx: ops.Context, w: Workload):
         sphere, _, _ = ctx.lift_gum(w.rig.gum_vector(which), torch.from_numpy(np.ascontiguousarray(uv)).to(ctx.device))
         return sphere.cpu().numpy()
     return lift
+
+
+class DeviceRenderer:
+    """synth.render_omni on the device: the per-pixel viewing rays come from sos_lift_gum once per view, the ray/box
+    intersection and the texture lookup are plain torch ops (input generation only, not part of the hot path)."""
+
+    def __init__(self, ctx: ops.Context, w: Workload):
+        self.ctx, self.w = ctx, w
+        rig = w.rig
+        self.tex = torch.from_numpy(w.scene.texture).to(ctx.device)
+        self.half = torch.from_numpy(w.scene.half_extent).to(ctx.device)
+        self.views = []
+        for which in ("top", "bot"):
+            m = torch.from_numpy(rig.mask(which) != 0).to(ctx.device)
+            idx = m.nonzero()  # (y, x)
+            uv = torch.stack([idx[:, 1], idx[:, 0]], 1).to(torch.float64).contiguous()
+            rays, _, _ = ctx.lift_gum(rig.gum_vector(which), uv)
+            f = torch.from_numpy(rig.f_top if which == "top" else rig.f_bot).to(ctx.device)
+            self.views.append((idx, rays, f))
+
+    def render(self, T_c_wrt_w: np.ndarray) -> torch.Tensor:
+        rig = self.w.rig
+        img = torch.zeros((rig.height, rig.width, 3), dtype=torch.uint8, device=self.ctx.device)
+        R = torch.from_numpy(T_c_wrt_w[:3, :3].copy()).to(self.ctx.device)
+        t = torch.from_numpy(T_c_wrt_w[:3, 3].copy()).to(self.ctx.device)
+        for idx, rays, f in self.views:
+            o = R @ f + t
+            d = rays @ R.T
+            tt = torch.where(d > 0, (self.half - o) / d, (-self.half - o) / d)
+            tmin, k = tt.min(dim=1)
+            hit = o + d * tmin[:, None]
+            ar = torch.arange(len(d), device=d.device)
+            face = 2 * k + (d[ar, k] > 0).long()
+            T = self.tex.shape[1]
+            iu = torch.remainder(torch.floor(hit[ar, (k + 1) % 3] / 0.12).long(), T)
+            iv = torch.remainder(torch.floor(hit[ar, (k + 2) % 3] / 0.12).long(), T)
+            img[idx[:, 0], idx[:, 1]] = self.tex[face, iu, iv]
+        return img
 
 
 INPUT_KEYS = ("omni", "px_top", "desc_top", "boff_top", "px_bot", "desc_bot", "boff_bot")
