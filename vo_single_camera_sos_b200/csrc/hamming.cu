@@ -12,6 +12,8 @@
 //     (distance << 22 | train index) — min/max on the key gives OpenCV's (distance, lowest index) order;
 //   * the train range of a segment is split over blockIdx.y so that small problems still fill 148 SMs;
 //     the per-split partial keys are merged by a second, tiny kernel.
+#include <stdlib.h>
+
 #include "sos_common.cuh"
 
 namespace {
@@ -23,25 +25,105 @@ constexpr int HB_TILE_T = 256;   // train descriptors per shared-memory tile (8 
 constexpr int KEY_IDX_BITS = 22; // up to 4M train rows per segment; distance <= 256 needs 9 bits
 constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
 
-__device__ __forceinline__ uint32_t hamming256(const uint4& qa, const uint4& qb, const uint4& ta, const uint4& tb) {
-  uint32_t s0 = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z);
-  uint32_t s1 = __popc(qa.w ^ ta.w) + __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y);
-  uint32_t s2 = __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w) + s0;
-  return s1 + s2;
+// carry-save adder on 32 bit lanes: a + b + c = sum + 2 * carry (one LOP3 each)
+__device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& sum, uint32_t& carry) {
+  sum = a ^ b ^ c;
+  carry = (a & b) | (a & c) | (b & c);
 }
 
+// Packed key (distance << KEY_IDX_BITS) + tj of one descriptor pair.
+//   VARIANT 0: 8 POPC + adds                      (POPC = XU pipe, 16 lanes/clk/SM: the narrow pipe)
+//   VARIANT 1: three carry-save adders first, 5 POPC: moves work from the XU pipe to the 4x wider ALU pipe; the
+//              weighted sum and the key are formed by IMADs on the FMA pipe
+//   VARIANT 2: full Harley-Seal tree, 4 POPC
+template <int VARIANT>
+__device__ __forceinline__ uint32_t hamming_key(const uint4& qa, const uint4& qb, const uint4& ta, const uint4& tb,
+                                                uint32_t tj) {
+  const uint32_t x0 = qa.x ^ ta.x, x1 = qa.y ^ ta.y, x2 = qa.z ^ ta.z, x3 = qa.w ^ ta.w;
+  const uint32_t x4 = qb.x ^ tb.x, x5 = qb.y ^ tb.y, x6 = qb.z ^ tb.z, x7 = qb.w ^ tb.w;
+  if (VARIANT == 0) {
+    const uint32_t s0 = __popc(x0) + __popc(x1) + __popc(x2);
+    const uint32_t s1 = __popc(x3) + __popc(x4) + __popc(x5);
+    const uint32_t s2 = __popc(x6) + __popc(x7) + s0;
+    return ((s1 + s2) << KEY_IDX_BITS) | tj;
+  } else if (VARIANT == 1) {
+    uint32_t s1, c1, s2, c2, s3, c3;
+    csa(x0, x1, x2, s1, c1);
+    csa(x3, x4, x5, s2, c2);
+    csa(s1, s2, x6, s3, c3);
+    const uint32_t ones = __popc(s3) + __popc(x7);
+    const uint32_t twos = __popc(c1) + __popc(c2) + __popc(c3);
+    return twos * (2u << KEY_IDX_BITS) + (ones * (1u << KEY_IDX_BITS) + tj);
+  } else {
+    uint32_t s1, c1, s2, c2, s3, c3, s5, c5;
+    csa(x0, x1, x2, s1, c1);
+    csa(x3, x4, x5, s2, c2);
+    csa(s1, s2, x6, s3, c3);
+    const uint32_t ones = s3 ^ x7, c4 = s3 & x7;
+    csa(c1, c2, c3, s5, c5);
+    const uint32_t twos = s5 ^ c4, c6 = s5 & c4;
+    const uint32_t fours = c5 ^ c6, eights = c5 & c6;
+    uint32_t key = __popc(ones) * (1u << KEY_IDX_BITS) + tj;
+    key = __popc(twos) * (2u << KEY_IDX_BITS) + key;
+    key = __popc(fours) * (4u << KEY_IDX_BITS) + key;
+    return __popc(eights) * (8u << KEY_IDX_BITS) + key;
+  }
+}
+
+// Work list: segment lengths live on the device, so the host can only size the grid for the worst case.  Launching
+// that grid directly leaves the SMs unevenly loaded (blocks of short segments exit at once and everything fits in
+// one wave: measured 66 % average SM activity).  Instead one small block compacts the ACTIVE (segment, query tile,
+// train split) items into a list; block i of the main kernel takes item i, so the active blocks are contiguous in
+// launch order and the hardware scheduler balances them.
+constexpr int ITEM_SPLIT_BITS = 6, ITEM_TILE_BITS = 10;  // item = seg << 16 | tile << 6 | split
+
+__global__ void __launch_bounds__(256)
+hamming_plan_kernel(const int32_t* __restrict__ q_len, int n_seg, int max_nq, int splits, uint32_t* __restrict__ items,
+                    int32_t* __restrict__ n_items) {
+  __shared__ int warp_tot[8];
+  __shared__ int carry_sh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_sh = 0;
+  __syncthreads();
+  for (int base = 0; base < n_seg; base += 256) {
+    const int seg = base + tid;
+    const int tiles = seg < n_seg ? (min(q_len[seg], max_nq) + HB_TILE_Q - 1) / HB_TILE_Q : 0;
+    const int cnt = tiles * splits;
+    int incl = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+      if (lane >= off) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int before = carry_sh;
+    for (int w = 0; w < warp; ++w) before += warp_tot[w];
+    const int first = before + incl - cnt;
+    for (int k = 0; k < cnt; ++k)
+      items[first + k] = ((uint32_t)seg << 16) | ((uint32_t)(k / splits) << ITEM_SPLIT_BITS) | (uint32_t)(k % splits);
+    __syncthreads();
+    if (tid == 255) carry_sh = before + incl;
+    __syncthreads();
+  }
+  if (tid == 0) *n_items = carry_sh;
+}
+
+template <int VARIANT, bool TOP2>
 __global__ void __launch_bounds__(HB_THREADS)
 hamming_partial_kernel(const uint4* __restrict__ q, const uint4* __restrict__ t, const int32_t* __restrict__ q_start,
                        const int32_t* __restrict__ q_len, const int32_t* __restrict__ t_start,
-                       const int32_t* __restrict__ t_len, int max_nq, int splits, uint2* __restrict__ partial) {
+                       const int32_t* __restrict__ t_len, int max_nq, int splits, const uint32_t* __restrict__ items,
+                       const int32_t* __restrict__ n_items, uint2* __restrict__ partial) {
   __shared__ uint4 tile[HB_TILE_T * 2];
 
-  const int seg = blockIdx.z;
+  if ((int)blockIdx.x >= *n_items) return;
+  const uint32_t item = items[blockIdx.x];
+  const int seg = (int)(item >> 16);
   const int q0 = q_start[seg], nq = min(q_len[seg], max_nq);
-  const int q_tile = blockIdx.x * HB_TILE_Q;
-  if (q_tile >= nq) return;
+  const int q_tile = (int)((item >> ITEM_SPLIT_BITS) & ((1u << ITEM_TILE_BITS) - 1u)) * HB_TILE_Q;
   const int t0 = t_start[seg], nt = t_len[seg];
-  const int split = blockIdx.y;
+  const int split = (int)(item & ((1u << ITEM_SPLIT_BITS) - 1u));
   const int chunk = (nt + splits - 1) / splits;
   const int t_begin = min(nt, split * chunk);
   const int t_end = min(nt, t_begin + chunk);
@@ -74,8 +156,8 @@ hamming_partial_kernel(const uint4* __restrict__ q, const uint4* __restrict__ t,
         const uint32_t tj = (uint32_t)(tb + j + u);
 #pragma unroll
         for (int r = 0; r < HB_QPT; ++r) {
-          const uint32_t key = (hamming256(qa[r], qb[r], ta, tbv) << KEY_IDX_BITS) | tj;
-          k1[r] = min(k1[r], max(k0[r], key));
+          const uint32_t key = hamming_key<VARIANT>(qa[r], qb[r], ta, tbv, tj);
+          if (TOP2) k1[r] = min(k1[r], max(k0[r], key));
           k0[r] = min(k0[r], key);
         }
       }
@@ -85,8 +167,8 @@ hamming_partial_kernel(const uint4* __restrict__ q, const uint4* __restrict__ t,
       const uint32_t tj = (uint32_t)(tb + j);
 #pragma unroll
       for (int r = 0; r < HB_QPT; ++r) {
-        const uint32_t key = (hamming256(qa[r], qb[r], ta, tbv) << KEY_IDX_BITS) | tj;
-        k1[r] = min(k1[r], max(k0[r], key));
+        const uint32_t key = hamming_key<VARIANT>(qa[r], qb[r], ta, tbv, tj);
+        if (TOP2) k1[r] = min(k1[r], max(k0[r], key));
         k0[r] = min(k0[r], key);
       }
     }
@@ -252,20 +334,43 @@ extern "C" int sos_hamming_top2(sos_ctx* ctx, const uint32_t* q, const uint32_t*
 
   const int q_tiles = sos_div_up(max_nq, HB_TILE_Q);
   const int t_tiles = sos_div_up(max_nt > 0 ? max_nt : 1, HB_TILE_T);
-  // enough blocks for ~4 per SM, but never split finer than one shared-memory tile
-  int splits = sos_div_up(4 * ctx->sm_count, q_tiles * n_seg);
+  SOS_CHECK_ARG(q_tiles <= (1 << ITEM_TILE_BITS), "segment has too many query rows (limit 262144)");
+  // split the train range so that a work item is ~256 x 1024 descriptor pairs and small problems still give every SM
+  // several items; never finer than one shared-memory tile
+  int splits = sos_div_up(max_nt > 0 ? max_nt : 1, 1024);
+  const int fill = sos_div_up(4 * ctx->sm_count, q_tiles * n_seg);
+  if (splits < fill) splits = fill;
   if (splits > t_tiles) splits = t_tiles;
-  if (splits > 64) splits = 64;
+  if (splits > (1 << ITEM_SPLIT_BITS)) splits = 1 << ITEM_SPLIT_BITS;
   if (splits < 1) splits = 1;
 
   void* ws = nullptr;
   const size_t rows_bound = (size_t)max_nq * (size_t)n_seg;
-  int rc = sos_arena_get(ctx, rows_bound * splits * sizeof(uint2), &ws);
+  const size_t max_items = (size_t)q_tiles * splits * n_seg;
+  SOS_CHECK_ARG(max_items < ((size_t)1 << 31), "too many work items");
+  const size_t partial_bytes = sos_align_up(rows_bound * splits * sizeof(uint2), 256);
+  const size_t items_bytes = sos_align_up(max_items * sizeof(uint32_t), 256);
+  int rc = sos_arena_get(ctx, partial_bytes + items_bytes + 256, &ws);
   if (rc != SOS_OK) return rc;
+  uint32_t* items = (uint32_t*)((char*)ws + partial_bytes);
+  int32_t* n_items = (int32_t*)((char*)ws + partial_bytes + items_bytes);
 
-  dim3 grid(q_tiles, splits, n_seg);
-  hamming_partial_kernel<<<grid, HB_THREADS, 0, ctx->stream>>>((const uint4*)q, (const uint4*)t, q_start, q_len, t_start,
-                                                               t_len, max_nq, splits, (uint2*)ws);
+  hamming_plan_kernel<<<1, 256, 0, ctx->stream>>>(q_len, n_seg, max_nq, splits, items, n_items);
+  SOS_LAUNCHED(ctx);
+  const unsigned grid = (unsigned)max_items;
+  static const int variant = [] {
+    const char* e = getenv("SOS_HAMMING_VARIANT");  // A/B switch for profiling; default = the fastest measured
+    return e ? atoi(e) : 1;
+  }();
+  const bool top2 = idx1 != nullptr || d1 != nullptr;
+#define HB_LAUNCH(V, T2)                                                                                              \
+  hamming_partial_kernel<V, T2><<<grid, HB_THREADS, 0, ctx->stream>>>((const uint4*)q, (const uint4*)t, q_start, q_len, \
+                                                                      t_start, t_len, max_nq, splits, items, n_items,   \
+                                                                      (uint2*)ws)
+  if (variant == 0) { if (top2) HB_LAUNCH(0, true); else HB_LAUNCH(0, false); }
+  else if (variant == 2) { if (top2) HB_LAUNCH(2, true); else HB_LAUNCH(2, false); }
+  else { if (top2) HB_LAUNCH(1, true); else HB_LAUNCH(1, false); }
+#undef HB_LAUNCH
   SOS_LAUNCHED(ctx);
   dim3 mgrid(sos_div_up(max_nq, 256), n_seg);
   hamming_merge_kernel<<<mgrid, 256, 0, ctx->stream>>>((const uint2*)ws, q_start, q_len, max_nq, splits, idx0, d0, idx1, d1);

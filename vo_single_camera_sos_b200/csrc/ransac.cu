@@ -298,8 +298,8 @@ __device__ __forceinline__ bool classify(const float* __restrict__ A, const floa
   } else {
     const float s = __fmaf_rn(q.z, z, __fmaf_rn(q.y, y, __fmul_rn(q.x, x)));
     const float n2 = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
-    const float D = __fmaf_rn(s, s, -__fmul_rn(k.cos_min_sq, n2));
-    in = (s > 0.f) && (D > 0.f);
+    const float D = __fmaf_rn(s, fabsf(s), -__fmul_rn(k.cos_min_sq, n2));  // s|s| folds the s > 0 test into D
+    in = D > 0.f;
     return fabsf(D) < __fmaf_rn(k.guard_rel, n2, guard_j);
   }
 }
@@ -317,65 +317,103 @@ __device__ __forceinline__ float guard_of(int mode, float px, float py, float pz
 constexpr int RS_THREADS = 128;
 constexpr int RS_HPT = 4;                       // hypotheses per thread
 constexpr int RS_TILE_H = RS_THREADS * RS_HPT;  // hypotheses per block
-constexpr int RS_CHUNK = 1024;                  // correspondences per block (2 x float4 each = 32 KB)
+constexpr int RS_CHUNK = 512;                   // correspondences per block (2 x float4 each = 16 KB)
+constexpr int RS_QCAP = 2048;                   // deferred exact evaluations per block (expected: a few dozen)
 
-template <int MODE, int NCAMS>
+// A thread owns RS_HPT hypotheses (12 registers each) and walks the block's chunk of correspondences in shared
+// memory; every lane reads the SAME correspondence (broadcast LDS.128 x2).  The scoring transform depends on the
+// camera of the correspondence: the stacked list is camera-sorted (top view first, pose_est_tools.py:752-778), so the
+// transforms are reloaded at most once per chunk, at the block-uniform point where the camera index changes.
+// Pairs whose float32 decision is uncertain are queued and re-decided in float64 after the loop.
+template <int MODE>
 __global__ void __launch_bounds__(RS_THREADS)
 score_kernel(const float* __restrict__ p_ref, const float* __restrict__ q_arr, const uint8_t* __restrict__ cam,
-             const int32_t* __restrict__ n_arr, int cap, const HypRec* __restrict__ recs, int n_hyp, ScoreConst k, Rig rig,
-             int32_t* __restrict__ counts) {
+             const int32_t* __restrict__ n_arr, int cap, const HypRec* __restrict__ recs, int n_hyp, ScoreConst k,
+             const __grid_constant__ Rig rig, int32_t* __restrict__ counts) {
   __shared__ float4 sp[RS_CHUNK];  // p_ref.xyz, guard (sign bit = camera index)
   __shared__ float4 sq[RS_CHUNK];  // p_cur.xyz (EUCLID) or f_cur.xyz (BEARING)
+  __shared__ uint32_t queue[RS_QCAP];
+  __shared__ int queue_n;
   const int b = blockIdx.z;
   const int n = n_arr[b];
   const int j0 = blockIdx.y * RS_CHUNK;
   if (j0 >= n) return;
   const int nj = min(RS_CHUNK, n - j0);
+  const bool multi_cam = rig.n_cams > 1 && cam != nullptr;
+  if (threadIdx.x == 0) queue_n = 0;
   for (int j = threadIdx.x; j < nj; j += RS_THREADS) {
     const size_t o = ((size_t)b * cap + j0 + j) * 3;
-    const int c = (NCAMS > 1 && cam) ? (cam[(size_t)b * cap + j0 + j] ? 1 : 0) : 0;
+    const int c = multi_cam ? (cam[(size_t)b * cap + j0 + j] ? 1 : 0) : 0;
     const float px = p_ref[o], py = p_ref[o + 1], pz = p_ref[o + 2];
     const float qx = q_arr[o], qy = q_arr[o + 1], qz = q_arr[o + 2];
     const float g = guard_of(MODE, px, py, pz, qx, qy, qz, k.thr);
     sp[j] = make_float4(px, py, pz, c ? -g : g);
     sq[j] = make_float4(qx, qy, qz, 0.f);
   }
-  float A[RS_HPT][NCAMS][12];
+  float A[RS_HPT][12];
   int cnt[RS_HPT];
-  int hyp_of[RS_HPT];
+  const HypRec* rec[RS_HPT];
 #pragma unroll
   for (int r = 0; r < RS_HPT; ++r) {
     int h = blockIdx.x * RS_TILE_H + r * RS_THREADS + threadIdx.x;
     if (h >= n_hyp) h = n_hyp - 1;  // duplicate work, never stored
-    hyp_of[r] = h;
-    const HypRec* rec = recs + (size_t)b * n_hyp + h;
-#pragma unroll
-    for (int c = 0; c < NCAMS; ++c)
-#pragma unroll
-      for (int i = 0; i < 12; ++i) A[r][c][i] = rec->xf[c][i];
+    rec[r] = recs + (size_t)b * n_hyp + h;
     cnt[r] = 0;
   }
   __syncthreads();
+  int cur_cam = -1;
 #pragma unroll 2
   for (int j = 0; j < nj; ++j) {
     const float4 p = sp[j];
     const float4 q = sq[j];
+    const int c = (int)(__float_as_uint(p.w) >> 31);
+    if (c != cur_cam) {  // block-uniform
+      cur_cam = c;
+#pragma unroll
+      for (int r = 0; r < RS_HPT; ++r)
+#pragma unroll
+        for (int i = 0; i < 12; ++i) A[r][i] = __ldg(&rec[r]->xf[c][i]);
+    }
     const float g = fabsf(p.w);
-    const int c = (NCAMS > 1) ? (int)(__float_as_uint(p.w) >> 31) : 0;  // block-uniform: every lane sees the same point
 #pragma unroll
     for (int r = 0; r < RS_HPT; ++r) {
       bool in;
-      bool unsure;
-      if (NCAMS == 1 || c == 0) unsure = classify<MODE>(A[r][0], p, q, g, k, in);
-      else unsure = classify<MODE>(A[r][NCAMS - 1], p, q, g, k, in);
-      if (unsure) in = inlier_exact(MODE, recs[(size_t)b * n_hyp + hyp_of[r]].pose64, rig, c, p, q, k.thr);
+      if (classify<MODE>(A[r], p, q, g, k, in)) {
+        const int slot = atomicAdd(&queue_n, 1);
+        if (slot < RS_QCAP) queue[slot] = ((uint32_t)j << 16) | ((uint32_t)r << 8) | threadIdx.x;
+        in = false;  // counted by the deferred pass
+      }
       cnt[r] += in ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  int nq = queue_n;
+  if (nq > RS_QCAP) {  // block-uniform; queue overflow has never been observed: redo the whole chunk in float64
+    nq = 0;
+#pragma unroll 1
+    for (int r = 0; r < RS_HPT; ++r) {
+      cnt[r] = 0;
+#pragma unroll 1
+      for (int j = 0; j < nj; ++j) {
+        const float4 p = sp[j];
+        cnt[r] += inlier_exact(MODE, rec[r]->pose64, rig, (int)(__float_as_uint(p.w) >> 31), p, sq[j], k.thr) ? 1 : 0;
+      }
     }
   }
 #pragma unroll
   for (int r = 0; r < RS_HPT; ++r) {
     const int h = blockIdx.x * RS_TILE_H + r * RS_THREADS + threadIdx.x;
     if (h < n_hyp && cnt[r] != 0) atomicAdd(&counts[(size_t)b * n_hyp + h], cnt[r]);
+  }
+  for (int e = threadIdx.x; e < nq; e += RS_THREADS) {
+    const uint32_t v = queue[e];
+    const int j = (int)(v >> 16), r = (int)((v >> 8) & 0xFF), t = (int)(v & 0xFF);
+    const int h = blockIdx.x * RS_TILE_H + r * RS_THREADS + t;
+    if (h >= n_hyp) continue;
+    const float4 p = sp[j];
+    const int c = (int)(__float_as_uint(p.w) >> 31);
+    if (inlier_exact(MODE, recs[(size_t)b * n_hyp + h].pose64, rig, c, p, sq[j], k.thr))
+      atomicAdd(&counts[(size_t)b * n_hyp + h], 1);
   }
 }
 
@@ -424,7 +462,7 @@ argmax_kernel(const int32_t* __restrict__ counts, const HypRec* __restrict__ rec
 // which by construction agrees with every decision the scoring kernel took.
 __global__ void __launch_bounds__(256)
 mask_kernel(int mode, const float* __restrict__ p_ref, const float* __restrict__ q_arr, const uint8_t* __restrict__ cam,
-            const int32_t* __restrict__ n_arr, int cap, const HypRec* __restrict__ best_rec, Rig rig, double thr,
+            const int32_t* __restrict__ n_arr, int cap, const HypRec* __restrict__ best_rec, const __grid_constant__ Rig rig, double thr,
             uint8_t* __restrict__ mask, int32_t* __restrict__ count_out) {
   const int b = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -562,10 +600,7 @@ int ransac_scratch(sos_ctx* ctx, int n_problems, int n_hyp, RansacScratch& s) {
 template <int MODE>
 int launch_score(sos_ctx* ctx, const Rig& rig, dim3 grid, const float* p_ref, const float* q, const uint8_t* cam,
                  const int32_t* n, int cap, const HypRec* recs, int n_hyp, ScoreConst k, int32_t* counts) {
-  if (rig.n_cams <= 1 || cam == nullptr)
-    score_kernel<MODE, 1><<<grid, RS_THREADS, 0, ctx->stream>>>(p_ref, q, cam, n, cap, recs, n_hyp, k, rig, counts);
-  else
-    score_kernel<MODE, 2><<<grid, RS_THREADS, 0, ctx->stream>>>(p_ref, q, cam, n, cap, recs, n_hyp, k, rig, counts);
+  score_kernel<MODE><<<grid, RS_THREADS, 0, ctx->stream>>>(p_ref, q, cam, n, cap, recs, n_hyp, k, rig, counts);
   SOS_LAUNCHED(ctx);
   return SOS_OK;
 }

@@ -13,6 +13,8 @@
 // Layout: block = 8 warps = 8 panorama rows x 128 columns, a thread owns 4 consecutive pixels, so LUT reads
 // are 2 x LDG.128 per thread, stores are 4*ch contiguous bytes per thread, and neighbouring rows/columns of
 // the tile hit the same source cache lines in L1.
+#include <stdlib.h>
+
 #include "sos_common.cuh"
 
 namespace {
@@ -63,10 +65,34 @@ __device__ __forceinline__ void load_tap(const uint8_t* __restrict__ p, uint32_t
   for (int c = 0; c < CH; ++c) acc[c] += w * (uint32_t)__ldg(p + c);
 }
 
+// Six consecutive bytes (two horizontally adjacent BGR taps) starting at p, fetched as two aligned 64-bit words and
+// funnel-shifted: 2 load instructions instead of 6.  Requires p + 16 <= end of the allocation (checked by the caller).
+__device__ __forceinline__ uint64_t load6(const uint8_t* __restrict__ p) {
+  const uintptr_t a = (uintptr_t)p;
+  const uint64_t* w = (const uint64_t*)(a & ~(uintptr_t)7);
+  const uint64_t w0 = __ldg(w), w1 = __ldg(w + 1);
+  const uint32_t sh = (uint32_t)(a & 7) * 8u;
+  return (w0 >> sh) | ((w1 << 1) << (63u - sh));  // (w1 << (64 - sh)) without the undefined shift by 64
+}
+
+// Fast path for 3-channel pixels whose four taps are inside the image and unmasked.  Horizontal then vertical
+// interpolation with the 6-bit weights: sum_i w_i p_i = 32 * V, so (sum + 16384) >> 15 == (V + 512) >> 10 exactly.
+__device__ __forceinline__ void remap_pixel3_fast(const uint8_t* __restrict__ p, size_t row_bytes, uint32_t ax, uint32_t ay,
+                                                  uint32_t* out) {
+  const uint64_t r0 = load6(p), r1 = load6(p + row_bytes);
+  const uint32_t wl = 32u - ax, wt = 32u - ay;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const uint32_t h0 = wl * (uint32_t)((r0 >> (8 * c)) & 0xFF) + ax * (uint32_t)((r0 >> (8 * c + 24)) & 0xFF);
+    const uint32_t h1 = wl * (uint32_t)((r1 >> (8 * c)) & 0xFF) + ax * (uint32_t)((r1 >> (8 * c + 24)) & 0xFF);
+    out[c] = (wt * h0 + ay * h1 + 512u) >> 10;
+  }
+}
+
 // One output pixel: returns CH bytes in out[].
 template <int CH>
-__device__ __forceinline__ void remap_pixel(const uint8_t* __restrict__ src, int src_w, uint64_t e,
-                                            const uint32_t* border, const uint32_t* bg, uint32_t* out) {
+__device__ __forceinline__ void remap_pixel(const uint8_t* __restrict__ src, const uint8_t* __restrict__ wide_end, int src_w,
+                                            uint64_t e, const uint32_t* border, const uint32_t* bg, uint32_t* out) {
   const int x0 = (int)(int16_t)(e & 0xFFFF);
   const int y0 = (int)(int16_t)((e >> 16) & 0xFFFF);
   const uint32_t hi = (uint32_t)(e >> 32);
@@ -82,6 +108,10 @@ __device__ __forceinline__ void remap_pixel(const uint8_t* __restrict__ src, int
 #pragma unroll
   for (int c = 0; c < CH; ++c) acc[c] = 16384u;
   const uint8_t* p = src + ((size_t)y0 * src_w + x0) * CH;
+  if (CH == 3 && live == 15u && p + (size_t)src_w * 3 + 16 <= wide_end) {
+    remap_pixel3_fast(p, (size_t)src_w * 3, ax, ay, out);
+    return;
+  }
   if (live == 15u) {
     load_tap<CH>(p, w[0], acc);
     load_tap<CH>(p + CH, w[1], acc);
@@ -111,8 +141,8 @@ struct RemapConst {
 
 template <int CH>
 __global__ void __launch_bounds__(256)
-remap_kernel(const uint8_t* __restrict__ src, int src_h, int src_w, const uint64_t* __restrict__ lut, int views,
-             int rows, int cols, RemapConst k, uint8_t* __restrict__ dst) {
+remap_kernel(const uint8_t* __restrict__ src, const uint8_t* __restrict__ wide_end, int src_h, int src_w,
+             const uint64_t* __restrict__ lut, int views, int rows, int cols, RemapConst k, uint8_t* __restrict__ dst) {
   const int lane_col = blockIdx.x * RM_TILE_COLS + (threadIdx.x & 31) * RM_PX;
   const int row = blockIdx.y * RM_TILE_ROWS + (threadIdx.x >> 5);
   if (row >= rows || lane_col >= cols) return;
@@ -135,7 +165,7 @@ remap_kernel(const uint8_t* __restrict__ src, int src_h, int src_w, const uint64
   uint32_t o[RM_PX][CH];
 #pragma unroll
   for (int i = 0; i < RM_PX; ++i) {
-    if (i < n) remap_pixel<CH>(s, src_w, e[i], k.border, k.bg, o[i]);
+    if (i < n) remap_pixel<CH>(s, wide_end, src_w, e[i], k.border, k.bg, o[i]);
   }
   if (n == RM_PX && (((uintptr_t)d) & 3) == 0) {
     // RM_PX * CH bytes = CH 32-bit words
@@ -207,10 +237,13 @@ extern "C" int sos_remap_u8(sos_ctx* ctx, const uint8_t* src, int batch, int src
     k.bg[c] = (background && c < channels) ? background[c] : 0;
   }
   dim3 grid(sos_div_up(cols, RM_TILE_COLS), sos_div_up(rows, RM_TILE_ROWS), batch * views);
+  // the wide (2 x 64-bit) tap loads may touch up to 15 bytes past the taps: allowed only inside [src, wide_end)
+  static const bool wide_off = getenv("SOS_REMAP_BYTE_LOADS") != nullptr;  // A/B switch for profiling
+  const uint8_t* wide_end = (((uintptr_t)src & 7) == 0 && !wide_off) ? src + (size_t)batch * src_h * src_w * channels : nullptr;
   switch (channels) {
-    case 1: remap_kernel<1><<<grid, 256, 0, ctx->stream>>>(src, src_h, src_w, lut, views, rows, cols, k, dst); break;
-    case 3: remap_kernel<3><<<grid, 256, 0, ctx->stream>>>(src, src_h, src_w, lut, views, rows, cols, k, dst); break;
-    default: remap_kernel<4><<<grid, 256, 0, ctx->stream>>>(src, src_h, src_w, lut, views, rows, cols, k, dst); break;
+    case 1: remap_kernel<1><<<grid, 256, 0, ctx->stream>>>(src, wide_end, src_h, src_w, lut, views, rows, cols, k, dst); break;
+    case 3: remap_kernel<3><<<grid, 256, 0, ctx->stream>>>(src, wide_end, src_h, src_w, lut, views, rows, cols, k, dst); break;
+    default: remap_kernel<4><<<grid, 256, 0, ctx->stream>>>(src, wide_end, src_h, src_w, lut, views, rows, cols, k, dst); break;
   }
   SOS_LAUNCHED(ctx);
   return SOS_OK;
