@@ -198,3 +198,23 @@ def test_refit_inliers(ctx):
     o = ransac.refit(a, c, mask.cpu().numpy()[0].astype(bool))
     assert int(used.cpu().numpy()[0]) == int(best_count.cpu().numpy()[0])
     assert np.allclose(refit.cpu().numpy()[0], o, rtol=1e-4, atol=1e-5)
+
+
+def test_parallel_ransac_split_single_rank(ctx):
+    """parallel.ransac_split with one rank must equal the plain call (the multi-rank path is exercised by
+    scripts/bench_c4.py under torchrun and, for the reduce logic, by tests/test_parallel_cpu.py on gloo)."""
+    from vo_single_camera_sos_b200 import parallel
+    rng = np.random.default_rng(12)
+    a, c, f, cm = make_problem(rng, 2500)
+    hyp = hyp_list(rng, 700)
+    args = (dev(a[None]), dev(c[None]), dev(np.array([len(a)], np.int32)))
+    full = ctx.ransac_p3d(*args, as_i32(hyp), 0, 0.05)
+    pose, count, mask, winner = parallel.ransac_split(ctx, *args, as_i32(hyp), 0, 0.05, rank=0, world=1)
+    assert int(winner[0]) == int(full[1][0]) and int(count[0]) == int(full[2][0])
+    assert torch.equal(mask, full[3]) and torch.equal(pose, full[0])
+    # emulate 3 ranks on one GPU: keys of the slices, max, eval — what the NCCL all-reduce computes
+    keys = []
+    for r in range(3):
+        lo, hi = parallel.shard_hypotheses(len(hyp), 3, r)
+        keys.append(int(ctx.ransac_p3d(*args, as_i32(hyp[lo:hi]), 0, 0.05, hyp_offset=lo, want_mask=False)[4][0]))
+    assert parallel.unpack_key(max(keys)) == (int(full[2][0]), int(full[1][0]))
