@@ -167,6 +167,12 @@ int sos_match_select(sos_ctx* ctx, int mode, double ratio, const int32_t* idx0, 
                      const float* px_t, double max_du, double min_dv, int32_t* out_q,
                      int32_t* out_t, int32_t* out_d, int32_t* out_count);
 
+/* replaces: filter_pixel_correspondences (common_cv.py:167-188) as a stand-alone call on n already paired points:
+ * valid[i] = (max_du <= 0 || |top[i].u - bot[i].u| <= max_du) && (min_dv < 0 || top[i].v - bot[i].v >= min_dv).
+ * pts_top, pts_bot [n,2] float64 (the reference hands it float64 coordinates); valid [n] uint8. */
+int sos_pixel_gate(sos_ctx* ctx, const double* pts_top, const double* pts_bot, int n, double max_du, double min_dv,
+                   uint8_t* valid);
+
 /* ------------------------------------------------------------------------------------------------
  * Steps 3+4 — lifting and midpoint triangulation, RGB-D back-projection (F12)
  * ---------------------------------------------------------------------------------------------- */
@@ -179,6 +185,8 @@ enum { SOS_PANO_COLS = 0, SOS_PANO_ROWS, SOS_PANO_PIXEL_SIZE, SOS_PANO_HEIGHT_MA
  * GUM.get_3D_point_from_angles_wrt_focus (gum.py:2564 -> camera_models.py:1031-1065).
  * uv [n,2] float32 -> az, el [n] float32, bearing [n,3] float32 (NaN outside the panorama). Any output may be NULL. */
 int sos_lift_pano(sos_ctx* ctx, const double* pano, const float* uv, int n, float* az, float* el, float* bearing);
+/* Same with float64 in and out (the reference's dtype; used by the per-call Python mirror). */
+int sos_lift_pano_f64(sos_ctx* ctx, const double* pano, const double* uv, int n, double* az, double* el, double* bearing);
 
 /* replaces: GUM.lift_pixel_to_unit_sphere_wrt_focus (gum.py:2673-2940, new_method branch) and
  * OmniCamModel.get_direction_angles_from_pixel (camera_models.py:1183-1194).
@@ -194,6 +202,15 @@ int sos_lift_gum(sos_ctx* ctx, const double* gum, const double* uv, int n, doubl
 int sos_triangulate_midpoint(sos_ctx* ctx, const float* az1, const float* el1, const float* az2,
                              const float* el2, int n, const double* f1, const double* f2, double rmin,
                              double rmax, int homogeneous_norm, float* xyz, uint8_t* valid);
+/* replaces: OmniCamModel.map_angles_to_unit_sphere (camera_models.py:1031-1065) as a stand-alone call: az, el [n]
+ * float64 -> sphere [n,3] float64, NaN-propagating. */
+int sos_angles_to_sphere_f64(sos_ctx* ctx, const double* az, const double* el, int n, double* sphere);
+/* replaces: filter_panoramic_points_due_to_range (camera_models.py:3299-3321) as a stand-alone call: xyz [n,3] float64. */
+int sos_range_gate_f64(sos_ctx* ctx, const double* xyz, int n, double rmin, double rmax, int homogeneous_norm,
+                       uint8_t* valid);
+int sos_triangulate_midpoint_f64(sos_ctx* ctx, const double* az1, const double* el1, const double* az2,
+                                 const double* el2, int n, const double* f1, const double* f2, double rmin,
+                                 double rmax, int homogeneous_norm, double* xyz, uint8_t* valid);
 
 /* Fused steps 3+4 over matched pairs, driven by DEVICE-side counts (no host sync), as
  * StereoPanoramicFrame.establish_stereo_correspondences does after matching (pose_est_tools.py:344-397).
@@ -236,8 +253,10 @@ int sos_rgbd_backproject(sos_ctx* ctx, const double* cam, const float* depth, in
 /* replaces: transformations.superimposition_matrix(v0, v1, scale=False, usesvd=True)
  * (transformations.py:982-1030 -> 874-980) for n_sets independent point sets of k points each.
  * v0, v1 [n_sets, k, 3] float64 -> M [n_sets, 12] float64 (row-major 3x4 [R|t], v1 ~ R v0 + t);
+ * with_scale != 0 adds Umeyama's uniform scale (scale=True, transformations.py:971-975): v1 ~ s R v0 + t, M = [sR|t];
  * ok [n_sets] uint8 = 0 for degenerate (rank < 2) sets. */
-int sos_arun_batch(sos_ctx* ctx, const double* v0, const double* v1, int n_sets, int k, double* M, uint8_t* ok);
+int sos_arun_batch(sos_ctx* ctx, const double* v0, const double* v1, int n_sets, int k, int with_scale, double* M,
+                   uint8_t* ok);
 
 /* One RANSAC problem per `problem` (frame pair).  The correspondences of problem b are rows
  * [b*cap, b*cap + n[b]) of the arrays below, n DEVICE int32 [n_problems].

@@ -41,12 +41,17 @@ PROTOTYPES = {
     "sos_hamming_top2": (I, [c_ctx, P, P, P, P, P, P, I, I, I, P, P, P, P]),
     "sos_match_select": (I, [c_ctx, I, D, P, P, P, P, P, P, P, I, P, P, D, D, P, P, P, P]),
     "sos_lift_pano": (I, [c_ctx, P, P, I, P, P, P]),
+    "sos_lift_pano_f64": (I, [c_ctx, P, P, I, P, P, P]),
+    "sos_angles_to_sphere_f64": (I, [c_ctx, P, P, I, P]),
+    "sos_range_gate_f64": (I, [c_ctx, P, I, D, D, I, P]),
+    "sos_triangulate_midpoint_f64": (I, [c_ctx, P, P, P, P, I, P, P, D, D, I, P, P]),
     "sos_lift_gum": (I, [c_ctx, P, P, I, P, P, P]),
     "sos_triangulate_midpoint": (I, [c_ctx, P, P, P, P, I, P, P, D, D, I, P, P]),
     "sos_stereo_lift_triangulate": (I, [c_ctx, P, P, P, P, P, P, P, P, I, I, P, P, D, D, I, I, P, P, P, P, P, P, P, P]),
     "sos_rgbd_depth_to_z": (I, [c_ctx, P, P, I, I, I, P]),
     "sos_rgbd_backproject": (I, [c_ctx, P, P, I, I, I, P, P, I, D, D, P, P, P]),
-    "sos_arun_batch": (I, [c_ctx, P, P, I, I, P, P]),
+    "sos_arun_batch": (I, [c_ctx, P, P, I, I, I, P, P]),
+    "sos_pixel_gate": (I, [c_ctx, P, P, I, D, D, P]),
     "sos_ransac_p3d": (I, [c_ctx, P, P, P, P, P, I, I, P, I, P, I, I, I, D, P, P, P, P, P, P]),
     "sos_ransac_p3d_eval": (I, [c_ctx, P, P, P, P, P, I, I, P, I, P, I, D, P, P, P]),
     "sos_refit_inliers": (I, [c_ctx, P, P, P, P, I, I, P, P]),

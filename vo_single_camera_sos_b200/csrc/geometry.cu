@@ -71,33 +71,36 @@ __device__ __forceinline__ bool range_ok(Vec3 p, double rmin, double rmax, int h
   return true;
 }
 
-__global__ void lift_pano_kernel(PanoP p, const float2* __restrict__ uv, int n, float* __restrict__ az_out,
-                                 float* __restrict__ el_out, float* __restrict__ bearing) {
+// T = float: the storage type of the batched hot path; T = double: the reference's own dtype, used by the per-call
+// Python mirror (omnistereo.panorama / camera_models) so that chained calls lose nothing between kernels.
+template <typename T>
+__global__ void lift_pano_kernel(PanoP p, const T* __restrict__ uv, int n, T* __restrict__ az_out,
+                                 T* __restrict__ el_out, T* __restrict__ bearing) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float2 m = uv[i];
   double az, el;
-  pano_pixel_to_angles(p, (double)m.x, (double)m.y, az, el);
-  if (az_out) az_out[i] = (float)az;
-  if (el_out) el_out[i] = (float)el;
+  pano_pixel_to_angles(p, (double)uv[2 * i], (double)uv[2 * i + 1], az, el);
+  if (az_out) az_out[i] = (T)az;
+  if (el_out) el_out[i] = (T)el;
   if (bearing) {
     const Vec3 s = angles_to_sphere(az, el);
-    bearing[3 * i + 0] = (float)s.x;
-    bearing[3 * i + 1] = (float)s.y;
-    bearing[3 * i + 2] = (float)s.z;
+    bearing[3 * i + 0] = (T)s.x;
+    bearing[3 * i + 1] = (T)s.y;
+    bearing[3 * i + 2] = (T)s.z;
   }
 }
 
-__global__ void triangulate_kernel(const float* __restrict__ az1, const float* __restrict__ el1,
-                                   const float* __restrict__ az2, const float* __restrict__ el2, int n, Vec3 f1, Vec3 f2,
-                                   double rmin, double rmax, int homo, float* __restrict__ xyz,
+template <typename T>
+__global__ void triangulate_kernel(const T* __restrict__ az1, const T* __restrict__ el1,
+                                   const T* __restrict__ az2, const T* __restrict__ el2, int n, Vec3 f1, Vec3 f2,
+                                   double rmin, double rmax, int homo, T* __restrict__ xyz,
                                    uint8_t* __restrict__ valid) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const Vec3 P = triangulate_midpoint((double)az1[i], (double)el1[i], (double)az2[i], (double)el2[i], f1, f2);
-  xyz[3 * i + 0] = (float)P.x;
-  xyz[3 * i + 1] = (float)P.y;
-  xyz[3 * i + 2] = (float)P.z;
+  xyz[3 * i + 0] = (T)P.x;
+  xyz[3 * i + 1] = (T)P.y;
+  xyz[3 * i + 2] = (T)P.z;
   if (valid) valid[i] = range_ok(P, rmin, rmax, homo) ? 1 : 0;
 }
 
@@ -339,14 +342,39 @@ static PanoP load_pano(const double* g) {
 
 }  // namespace
 
-extern "C" int sos_lift_pano(sos_ctx* ctx, const double* pano, const float* uv, int n, float* az, float* el,
-                             float* bearing) {
+template <typename T>
+static int lift_pano_impl(sos_ctx* ctx, const double* pano, const T* uv, int n, T* az, T* el, T* bearing) {
   SOS_CHECK_ARG(ctx && pano, "NULL argument");
   SOS_CHECK_ARG(n >= 0, "negative size");
   if (n == 0) return SOS_OK;
   SOS_CHECK_ARG(uv, "uv is NULL");
   SOS_CUDA(cudaSetDevice(ctx->device));
-  lift_pano_kernel<<<sos_div_up(n, 256), 256, 0, ctx->stream>>>(load_pano(pano), (const float2*)uv, n, az, el, bearing);
+  lift_pano_kernel<T><<<sos_div_up(n, 256), 256, 0, ctx->stream>>>(load_pano(pano), uv, n, az, el, bearing);
+  SOS_LAUNCHED(ctx);
+  return SOS_OK;
+}
+
+extern "C" int sos_lift_pano(sos_ctx* ctx, const double* pano, const float* uv, int n, float* az, float* el,
+                             float* bearing) {
+  return lift_pano_impl<float>(ctx, pano, uv, n, az, el, bearing);
+}
+
+extern "C" int sos_lift_pano_f64(sos_ctx* ctx, const double* pano, const double* uv, int n, double* az, double* el,
+                                 double* bearing) {
+  return lift_pano_impl<double>(ctx, pano, uv, n, az, el, bearing);
+}
+
+template <typename T>
+static int triangulate_impl(sos_ctx* ctx, const T* az1, const T* el1, const T* az2, const T* el2, int n, const double* f1,
+                            const double* f2, double rmin, double rmax, int homogeneous_norm, T* xyz, uint8_t* valid) {
+  SOS_CHECK_ARG(ctx && f1 && f2, "NULL argument");
+  SOS_CHECK_ARG(n >= 0, "negative size");
+  if (n == 0) return SOS_OK;
+  SOS_CHECK_ARG(az1 && el1 && az2 && el2 && xyz, "NULL array");
+  SOS_CUDA(cudaSetDevice(ctx->device));
+  triangulate_kernel<T><<<sos_div_up(n, 256), 256, 0, ctx->stream>>>(az1, el1, az2, el2, n, {f1[0], f1[1], f1[2]},
+                                                                    {f2[0], f2[1], f2[2]}, rmin, rmax, homogeneous_norm,
+                                                                    xyz, valid);
   SOS_LAUNCHED(ctx);
   return SOS_OK;
 }
@@ -354,16 +382,13 @@ extern "C" int sos_lift_pano(sos_ctx* ctx, const double* pano, const float* uv, 
 extern "C" int sos_triangulate_midpoint(sos_ctx* ctx, const float* az1, const float* el1, const float* az2,
                                         const float* el2, int n, const double* f1, const double* f2, double rmin,
                                         double rmax, int homogeneous_norm, float* xyz, uint8_t* valid) {
-  SOS_CHECK_ARG(ctx && f1 && f2, "NULL argument");
-  SOS_CHECK_ARG(n >= 0, "negative size");
-  if (n == 0) return SOS_OK;
-  SOS_CHECK_ARG(az1 && el1 && az2 && el2 && xyz, "NULL array");
-  SOS_CUDA(cudaSetDevice(ctx->device));
-  triangulate_kernel<<<sos_div_up(n, 256), 256, 0, ctx->stream>>>(az1, el1, az2, el2, n, {f1[0], f1[1], f1[2]},
-                                                                 {f2[0], f2[1], f2[2]}, rmin, rmax, homogeneous_norm,
-                                                                 xyz, valid);
-  SOS_LAUNCHED(ctx);
-  return SOS_OK;
+  return triangulate_impl<float>(ctx, az1, el1, az2, el2, n, f1, f2, rmin, rmax, homogeneous_norm, xyz, valid);
+}
+
+extern "C" int sos_triangulate_midpoint_f64(sos_ctx* ctx, const double* az1, const double* el1, const double* az2,
+                                            const double* el2, int n, const double* f1, const double* f2, double rmin,
+                                            double rmax, int homogeneous_norm, double* xyz, uint8_t* valid) {
+  return triangulate_impl<double>(ctx, az1, el1, az2, el2, n, f1, f2, rmin, rmax, homogeneous_norm, xyz, valid);
 }
 
 extern "C" int sos_stereo_lift_triangulate(sos_ctx* ctx, const double* pano_top, const double* pano_bot,
@@ -460,6 +485,49 @@ extern "C" int sos_rgbd_backproject(sos_ctx* ctx, const double* cam, const float
   for (int i = 0; i < SOS_RGBD_NPARAMS; ++i) c.v[i] = cam[i];
   dim3 grid(sos_div_up(n, 256), batch);
   rgbd_backproject_kernel<<<grid, 256, 0, ctx->stream>>>(c, depth, h, w, u, v, n, zmin, zmax, xyz, bearing, valid);
+  SOS_LAUNCHED(ctx);
+  return SOS_OK;
+}
+
+// ---- stand-alone F8 and F11 for the per-call Python mirror (float64, the reference's dtype) ---------------------
+namespace {
+__global__ void angles_to_sphere_kernel(const double* __restrict__ az, const double* __restrict__ el, int n,
+                                        double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Vec3 s = angles_to_sphere(az[i], el[i]);  // NaN elevation / azimuth propagate as in camera_models.py:1046-1053
+  out[3 * i] = s.x;
+  out[3 * i + 1] = s.y;
+  out[3 * i + 2] = s.z;
+}
+
+__global__ void range_gate_kernel(const double* __restrict__ xyz, int n, double rmin, double rmax, int homo,
+                                  uint8_t* __restrict__ valid) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  valid[i] = range_ok({xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}, rmin, rmax, homo) ? 1 : 0;
+}
+}  // namespace
+
+extern "C" int sos_angles_to_sphere_f64(sos_ctx* ctx, const double* az, const double* el, int n, double* sphere) {
+  SOS_CHECK_ARG(ctx, "ctx is NULL");
+  SOS_CHECK_ARG(n >= 0, "negative size");
+  if (n == 0) return SOS_OK;
+  SOS_CHECK_ARG(az && el && sphere, "NULL array");
+  SOS_CUDA(cudaSetDevice(ctx->device));
+  angles_to_sphere_kernel<<<sos_div_up(n, 256), 256, 0, ctx->stream>>>(az, el, n, sphere);
+  SOS_LAUNCHED(ctx);
+  return SOS_OK;
+}
+
+extern "C" int sos_range_gate_f64(sos_ctx* ctx, const double* xyz, int n, double rmin, double rmax, int homogeneous_norm,
+                                  uint8_t* valid) {
+  SOS_CHECK_ARG(ctx, "ctx is NULL");
+  SOS_CHECK_ARG(n >= 0, "negative size");
+  if (n == 0) return SOS_OK;
+  SOS_CHECK_ARG(xyz && valid, "NULL array");
+  SOS_CUDA(cudaSetDevice(ctx->device));
+  range_gate_kernel<<<sos_div_up(n, 256), 256, 0, ctx->stream>>>(xyz, n, rmin, rmax, homogeneous_norm, valid);
   SOS_LAUNCHED(ctx);
   return SOS_OK;
 }

@@ -403,3 +403,29 @@ extern "C" int sos_match_select(sos_ctx* ctx, int mode, double ratio, const int3
   SOS_LAUNCHED(ctx);
   return SOS_OK;
 }
+
+namespace {
+__global__ void pixel_gate_kernel(const double2* __restrict__ top, const double2* __restrict__ bot, int n, double max_du,
+                                  double min_dv, uint8_t* __restrict__ valid) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double2 a = top[i], b = bot[i];
+  bool ok = true;
+  if (max_du > 0.0) ok = ok && (fabs(a.x - b.x) <= max_du);  // common_cv.py:177-178
+  if (min_dv >= 0.0) ok = ok && (a.y - b.y >= min_dv);       // common_cv.py:182-184
+  valid[i] = ok ? 1 : 0;
+}
+}  // namespace
+
+extern "C" int sos_pixel_gate(sos_ctx* ctx, const double* pts_top, const double* pts_bot, int n, double max_du,
+                              double min_dv, uint8_t* valid) {
+  SOS_CHECK_ARG(ctx, "ctx is NULL");
+  SOS_CHECK_ARG(n >= 0, "negative size");
+  if (n == 0) return SOS_OK;
+  SOS_CHECK_ARG(pts_top && pts_bot && valid, "NULL array");
+  SOS_CUDA(cudaSetDevice(ctx->device));
+  pixel_gate_kernel<<<sos_div_up(n, 256), 256, 0, ctx->stream>>>((const double2*)pts_top, (const double2*)pts_bot, n, max_du,
+                                                                  min_dv, valid);
+  SOS_LAUNCHED(ctx);
+  return SOS_OK;
+}

@@ -486,13 +486,30 @@ mask_kernel(int mode, const float* __restrict__ p_ref, const float* __restrict__
 
 // generic k-point Arun, one thread per set (parity with transformations.superimposition_matrix)
 __global__ void arun_batch_kernel(const double* __restrict__ v0, const double* __restrict__ v1, int n_sets, int k,
-                                  double* __restrict__ M, uint8_t* __restrict__ ok) {
+                                  int with_scale, double* __restrict__ M, uint8_t* __restrict__ ok) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_sets) return;
   const double* a = v0 + (size_t)s * k * 3;
   const double* b = v1 + (size_t)s * k * 3;
   double out[12];
   const bool good = arun_fit(a, b, k, out);
+  if (good && with_scale) {
+    // Umeyama: uniform scale = ratio of the RMS deviations from the centroids (transformations.py:971-975)
+    double c0[3] = {0, 0, 0}, c1[3] = {0, 0, 0}, s0 = 0.0, s1 = 0.0;
+    for (int i = 0; i < k; ++i)
+      for (int d = 0; d < 3; ++d) { c0[d] += a[3 * i + d]; c1[d] += b[3 * i + d]; }
+    for (int d = 0; d < 3; ++d) { c0[d] /= (double)k; c1[d] /= (double)k; }
+    for (int i = 0; i < k; ++i)
+      for (int d = 0; d < 3; ++d) {
+        s0 += (a[3 * i + d] - c0[d]) * (a[3 * i + d] - c0[d]);
+        s1 += (b[3 * i + d] - c1[d]) * (b[3 * i + d] - c1[d]);
+      }
+    const double sc = sqrt(s1 / s0);
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) out[r * 4 + c] *= sc;
+      out[r * 4 + 3] = c1[r] - (out[r * 4] * c0[0] + out[r * 4 + 1] * c0[1] + out[r * 4 + 2] * c0[2]);
+    }
+  }
   for (int i = 0; i < 12; ++i) M[(size_t)s * 12 + i] = good ? out[i] : CUDART_NAN;
   if (ok) ok[s] = good ? 1 : 0;
 }
@@ -607,14 +624,14 @@ int launch_score(sos_ctx* ctx, const Rig& rig, dim3 grid, const float* p_ref, co
 
 }  // namespace
 
-extern "C" int sos_arun_batch(sos_ctx* ctx, const double* v0, const double* v1, int n_sets, int k, double* M,
-                              uint8_t* ok) {
+extern "C" int sos_arun_batch(sos_ctx* ctx, const double* v0, const double* v1, int n_sets, int k, int with_scale,
+                              double* M, uint8_t* ok) {
   SOS_CHECK_ARG(ctx, "ctx is NULL");
   SOS_CHECK_ARG(n_sets >= 0 && k >= 3, "need k >= 3 points per set");
   if (n_sets == 0) return SOS_OK;
   SOS_CHECK_ARG(v0 && v1 && M, "NULL array");
   SOS_CUDA(cudaSetDevice(ctx->device));
-  arun_batch_kernel<<<sos_div_up(n_sets, 128), 128, 0, ctx->stream>>>(v0, v1, n_sets, k, M, ok);
+  arun_batch_kernel<<<sos_div_up(n_sets, 128), 128, 0, ctx->stream>>>(v0, v1, n_sets, k, with_scale, M, ok);
   SOS_LAUNCHED(ctx);
   return SOS_OK;
 }

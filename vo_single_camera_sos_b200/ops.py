@@ -219,6 +219,48 @@ class Context:
                                      bearing.data_ptr() if want_bearing else None))
         return az, el, bearing
 
+    def lift_pano_f64(self, pano, uv: torch.Tensor):
+        """float64 in / out variant of lift_pano (the reference's dtype)."""
+        self._sync_stream()
+        p = _darr(pano, len(PANO_FIELDS), "pano")
+        n = uv.shape[0]
+        az = self.empty((n,), torch.float64)
+        el = self.empty((n,), torch.float64)
+        bearing = self.empty((n, 3), torch.float64)
+        check(self.lib.sos_lift_pano_f64(self._h, _ptr(p), self._t(uv, torch.float64, "uv"), n, az.data_ptr(),
+                                         el.data_ptr(), bearing.data_ptr()))
+        return az, el, bearing
+
+    def angles_to_sphere_f64(self, az: torch.Tensor, el: torch.Tensor):
+        self._sync_stream()
+        n = az.shape[0]
+        out = self.empty((n, 3), torch.float64)
+        check(self.lib.sos_angles_to_sphere_f64(self._h, self._t(az, torch.float64, "az"), self._t(el, torch.float64, "el"),
+                                                n, out.data_ptr()))
+        return out
+
+    def range_gate(self, xyz: torch.Tensor, rmin: float, rmax: float, homogeneous_norm: bool):
+        self._sync_stream()
+        n = xyz.shape[0]
+        valid = self.empty((n,), torch.uint8)
+        check(self.lib.sos_range_gate_f64(self._h, self._t(xyz, torch.float64, "xyz"), n, float(rmin), float(rmax),
+                                          int(bool(homogeneous_norm)), valid.data_ptr()))
+        return valid
+
+    def triangulate_midpoint_f64(self, az1, el1, az2, el2, f1, f2, rmin: float = 0.0, rmax: float = 0.0,
+                                 homogeneous_norm: bool = False):
+        self._sync_stream()
+        n = az1.shape[0]
+        a = _darr(f1, 3, "f1")
+        b = _darr(f2, 3, "f2")
+        xyz = self.empty((n, 3), torch.float64)
+        valid = self.empty((n,), torch.uint8)
+        check(self.lib.sos_triangulate_midpoint_f64(
+            self._h, self._t(az1, torch.float64, "az1"), self._t(el1, torch.float64, "el1"),
+            self._t(az2, torch.float64, "az2"), self._t(el2, torch.float64, "el2"), n, _ptr(a), _ptr(b), float(rmin),
+            float(rmax), int(bool(homogeneous_norm)), xyz.data_ptr(), valid.data_ptr()))
+        return xyz, valid
+
     def lift_gum(self, gum, uv: torch.Tensor):
         self._sync_stream()
         g = _darr(gum, len(GUM_FIELDS), "gum")
@@ -300,15 +342,25 @@ class Context:
         return xyz, bearing, valid
 
     # -- step 5 -------------------------------------------------------------------------------------------------
-    def arun_batch(self, v0: torch.Tensor, v1: torch.Tensor):
+    def arun_batch(self, v0: torch.Tensor, v1: torch.Tensor, with_scale: bool = False):
         """v0, v1 [n_sets, k, 3] float64 -> M [n_sets, 3, 4] float64, ok [n_sets] uint8."""
         self._sync_stream()
         n_sets, k, _ = v0.shape
         M = self.empty((n_sets, 3, 4), torch.float64)
         ok = self.empty((n_sets,), torch.uint8)
         check(self.lib.sos_arun_batch(self._h, self._t(v0, torch.float64, "v0"), self._t(v1, torch.float64, "v1"),
-                                      n_sets, k, M.data_ptr(), ok.data_ptr()))
+                                      n_sets, k, int(bool(with_scale)), M.data_ptr(), ok.data_ptr()))
         return M, ok
+
+    def pixel_gate(self, pts_top: torch.Tensor, pts_bot: torch.Tensor, max_du: float, min_dv: float):
+        """pts_* [n,2] float64 -> valid [n] uint8 (common_cv.filter_pixel_correspondences)."""
+        self._sync_stream()
+        n = pts_top.shape[0]
+        valid = self.empty((n,), torch.uint8)
+        check(self.lib.sos_pixel_gate(self._h, self._t(pts_top, torch.float64, "pts_top"),
+                                      self._t(pts_bot, torch.float64, "pts_bot"), n, float(max_du), float(min_dv),
+                                      valid.data_ptr()))
+        return valid
 
     @staticmethod
     def _rig(rig, n_cams):

@@ -1,0 +1,112 @@
+"""`pyopengv`-compatible module backed by the batched RANSAC kernels (SURVEY §8b, row "L3 -> OpenGV").
+
+The reference imports seven names from `pyopengv` (pose_est_tools.py:42,78,647-649).  OpenGV is neither vendored nor
+installed and its outputs are pinned by no test of the reference, so parity with OpenGV itself is UNPINNED; the
+semantics implemented here are the ones written down in include/sosfront.h:
+
+  * hypotheses: Arun / Kabsch rigid registration on 3 sampled 3D-3D correspondences (transformations.py:874-1030) drawn
+    from a seeded list, instead of OpenGV's GP3P / EPnP minimal solvers.  That needs the 3D points of the CURRENT frame,
+    which the reference has at the call site (pose_est_tools.py:753-756) but does not pass to OpenGV: pass them as
+    `points_cur=` (the mirrored trackers in omnistereo.pose_est_tools do).  Without them the call raises.
+  * score: OpenGV's bearing-angle score 1 - f . reprojection, threshold and iteration budget as given.
+  * first maximum wins; the inlier indices are returned ascending, as the caller assumes (pose_est_tools.py:787).
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+_SEED = 0
+
+
+def _ctx():
+    return ops.default_context()
+
+
+def _dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def hypothesis_list(n_hyp: int, seed: int = _SEED) -> np.ndarray:
+    """The shared seeded hypothesis list: uint32 [n_hyp, 3]; sample j of hypothesis h is row floor(u * n / 2^32)."""
+    return np.random.default_rng(seed).integers(0, 2 ** 32, (int(n_hyp), 3), dtype=np.uint64).astype(np.uint32)
+
+
+def _rig(cam_offsets, cam_rotations):
+    off = np.asarray(cam_offsets, np.float64).reshape(-1, 3)
+    rot = np.asarray(cam_rotations, np.float64).reshape(-1, 3, 3)
+    if len(off) > 2:
+        raise NotImplementedError("the SOS rig has two cameras")
+    return np.concatenate([rot, off[:, :, None]], axis=2), len(off)
+
+
+def _ransac(bearings, points, points_cur, threshold, max_iterations, cam=None, rig=None, n_cams=0, seed=_SEED):
+    if points_cur is None:
+        raise NotImplementedError(
+            "this pyopengv replacement hypothesises with 3D-3D Arun registration and needs the current frame's 3D points: "
+            "pass points_cur= (N x 3).  OpenGV's GP3P / EPnP minimal solvers are not re-implemented (see INTEGRATION.md)")
+    b = np.asarray(bearings, np.float32)[:, :3]
+    p = np.asarray(points, np.float32)[:, :3]
+    pc = np.asarray(points_cur, np.float32)[:, :3]
+    n = len(p)
+    hyp = hypothesis_list(max_iterations, seed)
+    ctx = _ctx()
+    pose, best_hyp, best_count, mask, _ = ctx.ransac_p3d(
+        _dev(p[None]), _dev(pc[None]), torch.tensor([n], dtype=torch.int32, device=ctx.device), _dev(hyp.view(np.int32)),
+        ops.SCORE_BEARING, float(threshold), f_cur=_dev(b[None]),
+        cam=None if cam is None else _dev(np.asarray(cam).reshape(-1).astype(np.uint8)[None]), rig=rig, n_cams=n_cams)
+    T = pose.cpu().numpy()[0].astype(np.float64)
+    inliers = np.nonzero(mask.cpu().numpy()[0])[0].astype(np.int64)
+    return T, inliers
+
+
+def absolute_pose_noncentral_ransac(bearing_vectors, cam_correspondences, points, cam_offsets, cam_rotations, threshold,
+                                    max_iterations, points_cur=None, seed=_SEED):
+    """-> (T 3x4 [R|t] of the current frame wrt the reference frame, ascending inlier indices): pose_est_tools.py:785."""
+    rig, n_cams = _rig(cam_offsets, cam_rotations)
+    return _ransac(bearing_vectors, points, points_cur, threshold, max_iterations, cam=cam_correspondences, rig=rig,
+                   n_cams=n_cams, seed=seed)
+
+
+def absolute_pose_ransac(bearing_vectors, points, algo_name, threshold, max_iterations, points_cur=None, seed=_SEED):
+    """Central camera (RGB-D path, pose_est_tools.py:915); `algo_name` ("EPNP", "KNEIP", ...) is accepted and ignored."""
+    return _ransac(bearing_vectors, points, points_cur, threshold, max_iterations, seed=seed)
+
+
+def _refit(points, points_cur, t, R):
+    if points_cur is None:  # nothing to refine with: hand the RANSAC model back (documented approximation)
+        return np.hstack([np.asarray(R, float).reshape(3, 3), np.asarray(t, float).reshape(3, 1)])
+    p = np.asarray(points, np.float32)[:, :3]
+    pc = np.asarray(points_cur, np.float32)[:, :3]
+    ctx = _ctx()
+    n = len(p)
+    pose, used = ctx.refit_inliers(_dev(p[None]), _dev(pc[None]), torch.ones((1, n), dtype=torch.uint8, device=ctx.device),
+                                   torch.tensor([n], dtype=torch.int32, device=ctx.device))
+    if int(used.cpu().numpy()[0]) < 3:
+        return np.hstack([np.asarray(R, float).reshape(3, 3), np.asarray(t, float).reshape(3, 1)])
+    return pose.cpu().numpy()[0].astype(np.float64)
+
+
+def absolute_pose_noncentral_optimize_nonlinear(bearing_vectors, cam_correspondences, points, cam_offsets, cam_rotations, t, R,
+                                                points_cur=None):
+    """Stand-in for OpenGV's non-linear refinement (pose_est_tools.py:830): Arun refit on the given (inlier) set — an
+    APPROXIMATION; the true bearing-error Gauss-Newton refinement is SURVEY §8f row N1."""
+    return _refit(points, points_cur, t, R)
+
+
+def absolute_pose_optimize_nonlinear(bearing_vectors, points, t, R, points_cur=None):
+    return _refit(points, points_cur, t, R)
+
+
+def relative_pose_ransac(*args, **kwargs):
+    raise NotImplementedError("2D-2D relative pose is not on the SOS / RGB-D hot path (pose_est_tools.py:78 is a disabled branch)")
+
+
+def triangulation_triangulate(*args, **kwargs):
+    raise NotImplementedError("OpenGV triangulation is a disabled branch (use_opengv_triangulation = False, pose_est_tools.py:284)")
+
+
+triangulation_triangulate2 = triangulation_triangulate
