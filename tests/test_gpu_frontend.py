@@ -141,7 +141,9 @@ def test_frontend_two_steps_stage_by_stage(ctx, mode, graph):
         torch.cuda.synchronize()
         buf = host(fe.buffers())
         # slot 0 now holds the carried frame == slot B (the copy at the end of the step)
-        assert buf["n"][0] == buf["n"][B] and np.array_equal(buf["xyz"][0], buf["xyz"][B])
+        nB = int(buf["n"][B])
+        assert buf["n"][0] == nB and np.array_equal(buf["xyz"][0, :nB], buf["xyz"][B, :nB])
+        assert np.array_equal(buf["desc_c"][:, 0, :nB], buf["desc_c"][:, B, :nB])
         prev = check_step(w, fr, buf, prev, mode)
         rel.append((buf["pose"].copy(), buf["stats"].copy()))
     # sanity against the ground-truth motion (not a parity bar): the refit pose of pair i is frame i wrt frame i-1

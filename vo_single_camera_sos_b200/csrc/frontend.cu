@@ -69,7 +69,7 @@ __global__ void temporal_segments_kernel(const int32_t* __restrict__ n, int B, i
 }
 
 // Stack the temporal matches of both views into one correspondence list per frame pair (pose_est_tools.py:752-778).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 assemble_kernel(const int32_t* __restrict__ m_q, const int32_t* __restrict__ m_t, const int32_t* __restrict__ m_count,
                 const int32_t* __restrict__ q_start, int B, int cap, const float* __restrict__ xyz,
                 const float* __restrict__ b_top, const float* __restrict__ b_bot, float* __restrict__ p_ref,
@@ -99,6 +99,29 @@ assemble_kernel(const int32_t* __restrict__ m_q, const int32_t* __restrict__ m_t
       f_cur[o + d] = bq[d];
     }
     cam[(size_t)i * cap2 + k] = (uint8_t)view;
+  }
+}
+
+__global__ void carry_over_kernel(int B, int cap, float* __restrict__ uv_top, float* __restrict__ uv_bot,
+                                  float* __restrict__ b_top, float* __restrict__ b_bot, float* __restrict__ xyz,
+                                  uint32_t* __restrict__ desc_c, int32_t* __restrict__ n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cnt = n[B];
+  if (k == 0) n[0] = cnt;
+  if (k >= cnt) return;
+  const size_t src = (size_t)B * cap + k, dst = k;
+  ((float2*)uv_top)[dst] = ((const float2*)uv_top)[src];
+  ((float2*)uv_bot)[dst] = ((const float2*)uv_bot)[src];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    b_top[3 * dst + c] = b_top[3 * src + c];
+    b_bot[3 * dst + c] = b_bot[3 * src + c];
+    xyz[3 * dst + c] = xyz[3 * src + c];
+  }
+  for (int view = 0; view < 2; ++view) {
+    uint4* base = (uint4*)(desc_c + (size_t)view * (B + 1) * cap * 8);
+    base[2 * dst] = base[2 * src];
+    base[2 * dst + 1] = base[2 * src + 1];
   }
 }
 
@@ -217,7 +240,7 @@ int enqueue_step(sos_frontend* fe, const uint8_t* omni, const float* px_top, con
                         d.tm_t_start, 2 * B, d.uv_c, d.uv_c, c.temporal_max_du, -1.0, d.tm_pair_q, d.tm_pair_t, d.tm_pair_d,
                         d.tm_pair_count);
   if (rc) return rc;
-  assemble_kernel<<<B, 256, 0, ctx->stream>>>(d.tm_pair_q, d.tm_pair_t, d.tm_pair_count, d.tm_q_start, B, cap, d.xyz, d.b_top,
+  assemble_kernel<<<B, 1024, 0, ctx->stream>>>(d.tm_pair_q, d.tm_pair_t, d.tm_pair_count, d.tm_q_start, B, cap, d.xyz, d.b_top,
                                               d.b_bot, d.p_ref, d.p_cur, d.f_cur, d.cam, d.n_corr, d.n_corr_top);
   SOS_LAUNCHED(ctx);
   // step 5
@@ -233,19 +256,10 @@ int enqueue_step(sos_frontend* fe, const uint8_t* omni, const float* px_top, con
   }
   stats_kernel<<<sos_div_up(B, 128), 128, 0, ctx->stream>>>(d.n, d.n_corr, d.best_count, d.best_hyp, B, d.stats);
   SOS_LAUNCHED(ctx);
-  // carry the last frame over as the reference of the next step: slot B -> slot 0
-  const size_t last = (size_t)B * cap;
-  SOS_CUDA(cudaMemcpyAsync(d.uv_top, d.uv_top + last * 2, (size_t)cap * 2 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
-  SOS_CUDA(cudaMemcpyAsync(d.uv_bot, d.uv_bot + last * 2, (size_t)cap * 2 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
-  SOS_CUDA(cudaMemcpyAsync(d.b_top, d.b_top + last * 3, (size_t)cap * 3 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
-  SOS_CUDA(cudaMemcpyAsync(d.b_bot, d.b_bot + last * 3, (size_t)cap * 3 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
-  SOS_CUDA(cudaMemcpyAsync(d.xyz, d.xyz + last * 3, (size_t)cap * 3 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
-  for (int view = 0; view < 2; ++view) {
-    uint32_t* base = d.desc_c + (size_t)view * (B + 1) * cap * 8;
-    SOS_CUDA(cudaMemcpyAsync(base, base + last * 8, (size_t)cap * 32, cudaMemcpyDeviceToDevice, ctx->stream));
-  }
-  SOS_CUDA(cudaMemcpyAsync(d.n, d.n + B, sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-  if (ctx->prof) sos_prof_mark_launch(ctx, "carry_over_copies");  // keeps the copies out of the next kernel's interval
+  // carry the last frame over as the reference of the next step: slot B -> slot 0 (one kernel instead of 8 copy nodes)
+  carry_over_kernel<<<sos_div_up(cap, 256), 256, 0, ctx->stream>>>(B, cap, d.uv_top, d.uv_bot, d.b_top, d.b_bot, d.xyz,
+                                                                    d.desc_c, d.n);
+  SOS_LAUNCHED(ctx);
   return SOS_OK;
 }
 

@@ -121,7 +121,7 @@ struct StereoArgs {
   int32_t *out_src_top, *out_src_bot, *out_n;
 };
 
-constexpr int ST_THREADS = 256;
+constexpr int ST_THREADS = 1024;  // one block per frame: wide block, the float64 transcendental math is latency bound
 
 __global__ void __launch_bounds__(ST_THREADS) stereo_lift_triangulate_kernel(StereoArgs a) {
   __shared__ int warp_sums[ST_THREADS / 32];

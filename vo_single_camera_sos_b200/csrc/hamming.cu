@@ -26,9 +26,12 @@ constexpr int KEY_IDX_BITS = 22; // up to 4M train rows per segment; distance <=
 constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
 
 // carry-save adder on 32 bit lanes: a + b + c = sum + 2 * carry (one LOP3 each)
+// Written as two explicit LOP3s (truth tables 0x96 = a^b^c, 0xE8 = majority): left to itself the compiler re-factors
+// the boolean network together with the XORs feeding it and ends up with ~50 % more LOP3s (measured in SASS), which
+// makes the ALU pipe the bottleneck instead of the XU pipe.
 __device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& sum, uint32_t& carry) {
-  sum = a ^ b ^ c;
-  carry = (a & b) | (a & c) | (b & c);
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(sum) : "r"(a), "r"(b), "r"(c));
+  asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(carry) : "r"(a), "r"(b), "r"(c));
 }
 
 // Packed key (distance << KEY_IDX_BITS) + tj of one descriptor pair.

@@ -283,24 +283,23 @@ __device__ __noinline__ bool inlier_exact(int mode, const double* __restrict__ M
 }
 
 // Returns the fast decision in `in` and whether it is uncertain.
+// Decision variable D (inlier <=> D > 0) and the bound g of its float32 rounding error (uncertain <=> |D| < g).
 template <int MODE>
-__device__ __forceinline__ bool classify(const float* __restrict__ A, const float4& p, const float4& q, float guard_j,
-                                         const ScoreConst& k, bool& in) {
+__device__ __forceinline__ void decision(const float* __restrict__ A, const float4& p, const float4& q, float guard_j,
+                                         const ScoreConst& k, float& D, float& g) {
   const float x = __fmaf_rn(A[2], p.z, __fmaf_rn(A[1], p.y, __fmaf_rn(A[0], p.x, A[9])));
   const float y = __fmaf_rn(A[5], p.z, __fmaf_rn(A[4], p.y, __fmaf_rn(A[3], p.x, A[10])));
   const float z = __fmaf_rn(A[8], p.z, __fmaf_rn(A[7], p.y, __fmaf_rn(A[6], p.x, A[11])));
   if (MODE == SOS_SCORE_EUCLID) {
     const float dx = __fsub_rn(x, q.x), dy = __fsub_rn(y, q.y), dz = __fsub_rn(z, q.z);
     const float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-    const float D = __fsub_rn(r2, k.thr_sq);
-    in = D < 0.f;
-    return fabsf(D) < guard_j;
+    D = __fsub_rn(k.thr_sq, r2);
+    g = guard_j;
   } else {
     const float s = __fmaf_rn(q.z, z, __fmaf_rn(q.y, y, __fmul_rn(q.x, x)));
     const float n2 = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
-    const float D = __fmaf_rn(s, fabsf(s), -__fmul_rn(k.cos_min_sq, n2));  // s|s| folds the s > 0 test into D
-    in = D > 0.f;
-    return fabsf(D) < __fmaf_rn(k.guard_rel, n2, guard_j);
+    D = __fmaf_rn(s, fabsf(s), -__fmul_rn(k.cos_min_sq, n2));  // s|s| folds the s > 0 test into D
+    g = __fmaf_rn(k.guard_rel, n2, guard_j);
   }
 }
 
@@ -315,42 +314,130 @@ __device__ __forceinline__ float guard_of(int mode, float px, float py, float pz
 }
 
 constexpr int RS_THREADS = 128;
-constexpr int RS_HPT = 4;                       // hypotheses per thread
+constexpr int RS_HPT = 4;                       // hypotheses per thread = 2 packed pairs
 constexpr int RS_TILE_H = RS_THREADS * RS_HPT;  // hypotheses per block
-constexpr int RS_CHUNK = 512;                   // correspondences per block (2 x float4 each = 16 KB)
-constexpr int RS_QCAP = 2048;                   // deferred exact evaluations per block (expected: a few dozen)
+constexpr int RS_CHUNK = 512;                   // correspondences per block (64 B each in shared memory)
+constexpr int RS_BATCH = 32;                    // correspondences per branch-free batch
+constexpr int RS_QCAP = 2048;                   // deferred (batch, hypothesis) re-evaluations per block (expected: a few)
 
-// A thread owns RS_HPT hypotheses (12 registers each) and walks the block's chunk of correspondences in shared
-// memory; every lane reads the SAME correspondence (broadcast LDS.128 x2).  The scoring transform depends on the
-// camera of the correspondence: the stacked list is camera-sorted (top view first, pose_est_tools.py:752-778), so the
-// transforms are reloaded at most once per chunk, at the block-uniform point where the camera index changes.
-// Pairs whose float32 decision is uncertain are queued and re-decided in float64 after the loop.
+// Blackwell packed FP32: one FFMA2 / FMUL2 / FADD2 instruction does two IEEE float32 operations on a 64-bit register
+// pair (SASS FFMA2 / FMUL2 / FADD2, sm_100+).  Each lane rounds exactly like fmaf / fmul / fadd, so the guard-band
+// analysis above is unchanged; the point is the halved instruction-issue count (the scalar kernel was issue bound).
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)), "l"(reinterpret_cast<uint64_t&>(c)));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 fabs2(float2 a) {
+  return make_float2(fabsf(a.x), fabsf(a.y));
+}
+// sign bit of a float as 0 / 1 (1 for negative, -0 and negative NaN)
+__device__ __forceinline__ int neg_bit(float v) { return (int)(__float_as_uint(v) >> 31); }
+
+// Shared-memory record of one correspondence: every component duplicated so that one LDS.128 hands the packed
+// arithmetic its (v, v) operands without any register shuffling.  q holds p_cur NEGATED (EUCLID) or f_cur (BEARING).
+struct __align__(16) PointRec {
+  float2 px, py;  // 16 B
+  float2 pz, g;   // additive term of t = D - g:  thr^2 - guard_j (EUCLID), -guard_j (BEARING)
+  float2 qx, qy;
+  float2 qz, pad; // additive term of u = D + g:  thr^2 + guard_j (EUCLID), +guard_j (BEARING)
+};
+
+// Decision variable of two hypotheses (packed lanes) for one correspondence: returns t ~ D - g and u ~ D + g.
+// certain inlier <=> t > 0, certain outlier <=> u < 0 (i.e. D < -g); anything else is uncertain.
+template <int MODE>
+__device__ __forceinline__ void decision2(const float2* __restrict__ A, const PointRec& c, const float2 k_a, const float2 k_b,
+                                          float2& t, float2& u) {
+  const float2 x = ffma2(A[2], c.pz, ffma2(A[1], c.py, ffma2(A[0], c.px, A[9])));
+  const float2 y = ffma2(A[5], c.pz, ffma2(A[4], c.py, ffma2(A[3], c.px, A[10])));
+  const float2 z = ffma2(A[8], c.pz, ffma2(A[7], c.py, ffma2(A[6], c.px, A[11])));
+  if (MODE == SOS_SCORE_EUCLID) {
+    const float2 dx = fadd2(x, c.qx), dy = fadd2(y, c.qy), dz = fadd2(z, c.qz);  // q = -p_cur
+    const float2 r2 = ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx)));
+    // D = thr^2 - r2, g = guard_j: the record carries thr^2 - g and thr^2 + g (k_b = -1)
+    t = ffma2(r2, k_b, c.g);
+    u = ffma2(r2, k_b, c.pad);
+  } else {
+    const float2 s = ffma2(c.qz, z, ffma2(c.qy, y, fmul2(c.qx, x)));
+    const float2 n2 = ffma2(z, z, ffma2(y, y, fmul2(x, x)));
+    const float2 sa = fabs2(s);
+    // D = s|s| - c^2 n2, g = g_rel n2 + guard_j:  t = s|s| - (c^2 + g_rel) n2 - guard_j,  u = s|s| - (c^2 - g_rel) n2 + guard_j
+    // (k_a = -(c^2 + g_rel), k_b = -(c^2 - g_rel); the record carries -guard_j and +guard_j)
+    t = ffma2(s, sa, ffma2(n2, k_a, c.g));
+    u = ffma2(s, sa, ffma2(n2, k_b, c.pad));
+  }
+}
+
+// A thread owns RS_HPT hypotheses as RS_HPT/2 packed pairs (24 registers per pair) and walks the block's chunk of
+// correspondences in shared memory; every lane reads the SAME correspondence (broadcast LDS.128 x4).  The stacked
+// correspondence list is camera-sorted (top view first, pose_est_tools.py:752-778): at most one camera switch per chunk,
+// found during staging, so the transforms are loaded once per camera run.  The loop body is branch free: per hypothesis
+// two counters, nlo += sign(D - g) and nhi += sign(D + g); nlo == nhi over a batch of RS_BATCH correspondences means no
+// pair of the batch was inside the guard band.  Otherwise the (batch, hypothesis) is queued and re-decided after the
+// loop, uncertain pairs in float64 — keeping that path out of the loop keeps the warps converged (measured: the
+// in-loop version ran with 24 of 32 lanes active).
 template <int MODE>
 __global__ void __launch_bounds__(RS_THREADS)
 score_kernel(const float* __restrict__ p_ref, const float* __restrict__ q_arr, const uint8_t* __restrict__ cam,
              const int32_t* __restrict__ n_arr, int cap, const HypRec* __restrict__ recs, int n_hyp, ScoreConst k,
              const __grid_constant__ Rig rig, int32_t* __restrict__ counts) {
-  __shared__ float4 sp[RS_CHUNK];  // p_ref.xyz, guard (sign bit = camera index)
-  __shared__ float4 sq[RS_CHUNK];  // p_cur.xyz (EUCLID) or f_cur.xyz (BEARING)
+  __shared__ PointRec pts[RS_CHUNK];
+  __shared__ unsigned char pcam[RS_CHUNK];
+  __shared__ float pguard[RS_CHUNK];
   __shared__ uint32_t queue[RS_QCAP];
-  __shared__ int queue_n;
+  __shared__ int queue_n, switch_count, switch_at;
   const int b = blockIdx.z;
   const int n = n_arr[b];
   const int j0 = blockIdx.y * RS_CHUNK;
   if (j0 >= n) return;
   const int nj = min(RS_CHUNK, n - j0);
   const bool multi_cam = rig.n_cams > 1 && cam != nullptr;
-  if (threadIdx.x == 0) queue_n = 0;
+  if (threadIdx.x == 0) {
+    queue_n = 0;
+    switch_count = 0;
+    switch_at = 0;
+  }
+  __syncthreads();
+  const float qsign = MODE == SOS_SCORE_EUCLID ? -1.f : 1.f;
   for (int j = threadIdx.x; j < nj; j += RS_THREADS) {
     const size_t o = ((size_t)b * cap + j0 + j) * 3;
     const int c = multi_cam ? (cam[(size_t)b * cap + j0 + j] ? 1 : 0) : 0;
+    if (multi_cam && j > 0 && ((cam[(size_t)b * cap + j0 + j - 1] ? 1 : 0) != c)) {
+      atomicAdd(&switch_count, 1);
+      switch_at = j;  // only read when there is exactly one switch
+    }
     const float px = p_ref[o], py = p_ref[o + 1], pz = p_ref[o + 2];
     const float qx = q_arr[o], qy = q_arr[o + 1], qz = q_arr[o + 2];
     const float g = guard_of(MODE, px, py, pz, qx, qy, qz, k.thr);
-    sp[j] = make_float4(px, py, pz, c ? -g : g);
-    sq[j] = make_float4(qx, qy, qz, 0.f);
+    PointRec r;
+    const float base = MODE == SOS_SCORE_EUCLID ? k.thr_sq : 0.f;
+    r.px = make_float2(px, px); r.py = make_float2(py, py); r.pz = make_float2(pz, pz);
+    r.g = make_float2(base - g, base - g);
+    r.qx = make_float2(qsign * qx, qsign * qx); r.qy = make_float2(qsign * qy, qsign * qy);
+    r.qz = make_float2(qsign * qz, qsign * qz);
+    r.pad = make_float2(base + g, base + g);
+    pts[j] = r;
+    pcam[j] = (unsigned char)c;
+    pguard[j] = g;
   }
-  float A[RS_HPT][12];
+  constexpr int NP = RS_HPT / 2;
+  float2 A[NP][12];
   int cnt[RS_HPT];
   const HypRec* rec[RS_HPT];
 #pragma unroll
@@ -360,31 +447,57 @@ score_kernel(const float* __restrict__ p_ref, const float* __restrict__ q_arr, c
     rec[r] = recs + (size_t)b * n_hyp + h;
     cnt[r] = 0;
   }
+  const float ka = MODE == SOS_SCORE_EUCLID ? 0.f : -(k.cos_min_sq + k.guard_rel);
+  const float kb = MODE == SOS_SCORE_EUCLID ? -1.f : -(k.cos_min_sq - k.guard_rel);
+  const float2 k_a = make_float2(ka, ka), k_b = make_float2(kb, kb);
   __syncthreads();
-  int cur_cam = -1;
+  const int n_switch = switch_count;
+  const int split = n_switch == 0 ? nj : (n_switch == 1 ? switch_at : 0);
+  // generic camera order (n_switch > 1): every run of equal camera index is handled like a sorted run
+  int j_begin = 0;
+  while (j_begin < nj) {
+    const int c = pcam[j_begin];
+    int j_end;
+    if (n_switch <= 1) {
+      j_end = (j_begin < split) ? split : nj;
+    } else {
+      j_end = j_begin + 1;
+      while (j_end < nj && pcam[j_end] == c) ++j_end;
+    }
+#pragma unroll
+    for (int pr = 0; pr < NP; ++pr)
+#pragma unroll
+      for (int i = 0; i < 12; ++i)
+        A[pr][i] = make_float2(__ldg(&rec[2 * pr]->xf[c][i]), __ldg(&rec[2 * pr + 1]->xf[c][i]));
+    for (int jb = j_begin; jb < j_end; jb += RS_BATCH) {
+      const int je = min(j_end, jb + RS_BATCH);
+      int nlo[RS_HPT], nhi[RS_HPT];
+#pragma unroll
+      for (int r = 0; r < RS_HPT; ++r) nlo[r] = nhi[r] = 0;
 #pragma unroll 2
-  for (int j = 0; j < nj; ++j) {
-    const float4 p = sp[j];
-    const float4 q = sq[j];
-    const int c = (int)(__float_as_uint(p.w) >> 31);
-    if (c != cur_cam) {  // block-uniform
-      cur_cam = c;
+      for (int j = jb; j < je; ++j) {
+        const PointRec pt = pts[j];
 #pragma unroll
-      for (int r = 0; r < RS_HPT; ++r)
-#pragma unroll
-        for (int i = 0; i < 12; ++i) A[r][i] = __ldg(&rec[r]->xf[c][i]);
-    }
-    const float g = fabsf(p.w);
-#pragma unroll
-    for (int r = 0; r < RS_HPT; ++r) {
-      bool in;
-      if (classify<MODE>(A[r], p, q, g, k, in)) {
-        const int slot = atomicAdd(&queue_n, 1);
-        if (slot < RS_QCAP) queue[slot] = ((uint32_t)j << 16) | ((uint32_t)r << 8) | threadIdx.x;
-        in = false;  // counted by the deferred pass
+        for (int pr = 0; pr < NP; ++pr) {
+          float2 t, u;
+          decision2<MODE>(A[pr], pt, k_a, k_b, t, u);
+          nlo[2 * pr] += neg_bit(t.x);
+          nlo[2 * pr + 1] += neg_bit(t.y);
+          nhi[2 * pr] += neg_bit(u.x);
+          nhi[2 * pr + 1] += neg_bit(u.y);
+        }
       }
-      cnt[r] += in ? 1 : 0;
+#pragma unroll
+      for (int r = 0; r < RS_HPT; ++r) {
+        if (nlo[r] == nhi[r]) {
+          cnt[r] += (je - jb) - nlo[r];  // all decided: inliers = pairs whose D - g is not negative
+        } else {  // rare; two instructions long so that the warp stays converged
+          const int slot = atomicAdd(&queue_n, 1);
+          if (slot < RS_QCAP) queue[slot] = ((uint32_t)jb << 16) | ((uint32_t)(je - jb) << 10) | ((uint32_t)r << 8) | threadIdx.x;
+        }
+      }
     }
+    j_begin = j_end;
   }
   __syncthreads();
   int nq = queue_n;
@@ -395,8 +508,10 @@ score_kernel(const float* __restrict__ p_ref, const float* __restrict__ q_arr, c
       cnt[r] = 0;
 #pragma unroll 1
       for (int j = 0; j < nj; ++j) {
-        const float4 p = sp[j];
-        cnt[r] += inlier_exact(MODE, rec[r]->pose64, rig, (int)(__float_as_uint(p.w) >> 31), p, sq[j], k.thr) ? 1 : 0;
+        const PointRec pt = pts[j];
+        const float4 p = make_float4(pt.px.x, pt.py.x, pt.pz.x, 0.f);
+        const float4 q = make_float4(qsign * pt.qx.x, qsign * pt.qy.x, qsign * pt.qz.x, 0.f);
+        cnt[r] += inlier_exact(MODE, rec[r]->pose64, rig, (int)pcam[j], p, q, k.thr) ? 1 : 0;
       }
     }
   }
@@ -405,15 +520,29 @@ score_kernel(const float* __restrict__ p_ref, const float* __restrict__ q_arr, c
     const int h = blockIdx.x * RS_TILE_H + r * RS_THREADS + threadIdx.x;
     if (h < n_hyp && cnt[r] != 0) atomicAdd(&counts[(size_t)b * n_hyp + h], cnt[r]);
   }
+  // deferred pass: queue entry = (first point, length <= RS_BATCH, hypothesis slot r, owning thread); every pair of the
+  // entry is re-classified with the scalar form of the same arithmetic, uncertain ones by the exact float64 path
   for (int e = threadIdx.x; e < nq; e += RS_THREADS) {
     const uint32_t v = queue[e];
-    const int j = (int)(v >> 16), r = (int)((v >> 8) & 0xFF), t = (int)(v & 0xFF);
+    const int jb = (int)(v >> 16), len = (int)((v >> 10) & 0x3F), r = (int)((v >> 8) & 0x3), t = (int)(v & 0xFF);
     const int h = blockIdx.x * RS_TILE_H + r * RS_THREADS + t;
     if (h >= n_hyp) continue;
-    const float4 p = sp[j];
-    const int c = (int)(__float_as_uint(p.w) >> 31);
-    if (inlier_exact(MODE, recs[(size_t)b * n_hyp + h].pose64, rig, c, p, sq[j], k.thr))
-      atomicAdd(&counts[(size_t)b * n_hyp + h], 1);
+    const HypRec* hr = recs + (size_t)b * n_hyp + h;
+    int add = 0;
+    for (int j = jb; j < jb + len; ++j) {
+      const PointRec pt = pts[j];
+      const float4 p = make_float4(pt.px.x, pt.py.x, pt.pz.x, 0.f);
+      const float4 q = make_float4(qsign * pt.qx.x, qsign * pt.qy.x, qsign * pt.qz.x, 0.f);
+      const int c = (int)pcam[j];
+      float Ax[12];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) Ax[i] = __ldg(&hr->xf[c][i]);
+      float D, g;
+      decision<MODE>(Ax, p, q, pguard[j], k, D, g);
+      if (fabsf(D) < g) add += inlier_exact(MODE, hr->pose64, rig, c, p, q, k.thr) ? 1 : 0;
+      else add += (D > 0.f) ? 1 : 0;
+    }
+    if (add) atomicAdd(&counts[(size_t)b * n_hyp + h], add);
   }
 }
 
@@ -515,10 +644,10 @@ __global__ void arun_batch_kernel(const double* __restrict__ v0, const double* _
 }
 
 // Arun refit over the inlier set: one block per problem, float64 accumulation, two passes (centroids, covariance).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 refit_kernel(const float* __restrict__ p_ref, const float* __restrict__ p_cur, const uint8_t* __restrict__ mask,
              const int32_t* __restrict__ n_arr, int cap, float* __restrict__ pose, int32_t* __restrict__ n_used) {
-  __shared__ double red[8][16];
+  __shared__ double red[32][16];
   __shared__ double cen[6];
   __shared__ int cnt_sh;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -540,7 +669,7 @@ refit_kernel(const float* __restrict__ p_ref, const float* __restrict__ p_cur, c
   __syncthreads();
   if (tid == 0) {
     double tot[7];
-    for (int i = 0; i < 7; ++i) { tot[i] = 0; for (int w = 0; w < 8; ++w) tot[i] += red[w][i]; }
+    for (int i = 0; i < 7; ++i) { tot[i] = 0; for (int w = 0; w < 32; ++w) tot[i] += red[w][i]; }
     cnt_sh = (int)tot[6];
     for (int i = 0; i < 6; ++i) cen[i] = tot[6] > 0 ? tot[i] / tot[6] : 0.0;
   }
@@ -564,7 +693,7 @@ refit_kernel(const float* __restrict__ p_ref, const float* __restrict__ p_cur, c
   __syncthreads();
   if (tid == 0) {
     double Hm[9], R[9];
-    for (int i = 0; i < 9; ++i) { Hm[i] = 0; for (int w = 0; w < 8; ++w) Hm[i] += red[w][i]; }
+    for (int i = 0; i < 9; ++i) { Hm[i] = 0; for (int w = 0; w < 32; ++w) Hm[i] += red[w][i]; }
     const bool ok = cnt_sh >= 3 && kabsch_rotation(Hm, R);
     if (n_used) n_used[b] = ok ? cnt_sh : -1;
     for (int r = 0; r < 3; ++r) {
@@ -730,7 +859,7 @@ extern "C" int sos_refit_inliers(sos_ctx* ctx, const float* p_ref, const float* 
   if (n_problems == 0) return SOS_OK;
   SOS_CHECK_ARG(p_ref && p_cur && inlier_mask && n && pose, "NULL array");
   SOS_CUDA(cudaSetDevice(ctx->device));
-  refit_kernel<<<n_problems, 256, 0, ctx->stream>>>(p_ref, p_cur, inlier_mask, n, cap, pose, n_used);
+  refit_kernel<<<n_problems, 1024, 0, ctx->stream>>>(p_ref, p_cur, inlier_mask, n, cap, pose, n_used);
   SOS_LAUNCHED(ctx);
   return SOS_OK;
 }
