@@ -311,7 +311,7 @@ def run_gpu(args, rank, local_rank, world):
                             "unit": "TFLOP/s", "frac": fl / (t * 1e-3) / 1e12 / ffma_peak, "ms": t,
                             "peak_source": "FFMA microbenchmark run in this process",
                             "hypothesis_point_pairs": float(w.cfg.n_hyp) * float(n_corr.sum()), "traffic": None}
-    t = k_ms("sos_stereo_lift_triangulate#0")
+    t = k_ms("sos_stereo_lift_triangulate#0") + k_ms("sos_stereo_lift_triangulate#1")  # geometry + compaction
     lt_bytes = 53.0 * float(buf["st_pair_count"].sum())
     roof["lift_triangulate"] = {"kernel": "stereo_lift_triangulate_kernel", "bound": "hbm", "achieved": lt_bytes / (t * 1e-3) / 1e9,
                                 "peak": hbm_peak, "unit": "GB/s", "frac": lt_bytes / (t * 1e-3) / 1e9 / hbm_peak, "ms": t,

@@ -84,6 +84,7 @@ int sos_memset(sos_ctx* ctx, void* dst_dev, int value, size_t bytes);
  *   bits 32..36  ax  = cvRound(32*map_x) & 31        bits 37..41  ay = cvRound(32*map_y) & 31
  *   bits 48..51  tap i lies inside the source image  (i = 0:(y0,x0) 1:(y0,x0+1) 2:(y0+1,x0) 3:(y0+1,x0+1))
  *   bits 52..55  tap i is inside AND its mask byte is non-zero (mask == NULL: same as inside)
+ *   bit  56      all four taps usable and the 16-byte windows of the 3-channel fast path end inside the image
  * NaN / |32*x| >= 2^31 map to INT_MIN exactly as cvtps2dq does inside cv::remap. */
 typedef uint64_t sos_lut_entry;
 
@@ -224,6 +225,7 @@ int sos_triangulate_midpoint_f64(sos_ctx* ctx, const double* az1, const double* 
 int sos_stereo_lift_triangulate(sos_ctx* ctx, const double* pano_top, const double* pano_bot, const float* px_top,
                                 const float* px_bot, const int32_t* pair_q, const int32_t* pair_t,
                                 const int32_t* pair_count, const int32_t* seg_off, int n_frames, int segs_per_frame,
+                                int max_pairs_per_seg /* HOST bound of any pair_count */, int pair_rows /* rows of pair_q */,
                                 const double* f1, const double* f2, double rmin, double rmax, int homogeneous_norm,
                                 int cap_per_frame, float* out_uv_top, float* out_uv_bot, float* out_b_top,
                                 float* out_b_bot, float* out_xyz, int32_t* out_src_top, int32_t* out_src_bot,

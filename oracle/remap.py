@@ -61,8 +61,11 @@ def lut_pack_spec(map_x: np.ndarray, map_y: np.ndarray, src_hw, mask: np.ndarray
         else:
             lv = ins & (mask[np.clip(y, 0, h - 1), np.clip(x, 0, w - 1)] != 0)
         live |= lv.astype(np.uint64) << np.uint64(tap)
+    p1 = ((y0 + 1) * w + x0) * 3
+    wide3 = ((live == 15) & (p1 + 16 <= h * w * 3)).astype(np.uint64)
     lo = (x0 & 0xFFFF).astype(np.uint64) | ((y0 & 0xFFFF).astype(np.uint64) << np.uint64(16))
-    hi = ax.astype(np.uint64) | (ay.astype(np.uint64) << np.uint64(5)) | (inside << np.uint64(16)) | (live << np.uint64(20))
+    hi = (ax.astype(np.uint64) | (ay.astype(np.uint64) << np.uint64(5)) | (inside << np.uint64(16)) | (live << np.uint64(20))
+          | (wide3 << np.uint64(24)))
     return lo | (hi << np.uint64(32))
 
 

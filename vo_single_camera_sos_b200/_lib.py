@@ -47,7 +47,7 @@ PROTOTYPES = {
     "sos_triangulate_midpoint_f64": (I, [c_ctx, P, P, P, P, I, P, P, D, D, I, P, P]),
     "sos_lift_gum": (I, [c_ctx, P, P, I, P, P, P]),
     "sos_triangulate_midpoint": (I, [c_ctx, P, P, P, P, I, P, P, D, D, I, P, P]),
-    "sos_stereo_lift_triangulate": (I, [c_ctx, P, P, P, P, P, P, P, P, I, I, P, P, D, D, I, I, P, P, P, P, P, P, P, P]),
+    "sos_stereo_lift_triangulate": (I, [c_ctx, P, P, P, P, P, P, P, P, I, I, I, I, P, P, D, D, I, I, P, P, P, P, P, P, P, P]),
     "sos_rgbd_depth_to_z": (I, [c_ctx, P, P, I, I, I, P]),
     "sos_rgbd_backproject": (I, [c_ctx, P, P, I, I, I, P, P, I, D, D, P, P, P]),
     "sos_arun_batch": (I, [c_ctx, P, P, I, I, I, P, P]),

@@ -217,7 +217,8 @@ int enqueue_step(sos_frontend* fe, const uint8_t* omni, const float* px_top, con
   if (rc) return rc;
   // steps 3+4 into store slots 1..B
   rc = sos_stereo_lift_triangulate(ctx, c.pano_top, c.pano_bot, px_top, px_bot, d.st_pair_q, d.st_pair_t, d.st_pair_count,
-                                   d.st_q_start, B, nb, c.f_top, c.f_bot, c.min_range, c.max_range, c.homogeneous_norm, cap,
+                                   d.st_q_start, B, nb, c.max_feat_per_bucket, B * F, c.f_top, c.f_bot, c.min_range,
+                                   c.max_range, c.homogeneous_norm, cap,
                                    d.uv_top + (size_t)cap * 2, d.uv_bot + (size_t)cap * 2, d.b_top + (size_t)cap * 3,
                                    d.b_bot + (size_t)cap * 3, d.xyz + (size_t)cap * 3, d.src_top + cap, d.src_bot + cap,
                                    d.n + 1);

@@ -105,8 +105,9 @@ __global__ void triangulate_kernel(const T* __restrict__ az1, const T* __restric
 }
 
 // ---- fused steps 3+4 with ordered compaction -------------------------------------------------------------------
-// One block per frame.  Segments of the frame are walked in order; within a segment pairs are taken in chunks of
-// blockDim, survivors are appended in pair order (block-wide exclusive scan of the keep flags).
+// Two kernels: (A) one thread per matched pair does the float64 geometry (fully parallel over all frames and buckets)
+// and parks bearings / xyz / keep flag in scratch; (B) one block per frame walks its segments in order and appends the
+// survivors to the frame's store (block-wide ballot scan), which is pure data movement.
 struct StereoArgs {
   PanoP pano_top, pano_bot;
   const float2 *px_top, *px_bot;
@@ -116,72 +117,85 @@ struct StereoArgs {
   double rmin, rmax;
   int homo;
   int cap;
+  float* tmp;        // [pair_rows, 9]: b_top, b_bot, xyz
+  uint8_t* tmp_keep; // [pair_rows]
+  int32_t* seg_keep; // [n_segments]: survivors per segment (zeroed before the geometry kernel)
   float2 *out_uv_top, *out_uv_bot;
   float *out_b_top, *out_b_bot, *out_xyz;
   int32_t *out_src_top, *out_src_bot, *out_n;
 };
 
-constexpr int ST_THREADS = 1024;  // one block per frame: wide block, the float64 transcendental math is latency bound
+__global__ void __launch_bounds__(256) stereo_geometry_kernel(StereoArgs a) {
+  const int s = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.pair_count[s]) return;
+  const int row = a.seg_off[s] + k;
+  const int rq = a.pair_q[row];  // bottom-view feature row (query, camera_models.py:3042)
+  const int rt = a.pair_t[row];  // top-view feature row (train)
+  const float2 mt = a.px_top[rt], mb = a.px_bot[rq];
+  double az1, el1, az2, el2;
+  pano_pixel_to_angles(a.pano_top, (double)mt.x, (double)mt.y, az1, el1);
+  pano_pixel_to_angles(a.pano_bot, (double)mb.x, (double)mb.y, az2, el2);
+  const Vec3 bt = angles_to_sphere(az1, el1), bb = angles_to_sphere(az2, el2);
+  const Vec3 P = triangulate_midpoint(az1, el1, az2, el2, a.f1, a.f2);
+  float* t = a.tmp + (size_t)row * 9;
+  t[0] = (float)bt.x; t[1] = (float)bt.y; t[2] = (float)bt.z;
+  t[3] = (float)bb.x; t[4] = (float)bb.y; t[5] = (float)bb.z;
+  t[6] = (float)P.x; t[7] = (float)P.y; t[8] = (float)P.z;
+  const bool keep = range_ok(P, a.rmin, a.rmax, a.homo);
+  a.tmp_keep[row] = keep ? 1 : 0;
+  const unsigned vote = __ballot_sync(__activemask(), keep);
+  if (keep && (threadIdx.x & 31) == (__ffs(vote) - 1)) atomicAdd(&a.seg_keep[s], __popc(vote));
+}
 
-__global__ void __launch_bounds__(ST_THREADS) stereo_lift_triangulate_kernel(StereoArgs a) {
+constexpr int ST_THREADS = 1024;
+
+// One block per SEGMENT: its survivors start after those of the earlier segments of the same frame.
+__global__ void __launch_bounds__(ST_THREADS) stereo_compact_kernel(StereoArgs a) {
   __shared__ int warp_sums[ST_THREADS / 32];
-  __shared__ int base_sh;
-  const int frame = blockIdx.x;
+  const int s = blockIdx.x;
+  const int frame = s / a.segs_per_frame;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) base_sh = 0;
-  __syncthreads();
-  for (int s = frame * a.segs_per_frame; s < (frame + 1) * a.segs_per_frame; ++s) {
-    const int off = a.seg_off[s];
-    const int cnt = a.pair_count[s];
-    for (int k0 = 0; k0 < cnt; k0 += ST_THREADS) {
-      const int k = k0 + tid;
-      bool keep = false;
-      int rq = 0, rt = 0;
-      float2 mt = {0.f, 0.f}, mb = {0.f, 0.f};
-      Vec3 bt = {0, 0, 0}, bb = {0, 0, 0}, P = {0, 0, 0};
-      if (k < cnt) {
-        rq = a.pair_q[off + k];  // bottom-view feature row (query, camera_models.py:3042)
-        rt = a.pair_t[off + k];  // top-view feature row (train)
-        mt = a.px_top[rt];
-        mb = a.px_bot[rq];
-        double az1, el1, az2, el2;
-        pano_pixel_to_angles(a.pano_top, (double)mt.x, (double)mt.y, az1, el1);
-        pano_pixel_to_angles(a.pano_bot, (double)mb.x, (double)mb.y, az2, el2);
-        bt = angles_to_sphere(az1, el1);
-        bb = angles_to_sphere(az2, el2);
-        P = triangulate_midpoint(az1, el1, az2, el2, a.f1, a.f2);
-        keep = range_ok(P, a.rmin, a.rmax, a.homo);
-      }
-      const unsigned vote = __ballot_sync(0xFFFFFFFFu, keep);
-      if (lane == 0) warp_sums[warp] = __popc(vote);
-      __syncthreads();
-      int before = 0, total = 0;
+  int base = 0;
+  for (int e = frame * a.segs_per_frame; e < s; ++e) base += a.seg_keep[e];
+  if (s == (frame + 1) * a.segs_per_frame - 1 && tid == 0) a.out_n[frame] = min(base + a.seg_keep[s], a.cap);
+  const int off = a.seg_off[s];
+  const int cnt = a.pair_count[s];
+  for (int k0 = 0; k0 < cnt; k0 += ST_THREADS) {
+    const int k = k0 + tid;
+    const bool keep = (k < cnt) && a.tmp_keep[off + k] != 0;
+    const unsigned vote = __ballot_sync(0xFFFFFFFFu, keep);
+    if (lane == 0) warp_sums[warp] = __popc(vote);
+    __syncthreads();
+    int before = 0, total = 0;
 #pragma unroll
-      for (int w = 0; w < ST_THREADS / 32; ++w) {
-        const int c = warp_sums[w];
-        if (w < warp) before += c;
-        total += c;
-      }
-      const int base = base_sh;
-      if (keep) {
-        const int pos = base + before + __popc(vote & ((1u << lane) - 1u));
-        if (pos < a.cap) {
-          const size_t o = (size_t)frame * a.cap + pos;
-          a.out_uv_top[o] = mt;
-          a.out_uv_bot[o] = mb;
-          a.out_b_top[3 * o + 0] = (float)bt.x; a.out_b_top[3 * o + 1] = (float)bt.y; a.out_b_top[3 * o + 2] = (float)bt.z;
-          a.out_b_bot[3 * o + 0] = (float)bb.x; a.out_b_bot[3 * o + 1] = (float)bb.y; a.out_b_bot[3 * o + 2] = (float)bb.z;
-          a.out_xyz[3 * o + 0] = (float)P.x; a.out_xyz[3 * o + 1] = (float)P.y; a.out_xyz[3 * o + 2] = (float)P.z;
-          a.out_src_top[o] = rt;
-          a.out_src_bot[o] = rq;
-        }
-      }
-      __syncthreads();
-      if (tid == 0) base_sh = base + total;
-      __syncthreads();
+    for (int w = 0; w < ST_THREADS / 32; ++w) {
+      const int c = warp_sums[w];
+      if (w < warp) before += c;
+      total += c;
     }
+    if (keep) {
+      const int pos = base + before + __popc(vote & ((1u << lane) - 1u));
+      if (pos < a.cap) {
+        const size_t o = (size_t)frame * a.cap + pos;
+        const int row = off + k;
+        const int rq = a.pair_q[row], rt = a.pair_t[row];
+        const float* t = a.tmp + (size_t)row * 9;
+        a.out_uv_top[o] = a.px_top[rt];
+        a.out_uv_bot[o] = a.px_bot[rq];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          a.out_b_top[3 * o + c] = t[c];
+          a.out_b_bot[3 * o + c] = t[3 + c];
+          a.out_xyz[3 * o + c] = t[6 + c];
+        }
+        a.out_src_top[o] = rt;
+        a.out_src_bot[o] = rq;
+      }
+    }
+    base += total;
+    __syncthreads();
   }
-  if (tid == 0) a.out_n[frame] = min(base_sh, a.cap);
 }
 
 // ---- F3: GUM forward projection, gum.py:2512-2562, 1368-1385, 2942-2959 ----------------------------------------
@@ -394,12 +408,15 @@ extern "C" int sos_triangulate_midpoint_f64(sos_ctx* ctx, const double* az1, con
 extern "C" int sos_stereo_lift_triangulate(sos_ctx* ctx, const double* pano_top, const double* pano_bot,
                                            const float* px_top, const float* px_bot, const int32_t* pair_q,
                                            const int32_t* pair_t, const int32_t* pair_count, const int32_t* seg_off,
-                                           int n_frames, int segs_per_frame, const double* f1, const double* f2,
-                                           double rmin, double rmax, int homogeneous_norm, int cap_per_frame,
+                                           int n_frames, int segs_per_frame, int max_pairs_per_seg, int pair_rows,
+                                           const double* f1, const double* f2, double rmin, double rmax,
+                                           int homogeneous_norm, int cap_per_frame,
                                            float* out_uv_top, float* out_uv_bot, float* out_b_top, float* out_b_bot,
                                            float* out_xyz, int32_t* out_src_top, int32_t* out_src_bot, int32_t* out_n) {
   SOS_CHECK_ARG(ctx && pano_top && pano_bot && f1 && f2, "NULL argument");
-  SOS_CHECK_ARG(n_frames >= 0 && segs_per_frame >= 0 && cap_per_frame >= 0, "negative size");
+  SOS_CHECK_ARG(n_frames >= 0 && segs_per_frame >= 0 && cap_per_frame >= 0 && max_pairs_per_seg >= 0 && pair_rows >= 0,
+                "negative size");
+  SOS_CHECK_ARG((long long)n_frames * segs_per_frame <= 65535, "too many segments");
   if (n_frames == 0) return SOS_OK;
   SOS_CHECK_ARG(px_top && px_bot && pair_q && pair_t && pair_count && seg_off, "NULL input array");
   SOS_CHECK_ARG(out_uv_top && out_uv_bot && out_b_top && out_b_bot && out_xyz && out_src_top && out_src_bot && out_n,
@@ -416,7 +433,26 @@ extern "C" int sos_stereo_lift_triangulate(sos_ctx* ctx, const double* pano_top,
   a.out_uv_top = (float2*)out_uv_top; a.out_uv_bot = (float2*)out_uv_bot;
   a.out_b_top = out_b_top; a.out_b_bot = out_b_bot; a.out_xyz = out_xyz;
   a.out_src_top = out_src_top; a.out_src_bot = out_src_bot; a.out_n = out_n;
-  stereo_lift_triangulate_kernel<<<n_frames, ST_THREADS, 0, ctx->stream>>>(a);
+  void* ws = nullptr;
+  const size_t tmp_bytes = sos_align_up((size_t)pair_rows * 9 * sizeof(float), 256);
+  const int n_segs = n_frames * segs_per_frame;
+  const size_t keep_bytes = sos_align_up((size_t)pair_rows + 1, 256);
+  const int rc = sos_arena_get(ctx, tmp_bytes + keep_bytes + (size_t)(n_segs + 1) * sizeof(int32_t) + 256, &ws);
+  if (rc != SOS_OK) return rc;
+  a.tmp = (float*)ws;
+  a.tmp_keep = (uint8_t*)ws + tmp_bytes;
+  a.seg_keep = (int32_t*)((uint8_t*)ws + tmp_bytes + keep_bytes);
+  if (n_segs == 0) {
+    SOS_CUDA(cudaMemsetAsync(out_n, 0, (size_t)n_frames * sizeof(int32_t), ctx->stream));
+    return SOS_OK;
+  }
+  SOS_CUDA(cudaMemsetAsync(a.seg_keep, 0, (size_t)n_segs * sizeof(int32_t), ctx->stream));
+  if (max_pairs_per_seg > 0) {
+    dim3 grid(sos_div_up(max_pairs_per_seg, 256), n_segs);
+    stereo_geometry_kernel<<<grid, 256, 0, ctx->stream>>>(a);
+    SOS_LAUNCHED(ctx);
+  }
+  stereo_compact_kernel<<<n_segs, ST_THREADS, 0, ctx->stream>>>(a);
   SOS_LAUNCHED(ctx);
   return SOS_OK;
 }

@@ -50,8 +50,14 @@ lut_pack_kernel(const T* __restrict__ map_x, const T* __restrict__ map_y, int n,
       if (mask == nullptr || mask[(size_t)y * src_w + x] != 0) live |= 1u << tap;
     }
   }
+  // bit 56: all four taps usable AND the two 16-byte windows the 3-channel fast path loads stay inside the image
+  uint32_t wide3 = 0;
+  if (live == 15u) {
+    const long long p1 = (((long long)y0 + 1) * src_w + x0) * 3;
+    wide3 = (p1 + 16 <= (long long)src_h * src_w * 3) ? 1u : 0u;
+  }
   const uint64_t lo = (uint32_t)(x0 & 0xFFFF) | ((uint32_t)(y0 & 0xFFFF) << 16);
-  const uint64_t hi = ax | (ay << 5) | (inside << 16) | (live << 20);
+  const uint64_t hi = ax | (ay << 5) | (inside << 16) | (live << 20) | (wide3 << 24);
   lut[i] = lo | (hi << 32);
 }
 
@@ -193,6 +199,88 @@ remap_kernel(const uint8_t* __restrict__ src, const uint8_t* __restrict__ wide_e
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 3-channel kernel (the hot case).  A warp produces 128 consecutive pixels of one panorama row in 4 passes; in a pass
+// LANE l owns pixel 32*pass + l, so the 32 source positions of one load instruction are neighbours on the mirror
+// circle and share a handful of 32-byte sectors (the 4-pixels-per-thread layout touched ~28 sectors per request and
+// saturated L1).  Per pixel: 4 aligned LDG.64 + 32-bit funnel shifts give the two 6-byte tap pairs; horizontal
+// interpolation is one PRMT + DP4A per row and channel, the vertical one a DP2A:  V + 512 = wt*h0 + ay*h1 + 512,
+// dst = (V + 512) >> 10  ==  (sum_i w_i p_i + 16384) >> 15 of cv::remap because sum_i w_i p_i = 32 V exactly.
+// Results go through shared memory so that the row segment leaves as 16-byte stores.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load6_32(const uint8_t* __restrict__ p, uint32_t& lo, uint32_t& hi) {
+  const uintptr_t a = (uintptr_t)p;
+  const uint2* w = (const uint2*)(a & ~(uintptr_t)7);
+  const uint2 w0 = __ldg(w), w1 = __ldg(w + 1);
+  const uint32_t o = (uint32_t)a & 7u, sh = (o & 3u) * 8u;
+  const bool k = o >= 4u;
+  const uint32_t A = k ? w0.y : w0.x, B = k ? w1.x : w0.y, C = k ? w1.y : w1.x;
+  lo = __funnelshift_r(A, B, sh);
+  hi = __funnelshift_r(B, C, sh);
+}
+
+constexpr int R3_WARPS = 8;
+constexpr int R3_COLS = 128;
+
+__global__ void __launch_bounds__(R3_WARPS * 32)
+remap3_kernel(const uint8_t* __restrict__ src, int wide_ok, int src_h, int src_w, const uint64_t* __restrict__ lut, int views,
+              int rows, int cols, RemapConst k, uint8_t* __restrict__ dst) {
+  __shared__ __align__(16) uint8_t sout[R3_WARPS][R3_COLS * 3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col0 = blockIdx.x * R3_COLS;
+  const int row = blockIdx.y * R3_WARPS + warp;
+  if (row >= rows || col0 >= cols) return;  // whole warps leave together; only __syncwarp below
+  const int img = blockIdx.z;
+  const int view = img % views, b = img / views;
+  const uint8_t* s = src + (size_t)b * src_h * src_w * 3;
+  const size_t px0 = (size_t)row * cols + col0;
+  const uint64_t* l = lut + (size_t)view * rows * cols + px0;
+  uint8_t* d = dst + ((size_t)img * rows * cols + px0) * 3;
+  const int npx = min(R3_COLS, cols - col0);
+  const size_t row_bytes = (size_t)src_w * 3;
+  uint8_t* so = sout[warp];
+#pragma unroll
+  for (int pass = 0; pass < R3_COLS / 32; ++pass) {
+    const int c = pass * 32 + lane;
+    if (c < npx) {
+      const uint64_t e = __ldg(l + c);
+      const uint32_t hi = (uint32_t)(e >> 32);
+      uint32_t o[3];
+      if (wide_ok && (hi & (1u << 24))) {
+        const int x0 = (int)(int16_t)(e & 0xFFFF), y0 = (int)(int16_t)((e >> 16) & 0xFFFF);
+        const uint32_t ax = hi & 31u, ay = (hi >> 5) & 31u;
+        const uint8_t* p = s + ((size_t)y0 * src_w + x0) * 3;
+        uint32_t r0l, r0h, r1l, r1h;
+        load6_32(p, r0l, r0h);
+        load6_32(p + row_bytes, r1l, r1h);
+        const uint32_t wx = (32u - ax) | (ax << 8), wy = (32u - ay) | (ay << 8);
+        // channel c: bytes c (left tap) and c + 3 (right tap) of the 6-byte group -> PRMT selectors 0x30, 0x41, 0x52
+        const uint32_t h0 = __dp4a(__byte_perm(r0l, r0h, 0x0030), wx, __dp4a(__byte_perm(r1l, r1h, 0x0030), wx, 0u) << 16);
+        const uint32_t h1 = __dp4a(__byte_perm(r0l, r0h, 0x0041), wx, __dp4a(__byte_perm(r1l, r1h, 0x0041), wx, 0u) << 16);
+        const uint32_t h2 = __dp4a(__byte_perm(r0l, r0h, 0x0052), wx, __dp4a(__byte_perm(r1l, r1h, 0x0052), wx, 0u) << 16);
+        o[0] = __dp2a_lo(h0, wy, 512u) >> 10;
+        o[1] = __dp2a_lo(h1, wy, 512u) >> 10;
+        o[2] = __dp2a_lo(h2, wy, 512u) >> 10;
+      } else {
+        remap_pixel<3>(s, nullptr, src_w, e, k.border, k.bg, o);
+      }
+      so[c * 3 + 0] = (uint8_t)o[0];
+      so[c * 3 + 1] = (uint8_t)o[1];
+      so[c * 3 + 2] = (uint8_t)o[2];
+    }
+  }
+  __syncwarp();
+  const int nbytes = npx * 3;
+  if ((((uintptr_t)d) & 15) == 0) {
+    const int n16 = nbytes >> 4;
+    if (lane < n16) ((uint4*)d)[lane] = ((const uint4*)so)[lane];  // nbytes <= 384 -> at most 24 vectors
+    for (int i = (n16 << 4) + lane; i < nbytes; i += 32) d[i] = so[i];
+  } else {
+    for (int i = lane; i < nbytes; i += 32) d[i] = so[i];
+  }
+}
+
 }  // namespace
 
 template <typename T>
@@ -240,10 +328,17 @@ extern "C" int sos_remap_u8(sos_ctx* ctx, const uint8_t* src, int batch, int src
   // the wide (2 x 64-bit) tap loads may touch up to 15 bytes past the taps: allowed only inside [src, wide_end)
   static const bool wide_off = getenv("SOS_REMAP_BYTE_LOADS") != nullptr;  // A/B switch for profiling
   const uint8_t* wide_end = (((uintptr_t)src & 7) == 0 && !wide_off) ? src + (size_t)batch * src_h * src_w * channels : nullptr;
-  switch (channels) {
-    case 1: remap_kernel<1><<<grid, 256, 0, ctx->stream>>>(src, wide_end, src_h, src_w, lut, views, rows, cols, k, dst); break;
-    case 3: remap_kernel<3><<<grid, 256, 0, ctx->stream>>>(src, wide_end, src_h, src_w, lut, views, rows, cols, k, dst); break;
-    default: remap_kernel<4><<<grid, 256, 0, ctx->stream>>>(src, wide_end, src_h, src_w, lut, views, rows, cols, k, dst); break;
+  static const bool old_kernel = getenv("SOS_REMAP_V1") != nullptr;  // A/B switch for profiling
+  if (channels == 3 && !old_kernel) {
+    dim3 g3(sos_div_up(cols, R3_COLS), sos_div_up(rows, R3_WARPS), batch * views);
+    const int wide_ok = (((uintptr_t)src & 7) == 0 && !wide_off) ? 1 : 0;
+    remap3_kernel<<<g3, R3_WARPS * 32, 0, ctx->stream>>>(src, wide_ok, src_h, src_w, lut, views, rows, cols, k, dst);
+  } else {
+    switch (channels) {
+      case 1: remap_kernel<1><<<grid, 256, 0, ctx->stream>>>(src, wide_end, src_h, src_w, lut, views, rows, cols, k, dst); break;
+      case 3: remap_kernel<3><<<grid, 256, 0, ctx->stream>>>(src, wide_end, src_h, src_w, lut, views, rows, cols, k, dst); break;
+      default: remap_kernel<4><<<grid, 256, 0, ctx->stream>>>(src, wide_end, src_h, src_w, lut, views, rows, cols, k, dst); break;
+    }
   }
   SOS_LAUNCHED(ctx);
   return SOS_OK;

@@ -288,7 +288,8 @@ class Context:
 
     def stereo_lift_triangulate(self, pano_top, pano_bot, px_top, px_bot, pair_q, pair_t, pair_count, seg_off,
                                 n_frames: int, segs_per_frame: int, f1, f2, rmin: float, rmax: float, cap_per_frame: int,
-                                homogeneous_norm: bool = True, out: Optional[dict] = None):
+                                homogeneous_norm: bool = True, out: Optional[dict] = None,
+                                max_pairs_per_seg: Optional[int] = None):
         self._sync_stream()
         pt = _darr(pano_top, len(PANO_FIELDS), "pano_top")
         pb = _darr(pano_bot, len(PANO_FIELDS), "pano_bot")
@@ -306,7 +307,8 @@ class Context:
             self._h, _ptr(pt), _ptr(pb), self._t(px_top, torch.float32, "px_top"),
             self._t(px_bot, torch.float32, "px_bot"), self._t(pair_q, torch.int32, "pair_q"),
             self._t(pair_t, torch.int32, "pair_t"), self._t(pair_count, torch.int32, "pair_count"),
-            self._t(seg_off, torch.int32, "seg_off"), int(n_frames), int(segs_per_frame), _ptr(a), _ptr(b),
+            self._t(seg_off, torch.int32, "seg_off"), int(n_frames), int(segs_per_frame),
+            int(max_pairs_per_seg if max_pairs_per_seg is not None else pair_q.shape[0]), int(pair_q.shape[0]), _ptr(a), _ptr(b),
             float(rmin), float(rmax), int(bool(homogeneous_norm)), int(cap_per_frame),
             out["uv_top"].data_ptr(), out["uv_bot"].data_ptr(), out["b_top"].data_ptr(), out["b_bot"].data_ptr(),
             out["xyz"].data_ptr(), out["src_top"].data_ptr(), out["src_bot"].data_ptr(), out["n"].data_ptr()))
