@@ -297,6 +297,20 @@ int sos_ransac_p3d_eval(sos_ctx* ctx, const float* p_ref, const float* p_cur, co
 int sos_refit_inliers(sos_ctx* ctx, const float* p_ref, const float* p_cur, const uint8_t* inlier_mask,
                       const int32_t* n, int n_problems, int cap, float* pose, int32_t* n_used);
 
+/* Non-linear pose refinement on the inlier set.
+ * replaces: pyopengv.absolute_pose_noncentral_optimize_nonlinear (pose_est_tools.py:830) and
+ *           pyopengv.absolute_pose_optimize_nonlinear (pose_est_tools.py:937; n_cams = 0 -> central camera).
+ * Levenberg-Marquardt in float64 on sum_i r_i^2, r_i = 1 - f_i . normalize(Rc^T (R^T (p_i - t) - tc)) — OpenGV's
+ * published residual, the same one the bearing score uses (pose_est_tools.py:150-203) — starting from pose_in.
+ * One thread-block cluster per problem (cluster_size CTAs, 0 = choose from cap, at most 8).
+ * inlier_mask NULL = use all n[b] rows.  pose_out float32 [n_problems,12] and/or pose_out64 float64 [n_problems,12]
+ * (either may be NULL, not both); stats (nullable) float64 [n_problems,4] = initial cost, final cost, cost
+ * evaluations, rows used.  Fewer than 6 usable rows -> pose_in is passed through. */
+int sos_refine_pose(sos_ctx* ctx, const float* p_ref, const float* f_cur, const uint8_t* cam,
+                    const uint8_t* inlier_mask, const int32_t* n, int n_problems, int cap, const double* rig,
+                    int n_cams, const float* pose_in, int max_iters, int cluster_size, float* pose_out,
+                    double* pose_out64, double* stats);
+
 /* ------------------------------------------------------------------------------------------------
  * The batched, GPU-resident front-end: B new frames in, B frame-pair poses out
  * ---------------------------------------------------------------------------------------------- */

@@ -145,3 +145,51 @@ def num_iterations(outlier_fraction: float = 0.65, n_points: int = 3, p: float =
     k = log10(1.0 - p) / log10(1.0 - w ** n_points)
     std = sqrt(1.0 - w ** n_points) / (w ** n_points)
     return int(k + 3 * std)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Non-linear refinement.  OpenGV is absent (parity unpinned); this restates its published algorithm:
+# absolute_pose::optimize_nonlinear = Levenberg-Marquardt (Eigen's MINPACK port) over x = (t, Cayley(R)) with one
+# residual per correspondence, 1 - f . reprojection — the same residual as score_bearing above.  scipy's
+# least_squares(method="lm") is the original MINPACK driver.
+# ---------------------------------------------------------------------------------------------------------------
+def cayley_to_rot(c: np.ndarray) -> np.ndarray:
+    c = np.asarray(c, np.float64)
+    x, y, z = c
+    s = 1.0 + x * x + y * y + z * z
+    return np.array([[1 + x * x - y * y - z * z, 2 * (x * y - z), 2 * (x * z + y)],
+                     [2 * (x * y + z), 1 - x * x + y * y - z * z, 2 * (y * z - x)],
+                     [2 * (x * z - y), 2 * (y * z + x), 1 - x * x - y * y + z * z]]) / s
+
+
+def rot_to_cayley(R: np.ndarray) -> np.ndarray:
+    """Inverse of cayley_to_rot: [c]x = (R - I)(R + I)^-1."""
+    R = np.asarray(R, np.float64)
+    C = (R - np.eye(3)) @ np.linalg.inv(R + np.eye(3))
+    return np.array([C[2, 1] - C[1, 2], C[0, 2] - C[2, 0], C[1, 0] - C[0, 1]]) * 0.5
+
+
+def refine_pose_lm(p_ref, f_cur, pose0, cam=None, rig=None, mask=None, tol: float = 1e-15):
+    """Refined [3,4] pose, and (initial cost, final cost) with cost = sum r^2."""
+    from scipy.optimize import least_squares
+    p_ref = np.asarray(p_ref, np.float64)
+    f_cur = np.asarray(f_cur, np.float64)
+    if mask is not None:
+        m = np.asarray(mask, bool)
+        p_ref, f_cur = p_ref[m], f_cur[m]
+        cam = None if cam is None else np.asarray(cam)[m]
+    pose0 = np.asarray(pose0, np.float64).reshape(3, 4)
+
+    def unpack(x):
+        M = np.zeros((3, 4))
+        M[:, :3] = cayley_to_rot(x[3:])
+        M[:, 3] = x[:3]
+        return M
+
+    def fun(x):
+        return score_bearing(unpack(x), p_ref, f_cur, cam, rig)
+
+    x0 = np.concatenate([pose0[:, 3], rot_to_cayley(pose0[:, :3])])
+    sol = least_squares(fun, x0, method="lm", xtol=tol, ftol=tol, gtol=tol, max_nfev=2000)
+    r0 = fun(x0)
+    return unpack(sol.x), float(r0 @ r0), float(sol.fun @ sol.fun)

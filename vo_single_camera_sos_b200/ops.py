@@ -419,6 +419,24 @@ class Context:
                                          self._t(n, torch.int32, "n"), B, cap, pose.data_ptr(), used.data_ptr()))
         return pose, used
 
+    def refine_pose(self, p_ref, f_cur, cam, mask, n, rig, pose_in, max_iters: int = 30, cluster_size: int = 0):
+        """Levenberg-Marquardt refinement of the bearing residual on the masked rows (sos_refine_pose).
+        Returns (pose float32 [B,3,4], pose64 float64 [B,3,4], stats float64 [B,4])."""
+        self._sync_stream()
+        B, cap, _ = p_ref.shape
+        pose = self.empty((B, 3, 4), torch.float32)
+        pose64 = self.empty((B, 3, 4), torch.float64)
+        stats = self.empty((B, 4), torch.float64)
+        rig_arr = None if rig is None else np.ascontiguousarray(np.asarray(rig, np.float64).reshape(-1, 12))
+        check(self.lib.sos_refine_pose(
+            self._h, self._t(p_ref, torch.float32, "p_ref"), self._t(f_cur, torch.float32, "f_cur"),
+            None if cam is None else self._t(cam, torch.uint8, "cam"),
+            None if mask is None else self._t(mask, torch.uint8, "mask"), self._t(n, torch.int32, "n"), B, cap,
+            None if rig_arr is None else rig_arr.ctypes.data, 0 if rig_arr is None else len(rig_arr),
+            self._t(pose_in, torch.float32, "pose_in"), int(max_iters), int(cluster_size), pose.data_ptr(),
+            pose64.data_ptr(), stats.data_ptr()))
+        return pose, pose64, stats
+
     # -- roofline denominators -----------------------------------------------------------------------------------
     def peak_popc(self) -> float:
         self._sync_stream()
