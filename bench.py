@@ -114,11 +114,12 @@ def host_workload(name: str, seed: int):
 class CpuPath:
     """One frame pair per call through oracle.pipeline (OpenCV with all its threads + NumPy)."""
 
-    def __init__(self, name: str, seed: int, n_frames: int, score_mode: str):
+    def __init__(self, name: str, seed: int, n_frames: int, score_mode: str, refine: str = "arun"):
         import cv2
         from vo_single_camera_sos_b200 import synth
         self.rig, self.scene, self.maps, self.masks, self.hyp, self.c = host_workload(name, seed)
         self.mode = score_mode
+        self.refine = refine
         self.thr = 1.0 - math.cos(math.radians(5.0)) if score_mode == "bearing" else 0.05
         self.traj = synth.make_trajectory(n_frames, seed=seed)
         self.threads = cv2.getNumThreads()
@@ -156,7 +157,7 @@ class CpuPath:
         from oracle import pipeline
         cur = self._frame(self.cursor)
         out = pipeline.track_pair(self.state, cur, self.hyp, self.mode, self.thr, self.rigm,
-                                  0.125 * 0.5 * self.rig.pano["cols"])
+                                  0.125 * 0.5 * self.rig.pano["cols"], refine=self.refine)
         self.state = cur
         self.cursor += 1
         return out
@@ -166,7 +167,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     t_build = time.perf_counter()
-    cpu = CpuPath(args.workload, seed=0, n_frames=min(args.steps + args.warmup + 1, 6), score_mode=args.score)
+    cpu = CpuPath(args.workload, seed=0, n_frames=min(args.steps + args.warmup + 1, 6), score_mode=args.score, refine=args.refine)
     cpu.prime()
     for _ in range(args.warmup):
         cpu.pair()
@@ -194,7 +195,8 @@ def run_reference(args, rank, world):
 
 def workload_config(args, c, batch, note=""):
     return {"workload": f"{args.workload}: {c['width']}x{c['height']} omni -> 2 x {c['pano_cols']}-wide panoramas, "
-                        f"{c['feat']} ORB features/view in 12 azimuth buckets, {c['n_hyp']} RANSAC hypotheses, score={args.score}",
+                        f"{c['feat']} ORB features/view in 12 azimuth buckets, {c['n_hyp']} RANSAC hypotheses, score={args.score}, "
+                        f"refine={args.refine}",
             "frames_per_step": batch, "note": note}
 
 
@@ -214,6 +216,7 @@ def run_gpu(args, rank, local_rank, world):
     n_sets = 2
     score = ops.SCORE_BEARING if args.score == "bearing" else ops.SCORE_EUCLID
     w = workload.build(ctx, args.workload, batch=B, n_frames=n_sets * B + 1, seed=rank, score_mode=score)
+    w.cfg.refit = {"none": ops.REFINE_NONE, "arun": ops.REFINE_ARUN, "lm": ops.REFINE_LM}[args.refine]
     c = workload.CONFIGS[args.workload]
     renderer = workload.DeviceRenderer(ctx, w)
     sets = [workload.make_frames(w, s * B, B, renderer=renderer) for s in range(n_sets)]
@@ -385,7 +388,7 @@ def summarize_kernels(marks, steps):
 
 def cpu_baseline(args):
     n_pairs = 3 if args.workload == "c2" else 6
-    cpu = CpuPath(args.workload, seed=0, n_frames=n_pairs + 2, score_mode=args.score)
+    cpu = CpuPath(args.workload, seed=0, n_frames=n_pairs + 2, score_mode=args.score, refine=args.refine)
     cpu.prime()
     cpu.pair()  # warm-up (OpenCV thread pool, NumPy caches)
     t0 = time.perf_counter()
@@ -407,6 +410,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "tiny"])
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--score", default="bearing", choices=["bearing", "euclid"])
+    ap.add_argument("--refine", default="arun", choices=["none", "arun", "lm"],
+                    help="pose after RANSAC: Arun refit on the inliers, or Levenberg-Marquardt on the bearing residual")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)

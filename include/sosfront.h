@@ -319,6 +319,13 @@ int sos_refine_pose(sos_ctx* ctx, const float* p_ref, const float* f_cur, const 
  * StereoPanoramicFrame.establish_stereo_correspondences (pose_est_tools.py:320-402) and
  * TrackerStereoSE3.track_frame (pose_est_tools.py:736-847) do for one frame; defaults in pose_est_tools.py:284-308,
  * 672-707, 862-878.  Feature detection is upstream of the hot path: features arrive as input. */
+/* sos_frontend_config.refit */
+enum {
+  SOS_REFINE_NONE = 0, /* pose = RANSAC model */
+  SOS_REFINE_ARUN = 1, /* Arun refit on the inliers (sos_refit_inliers) */
+  SOS_REFINE_LM = 2    /* Levenberg-Marquardt on the bearing residual (sos_refine_pose), as the reference does with OpenGV */
+};
+
 typedef struct sos_frontend_config {
   int32_t batch;               /* frames per step; pair i = (frame i-1, frame i), frame -1 = last frame of the previous step */
   int32_t src_h, src_w, channels;
@@ -330,7 +337,8 @@ typedef struct sos_frontend_config {
   int32_t n_hyp;               /* RANSAC hypotheses (210 in the reference, pose_est_tools.py:709-720) */
   int32_t score_mode;          /* SOS_SCORE_* */
   int32_t homogeneous_norm;    /* 1 = range gate on the homogeneous norm as the reference does (pose_est_tools.py:365-372) */
-  int32_t refit;               /* 1 = Arun refit on the inliers after RANSAC */
+  int32_t refit;               /* SOS_REFINE_*: what turns the RANSAC pose into the output pose */
+  int32_t refine_iters;        /* SOS_REFINE_LM: maximum cost evaluations (0 = 20) */
   double ransac_threshold;     /* 1 - cos(5 deg) for SOS_SCORE_BEARING (pose_est_tools.py:675-676) */
   double stereo_max_du, stereo_min_dv; /* 2.5, 1 (pose_est_tools.py:298-304) */
   double temporal_max_du;      /* 0.125 * 0.5 * cols (pose_est_tools.py:866) */
@@ -361,6 +369,7 @@ typedef struct sos_frontend_buffers {
   int32_t *best_hyp, *best_count, *n_refit;        /* [batch] */
   uint8_t* inlier_mask;                            /* [batch, 2*cap] */
   int32_t* stats;                                  /* [batch, 4]: n_stereo, n_correspondences, n_inliers, best_hyp */
+  double* refine_stats;                            /* [batch, 4] of sos_refine_pose (SOS_REFINE_LM only) */
   int32_t batch, cap, launches_per_step;
 } sos_frontend_buffers;
 

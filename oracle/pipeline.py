@@ -60,7 +60,7 @@ def stereo_frame(pano_g, f_top, f_bot, px_top, desc_top, boff_top, px_bot, desc_
                 desc_top=desc_top[rt][keep], desc_bot=desc_bot[rq][keep])
 
 
-def track_pair(ref, cur, hyp, mode, threshold, rig, max_du, hyp_limit=None):
+def track_pair(ref, cur, hyp, mode, threshold, rig, max_du, hyp_limit=None, refine="arun"):
     """match_features_frame_to_frame for both views (pose_est_tools.py:741-749), stacking (:752-778), RANSAC + refit."""
     parts = []
     for view, (uvk, dk, bk) in enumerate((("uv_top", "desc_top", "b_top"), ("uv_bot", "desc_bot", "b_bot"))):
@@ -77,6 +77,11 @@ def track_pair(ref, cur, hyp, mode, threshold, rig, max_du, hyp_limit=None):
     h = hyp if hyp_limit is None else hyp[:hyp_limit]
     o = ransac.ransac_p3d(f32(p_ref), f32(p_cur), h, mode, threshold, f_cur=f32(f_cur), cam=cam, rig=rig)
     if o["best_hyp"] >= 0:
-        o["refit"] = ransac.refit(p_ref, p_cur, o["mask"])
+        if refine == "lm":  # pose_est_tools.py:824-834: non-linear refinement on the inliers, started at the RANSAC pose
+            o["refit"] = ransac.refine_pose_lm(f32(p_ref), f32(f_cur), o["pose"], cam, rig, o["mask"])[0]
+        elif refine == "arun":
+            o["refit"] = ransac.refit(p_ref, p_cur, o["mask"])
+        else:
+            o["refit"] = o["pose"]
     o["n_corr"] = len(p_ref)
     return o

@@ -194,3 +194,39 @@ def test_frontend_rejects_bad_inputs(ctx):
     with pytest.raises(TypeError):
         fe.step(dev[0].cpu(), *dev[1:])
     fe.close()
+
+
+def test_frontend_lm_refinement_matches_minpack(ctx):
+    """SOS_REFINE_LM inside the captured chain: the output pose is the Levenberg-Marquardt minimiser of the bearing
+    residual over the RANSAC inliers, started at the RANSAC pose (pose_est_tools.py:824-834) — checked against the
+    MINPACK oracle on exactly the device's float32 correspondences (1e-6 absolute; float32 output)."""
+    from vo_single_camera_sos_b200 import ops, workload
+    B = 3
+    w = workload.build(ctx, "tiny", batch=B, n_frames=2 * B, seed=4, score_mode=ops.SCORE_BEARING)
+    w.cfg.refit = ops.REFINE_LM
+    w.cfg.refine_iters = 60
+    fe = w.frontend(ctx)
+    rig = np.zeros((2, 3, 4)); rig[:, :, :3] = np.eye(3); rig[0, :, 3] = w.rig.f_top; rig[1, :, 3] = w.rig.f_bot
+    for step in range(2):
+        fr = workload.make_frames(w, step * B, B)
+        fe.step(*workload.to_device(ctx, fr))
+        torch.cuda.synchronize()
+        buf = host(fe.buffers())
+        for i in range(B):
+            m = int(buf["n_corr"][i])
+            if buf["best_hyp"][i] < 0:
+                assert np.array_equal(buf["pose"][i], buf["ransac_pose"][i]) or np.isnan(buf["ransac_pose"][i]).any()
+                continue
+            mask = buf["inlier_mask"][i, :m].astype(bool)
+            want, c0, c1 = ransac.refine_pose_lm(buf["p_ref"][i, :m], buf["f_cur"][i, :m], buf["ransac_pose"][i],
+                                                 buf["cam"][i, :m], rig, mask)
+            rs = buf["refine_stats"][i]
+            assert rs[3] == mask.sum() and rs[2] <= 60
+            assert rs[1] <= c1 * (1 + 1e-9) and rs[1] <= rs[0]
+            np.testing.assert_allclose(buf["pose"][i], want, rtol=0, atol=1e-6)
+    # sanity against the ground-truth motion
+    for i in range(B):
+        T_rel = np.linalg.inv(w.trajectory[B + i - 1]) @ w.trajectory[B + i]
+        assert np.allclose(buf["pose"][i][:, :3], T_rel[:3, :3], atol=0.05)
+        assert np.allclose(buf["pose"][i][:, 3], T_rel[:3, 3], atol=0.15)
+    fe.close()

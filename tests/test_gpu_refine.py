@@ -85,3 +85,20 @@ def test_refine_without_mask_and_passthrough(ctx):
     np.testing.assert_allclose(pose64[0], want, rtol=0, atol=1e-6)
     np.testing.assert_array_equal(pose.cpu().numpy()[1], pose0[1])
     assert s[1, 3] == 4
+
+
+def test_pyopengv_optimize_nonlinear_signature_and_result(ctx):
+    """The reference's call (pose_est_tools.py:830, :937): float64 arrays in, T 3x4 float64 out."""
+    import pyopengv
+    rng = np.random.default_rng(21)
+    P, F, C, M, pose0 = build(rng, [900], 1024, RIG)
+    m = M[0, :900].astype(bool)
+    p, f, cam = P[0, :900][m].astype(np.float64), F[0, :900][m].astype(np.float64), C[0, :900][m]
+    t0, R0 = pose0[0][:, 3].astype(np.float64), pose0[0][:, :3].astype(np.float64)
+    T = pyopengv.absolute_pose_noncentral_optimize_nonlinear(f, cam.reshape(-1, 1), p, RIG[:, :, 3], RIG[:, :, :3], t0, R0)
+    assert T.shape == (3, 4) and T.dtype == np.float64
+    want, _, _ = ransac.refine_pose_lm(p, f, pose0[0], cam, RIG, None)
+    np.testing.assert_allclose(T, want, rtol=0, atol=1e-7)
+    Tc = pyopengv.absolute_pose_optimize_nonlinear(f, p, t0, R0)
+    want_c, _, _ = ransac.refine_pose_lm(p, f, pose0[0], None, None, None)
+    np.testing.assert_allclose(Tc, want_c, rtol=0, atol=1e-7)

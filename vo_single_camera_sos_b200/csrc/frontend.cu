@@ -249,7 +249,11 @@ int enqueue_step(sos_frontend* fe, const uint8_t* omni, const float* px_top, con
                       c.score_mode, c.ransac_threshold, d.ransac_pose, d.best_hyp, d.best_count, d.inlier_mask, nullptr,
                       nullptr);
   if (rc) return rc;
-  if (c.refit) {
+  if (c.refit == SOS_REFINE_LM) {
+    rc = sos_refine_pose(ctx, d.p_ref, d.f_cur, d.cam, d.inlier_mask, d.n_corr, B, 2 * cap, c.rig, 2, d.ransac_pose,
+                         c.refine_iters > 0 ? c.refine_iters : 20, 0, d.pose, nullptr, d.refine_stats);
+    if (rc) return rc;
+  } else if (c.refit == SOS_REFINE_ARUN) {
     rc = sos_refit_inliers(ctx, d.p_ref, d.p_cur, d.inlier_mask, d.n_corr, B, 2 * cap, d.pose, d.n_refit);
     if (rc) return rc;
   } else {
@@ -360,7 +364,7 @@ extern "C" int sos_frontend_create(sos_ctx* ctx, const sos_frontend_config* cfg,
   FE_ALLOC(p_ref, B * 2 * cap * 3); FE_ALLOC(p_cur, B * 2 * cap * 3); FE_ALLOC(f_cur, B * 2 * cap * 3);
   FE_ALLOC(cam, B * 2 * cap); FE_ALLOC(n_corr, B); FE_ALLOC(n_corr_top, B);
   FE_ALLOC(ransac_pose, B * 12); FE_ALLOC(pose, B * 12); FE_ALLOC(best_hyp, B); FE_ALLOC(best_count, B);
-  FE_ALLOC(n_refit, B); FE_ALLOC(inlier_mask, B * 2 * cap); FE_ALLOC(stats, B * 4);
+  FE_ALLOC(n_refit, B); FE_ALLOC(inlier_mask, B * 2 * cap); FE_ALLOC(stats, B * 4); FE_ALLOC(refine_stats, B * 4);
 #undef FE_ALLOC
   if (rc != SOS_OK) {
     sos_frontend_destroy(fe);

@@ -23,6 +23,7 @@ class _Config(C.Structure):
         ("pano_rows", C.c_int32), ("pano_cols", C.c_int32), ("n_buckets", C.c_int32),
         ("max_feat_per_view", C.c_int32), ("max_feat_per_bucket", C.c_int32), ("cap", C.c_int32),
         ("n_hyp", C.c_int32), ("score_mode", C.c_int32), ("homogeneous_norm", C.c_int32), ("refit", C.c_int32),
+        ("refine_iters", C.c_int32),
         ("ransac_threshold", C.c_double), ("stereo_max_du", C.c_double), ("stereo_min_dv", C.c_double),
         ("temporal_max_du", C.c_double), ("min_range", C.c_double), ("max_range", C.c_double),
         ("pano_top", C.c_double * 6), ("pano_bot", C.c_double * 6), ("f_top", C.c_double * 3), ("f_bot", C.c_double * 3),
@@ -39,7 +40,7 @@ _BUF_FIELDS = [
     ("tm_idx0", "i32"), ("tm_d0", "i32"), ("tm_pair_q", "i32"), ("tm_pair_t", "i32"), ("tm_pair_d", "i32"),
     ("tm_pair_count", "i32"), ("p_ref", "f32"), ("p_cur", "f32"), ("f_cur", "f32"), ("cam", "u8"),
     ("n_corr", "i32"), ("n_corr_top", "i32"), ("ransac_pose", "f32"), ("pose", "f32"), ("best_hyp", "i32"),
-    ("best_count", "i32"), ("n_refit", "i32"), ("inlier_mask", "u8"), ("stats", "i32"),
+    ("best_count", "i32"), ("n_refit", "i32"), ("inlier_mask", "u8"), ("stats", "i32"), ("refine_stats", "f64"),
 ]
 
 
@@ -69,7 +70,8 @@ class FrontendConfig:
     score_mode: int = ops.SCORE_BEARING
     ransac_threshold: float = 1.0 - math.cos(math.radians(5.0))
     homogeneous_norm: bool = True
-    refit: bool = True
+    refit: int = 1                    # ops.REFINE_NONE / REFINE_ARUN / REFINE_LM (True == REFINE_ARUN)
+    refine_iters: int = 0             # REFINE_LM: maximum cost evaluations (0 -> 20)
     stereo_max_du: float = 2.5
     stereo_min_dv: float = 1.0
     temporal_max_du: Optional[float] = None   # None -> 0.125 * 0.5 * pano_cols
@@ -85,7 +87,8 @@ class FrontendConfig:
                   "max_feat_per_bucket", "cap", "n_hyp", "score_mode"):
             setattr(c, k, int(getattr(self, k)))
         c.homogeneous_norm = int(bool(self.homogeneous_norm))
-        c.refit = int(bool(self.refit))
+        c.refit = int(self.refit)
+        c.refine_iters = int(self.refine_iters)
         c.ransac_threshold = float(self.ransac_threshold)
         c.stereo_max_du, c.stereo_min_dv = float(self.stereo_max_du), float(self.stereo_min_dv)
         c.temporal_max_du = float(0.125 * 0.5 * self.pano_cols if self.temporal_max_du is None else self.temporal_max_du)
@@ -116,7 +119,8 @@ class _DeviceArray:
         self._owner = owner
 
 
-_TYPES = {"u8": ("|u1", torch.uint8), "i32": ("<i4", torch.int32), "f32": ("<f4", torch.float32)}
+_TYPES = {"u8": ("|u1", torch.uint8), "i32": ("<i4", torch.int32), "f32": ("<f4", torch.float32),
+          "f64": ("<f8", torch.float64)}
 
 
 class Frontend:
@@ -235,7 +239,7 @@ class Frontend:
             "tm_pair_t": (2 * slots * cap,), "tm_pair_d": (2 * slots * cap,), "tm_pair_count": (2 * B,),
             "p_ref": (B, 2 * cap, 3), "p_cur": (B, 2 * cap, 3), "f_cur": (B, 2 * cap, 3), "cam": (B, 2 * cap),
             "n_corr": (B,), "n_corr_top": (B,), "ransac_pose": (B, 3, 4), "pose": (B, 3, 4), "best_hyp": (B,),
-            "best_count": (B,), "n_refit": (B,), "inlier_mask": (B, 2 * cap), "stats": (B, 4),
+            "best_count": (B,), "n_refit": (B,), "inlier_mask": (B, 2 * cap), "stats": (B, 4), "refine_stats": (B, 4),
         }
         out = {}
         for name, kind in _BUF_FIELDS:

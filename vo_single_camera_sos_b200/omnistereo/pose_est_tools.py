@@ -4,7 +4,7 @@ Differences from the reference that are visible to a caller:
   * the RANSAC behind `pyopengv.absolute_pose_*_ransac` hypothesises with 3-point Arun registration on 3D-3D
     correspondences under a seeded hypothesis list (see vo_single_camera_sos_b200/pyopengv.py); the trackers therefore
     also hand the current frame's triangulated points to it;
-  * `*_optimize_nonlinear` is an Arun refit on the inliers (approximation, SURVEY §8f N1);
+  * `*_optimize_nonlinear` is Levenberg-Marquardt on OpenGV's bearing residual over the inliers (sos_refine_pose);
   * frames accept pre-computed features (`features=`) because feature detection is upstream of the hot path.
 """
 from math import log10, sqrt

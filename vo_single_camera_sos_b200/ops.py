@@ -18,6 +18,7 @@ from ._lib import SosError, check  # noqa: F401  (re-exported)
 
 MATCH_NN, MATCH_RATIO, MATCH_CROSS = 0, 1, 2
 SCORE_EUCLID, SCORE_BEARING = 0, 1
+REFINE_NONE, REFINE_ARUN, REFINE_LM = 0, 1, 2
 
 GUM_FIELDS = ("xi1", "xi2", "xi3", "k1", "k2", "k3", "gamma1", "gamma2", "alpha_c", "u_center", "v_center",
               "l1", "l2", "l3", "p1", "p2", "plane_k", "use_distortion")

@@ -10,6 +10,8 @@ semantics implemented here are the ones written down in include/sosfront.h:
     `points_cur=` (the mirrored trackers in omnistereo.pose_est_tools do).  Without them the call raises.
   * score: OpenGV's bearing-angle score 1 - f . reprojection, threshold and iteration budget as given.
   * first maximum wins; the inlier indices are returned ascending, as the caller assumes (pose_est_tools.py:787).
+  * *_optimize_nonlinear: OpenGV's published algorithm — Levenberg-Marquardt on one residual 1 - f . reprojection per
+    correspondence — run by sos_refine_pose (csrc/refine.cu); checked against scipy's MINPACK driver in the tests.
 """
 import numpy as np
 import torch
@@ -76,29 +78,34 @@ def absolute_pose_ransac(bearing_vectors, points, algo_name, threshold, max_iter
     return _ransac(bearing_vectors, points, points_cur, threshold, max_iterations, seed=seed)
 
 
-def _refit(points, points_cur, t, R):
-    if points_cur is None:  # nothing to refine with: hand the RANSAC model back (documented approximation)
-        return np.hstack([np.asarray(R, float).reshape(3, 3), np.asarray(t, float).reshape(3, 1)])
+def _refine(bearings, points, t, R, cam=None, rig=None, max_iters=60):
+    """Levenberg-Marquardt on sum (1 - f . reprojection)^2 over ALL rows given (the caller passes the inliers),
+    started at (t, R): sos_refine_pose.  float64 result."""
+    b = np.asarray(bearings, np.float32)[:, :3]
     p = np.asarray(points, np.float32)[:, :3]
-    pc = np.asarray(points_cur, np.float32)[:, :3]
-    ctx = _ctx()
     n = len(p)
-    pose, used = ctx.refit_inliers(_dev(p[None]), _dev(pc[None]), torch.ones((1, n), dtype=torch.uint8, device=ctx.device),
-                                   torch.tensor([n], dtype=torch.int32, device=ctx.device))
-    if int(used.cpu().numpy()[0]) < 3:
-        return np.hstack([np.asarray(R, float).reshape(3, 3), np.asarray(t, float).reshape(3, 1)])
-    return pose.cpu().numpy()[0].astype(np.float64)
+    pose0 = np.hstack([np.asarray(R, np.float64).reshape(3, 3), np.asarray(t, np.float64).reshape(3, 1)])
+    if n == 0:
+        return pose0
+    ctx = _ctx()
+    _, pose64, _ = ctx.refine_pose(
+        _dev(p[None]), _dev(b[None]), None if cam is None else _dev(np.asarray(cam).reshape(-1).astype(np.uint8)[None]),
+        None, torch.tensor([n], dtype=torch.int32, device=ctx.device), rig, _dev(pose0.astype(np.float32)[None]),
+        max_iters=max_iters)
+    return pose64.cpu().numpy()[0]
 
 
 def absolute_pose_noncentral_optimize_nonlinear(bearing_vectors, cam_correspondences, points, cam_offsets, cam_rotations, t, R,
                                                 points_cur=None):
-    """Stand-in for OpenGV's non-linear refinement (pose_est_tools.py:830): Arun refit on the given (inlier) set — an
-    APPROXIMATION; the true bearing-error Gauss-Newton refinement is SURVEY §8f row N1."""
-    return _refit(points, points_cur, t, R)
+    """pose_est_tools.py:830 -> refined T 3x4.  OpenGV's algorithm (LM on the bearing residual over the rows given);
+    `points_cur` is accepted for symmetry with the RANSAC call and not needed."""
+    rig, _ = _rig(cam_offsets, cam_rotations)
+    return _refine(bearing_vectors, points, t, R, cam=cam_correspondences, rig=rig)
 
 
 def absolute_pose_optimize_nonlinear(bearing_vectors, points, t, R, points_cur=None):
-    return _refit(points, points_cur, t, R)
+    """Central camera (pose_est_tools.py:937)."""
+    return _refine(bearing_vectors, points, t, R)
 
 
 def relative_pose_ransac(*args, **kwargs):
