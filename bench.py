@@ -358,7 +358,9 @@ def run_gpu(args, rank, local_rank, world):
             "cpu_baseline": cpu_base,
             "clocks": clocks,
             "stats_last_step": {"stereo_correspondences": stats[:, 0].tolist(), "temporal_correspondences": stats[:, 1].tolist(),
-                                "ransac_inliers": stats[:, 2].tolist()},
+                                "ransac_inliers": stats[:, 2].tolist(),
+                                "refine_evaluations": (buf["refine_stats"][:, 2].cpu().numpy().astype(int).tolist()
+                                                       if args.refine == "lm" else None)},
             "peaks": {"hbm_gbs": hbm_peak, "popc_tera_per_s": popc_peak, "ffma_tflops": ffma_peak},
         }
         print(json.dumps(line), flush=True)

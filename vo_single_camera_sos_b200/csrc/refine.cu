@@ -25,6 +25,8 @@ constexpr int RF_THREADS = 256;
 constexpr int RF_MAX_CAMS = 2;
 constexpr int RF_NACC = 28;          // 21 (upper triangle of J^T J) + 6 (J^T r) + 1 (sum r^2)
 constexpr int RF_MAX_CLUSTER = 8;
+constexpr double RF_STEP_TOL = 1e-10;
+constexpr int RF_CACHE_ROWS = 8;               // rows per thread staged in shared memory (56 KB); the rest re-read from HBM
 constexpr double RF_SECOND_ORDER_MAX = 0.05;  // 1 - cos(18 deg)
 
 struct RefineRig {
@@ -37,12 +39,14 @@ struct RefineState {                 // lives in every CTA's shared memory; writ
   int pad;
 };
 
-__device__ inline void rodrigues(const double* d, double* E) {  // E = exp([d]x)
+__device__ inline void rodrigues(const double* d, double* E) {  // E = exp([d]x) = I + a [d]x + b [d]x^2
   const double th2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
-  double a, b;                        // E = I + a [d]x + b [d]x^2
-  if (th2 < 1e-16) {
-    a = 1.0 - th2 / 6.0;
-    b = 0.5 - th2 / 24.0;
+  double a, b;
+  if (th2 < 0.25) {   // LM steps are small: Taylor series of sin(t)/t and (1 - cos t)/t^2 in t^2, < 1e-17 at t = 0.5
+    a = 1.0 + th2 * (-1.0 / 6 + th2 * (1.0 / 120 + th2 * (-1.0 / 5040 + th2 * (1.0 / 362880 + th2 * (-1.0 / 39916800 +
+        th2 * (1.0 / 6227020800.0 + th2 * (-1.0 / 1307674368000.0)))))));
+    b = 0.5 + th2 * (-1.0 / 24 + th2 * (1.0 / 720 + th2 * (-1.0 / 40320 + th2 * (1.0 / 3628800 + th2 * (-1.0 / 479001600 +
+        th2 * (1.0 / 87178291200.0 + th2 * (-1.0 / 20922789888000.0)))))));
   } else {
     const double th = sqrt(th2);
     a = sin(th) / th;
@@ -55,37 +59,51 @@ __device__ inline void rodrigues(const double* d, double* E) {  // E = exp([d]x)
 }
 
 // Solve (A + lambda diag(A)) x = -g for the symmetric 6x6 A given as its upper triangle; false if not positive definite.
-__device__ bool solve_damped(const double* Au, const double* g, double lambda, double* x) {
-  double L[6][6];
+__device__ __forceinline__ bool solve_damped(const double* Au, const double* g, double lambda, double* x) {
+  double L[6][6];   // every loop below is fully unrolled: L stays in registers
   int k = 0;
+#pragma unroll
   for (int i = 0; i < 6; ++i)
+#pragma unroll
     for (int j = i; j < 6; ++j) { L[i][j] = Au[k]; L[j][i] = Au[k]; ++k; }
+#pragma unroll
   for (int i = 0; i < 6; ++i) {
     const double dgl = L[i][i];
     L[i][i] = dgl + lambda * (dgl > 0.0 ? dgl : 1.0);
   }
-  for (int j = 0; j < 6; ++j) {       // Cholesky, lower triangle in place
+  bool pd = true;
+  double dinv[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {       // Cholesky, lower triangle in place; one rsqrt per column, no divisions
     double s = L[j][j];
+#pragma unroll
     for (int m = 0; m < j; ++m) s -= L[j][m] * L[j][m];
-    if (!(s > 0.0)) return false;
-    const double d = sqrt(s);
-    L[j][j] = d;
+    pd = pd && (s > 0.0);
+    const double di = rsqrt(s);
+    dinv[j] = di;
+#pragma unroll
     for (int i = j + 1; i < 6; ++i) {
       double v = L[i][j];
+#pragma unroll
       for (int m = 0; m < j; ++m) v -= L[i][m] * L[j][m];
-      L[i][j] = v / d;
+      L[i][j] = v * di;
     }
   }
+  if (!pd) return false;
   double y[6];
+#pragma unroll
   for (int i = 0; i < 6; ++i) {
     double v = -g[i];
+#pragma unroll
     for (int m = 0; m < i; ++m) v -= L[i][m] * y[m];
-    y[i] = v / L[i][i];
+    y[i] = v * dinv[i];
   }
+#pragma unroll
   for (int i = 5; i >= 0; --i) {
     double v = y[i];
+#pragma unroll
     for (int m = i + 1; m < 6; ++m) v -= L[m][i] * x[m];
-    x[i] = v / L[i][i];
+    x[i] = v * dinv[i];
   }
   return true;
 }
@@ -101,12 +119,14 @@ refine_kernel(const float* __restrict__ p_ref, const float* __restrict__ f_cur, 
   const int b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+  extern __shared__ float cache[];                       // [RF_CACHE_ROWS][7][RF_THREADS]
   __shared__ RefineState st;
   __shared__ double partial[RF_NACC];                    // this CTA's sums; read by rank 0 through DSMEM
   __shared__ double wred[RF_THREADS / 32][RF_NACC];
   __shared__ double Msh[RF_MAX_CAMS][9];
+  __shared__ float Mf[RF_MAX_CAMS][9], Rcf[RF_MAX_CAMS][9];   // float copies for the float32 Hessian
   // rank 0 only
-  __shared__ double curR[9], curT[3], curA[21], curG[6];
+  __shared__ double curR[9], curT[3], curAG[27], tot[RF_NACC];
   __shared__ double cur_cost, lambda, first_cost, nu, pred, step_max;
   __shared__ int have_cur, iters_done, n_used_sh;
 
@@ -133,6 +153,20 @@ refine_kernel(const float* __restrict__ p_ref, const float* __restrict__ f_cur, 
     st.stop = 0;
     if (rank == 0) { have_cur = 0; iters_done = 0; lambda = 1e-4; nu = 2.0; pred = 1.0; step_max = 1.0; n_used_sh = 0; }
   }
+  // stage this thread's rows (the same in every evaluation): SoA in shared memory, slot 6 = camera index or -1
+  const int rows_per_thread = (n + S * RF_THREADS - 1) / (S * RF_THREADS);
+  for (int k = 0; k < min(rows_per_thread, RF_CACHE_ROWS); ++k) {
+    const int j = (k * S + rank) * RF_THREADS + tid;
+    const bool live = j < n && (!mask || mask[base + j]);
+    const size_t o = (base + (live ? j : 0)) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      cache[(k * 7 + c) * RF_THREADS + tid] = live ? p_ref[o + c] : 0.f;
+      cache[(k * 7 + 3 + c) * RF_THREADS + tid] = live ? f_cur[o + c] : 0.f;
+    }
+    const int ci = live ? (cam ? min((int)cam[base + j], RF_MAX_CAMS - 1) : 0) : -1;
+    cache[(k * 7 + 6) * RF_THREADS + tid] = __int_as_float(ci);
+  }
   cluster.sync();  // every CTA of the cluster is resident and rank 0's counters are initialised before any DSMEM access
 
   for (int it = 0;; ++it) {
@@ -140,7 +174,10 @@ refine_kernel(const float* __restrict__ p_ref, const float* __restrict__ f_cur, 
     if (tid < RF_MAX_CAMS * 9) {  // M_c = R Rc, so that Rc^T R^T = M_c^T
       const int c = tid / 9, r = (tid % 9) / 3, k = tid % 3;
       const double* Rt = rig.Rt[c];
-      Msh[c][r * 3 + k] = st.R[r * 3] * Rt[k] + st.R[r * 3 + 1] * Rt[4 + k] + st.R[r * 3 + 2] * Rt[8 + k];
+      const double v = st.R[r * 3] * Rt[k] + st.R[r * 3 + 1] * Rt[4 + k] + st.R[r * 3 + 2] * Rt[8 + k];
+      Msh[c][r * 3 + k] = v;
+      Mf[c][r * 3 + k] = (float)v;
+      Rcf[c][r * 3 + k] = (float)Rt[r * 4 + k];
     }
     __syncthreads();
     double R[9], t[3];
@@ -148,17 +185,33 @@ refine_kernel(const float* __restrict__ p_ref, const float* __restrict__ f_cur, 
     for (int i = 0; i < 9; ++i) R[i] = st.R[i];
 #pragma unroll
     for (int i = 0; i < 3; ++i) t[i] = st.t[i];
-    double acc[RF_NACC];
+    // float64: cost (1) and gradient J^T r (6) — they define the minimiser.  float32: the model Hessian (21) — it only
+    // shapes the step, so single precision costs convergence nothing and takes the 84 FMAs per row off the FP64 pipe.
+    double accg[7];
+    float acch[21];
 #pragma unroll
-    for (int i = 0; i < RF_NACC; ++i) acc[i] = 0.0;
+    for (int i = 0; i < 7; ++i) accg[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 21; ++i) acch[i] = 0.f;
     int used = 0;
-    for (int j = rank * RF_THREADS + tid; j < n; j += S * RF_THREADS) {
-      if (mask && !mask[base + j]) continue;
-      const size_t o = (base + j) * 3;
-      const int ci = cam ? min((int)cam[base + j], RF_MAX_CAMS - 1) : 0;
+    for (int k = 0; k < rows_per_thread; ++k) {
+      float pf[6];
+      int ci;
+      if (k < RF_CACHE_ROWS) {          // rows of this thread are the same in every evaluation: staged once in smem
+        ci = __float_as_int(cache[(k * 7 + 6) * RF_THREADS + tid]);
+        if (ci < 0) continue;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) pf[c] = cache[(k * 7 + c) * RF_THREADS + tid];
+      } else {
+        const int j = (k * S + rank) * RF_THREADS + tid;
+        if (j >= n || (mask && !mask[base + j])) continue;
+        const size_t o = (base + j) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { pf[c] = p_ref[o + c]; pf[3 + c] = f_cur[o + c]; }
+        ci = cam ? min((int)cam[base + j], RF_MAX_CAMS - 1) : 0;
+      }
       const double* Rt = rig.Rt[ci];
-      const double* M = Msh[ci];
-      const double d0 = (double)p_ref[o] - t[0], d1 = (double)p_ref[o + 1] - t[1], d2 = (double)p_ref[o + 2] - t[2];
+      const double d0 = (double)pf[0] - t[0], d1 = (double)pf[1] - t[1], d2 = (double)pf[2] - t[2];
       const double q[3] = {R[0] * d0 + R[3] * d1 + R[6] * d2, R[1] * d0 + R[4] * d1 + R[7] * d2,
                            R[2] * d0 + R[5] * d1 + R[8] * d2};                      // R^T (p - t)
       const double e0 = q[0] - Rt[3], e1 = q[1] - Rt[7], e2 = q[2] - Rt[11];
@@ -166,47 +219,65 @@ refine_kernel(const float* __restrict__ p_ref, const float* __restrict__ f_cur, 
                            Rt[2] * e0 + Rt[6] * e1 + Rt[10] * e2};                  // Rc^T (q - tc)
       const double ny2 = y[0] * y[0] + y[1] * y[1] + y[2] * y[2];
       if (!(ny2 > 0.0)) continue;
-      const double inv = 1.0 / sqrt(ny2);
+      const double inv = rsqrt(ny2);
       const double nv[3] = {y[0] * inv, y[1] * inv, y[2] * inv};
-      const double f[3] = {(double)f_cur[o], (double)f_cur[o + 1], (double)f_cur[o + 2]};
-      const double r = 1.0 - (f[0] * nv[0] + f[1] * nv[1] + f[2] * nv[2]);
-      // Dy = dy/dx (3x6): translation columns -M^T (dq = -R^T dt), rotation columns Rc^T [q]x (dq = [q]x d)
-      double N[3][6];
+      const double f[3] = {(double)pf[3], (double)pf[4], (double)pf[5]};
+      const double cosv = f[0] * nv[0] + f[1] * nv[1] + f[2] * nv[2];
+      const double r = 1.0 - cosv;
+      // float64 Jacobian row: dr/dy = g = -(f - cos n)/|y|;  h = Rc g;  dq = -R^T dt + [q]x d  ->  J = (-R h, h x q)
+      const double g0 = -(f[0] - cosv * nv[0]) * inv, g1 = -(f[1] - cosv * nv[1]) * inv, g2 = -(f[2] - cosv * nv[2]) * inv;
+      const double h[3] = {Rt[0] * g0 + Rt[1] * g1 + Rt[2] * g2, Rt[4] * g0 + Rt[5] * g1 + Rt[6] * g2,
+                           Rt[8] * g0 + Rt[9] * g1 + Rt[10] * g2};
+      double J[6];
+      J[0] = -(R[0] * h[0] + R[1] * h[1] + R[2] * h[2]);
+      J[1] = -(R[3] * h[0] + R[4] * h[1] + R[5] * h[2]);
+      J[2] = -(R[6] * h[0] + R[7] * h[1] + R[8] * h[2]);
+      J[3] = h[1] * q[2] - h[2] * q[1];
+      J[4] = h[2] * q[0] - h[0] * q[2];
+      J[5] = h[0] * q[1] - h[1] * q[0];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) accg[a] += J[a] * r;
+      accg[6] += r * r;
+      // float32 model Hessian J J^T + r N^T N with N = dn/dx = (I - n n^T) Dy / |y|, Dy = (-M^T | Rc^T [q]x).
+      // The second term is the part of r * d2r/dx2 that Gauss-Newton drops; because r = |f - n|^2 / 2 has a vanishing
+      // gradient at a perfect fit it is as large as J J^T and without it LM only converges linearly.  It is valid
+      // for small residuals, so rows with r >= RF_SECOND_ORDER_MAX get plain Gauss-Newton.
+      const float qf[3] = {(float)q[0], (float)q[1], (float)q[2]};
+      const float nf[3] = {(float)nv[0], (float)nv[1], (float)nv[2]};
+      const float invf = (float)inv;
+      float N[3][6];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        N[i][0] = -M[i];          // -(M^T)[i][0] = -M[0][i]
-        N[i][1] = -M[3 + i];
-        N[i][2] = -M[6 + i];
-        // Rc^T [q]x: row i = (column i of Rc) x ... : ([q]x)^T Rc[:,i] = -q x Rc[:,i] -> row_i = Rc[:,i] x q
-        const double a0 = Rt[i], a1 = Rt[4 + i], a2 = Rt[8 + i];
-        N[i][3] = a1 * q[2] - a2 * q[1];
-        N[i][4] = a2 * q[0] - a0 * q[2];
-        N[i][5] = a0 * q[1] - a1 * q[0];
+        N[i][0] = -Mf[ci][i];
+        N[i][1] = -Mf[ci][3 + i];
+        N[i][2] = -Mf[ci][6 + i];
+        const float a0 = Rcf[ci][i], a1 = Rcf[ci][3 + i], a2 = Rcf[ci][6 + i];   // column i of Rc
+        N[i][3] = a1 * qf[2] - a2 * qf[1];
+        N[i][4] = a2 * qf[0] - a0 * qf[2];
+        N[i][5] = a0 * qf[1] - a1 * qf[0];
       }
-      // N = dn/dx = (I - n n^T) Dy / |y|;  J = dr/dx = -f^T N
-      double J[6];
+      float Jf[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        const double nd = nv[0] * N[0][k] + nv[1] * N[1][k] + nv[2] * N[2][k];
+      for (int c = 0; c < 6; ++c) {
+        const float nd = nf[0] * N[0][c] + nf[1] * N[1][c] + nf[2] * N[2][c];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) N[i][k] = (N[i][k] - nv[i] * nd) * inv;
-        J[k] = -(f[0] * N[0][k] + f[1] * N[1][k] + f[2] * N[2][k]);
+        for (int i = 0; i < 3; ++i) N[i][c] = (N[i][c] - nf[i] * nd) * invf;
+        Jf[c] = (float)J[c];
       }
-      // model Hessian: J J^T + r N^T N.  The second term is the part of r * d2r/dx2 that Gauss-Newton drops; because
-      // r = |f - n|^2 / 2 has a vanishing gradient at a perfect fit it is as large as J J^T and without it LM only
-      // converges linearly.  It is valid for small residuals, so rows with r >= RF_SECOND_ORDER_MAX get plain GN.
-      const double w = r < RF_SECOND_ORDER_MAX ? r : 0.0;
-      int k = 0;
+      const float w = r < RF_SECOND_ORDER_MAX ? (float)r : 0.f;
+      int kk = 0;
 #pragma unroll
       for (int a = 0; a < 6; ++a)
 #pragma unroll
         for (int c = a; c < 6; ++c)
-          acc[k++] += J[a] * J[c] + w * (N[0][a] * N[0][c] + N[1][a] * N[1][c] + N[2][a] * N[2][c]);
-#pragma unroll
-      for (int a = 0; a < 6; ++a) acc[21 + a] += J[a] * r;
-      acc[27] += r * r;
+          acch[kk++] += Jf[a] * Jf[c] + w * (N[0][a] * N[0][c] + N[1][a] * N[1][c] + N[2][a] * N[2][c]);
       ++used;
     }
+    double acc[RF_NACC];
+#pragma unroll
+    for (int i = 0; i < 21; ++i) acc[i] = (double)acch[i];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) acc[21 + i] = accg[i];
 #pragma unroll
     for (int i = 0; i < RF_NACC; ++i) {
       double v = acc[i];
@@ -225,83 +296,112 @@ refine_kernel(const float* __restrict__ p_ref, const float* __restrict__ f_cur, 
     }
     cluster.sync();
 
-    // ---- rank 0: gather, decide, solve, scatter ----
-    if (rank == 0 && tid == 0) {
-      double tot[RF_NACC];
-      for (int i = 0; i < RF_NACC; ++i) tot[i] = 0.0;
-      for (int s = 0; s < S; ++s) {
-        const double* pp = cluster.map_shared_rank(partial, s);
-        for (int i = 0; i < RF_NACC; ++i) tot[i] += pp[i];
+    // ---- rank 0, warp 0: gather, decide, solve, scatter ----
+    // A lone thread issues one dependent instruction every ~8 cycles, so the control step is kept short: every lane of
+    // the warp runs the scalar logic redundantly (no divergence, no broadcasts), copies and DSMEM traffic are spread
+    // over the lanes, and the rotation update uses series instead of sin/cos.
+    if (rank == 0 && warp == 0) {
+      if (lane < RF_NACC) {               // one lane per accumulator, fixed rank order -> deterministic sums
+        double v = 0.0;
+        for (int s = 0; s < S; ++s) v += cluster.map_shared_rank(partial, s)[lane];
+        tot[lane] = v;
       }
+      __syncwarp();
       const double cost = tot[27];
+      const double prev_cost = cur_cost;
+      double lam = lambda, nuv = nu;
       int stop = 0;
       bool accepted = false;
       if (!have_cur) {
-        first_cost = cost;
         accepted = true;
-      } else if (cost < cur_cost) {
+      } else if (cost < prev_cost) {
         accepted = true;
-        if (cur_cost - cost <= 1e-14 * cur_cost) stop = 1;   // converged: no measurable decrease left
-        const double rho = (cur_cost - cost) / pred;          // Nielsen's gain-ratio damping update
+        if (prev_cost - cost <= 1e-14 * prev_cost) stop = 1;   // converged: no measurable decrease left
+        const double rho = (prev_cost - cost) / pred;           // Nielsen's gain-ratio damping update
         const double g3 = (2.0 * rho - 1.0) * (2.0 * rho - 1.0) * (2.0 * rho - 1.0);
-        lambda = fmax(lambda * fmax(1.0 / 3.0, 1.0 - g3), 1e-12);
-        nu = 2.0;
+        lam = fmax(lam * fmax(1.0 / 3.0, 1.0 - g3), 1e-12);
+        nuv = 2.0;
       } else {
-        if (step_max < 1e-9) stop = 1;                        // rejected although the step is at rounding level
-        lambda *= nu;
-        nu *= 2.0;
-        if (lambda > 1e12) stop = 1;
+        if (step_max < 1e-9) stop = 1;                          // rejected although the step is at rounding level
+        lam *= nuv;
+        nuv *= 2.0;
+        if (lam > 1e12) stop = 1;
       }
-      if (accepted) {
-        for (int i = 0; i < 9; ++i) curR[i] = st.R[i];
-        for (int i = 0; i < 3; ++i) curT[i] = st.t[i];
-        for (int i = 0; i < 21; ++i) curA[i] = tot[i];
-        for (int i = 0; i < 6; ++i) curG[i] = tot[21 + i];
-        cur_cost = cost;
-        have_cur = 1;
-      }
-      iters_done = it + 1;
       if (it + 1 >= max_iters || n_used_sh < 6 || !(cost == cost)) stop = 1;
+      const bool first = !have_cur;
+      __syncwarp();                        // everyone has read the scalars that lane 0 rewrites below
+      if (accepted) {
+        if (lane < 9) curR[lane] = st.R[lane];
+        else if (lane < 12) curT[lane - 9] = st.t[lane - 9];
+        if (lane < 27) curAG[lane] = tot[lane];
+      }
+      __syncwarp();
+      double A[21], g[6], dx[6];
+#pragma unroll
+      for (int i = 0; i < 21; ++i) A[i] = curAG[i];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) g[i] = curAG[21 + i];
+      double new_pred = pred, new_step = step_max;
       double nR[9], nT[3];
       if (!stop) {
-        double dx[6];
         bool ok = false;
         for (int tries = 0; tries < 40 && !ok; ++tries) {
-          ok = solve_damped(curA, curG, lambda, dx);
-          if (!ok) lambda *= 10.0;
+          ok = solve_damped(A, g, lam, dx);
+          if (!ok) lam *= 10.0;
         }
         double m = 0.0;
+#pragma unroll
         for (int i = 0; i < 6; ++i) m = fmax(m, fabs(dx[i]));
-        if (!ok || !(m == m) || m < 1e-14) {
+        if (!ok || !(m == m) || m < RF_STEP_TOL) {   // the proposed step is below what the float32 pose output resolves
           stop = 1;
         } else {
-          step_max = m;
+          new_step = m;
           double quad = 0.0, lin = 0.0;   // predicted decrease of sum r^2 under the model: -(2 g.dx + dx^T A dx)
           int k = 0;
+#pragma unroll
           for (int a = 0; a < 6; ++a) {
-            lin += curG[a] * dx[a];
-            for (int c = a; c < 6; ++c) { quad += (a == c ? 1.0 : 2.0) * curA[k] * dx[a] * dx[c]; ++k; }
+            lin += g[a] * dx[a];
+#pragma unroll
+            for (int c = a; c < 6; ++c) { quad += (a == c ? 1.0 : 2.0) * A[k] * dx[a] * dx[c]; ++k; }
           }
-          pred = -(2.0 * lin + quad);
-          if (!(pred > 0.0)) pred = 1e-300;
+          new_pred = -(2.0 * lin + quad);
+          if (!(new_pred > 0.0)) new_pred = 1e-300;
           double E[9];
           rodrigues(dx + 3, E);
+#pragma unroll
           for (int r = 0; r < 3; ++r)
+#pragma unroll
             for (int c = 0; c < 3; ++c)
               nR[r * 3 + c] = curR[r * 3] * E[c] + curR[r * 3 + 1] * E[3 + c] + curR[r * 3 + 2] * E[6 + c];
+#pragma unroll
           for (int i = 0; i < 3; ++i) nT[i] = curT[i] + dx[i];
         }
       }
       if (stop) {
+#pragma unroll
         for (int i = 0; i < 9; ++i) nR[i] = curR[i];
+#pragma unroll
         for (int i = 0; i < 3; ++i) nT[i] = curT[i];
       }
-      for (int s = 0; s < S; ++s) {
-        RefineState* q = cluster.map_shared_rank(&st, s);
-        for (int i = 0; i < 9; ++i) q->R[i] = nR[i];
-        for (int i = 0; i < 3; ++i) q->t[i] = nT[i];
-        q->stop = stop;
+      if (lane == 0) {
+        if (first) first_cost = cost;
+        if (accepted) { cur_cost = cost; have_cur = 1; }
+        lambda = lam; nu = nuv; pred = new_pred; step_max = new_step;
+        iters_done = it + 1;
       }
+      // lane l < 13 owns element l of the state (R 0..8, t 9..11, stop 12) and pushes it into every CTA of the cluster
+      double mine = 0.0;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) if (lane == i) mine = nR[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) if (lane == 9 + i) mine = nT[i];
+      if (lane < 13)
+        for (int s = 0; s < S; ++s) {
+          RefineState* q = cluster.map_shared_rank(&st, s);
+          if (lane < 9) q->R[lane] = mine;
+          else if (lane < 12) q->t[lane - 9] = mine;
+          else q->stop = stop;
+        }
     }
     cluster.sync();
     if (st.stop) break;
@@ -352,7 +452,8 @@ extern "C" int sos_refine_pose(sos_ctx* ctx, const float* p_ref, const float* f_
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(S, n_problems, 1);
   cfg.blockDim = dim3(RF_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = RF_CACHE_ROWS * 7 * RF_THREADS * sizeof(float);
+  SOS_CUDA(cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes));
   cfg.stream = ctx->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
