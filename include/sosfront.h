@@ -339,6 +339,9 @@ typedef struct sos_frontend_config {
   int32_t homogeneous_norm;    /* 1 = range gate on the homogeneous norm as the reference does (pose_est_tools.py:365-372) */
   int32_t refit;               /* SOS_REFINE_*: what turns the RANSAC pose into the output pose */
   int32_t refine_iters;        /* SOS_REFINE_LM: maximum cost evaluations (0 = 20) */
+  int32_t keyframe_mode;       /* 0: pair i = (slot i, slot i+1), the last frame is carried over automatically (throughput mode);
+                                  1: pair i = (slot ref_slot[i], slot i+1) and slot 0 only changes through sos_frontend_promote —
+                                     the reference's keyframe tracking (pose_est_tools.py:1489, 1553-1566), SURVEY §8f N2 */
   double ransac_threshold;     /* 1 - cos(5 deg) for SOS_SCORE_BEARING (pose_est_tools.py:675-676) */
   double stereo_max_du, stereo_min_dv; /* 2.5, 1 (pose_est_tools.py:298-304) */
   double temporal_max_du;      /* 0.125 * 0.5 * cols (pose_est_tools.py:866) */
@@ -370,6 +373,7 @@ typedef struct sos_frontend_buffers {
   uint8_t* inlier_mask;                            /* [batch, 2*cap] */
   int32_t* stats;                                  /* [batch, 4]: n_stereo, n_correspondences, n_inliers, best_hyp */
   double* refine_stats;                            /* [batch, 4] of sos_refine_pose (SOS_REFINE_LM only) */
+  int32_t* ref_slot;                               /* [batch] reference slot of pair i (keyframe_mode only) */
   int32_t batch, cap, launches_per_step;
 } sos_frontend_buffers;
 
@@ -382,6 +386,18 @@ int sos_frontend_create(sos_ctx* ctx, const sos_frontend_config* cfg, const sos_
 int sos_frontend_destroy(sos_frontend* fe);
 int sos_frontend_reset(sos_frontend* fe);                /* forget the carried reference frame */
 int sos_frontend_set_graph(sos_frontend* fe, int enabled); /* CUDA-graph replay (default) or eager launches */
+
+/* Keyframe mode (sos_frontend_config.keyframe_mode = 1), the device side of the reference's VO loop
+ * (pose_est_tools.py:1481-1566): a step tracks every frame of the batch against a reference slot, normally the current
+ * keyframe in slot 0; when the host's keyframe policy promotes frame j, the frames after j are re-tracked against it
+ * without repeating remap / stereo matching / triangulation.
+ *   set_ref_slots: HOST int32 [batch]; ref_slots[i] in [0, batch] is the store slot pair i tracks against (slot i+1 is
+ *                  the frame itself and not allowed), -1 switches pair i off.  Initially all 0.
+ *   promote:       copy store slot `slot` (1..batch) into slot 0.
+ *   retrack:       re-run temporal matching + RANSAC + refinement of the current store with the current ref_slots. */
+int sos_frontend_set_ref_slots(sos_frontend* fe, const int32_t* ref_slots);
+int sos_frontend_promote(sos_frontend* fe, int slot);
+int sos_frontend_retrack(sos_frontend* fe);
 int sos_frontend_get_buffers(sos_frontend* fe, sos_frontend_buffers* out);
 /* Same as sos_ctx_profile_begin/_end for the front-end's own launches (steps run eagerly while profiling). */
 int sos_frontend_profile_begin(sos_frontend* fe);

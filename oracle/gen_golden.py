@@ -337,6 +337,29 @@ def gen_arun():
     np.savez_compressed(os.path.join(OUT, "arun.npz"), **out)
 
 
+def gen_driver():
+    """Pose bookkeeping of run_VO (pose_est_tools.py:1510-1512, 1609-1612): the reference's metrics, quaternion and
+    matrix chaining on random rigid transforms (exact-rotation and slightly non-orthonormal, as float32 poses are)."""
+    from omnistereo import transformations as tr
+    rng = np.random.default_rng(6)
+    T = np.zeros((40, 4, 4))
+    for i in range(40):
+        M = tr.random_rotation_matrix(rng.random(3))
+        M[:3, 3] = rng.normal(size=3) * (0.001 if i % 4 == 0 else 0.3)
+        if i % 3 == 0:  # small rotation, like a frame-to-keyframe motion
+            M[:3, :3] = tr.rotation_matrix(rng.normal() * 0.02, rng.normal(size=3))[:3, :3]
+        if i % 5 == 0:
+            M[:3, :3] = M[:3, :3].astype(np.float32).astype(np.float64)
+        T[i] = M
+    out = dict(T=T,
+               quat=np.array([tr.quaternion_from_matrix(matrix=M, isprecise=False) for M in T]),
+               trans=np.array([tr.translation_from_matrix(matrix=M) for M in T]),
+               dist=np.array([tr.rpe_translation_metric(M) for M in T]),
+               angle=np.array([tr.rpe_rotation_metric(M) for M in T]),
+               chain=np.array([tr.concatenate_matrices(T[i], T[i + 1]) for i in range(39)]))
+    np.savez_compressed(os.path.join(OUT, "driver.npz"), **out)
+
+
 def main():
     if not os.path.isdir("/root/reference/omnistereo"):
         sys.exit("gen_golden needs /root/reference (build container only)")
@@ -352,6 +375,7 @@ def main():
         gen_lifting()
         gen_rgbd()
         gen_arun()
+        gen_driver()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -65,6 +65,9 @@ PROTOTYPES = {
     "sos_frontend_reset": (I, [C.c_void_p]),
     "sos_frontend_set_graph": (I, [C.c_void_p, I]),
     "sos_frontend_get_buffers": (I, [C.c_void_p, P]),
+    "sos_frontend_set_ref_slots": (I, [C.c_void_p, P]),
+    "sos_frontend_promote": (I, [C.c_void_p, I]),
+    "sos_frontend_retrack": (I, [C.c_void_p]),
     "sos_frontend_step": (I, [C.c_void_p, P, P, P, P, P, P, P]),
     "sos_frontend_submit_host": (I, [C.c_void_p, P, P, P, P, P, P, P, C.POINTER(I)]),
     "sos_frontend_wait_host": (I, [C.c_void_p, I, P, P]),

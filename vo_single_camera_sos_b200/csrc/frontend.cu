@@ -56,16 +56,20 @@ __global__ void gather_desc_kernel(const uint4* __restrict__ desc_top, const uin
   o[1] = __ldg(d + 1);
 }
 
-__global__ void temporal_segments_kernel(const int32_t* __restrict__ n, int B, int cap, int32_t* __restrict__ q_start,
-                                         int32_t* __restrict__ q_len, int32_t* __restrict__ t_start,
-                                         int32_t* __restrict__ t_len) {
+// Pair i tracks store slot i + 1 against its reference slot: slot i (consecutive frames) or ref_slot[i] (keyframe mode:
+// the slot of the tracking reference, pose_est_tools.py:1489; -1 = pair switched off).
+__global__ void temporal_segments_kernel(const int32_t* __restrict__ n, const int32_t* __restrict__ ref_slot, int B, int cap,
+                                         int32_t* __restrict__ q_start, int32_t* __restrict__ q_len,
+                                         int32_t* __restrict__ t_start, int32_t* __restrict__ t_len) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= 2 * B) return;
-  const int view = s / B, i = s % B;  // pair i: reference = slot i, current = slot i + 1
+  const int view = s / B, i = s % B;
+  const int r = ref_slot ? ref_slot[i] : i;
+  const bool on = r >= 0 && r <= B && r != i + 1;
   q_start[s] = (view * (B + 1) + i + 1) * cap;  // query = current frame (pose_est_tools.py:215)
-  q_len[s] = n[i + 1];
-  t_start[s] = (view * (B + 1) + i) * cap;      // train = reference frame
-  t_len[s] = n[i];
+  q_len[s] = on ? n[i + 1] : 0;
+  t_start[s] = (view * (B + 1) + (on ? r : 0)) * cap;  // train = reference frame
+  t_len[s] = on ? n[r] : 0;
 }
 
 // Stack the temporal matches of both views into one correspondence list per frame pair (pose_est_tools.py:752-778).
@@ -102,14 +106,15 @@ assemble_kernel(const int32_t* __restrict__ m_q, const int32_t* __restrict__ m_t
   }
 }
 
-__global__ void carry_over_kernel(int B, int cap, float* __restrict__ uv_top, float* __restrict__ uv_bot,
+// Store slot `from` -> slot 0 (the tracking reference of what follows).
+__global__ void carry_over_kernel(int B, int from, int cap, float* __restrict__ uv_top, float* __restrict__ uv_bot,
                                   float* __restrict__ b_top, float* __restrict__ b_bot, float* __restrict__ xyz,
                                   uint32_t* __restrict__ desc_c, int32_t* __restrict__ n) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int cnt = n[B];
+  const int cnt = n[from];
   if (k == 0) n[0] = cnt;
   if (k >= cnt) return;
-  const size_t src = (size_t)B * cap + k, dst = k;
+  const size_t src = (size_t)from * cap + k, dst = k;
   ((float2*)uv_top)[dst] = ((const float2*)uv_top)[src];
   ((float2*)uv_bot)[dst] = ((const float2*)uv_bot)[src];
 #pragma unroll
@@ -191,8 +196,8 @@ int fe_alloc(sos_frontend* fe, T** out, size_t count) {
   return SOS_OK;
 }
 
-// The kernel chain of one step, enqueued on ctx->stream.
-int enqueue_step(sos_frontend* fe, const uint8_t* omni, const float* px_top, const uint32_t* desc_top,
+// Stage A of a step (remap, stereo matching, lifting + triangulation into store slots 1..B), enqueued on ctx->stream.
+int enqueue_stage_a(sos_frontend* fe, const uint8_t* omni, const float* px_top, const uint32_t* desc_top,
                  const int32_t* boff_top, const float* px_bot, const uint32_t* desc_bot, const int32_t* boff_bot) {
   sos_ctx* ctx = fe->ctx;
   const sos_frontend_config& c = fe->cfg;
@@ -229,9 +234,19 @@ int enqueue_step(sos_frontend* fe, const uint8_t* omni, const float* px_top, con
                                                       d.n, B, cap, (uint4*)d.desc_c);
     SOS_LAUNCHED(ctx);
   }
+  return SOS_OK;
+}
+
+// Stage B: temporal matching against the reference slots, RANSAC, refinement.  Re-runnable on its own (sos_frontend_retrack).
+int enqueue_stage_b(sos_frontend* fe) {
+  sos_ctx* ctx = fe->ctx;
+  const sos_frontend_config& c = fe->cfg;
+  sos_frontend_buffers& d = fe->d;
+  const int B = c.batch, cap = c.cap;
+  int rc;
   // step 2b: temporal matching, 2 views x B pairs
-  temporal_segments_kernel<<<sos_div_up(2 * B, 128), 128, 0, ctx->stream>>>(d.n, B, cap, d.tm_q_start, d.tm_q_len,
-                                                                            d.tm_t_start, d.tm_t_len);
+  temporal_segments_kernel<<<sos_div_up(2 * B, 128), 128, 0, ctx->stream>>>(d.n, c.keyframe_mode ? d.ref_slot : nullptr, B, cap,
+                                                                            d.tm_q_start, d.tm_q_len, d.tm_t_start, d.tm_t_len);
   SOS_LAUNCHED(ctx);
   rc = sos_hamming_top2(ctx, d.desc_c, d.desc_c, d.tm_q_start, d.tm_q_len, d.tm_t_start, d.tm_t_len, 2 * B, cap, cap,
                         d.tm_idx0, d.tm_d0, nullptr, nullptr);
@@ -261,11 +276,27 @@ int enqueue_step(sos_frontend* fe, const uint8_t* omni, const float* px_top, con
   }
   stats_kernel<<<sos_div_up(B, 128), 128, 0, ctx->stream>>>(d.n, d.n_corr, d.best_count, d.best_hyp, B, d.stats);
   SOS_LAUNCHED(ctx);
-  // carry the last frame over as the reference of the next step: slot B -> slot 0 (one kernel instead of 8 copy nodes)
-  carry_over_kernel<<<sos_div_up(cap, 256), 256, 0, ctx->stream>>>(B, cap, d.uv_top, d.uv_bot, d.b_top, d.b_bot, d.xyz,
-                                                                    d.desc_c, d.n);
+  return SOS_OK;
+}
+
+int enqueue_carry(sos_frontend* fe, int from) {
+  sos_ctx* ctx = fe->ctx;
+  sos_frontend_buffers& d = fe->d;
+  carry_over_kernel<<<sos_div_up(fe->cfg.cap, 256), 256, 0, ctx->stream>>>(fe->cfg.batch, from, fe->cfg.cap, d.uv_top, d.uv_bot,
+                                                                            d.b_top, d.b_bot, d.xyz, d.desc_c, d.n);
   SOS_LAUNCHED(ctx);
   return SOS_OK;
+}
+
+// The kernel chain of one step.  Consecutive mode ends by carrying the last frame over as the reference of the next
+// step (slot B -> slot 0, one kernel instead of 8 copy nodes); in keyframe mode the caller promotes a slot itself.
+int enqueue_step(sos_frontend* fe, const uint8_t* omni, const float* px_top, const uint32_t* desc_top,
+                 const int32_t* boff_top, const float* px_bot, const uint32_t* desc_bot, const int32_t* boff_bot) {
+  int rc = enqueue_stage_a(fe, omni, px_top, desc_top, boff_top, px_bot, desc_bot, boff_bot);
+  if (rc) return rc;
+  rc = enqueue_stage_b(fe);
+  if (rc) return rc;
+  return fe->cfg.keyframe_mode ? SOS_OK : enqueue_carry(fe, fe->cfg.batch);
 }
 
 int run_step(sos_frontend* fe, const uint8_t* omni, const float* px_top, const uint32_t* desc_top, const int32_t* boff_top,
@@ -364,7 +395,7 @@ extern "C" int sos_frontend_create(sos_ctx* ctx, const sos_frontend_config* cfg,
   FE_ALLOC(p_ref, B * 2 * cap * 3); FE_ALLOC(p_cur, B * 2 * cap * 3); FE_ALLOC(f_cur, B * 2 * cap * 3);
   FE_ALLOC(cam, B * 2 * cap); FE_ALLOC(n_corr, B); FE_ALLOC(n_corr_top, B);
   FE_ALLOC(ransac_pose, B * 12); FE_ALLOC(pose, B * 12); FE_ALLOC(best_hyp, B); FE_ALLOC(best_count, B);
-  FE_ALLOC(n_refit, B); FE_ALLOC(inlier_mask, B * 2 * cap); FE_ALLOC(stats, B * 4); FE_ALLOC(refine_stats, B * 4);
+  FE_ALLOC(n_refit, B); FE_ALLOC(inlier_mask, B * 2 * cap); FE_ALLOC(stats, B * 4); FE_ALLOC(refine_stats, B * 4); FE_ALLOC(ref_slot, B);
 #undef FE_ALLOC
   if (rc != SOS_OK) {
     sos_frontend_destroy(fe);
@@ -411,6 +442,53 @@ extern "C" int sos_frontend_set_graph(sos_frontend* fe, int enabled) {
   SOS_CHECK_ARG(fe, "fe is NULL");
   fe->use_graph = enabled != 0;
   return SOS_OK;
+}
+
+namespace {
+struct Fence {  // order the front-end's own stream after / before the caller's stream
+  sos_frontend* fe;
+  explicit Fence(sos_frontend* f) : fe(f) {
+    cudaEventRecord(fe->ev_in, fe->parent->stream);
+    cudaStreamWaitEvent(fe->ctx->stream, fe->ev_in, 0);
+  }
+  ~Fence() {
+    cudaEventRecord(fe->ev_out, fe->ctx->stream);
+    cudaStreamWaitEvent(fe->parent->stream, fe->ev_out, 0);
+  }
+};
+}  // namespace
+
+extern "C" int sos_frontend_set_ref_slots(sos_frontend* fe, const int32_t* ref_slots) {
+  SOS_CHECK_ARG(fe && ref_slots, "NULL argument");
+  SOS_CHECK_ARG(fe->cfg.keyframe_mode, "reference slots are only used in keyframe mode");
+  for (int i = 0; i < fe->cfg.batch; ++i)
+    SOS_CHECK_ARG(ref_slots[i] >= -1 && ref_slots[i] <= fe->cfg.batch && ref_slots[i] != i + 1, "reference slot out of range");
+  SOS_CUDA(cudaSetDevice(fe->ctx->device));
+  Fence fence(fe);
+  SOS_CUDA(cudaMemcpyAsync(fe->d.ref_slot, ref_slots, sizeof(int32_t) * fe->cfg.batch, cudaMemcpyHostToDevice, fe->ctx->stream));
+  SOS_CUDA(cudaStreamSynchronize(fe->ctx->stream));  // ref_slots may be pageable / reused by the caller
+  return SOS_OK;
+}
+
+extern "C" int sos_frontend_promote(sos_frontend* fe, int slot) {
+  SOS_CHECK_ARG(fe, "fe is NULL");
+  SOS_CHECK_ARG(slot >= 1 && slot <= fe->cfg.batch, "slot out of range");
+  SOS_CUDA(cudaSetDevice(fe->ctx->device));
+  Fence fence(fe);
+  const int64_t before = fe->ctx->launches;
+  const int rc = enqueue_carry(fe, slot);
+  fe->parent->launches += fe->ctx->launches - before;
+  return rc;
+}
+
+extern "C" int sos_frontend_retrack(sos_frontend* fe) {
+  SOS_CHECK_ARG(fe, "fe is NULL");
+  SOS_CUDA(cudaSetDevice(fe->ctx->device));
+  Fence fence(fe);
+  const int64_t before = fe->ctx->launches;
+  const int rc = enqueue_stage_b(fe);
+  fe->parent->launches += fe->ctx->launches - before;
+  return rc;
 }
 
 extern "C" int sos_frontend_profile_begin(sos_frontend* fe) {

@@ -23,7 +23,7 @@ class _Config(C.Structure):
         ("pano_rows", C.c_int32), ("pano_cols", C.c_int32), ("n_buckets", C.c_int32),
         ("max_feat_per_view", C.c_int32), ("max_feat_per_bucket", C.c_int32), ("cap", C.c_int32),
         ("n_hyp", C.c_int32), ("score_mode", C.c_int32), ("homogeneous_norm", C.c_int32), ("refit", C.c_int32),
-        ("refine_iters", C.c_int32),
+        ("refine_iters", C.c_int32), ("keyframe_mode", C.c_int32),
         ("ransac_threshold", C.c_double), ("stereo_max_du", C.c_double), ("stereo_min_dv", C.c_double),
         ("temporal_max_du", C.c_double), ("min_range", C.c_double), ("max_range", C.c_double),
         ("pano_top", C.c_double * 6), ("pano_bot", C.c_double * 6), ("f_top", C.c_double * 3), ("f_bot", C.c_double * 3),
@@ -40,7 +40,7 @@ _BUF_FIELDS = [
     ("tm_idx0", "i32"), ("tm_d0", "i32"), ("tm_pair_q", "i32"), ("tm_pair_t", "i32"), ("tm_pair_d", "i32"),
     ("tm_pair_count", "i32"), ("p_ref", "f32"), ("p_cur", "f32"), ("f_cur", "f32"), ("cam", "u8"),
     ("n_corr", "i32"), ("n_corr_top", "i32"), ("ransac_pose", "f32"), ("pose", "f32"), ("best_hyp", "i32"),
-    ("best_count", "i32"), ("n_refit", "i32"), ("inlier_mask", "u8"), ("stats", "i32"), ("refine_stats", "f64"),
+    ("best_count", "i32"), ("n_refit", "i32"), ("inlier_mask", "u8"), ("stats", "i32"), ("refine_stats", "f64"), ("ref_slot", "i32"),
 ]
 
 
@@ -72,6 +72,7 @@ class FrontendConfig:
     homogeneous_norm: bool = True
     refit: int = 1                    # ops.REFINE_NONE / REFINE_ARUN / REFINE_LM (True == REFINE_ARUN)
     refine_iters: int = 0             # REFINE_LM: maximum cost evaluations (0 -> 20)
+    keyframe_mode: bool = False       # track against reference slots (set_ref_slots / promote / retrack)
     stereo_max_du: float = 2.5
     stereo_min_dv: float = 1.0
     temporal_max_du: Optional[float] = None   # None -> 0.125 * 0.5 * pano_cols
@@ -89,6 +90,7 @@ class FrontendConfig:
         c.homogeneous_norm = int(bool(self.homogeneous_norm))
         c.refit = int(self.refit)
         c.refine_iters = int(self.refine_iters)
+        c.keyframe_mode = int(bool(self.keyframe_mode))
         c.ransac_threshold = float(self.ransac_threshold)
         c.stereo_max_du, c.stereo_min_dv = float(self.stereo_max_du), float(self.stereo_min_dv)
         c.temporal_max_du = float(0.125 * 0.5 * self.pano_cols if self.temporal_max_du is None else self.temporal_max_du)
@@ -218,6 +220,19 @@ class Frontend:
         check(self.ctx.lib.sos_frontend_wait_host(self._h, int(ticket), poses.ctypes.data, stats.ctypes.data))
         return poses, stats
 
+    # -- keyframe mode (sos_frontend_config.keyframe_mode) ---------------------------------------------------------
+    def set_ref_slots(self, slots: Sequence[int]):
+        arr = np.ascontiguousarray(np.asarray(slots, np.int32))
+        if arr.shape != (self.cfg.batch,):
+            raise ValueError("one reference slot per pair of the batch")
+        check(self.ctx.lib.sos_frontend_set_ref_slots(self._h, arr.ctypes.data))
+
+    def promote(self, slot: int):
+        check(self.ctx.lib.sos_frontend_promote(self._h, int(slot)))
+
+    def retrack(self):
+        check(self.ctx.lib.sos_frontend_retrack(self._h))
+
     def step_host(self, *inputs):
         return self.wait_host(self.submit_host(*inputs))
 
@@ -239,7 +254,7 @@ class Frontend:
             "tm_pair_t": (2 * slots * cap,), "tm_pair_d": (2 * slots * cap,), "tm_pair_count": (2 * B,),
             "p_ref": (B, 2 * cap, 3), "p_cur": (B, 2 * cap, 3), "f_cur": (B, 2 * cap, 3), "cam": (B, 2 * cap),
             "n_corr": (B,), "n_corr_top": (B,), "ransac_pose": (B, 3, 4), "pose": (B, 3, 4), "best_hyp": (B,),
-            "best_count": (B,), "n_refit": (B,), "inlier_mask": (B, 2 * cap), "stats": (B, 4), "refine_stats": (B, 4),
+            "best_count": (B,), "n_refit": (B,), "inlier_mask": (B, 2 * cap), "stats": (B, 4), "refine_stats": (B, 4), "ref_slot": (B,),
         }
         out = {}
         for name, kind in _BUF_FIELDS:
