@@ -294,7 +294,7 @@ def run_gpu(args, rank, local_rank, world):
 
     roof = {}
     t = k_ms("sos_remap_u8#0")
-    roof["remap"] = {"kernel": "remap_kernel<3>", "bound": "hbm", "achieved": remap_bytes / (t * 1e-3) / 1e9, "peak": hbm_peak,
+    roof["remap"] = {"kernel": "remap3p_kernel", "bound": "hbm", "achieved": remap_bytes / (t * 1e-3) / 1e9, "peak": hbm_peak,
                      "unit": "GB/s", "frac": remap_bytes / (t * 1e-3) / 1e9 / hbm_peak, "ms": t, "peak_source": hbm_src,
                      "algorithmic_bytes": remap_bytes, "traffic": None}
     t = k_ms("sos_hamming_top2:partial:temporal")
@@ -316,9 +316,18 @@ def run_gpu(args, rank, local_rank, world):
                             "hypothesis_point_pairs": float(w.cfg.n_hyp) * float(n_corr.sum()), "traffic": None}
     t = k_ms("sos_stereo_lift_triangulate#0") + k_ms("sos_stereo_lift_triangulate#1")  # geometry + compaction
     lt_bytes = 53.0 * float(buf["st_pair_count"].sum())
-    roof["lift_triangulate"] = {"kernel": "stereo_lift_triangulate_kernel", "bound": "hbm", "achieved": lt_bytes / (t * 1e-3) / 1e9,
+    roof["lift_triangulate"] = {"kernel": "stereo_geometry_kernel + stereo_compact_kernel", "bound": "hbm", "achieved": lt_bytes / (t * 1e-3) / 1e9,
                                 "peak": hbm_peak, "unit": "GB/s", "frac": lt_bytes / (t * 1e-3) / 1e9 / hbm_peak, "ms": t,
                                 "traffic": None}
+    # DRAM traffic per launch from the committed ncu --set full captures (same workload and batch only)
+    tpath = os.path.join(ROOT, "profiles", "r01", "traffic.json")
+    if os.path.exists(tpath):
+        tr = json.load(open(tpath))
+        if tr.get("workload") == args.workload and tr.get("batch") == B:
+            for k in roof:
+                if k in tr:
+                    roof[k]["traffic"] = tr[k]
+                    roof[k]["traffic_source"] = "profiles/r01/traffic.json (ncu dram__bytes_read+write per launch)"
     dominant = max((k for k in roof if not math.isnan(roof[k]["ms"])), key=lambda k: roof[k]["ms"])
 
     # ---- reduce over ranks -------------------------------------------------------------------------------------------

@@ -1,3 +1,5 @@
+"""Count the distinct 128-byte lines one warp-wide tap load touches for several lane-to-pixel mappings, on the C2 LUT
+(CPU only; backs the remap analysis in DESIGN.md section 5)."""
 import sys; sys.path.insert(0,'/root/repo')
 import numpy as np
 from vo_single_camera_sos_b200 import synth
