@@ -179,16 +179,19 @@ class BatchedVO:
         # TrackerStereoSE3.track_frame refuses fewer than 2 * 3 * 0.33 * 2 correspondences (pose_est_tools.py:779-781)
         self.min_correspondences = 2 * 3 * (0.33 * 2) if min_correspondences is None else min_correspondences
         c = cfg
-        self._host = {
-            "omni": np.zeros((c.batch, c.src_h, c.src_w, c.channels), np.uint8),
-            "px_top": np.zeros((c.batch, c.max_feat_per_view, 2), np.float32),
-            "px_bot": np.zeros((c.batch, c.max_feat_per_view, 2), np.float32),
-            "desc_top": np.zeros((c.batch, c.max_feat_per_view, 32), np.uint8),
-            "desc_bot": np.zeros((c.batch, c.max_feat_per_view, 32), np.uint8),
-            "boff_top": np.zeros((c.batch, c.n_buckets + 1), np.int32),
-            "boff_bot": np.zeros((c.batch, c.n_buckets + 1), np.int32),
+        shapes = {
+            "omni": ((c.batch, c.src_h, c.src_w, c.channels), torch.uint8),
+            "px_top": ((c.batch, c.max_feat_per_view, 2), torch.float32),
+            "px_bot": ((c.batch, c.max_feat_per_view, 2), torch.float32),
+            "desc_top": ((c.batch, c.max_feat_per_view, 32), torch.uint8),
+            "desc_bot": ((c.batch, c.max_feat_per_view, 32), torch.uint8),
+            "boff_top": ((c.batch, c.n_buckets + 1), torch.int32),
+            "boff_bot": ((c.batch, c.n_buckets + 1), torch.int32),
         }
-        self._dev = {k: torch.from_numpy(v).to(ctx.device) for k, v in self._host.items()}
+        # pinned staging (one batch) + its device twin; frames are packed into the staging arrays on the host
+        self._pinned = {k: torch.zeros(shape, dtype=dt).pin_memory() for k, (shape, dt) in shapes.items()}
+        self._host = {k: v.numpy() for k, v in self._pinned.items()}
+        self._dev = {k: v.to(ctx.device) for k, v in self._pinned.items()}
 
     def close(self):
         self.fe.close()
@@ -200,7 +203,7 @@ class BatchedVO:
             h[len(frames):] = 0            # unused slots: empty frames (no features -> no work after the remap)
             for i, f in enumerate(frames):
                 h[i] = f[k]
-            self._dev[k].copy_(torch.from_numpy(h))
+            self._dev[k].copy_(self._pinned[k], non_blocking=True)
         assert len(frames) <= B
 
     def _read(self):
