@@ -210,7 +210,18 @@ def run_gpu(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL may print its version banner on stdout when the communicator comes up: keep stdout for the JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     ctx = ops.Context(local_rank)
     B, K, W = args.batch, args.steps, args.warmup
     n_sets = 2
@@ -331,6 +342,8 @@ def run_gpu(args, rank, local_rank, world):
     dominant = max((k for k in roof if not math.isnan(roof[k]["ms"])), key=lambda k: roof[k]["ms"])
 
     # ---- reduce over ranks -------------------------------------------------------------------------------------------
+    print(f"[bench rank {rank}] device-resident {ms_dev / K:.4f} ms/step, e2e {ms_e2e / K:.4f} ms/step, clocks {clocks}",
+          file=sys.stderr, flush=True)
     if world > 1:
         tt = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)

@@ -297,6 +297,18 @@ int sos_ransac_p3d_eval(sos_ctx* ctx, const float* p_ref, const float* p_cur, co
 int sos_refit_inliers(sos_ctx* ctx, const float* p_ref, const float* p_cur, const uint8_t* inlier_mask,
                       const int32_t* n, int n_problems, int cap, float* pose, int32_t* n_used);
 
+/* Dense triangulation of panoramic disparity maps into point clouds.
+ * replaces: OmniStereoModel.resolve_pano_correspondences_from_disparity_map (camera_models.py:2492-2538) + the lifting and
+ *           midpoint triangulation of triangulate_from_depth_map (camera_models.py:2567-2685, own midpoint method).
+ * disparity float32 [n_maps, rows, cols] is linked to the TOP panorama: pixel (u, v) matches (u, v - d) in the bottom
+ * panorama.  A pixel is valid iff roi_col0 <= u < roi_col1 (negative = whole width), d != 0, min_disparity <= d <=
+ * max_disparity (0 = the ROI-masked map's maximum) and v - d <= lowest_reference_row.
+ * xyz float32 [n_maps, rows, cols, 3] wrt [C] (NaN where invalid); valid uint8 [n_maps, rows, cols] (nullable). */
+int sos_dense_triangulate(sos_ctx* ctx, const double* pano_top, const double* pano_bot, const float* disparity,
+                          int n_maps, int rows, int cols, double min_disparity, double max_disparity,
+                          double lowest_reference_row, int roi_col0, int roi_col1, const double* f1,
+                          const double* f2, float* xyz, uint8_t* valid);
+
 /* Non-linear pose refinement on the inlier set.
  * replaces: pyopengv.absolute_pose_noncentral_optimize_nonlinear (pose_est_tools.py:830) and
  *           pyopengv.absolute_pose_optimize_nonlinear (pose_est_tools.py:937; n_cams = 0 -> central camera).

@@ -360,6 +360,39 @@ def gen_driver():
     np.savez_compressed(os.path.join(OUT, "driver.npz"), **out)
 
 
+def gen_dense():
+    """Dense triangulation of a panoramic disparity map: resolve_pano_correspondences_from_disparity_map
+    (camera_models.py:2492-2538) + the lifting / midpoint triangulation of triangulate_from_depth_map (:2567-2685,
+    use_opengv_triangulation=False) on a synthetic disparity map with zeros, out-of-range values and an ROI."""
+    gs, _ = build_gums()
+    top, bot = gs.top_model, gs.bot_model
+    rows, cols = top.panorama.rows, top.panorama.cols
+    rng = np.random.default_rng(8)
+    disp = rng.uniform(0.0, 14.0, (rows, cols)).astype(np.float32)
+    disp[rng.random((rows, cols)) < 0.3] = 0.0
+    disp[:, ::7] = np.round(disp[:, ::7])          # integer disparities, as a block matcher produces
+    disp = np.minimum(disp, np.arange(rows, dtype=np.float32)[:, None])   # the match stays inside the bottom panorama
+    out = dict(disparity=disp)
+    out.update(flat("pano_top_", pano_dict(top.panorama)))
+    out.update(flat("pano_bot_", pano_dict(bot.panorama)))
+    out["f1"], out["f2"] = top.F[:3, 0].copy(), bot.F[:3, 0].copy()
+    out["lowest_reference_row"] = np.float64(bot.panorama.get_panorama_row_from_elevation(bot.lowest_elevation_angle))
+    ref_uv = np.transpose(np.indices(disp.shape[::-1]), (1, 2, 0))
+    for tag, kw in (("all", dict(min_disparity=1, max_disparity=0, roi_cols=None)),
+                    ("roi", dict(min_disparity=2, max_disparity=9, roi_cols=(30, 150)))):
+        gs.disparity_map = disp
+        tp, bp, dd = gs.resolve_pano_correspondences_from_disparity_map(ref_uv, **kw)
+        az1, el1 = top.panorama.get_direction_angles_from_pixel_pano(tp, use_LUTs=False)
+        az2, el2 = bot.panorama.get_direction_angles_from_pixel_pano(bp, use_LUTs=False)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            xyz = gs.get_triangulated_point_from_direction_angles(dir_angs_top=(az1, el1), dir_angs_bot=(az2, el2),
+                                                                  use_midpoint_triangulation=True)
+        out[tag + "_top_px"], out[tag + "_bot_px"], out[tag + "_disp"], out[tag + "_xyz"] = tp[0], bp[0], dd, xyz[0, :, :3]
+        out[tag + "_args"] = np.array([kw["min_disparity"], kw["max_disparity"], *(kw["roi_cols"] or (-1, -1))], np.float64)
+    np.savez_compressed(os.path.join(OUT, "dense.npz"), **out)
+
+
 def main():
     if not os.path.isdir("/root/reference/omnistereo"):
         sys.exit("gen_golden needs /root/reference (build container only)")
@@ -376,6 +409,7 @@ def main():
         gen_rgbd()
         gen_arun()
         gen_driver()
+        gen_dense()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -76,6 +76,30 @@ def range_filter(xyz: np.ndarray, min_range: float = 0.0, max_range: float = 0.0
     return ok
 
 
+def dense_triangulate(pano_top: dict, pano_bot: dict, disparity: np.ndarray, f1, f2, min_disparity: float = 1.0,
+                      max_disparity: float = 0.0, lowest_reference_row: float = np.inf, roi_cols=None):
+    """Dense triangulation of a panoramic disparity map: the validity chain of
+    resolve_pano_correspondences_from_disparity_map (camera_models.py:2492-2538: ROI columns, d != 0, min <= d <= max with
+    max = 0 meaning the map's maximum, v - d <= lowest reference row), target pixel (u, v - d) in the bottom panorama,
+    then the lifting + midpoint triangulation of triangulate_from_depth_map (:2567-2685, own midpoint method).
+    -> xyz [rows, cols, 3] float64 (NaN where invalid), valid [rows, cols] bool."""
+    d = np.asarray(disparity, np.float64)
+    rows, cols = d.shape
+    if roi_cols is not None:
+        dd = np.zeros_like(d)
+        dd[:, roi_cols[0]:roi_cols[1]] = d[:, roi_cols[0]:roi_cols[1]]
+        d = dd
+    if max_disparity == 0:
+        max_disparity = d.max()
+    v, u = np.mgrid[:rows, :cols].astype(np.float64)
+    valid = (d != 0) & (min_disparity <= d) & (d <= max_disparity) & (v - d <= lowest_reference_row)
+    az1, el1 = pano_pixel_to_angles(pano_top, np.stack([u, v], -1))
+    az2, el2 = pano_pixel_to_angles(pano_bot, np.stack([u, v - d], -1))
+    xyz = triangulate_midpoint(az1, el1, az2, el2, f1, f2)
+    xyz[~valid] = np.nan
+    return xyz, valid
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # GUM
 # ---------------------------------------------------------------------------------------------------------------

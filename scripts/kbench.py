@@ -44,6 +44,28 @@ def bench_hamming(ctx, popc_peak, n=4500, segs=32, top2=False):
                 pairs_per_s=pairs / (ms * 1e-3), tpopc_equiv=tp, frac_of_popc_peak=tp / popc_peak)
 
 
+def bench_dense(ctx, hbm_peak, B=16, rows=849, cols=2400):
+    """Dense triangulation: 4 B disparity in, 12 B xyz + 1 B valid out per panorama pixel."""
+    from vo_single_camera_sos_b200 import synth
+    rig = synth.make_rig(2048, 2048, cols, seed=0)
+    rows = rig.pano["rows"]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    disp = [torch.rand((B, rows, cols), device="cuda", generator=g) * 40.0 for _ in range(2)]
+    for d in disp:
+        d[d < 6.0] = 0.0
+    out = ctx.dense_triangulate(rig.pano_vector(), rig.pano_vector(), disp[0], rig.f_top, rig.f_bot, 1.0, 64.0, rows - 1.0)
+    it = [0]
+
+    def run():
+        ctx.dense_triangulate(rig.pano_vector(), rig.pano_vector(), disp[it[0] & 1], rig.f_top, rig.f_bot, 1.0, 64.0, rows - 1.0,
+                              out=out)
+        it[0] += 1
+    ms = timeit(run)
+    nbytes = B * rows * cols * 17
+    return dict(kernel="dense_triangulate", ms=ms, pixels=B * rows * cols, gbps=nbytes / (ms * 1e-3) / 1e9,
+                frac_of_hbm_peak=nbytes / (ms * 1e-3) / 1e9 / hbm_peak, valid_frac=float(out[1].float().mean()))
+
+
 def bench_ransac(ctx, ffma_peak, n=8700, B=16, H=4096, mode=ops.SCORE_BEARING):
     rng = np.random.default_rng(0)
     cap = 16384
@@ -110,6 +132,8 @@ def main():
         res.append(bench_ransac(ctx, pk, mode=ops.SCORE_EUCLID))
     if what in ("remap", "all"):
         res.append(bench_remap(ctx, 6451.2))
+    if what in ("dense", "all"):
+        res.append(bench_dense(ctx, 6451.2))
     for r in res:
         print(json.dumps(r))
 

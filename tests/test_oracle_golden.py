@@ -144,3 +144,20 @@ def test_arun_and_score_oracle():
     assert np.allclose(sc, g["score_values"], rtol=0, atol=1e-14)
     assert np.array_equal(np.nonzero(sc < float(g["score_thr"]))[0], g["score_inliers"])
     assert ransac.num_iterations() == int(g["ransac_iters_default"]) == 210
+
+
+def test_dense_triangulation_oracle():
+    """the oracle's validity chain + geometry reproduce the reference's dense point list exactly."""
+    g = load_golden("dense.npz")
+    pt = {k[9:]: float(g[k]) for k in g if k.startswith("pano_top_")}
+    pb = {k[9:]: float(g[k]) for k in g if k.startswith("pano_bot_")}
+    for tag in ("all", "roi"):
+        a = g[tag + "_args"]
+        roi = None if a[2] < 0 else (int(a[2]), int(a[3]))
+        xyz, valid = geometry.dense_triangulate(pt, pb, g["disparity"], g["f1"], g["f2"], a[0], a[1],
+                                                float(g["lowest_reference_row"]), roi)
+        vt = valid.T
+        uu, vv = np.nonzero(vt)
+        assert np.array_equal(np.stack([uu, vv], 1), g[tag + "_top_px"])
+        assert np.allclose(xyz.transpose(1, 0, 2)[vt], g[tag + "_xyz"], rtol=1e-12, atol=1e-12)
+        assert np.array_equal(g[tag + "_bot_px"][:, 1], vv - g["disparity"][vv, uu])

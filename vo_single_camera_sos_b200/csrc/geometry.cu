@@ -198,6 +198,60 @@ __global__ void __launch_bounds__(ST_THREADS) stereo_compact_kernel(StereoArgs a
   }
 }
 
+// ---- N4: dense triangulation of a panoramic disparity map (camera_models.py:2492-2538, 2567-2685) -----------------
+// One thread per panorama pixel: 4 B in, 13 B out — an HBM-bound streaming kernel.  Per-column azimuth terms and per-row
+// elevations would be shared, but the kernel is far from the FP64 pipe's limit at 17 B per pixel, so they are recomputed.
+__global__ void __launch_bounds__(256)
+dense_triangulate_kernel(PanoP pano_top, PanoP pano_bot, const float* __restrict__ disparity, int rows, int cols, int n_maps,
+                         double min_disp, const float* __restrict__ max_disp_dev, double max_disp_host, double lowest_row,
+                         int roi0, int roi1, Vec3 f1, Vec3 f2, float* __restrict__ xyz, uint8_t* __restrict__ valid) {
+  const size_t per_map = (size_t)rows * cols;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per_map * n_maps) return;
+  const int map = (int)(i / per_map);
+  const size_t px = i - (size_t)map * per_map;
+  const int v = (int)(px / cols), u = (int)(px - (size_t)v * cols);
+  double d = (double)disparity[i];
+  if (u < roi0 || u >= roi1) d = 0.0;                                            // :2500-2503
+  const double dmax = max_disp_dev ? (double)max_disp_dev[map] : max_disp_host;  // :2507-2508 (0 -> the map's maximum)
+  const bool ok = d != 0.0 && min_disp <= d && d <= dmax && ((double)v - d) <= lowest_row;   // :2511-2525
+  float o0 = CUDART_NAN_F, o1 = CUDART_NAN_F, o2 = CUDART_NAN_F;
+  if (ok) {
+    double az1, el1, az2, el2;
+    pano_pixel_to_angles(pano_top, (double)u, (double)v, az1, el1);
+    pano_pixel_to_angles(pano_bot, (double)u, (double)v - d, az2, el2);          // :2529
+    const Vec3 P = triangulate_midpoint(az1, el1, az2, el2, f1, f2);
+    o0 = (float)P.x; o1 = (float)P.y; o2 = (float)P.z;
+  }
+  xyz[3 * i + 0] = o0;
+  xyz[3 * i + 1] = o1;
+  xyz[3 * i + 2] = o2;
+  if (valid) valid[i] = ok ? 1 : 0;
+}
+
+// per-map maximum of the ROI-masked disparity (max_disparity = 0 in the reference means "the map's maximum")
+__global__ void __launch_bounds__(1024)
+disparity_max_kernel(const float* __restrict__ disparity, int rows, int cols, int roi0, int roi1, float* __restrict__ out) {
+  __shared__ float red[32];
+  const size_t per_map = (size_t)rows * cols;
+  const float* d = disparity + (size_t)blockIdx.x * per_map;
+  float m = 0.f;   // the ROI mask writes zeros, so the maximum is never below 0 (camera_models.py:2500-2503)
+  bool any_outside = roi0 > 0 || roi1 < cols;
+  if (!any_outside) m = -CUDART_INF_F;
+  for (size_t k = threadIdx.x; k < per_map; k += blockDim.x) {
+    const int u = (int)(k % cols);
+    if (u >= roi0 && u < roi1) m = fmaxf(m, d[k]);
+  }
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, off));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = red[threadIdx.x];
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, off));
+    if (threadIdx.x == 0) out[blockIdx.x] = m;
+  }
+}
+
 // ---- F3: GUM forward projection, gum.py:2512-2562, 1368-1385, 2942-2959 ----------------------------------------
 __device__ __forceinline__ void gum_project(const GumP& g, Vec3 P, double& u, double& v) {
   const double nrm = sqrt(P.x * P.x + P.y * P.y + P.z * P.z);
@@ -564,6 +618,36 @@ extern "C" int sos_range_gate_f64(sos_ctx* ctx, const double* xyz, int n, double
   SOS_CHECK_ARG(xyz && valid, "NULL array");
   SOS_CUDA(cudaSetDevice(ctx->device));
   range_gate_kernel<<<sos_div_up(n, 256), 256, 0, ctx->stream>>>(xyz, n, rmin, rmax, homogeneous_norm, valid);
+  SOS_LAUNCHED(ctx);
+  return SOS_OK;
+}
+
+extern "C" int sos_dense_triangulate(sos_ctx* ctx, const double* pano_top, const double* pano_bot, const float* disparity,
+                                     int n_maps, int rows, int cols, double min_disparity, double max_disparity,
+                                     double lowest_reference_row, int roi_col0, int roi_col1, const double* f1,
+                                     const double* f2, float* xyz, uint8_t* valid) {
+  SOS_CHECK_ARG(ctx && pano_top && pano_bot && f1 && f2, "NULL argument");
+  SOS_CHECK_ARG(n_maps >= 0 && rows >= 0 && cols >= 0, "negative size");
+  if (n_maps == 0 || rows == 0 || cols == 0) return SOS_OK;
+  SOS_CHECK_ARG(disparity && xyz, "NULL array");
+  SOS_CHECK_ARG(n_maps <= 65535, "too many maps");
+  SOS_CUDA(cudaSetDevice(ctx->device));
+  if (roi_col0 < 0 || roi_col1 < 0) { roi_col0 = 0; roi_col1 = cols; }
+  roi_col1 = roi_col1 < cols ? roi_col1 : cols;
+  float* dmax = nullptr;
+  if (max_disparity == 0.0) {
+    void* ws = nullptr;
+    const int rc = sos_arena_get(ctx, sos_align_up((size_t)n_maps * sizeof(float), 256), &ws);
+    if (rc != SOS_OK) return rc;
+    dmax = (float*)ws;
+    disparity_max_kernel<<<n_maps, 1024, 0, ctx->stream>>>(disparity, rows, cols, roi_col0, roi_col1, dmax);
+    SOS_LAUNCHED(ctx);
+  }
+  const size_t total = (size_t)n_maps * rows * cols;
+  SOS_CHECK_ARG(total / 256 < (1ull << 31), "disparity maps too large");
+  dense_triangulate_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
+      load_pano(pano_top), load_pano(pano_bot), disparity, rows, cols, n_maps, min_disparity, dmax, max_disparity,
+      lowest_reference_row, roi_col0, roi_col1, {f1[0], f1[1], f1[2]}, {f2[0], f2[1], f2[2]}, xyz, valid);
   SOS_LAUNCHED(ctx);
   return SOS_OK;
 }

@@ -358,6 +358,28 @@ class OmniStereoModel(object):
         out[..., :3] = xyz.cpu().numpy().reshape(out.shape[:-1] + (3,))
         return out
 
+    # ---- N4: dense triangulation of the panoramic disparity map (camera_models.py:2492-2538, 2567-2685) ----------------
+    def triangulate_from_depth_map(self, min_disparity=1, max_disparity=0, roi_cols=None, use_midpoint_triangulation=True,
+                                   **unused):
+        """Point cloud of `self.disparity_map` (float32 rows x cols, linked to the top panorama).  Returns
+        (points_3D_wrt_C_homo [1, N, 4], top_pano_points_coords [1, N, 2]) in the reference's order (u-major); colours
+        and PCL export of generate_point_clouds (camera_models.py:2687-2790) are left to the caller."""
+        if not use_midpoint_triangulation:
+            raise NotImplementedError("only the midpoint method is implemented (see get_triangulated_point_from_direction_angles)")
+        top, bot = self.top_model.panorama, self.bot_model.panorama
+        disp = np.ascontiguousarray(self.disparity_map, np.float32)
+        # Panorama.get_panorama_row_from_elevation(bot.lowest_elevation_angle) (panorama.py:676-689)
+        lowest_row = float(np.uint((bot.cyl_height_max - np.tan(self.bot_model.lowest_elevation_angle)) / bot.pixel_size))
+        xyz, valid = device_context().dense_triangulate(top.pano_vector(), bot.pano_vector(), to_device(disp),
+                                                        self.top_model.F[:3, 0], self.bot_model.F[:3, 0],
+                                                        float(min_disparity), float(max_disparity), lowest_row, roi_cols)
+        vt = valid.cpu().numpy().astype(bool).T                       # [cols, rows]: u-major like np.indices(shape[::-1])
+        pts = xyz.cpu().numpy().astype(np.float64).transpose(1, 0, 2)[vt]
+        uu, vv = np.nonzero(vt)
+        homo = np.ones((1, len(pts), 4))
+        homo[0, :, :3] = pts
+        return homo, np.stack([uu, vv], 1)[np.newaxis, ...]
+
     def filter_panoramic_points_due_to_range(self, xyz_points_wrt_C, min_3D_range=0, max_3D_range=0.):
         """camera_models.py:3299-3321: norm over the LAST axis of whatever is passed (the frame code passes N x 4)."""
         p = np.asarray(xyz_points_wrt_C, np.float64)

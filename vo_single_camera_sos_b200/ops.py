@@ -262,6 +262,24 @@ class Context:
             float(rmax), int(bool(homogeneous_norm)), xyz.data_ptr(), valid.data_ptr()))
         return xyz, valid
 
+    def dense_triangulate(self, pano_top, pano_bot, disparity: torch.Tensor, f1, f2, min_disparity: float = 1.0,
+                          max_disparity: float = 0.0, lowest_reference_row: float = float("inf"), roi_cols=None, out=None):
+        """Disparity maps float32 [n, rows, cols] (or [rows, cols]) -> xyz float32 [..., rows, cols, 3] (NaN = invalid),
+        valid uint8 [..., rows, cols]  (sos_dense_triangulate)."""
+        self._sync_stream()
+        squeeze = disparity.dim() == 2
+        d = disparity[None] if squeeze else disparity
+        n, rows, cols = d.shape
+        pt, pb = _darr(pano_top, 6, "pano_top"), _darr(pano_bot, 6, "pano_bot")
+        a, b = _darr(f1, 3, "f1"), _darr(f2, 3, "f2")
+        xyz, valid = out if out is not None else (self.empty((n, rows, cols, 3), torch.float32),
+                                                  self.empty((n, rows, cols), torch.uint8))
+        r0, r1 = (-1, -1) if roi_cols is None else (int(roi_cols[0]), int(roi_cols[1]))
+        check(self.lib.sos_dense_triangulate(
+            self._h, _ptr(pt), _ptr(pb), self._t(d, torch.float32, "disparity"), n, rows, cols, float(min_disparity),
+            float(max_disparity), float(lowest_reference_row), r0, r1, _ptr(a), _ptr(b), xyz.data_ptr(), valid.data_ptr()))
+        return (xyz[0], valid[0]) if squeeze and out is None else (xyz, valid)
+
     def lift_gum(self, gum, uv: torch.Tensor):
         self._sync_stream()
         g = _darr(gum, len(GUM_FIELDS), "gum")
