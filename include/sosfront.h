@@ -441,6 +441,7 @@ int sos_frontend_step_host(sos_frontend* fe, const uint8_t* omni, const float* p
  * ---------------------------------------------------------------------------------------------- */
 int sos_peak_popc(sos_ctx* ctx, double* tera_popc_per_s);
 int sos_peak_ffma(sos_ctx* ctx, double* tflops);
+int sos_peak_dfma(sos_ctx* ctx, double* tflops); /* float64 FMA pipe (dense triangulation, LM refinement) */
 
 #ifdef __cplusplus
 }

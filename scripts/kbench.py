@@ -60,10 +60,17 @@ def bench_dense(ctx, hbm_peak, B=16, rows=849, cols=2400):
         ctx.dense_triangulate(rig.pano_vector(), rig.pano_vector(), disp[it[0] & 1], rig.f_top, rig.f_bot, 1.0, 64.0, rows - 1.0,
                               out=out)
         it[0] += 1
-    ms = timeit(run)
+    ms_call = timeit(run)          # per call incl. host overhead of the wrapper
+    ctx.profile_begin()            # per launch, CUDA events on the launching stream
+    for _ in range(20):
+        run()
+    marks = ctx.profile_end()
+    per = {"column_table": [t for _, t in marks[0::2]], "dense": [t for _, t in marks[1::2]]}   # two launches per call
+    ms = float(np.median(per["dense"]))
     nbytes = B * rows * cols * 17
-    return dict(kernel="dense_triangulate", ms=ms, pixels=B * rows * cols, gbps=nbytes / (ms * 1e-3) / 1e9,
-                frac_of_hbm_peak=nbytes / (ms * 1e-3) / 1e9 / hbm_peak, valid_frac=float(out[1].float().mean()))
+    return dict(kernel="dense_triangulate", ms=ms, ms_per_call=ms_call, pixels=B * rows * cols, gbps=nbytes / (ms * 1e-3) / 1e9,
+                frac_of_hbm_peak=nbytes / (ms * 1e-3) / 1e9 / hbm_peak, valid_frac=float(out[1].float().mean()),
+                launches={k: float(np.median(v)) for k, v in per.items()})
 
 
 def bench_ransac(ctx, ffma_peak, n=8700, B=16, H=4096, mode=ops.SCORE_BEARING):

@@ -75,6 +75,7 @@ PROTOTYPES = {
     "sos_frontend_step_host": (I, [C.c_void_p, P, P, P, P, P, P, P, P, P]),
     "sos_peak_popc": (I, [c_ctx, C.POINTER(D)]),
     "sos_peak_ffma": (I, [c_ctx, C.POINTER(D)]),
+    "sos_peak_dfma": (I, [c_ctx, C.POINTER(D)]),
 }
 
 

@@ -199,34 +199,88 @@ __global__ void __launch_bounds__(ST_THREADS) stereo_compact_kernel(StereoArgs a
 }
 
 // ---- N4: dense triangulation of a panoramic disparity map (camera_models.py:2492-2538, 2567-2685) -----------------
-// One thread per panorama pixel: 4 B in, 13 B out — an HBM-bound streaming kernel.  Per-column azimuth terms and per-row
-// elevations would be shared, but the kernel is far from the FP64 pipe's limit at 17 B per pixel, so they are recomputed.
+// One thread per panorama pixel: 4 B in, 13 B out — meant to be an HBM-bound streaming kernel, so the float64 work per
+// pixel is kept to ~40 FMAs and one reciprocal:
+//   * rays on the unit cylinder are v = (cos az, sin az, tan el) with tan(el) = tan(atan2(h, r)) = h / r: no atan/tan;
+//   * cos/sin of the azimuth depend on the column only: a per-column table (built by dense_column_table_kernel);
+//   * with w = v1 x v2 and b = f2 - f1 the 3x3 solve of triangulate_midpoint() collapses to
+//       P = f1 + ((b x v2).w / |w|^2) v1 + 0.5 (w.b / |w|^2) w        (n = w/|w|, det[v1,-v2,n] = -|w|).
+//   Everything that depends on the column only is tabulated too (w.z, (b x v2).z, b.z sin az2, b.z cos az2).
+__global__ void dense_column_table_kernel(PanoP pano_top, PanoP pano_bot, Vec3 b, int cols, double4* __restrict__ table) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= cols) return;
+  double az1, az2, el;
+  pano_pixel_to_angles(pano_top, (double)u, 0.0, az1, el);
+  pano_pixel_to_angles(pano_bot, (double)u, 0.0, az2, el);
+  double c1, s1, c2, s2;
+  sincos(az1, &s1, &c1);
+  sincos(az2, &s2, &c2);
+  table[2 * u + 0] = make_double4(c1, s1, c2, s2);
+  table[2 * u + 1] = make_double4(c1 * s2 - s1 * c2, b.x * s2 - b.y * c2, b.z * s2, b.z * c2);   // w.z, (b x v2).z, ...
+}
+
+constexpr int DT_ROWS = 16;   // rows per block: the column terms live in registers and are reused for all of them
+
 __global__ void __launch_bounds__(256)
-dense_triangulate_kernel(PanoP pano_top, PanoP pano_bot, const float* __restrict__ disparity, int rows, int cols, int n_maps,
+dense_triangulate_kernel(PanoP pano_top, PanoP pano_bot, const double4* __restrict__ table,
+                         const float* __restrict__ disparity, int rows, int cols, int n_maps,
                          double min_disp, const float* __restrict__ max_disp_dev, double max_disp_host, double lowest_row,
-                         int roi0, int roi1, Vec3 f1, Vec3 f2, float* __restrict__ xyz, uint8_t* __restrict__ valid) {
-  const size_t per_map = (size_t)rows * cols;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= per_map * n_maps) return;
-  const int map = (int)(i / per_map);
-  const size_t px = i - (size_t)map * per_map;
-  const int v = (int)(px / cols), u = (int)(px - (size_t)v * cols);
-  double d = (double)disparity[i];
-  if (u < roi0 || u >= roi1) d = 0.0;                                            // :2500-2503
+                         int roi0, int roi1, Vec3 f1, Vec3 f2, double inv_r_top, double inv_r_bot, float* __restrict__ xyz,
+                         uint8_t* __restrict__ valid) {
+  // grid = (column blocks, row chunks, maps); thread = one panorama column, looping over DT_ROWS rows
+  __shared__ float sxyz[3 * 256];   // a row segment's 256 x 3 floats leave as three fully coalesced store instructions
+  const int u = blockIdx.x * blockDim.x + threadIdx.x, map = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool inside = u < cols;
+  const int uc = inside ? u : cols - 1;
+  const double4 cs = table[2 * uc], ct = table[2 * uc + 1];
+  const Vec3 b = {f2.x - f1.x, f2.y - f1.y, f2.z - f1.z};
   const double dmax = max_disp_dev ? (double)max_disp_dev[map] : max_disp_host;  // :2507-2508 (0 -> the map's maximum)
-  const bool ok = d != 0.0 && min_disp <= d && d <= dmax && ((double)v - d) <= lowest_row;   // :2511-2525
-  float o0 = CUDART_NAN_F, o1 = CUDART_NAN_F, o2 = CUDART_NAN_F;
-  if (ok) {
-    double az1, el1, az2, el2;
-    pano_pixel_to_angles(pano_top, (double)u, (double)v, az1, el1);
-    pano_pixel_to_angles(pano_bot, (double)u, (double)v - d, az2, el2);          // :2529
-    const Vec3 P = triangulate_midpoint(az1, el1, az2, el2, f1, f2);
-    o0 = (float)P.x; o1 = (float)P.y; o2 = (float)P.z;
+  const bool in_roi = inside && u >= roi0 && u < roi1;                            // :2500-2503
+  const int u0 = blockIdx.x * blockDim.x;
+  const int nfl = 3 * min((int)blockDim.x, cols - u0);
+  const int v0 = blockIdx.y * DT_ROWS;
+  const int v_end = min(rows, v0 + DT_ROWS);
+  float dreg[DT_ROWS];   // all disparities of the block's rows are in flight before the first one is used
+#pragma unroll
+  for (int k = 0; k < DT_ROWS; ++k)
+    dreg[k] = (in_roi && v0 + k < rows) ? __ldg(disparity + ((size_t)map * rows + v0 + k) * cols + uc) : 0.f;
+#pragma unroll
+  for (int k = 0; k < DT_ROWS; ++k) {
+    const int v = v0 + k;
+    if (v >= v_end) break;
+    const size_t i = ((size_t)map * rows + v) * cols + uc;
+    const double d = (double)dreg[k];
+    const bool ok = d != 0.0 && min_disp <= d && d <= dmax && ((double)v - d) <= lowest_row;   // :2511-2525
+    float o0 = CUDART_NAN_F, o1 = CUDART_NAN_F, o2 = CUDART_NAN_F;
+    const double vb = (double)v - d;                                               // :2529: bottom pixel (u, v - d)
+    if (ok && 0.0 <= vb && vb < pano_bot.v[SOS_PANO_ROWS] && (double)v < pano_top.v[SOS_PANO_ROWS]) {
+      const double t1 = (pano_top.v[SOS_PANO_HEIGHT_MAX] - pano_top.v[SOS_PANO_PIXEL_SIZE] * (double)v) * inv_r_top;
+      const double t2 = (pano_bot.v[SOS_PANO_HEIGHT_MAX] - pano_bot.v[SOS_PANO_PIXEL_SIZE] * vb) * inv_r_bot;
+      const Vec3 w = {cs.y * t2 - t1 * cs.w, t1 * cs.z - cs.x * t2, ct.x};      // v1 x v2
+      const Vec3 bv = {b.y * t2 - ct.z, ct.w - b.x * t2, ct.y};                  // b x v2
+      const double inv = 1.0 / (w.x * w.x + w.y * w.y + w.z * w.z);
+      const double l1 = (bv.x * w.x + bv.y * w.y + bv.z * w.z) * inv;
+      const double hp = 0.5 * (w.x * b.x + w.y * b.y + w.z * b.z) * inv;
+      o0 = (float)(f1.x + l1 * cs.x + hp * w.x);
+      o1 = (float)(f1.y + l1 * cs.y + hp * w.y);
+      o2 = (float)(f1.z + l1 * t1 + hp * w.z);
+    }
+    // each warp stages its 32 x 3 floats and writes them as three coalesced 128-byte stores: no block-wide barrier
+    float* sw = sxyz + 96 * warp;
+    sw[3 * lane + 0] = o0;
+    sw[3 * lane + 1] = o1;
+    sw[3 * lane + 2] = o2;
+    if (valid && inside) valid[i] = ok ? 1 : 0;
+    __syncwarp();
+    float* dst = xyz + 3 * (((size_t)map * rows + v) * cols + u0 + 32 * warp);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const int j = q * 32 + lane;
+      if (96 * warp + j < nfl) dst[j] = sw[j];
+    }
+    __syncwarp();
   }
-  xyz[3 * i + 0] = o0;
-  xyz[3 * i + 1] = o1;
-  xyz[3 * i + 2] = o2;
-  if (valid) valid[i] = ok ? 1 : 0;
 }
 
 // per-map maximum of the ROI-masked disparity (max_disparity = 0 in the reference means "the map's maximum")
@@ -635,19 +689,24 @@ extern "C" int sos_dense_triangulate(sos_ctx* ctx, const double* pano_top, const
   if (roi_col0 < 0 || roi_col1 < 0) { roi_col0 = 0; roi_col1 = cols; }
   roi_col1 = roi_col1 < cols ? roi_col1 : cols;
   float* dmax = nullptr;
+  void* ws = nullptr;
+  const size_t table_bytes = sos_align_up((size_t)cols * 2 * sizeof(double4), 256);
+  const int rc = sos_arena_get(ctx, table_bytes + sos_align_up((size_t)n_maps * sizeof(float), 256), &ws);
+  if (rc != SOS_OK) return rc;
+  double4* table = (double4*)ws;
+  dense_column_table_kernel<<<sos_div_up(cols, 256), 256, 0, ctx->stream>>>(
+      load_pano(pano_top), load_pano(pano_bot), {f2[0] - f1[0], f2[1] - f1[1], f2[2] - f1[2]}, cols, table);
+  SOS_LAUNCHED(ctx);
   if (max_disparity == 0.0) {
-    void* ws = nullptr;
-    const int rc = sos_arena_get(ctx, sos_align_up((size_t)n_maps * sizeof(float), 256), &ws);
-    if (rc != SOS_OK) return rc;
-    dmax = (float*)ws;
+    dmax = (float*)((uint8_t*)ws + table_bytes);
     disparity_max_kernel<<<n_maps, 1024, 0, ctx->stream>>>(disparity, rows, cols, roi_col0, roi_col1, dmax);
     SOS_LAUNCHED(ctx);
   }
-  const size_t total = (size_t)n_maps * rows * cols;
-  SOS_CHECK_ARG(total / 256 < (1ull << 31), "disparity maps too large");
-  dense_triangulate_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
-      load_pano(pano_top), load_pano(pano_bot), disparity, rows, cols, n_maps, min_disparity, dmax, max_disparity,
-      lowest_reference_row, roi_col0, roi_col1, {f1[0], f1[1], f1[2]}, {f2[0], f2[1], f2[2]}, xyz, valid);
+  SOS_CHECK_ARG(rows <= 65535, "more than 65535 panorama rows");
+  dense_triangulate_kernel<<<dim3(sos_div_up(cols, 256), sos_div_up(rows, DT_ROWS), n_maps), 256, 0, ctx->stream>>>(
+      load_pano(pano_top), load_pano(pano_bot), table, disparity, rows, cols, n_maps, min_disparity, dmax, max_disparity,
+      lowest_reference_row, roi_col0, roi_col1, {f1[0], f1[1], f1[2]}, {f2[0], f2[1], f2[2]},
+      1.0 / pano_top[SOS_PANO_RADIUS], 1.0 / pano_bot[SOS_PANO_RADIUS], xyz, valid);
   SOS_LAUNCHED(ctx);
   return SOS_OK;
 }

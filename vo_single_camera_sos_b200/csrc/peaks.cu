@@ -41,6 +41,20 @@ __global__ void __launch_bounds__(256) ffma_peak_kernel(float a, float b, float*
   if (s == 12345.678f) out[0] = s;
 }
 
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double a, double b, double* out) {
+  double x[PK_ILP];
+#pragma unroll
+  for (int i = 0; i < PK_ILP; ++i) x[i] = a * (double)(threadIdx.x + i);
+  for (int it = 0; it < PK_ITERS / 4; ++it) {
+#pragma unroll
+    for (int i = 0; i < PK_ILP; ++i) x[i] = fma(x[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < PK_ILP; ++i) s += x[i];
+  if (s == 12345.678) out[0] = s;
+}
+
 template <typename F>
 int time_kernel(sos_ctx* ctx, F launch, float* best_ms) {
   cudaEvent_t e0, e1;
@@ -90,5 +104,20 @@ extern "C" int sos_peak_ffma(sos_ctx* ctx, double* tflops) {
   if (rc != SOS_OK) return rc;
   SOS_CUDA(cudaGetLastError());
   *tflops = 2.0 * (double)blocks * 256.0 * PK_ITERS * PK_ILP / (ms * 1e-3) / 1e12;
+  return SOS_OK;
+}
+
+extern "C" int sos_peak_dfma(sos_ctx* ctx, double* tflops) {
+  SOS_CHECK_ARG(ctx && tflops, "NULL argument");
+  SOS_CUDA(cudaSetDevice(ctx->device));
+  void* scratch;
+  int rc = sos_arena_get(ctx, 256, &scratch);
+  if (rc != SOS_OK) return rc;
+  const int blocks = ctx->sm_count * 16;
+  float ms;
+  rc = time_kernel(ctx, [&] { dfma_peak_kernel<<<blocks, 256, 0, ctx->stream>>>(1.0000001, 0.5, (double*)scratch); ctx->launches++; }, &ms);
+  if (rc != SOS_OK) return rc;
+  SOS_CUDA(cudaGetLastError());
+  *tflops = 2.0 * (double)blocks * 256.0 * (PK_ITERS / 4) * PK_ILP / (ms * 1e-3) / 1e12;
   return SOS_OK;
 }

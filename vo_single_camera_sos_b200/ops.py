@@ -456,11 +456,31 @@ class Context:
             pose64.data_ptr(), stats.data_ptr()))
         return pose, pose64, stats
 
+    # -- per-launch device timing (sos_ctx_profile_*) ------------------------------------------------------------
+    def profile_begin(self):
+        self._sync_stream()
+        check(self.lib.sos_ctx_profile_begin(self._h))
+
+    def profile_end(self, max_n: int = 4096):
+        """-> list of (entry point name#launch index, milliseconds) in launch order."""
+        names = C.create_string_buffer(64 * max_n)
+        ms = (C.c_float * max_n)()
+        n = C.c_int()
+        check(self.lib.sos_ctx_profile_end(self._h, names, len(names), ms, max_n, C.byref(n)))
+        nm = names.value.decode().split("\n")[: n.value]
+        return [(nm[i], float(ms[i])) for i in range(n.value)]
+
     # -- roofline denominators -----------------------------------------------------------------------------------
     def peak_popc(self) -> float:
         self._sync_stream()
         v = C.c_double()
         check(self.lib.sos_peak_popc(self._h, C.byref(v)))
+        return v.value
+
+    def peak_dfma(self) -> float:
+        self._sync_stream()
+        v = C.c_double()
+        check(self.lib.sos_peak_dfma(self._h, C.byref(v)))
         return v.value
 
     def peak_ffma(self) -> float:
