@@ -297,6 +297,26 @@ int sos_ransac_p3d_eval(sos_ctx* ctx, const float* p_ref, const float* p_cur, co
 int sos_refit_inliers(sos_ctx* ctx, const float* p_ref, const float* p_cur, const uint8_t* inlier_mask,
                       const int32_t* n, int n_problems, int cap, float* pose, int32_t* n_used);
 
+/* ------------------------------------------------------------------------------------------------
+ * Feature description on the panoramas (description half)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* replaces: cv2.cvtColor(pano_img, cv2.COLOR_BGR2GRAY) (camera_models.py:1711).  Bit-exact with OpenCV 4.x (15-bit fixed point). */
+int sos_bgr_to_gray(sos_ctx* ctx, const uint8_t* bgr, size_t n_pixels, uint8_t* gray);
+
+/* The blur inside cv2.ORB.compute: separable 7-tap Gaussian of sigma 2, BORDER_REFLECT_101, exact arithmetic rounded
+ * once (not cv2.GaussianBlur's fixed-point path; identified and pinned by oracle/derive_orb_pattern.py).
+ * gray, blurred: uint8 [n_images, height, width]; not in place. */
+int sos_orb_blur(sos_ctx* ctx, const uint8_t* gray, int n_images, int height, int width, uint8_t* blurred);
+
+/* replaces: cv2.ORB_create(nfeatures).compute(image = gray panorama, keypoints) (camera_models.py:1683, 1766) for
+ * keypoints of octave 0 (what cv2.KeyPoint_convert and single-scale detectors produce).  Bit-exact with OpenCV 4.13.
+ *   kp_xy        float32 [n, 2] pixel coordinates          kp_angle_deg float32 [n] or NULL (= -1, KeyPoint_convert's angle)
+ *   kp_image     int32 [n] image index or NULL (= 0)       desc uint32 [n, 8] (256 bits, OpenCV byte order)
+ *   keep         uint8 [n] (nullable): 0 where OpenCV drops the keypoint (closer than 31 px to the border; desc = 0) */
+int sos_orb_describe(sos_ctx* ctx, const uint8_t* gray, int n_images, int height, int width, const float* kp_xy,
+                     const float* kp_angle_deg, const int32_t* kp_image, int n, uint32_t* desc, uint8_t* keep);
+
 /* Dense triangulation of panoramic disparity maps into point clouds.
  * replaces: OmniStereoModel.resolve_pano_correspondences_from_disparity_map (camera_models.py:2492-2538) + the lifting and
  *           midpoint triangulation of triangulate_from_depth_map (camera_models.py:2567-2685, own midpoint method).

@@ -262,6 +262,36 @@ class Context:
             float(rmax), int(bool(homogeneous_norm)), xyz.data_ptr(), valid.data_ptr()))
         return xyz, valid
 
+    # -- N3: feature description ---------------------------------------------------------------------------------
+    def bgr_to_gray(self, bgr: torch.Tensor) -> torch.Tensor:
+        """uint8 [..., 3] -> uint8 [...]  (cv2.COLOR_BGR2GRAY, bit-exact)."""
+        self._sync_stream()
+        if bgr.shape[-1] != 3:
+            raise ValueError("expected a [..., 3] BGR image")
+        gray = self.empty(tuple(bgr.shape[:-1]), torch.uint8)
+        check(self.lib.sos_bgr_to_gray(self._h, self._t(bgr, torch.uint8, "bgr"), gray.numel(), gray.data_ptr()))
+        return gray
+
+    def orb_blur(self, gray: torch.Tensor) -> torch.Tensor:
+        self._sync_stream()
+        g = gray[None] if gray.dim() == 2 else gray
+        out = self.empty(tuple(g.shape), torch.uint8)
+        check(self.lib.sos_orb_blur(self._h, self._t(g, torch.uint8, "gray"), g.shape[0], g.shape[1], g.shape[2], out.data_ptr()))
+        return out[0] if gray.dim() == 2 else out
+
+    def orb_describe(self, gray: torch.Tensor, kp_xy: torch.Tensor, kp_angle_deg=None, kp_image=None):
+        """gray uint8 [H, W] or [n_images, H, W]; kp_xy float32 [n, 2] -> (desc uint8 [n, 32], keep uint8 [n])."""
+        self._sync_stream()
+        g = gray[None] if gray.dim() == 2 else gray
+        n = kp_xy.shape[0]
+        desc = self.empty((n, 32), torch.uint8)
+        keep = self.empty((n,), torch.uint8)
+        check(self.lib.sos_orb_describe(
+            self._h, self._t(g, torch.uint8, "gray"), g.shape[0], g.shape[1], g.shape[2], self._t(kp_xy, torch.float32, "kp_xy"),
+            None if kp_angle_deg is None else self._t(kp_angle_deg, torch.float32, "kp_angle_deg"),
+            None if kp_image is None else self._t(kp_image, torch.int32, "kp_image"), n, desc.data_ptr(), keep.data_ptr()))
+        return desc, keep
+
     def dense_triangulate(self, pano_top, pano_bot, disparity: torch.Tensor, f1, f2, min_disparity: float = 1.0,
                           max_disparity: float = 0.0, lowest_reference_row: float = float("inf"), roi_cols=None, out=None):
         """Disparity maps float32 [n, rows, cols] (or [rows, cols]) -> xyz float32 [..., rows, cols, 3] (NaN = invalid),
