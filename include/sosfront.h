@@ -317,6 +317,22 @@ int sos_orb_blur(sos_ctx* ctx, const uint8_t* gray, int n_images, int height, in
 int sos_orb_describe(sos_ctx* ctx, const uint8_t* gray, int n_images, int height, int width, const float* kp_xy,
                      const float* kp_angle_deg, const int32_t* kp_image, int n, uint32_t* desc, uint8_t* keep);
 
+/* replaces: cv2.cornerMinEigenVal(gray, blockSize = 3, ksize = 3) — the corner measure inside goodFeaturesToTrack.
+ * gray uint8 [n_images, height, width] -> eig float32 [n_images, height, width].  Same float32 arithmetic as OpenCV 4.13
+ * (bit-equal except at cv2's own SIMD tail columns, where its last bit depends on the image width). */
+int sos_corner_min_eigenval(sos_ctx* ctx, const uint8_t* gray, int n_images, int height, int width, float* eig);
+
+/* replaces: cv2.goodFeaturesToTrack(image = gray, maxCorners, qualityLevel, minDistance, mask = masks[m],
+ * useHarrisDetector = False) for every (image, mask) pair (camera_models.py:1737, one call per azimuthal mask).
+ *   masks     uint8 [n_masks, height, width], shared by all images; NULL with n_masks = 1 = no mask
+ *   out_xy    float32 [n_images, n_masks, max_corners, 2] corner (x, y), strongest first
+ *   out_count int32 [n_images, n_masks]
+ *   eig_out   float32 [n_images, height, width] (nullable) receives the corner measure
+ * At most 16384 local maxima above the quality threshold are considered per (image, mask). */
+int sos_gft_detect(sos_ctx* ctx, const uint8_t* gray, const uint8_t* masks, int n_images, int height, int width,
+                   int n_masks, int max_corners, double quality_level, double min_distance, float* out_xy,
+                   int32_t* out_count, float* eig_out);
+
 /* Dense triangulation of panoramic disparity maps into point clouds.
  * replaces: OmniStereoModel.resolve_pano_correspondences_from_disparity_map (camera_models.py:2492-2538) + the lifting and
  *           midpoint triangulation of triangulate_from_depth_map (camera_models.py:2567-2685, own midpoint method).

@@ -58,6 +58,8 @@ PROTOTYPES = {
     "sos_bgr_to_gray": (I, [c_ctx, P, C.c_size_t, P]),
     "sos_orb_blur": (I, [c_ctx, P, I, I, I, P]),
     "sos_orb_describe": (I, [c_ctx, P, I, I, I, P, P, P, I, P, P]),
+    "sos_corner_min_eigenval": (I, [c_ctx, P, I, I, I, P]),
+    "sos_gft_detect": (I, [c_ctx, P, P, I, I, I, I, I, D, D, P, P, P]),
     "sos_dense_triangulate": (I, [c_ctx, P, P, P, I, I, I, D, D, D, I, I, P, P, P, P]),
     "sos_refine_pose": (I, [c_ctx, P, P, P, P, P, I, I, P, I, P, I, I, P, P, P]),
     "sos_ctx_profile_begin": (I, [c_ctx]),

@@ -1,0 +1,314 @@
+// Shi-Tomasi corner detection on the panoramas (detection half).
+//
+// replaces: cv2.goodFeaturesToTrack(image, maxCorners, qualityLevel = 0.01, minDistance = 5, mask = m,
+//           useHarrisDetector = False) per azimuthal mask in OmniCamModel.detect_sparse_features_on_panorama
+//           (camera_models.py:1737), i.e. cv::cornerMinEigenVal (blockSize 3, Sobel 3) + threshold at
+//           quality * max over the mask + 3x3 non-maximum suppression + strongest-first minimum-distance selection.
+//
+// Arithmetic of cornerMinEigenVal, identified against cv2 (scratch probes): Sobel in float32 with the scale
+// 1/(4*3*255) folded into the smoothing taps and one fused multiply-add, dx = fma(s, r[-1] + r[+1], 2s * r[0]); covariance
+// products in float32; the 3x3 box sums accumulate in float64 and are rounded once; eigenvalue (a + c) - sqrt((a - c)^2 + b^2)
+// in float32 without contraction.  cv2's own SIMD tail columns skip the FMA, so a handful of pixels per row end differ
+// in the last bit from cv2 — the detected corners are the same except for exact near-ties.
+//
+// Selection: candidates of one (image, mask) are sorted by (strength desc, pixel index desc) — cv2's comparator — and the
+// strongest-first greedy of cv2 is evaluated in parallel rounds (a candidate is accepted once every stronger candidate
+// closer than minDistance has been rejected, rejected once one of them has been accepted): same result, no serial walk.
+#include <math_constants.h>
+
+#include "sos_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ int refl(int p, int n) {
+  if (n == 1) return 0;
+  while (p < 0 || p >= n) p = p < 0 ? -p : 2 * n - 2 - p;
+  return p;
+}
+
+// covariance terms (dx^2, dx dy, dy^2) per pixel
+__global__ void __launch_bounds__(256) gft_cov_kernel(const uint8_t* __restrict__ gray, int H, int W, float* __restrict__ cov) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const uint8_t* img = gray + (size_t)blockIdx.z * H * W;
+  const int xm = refl(x - 1, W), xp = refl(x + 1, W), ym = refl(y - 1, H), yp = refl(y + 1, H);
+  const float s = (float)(1.0 / (4.0 * 3.0 * 255.0)), s2 = 2.0f * s;
+  const float a00 = img[(size_t)ym * W + xm], a01 = img[(size_t)ym * W + x], a02 = img[(size_t)ym * W + xp];
+  const float a10 = img[(size_t)y * W + xm], a11 = img[(size_t)y * W + x], a12 = img[(size_t)y * W + xp];
+  const float a20 = img[(size_t)yp * W + xm], a21 = img[(size_t)yp * W + x], a22 = img[(size_t)yp * W + xp];
+  // d/dx: rows differentiated exactly ([-1 0 1]), columns smoothed with (s, 2s, s)
+  const float ru = a02 - a00, r0 = a12 - a10, rd = a22 - a20;
+  const float dx = __fmaf_rn(s, ru + rd, __fmul_rn(s2, r0));
+  // d/dy: rows smoothed with (s, 2s, s), columns differentiated
+  const float su = __fmaf_rn(s, a00 + a02, __fmul_rn(s2, a01));
+  const float sd = __fmaf_rn(s, a20 + a22, __fmul_rn(s2, a21));
+  const float dy = __fsub_rn(sd, su);
+  float* c = cov + 3 * (((size_t)blockIdx.z * H + y) * W + x);
+  c[0] = __fmul_rn(dx, dx);
+  c[1] = __fmul_rn(dx, dy);
+  c[2] = __fmul_rn(dy, dy);
+  (void)a11;
+}
+
+__global__ void __launch_bounds__(256) gft_eig_kernel(const float* __restrict__ cov, int H, int W, float* __restrict__ eig) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= W) return;
+  const float* c = cov + 3 * (size_t)blockIdx.z * H * W;
+  double sa = 0.0, sb = 0.0, sc = 0.0;
+#pragma unroll
+  for (int j = -1; j <= 1; ++j) {
+    const int yy = refl(y + j, H);
+#pragma unroll
+    for (int i = -1; i <= 1; ++i) {
+      const float* p = c + 3 * ((size_t)yy * W + refl(x + i, W));
+      sa += (double)p[0];
+      sb += (double)p[1];
+      sc += (double)p[2];
+    }
+  }
+  const float a = __fmul_rn((float)sa, 0.5f), b = (float)sb, cc = __fmul_rn((float)sc, 0.5f);
+  const float t = __fsub_rn(a, cc);
+  const float r = __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b)));
+  eig[((size_t)blockIdx.z * H + y) * W + x] = __fsub_rn(__fadd_rn(a, cc), r);
+}
+
+// max of eig over each mask (minMaxLoc with mask): non-negative floats order like their bit patterns
+__global__ void __launch_bounds__(256)
+gft_masked_max_kernel(const float* __restrict__ eig, const uint8_t* __restrict__ masks, int H, int W, int n_masks,
+                      uint32_t* __restrict__ max_bits) {
+  const size_t per = (size_t)H * W;
+  const int img = blockIdx.z, m = blockIdx.y;
+  const float* e = eig + (size_t)img * per;
+  const uint8_t* mk = masks ? masks + (size_t)m * per : nullptr;
+  float best = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (size_t)gridDim.x * blockDim.x)
+    if (!mk || mk[i]) best = fmaxf(best, e[i]);
+  for (int off = 16; off > 0; off >>= 1) best = fmaxf(best, __shfl_xor_sync(0xFFFFFFFFu, best, off));
+  if ((threadIdx.x & 31) == 0 && best > 0.f) atomicMax(&max_bits[img * n_masks + m], __float_as_uint(best));
+}
+
+// candidates: interior pixels above the mask's threshold that equal the maximum of their 3x3 neighbourhood
+__global__ void __launch_bounds__(256)
+gft_candidates_kernel(const float* __restrict__ eig, const uint8_t* __restrict__ masks, int H, int W, int n_masks,
+                      const uint32_t* __restrict__ max_bits, double quality, int cap, unsigned long long* __restrict__ keys,
+                      int32_t* __restrict__ counts) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, img = blockIdx.z;
+  if (x < 1 || x >= W - 1 || y < 1 || y >= H - 1) return;
+  const float* e = eig + (size_t)img * H * W;
+  const float v = e[(size_t)y * W + x];
+  if (!(v > 0.f)) return;
+  float nb = 0.f;
+#pragma unroll
+  for (int j = -1; j <= 1; ++j)
+#pragma unroll
+    for (int i = -1; i <= 1; ++i) nb = fmaxf(nb, e[(size_t)(y + j) * W + x + i]);
+  if (v != nb) return;
+  const size_t px = (size_t)y * W + x;
+  for (int m = 0; m < n_masks; ++m) {
+    if (masks && !masks[(size_t)m * H * W + px]) continue;
+    const float mx = __uint_as_float(max_bits[img * n_masks + m]);
+    const float thr = (float)((double)mx * quality);   // threshold(eig, eig, maxVal * qualityLevel, 0, THRESH_TOZERO)
+    if (!(v > thr)) continue;
+    const int slot = atomicAdd(&counts[img * n_masks + m], 1);
+    if (slot < cap) keys[((size_t)(img * n_masks + m)) * cap + slot] = ((unsigned long long)__float_as_uint(v) << 32) | (uint32_t)px;
+  }
+}
+
+constexpr int GFT_CAP = 16384;      // candidates per (image, mask) kept for the selection (128 KB of shared memory)
+constexpr int GFT_THREADS = 1024;
+
+// one block per (image, mask): sort descending, greedy minimum-distance selection in parallel rounds, strongest first out
+__global__ void __launch_bounds__(GFT_THREADS)
+gft_select_kernel(const unsigned long long* __restrict__ keys_in, const int32_t* __restrict__ counts, int cap, int H, int W,
+                  int n_masks, int mask_index, int max_corners, int min_dist_sq, int reach, int32_t* __restrict__ rank_img,
+                  uint8_t* __restrict__ state_all, float* __restrict__ out_xy, int32_t* __restrict__ out_count) {
+  extern __shared__ unsigned long long skey[];
+  __shared__ int n_undecided, n_acc_total;
+  __shared__ int warp_sums[GFT_THREADS / 32];
+  const int img = blockIdx.x;             // one launch per mask: the rank image of an image serves one mask at a time
+  const int list = img * n_masks + mask_index;
+  const int n = min(counts[list], cap);
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  const unsigned long long* kin = keys_in + (size_t)list * cap;
+  for (int i = threadIdx.x; i < np2; i += blockDim.x) skey[i] = i < n ? kin[i] : 0ull;
+  __syncthreads();
+  // bitonic sort, descending (key = strength bits << 32 | pixel index: cv2's greaterThanPtr order)
+  for (int k = 2; k <= np2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = skey[i], b = skey[l];
+          const bool desc = (i & k) == 0;
+          if (desc ? (a < b) : (a > b)) { skey[i] = b; skey[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  int32_t* rimg = rank_img + (size_t)img * H * W;   // one mask at a time per image: this kernel runs once per mask
+  uint8_t* state = state_all + (size_t)img * cap;    // 0 undecided, 1 accepted, 2 rejected
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    rimg[(uint32_t)skey[i]] = i;
+    state[i] = 0;
+  }
+  if (threadIdx.x == 0) n_undecided = n;
+  __syncthreads();
+  if (min_dist_sq > 0) {
+    while (n_undecided > 0) {
+      __syncthreads();
+      if (threadIdx.x == 0) n_undecided = 0;
+      __syncthreads();
+      int still = 0;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (state[i] != 0) continue;
+        const int px = (int)(uint32_t)skey[i];
+        const int y = px / W, x = px - y * W;
+        bool rejected = false, wait = false;
+        for (int dy = -reach; dy <= reach && !rejected; ++dy) {
+          const int yy = y + dy;
+          if (yy < 0 || yy >= H) continue;
+          for (int dx = -reach; dx <= reach; ++dx) {
+            const int xx = x + dx;
+            if (xx < 0 || xx >= W || dx * dx + dy * dy >= min_dist_sq || (dx == 0 && dy == 0)) continue;
+            const int j = rimg[(size_t)yy * W + xx];
+            if (j < 0 || j >= i) continue;               // no candidate there, or a weaker one
+            const uint8_t sj = ((volatile uint8_t*)state)[j];
+            if (sj == 1) { rejected = true; break; }
+            if (sj == 0) wait = true;
+          }
+        }
+        // decisions taken in this round only depend on FINAL states of stronger candidates, so the order of evaluation
+        // inside a round does not matter
+        if (rejected) state[i] = 2;
+        else if (!wait) state[i] = 1;
+        else ++still;
+      }
+      if (still) atomicAdd(&n_undecided, still);
+      __syncthreads();
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) state[i] = 1;
+    __syncthreads();
+  }
+  // ordered compaction of the accepted candidates, at most max_corners
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int base = 0;
+  for (int i0 = 0; i0 < n && base < max_corners; i0 += blockDim.x) {
+    const int i = i0 + threadIdx.x;
+    const bool acc = i < n && state[i] == 1;
+    const unsigned vote = __ballot_sync(0xFFFFFFFFu, acc);
+    if (lane == 0) warp_sums[warp] = __popc(vote);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < GFT_THREADS / 32; ++w) {
+      const int c = warp_sums[w];
+      if (w < warp) before += c;
+      total += c;
+    }
+    if (acc) {
+      const int pos = base + before + __popc(vote & ((1u << lane) - 1u));
+      if (pos < max_corners) {
+        const int px = (int)(uint32_t)skey[i];
+        const int y = px / W, x = px - y * W;
+        out_xy[((size_t)list * max_corners + pos) * 2 + 0] = (float)x;
+        out_xy[((size_t)list * max_corners + pos) * 2 + 1] = (float)y;
+      }
+    }
+    base += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    n_acc_total = min(base, max_corners);
+    out_count[list] = n_acc_total;
+  }
+  // leave the rank image clean for the next mask
+  for (int i = threadIdx.x; i < n; i += blockDim.x) rimg[(uint32_t)skey[i]] = -1;
+}
+
+}  // namespace
+
+extern "C" int sos_corner_min_eigenval(sos_ctx* ctx, const uint8_t* gray, int n_images, int height, int width, float* eig) {
+  SOS_CHECK_ARG(ctx, "ctx is NULL");
+  SOS_CHECK_ARG(n_images >= 0 && height >= 0 && width >= 0, "negative size");
+  if (n_images == 0 || height == 0 || width == 0) return SOS_OK;
+  SOS_CHECK_ARG(gray && eig, "NULL array");
+  SOS_CHECK_ARG(n_images <= 65535 && height <= 65535, "too many images / rows");
+  SOS_CUDA(cudaSetDevice(ctx->device));
+  void* ws = nullptr;
+  const size_t px = (size_t)n_images * height * width;
+  const int rc = sos_arena_get(ctx, sos_align_up(px * 3 * sizeof(float), 256), &ws);
+  if (rc != SOS_OK) return rc;
+  dim3 grid(sos_div_up(width, 256), height, n_images);
+  gft_cov_kernel<<<grid, 256, 0, ctx->stream>>>(gray, height, width, (float*)ws);
+  SOS_LAUNCHED(ctx);
+  gft_eig_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)ws, height, width, eig);
+  SOS_LAUNCHED(ctx);
+  return SOS_OK;
+}
+
+extern "C" int sos_gft_detect(sos_ctx* ctx, const uint8_t* gray, const uint8_t* masks, int n_images, int height, int width,
+                              int n_masks, int max_corners, double quality_level, double min_distance, float* out_xy,
+                              int32_t* out_count, float* eig_out) {
+  SOS_CHECK_ARG(ctx, "ctx is NULL");
+  SOS_CHECK_ARG(n_images >= 0 && height >= 0 && width >= 0 && n_masks >= 1 && max_corners >= 0, "bad size");
+  SOS_CHECK_ARG(quality_level > 0.0 && min_distance >= 0.0 && min_distance < 64.0, "bad quality level / minimum distance");
+  if (n_images == 0) return SOS_OK;
+  SOS_CHECK_ARG(gray && out_count && (out_xy || max_corners == 0), "NULL array");
+  SOS_CHECK_ARG(height >= 3 && width >= 3 && (size_t)height * width < (1ull << 31), "image size out of range");
+  SOS_CHECK_ARG((long long)n_images * n_masks <= 65535, "too many (image, mask) lists");
+  SOS_CUDA(cudaSetDevice(ctx->device));
+  const size_t px = (size_t)n_images * height * width;
+  const int lists = n_images * n_masks;
+  // scratch layout
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += sos_align_up(bytes, 256); return o; };
+  const size_t o_cov = take(px * 3 * sizeof(float));
+  const size_t o_eig = take(px * sizeof(float));
+  const size_t o_max = take((size_t)lists * sizeof(uint32_t));
+  const size_t o_cnt = take((size_t)lists * sizeof(int32_t));
+  const size_t o_keys = take((size_t)lists * GFT_CAP * sizeof(unsigned long long));
+  const size_t o_rank = take(px * sizeof(int32_t));
+  const size_t o_state = take((size_t)n_images * GFT_CAP);
+  void* ws = nullptr;
+  const int rc = sos_arena_get(ctx, off, &ws);
+  if (rc != SOS_OK) return rc;
+  uint8_t* base = (uint8_t*)ws;
+  float* cov = (float*)(base + o_cov);
+  float* eig = (float*)(base + o_eig);
+  uint32_t* max_bits = (uint32_t*)(base + o_max);
+  int32_t* counts = (int32_t*)(base + o_cnt);
+  unsigned long long* keys = (unsigned long long*)(base + o_keys);
+  int32_t* rank_img = (int32_t*)(base + o_rank);
+  uint8_t* state = base + o_state;
+
+  dim3 grid(sos_div_up(width, 256), height, n_images);
+  gft_cov_kernel<<<grid, 256, 0, ctx->stream>>>(gray, height, width, cov);
+  SOS_LAUNCHED(ctx);
+  gft_eig_kernel<<<grid, 256, 0, ctx->stream>>>(cov, height, width, eig);
+  SOS_LAUNCHED(ctx);
+  if (eig_out) SOS_CUDA(cudaMemcpyAsync(eig_out, eig, px * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  SOS_CUDA(cudaMemsetAsync(base + o_max, 0, (o_keys - o_max), ctx->stream));          // max_bits and counts
+  SOS_CUDA(cudaMemsetAsync(rank_img, 0xFF, px * sizeof(int32_t), ctx->stream));       // -1
+  gft_masked_max_kernel<<<dim3(32, n_masks, n_images), 256, 0, ctx->stream>>>(eig, masks, height, width, n_masks, max_bits);
+  SOS_LAUNCHED(ctx);
+  gft_candidates_kernel<<<grid, 256, 0, ctx->stream>>>(eig, masks, height, width, n_masks, max_bits, quality_level, GFT_CAP,
+                                                       keys, counts);
+  SOS_LAUNCHED(ctx);
+  static bool attr_set = false;
+  const size_t smem = (size_t)GFT_CAP * sizeof(unsigned long long);
+  if (!attr_set) {
+    SOS_CUDA(cudaFuncSetAttribute(gft_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const double md2 = min_distance * min_distance;
+  const int min_dist_sq = min_distance >= 1.0 ? (int)ceil(md2) : 0;   // integer offsets: dx^2 + dy^2 < minDistance^2
+  const int reach = (int)ceil(min_distance);
+  // masks may overlap, and each selection needs the rank image of its image to itself: one launch per mask
+  for (int m = 0; m < n_masks; ++m) {
+    gft_select_kernel<<<n_images, GFT_THREADS, smem, ctx->stream>>>(keys, counts, GFT_CAP, height, width, n_masks, m, max_corners,
+                                                                    min_dist_sq, reach, rank_img, state, out_xy, out_count);
+    SOS_LAUNCHED(ctx);
+  }
+  return SOS_OK;
+}

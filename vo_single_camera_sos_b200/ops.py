@@ -292,6 +292,31 @@ class Context:
             None if kp_image is None else self._t(kp_image, torch.int32, "kp_image"), n, desc.data_ptr(), keep.data_ptr()))
         return desc, keep
 
+    def corner_min_eigenval(self, gray: torch.Tensor) -> torch.Tensor:
+        self._sync_stream()
+        g = gray[None] if gray.dim() == 2 else gray
+        eig = self.empty(tuple(g.shape), torch.float32)
+        check(self.lib.sos_corner_min_eigenval(self._h, self._t(g, torch.uint8, "gray"), g.shape[0], g.shape[1], g.shape[2],
+                                               eig.data_ptr()))
+        return eig[0] if gray.dim() == 2 else eig
+
+    def gft_detect(self, gray: torch.Tensor, masks, max_corners: int, quality_level: float = 0.01, min_distance: float = 5.0,
+                   want_eig: bool = False):
+        """cv2.goodFeaturesToTrack for every (image, mask): gray uint8 [n, H, W] (or [H, W]), masks uint8 [m, H, W] or None
+        -> xy float32 [n, m, max_corners, 2] (strongest first), count int32 [n, m] (and eig float32 [n, H, W])."""
+        self._sync_stream()
+        g = gray[None] if gray.dim() == 2 else gray
+        n, H, W = g.shape
+        m = 1 if masks is None else masks.shape[0]
+        xy = self.empty((n, m, max_corners, 2), torch.float32)
+        count = self.empty((n, m), torch.int32)
+        eig = self.empty((n, H, W), torch.float32) if want_eig else None
+        check(self.lib.sos_gft_detect(
+            self._h, self._t(g, torch.uint8, "gray"), None if masks is None else self._t(masks, torch.uint8, "masks"), n, H, W,
+            m, int(max_corners), float(quality_level), float(min_distance), xy.data_ptr(), count.data_ptr(),
+            None if eig is None else eig.data_ptr()))
+        return (xy, count, eig) if want_eig else (xy, count)
+
     def dense_triangulate(self, pano_top, pano_bot, disparity: torch.Tensor, f1, f2, min_disparity: float = 1.0,
                           max_disparity: float = 0.0, lowest_reference_row: float = float("inf"), roi_cols=None, out=None):
         """Disparity maps float32 [n, rows, cols] (or [rows, cols]) -> xyz float32 [..., rows, cols, 3] (NaN = invalid),
