@@ -72,19 +72,21 @@ __global__ void __launch_bounds__(256) gft_eig_kernel(const float* __restrict__ 
   eig[((size_t)blockIdx.z * H + y) * W + x] = __fsub_rn(__fadd_rn(a, cc), r);
 }
 
-// max of eig over each mask (minMaxLoc with mask): non-negative floats order like their bit patterns
+// max of eig over each mask (minMaxLoc with mask): non-negative floats order like their bit patterns.  One pass over the
+// pixels; per mask a warp maximum and at most one atomic per warp.
 __global__ void __launch_bounds__(256)
 gft_masked_max_kernel(const float* __restrict__ eig, const uint8_t* __restrict__ masks, int H, int W, int n_masks,
                       uint32_t* __restrict__ max_bits) {
-  const size_t per = (size_t)H * W;
-  const int img = blockIdx.z, m = blockIdx.y;
-  const float* e = eig + (size_t)img * per;
-  const uint8_t* mk = masks ? masks + (size_t)m * per : nullptr;
-  float best = 0.f;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (size_t)gridDim.x * blockDim.x)
-    if (!mk || mk[i]) best = fmaxf(best, e[i]);
-  for (int off = 16; off > 0; off >>= 1) best = fmaxf(best, __shfl_xor_sync(0xFFFFFFFFu, best, off));
-  if ((threadIdx.x & 31) == 0 && best > 0.f) atomicMax(&max_bits[img * n_masks + m], __float_as_uint(best));
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, img = blockIdx.z;
+  const bool in = x < W;
+  const size_t px = (size_t)y * W + (in ? x : 0);
+  const float v = in ? eig[(size_t)img * H * W + px] : 0.f;
+  for (int m = 0; m < n_masks; ++m) {
+    float best = (in && (!masks || masks[(size_t)m * H * W + px])) ? v : 0.f;
+    for (int off = 16; off > 0; off >>= 1) best = fmaxf(best, __shfl_xor_sync(0xFFFFFFFFu, best, off));
+    if ((threadIdx.x & 31) == 0 && best > 0.f && __float_as_uint(best) > max_bits[img * n_masks + m])
+      atomicMax(&max_bits[img * n_masks + m], __float_as_uint(best));
+  }
 }
 
 // candidates: interior pixels above the mask's threshold that equal the maximum of their 3x3 neighbourhood
@@ -116,12 +118,14 @@ gft_candidates_kernel(const float* __restrict__ eig, const uint8_t* __restrict__
 
 constexpr int GFT_CAP = 16384;      // candidates per (image, mask) kept for the selection (128 KB of shared memory)
 constexpr int GFT_THREADS = 1024;
+constexpr int GFT_K = 16;           // stronger neighbours remembered per candidate
 
 // one block per (image, mask): sort descending, greedy minimum-distance selection in parallel rounds, strongest first out
 __global__ void __launch_bounds__(GFT_THREADS)
 gft_select_kernel(const unsigned long long* __restrict__ keys_in, const int32_t* __restrict__ counts, int cap, int H, int W,
                   int n_masks, int mask_index, int max_corners, int min_dist_sq, int reach, int32_t* __restrict__ rank_img,
-                  uint8_t* __restrict__ state_all, float* __restrict__ out_xy, int32_t* __restrict__ out_count) {
+                  uint8_t* __restrict__ state_all, uint16_t* __restrict__ nbr_all, uint8_t* __restrict__ ncnt_all,
+                  float* __restrict__ out_xy, int32_t* __restrict__ out_count) {
   extern __shared__ unsigned long long skey[];
   __shared__ int n_undecided, n_acc_total;
   __shared__ int warp_sums[GFT_THREADS / 32];
@@ -155,37 +159,72 @@ gft_select_kernel(const unsigned long long* __restrict__ keys_in, const int32_t*
   if (threadIdx.x == 0) n_undecided = n;
   __syncthreads();
   if (min_dist_sq > 0) {
-    while (n_undecided > 0) {
+    // phase A (once): the stronger candidates closer than minDistance to candidate i.  All rank-image loads of a candidate
+    // are independent, so they overlap; the rounds below then touch only these few entries.
+    uint16_t* nbr = nbr_all + (size_t)img * cap * GFT_K;
+    uint8_t* ncnt = ncnt_all + (size_t)img * cap;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int px = (int)(uint32_t)skey[i];
+      const int y = px / W, x = px - y * W;
+      int cnt = 0;
+      for (int dy = -reach; dy <= reach; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= H) continue;
+        for (int dx = -reach; dx <= reach; ++dx) {
+          const int xx = x + dx;
+          if (xx < 0 || xx >= W || dx * dx + dy * dy >= min_dist_sq) continue;
+          const int j = rimg[(size_t)yy * W + xx];
+          if (j >= 0 && j < i) {
+            if (cnt < GFT_K) nbr[(size_t)i * GFT_K + cnt] = (uint16_t)j;
+            ++cnt;
+          }
+        }
+      }
+      ncnt[i] = (uint8_t)min(cnt, 255);
+      if (cnt == 0) state[i] = 1;            // nothing stronger nearby: accepted outright
+    }
+    __syncthreads();
+    // phase B: rounds over the undecided candidates
+    while (true) {
       __syncthreads();
       if (threadIdx.x == 0) n_undecided = 0;
       __syncthreads();
       int still = 0;
       for (int i = threadIdx.x; i < n; i += blockDim.x) {
         if (state[i] != 0) continue;
-        const int px = (int)(uint32_t)skey[i];
-        const int y = px / W, x = px - y * W;
         bool rejected = false, wait = false;
-        for (int dy = -reach; dy <= reach && !rejected; ++dy) {
-          const int yy = y + dy;
-          if (yy < 0 || yy >= H) continue;
-          for (int dx = -reach; dx <= reach; ++dx) {
-            const int xx = x + dx;
-            if (xx < 0 || xx >= W || dx * dx + dy * dy >= min_dist_sq || (dx == 0 && dy == 0)) continue;
-            const int j = rimg[(size_t)yy * W + xx];
-            if (j < 0 || j >= i) continue;               // no candidate there, or a weaker one
-            const uint8_t sj = ((volatile uint8_t*)state)[j];
+        const int cnt = ncnt[i];
+        if (cnt <= GFT_K) {
+          for (int q = 0; q < cnt; ++q) {
+            const uint8_t sj = ((volatile uint8_t*)state)[nbr[(size_t)i * GFT_K + q]];
             if (sj == 1) { rejected = true; break; }
             if (sj == 0) wait = true;
           }
+        } else {                              // more neighbours than the list holds (plateaus): rescan the rank image
+          const int px = (int)(uint32_t)skey[i];
+          const int y = px / W, x = px - y * W;
+          for (int dy = -reach; dy <= reach && !rejected; ++dy) {
+            const int yy = y + dy;
+            if (yy < 0 || yy >= H) continue;
+            for (int dx = -reach; dx <= reach; ++dx) {
+              const int xx = x + dx;
+              if (xx < 0 || xx >= W || dx * dx + dy * dy >= min_dist_sq) continue;
+              const int j = rimg[(size_t)yy * W + xx];
+              if (j < 0 || j >= i) continue;
+              const uint8_t sj = ((volatile uint8_t*)state)[j];
+              if (sj == 1) { rejected = true; break; }
+              if (sj == 0) wait = true;
+            }
+          }
         }
-        // decisions taken in this round only depend on FINAL states of stronger candidates, so the order of evaluation
-        // inside a round does not matter
+        // a decision only depends on FINAL states of stronger candidates, so the evaluation order inside a round is free
         if (rejected) state[i] = 2;
         else if (!wait) state[i] = 1;
         else ++still;
       }
       if (still) atomicAdd(&n_undecided, still);
       __syncthreads();
+      if (n_undecided == 0) break;
     }
   } else {
     for (int i = threadIdx.x; i < n; i += blockDim.x) state[i] = 1;
@@ -270,6 +309,8 @@ extern "C" int sos_gft_detect(sos_ctx* ctx, const uint8_t* gray, const uint8_t* 
   const size_t o_keys = take((size_t)lists * GFT_CAP * sizeof(unsigned long long));
   const size_t o_rank = take(px * sizeof(int32_t));
   const size_t o_state = take((size_t)n_images * GFT_CAP);
+  const size_t o_nbr = take((size_t)n_images * GFT_CAP * GFT_K * sizeof(uint16_t));
+  const size_t o_ncnt = take((size_t)n_images * GFT_CAP);
   void* ws = nullptr;
   const int rc = sos_arena_get(ctx, off, &ws);
   if (rc != SOS_OK) return rc;
@@ -290,7 +331,7 @@ extern "C" int sos_gft_detect(sos_ctx* ctx, const uint8_t* gray, const uint8_t* 
   if (eig_out) SOS_CUDA(cudaMemcpyAsync(eig_out, eig, px * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
   SOS_CUDA(cudaMemsetAsync(base + o_max, 0, (o_keys - o_max), ctx->stream));          // max_bits and counts
   SOS_CUDA(cudaMemsetAsync(rank_img, 0xFF, px * sizeof(int32_t), ctx->stream));       // -1
-  gft_masked_max_kernel<<<dim3(32, n_masks, n_images), 256, 0, ctx->stream>>>(eig, masks, height, width, n_masks, max_bits);
+  gft_masked_max_kernel<<<grid, 256, 0, ctx->stream>>>(eig, masks, height, width, n_masks, max_bits);
   SOS_LAUNCHED(ctx);
   gft_candidates_kernel<<<grid, 256, 0, ctx->stream>>>(eig, masks, height, width, n_masks, max_bits, quality_level, GFT_CAP,
                                                        keys, counts);
@@ -307,7 +348,8 @@ extern "C" int sos_gft_detect(sos_ctx* ctx, const uint8_t* gray, const uint8_t* 
   // masks may overlap, and each selection needs the rank image of its image to itself: one launch per mask
   for (int m = 0; m < n_masks; ++m) {
     gft_select_kernel<<<n_images, GFT_THREADS, smem, ctx->stream>>>(keys, counts, GFT_CAP, height, width, n_masks, m, max_corners,
-                                                                    min_dist_sq, reach, rank_img, state, out_xy, out_count);
+                                                                    min_dist_sq, reach, rank_img, state, (uint16_t*)(base + o_nbr), base + o_ncnt, out_xy,
+                                                                    out_count);
     SOS_LAUNCHED(ctx);
   }
   return SOS_OK;
