@@ -301,6 +301,11 @@ int sos_refit_inliers(sos_ctx* ctx, const float* p_ref, const float* p_cur, cons
  * Feature description on the panoramas (description half)
  * ---------------------------------------------------------------------------------------------- */
 
+/* replaces: cv2.medianBlur(pano_img, 11) (camera_models.py:1708-1709 with median_win_size = 11, pose_est_tools.py:297):
+ * exact per-channel median of the 11 x 11 window, BORDER_REPLICATE.  src, dst uint8 [n_images, height, width, channels],
+ * channels 1 or 3, not in place.  Bit-exact. */
+int sos_median_blur_11(sos_ctx* ctx, const uint8_t* src, int n_images, int height, int width, int channels, uint8_t* dst);
+
 /* replaces: cv2.cvtColor(pano_img, cv2.COLOR_BGR2GRAY) (camera_models.py:1711).  Bit-exact with OpenCV 4.x (15-bit fixed point). */
 int sos_bgr_to_gray(sos_ctx* ctx, const uint8_t* bgr, size_t n_pixels, uint8_t* gray);
 

@@ -263,6 +263,20 @@ class Context:
         return xyz, valid
 
     # -- N3: feature description ---------------------------------------------------------------------------------
+    def median_blur_11(self, img: torch.Tensor) -> torch.Tensor:
+        """cv2.medianBlur(img, 11): uint8 [H, W], [H, W, 3], [n, H, W] (gray batch is [n, H, W, 1]) or [n, H, W, 3]."""
+        self._sync_stream()
+        if img.dim() == 2:
+            x = img[None, :, :, None]
+        elif img.dim() == 3:
+            x = img[None] if img.shape[-1] == 3 else img[..., None]
+        else:
+            x = img
+        n, H, W, ch = x.shape
+        out = self.empty((n, H, W, ch), torch.uint8)
+        check(self.lib.sos_median_blur_11(self._h, self._t(x, torch.uint8, "img"), n, H, W, ch, out.data_ptr()))
+        return out.reshape(img.shape)
+
     def bgr_to_gray(self, bgr: torch.Tensor) -> torch.Tensor:
         """uint8 [..., 3] -> uint8 [...]  (cv2.COLOR_BGR2GRAY, bit-exact)."""
         self._sync_stream()
