@@ -219,3 +219,44 @@ def test_trackers_on_a_synthetic_pair(gums):
     # models with lazily built device state survive a pickle round trip (demo_vo_sos.py:109 loads a pickled GUMStereo)
     gs2 = pickle.loads(pickle.dumps(gs))
     assert np.array_equal(gs2.top_model.panorama.world2cam_LUT_map_x, gs.top_model.panorama.world2cam_LUT_map_x, equal_nan=True)
+
+
+def test_detect_sparse_features_gft_on_device(gums):
+    """OmniCamModel.detect_sparse_features_on_panorama(feature_detection_method="GFT", median_win_size=11) — the
+    reference's default detector (pose_est_tools.py:681, 297) — against the reference's own call sequence made with cv2:
+    medianBlur -> BGR2GRAY -> goodFeaturesToTrack per azimuthal mask -> KeyPoint_convert -> ORB.compute
+    (camera_models.py:1706-1768)."""
+    gs, _ = gums
+    rng = np.random.default_rng(11)
+    for model in (gs.top_model, gs.bot_model):
+        pano_obj = model.panorama
+        rows, cols = pano_obj.rows, pano_obj.cols
+        # a textured panorama large enough for ORB's 31-pixel border (the golden rig's own panorama is 48 rows high)
+        pano = cv2.GaussianBlur(rng.integers(0, 256, (160, 480, 3), dtype=np.uint8), (0, 0), 1.6)
+        masks = []
+        for k in range(4):
+            m = np.zeros(pano.shape[:2], np.uint8)
+            m[8:-8, k * 120:(k + 1) * 120] = 255
+            masks.append(m)
+        saved = pano_obj.panoramic_img, pano_obj.azimuthal_masks
+        pano_obj.panoramic_img, pano_obj.azimuthal_masks = pano, masks
+        try:
+            kl, dl = model.detect_sparse_features_on_panorama(feature_detection_method="GFT", num_of_features=60,
+                                                              median_win_size=11, show=False)
+        finally:
+            pano_obj.panoramic_img, pano_obj.azimuthal_masks = saved
+        blurred = cv2.cvtColor(cv2.medianBlur(pano, 11), cv2.COLOR_BGR2GRAY)
+        orb = cv2.ORB_create(nfeatures=60)
+        total = same = 0
+        for m, k_got, d_got in zip(masks, kl, dl):
+            pts = cv2.goodFeaturesToTrack(image=blurred, maxCorners=60, qualityLevel=0.01, minDistance=5, mask=m,
+                                          useHarrisDetector=False)
+            k_ref, d_ref = orb.compute(blurred, list(cv2.KeyPoint_convert(pts.reshape(-1, 2))))
+            assert abs(len(k_got) - len(k_ref)) <= 1 and d_got.shape[1] == 32
+            n = min(len(k_got), len(k_ref))
+            for a, b, da, db in zip(k_got[:n], k_ref[:n], d_got[:n], d_ref[:n]):
+                total += 1
+                if a.pt == b.pt:
+                    same += 1
+                    assert np.array_equal(da, db) and a.angle == b.angle == -1 and a.octave == b.octave == 0
+        assert total > 60 and same >= 0.98 * total, (same, total)

@@ -191,14 +191,48 @@ class OmniCamModel(object):
 
     def detect_sparse_features_on_panorama(self, feature_detection_method="ORB", num_of_features=50, median_win_size=0,
                                            show=True):
-        """Per-bucket keypoints + ORB descriptors on the panorama (camera_models.py:1610-1797).  Feature detection is
-        UPSTREAM of the hot path and stays on the host with OpenCV: median blur, then ORB per
-        azimuthal mask.  Returns (list of keypoint lists, list of N x 32 descriptor arrays), one entry per bucket."""
+        """Per-bucket keypoints + ORB descriptors on the panorama (camera_models.py:1610-1797).  Returns (list of keypoint
+        lists, list of N x 32 descriptor arrays), one entry per azimuthal mask.
+
+        The reference's default detector, "GFT" (pose_est_tools.py:681), runs on the device: 11 x 11 median
+        blur of the BGR panorama, BGR2GRAY, goodFeaturesToTrack(maxCorners, 0.01, 5, mask) per mask, KeyPoint_convert,
+        ORB.compute — sos_median_blur_11, sos_bgr_to_gray, sos_gft_detect, sos_orb_describe.  Other detectors stay on the
+        host with OpenCV (they are not the reference's default path)."""
         pano = self.panorama.panoramic_img
+        masks = self.panorama.azimuthal_masks or [None]
+        if feature_detection_method.upper() == "GFT":
+            if median_win_size not in (0, 11):
+                raise NotImplementedError("the device median filter is 11 x 11 (the reference's median_win_size)")
+            ctx = device_context()
+            img = to_device(np.ascontiguousarray(pano))
+            if pano.ndim == 3:
+                if median_win_size > 0:
+                    img = ctx.median_blur_11(img)
+                gray = ctx.bgr_to_gray(img)
+            else:
+                gray = img          # camera_models.py:1712-1713: a single-channel panorama is used UNblurred (sic)
+            key = tuple(id(m) for m in masks)
+            if getattr(self, "_masks_key", None) != key:
+                self._masks_dev = None if masks[0] is None else to_device(np.ascontiguousarray(np.stack(masks)))
+                self._masks_key = key
+            xy, cnt = ctx.gft_detect(gray, self._masks_dev, int(num_of_features), 0.01, 5.0)
+            cnt = cnt.cpu().numpy()[0]
+            pts = [xy[0, m, :int(cnt[m])] for m in range(len(masks))]
+            allpts = torch.cat(pts) if len(pts) > 1 else pts[0]
+            desc, keep = ctx.orb_describe(gray, allpts.contiguous())
+            desc, keep, allxy = desc.cpu().numpy(), keep.cpu().numpy().astype(bool), allpts.cpu().numpy()
+            kpts_list, desc_list, o = [], [], 0
+            for m in range(len(masks)):
+                sl = slice(o, o + int(cnt[m]))
+                o += int(cnt[m])
+                k = keep[sl]
+                # cv2.KeyPoint_convert: size 1, angle -1, response 1, octave 0, class_id -1
+                kpts_list.append([cv2.KeyPoint(float(x), float(y), 1.0, -1.0, 1.0, 0, -1) for x, y in allxy[sl][k]])
+                desc_list.append(desc[sl][k])
+            return kpts_list, desc_list
         gray = cv2.cvtColor(pano, cv2.COLOR_BGR2GRAY) if pano.ndim == 3 else pano
         if median_win_size > 0:
             gray = cv2.medianBlur(gray, median_win_size)
-        masks = self.panorama.azimuthal_masks or [None]
         orb = cv2.ORB_create(nfeatures=int(num_of_features))
         kpts_list, desc_list = [], []
         for mask in masks:
