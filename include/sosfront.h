@@ -310,7 +310,7 @@ int sos_median_blur_11(sos_ctx* ctx, const uint8_t* src, int n_images, int heigh
 int sos_bgr_to_gray(sos_ctx* ctx, const uint8_t* bgr, size_t n_pixels, uint8_t* gray);
 
 /* The blur inside cv2.ORB.compute: separable 7-tap Gaussian of sigma 2, BORDER_REFLECT_101, exact arithmetic rounded
- * once (not cv2.GaussianBlur's fixed-point path; identified and pinned by oracle/derive_orb_pattern.py).
+ * once (not cv2.GaussianBlur's fixed-point path; identified and pinned by scripts/derive_orb_pattern.py).
  * gray, blurred: uint8 [n_images, height, width]; not in place. */
 int sos_orb_blur(sos_ctx* ctx, const uint8_t* gray, int n_images, int height, int width, uint8_t* blurred);
 

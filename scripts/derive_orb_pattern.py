@@ -1,5 +1,6 @@
 """Derive the 256 x 2 test-point table of the ORB descriptor (Rublee et al. 2011; OpenCV's bit_pattern_31_) from the
-BEHAVIOUR of the installed cv2.ORB, and pin the rest of the descriptor model while doing so.  TEST INFRASTRUCTURE.
+BEHAVIOUR of the installed cv2.ORB, and pin the rest of the descriptor model while doing so.  Build-time tool: its
+outputs are committed (like the golden vectors), nothing imports it at run time.
 
 Model being identified (what cv2.ORB.compute does with user-supplied keypoints of octave 0):
     B = round(G * gray), G = separable 7-tap Gaussian of sigma 2, BORDER_REFLECT_101 (see blur());  c = (cvRound(kp.x), cvRound(kp.y))
@@ -8,7 +9,8 @@ Identification: on N random images every bit k is observed for a keypoint of ang
 31 x 31 patch survives only if it reproduces all N observations.  Exactly one pair survives per bit, which also confirms
 the blur model.  The table is then validated on random keypoints with random angles against cv2 bit for bit.
 
-Writes vo_single_camera_sos_b200/orb_pattern.npy (int8 [256, 4] = x0, y0, x1, y1) — run in the build container."""
+Writes vo_single_camera_sos_b200/csrc/orb_pattern.inc (compiled into the library) and tests/golden/orb_pattern.npy
+(int8 [256, 4] = x0, y0, x1, y1, used by the oracle) — run in the build container: python scripts/derive_orb_pattern.py"""
 from __future__ import annotations
 
 import os
@@ -17,7 +19,8 @@ import sys
 import cv2
 import numpy as np
 
-OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "vo_single_camera_sos_b200", "orb_pattern.npy")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "tests", "golden", "orb_pattern.npy")
 HALF = 15
 
 
@@ -113,9 +116,9 @@ if __name__ == "__main__":
     if bad:
         sys.exit(1)
     np.save(OUT, tab)
-    inc = os.path.join(os.path.dirname(OUT), "csrc", "orb_pattern.inc")
+    inc = os.path.join(ROOT, "vo_single_camera_sos_b200", "csrc", "orb_pattern.inc")
     with open(inc, "w") as f:
-        f.write("// ORB test-point table (x0, y0, x1, y1 per descriptor bit), generated by oracle/derive_orb_pattern.py from the\n"
+        f.write("// ORB test-point table (x0, y0, x1, y1 per descriptor bit), generated by scripts/derive_orb_pattern.py from the\n"
                 "// behaviour of cv2.ORB.compute (validated bit for bit on 409600 descriptor bits).  Do not edit.\n")
         for k in range(0, 256, 4):
             f.write("  " + " ".join("%d,%d,%d,%d," % tuple(int(v) for v in tab[j]) for j in range(k, k + 4)) + "\n")

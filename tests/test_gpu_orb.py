@@ -1,12 +1,12 @@
 """GPU: ORB description of given keypoints (description half) against cv2.ORB.compute itself — the call
 the reference makes (camera_models.py:1683, 1766).  Bit-exact: descriptors, dropped keypoints, gray conversion; and the
-blur model pinned by oracle/derive_orb_pattern.py."""
+blur model identified by scripts/derive_orb_pattern.py (restated in oracle/orb.py)."""
 import cv2
 import numpy as np
 import pytest
 import torch
 
-from oracle import derive_orb_pattern as orbm
+from oracle import orb as orbm
 
 pytestmark = pytest.mark.gpu
 

@@ -161,3 +161,22 @@ def test_dense_triangulation_oracle():
         assert np.array_equal(np.stack([uu, vv], 1), g[tag + "_top_px"])
         assert np.allclose(xyz.transpose(1, 0, 2)[vt], g[tag + "_xyz"], rtol=1e-12, atol=1e-12)
         assert np.array_equal(g[tag + "_bot_px"][:, 1], vv - g["disparity"][vv, uu])
+
+
+def test_orb_description_oracle_matches_cv2():
+    """the restated descriptor model (blur inside ORB, test-point table, float32 rotation, border filter)
+    equals cv2.ORB.compute bit for bit on random keypoints and angles."""
+    import cv2
+    from oracle import orb
+    rng = np.random.default_rng(4)
+    gray = cv2.GaussianBlur(rng.integers(0, 256, (200, 260), dtype=np.uint8), (0, 0), 1.5)
+    pts = np.stack([rng.uniform(0, 260, 400), rng.uniform(0, 200, 400)], 1).astype(np.float32)
+    ang = rng.uniform(0, 360, 400).astype(np.float32)
+    ang[::4] = -1.0
+    kps = [cv2.KeyPoint(float(p[0]), float(p[1]), 1.0, float(a), 1.0, 0, i) for i, (p, a) in enumerate(zip(pts, ang))]
+    k2, want = cv2.ORB_create(nfeatures=10).compute(gray, kps)
+    got, keep = orb.describe(gray, pts, ang)
+    kept = np.array([k.class_id for k in k2])
+    assert np.array_equal(np.sort(kept), np.flatnonzero(keep))
+    assert np.array_equal(got[kept], want)
+    assert orb.pattern().shape == (256, 4) and np.abs(orb.pattern()).max() == 13

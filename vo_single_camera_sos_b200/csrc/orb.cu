@@ -5,7 +5,7 @@
 //           cv2.cvtColor(pano_img, COLOR_BGR2GRAY) (camera_models.py:1711).
 //
 // What cv2.ORB.compute does with user-supplied keypoints of octave 0 was identified from its behaviour and is pinned bit
-// for bit by oracle/derive_orb_pattern.py (409 600 descriptor bits, zero differences):
+// for bit by scripts/derive_orb_pattern.py (409 600 descriptor bits, zero differences):
 //   * keypoints closer than 31 px to the image border are dropped (KeyPointsFilter::runByImageBorder, edgeThreshold);
 //   * the image is blurred by the separable 7-tap Gaussian of sigma 2 (BORDER_REFLECT_101) — evaluated exactly and
 //     rounded once, NOT cv2.GaussianBlur's fixed-point path;
