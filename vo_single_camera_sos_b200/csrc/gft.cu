@@ -89,6 +89,14 @@ gft_masked_max_kernel(const float* __restrict__ eig, const uint8_t* __restrict__
   }
 }
 
+__global__ void gft_mask_overlap_kernel(const uint8_t* __restrict__ masks, size_t per, int n_masks, int32_t* __restrict__ flag) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per) return;
+  int c = 0;
+  for (int m = 0; m < n_masks; ++m) c += masks[(size_t)m * per + i] ? 1 : 0;
+  if (c > 1) *flag = 1;
+}
+
 // candidates: interior pixels above the mask's threshold that equal the maximum of their 3x3 neighbourhood
 __global__ void __launch_bounds__(256)
 gft_candidates_kernel(const float* __restrict__ eig, const uint8_t* __restrict__ masks, int H, int W, int n_masks,
@@ -118,7 +126,7 @@ gft_candidates_kernel(const float* __restrict__ eig, const uint8_t* __restrict__
 
 constexpr int GFT_CAP = 16384;      // candidates per (image, mask) kept for the selection (128 KB of shared memory)
 constexpr int GFT_THREADS = 1024;
-constexpr int GFT_K = 16;           // stronger neighbours remembered per candidate
+constexpr int GFT_K = 4;            // stronger neighbours remembered per candidate (more: rescan the rank image)
 
 // one block per (image, mask): sort descending, greedy minimum-distance selection in parallel rounds, strongest first out
 __global__ void __launch_bounds__(GFT_THREADS)
@@ -129,8 +137,13 @@ gft_select_kernel(const unsigned long long* __restrict__ keys_in, const int32_t*
   extern __shared__ unsigned long long skey[];
   __shared__ int n_undecided, n_acc_total;
   __shared__ int warp_sums[GFT_THREADS / 32];
-  const int img = blockIdx.x;             // one launch per mask: the rank image of an image serves one mask at a time
-  const int list = img * n_masks + mask_index;
+  // mask_index >= 0: one launch per mask (masks may overlap, the rank image of an image serves one mask at a time);
+  // mask_index < 0: masks are pixel-disjoint, one launch for all lists, rank-image entries are tagged with their mask
+  const int img = mask_index >= 0 ? blockIdx.x : blockIdx.x / n_masks;
+  const int mk = mask_index >= 0 ? mask_index : blockIdx.x % n_masks;
+  const int list = img * n_masks + mk;
+  const int scratch = mask_index >= 0 ? img : list;   // which slice of state / nbr / ncnt this block owns
+  const int tag = mk << 16;
   const int n = min(counts[list], cap);
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
@@ -150,10 +163,10 @@ gft_select_kernel(const unsigned long long* __restrict__ keys_in, const int32_t*
       }
       __syncthreads();
     }
-  int32_t* rimg = rank_img + (size_t)img * H * W;   // one mask at a time per image: this kernel runs once per mask
-  uint8_t* state = state_all + (size_t)img * cap;    // 0 undecided, 1 accepted, 2 rejected
+  int32_t* rimg = rank_img + (size_t)img * H * W;
+  uint8_t* state = state_all + (size_t)scratch * cap;   // 0 undecided, 1 accepted, 2 rejected
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    rimg[(uint32_t)skey[i]] = i;
+    rimg[(uint32_t)skey[i]] = tag | i;
     state[i] = 0;
   }
   if (threadIdx.x == 0) n_undecided = n;
@@ -161,8 +174,8 @@ gft_select_kernel(const unsigned long long* __restrict__ keys_in, const int32_t*
   if (min_dist_sq > 0) {
     // phase A (once): the stronger candidates closer than minDistance to candidate i.  All rank-image loads of a candidate
     // are independent, so they overlap; the rounds below then touch only these few entries.
-    uint16_t* nbr = nbr_all + (size_t)img * cap * GFT_K;
-    uint8_t* ncnt = ncnt_all + (size_t)img * cap;
+    uint16_t* nbr = nbr_all + (size_t)scratch * cap * GFT_K;
+    uint8_t* ncnt = ncnt_all + (size_t)scratch * cap;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const int px = (int)(uint32_t)skey[i];
       const int y = px / W, x = px - y * W;
@@ -173,8 +186,9 @@ gft_select_kernel(const unsigned long long* __restrict__ keys_in, const int32_t*
         for (int dx = -reach; dx <= reach; ++dx) {
           const int xx = x + dx;
           if (xx < 0 || xx >= W || dx * dx + dy * dy >= min_dist_sq) continue;
-          const int j = rimg[(size_t)yy * W + xx];
-          if (j >= 0 && j < i) {
+          const int e = rimg[(size_t)yy * W + xx];
+          const int j = e & 0xFFFF;
+          if (e >= 0 && (e >> 16) == mk && j < i) {
             if (cnt < GFT_K) nbr[(size_t)i * GFT_K + cnt] = (uint16_t)j;
             ++cnt;
           }
@@ -209,8 +223,9 @@ gft_select_kernel(const unsigned long long* __restrict__ keys_in, const int32_t*
             for (int dx = -reach; dx <= reach; ++dx) {
               const int xx = x + dx;
               if (xx < 0 || xx >= W || dx * dx + dy * dy >= min_dist_sq) continue;
-              const int j = rimg[(size_t)yy * W + xx];
-              if (j < 0 || j >= i) continue;
+              const int e = rimg[(size_t)yy * W + xx];
+              const int j = e & 0xFFFF;
+              if (e < 0 || (e >> 16) != mk || j >= i) continue;
               const uint8_t sj = ((volatile uint8_t*)state)[j];
               if (sj == 1) { rejected = true; break; }
               if (sj == 0) wait = true;
@@ -308,9 +323,10 @@ extern "C" int sos_gft_detect(sos_ctx* ctx, const uint8_t* gray, const uint8_t* 
   const size_t o_cnt = take((size_t)lists * sizeof(int32_t));
   const size_t o_keys = take((size_t)lists * GFT_CAP * sizeof(unsigned long long));
   const size_t o_rank = take(px * sizeof(int32_t));
-  const size_t o_state = take((size_t)n_images * GFT_CAP);
-  const size_t o_nbr = take((size_t)n_images * GFT_CAP * GFT_K * sizeof(uint16_t));
-  const size_t o_ncnt = take((size_t)n_images * GFT_CAP);
+  const size_t o_state = take((size_t)lists * GFT_CAP);
+  const size_t o_nbr = take((size_t)lists * GFT_CAP * GFT_K * sizeof(uint16_t));
+  const size_t o_ncnt = take((size_t)lists * GFT_CAP);
+  const size_t o_flag = take(sizeof(int32_t));
   void* ws = nullptr;
   const int rc = sos_arena_get(ctx, off, &ws);
   if (rc != SOS_OK) return rc;
@@ -345,7 +361,25 @@ extern "C" int sos_gft_detect(sos_ctx* ctx, const uint8_t* gray, const uint8_t* 
   const double md2 = min_distance * min_distance;
   const int min_dist_sq = min_distance >= 1.0 ? (int)ceil(md2) : 0;   // integer offsets: dx^2 + dy^2 < minDistance^2
   const int reach = (int)ceil(min_distance);
-  // masks may overlap, and each selection needs the rank image of its image to itself: one launch per mask
+  // pixel-disjoint masks (the reference's default, overlap_degrees = 0): every list at once.  Overlapping masks: a pixel can
+  // be a candidate of two lists and each selection needs the rank image of its image to itself -> one launch per mask.
+  int overlap = 0;
+  if (masks && n_masks > 1) {
+    int32_t* flag = (int32_t*)(base + o_flag);
+    SOS_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t), ctx->stream));
+    gft_mask_overlap_kernel<<<sos_div_up((int)((size_t)height * width), 256), 256, 0, ctx->stream>>>(masks, (size_t)height * width,
+                                                                                                 n_masks, flag);
+    SOS_LAUNCHED(ctx);
+    SOS_CUDA(cudaMemcpyAsync(&overlap, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SOS_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  if (!overlap) {
+    gft_select_kernel<<<lists, GFT_THREADS, smem, ctx->stream>>>(keys, counts, GFT_CAP, height, width, n_masks, -1, max_corners,
+                                                                 min_dist_sq, reach, rank_img, state, (uint16_t*)(base + o_nbr),
+                                                                 base + o_ncnt, out_xy, out_count);
+    SOS_LAUNCHED(ctx);
+    return SOS_OK;
+  }
   for (int m = 0; m < n_masks; ++m) {
     gft_select_kernel<<<n_images, GFT_THREADS, smem, ctx->stream>>>(keys, counts, GFT_CAP, height, width, n_masks, m, max_corners,
                                                                     min_dist_sq, reach, rank_img, state, (uint16_t*)(base + o_nbr), base + o_ncnt, out_xy,
