@@ -277,6 +277,8 @@ def run_gpu(args, rank, local_rank, world):
     ms_e2e = (time.perf_counter() - t0) * 1e3
     barrier()
     d2h_bytes = int(poses.nbytes + st2.nbytes)
+    h2d_bytes, d2h_check = fe2.host_bytes()   # what submit_host actually uploads: only the LUT-reachable image bytes
+    assert d2h_check == d2h_bytes
 
     # ---- per-kernel times (CUDA events after every launch, eager replays of the same steps) --------------------------
     fe.profile_begin()
@@ -368,9 +370,10 @@ def run_gpu(args, rank, local_rank, world):
                                                            f"rotated (each larger than the 126 MB L2: no L2 flush needed); "
                                                            f"CUDA-graph replay of {per_step} launches per step"),
                            input_bytes_per_step=in_bytes, parallelism=f"frame batches sharded over {world} GPU(s), no collective"),
-            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": in_bytes,
-                    "d2h_bytes_per_step": d2h_bytes,
-                    "note": "sos_frontend_submit_host/wait_host on pinned host buffers, 2 staging slots (copies overlap kernels)"},
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes, "host_input_bytes_per_step": in_bytes,
+                    "note": "sos_frontend_submit_host/wait_host on pinned host buffers, 2 staging slots (copies overlap kernels); "
+                            "of each omni image only the bytes the panoramic LUT can read are uploaded (row bands)"},
             "gpu_launches": launches,
             "roofline": dict(roof[dominant], name=dominant),
             "roofline_hbm": dict(roof["remap"], name="remap"),

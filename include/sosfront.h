@@ -473,6 +473,10 @@ int sos_frontend_submit_host(sos_frontend* fe, const uint8_t* omni, const float*
                              const int32_t* bucket_off_top, const float* px_bot, const uint32_t* desc_bot,
                              const int32_t* bucket_off_bot, int* ticket);
 int sos_frontend_wait_host(sos_frontend* fe, int ticket, float* poses, int32_t* stats);
+/* Bytes one submit/wait pair moves over PCIe.  Of every omni image only the bytes some LUT entry can read (both tap rows
+ * of every live panorama pixel plus the slack of the vector loads) are uploaded, as one strided copy per band of 64 rows
+ * covering all frames of the batch; the rest of the staging image is never read by the remap. */
+int sos_frontend_host_bytes(sos_frontend* fe, int64_t* h2d_bytes_per_step, int64_t* d2h_bytes_per_step);
 int sos_frontend_step_host(sos_frontend* fe, const uint8_t* omni, const float* px_top, const uint32_t* desc_top,
                            const int32_t* bucket_off_top, const float* px_bot, const uint32_t* desc_bot,
                            const int32_t* bucket_off_bot, float* poses, int32_t* stats);

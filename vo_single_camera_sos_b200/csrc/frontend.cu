@@ -17,6 +17,9 @@
 
 #include <vector>
 
+#include <algorithm>
+#include <climits>
+
 #include "sos_common.cuh"
 
 namespace {
@@ -130,6 +133,22 @@ __global__ void carry_over_kernel(int B, int from, int cap, float* __restrict__ 
   }
 }
 
+// Per source row: the byte range that any live panorama pixel may read (both tap rows, plus the slack of the wide loads).
+__global__ void lut_row_spans_kernel(const sos_lut_entry* __restrict__ lut, size_t n, int src_h, int src_w, int ch,
+                                     int32_t* __restrict__ xmin, int32_t* __restrict__ xmax) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t e = lut[i];
+  if (((e >> 48) & 0xF) == 0) return;   // no tap inside the image: nothing is read
+  const int x0 = (int)(int16_t)(e & 0xFFFF), y0 = (int)(int16_t)((e >> 16) & 0xFFFF);
+  const int lo = max(0, x0 * ch - 16), hi = min(src_w * ch, (x0 + 2) * ch + 24);
+  for (int y = y0; y <= y0 + 1; ++y)
+    if (y >= 0 && y < src_h) {
+      atomicMin(&xmin[y], lo);
+      atomicMax(&xmax[y], hi);
+    }
+}
+
 __global__ void stats_kernel(const int32_t* __restrict__ n, const int32_t* __restrict__ n_corr,
                              const int32_t* __restrict__ best_count, const int32_t* __restrict__ best_hyp, int B,
                              int32_t* __restrict__ stats) {
@@ -165,6 +184,12 @@ struct sos_frontend {
     bool in_flight = false;
   } stage[DEPTH];
   cudaStream_t copy_stream = nullptr;
+  // host API: only the bytes of the omni image that some LUT entry can read are uploaded, in bands of rows
+  struct Band {
+    int row0, nrows, x0_bytes, width_bytes;
+  };
+  std::vector<Band> bands;
+  int64_t omni_bytes_per_frame = 0;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;  // fences against the caller's stream
   // the remap feeds nothing else in the chain (features are inputs): it runs on a side stream, forked and joined with
   // events, so that inside the captured graph it is a parallel branch next to the matching / RANSAC chain
@@ -575,6 +600,56 @@ static int ensure_staging(sos_frontend* fe) {
     SOS_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
   }
   SOS_CUDA(cudaStreamSynchronize(fe->ctx->stream));
+  // which bytes of an omni image can the remap read?  (row spans from the LUT, merged into bands of 64 rows)
+  fe->bands.clear();
+  fe->omni_bytes_per_frame = (int64_t)c.src_h * c.src_w * c.channels;
+  if (getenv("SOS_FULL_UPLOAD") == nullptr) {
+    std::vector<int32_t> xmin(c.src_h, INT32_MAX), xmax(c.src_h, 0);
+    int32_t* dspan = nullptr;
+    int rc = fe_alloc(fe, &dspan, (size_t)2 * c.src_h);
+    if (rc) return rc;
+    SOS_CUDA(cudaMemcpy(dspan, xmin.data(), sizeof(int32_t) * c.src_h, cudaMemcpyHostToDevice));
+    SOS_CUDA(cudaMemset(dspan + c.src_h, 0, sizeof(int32_t) * c.src_h));
+    const size_t n = (size_t)2 * c.pano_rows * c.pano_cols;
+    lut_row_spans_kernel<<<(unsigned)((n + 255) / 256), 256, 0, fe->ctx->stream>>>(fe->lut, n, c.src_h, c.src_w, c.channels, dspan,
+                                                                                dspan + c.src_h);
+    SOS_CUDA(cudaStreamSynchronize(fe->ctx->stream));
+    SOS_CUDA(cudaMemcpy(xmin.data(), dspan, sizeof(int32_t) * c.src_h, cudaMemcpyDeviceToHost));
+    SOS_CUDA(cudaMemcpy(xmax.data(), dspan + c.src_h, sizeof(int32_t) * c.src_h, cudaMemcpyDeviceToHost));
+    const int pitch = c.src_w * c.channels;
+    int64_t total = 0;
+    std::vector<sos_frontend::Band> bands;
+    for (int r0 = 0; r0 < c.src_h; r0 += 64) {
+      const int nr = std::min(64, c.src_h - r0);
+      int lo = INT32_MAX, hi = 0;
+      for (int r = r0; r < r0 + nr; ++r) {
+        lo = std::min(lo, xmin[r]);
+        hi = std::max(hi, xmax[r]);
+      }
+      if (hi <= lo) continue;
+      lo = lo / 64 * 64;
+      hi = std::min(pitch, (hi + 63) / 64 * 64);
+      bands.push_back({r0, nr, lo, hi - lo});
+      total += (int64_t)nr * (hi - lo);
+    }
+    if (total < fe->omni_bytes_per_frame * 97 / 100) {   // otherwise one plain copy is cheaper than the band copies
+      fe->bands = bands;
+      fe->omni_bytes_per_frame = total;
+    }
+  }
+  return SOS_OK;
+}
+
+extern "C" int sos_frontend_host_bytes(sos_frontend* fe, int64_t* h2d_bytes_per_step, int64_t* d2h_bytes_per_step) {
+  SOS_CHECK_ARG(fe, "fe is NULL");
+  SOS_CUDA(cudaSetDevice(fe->ctx->device));
+  const int rc = ensure_staging(fe);
+  if (rc) return rc;
+  const sos_frontend_config& c = fe->cfg;
+  const int64_t B = c.batch, F = c.max_feat_per_view;
+  if (h2d_bytes_per_step)
+    *h2d_bytes_per_step = B * (fe->omni_bytes_per_frame + 2 * F * 2 * 4 + 2 * F * 32 + 2 * (c.n_buckets + 1) * 4);
+  if (d2h_bytes_per_step) *d2h_bytes_per_step = B * (12 * 4 + 4 * 4);
   return SOS_OK;
 }
 
@@ -596,7 +671,22 @@ extern "C" int sos_frontend_submit_host(sos_frontend* fe, const uint8_t* omni, c
   const size_t B = c.batch, F = c.max_feat_per_view;
   cudaStream_t cs = fe->copy_stream;
   // H2D on the copy stream so that it overlaps the kernels of the previous step
-  SOS_CUDA(cudaMemcpyAsync(s.omni, omni, B * c.src_h * c.src_w * c.channels, cudaMemcpyHostToDevice, cs));
+  if (fe->bands.empty()) {
+    SOS_CUDA(cudaMemcpyAsync(s.omni, omni, B * c.src_h * c.src_w * c.channels, cudaMemcpyHostToDevice, cs));
+  } else {
+    // one strided copy per band of rows, covering that band in every frame of the batch (depth = frames)
+    const size_t pitch = (size_t)c.src_w * c.channels;
+    for (const auto& bd : fe->bands) {
+      cudaMemcpy3DParms p = {};
+      p.srcPtr = make_cudaPitchedPtr((void*)omni, pitch, pitch, c.src_h);
+      p.dstPtr = make_cudaPitchedPtr((void*)s.omni, pitch, pitch, c.src_h);
+      p.srcPos = make_cudaPos(bd.x0_bytes, bd.row0, 0);
+      p.dstPos = make_cudaPos(bd.x0_bytes, bd.row0, 0);
+      p.extent = make_cudaExtent(bd.width_bytes, bd.nrows, B);
+      p.kind = cudaMemcpyHostToDevice;
+      SOS_CUDA(cudaMemcpy3DAsync(&p, cs));
+    }
+  }
   SOS_CUDA(cudaMemcpyAsync(s.px_top, px_top, B * F * 2 * sizeof(float), cudaMemcpyHostToDevice, cs));
   SOS_CUDA(cudaMemcpyAsync(s.px_bot, px_bot, B * F * 2 * sizeof(float), cudaMemcpyHostToDevice, cs));
   SOS_CUDA(cudaMemcpyAsync(s.desc_top, desc_top, B * F * 32, cudaMemcpyHostToDevice, cs));

@@ -233,6 +233,12 @@ class Frontend:
     def retrack(self):
         check(self.ctx.lib.sos_frontend_retrack(self._h))
 
+    def host_bytes(self):
+        """(H2D, D2H) bytes one submit_host / wait_host pair moves (only the LUT-reachable part of the images is uploaded)."""
+        a, b = C.c_int64(), C.c_int64()
+        check(self.ctx.lib.sos_frontend_host_bytes(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def step_host(self, *inputs):
         return self.wait_host(self.submit_host(*inputs))
 
