@@ -458,7 +458,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "tiny"])
-    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--batch", type=int, default=32, help="frames (= frame pairs) per step and GPU")
     ap.add_argument("--score", default="bearing", choices=["bearing", "euclid"])
     ap.add_argument("--refine", default="arun", choices=["none", "arun", "lm"],
                     help="pose after RANSAC: Arun refit on the inliers, or Levenberg-Marquardt on the bearing residual")
