@@ -95,6 +95,68 @@ median11_kernel(const uint8_t* __restrict__ src, int H, int W, int strip_rows, u
   }
 }
 
+
+// ---- lane-per-(column, channel) variant ----------------------------------------------------------------------------------
+// ncu on the warp-cooperative kernel above: 219 instructions per two-pixel step with 18 of 32 lanes active on average, issue
+// slots 89 % busy, 5.8 shared-memory wavefronts per atomic.  Here every lane owns one (column, channel) histogram of byte
+// counters (layout word = bin * 8 + lane / 4, byte = lane % 4: 8 KB per warp) and walks down its column by itself: per row 11
+// values leave and 11 enter the window with plain byte read-modify-writes — no atomics, no ballots, no idle lanes.
+constexpr int ML_WARPS = 4;
+
+template <int C>
+__global__ void __launch_bounds__(ML_WARPS * 32)
+median11_lane_kernel(const uint8_t* __restrict__ src, int H, int W, int strip_rows, uint8_t* __restrict__ dst) {
+  constexpr int COLS = 32 / C;                           // columns per warp: 10 for BGR, 32 for gray
+  __shared__ uint32_t hist_all[ML_WARPS][256 * 8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int x0 = (blockIdx.x * ML_WARPS + warp) * COLS;
+  if (x0 >= W) return;                                   // whole warps leave together; only __syncwarp below
+  const int y0 = blockIdx.y * strip_rows, y1 = min(H, y0 + strip_rows);
+  const uint8_t* img = src + (size_t)blockIdx.z * H * W * C;
+  uint8_t* out = dst + (size_t)blockIdx.z * H * W * C;
+  uint32_t* hw = hist_all[warp];
+  for (int i = lane; i < 256 * 8; i += 32) hw[i] = 0u;
+  __syncwarp();
+  const int col = lane / C, ch = lane - col * C;
+  const bool active = col < COLS && x0 + col < W;
+  if (!active) return;
+  const int x = x0 + col;
+  uint8_t* hb = (uint8_t*)hw + lane;                     // this lane's counter of bin b lives at hb[b * 32]
+  int xo[2 * MB_R + 1];                                  // byte offsets of the window columns inside a row (replicated border)
+#pragma unroll
+  for (int k = 0; k <= 2 * MB_R; ++k) xo[k] = min(max(x + k - MB_R, 0), W - 1) * C + ch;
+  const size_t pitch = (size_t)W * C;
+  int m = 0, ltm = 0;                                    // median candidate and the number of window values below it
+
+  for (int r = y0 - MB_R; r <= y0 + MB_R; ++r) {
+    const uint8_t* row = img + (size_t)min(max(r, 0), H - 1) * pitch;
+#pragma unroll
+    for (int k = 0; k <= 2 * MB_R; ++k) hb[(int)row[xo[k]] * 32] += 1;
+  }
+  while (ltm + (int)hb[m * 32] <= MB_HALF) { ltm += hb[m * 32]; ++m; }
+  out[(size_t)y0 * pitch + (size_t)x * C + ch] = (uint8_t)m;
+
+  for (int y = y0 + 1; y < y1; ++y) {
+    const uint8_t* rold = img + (size_t)min(max(y - MB_R - 1, 0), H - 1) * pitch;
+    const uint8_t* rnew = img + (size_t)min(max(y + MB_R, 0), H - 1) * pitch;
+    int vo[2 * MB_R + 1], vn[2 * MB_R + 1];
+#pragma unroll
+    for (int k = 0; k <= 2 * MB_R; ++k) {                // all 22 loads first: they are independent
+      vo[k] = __ldg(rold + xo[k]);
+      vn[k] = __ldg(rnew + xo[k]);
+    }
+#pragma unroll
+    for (int k = 0; k <= 2 * MB_R; ++k) {
+      hb[vo[k] * 32] -= 1;
+      hb[vn[k] * 32] += 1;
+      ltm += (vn[k] < m ? 1 : 0) - (vo[k] < m ? 1 : 0);
+    }
+    while (ltm > MB_HALF) { --m; ltm -= hb[m * 32]; }
+    while (ltm + (int)hb[m * 32] <= MB_HALF) { ltm += hb[m * 32]; ++m; }
+    out[(size_t)y * pitch + (size_t)x * C + ch] = (uint8_t)m;
+  }
+}
+
 }  // namespace
 
 extern "C" int sos_median_blur_11(sos_ctx* ctx, const uint8_t* src, int n_images, int height, int width, int channels,
@@ -107,9 +169,17 @@ extern "C" int sos_median_blur_11(sos_ctx* ctx, const uint8_t* src, int n_images
   SOS_CHECK_ARG(n_images <= 65535, "too many images");
   SOS_CUDA(cudaSetDevice(ctx->device));
   const int strip = 128;
-  dim3 grid(sos_div_up(width, MB_WARPS * MB_COLS), sos_div_up(height, strip), n_images);
-  if (channels == 3) median11_kernel<3><<<grid, MB_WARPS * 32, 0, ctx->stream>>>(src, height, width, strip, dst);
-  else median11_kernel<1><<<grid, MB_WARPS * 32, 0, ctx->stream>>>(src, height, width, strip, dst);
+  static const bool coop = getenv("SOS_MEDIAN_V1") != nullptr;   // A/B switch: the warp-cooperative kernel
+  if (coop) {
+    dim3 grid(sos_div_up(width, MB_WARPS * MB_COLS), sos_div_up(height, strip), n_images);
+    if (channels == 3) median11_kernel<3><<<grid, MB_WARPS * 32, 0, ctx->stream>>>(src, height, width, strip, dst);
+    else median11_kernel<1><<<grid, MB_WARPS * 32, 0, ctx->stream>>>(src, height, width, strip, dst);
+  } else {
+    const int cols_per_block = ML_WARPS * (32 / channels);
+    dim3 grid(sos_div_up(width, cols_per_block), sos_div_up(height, strip), n_images);
+    if (channels == 3) median11_lane_kernel<3><<<grid, ML_WARPS * 32, 0, ctx->stream>>>(src, height, width, strip, dst);
+    else median11_lane_kernel<1><<<grid, ML_WARPS * 32, 0, ctx->stream>>>(src, height, width, strip, dst);
+  }
   SOS_LAUNCHED(ctx);
   return SOS_OK;
 }
