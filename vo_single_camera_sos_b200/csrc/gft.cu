@@ -50,10 +50,16 @@ __global__ void __launch_bounds__(256) gft_cov_kernel(const uint8_t* __restrict_
   (void)a11;
 }
 
-__global__ void __launch_bounds__(256) gft_eig_kernel(const float* __restrict__ cov, int H, int W, float* __restrict__ eig) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= W) return;
-  const float* c = cov + 3 * (size_t)blockIdx.z * H * W;
+// corner measure + (optionally) the maximum over each mask, fused: `mask_bits` holds one bit per mask and pixel; per warp
+// only the masks present in the warp are reduced (one atomic per mask and warp at most).  Non-negative floats order like
+// their bit patterns, so the maxima are kept as uint32.
+__global__ void __launch_bounds__(256)
+gft_eig_kernel(const float* __restrict__ cov, int H, int W, float* __restrict__ eig, const uint32_t* __restrict__ mask_bits,
+               int n_masks, uint32_t* __restrict__ max_bits) {
+  const int xr = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, img = blockIdx.z;
+  const bool in = xr < W;
+  const int x = in ? xr : W - 1;
+  const float* c = cov + 3 * (size_t)img * H * W;
   double sa = 0.0, sb = 0.0, sc = 0.0;
 #pragma unroll
   for (int j = -1; j <= 1; ++j) {
@@ -69,58 +75,102 @@ __global__ void __launch_bounds__(256) gft_eig_kernel(const float* __restrict__ 
   const float a = __fmul_rn((float)sa, 0.5f), b = (float)sb, cc = __fmul_rn((float)sc, 0.5f);
   const float t = __fsub_rn(a, cc);
   const float r = __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b)));
-  eig[((size_t)blockIdx.z * H + y) * W + x] = __fsub_rn(__fadd_rn(a, cc), r);
-}
-
-// max of eig over each mask (minMaxLoc with mask): non-negative floats order like their bit patterns.  One pass over the
-// pixels; per mask a warp maximum and at most one atomic per warp.
-__global__ void __launch_bounds__(256)
-gft_masked_max_kernel(const float* __restrict__ eig, const uint8_t* __restrict__ masks, int H, int W, int n_masks,
-                      uint32_t* __restrict__ max_bits) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, img = blockIdx.z;
-  const bool in = x < W;
-  const size_t px = (size_t)y * W + (in ? x : 0);
-  const float v = in ? eig[(size_t)img * H * W + px] : 0.f;
-  for (int m = 0; m < n_masks; ++m) {
-    float best = (in && (!masks || masks[(size_t)m * H * W + px])) ? v : 0.f;
-    for (int off = 16; off > 0; off >>= 1) best = fmaxf(best, __shfl_xor_sync(0xFFFFFFFFu, best, off));
-    if ((threadIdx.x & 31) == 0 && best > 0.f && __float_as_uint(best) > max_bits[img * n_masks + m])
-      atomicMax(&max_bits[img * n_masks + m], __float_as_uint(best));
+  const float v = __fsub_rn(__fadd_rn(a, cc), r);
+  if (in) eig[((size_t)img * H + y) * W + x] = v;
+  if (mask_bits) {
+    const uint32_t mb = (in && v > 0.f) ? mask_bits[(size_t)y * W + x] : 0u;
+    uint32_t present = __reduce_or_sync(0xFFFFFFFFu, mb);
+    while (present) {
+      const int m = __ffs(present) - 1;
+      present &= present - 1;
+      const uint32_t best = __reduce_max_sync(0xFFFFFFFFu, ((mb >> m) & 1u) ? __float_as_uint(v) : 0u);
+      if ((threadIdx.x & 31) == 0 && best > max_bits[img * n_masks + m]) atomicMax(&max_bits[img * n_masks + m], best);
+    }
   }
 }
 
-__global__ void gft_mask_overlap_kernel(const uint8_t* __restrict__ masks, size_t per, int n_masks, int32_t* __restrict__ flag) {
+// one bit per mask and pixel (masks are shared by all images); flags pixels that belong to more than one mask
+__global__ void gft_pack_masks_kernel(const uint8_t* __restrict__ masks, size_t per, int n_masks, uint32_t* __restrict__ bits,
+                                      int32_t* __restrict__ overlap) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= per) return;
-  int c = 0;
-  for (int m = 0; m < n_masks; ++m) c += masks[(size_t)m * per + i] ? 1 : 0;
-  if (c > 1) *flag = 1;
+  uint32_t b = 0;
+  if (!masks) b = 1u;
+  else
+    for (int m = 0; m < n_masks; ++m) b |= (masks[(size_t)m * per + i] ? 1u : 0u) << m;
+  bits[i] = b;
+  if (__popc(b) > 1) *overlap = 1;
 }
 
-// candidates: interior pixels above the mask's threshold that equal the maximum of their 3x3 neighbourhood
+// candidates: interior pixels above the mask's threshold that equal the maximum of their 3x3 neighbourhood.
+// A block covers GC_ROWS rows x 256 columns, stages its candidates in shared memory and reserves their slots in the
+// per-list arrays with ONE global atomic per (block, mask): returning atomics on a few hundred hot counters were the whole
+// cost of the first version (ncu: long-scoreboard stall 94, every pipe idle).
+constexpr int GC_ROWS = 8;
+constexpr int GC_STAGE = 1024;
+
 __global__ void __launch_bounds__(256)
-gft_candidates_kernel(const float* __restrict__ eig, const uint8_t* __restrict__ masks, int H, int W, int n_masks,
+gft_candidates_kernel(const float* __restrict__ eig, const uint32_t* __restrict__ mask_bits, int H, int W, int n_masks,
                       const uint32_t* __restrict__ max_bits, double quality, int cap, unsigned long long* __restrict__ keys,
                       int32_t* __restrict__ counts) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, img = blockIdx.z;
-  if (x < 1 || x >= W - 1 || y < 1 || y >= H - 1) return;
+  __shared__ unsigned long long s_key[GC_STAGE];
+  __shared__ uint8_t s_m[GC_STAGE];
+  __shared__ int s_n, s_cnt[32], s_base[32], s_fill[32];
+  __shared__ float s_thr[32];
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, img = blockIdx.z;
+  if (threadIdx.x < 32) {
+    s_cnt[threadIdx.x] = 0;
+    s_fill[threadIdx.x] = 0;
+    // threshold(eig, eig, maxVal * qualityLevel, 0, THRESH_TOZERO) with the mask's own maximum
+    s_thr[threadIdx.x] = threadIdx.x < n_masks ? (float)((double)__uint_as_float(max_bits[img * n_masks + threadIdx.x]) * quality)
+                                               : CUDART_INF_F;
+  }
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
   const float* e = eig + (size_t)img * H * W;
-  const float v = e[(size_t)y * W + x];
-  if (!(v > 0.f)) return;
-  float nb = 0.f;
+  for (int r = 0; r < GC_ROWS; ++r) {
+    const int y = blockIdx.y * GC_ROWS + r;
+    if (x < 1 || x >= W - 1 || y < 1 || y >= H - 1) continue;
+    const size_t px = (size_t)y * W + x;
+    const float v = e[px];
+    if (!(v > 0.f)) continue;
+    uint32_t mb = mask_bits[px], pass = 0;
+    while (mb) {                                         // the threshold test first: one load, removes most pixels
+      const int m = __ffs(mb) - 1;
+      mb &= mb - 1;
+      if (v > s_thr[m]) pass |= 1u << m;
+    }
+    if (!pass) continue;
+    float nb = 0.f;
 #pragma unroll
-  for (int j = -1; j <= 1; ++j)
+    for (int j = -1; j <= 1; ++j)
 #pragma unroll
-    for (int i = -1; i <= 1; ++i) nb = fmaxf(nb, e[(size_t)(y + j) * W + x + i]);
-  if (v != nb) return;
-  const size_t px = (size_t)y * W + x;
-  for (int m = 0; m < n_masks; ++m) {
-    if (masks && !masks[(size_t)m * H * W + px]) continue;
-    const float mx = __uint_as_float(max_bits[img * n_masks + m]);
-    const float thr = (float)((double)mx * quality);   // threshold(eig, eig, maxVal * qualityLevel, 0, THRESH_TOZERO)
-    if (!(v > thr)) continue;
-    const int slot = atomicAdd(&counts[img * n_masks + m], 1);
-    if (slot < cap) keys[((size_t)(img * n_masks + m)) * cap + slot] = ((unsigned long long)__float_as_uint(v) << 32) | (uint32_t)px;
+      for (int i = -1; i <= 1; ++i) nb = fmaxf(nb, e[(size_t)(y + j) * W + x + i]);
+    if (v != nb) continue;
+    const unsigned long long key = ((unsigned long long)__float_as_uint(v) << 32) | (uint32_t)px;
+    while (pass) {
+      const int m = __ffs(pass) - 1;
+      pass &= pass - 1;
+      const int i = atomicAdd(&s_n, 1);
+      if (i < GC_STAGE) {
+        s_key[i] = key;
+        s_m[i] = (uint8_t)m;
+        atomicAdd(&s_cnt[m], 1);
+      } else {                                           // staging full (cannot happen with 3x3 maxima on 8 x 256 pixels)
+        const int slot = atomicAdd(&counts[img * n_masks + m], 1);
+        if (slot < cap) keys[((size_t)(img * n_masks + m)) * cap + slot] = key;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < n_masks && s_cnt[threadIdx.x] > 0)
+    s_base[threadIdx.x] = atomicAdd(&counts[img * n_masks + threadIdx.x], s_cnt[threadIdx.x]);
+  __syncthreads();
+  const int n = min(s_n, GC_STAGE);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int m = s_m[i];
+    const int slot = s_base[m] + atomicAdd(&s_fill[m], 1);
+    if (slot < cap) keys[((size_t)(img * n_masks + m)) * cap + slot] = s_key[i];
   }
 }
 
@@ -296,7 +346,7 @@ extern "C" int sos_corner_min_eigenval(sos_ctx* ctx, const uint8_t* gray, int n_
   dim3 grid(sos_div_up(width, 256), height, n_images);
   gft_cov_kernel<<<grid, 256, 0, ctx->stream>>>(gray, height, width, (float*)ws);
   SOS_LAUNCHED(ctx);
-  gft_eig_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)ws, height, width, eig);
+  gft_eig_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)ws, height, width, eig, nullptr, 0, nullptr);
   SOS_LAUNCHED(ctx);
   return SOS_OK;
 }
@@ -305,7 +355,7 @@ extern "C" int sos_gft_detect(sos_ctx* ctx, const uint8_t* gray, const uint8_t* 
                               int n_masks, int max_corners, double quality_level, double min_distance, float* out_xy,
                               int32_t* out_count, float* eig_out) {
   SOS_CHECK_ARG(ctx, "ctx is NULL");
-  SOS_CHECK_ARG(n_images >= 0 && height >= 0 && width >= 0 && n_masks >= 1 && max_corners >= 0, "bad size");
+  SOS_CHECK_ARG(n_images >= 0 && height >= 0 && width >= 0 && n_masks >= 1 && n_masks <= 32 && max_corners >= 0, "bad size (at most 32 masks)");
   SOS_CHECK_ARG(quality_level > 0.0 && min_distance >= 0.0 && min_distance < 64.0, "bad quality level / minimum distance");
   if (n_images == 0) return SOS_OK;
   SOS_CHECK_ARG(gray && out_count && (out_xy || max_corners == 0), "NULL array");
@@ -327,6 +377,7 @@ extern "C" int sos_gft_detect(sos_ctx* ctx, const uint8_t* gray, const uint8_t* 
   const size_t o_nbr = take((size_t)lists * GFT_CAP * GFT_K * sizeof(uint16_t));
   const size_t o_ncnt = take((size_t)lists * GFT_CAP);
   const size_t o_flag = take(sizeof(int32_t));
+  const size_t o_bits = take((size_t)height * width * sizeof(uint32_t));
   void* ws = nullptr;
   const int rc = sos_arena_get(ctx, off, &ws);
   if (rc != SOS_OK) return rc;
@@ -340,17 +391,21 @@ extern "C" int sos_gft_detect(sos_ctx* ctx, const uint8_t* gray, const uint8_t* 
   uint8_t* state = base + o_state;
 
   dim3 grid(sos_div_up(width, 256), height, n_images);
+  const size_t per = (size_t)height * width;
+  uint32_t* mask_bits = (uint32_t*)(base + o_bits);
+  int32_t* flag = (int32_t*)(base + o_flag);
+  SOS_CUDA(cudaMemsetAsync(base + o_max, 0, (o_keys - o_max), ctx->stream));          // max_bits and counts
+  SOS_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t), ctx->stream));
+  SOS_CUDA(cudaMemsetAsync(rank_img, 0xFF, px * sizeof(int32_t), ctx->stream));       // -1
+  gft_pack_masks_kernel<<<(unsigned)((per + 255) / 256), 256, 0, ctx->stream>>>(masks, per, n_masks, mask_bits, flag);
+  SOS_LAUNCHED(ctx);
   gft_cov_kernel<<<grid, 256, 0, ctx->stream>>>(gray, height, width, cov);
   SOS_LAUNCHED(ctx);
-  gft_eig_kernel<<<grid, 256, 0, ctx->stream>>>(cov, height, width, eig);
+  gft_eig_kernel<<<grid, 256, 0, ctx->stream>>>(cov, height, width, eig, mask_bits, n_masks, max_bits);
   SOS_LAUNCHED(ctx);
   if (eig_out) SOS_CUDA(cudaMemcpyAsync(eig_out, eig, px * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
-  SOS_CUDA(cudaMemsetAsync(base + o_max, 0, (o_keys - o_max), ctx->stream));          // max_bits and counts
-  SOS_CUDA(cudaMemsetAsync(rank_img, 0xFF, px * sizeof(int32_t), ctx->stream));       // -1
-  gft_masked_max_kernel<<<grid, 256, 0, ctx->stream>>>(eig, masks, height, width, n_masks, max_bits);
-  SOS_LAUNCHED(ctx);
-  gft_candidates_kernel<<<grid, 256, 0, ctx->stream>>>(eig, masks, height, width, n_masks, max_bits, quality_level, GFT_CAP,
-                                                       keys, counts);
+  gft_candidates_kernel<<<dim3(sos_div_up(width, 256), sos_div_up(height, GC_ROWS), n_images), 256, 0, ctx->stream>>>(
+      eig, mask_bits, height, width, n_masks, max_bits, quality_level, GFT_CAP, keys, counts);
   SOS_LAUNCHED(ctx);
   static bool attr_set = false;
   const size_t smem = (size_t)GFT_CAP * sizeof(unsigned long long);
@@ -365,11 +420,6 @@ extern "C" int sos_gft_detect(sos_ctx* ctx, const uint8_t* gray, const uint8_t* 
   // be a candidate of two lists and each selection needs the rank image of its image to itself -> one launch per mask.
   int overlap = 0;
   if (masks && n_masks > 1) {
-    int32_t* flag = (int32_t*)(base + o_flag);
-    SOS_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t), ctx->stream));
-    gft_mask_overlap_kernel<<<sos_div_up((int)((size_t)height * width), 256), 256, 0, ctx->stream>>>(masks, (size_t)height * width,
-                                                                                                 n_masks, flag);
-    SOS_LAUNCHED(ctx);
     SOS_CUDA(cudaMemcpyAsync(&overlap, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     SOS_CUDA(cudaStreamSynchronize(ctx->stream));
   }
