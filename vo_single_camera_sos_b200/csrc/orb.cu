@@ -82,6 +82,20 @@ __global__ void __launch_bounds__(256)
 orb_describe_kernel(const uint8_t* __restrict__ blurred, int H, int W, const float2* __restrict__ kp,
                     const float* __restrict__ angle_deg, const int32_t* __restrict__ img_idx, int n,
                     uint32_t* __restrict__ desc, uint8_t* __restrict__ keep) {
+  // without per-keypoint angles (cv2.KeyPoint_convert: -1 degree for all) the rotated test offsets are the same for every
+  // keypoint: computed once per block
+  __shared__ int s_off[512];
+  if (!angle_deg) {
+    const float ang0 = __fmul_rn(-1.0f, (float)(CUDART_PI / 180.0f));
+    const float a0 = (float)cos((double)ang0), b0 = (float)sin((double)ang0);
+    for (int q = threadIdx.x; q < 512; q += blockDim.x) {
+      const float px = (float)c_orb_pattern[2 * q], py = (float)c_orb_pattern[2 * q + 1];
+      const int ix = __float2int_rn(__fsub_rn(__fmul_rn(px, a0), __fmul_rn(py, b0)));
+      const int iy = __float2int_rn(__fadd_rn(__fmul_rn(px, b0), __fmul_rn(py, a0)));
+      s_off[q] = iy * W + ix;
+    }
+    __syncthreads();
+  }
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (i >= n) return;
@@ -99,6 +113,14 @@ orb_describe_kernel(const uint8_t* __restrict__ blurred, int H, int W, const flo
     ang = __fmul_rn(ang, (float)(CUDART_PI / 180.0f));
     const float a = (float)cos((double)ang), b = (float)sin((double)ang);
     const uint8_t* center = img + (size_t)cy * W + cx;
+    if (!angle_deg) {
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int q = (lane * 8 + t) * 2;
+        const uint32_t v0 = center[s_off[q]], v1 = center[s_off[q + 1]];
+        byte |= (v0 < v1 ? 1u : 0u) << t;
+      }
+    } else
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       const int k = (lane * 8 + t) * 4;
