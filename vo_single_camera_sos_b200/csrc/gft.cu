@@ -16,6 +16,9 @@
 // closer than minDistance has been rejected, rejected once one of them has been accepted): same result, no serial walk.
 #include <math_constants.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "sos_common.cuh"
 
 namespace {
@@ -419,19 +422,29 @@ extern "C" int sos_gft_detect(sos_ctx* ctx, const uint8_t* gray, const uint8_t* 
   // pixel-disjoint masks (the reference's default, overlap_degrees = 0): every list at once.  Overlapping masks: a pixel can
   // be a candidate of two lists and each selection needs the rank image of its image to itself -> one launch per mask.
   int overlap = 0;
+  size_t sel_smem = smem;
   if (masks && n_masks > 1) {
+    // one small read-back: the overlap flag and the candidate counts, which size the selection's shared memory (a block
+    // sorts next_pow2(count) keys: 64 KB instead of 128 KB lets three blocks share an SM)
+    std::vector<int32_t> hc(lists);
     SOS_CUDA(cudaMemcpyAsync(&overlap, flag, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SOS_CUDA(cudaMemcpyAsync(hc.data(), counts, sizeof(int32_t) * lists, cudaMemcpyDeviceToHost, ctx->stream));
     SOS_CUDA(cudaStreamSynchronize(ctx->stream));
+    int mx = 1;
+    for (int v : hc) mx = std::max(mx, std::min(v, GFT_CAP));
+    int np2 = 1024;
+    while (np2 < mx) np2 <<= 1;
+    sel_smem = (size_t)np2 * sizeof(unsigned long long);
   }
   if (!overlap) {
-    gft_select_kernel<<<lists, GFT_THREADS, smem, ctx->stream>>>(keys, counts, GFT_CAP, height, width, n_masks, -1, max_corners,
+    gft_select_kernel<<<lists, GFT_THREADS, sel_smem, ctx->stream>>>(keys, counts, GFT_CAP, height, width, n_masks, -1, max_corners,
                                                                  min_dist_sq, reach, rank_img, state, (uint16_t*)(base + o_nbr),
                                                                  base + o_ncnt, out_xy, out_count);
     SOS_LAUNCHED(ctx);
     return SOS_OK;
   }
   for (int m = 0; m < n_masks; ++m) {
-    gft_select_kernel<<<n_images, GFT_THREADS, smem, ctx->stream>>>(keys, counts, GFT_CAP, height, width, n_masks, m, max_corners,
+    gft_select_kernel<<<n_images, GFT_THREADS, sel_smem, ctx->stream>>>(keys, counts, GFT_CAP, height, width, n_masks, m, max_corners,
                                                                     min_dist_sq, reach, rank_img, state, (uint16_t*)(base + o_nbr), base + o_ncnt, out_xy,
                                                                     out_count);
     SOS_LAUNCHED(ctx);
