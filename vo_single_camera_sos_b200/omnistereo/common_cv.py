@@ -31,3 +31,27 @@ def clean_up(wait_key_time=0):
         cv2.destroyAllWindows()
     except Exception:
         pass
+
+
+def get_images(filename_template, indices_list=[], show_images=False, return_names_only=False):
+    """common_cv.py:1293-1340: the files matching the template (fnmatch on the directory listing); here the names are sorted
+    so that the order does not depend on the file system.  With return_names_only=False the images are read with cv2."""
+    import fnmatch
+    from os import listdir
+    from os.path import join, split
+    import cv2
+    path, pattern = split(filename_template)
+    names = sorted(fnmatch.filter(listdir(path), pattern))
+    if indices_list is None or len(indices_list) == 0:
+        indices_list = range(len(names))
+    chosen = [join(path, names[i]) for i in indices_list]
+    if return_names_only:
+        return chosen
+    return [cv2.imread(fn) for fn in chosen]
+
+
+def get_depthmap_float32_from_png(depth_img_filename, conversion_factor=1. / 1000.0):
+    """common_cv.py: 16-bit depth PNG -> float32 map in metres (0 where there is no measurement)."""
+    import cv2
+    d = cv2.imread(depth_img_filename, cv2.IMREAD_UNCHANGED)
+    return d.astype(np.float32) * np.float32(conversion_factor)

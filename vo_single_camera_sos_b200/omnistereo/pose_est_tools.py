@@ -301,3 +301,124 @@ class TrackerRGBDSE3(TrackerSE3):
         key = self.T_Ckey_wrt_S_est_list[-1] if self.T_Ckey_wrt_S_est_list else tr.identity_matrix()
         self.T_C_curr_frame_wrt_S_est = tr.concatenate_matrices(key, T_homo)
         return True, "tracking used %d inlier point correspondences" % (self.num_tracked_correspondences)
+
+
+class RGBDKeyFrame(RGBDFrame):
+    def __init__(self, frame):
+        self.__dict__.update(frame.__dict__)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The VO loop of the demos (pose_est_tools.py:1264-1741): run_VO / driver_VO with the reference's signatures, headless.
+# One frame per iteration, like the reference; the batched form of the same loop is vo_single_camera_sos_b200.driver.
+# ---------------------------------------------------------------------------------------------------------------------
+def run_VO(visualizer_3D_VO, camera_model, gt_poses_filename=None, est_poses_filename="estimated_frame_poses_TUM.txt",
+           img_filename_template=None, depth_filename_template=None, img_indices=[], results_path="~/temp", thread_name=""):
+    """pose_est_tools.py:1264-1678 without the 3D visualisation (visualizer_3D_VO must be None: vispy / matplotlib drawing
+    is out of scope).  Writes, like the reference: <results>/estimated_frame_poses_TUM.txt, gt_associated_frame_poses_TUM.txt,
+    keyframe_ids.txt, printed_messages.log.  Returns the VOResult of the run."""
+    from os.path import expanduser, join, realpath
+    from .camera_models import OmniStereoModel, RGBDCamModel
+    from .common_cv import get_depthmap_float32_from_png, get_images
+    from .common_tools import get_poses_from_file, make_sure_path_exists
+    from ..driver import KeyframePolicy, TrackingState, tum_line
+    if visualizer_3D_VO is not None:
+        raise NotImplementedError("3D visualisation is not part of this build: pass visualizer_3D_VO=None")
+    prefix = thread_name + ": " if len(thread_name) > 0 else ""
+    is_sos = isinstance(camera_model, OmniStereoModel)
+    tracker_class, keyframe_class = (TrackerStereoSE3, StereoPanoramicKeyFrame) if is_sos else (TrackerRGBDSE3, RGBDKeyFrame)
+    results_path = realpath(expanduser(results_path))
+    make_sure_path_exists(results_path)
+    log = open(join(results_path, "printed_messages.log"), "w")
+    image_names = get_images(img_filename_template, indices_list=img_indices, show_images=False, return_names_only=True)
+    if not is_sos:
+        depth_names = get_images(depth_filename_template, indices_list=img_indices, show_images=False, return_names_only=True)
+    if img_indices is None or len(img_indices) == 0:
+        img_indices = list(range(len(image_names)))
+    tracker = tracker_class(camera_model=camera_model, show_3D_points=False, save_correspondence_images=False,
+                            results_path=results_path)
+    if gt_poses_filename is None:
+        gt_T = {idx: np.identity(4) for idx in img_indices}                    # pose_est_tools.py:1332-1352
+    else:
+        _, mats = get_poses_from_file(poses_filename=gt_poses_filename, input_units="m", output_working_units="m", indices=[],
+                                      pose_format="tum", zero_up_wrt_origin=True)
+        gt_T = {idx: mats[idx] for idx in img_indices if idx < len(mats)}
+    est_file = open(join(results_path, est_poses_filename), "w")
+    gt_file = open(join(results_path, est_poses_filename.replace("estimated", "gt_associated")), "w")
+    key_file = open(join(results_path, "keyframe_ids.txt"), "w")
+    state = TrackingState(KeyframePolicy(), tracker.number_of_cams, 1.0)        # T_frame_wrt_tracking_ref_frame is in [m] already
+    reference_frame = None
+    for n, idx in enumerate(img_indices):
+        if is_sos:
+            omni = cv2.imread(image_names[n])
+            camera_model.set_current_omni_image(omni, generate_panoramas=False, view=False, apply_mask=True, mask_RGB=(0, 0, 0))
+            frame = StereoPanoramicFrame(stereo_camera_model=camera_model, frame_id=idx,
+                                         parent_id=state.keyframe_id if state.keyframe_id is not None else idx)
+        else:
+            rgb = cv2.cvtColor(cv2.imread(image_names[n]), cv2.COLOR_BGR2RGB)
+            depth = get_depthmap_float32_from_png(depth_img_filename=depth_names[n], conversion_factor=camera_model.scaling_factor)
+            frame = RGBDFrame(camera_model, rgb, depth, idx)
+        if n == 0:
+            state.first_frame(idx, frame.num_valid_keypoints)
+            became_key = True
+        else:
+            ok, msg = tracker.track_frame(reference_frame=reference_frame, current_frame=frame)
+            if not ok:                                                          # pose_est_tools.py:1493-1497
+                print(msg, file=log)
+                print("%sWarning failed: %s" % (prefix, msg))
+                state.result.status = msg
+                break
+            T = frame.T_frame_wrt_tracking_ref_frame
+            became_key = state.tracked_frame(idx, T[:3], tracker.num_tracked_correspondences, frame.num_valid_keypoints)
+        if became_key:                                                          # pose_est_tools.py:1551-1566
+            reference_frame = keyframe_class(frame=frame)
+            tracker.T_Ckey_wrt_S_est_list.append(state.T_key_wrt_S[-1].copy())
+            print(idx, file=key_file)
+        T_est = state.T_curr_wrt_S
+        print(tum_line(idx, T_est), file=est_file)                              # pose_est_tools.py:1609-1612
+        T_gt = gt_T.get(idx, np.full((4, 4), np.nan))
+        print(tum_line(idx, T_gt) if not np.any(np.isnan(T_gt)) else " ".join([str(idx)] + 7 * ["nan"]), file=gt_file)
+        done = "%sDONE with F[%d] (Parent K[%d])" % (prefix, idx, state.result.parent_ids[-1])
+        print(done, file=log)
+    msg = "%sVO done with %d keyframes" % (prefix, len(state.result.keyframe_ids))
+    print(msg)
+    print(msg, file=log)
+    for f in (est_file, gt_file, key_file, log):
+        f.close()
+    return state.result
+
+
+def driver_VO(camera_model, scene_path, scene_path_vo_results, scene_img_filename_template, depth_filename_template,
+              num_scene_images, visualize_VO=False, use_multithreads_for_VO=True, step_for_scene_images=1, first_image_index=0,
+              last_image_index=-1, thread_name=""):
+    """pose_est_tools.py:1680-1741.  Visualisation is not available here: visualize_VO=True only prints a notice and the VO
+    runs headless; with use_multithreads_for_VO the loop runs on its own thread like the reference's."""
+    import os
+    import threading
+    from datetime import datetime
+    if use_multithreads_for_VO:
+        est_poses_filename = "estimated_frame_poses_TUM.txt"
+    else:
+        now = datetime.now()
+        est_poses_filename = "estimated_frame_poses_TUM-%d-%d-%d-%d-%d-%d.txt" % (now.year, now.month, now.day, now.hour, now.minute,
+                                                                                 now.second)
+    static = any(k in scene_path.lower() for k in ("static", "park", "grand")) or "GCT" in scene_path.upper() or "CCNY" in scene_path.upper()
+    gt_poses_filename = None if static else os.path.join(scene_path, "gt_TUM.txt")
+    if gt_poses_filename is not None and not os.path.exists(gt_poses_filename):
+        gt_poses_filename = None   # the reference would stop here; a sequence without ground truth still runs
+    last = min(last_image_index, num_scene_images) if last_image_index > 0 else num_scene_images
+    indices = list(range(first_image_index, last, step_for_scene_images))
+    if visualize_VO:
+        print("%s: 3D visualisation is not part of this build, running headless" % thread_name)
+    kwargs = dict(visualizer_3D_VO=None, camera_model=camera_model, gt_poses_filename=gt_poses_filename,
+                  est_poses_filename=est_poses_filename, img_filename_template=scene_img_filename_template,
+                  depth_filename_template=depth_filename_template, img_indices=indices, results_path=scene_path_vo_results,
+                  thread_name=thread_name)
+    if use_multithreads_for_VO:
+        t = threading.Thread(target=run_VO, kwargs=kwargs)
+        t.start()
+        t.join()
+    else:
+        run_VO(**kwargs)
+    print("%s Done with VO for %s!" % (thread_name, scene_path))
+    return "NOTHING"
