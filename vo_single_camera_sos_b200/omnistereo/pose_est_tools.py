@@ -343,6 +343,11 @@ def run_VO(visualizer_3D_VO, camera_model, gt_poses_filename=None, est_poses_fil
         _, mats = get_poses_from_file(poses_filename=gt_poses_filename, input_units="m", output_working_units="m", indices=[],
                                       pose_format="tum", zero_up_wrt_origin=True)
         gt_T = {idx: mats[idx] for idx in img_indices if idx < len(mats)}
+        hand_eye = getattr(camera_model, "T_Cest_wrt_Rgt", None)
+        if hand_eye is not None:                                                # pose_est_tools.py:1361-1368, 1466-1470
+            T_Rgt_wrt_S = tracker.T_C_wrt_S_init @ np.linalg.inv(np.asarray(hand_eye, float))
+            T_S_wrt_Rgt = np.linalg.inv(T_Rgt_wrt_S)
+            gt_T = {k: T_Rgt_wrt_S @ v @ T_S_wrt_Rgt for k, v in gt_T.items()}
     est_file = open(join(results_path, est_poses_filename), "w")
     gt_file = open(join(results_path, est_poses_filename.replace("estimated", "gt_associated")), "w")
     key_file = open(join(results_path, "keyframe_ids.txt"), "w")

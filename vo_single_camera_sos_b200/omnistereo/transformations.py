@@ -33,3 +33,41 @@ def concatenate_matrices(*matrices):
 
 def identity_matrix():
     return np.identity(4)
+
+
+def inverse_matrix(matrix):
+    return np.linalg.inv(matrix)
+
+
+def rotation_matrix(angle, direction, point=None):
+    """4 x 4 rotation by `angle` [rad] about the axis `direction` (through `point`), transformations.py:297-338 (Rodrigues)."""
+    d = np.asarray(direction, np.float64)[:3]
+    d = d / np.linalg.norm(d)
+    s, c = np.sin(angle), np.cos(angle)
+    K = np.array([[0.0, -d[2], d[1]], [d[2], 0.0, -d[0]], [-d[1], d[0], 0.0]])
+    M = np.identity(4)
+    M[:3, :3] = c * np.identity(3) + (1.0 - c) * np.outer(d, d) + s * K
+    if point is not None:
+        p = np.asarray(point, np.float64)[:3]
+        M[:3, 3] = p - M[:3, :3] @ p
+    return M
+
+
+def translation_from_matrix(matrix):
+    return np.array(matrix, copy=True)[:3, 3]
+
+
+def quaternion_from_matrix(matrix, isprecise=False):
+    """[w, x, y, z], w >= 0 (transformations.py:1258-1332, the isprecise=False branch for both settings)."""
+    from ..driver import quaternion_wxyz
+    return quaternion_wxyz(np.asarray(matrix, np.float64))
+
+
+def rpe_translation_metric(T):
+    from ..driver import translation_metric
+    return translation_metric(np.asarray(T))
+
+
+def rpe_rotation_metric(T):
+    from ..driver import rotation_metric
+    return rotation_metric(np.asarray(T))
