@@ -214,7 +214,7 @@ def run_reference(args, rank, world):
 def workload_config(args, c, batch, note=""):
     return {"workload": f"{args.workload}: {c['width']}x{c['height']} omni -> 2 x {c['pano_cols']}-wide panoramas, "
                         f"{c['feat']} ORB features/view in 12 azimuth buckets, {c['n_hyp']} RANSAC hypotheses, score={args.score}, "
-                        f"refine={args.refine}",
+                        f"refine={args.refine}" + (", solver=p3p" if getattr(args, "solver", "arun") == "p3p" else ""),
             "frames_per_step": batch, "note": note}
 
 
@@ -244,7 +244,8 @@ def run_gpu(args, rank, local_rank, world):
     B, K, W = args.batch, args.steps, args.warmup
     n_sets = 2
     score = ops.SCORE_BEARING if args.score == "bearing" else ops.SCORE_EUCLID
-    w = workload.build(ctx, args.workload, batch=B, n_frames=n_sets * B + 1, seed=rank, score_mode=score)
+    w = workload.build(ctx, args.workload, batch=B, n_frames=n_sets * B + 1, seed=rank, score_mode=score,
+                       solver=ops.SOLVER_P3P if args.solver == "p3p" else ops.SOLVER_ARUN)
     w.cfg.refit = {"none": ops.REFINE_NONE, "arun": ops.REFINE_ARUN, "lm": ops.REFINE_LM}[args.refine]
     c = workload.CONFIGS[args.workload]
     renderer = workload.DeviceRenderer(ctx, w)
@@ -462,6 +463,8 @@ def main():
     ap.add_argument("--score", default="bearing", choices=["bearing", "euclid"])
     ap.add_argument("--refine", default="arun", choices=["none", "arun", "lm"],
                     help="pose after RANSAC: Arun refit on the inliers, or Levenberg-Marquardt on the bearing residual")
+    ap.add_argument("--solver", default="arun", choices=["arun", "p3p"],
+                    help="RANSAC hypotheses: 3-point Arun on 3D-3D correspondences (north_star) or the bearing-only three-point solver")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)

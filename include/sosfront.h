@@ -249,6 +249,8 @@ int sos_rgbd_backproject(sos_ctx* ctx, const double* cam, const float* depth, in
  * Step 5 — batched RANSAC for rigid 3D-3D registration
  * ---------------------------------------------------------------------------------------------- */
 
+#define SOS_SOLVER_ARUN 0
+#define SOS_SOLVER_P3P 1
 #define SOS_SCORE_EUCLID 0  /* |p_ref - (R p_cur + t)| < thr */
 #define SOS_SCORE_BEARING 1 /* 1 - f . normalize(Rc^T (R^T (p_ref - t) - tc)) < thr  (pose_est_tools.py:150-203, 181-185) */
 
@@ -284,6 +286,21 @@ int sos_ransac_p3d(sos_ctx* ctx, const float* p_ref, const float* p_cur, const f
                    int n_hyp, int hyp_offset, int score_mode, double threshold, float* best_pose,
                    int32_t* best_hyp, int32_t* best_count, uint8_t* inlier_mask, uint64_t* best_key,
                    int32_t* all_counts);
+
+/* replaces: pyopengv.absolute_pose_noncentral_ransac(bearings, cam_idx, points, cam_offsets, cam_rotations, thr, iters)
+ * (pose_est_tools.py:785) and pyopengv.absolute_pose_ransac(bearings, points, algo, thr, iters) (pose_est_tools.py:915)
+ * WITH THE ARGUMENTS THE REFERENCE PASSES: bearings of the current frame and 3D points of the reference frame only.
+ * Same layout, scoring (bearing residual), first-maximum rule and outputs as sos_ransac_p3d, but
+ *   hyp [n_hyp,4] uint32: rows 0-2 are the minimal sample, row 3 picks among its solutions (OpenGV's sample size for its
+ *   three-point solvers); a hypothesis with a repeated row, a collinear triple or no solution scores negative.
+ * Minimal solver: depths along the three rays with |X_i - X_j| = |P_i - P_j| — Grunert's three-point problem for a common
+ * origin (quartic, closed form), then Newton on the three distance equations with each ray's own origin for a non-central
+ * rig (rig / cam as in sos_ransac_p3d; NULL = central) — and the pose of the two congruent triangles.  It solves the problem
+ * OpenGV's KNEIP / GP3P solvers solve, not by OpenGV's code (absent from the reference tree): parity with OpenGV unpinned. */
+int sos_ransac_p3p(sos_ctx* ctx, const float* p_ref, const float* f_cur, const uint8_t* cam, const int32_t* n,
+                   int n_problems, int cap, const double* rig, int n_cams, const uint32_t* hyp, int n_hyp,
+                   int hyp_offset, double threshold, float* best_pose, int32_t* best_hyp, int32_t* best_count,
+                   uint8_t* inlier_mask, uint64_t* best_key, int32_t* all_counts);
 
 /* Re-derive pose and inlier mask of hypothesis `hyp_index[b]` (DEVICE int32, GLOBAL index, i.e. the winner
  * of the cross-GPU reduce) without scoring the others. */
@@ -395,6 +412,8 @@ typedef struct sos_frontend_config {
   int32_t keyframe_mode;       /* 0: pair i = (slot i, slot i+1), the last frame is carried over automatically (throughput mode);
                                   1: pair i = (slot ref_slot[i], slot i+1) and slot 0 only changes through sos_frontend_promote —
                                      the reference's keyframe tracking (pose_est_tools.py:1489, 1553-1566), SURVEY §8f N2 */
+  int32_t solver;              /* SOS_SOLVER_ARUN: 3D-3D hypotheses, hyp [n_hyp,3] (sos_ransac_p3d);
+                                  SOS_SOLVER_P3P: bearing-only hypotheses, hyp [n_hyp,4], bearing score (sos_ransac_p3p) */
   double ransac_threshold;     /* 1 - cos(5 deg) for SOS_SCORE_BEARING (pose_est_tools.py:675-676) */
   double stereo_max_du, stereo_min_dv; /* 2.5, 1 (pose_est_tools.py:298-304) */
   double temporal_max_du;      /* 0.125 * 0.5 * cols (pose_est_tools.py:866) */

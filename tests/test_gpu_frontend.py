@@ -230,3 +230,35 @@ def test_frontend_lm_refinement_matches_minpack(ctx):
         assert np.allclose(buf["pose"][i][:, :3], T_rel[:3, :3], atol=0.05)
         assert np.allclose(buf["pose"][i][:, 3], T_rel[:3, 3], atol=0.15)
     fe.close()
+
+
+def test_frontend_bearing_only_solver_matches_oracle(ctx):
+    """solver = SOLVER_P3P inside the captured chain: RANSAC from the bearings of the current frame and the 3D points of the
+    reference frame only (what the reference hands to OpenGV, pose_est_tools.py:785) — winner, count and inlier set against
+    oracle/p3p.py on exactly the device's float32 correspondences."""
+    from oracle import p3p as op3p
+    from vo_single_camera_sos_b200 import ops, workload
+    B = 3
+    w = workload.build(ctx, "tiny", batch=B, n_frames=2 * B, seed=4, score_mode=ops.SCORE_BEARING, solver=ops.SOLVER_P3P)
+    w.cfg.refit = ops.REFINE_LM
+    fe = w.frontend(ctx)
+    rig = np.zeros((2, 3, 4)); rig[:, :, :3] = np.eye(3); rig[0, :, 3] = w.rig.f_top; rig[1, :, 3] = w.rig.f_bot
+    for step in range(2):
+        fr = workload.make_frames(w, step * B, B)
+        fe.step(*workload.to_device(ctx, fr))
+        torch.cuda.synchronize()
+        buf = host(fe.buffers())
+        for i in range(B):
+            m = int(buf["n_corr"][i])
+            if step == 0 and i == 0:
+                continue                                                  # no reference frame yet
+            M, h, c, inl, _ = op3p.ransac_p3p(buf["p_ref"][i, :m], buf["f_cur"][i, :m], buf["cam"][i, :m], rig, w.hyp_host,
+                                              w.cfg.ransac_threshold)
+            assert buf["best_hyp"][i] == h and buf["best_count"][i] == c and c > 0.5 * m
+            np.testing.assert_array_equal(buf["inlier_mask"][i, :m].astype(bool), inl)
+            np.testing.assert_allclose(buf["ransac_pose"][i], M, atol=2e-6)
+    for i in range(B):
+        T_rel = np.linalg.inv(w.trajectory[B + i - 1]) @ w.trajectory[B + i]
+        assert np.allclose(buf["pose"][i][:, :3], T_rel[:3, :3], atol=0.05)
+        assert np.allclose(buf["pose"][i][:, 3], T_rel[:3, 3], atol=0.15)
+    fe.close()

@@ -303,9 +303,12 @@ int enqueue_stage_b(sos_frontend* fe) {
                                               d.b_bot, d.p_ref, d.p_cur, d.f_cur, d.cam, d.n_corr, d.n_corr_top);
   SOS_LAUNCHED(ctx);
   // step 5
-  rc = sos_ransac_p3d(ctx, d.p_ref, d.p_cur, d.f_cur, d.cam, d.n_corr, B, 2 * cap, c.rig, 2, fe->hyp, c.n_hyp, 0,
-                      c.score_mode, c.ransac_threshold, d.ransac_pose, d.best_hyp, d.best_count, d.inlier_mask, nullptr,
-                      nullptr);
+  rc = c.solver == SOS_SOLVER_P3P
+           ? sos_ransac_p3p(ctx, d.p_ref, d.f_cur, d.cam, d.n_corr, B, 2 * cap, c.rig, 2, fe->hyp, c.n_hyp, 0, c.ransac_threshold,
+                            d.ransac_pose, d.best_hyp, d.best_count, d.inlier_mask, nullptr, nullptr)
+           : sos_ransac_p3d(ctx, d.p_ref, d.p_cur, d.f_cur, d.cam, d.n_corr, B, 2 * cap, c.rig, 2, fe->hyp, c.n_hyp, 0,
+                            c.score_mode, c.ransac_threshold, d.ransac_pose, d.best_hyp, d.best_count, d.inlier_mask, nullptr,
+                            nullptr);
   if (rc) return rc;
   if (c.refit == SOS_REFINE_LM) {
     rc = sos_refine_pose(ctx, d.p_ref, d.f_cur, d.cam, d.inlier_mask, d.n_corr, B, 2 * cap, c.rig, 2, d.ransac_pose,
@@ -399,6 +402,8 @@ extern "C" int sos_frontend_create(sos_ctx* ctx, const sos_frontend_config* cfg,
   SOS_CHECK_ARG(cfg->channels == 1 || cfg->channels == 3 || cfg->channels == 4, "channels must be 1, 3 or 4");
   SOS_CHECK_ARG(cfg->n_buckets > 0 && cfg->max_feat_per_view > 0 && cfg->max_feat_per_bucket > 0 && cfg->cap > 0, "bad capacity");
   SOS_CHECK_ARG(cfg->n_hyp >= 0, "negative n_hyp");
+  SOS_CHECK_ARG(cfg->solver == SOS_SOLVER_ARUN || cfg->solver == SOS_SOLVER_P3P, "unknown solver");
+  SOS_CHECK_ARG(cfg->solver != SOS_SOLVER_P3P || cfg->score_mode == SOS_SCORE_BEARING, "the bearing-only solver scores bearings");
   SOS_CUDA(cudaSetDevice(ctx->device));
   sos_frontend* fe = new sos_frontend();
   // private context: same device and stream, but its own scratch arena — the arena address is baked into the captured

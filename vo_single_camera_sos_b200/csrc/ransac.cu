@@ -236,6 +236,304 @@ hypothesize_kernel(const float* __restrict__ p_ref, const float* __restrict__ p_
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Bearing-only hypotheses (what the reference hands to OpenGV, pose_est_tools.py:785, 915: bearings of the current frame and
+// 3D points of the reference frame only).  Four sampled rows: three for the minimal problem, the fourth picks among its
+// solutions (OpenGV's sample size for its three-point solvers).  Depths along the three rays from Grunert's three-point
+// problem (common origin: quartic in v = s3/s1, solved by Ferrari's closed form and polished), then Newton on the three
+// distance equations with every ray's own origin (non-central rig), pose from the two congruent triangles.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int P3P_NEWTON_ITERS = 8;
+
+__device__ __forceinline__ double poly4(const double* c, double x) { return (((c[4] * x + c[3]) * x + c[2]) * x + c[1]) * x + c[0]; }
+__device__ __forceinline__ double dpoly4(const double* c, double x) { return ((4.0 * c[4] * x + 3.0 * c[3]) * x + 2.0 * c[2]) * x + c[1]; }
+
+// largest real root of m^3 + A m^2 + B m + C
+__device__ double cubic_largest_root(double A, double B, double C) {
+  const double P = B - A * A / 3.0, Q = 2.0 * A * A * A / 27.0 - A * B / 3.0 + C;
+  const double disc = 0.25 * Q * Q + P * P * P / 27.0;
+  double z;
+  if (disc > 0.0) {
+    const double sd = sqrt(disc);
+    z = cbrt(-0.5 * Q + sd) + cbrt(-0.5 * Q - sd);
+  } else if (P < 0.0) {
+    const double k = sqrt(-P / 3.0);
+    double arg = -0.5 * Q / (k * k * k);
+    arg = fmin(1.0, fmax(-1.0, arg));
+    z = 2.0 * k * cos(acos(arg) / 3.0);
+  } else {
+    z = 0.0;
+  }
+  double m = z - A / 3.0;
+  for (int it = 0; it < 2; ++it) {
+    const double f = ((m + A) * m + B) * m + C, df = (3.0 * m + 2.0 * A) * m + B;
+    if (df != 0.0) m -= f / df;
+  }
+  return m;
+}
+
+// real roots of c[4] x^4 + ... + c[0] (c[4] != 0), each polished on the quartic itself; returns their number
+__device__ int quartic_real_roots(const double* c, double* x) {
+  const double a = c[3] / c[4], b = c[2] / c[4], cc = c[1] / c[4], d = c[0] / c[4];
+  const double a2 = a * a;
+  const double p = b - 0.375 * a2;
+  const double q = cc - 0.5 * a * b + 0.125 * a2 * a;
+  const double r = d - 0.25 * a * cc + 0.0625 * a2 * b - (3.0 / 256.0) * a2 * a2;
+  double y[4];
+  int n = 0;
+  const double m = cubic_largest_root(p, 0.25 * p * p - r, -0.125 * q * q);
+  const double tiny = 1e-13 * fmax(1.0, fmax(fabs(p), sqrt(fabs(r))));
+  if (m > tiny) {
+    // y^4 + p y^2 + q y + r = (y^2 - s y + p/2 + m + q/(2s)) (y^2 + s y + p/2 + m - q/(2s)),  s = sqrt(2m)
+    const double s = sqrt(2.0 * m), h = 0.5 * p + m, g = q / (2.0 * s);
+#pragma unroll
+    for (int sign = 0; sign < 2; ++sign) {
+      const double lin = sign ? s : -s, con = sign ? h - g : h + g;
+      double disc = lin * lin - 4.0 * con;
+      if (disc < 0.0 && disc > -1e-12 * fmax(1.0, fmax(lin * lin, fabs(con)))) disc = 0.0;
+      if (disc >= 0.0) {
+        const double sd = sqrt(disc);
+        y[n++] = 0.5 * (-lin + sd);
+        y[n++] = 0.5 * (-lin - sd);
+      }
+    }
+  } else {
+    // biquadratic: y^2 = (-p +- sqrt(p^2 - 4r)) / 2
+    double disc = p * p - 4.0 * r;
+    if (disc < 0.0 && disc > -1e-12 * fmax(1.0, p * p)) disc = 0.0;
+    if (disc >= 0.0) {
+      const double sd = sqrt(disc);
+#pragma unroll
+      for (int sign = 0; sign < 2; ++sign) {
+        const double y2 = 0.5 * (-p + (sign ? -sd : sd));
+        if (y2 >= 0.0) {
+          y[n++] = sqrt(y2);
+          y[n++] = -sqrt(y2);
+        }
+      }
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    double v = y[i] - 0.25 * a;
+    for (int it = 0; it < 2; ++it) {
+      const double df = dpoly4(c, v);
+      if (df != 0.0) v -= poly4(c, v) / df;
+    }
+    x[i] = v;
+  }
+  return n;
+}
+
+__device__ __forceinline__ void cross3(const double* a, const double* b, double* o) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// orthonormal frame (columns e1, e2, e3 stored as rows of F) on the first two edges of a triangle T [3][3]
+__device__ __forceinline__ void triangle_frame(const double* T, double* F) {
+  double e1[3] = {T[3] - T[0], T[4] - T[1], T[5] - T[2]}, w[3] = {T[6] - T[0], T[7] - T[1], T[8] - T[2]}, e3[3], e2[3];
+  const double n1 = 1.0 / sqrt(dot3(e1, e1));
+  e1[0] *= n1; e1[1] *= n1; e1[2] *= n1;
+  cross3(e1, w, e3);
+  const double n3 = 1.0 / sqrt(dot3(e3, e3));
+  e3[0] *= n3; e3[1] *= n3; e3[2] *= n3;
+  cross3(e3, e1, e2);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    F[d] = e1[d];
+    F[3 + d] = e2[d];
+    F[6 + d] = e3[d];
+  }
+}
+
+__global__ void __launch_bounds__(128)
+hypothesize_p3p_kernel(const float* __restrict__ p_ref, const float* __restrict__ f_cur, const uint8_t* __restrict__ cam,
+                       const int32_t* __restrict__ n_arr, int cap, const uint32_t* __restrict__ hyp, int hyp_stride_problem,
+                       int n_hyp, Rig rig, HypRec* __restrict__ recs, int32_t* __restrict__ counts) {
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (h >= n_hyp) return;
+  const int n = n_arr[b];
+  const uint32_t* hr = hyp + (size_t)b * hyp_stride_problem + (size_t)h * 4;
+  bool ok = n >= 4;
+  int rows[4] = {0, 0, 0, 0};
+  if (ok) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rows[j] = (int)(((uint64_t)hr[j] * (uint64_t)n) >> 32);
+    ok = rows[0] != rows[1] && rows[0] != rows[2] && rows[1] != rows[2] && rows[3] != rows[0] && rows[3] != rows[1] &&
+         rows[3] != rows[2];
+  }
+  double P[12], dir[9], org[9], f4[3];
+  int cam4 = 0;
+  if (ok) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const size_t o = ((size_t)b * cap + rows[j]);
+      const int c = cam ? min((int)cam[o], rig.n_cams - 1) : 0;
+      const double f[3] = {(double)f_cur[o * 3], (double)f_cur[o * 3 + 1], (double)f_cur[o * 3 + 2]};
+#pragma unroll
+      for (int d = 0; d < 3; ++d) P[3 * j + d] = (double)p_ref[o * 3 + d];
+      if (j < 3) {
+        const double* C = rig.Rt[c];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          dir[3 * j + d] = C[4 * d] * f[0] + C[4 * d + 1] * f[1] + C[4 * d + 2] * f[2];
+          org[3 * j + d] = C[4 * d + 3];
+        }
+      } else {
+        cam4 = c;
+        f4[0] = f[0]; f4[1] = f[1]; f4[2] = f[2];
+      }
+    }
+    ok = !triangle_degenerate(P);
+  }
+  double best_M[12];
+  double best_res = CUDART_INF;
+  if (ok) {
+    double e[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) e[d] = P[3 + d] - P[6 + d];
+    const double a2 = dot3(e, e);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) e[d] = P[d] - P[6 + d];
+    const double b2 = dot3(e, e);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) e[d] = P[d] - P[3 + d];
+    const double c2 = dot3(e, e);
+    const double ca = dot3(dir + 3, dir + 6), cb = dot3(dir, dir + 6), cg = dot3(dir, dir + 3);
+    const double ra = a2 / b2, rc = c2 / b2;
+    // u = s2/s1 = N(v) / (2 D(v));  N^2 - 4 cg N D + 4 Q D^2 = 0   (lowest power first)
+    const double N[3] = {rc - ra - 1.0, 2.0 * (ra - rc) * cb, 1.0 - ra + rc};
+    const double D[2] = {-cg, ca};
+    const double Q[3] = {1.0 - rc, 2.0 * rc * cb, -rc};
+    const double DD[3] = {D[0] * D[0], 2.0 * D[0] * D[1], D[1] * D[1]};
+    double qc[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) qc[i + j] += N[i] * N[j] + 4.0 * Q[i] * DD[j];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) qc[i + j] -= 4.0 * cg * N[i] * D[j];
+    double scale = 0.0;
+    bool finite = true;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      scale = fmax(scale, fabs(qc[i]));
+      finite = finite && isfinite(qc[i]);
+    }
+    double vr[4];
+    const int nr = (finite && fabs(qc[4]) >= 1e-300) ? quartic_real_roots(qc, vr) : 0;
+    double om[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) om[d] = (org[d] + org[3 + d] + org[6 + d]) / 3.0;
+    for (int k = 0; k < nr; ++k) {
+      const double v = vr[k];
+      if (!(v > 0.0) || fabs(poly4(qc, v)) > 1e-6 * scale * fmax(1.0, v * v * v * v)) continue;
+      const double den = 2.0 * (D[1] * v + D[0]);
+      if (fabs(den) < 1e-12) continue;
+      const double u = ((N[2] * v + N[1]) * v + N[0]) / den;
+      const double w = 1.0 + v * v - 2.0 * v * cb;
+      if (!(u > 0.0) || !(w > 0.0)) continue;
+      const double s1 = sqrt(b2 / w);
+      double lam[3] = {s1, u * s1, v * s1};
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double off[3] = {org[3 * i] - om[0], org[3 * i + 1] - om[1], org[3 * i + 2] - om[2]};
+        lam[i] -= dot3(dir + 3 * i, off);
+      }
+      // Newton on g = (|X1-X2|^2 - c2, |X1-X3|^2 - b2, |X2-X3|^2 - a2),  X_i = o_i + lam_i d_i
+      double X[9];
+      bool good = true;
+      for (int it = 0; it <= P3P_NEWTON_ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int d = 0; d < 3; ++d) X[3 * i + d] = org[3 * i + d] + lam[i] * dir[3 * i + d];
+        double e12[3], e13[3], e23[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          e12[d] = X[d] - X[3 + d];
+          e13[d] = X[d] - X[6 + d];
+          e23[d] = X[3 + d] - X[6 + d];
+        }
+        const double g0 = dot3(e12, e12) - c2, g1 = dot3(e13, e13) - b2, g2 = dot3(e23, e23) - a2;
+        if (it == P3P_NEWTON_ITERS) {
+          good = lam[0] > 0.0 && lam[1] > 0.0 && lam[2] > 0.0 &&
+                 fmax(fabs(g0), fmax(fabs(g1), fabs(g2))) < 1e-9 * fmax(a2, fmax(b2, c2));
+          break;
+        }
+        // J = 2 [[j00, j01, 0], [j10, 0, j12], [0, j21, j22]]
+        const double j00 = 2.0 * dot3(e12, dir), j01 = -2.0 * dot3(e12, dir + 3);
+        const double j10 = 2.0 * dot3(e13, dir), j12 = -2.0 * dot3(e13, dir + 6);
+        const double j21 = 2.0 * dot3(e23, dir + 3), j22 = -2.0 * dot3(e23, dir + 6);
+        const double det = -j00 * j12 * j21 - j01 * j10 * j22;
+        if (!isfinite(det) || fabs(det) < 1e-300) {
+          good = false;
+          break;
+        }
+        // Cramer
+        const double d0 = g0 * (-j12 * j21) - j01 * (g1 * j22 - j12 * g2);
+        const double d1 = j00 * (g1 * j22 - j12 * g2) - g0 * (j10 * j22);
+        const double d2 = j00 * (-j21 * g1) - j01 * (j10 * g2) + g0 * (j10 * j21);
+        lam[0] -= d0 / det;
+        lam[1] -= d1 / det;
+        lam[2] -= d2 / det;
+      }
+      if (!good) continue;
+      // pose: P_i = R X_i + t
+      double Fp[9], Fx[9], M[12];
+      triangle_frame(P, Fp);
+      triangle_frame(X, Fx);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) M[4 * i + j] = Fp[i] * Fx[j] + Fp[3 + i] * Fx[3 + j] + Fp[6 + i] * Fx[6 + j];
+      double mp[3], mx[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        mp[d] = (P[d] + P[3 + d] + P[6 + d]) / 3.0;
+        mx[d] = (X[d] + X[3 + d] + X[6 + d]) / 3.0;
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) M[4 * i + 3] = mp[i] - (M[4 * i] * mx[0] + M[4 * i + 1] * mx[1] + M[4 * i + 2] * mx[2]);
+      // bearing residual of the fourth correspondence
+      const double dp[3] = {P[9] - M[3], P[10] - M[7], P[11] - M[11]};
+      const double* C = rig.Rt[cam4];
+      double yb[3], xc[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) yb[i] = M[i] * dp[0] + M[4 + i] * dp[1] + M[8 + i] * dp[2] - C[4 * i + 3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) xc[i] = C[i] * yb[0] + C[4 + i] * yb[1] + C[8 + i] * yb[2];
+      const double res = 1.0 - dot3(f4, xc) / sqrt(dot3(xc, xc));
+      if (res < best_res) {
+        best_res = res;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) best_M[i] = M[i];
+      }
+    }
+    ok = best_res < CUDART_INF;
+  }
+  HypRec rec;
+  if (ok) {
+    make_scoring_transforms(best_M, rig, rec);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      rec.pose[i] = CUDART_NAN_F;
+      rec.pose64[i] = CUDART_NAN;
+    }
+    for (int c = 0; c < RS_MAX_CAMS; ++c)
+#pragma unroll
+      for (int i = 0; i < 12; ++i) rec.xf[c][i] = CUDART_NAN_F;
+  }
+  recs[(size_t)b * n_hyp + h] = rec;
+  counts[(size_t)b * n_hyp + h] = ok ? 0 : -(1 << 30);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // The inlier test.
 //
 // Fast path: float32 FMAs on the per-hypothesis transform.  It also produces a rigorous bound `guard` on its own
@@ -765,7 +1063,9 @@ extern "C" int sos_arun_batch(sos_ctx* ctx, const double* v0, const double* v1, 
   return SOS_OK;
 }
 
-extern "C" int sos_ransac_p3d(sos_ctx* ctx, const float* p_ref, const float* p_cur, const float* f_cur,
+namespace {
+// solver 0: 3D-3D Arun hypotheses (3 sample numbers per hypothesis); solver 1: bearing-only three-point hypotheses (4 numbers)
+int ransac_run(sos_ctx* ctx, int solver, const float* p_ref, const float* p_cur, const float* f_cur,
                               const uint8_t* cam, const int32_t* n, int n_problems, int cap, const double* rig,
                               int n_cams, const uint32_t* hyp, int n_hyp, int hyp_offset, int score_mode,
                               double threshold, float* best_pose, int32_t* best_hyp, int32_t* best_count,
@@ -776,7 +1076,7 @@ extern "C" int sos_ransac_p3d(sos_ctx* ctx, const float* p_ref, const float* p_c
   SOS_CHECK_ARG(n_cams >= 0 && n_cams <= RS_MAX_CAMS, "at most 2 cameras in the rig");
   SOS_CHECK_ARG(n_problems <= 65535, "at most 65535 problems per call");
   if (n_problems == 0) return SOS_OK;
-  SOS_CHECK_ARG(p_ref && p_cur && n && best_pose && best_hyp && best_count, "NULL array");
+  SOS_CHECK_ARG(p_ref && (p_cur || solver == 1) && n && best_pose && best_hyp && best_count, "NULL array");
   SOS_CHECK_ARG(n_hyp == 0 || hyp, "hyp is NULL");
   SOS_CHECK_ARG(score_mode != SOS_SCORE_BEARING || f_cur, "bearing score needs f_cur");
   SOS_CHECK_ARG(score_mode != SOS_SCORE_BEARING || (threshold > 0.0 && threshold < 1.0), "bearing threshold must be in (0,1)");
@@ -790,7 +1090,10 @@ extern "C" int sos_ransac_p3d(sos_ctx* ctx, const float* p_ref, const float* p_c
   if (rc != SOS_OK) return rc;
   if (n_hyp > 0) {
     dim3 hgrid(sos_div_up(n_hyp, 128), n_problems);
-    hypothesize_kernel<<<hgrid, 128, 0, ctx->stream>>>(p_ref, p_cur, n, cap, hyp, 0, n_hyp, r, s.recs, s.counts);
+    if (solver == 1)
+      hypothesize_p3p_kernel<<<hgrid, 128, 0, ctx->stream>>>(p_ref, f_cur, cam, n, cap, hyp, 0, n_hyp, r, s.recs, s.counts);
+    else
+      hypothesize_kernel<<<hgrid, 128, 0, ctx->stream>>>(p_ref, p_cur, n, cap, hyp, 0, n_hyp, r, s.recs, s.counts);
     SOS_LAUNCHED(ctx);
     if (cap > 0) {
       dim3 sgrid(sos_div_up(n_hyp, RS_TILE_H), sos_div_up(cap, RS_CHUNK), n_problems);
@@ -814,6 +1117,25 @@ extern "C" int sos_ransac_p3d(sos_ctx* ctx, const float* p_ref, const float* p_c
     SOS_LAUNCHED(ctx);
   }
   return SOS_OK;
+}
+}  // namespace
+
+extern "C" int sos_ransac_p3d(sos_ctx* ctx, const float* p_ref, const float* p_cur, const float* f_cur,
+                              const uint8_t* cam, const int32_t* n, int n_problems, int cap, const double* rig,
+                              int n_cams, const uint32_t* hyp, int n_hyp, int hyp_offset, int score_mode,
+                              double threshold, float* best_pose, int32_t* best_hyp, int32_t* best_count,
+                              uint8_t* inlier_mask, uint64_t* best_key, int32_t* all_counts) {
+  return ransac_run(ctx, 0, p_ref, p_cur, f_cur, cam, n, n_problems, cap, rig, n_cams, hyp, n_hyp, hyp_offset, score_mode,
+                    threshold, best_pose, best_hyp, best_count, inlier_mask, best_key, all_counts);
+}
+
+extern "C" int sos_ransac_p3p(sos_ctx* ctx, const float* p_ref, const float* f_cur, const uint8_t* cam, const int32_t* n,
+                              int n_problems, int cap, const double* rig, int n_cams, const uint32_t* hyp, int n_hyp,
+                              int hyp_offset, double threshold, float* best_pose, int32_t* best_hyp, int32_t* best_count,
+                              uint8_t* inlier_mask, uint64_t* best_key, int32_t* all_counts) {
+  SOS_CHECK_ARG(f_cur || n_problems == 0, "f_cur is NULL");
+  return ransac_run(ctx, 1, p_ref, nullptr, f_cur, cam, n, n_problems, cap, rig, n_cams, hyp, n_hyp, hyp_offset,
+                    SOS_SCORE_BEARING, threshold, best_pose, best_hyp, best_count, inlier_mask, best_key, all_counts);
 }
 
 extern "C" int sos_ransac_p3d_eval(sos_ctx* ctx, const float* p_ref, const float* p_cur, const float* f_cur,

@@ -23,7 +23,7 @@ class _Config(C.Structure):
         ("pano_rows", C.c_int32), ("pano_cols", C.c_int32), ("n_buckets", C.c_int32),
         ("max_feat_per_view", C.c_int32), ("max_feat_per_bucket", C.c_int32), ("cap", C.c_int32),
         ("n_hyp", C.c_int32), ("score_mode", C.c_int32), ("homogeneous_norm", C.c_int32), ("refit", C.c_int32),
-        ("refine_iters", C.c_int32), ("keyframe_mode", C.c_int32),
+        ("refine_iters", C.c_int32), ("keyframe_mode", C.c_int32), ("solver", C.c_int32),
         ("ransac_threshold", C.c_double), ("stereo_max_du", C.c_double), ("stereo_min_dv", C.c_double),
         ("temporal_max_du", C.c_double), ("min_range", C.c_double), ("max_range", C.c_double),
         ("pano_top", C.c_double * 6), ("pano_bot", C.c_double * 6), ("f_top", C.c_double * 3), ("f_bot", C.c_double * 3),
@@ -73,6 +73,7 @@ class FrontendConfig:
     refit: int = 1                    # ops.REFINE_NONE / REFINE_ARUN / REFINE_LM (True == REFINE_ARUN)
     refine_iters: int = 0             # REFINE_LM: maximum cost evaluations (0 -> 20)
     keyframe_mode: bool = False       # track against reference slots (set_ref_slots / promote / retrack)
+    solver: int = 0                   # ops.SOLVER_ARUN (hyp [n_hyp,3]) / ops.SOLVER_P3P (bearing-only, hyp [n_hyp,4])
     stereo_max_du: float = 2.5
     stereo_min_dv: float = 1.0
     temporal_max_du: Optional[float] = None   # None -> 0.125 * 0.5 * pano_cols
@@ -91,6 +92,7 @@ class FrontendConfig:
         c.refit = int(self.refit)
         c.refine_iters = int(self.refine_iters)
         c.keyframe_mode = int(bool(self.keyframe_mode))
+        c.solver = int(self.solver)
         c.ransac_threshold = float(self.ransac_threshold)
         c.stereo_max_du, c.stereo_min_dv = float(self.stereo_max_du), float(self.stereo_min_dv)
         c.temporal_max_du = float(0.125 * 0.5 * self.pano_cols if self.temporal_max_du is None else self.temporal_max_du)
@@ -127,13 +129,13 @@ _TYPES = {"u8": ("|u1", torch.uint8), "i32": ("<i4", torch.int32), "f32": ("<f4"
 
 class Frontend:
     def __init__(self, ctx: ops.Context, cfg: FrontendConfig, lut: torch.Tensor, hyp: torch.Tensor):
-        """lut [2, rows, cols] int64 (packed LUT of the top and bottom view); hyp [n_hyp, 3] int32 (uint32 bits)."""
+        """lut [2, rows, cols] int64 (packed LUT of the top and bottom view); hyp [n_hyp, 3] int32 (uint32 bits; [n_hyp, 4] for SOLVER_P3P)."""
         self.ctx, self.cfg = ctx, cfg
         ctx._sync_stream()
         if tuple(lut.shape) != (2, cfg.pano_rows, cfg.pano_cols):
             raise ValueError("lut must be [2, pano_rows, pano_cols]")
-        if hyp.shape[0] != cfg.n_hyp:
-            raise ValueError("hyp must have n_hyp rows")
+        if hyp.shape[0] != cfg.n_hyp or hyp.shape[1] != (4 if cfg.solver == ops.SOLVER_P3P else 3):
+            raise ValueError("hyp must be [n_hyp, 3] (SOLVER_ARUN) or [n_hyp, 4] (SOLVER_P3P)")
         self._lut, self._hyp = lut, hyp  # keep alive
         self._c = cfg.to_c()
         h = C.c_void_p()

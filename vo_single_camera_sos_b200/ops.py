@@ -18,6 +18,7 @@ from ._lib import SosError, check  # noqa: F401  (re-exported)
 
 MATCH_NN, MATCH_RATIO, MATCH_CROSS = 0, 1, 2
 SCORE_EUCLID, SCORE_BEARING = 0, 1
+SOLVER_ARUN, SOLVER_P3P = 0, 1
 REFINE_NONE, REFINE_ARUN, REFINE_LM = 0, 1, 2
 
 GUM_FIELDS = ("xi1", "xi2", "xi3", "k1", "k2", "k3", "gamma1", "gamma2", "alpha_c", "u_center", "v_center",
@@ -479,6 +480,27 @@ class Context:
             self._t(n, torch.int32, "n"), B, cap, _ptr(r), n_cams, self._t(hyp, torch.int32, "hyp"), H, int(hyp_offset),
             int(score_mode), float(threshold), pose.data_ptr(), best_hyp.data_ptr(), best_count.data_ptr(),
             mask.data_ptr() if want_mask else None, key.data_ptr(),
+            self._t(all_counts, torch.int32, "all_counts", optional=True)))
+        return pose, best_hyp, best_count, mask, key
+
+    def ransac_p3p(self, p_ref, f_cur, n, hyp, threshold: float, cam=None, rig=None, n_cams: int = 0, hyp_offset: int = 0,
+                   want_mask: bool = True, all_counts=None):
+        """Bearing-only RANSAC (sos_ransac_p3p): p_ref, f_cur [B, cap, 3] float32; hyp [H,4] uint32 bits."""
+        self._sync_stream()
+        B, cap, _ = p_ref.shape
+        H = hyp.shape[0]
+        assert hyp.shape[1] == 4, "four sample numbers per hypothesis"
+        r, n_cams = self._rig(rig, n_cams)
+        pose = self.empty((B, 3, 4), torch.float32)
+        best_hyp = self.empty((B,), torch.int32)
+        best_count = self.empty((B,), torch.int32)
+        mask = self.empty((B, cap), torch.uint8) if want_mask else None
+        key = self.empty((B,), torch.int64)
+        check(self.lib.sos_ransac_p3p(
+            self._h, self._t(p_ref, torch.float32, "p_ref"), self._t(f_cur, torch.float32, "f_cur"),
+            self._t(cam, torch.uint8, "cam", optional=True), self._t(n, torch.int32, "n"), B, cap, _ptr(r), n_cams,
+            self._t(hyp, torch.int32, "hyp"), H, int(hyp_offset), float(threshold), pose.data_ptr(), best_hyp.data_ptr(),
+            best_count.data_ptr(), mask.data_ptr() if want_mask else None, key.data_ptr(),
             self._t(all_counts, torch.int32, "all_counts", optional=True)))
         return pose, best_hyp, best_count, mask, key
 

@@ -4,10 +4,14 @@ The reference imports seven names from `pyopengv` (pose_est_tools.py:42,78,647-6
 installed and its outputs are pinned by no test of the reference, so parity with OpenGV itself is UNPINNED; the
 semantics implemented here are the ones written down in include/sosfront.h:
 
-  * hypotheses: Arun / Kabsch rigid registration on 3 sampled 3D-3D correspondences (transformations.py:874-1030) drawn
-    from a seeded list, instead of OpenGV's GP3P / EPnP minimal solvers.  That needs the 3D points of the CURRENT frame,
-    which the reference has at the call site (pose_est_tools.py:753-756) but does not pass to OpenGV: pass them as
-    `points_cur=` (the mirrored trackers in omnistereo.pose_est_tools do).  Without them the call raises.
+  * hypotheses, with the arguments the reference passes (bearings of the current frame + 3D points of the reference frame):
+    a three-point absolute-pose solver on 3 + 1 sampled correspondences (sos_ransac_p3p: Grunert's quartic for a central
+    camera, Newton on the distance equations for the two-viewpoint rig, the 4th sample picks among the solutions) - the
+    problem OpenGV's KNEIP / GP3P solvers solve, by other code.  "EPNP" (the reference's central default, a 6-point fit
+    inside OpenGV's RANSAC) is served by the same minimal solver.
+  * hypotheses, when the caller also passes the 3D points of the current frame (`points_cur=`, which the mirrored trackers in
+    omnistereo.pose_est_tools do - the reference has them at the call site, pose_est_tools.py:753-756): Arun / Kabsch rigid
+    registration on 3 sampled 3D-3D correspondences (transformations.py:874-1030), what north_star asks for.
   * score: OpenGV's bearing-angle score 1 - f . reprojection, threshold and iteration budget as given.
   * first maximum wins; the inlier indices are returned ascending, as the caller assumes (pose_est_tools.py:787).
   * *_optimize_nonlinear: OpenGV's published algorithm — Levenberg-Marquardt on one residual 1 - f . reprojection per
@@ -32,9 +36,9 @@ def _dev(a, dtype=None):
     return t.cuda()
 
 
-def hypothesis_list(n_hyp: int, seed: int = _SEED) -> np.ndarray:
-    """The shared seeded hypothesis list: uint32 [n_hyp, 3]; sample j of hypothesis h is row floor(u * n / 2^32)."""
-    return np.random.default_rng(seed).integers(0, 2 ** 32, (int(n_hyp), 3), dtype=np.uint64).astype(np.uint32)
+def hypothesis_list(n_hyp: int, seed: int = _SEED, k: int = 3) -> np.ndarray:
+    """The shared seeded hypothesis list: uint32 [n_hyp, k]; sample j of hypothesis h is row floor(u * n / 2^32)."""
+    return np.random.default_rng(seed).integers(0, 2 ** 32, (int(n_hyp), int(k)), dtype=np.uint64).astype(np.uint32)
 
 
 def _rig(cam_offsets, cam_rotations):
@@ -46,20 +50,22 @@ def _rig(cam_offsets, cam_rotations):
 
 
 def _ransac(bearings, points, points_cur, threshold, max_iterations, cam=None, rig=None, n_cams=0, seed=_SEED):
-    if points_cur is None:
-        raise NotImplementedError(
-            "this pyopengv replacement hypothesises with 3D-3D Arun registration and needs the current frame's 3D points: "
-            "pass points_cur= (N x 3).  OpenGV's GP3P / EPnP minimal solvers are not re-implemented (see INTEGRATION.md)")
     b = np.asarray(bearings, np.float32)[:, :3]
     p = np.asarray(points, np.float32)[:, :3]
-    pc = np.asarray(points_cur, np.float32)[:, :3]
     n = len(p)
-    hyp = hypothesis_list(max_iterations, seed)
     ctx = _ctx()
-    pose, best_hyp, best_count, mask, _ = ctx.ransac_p3d(
-        _dev(p[None]), _dev(pc[None]), torch.tensor([n], dtype=torch.int32, device=ctx.device), _dev(hyp.view(np.int32)),
-        ops.SCORE_BEARING, float(threshold), f_cur=_dev(b[None]),
-        cam=None if cam is None else _dev(np.asarray(cam).reshape(-1).astype(np.uint8)[None]), rig=rig, n_cams=n_cams)
+    n_dev = torch.tensor([n], dtype=torch.int32, device=ctx.device)
+    cam_dev = None if cam is None else _dev(np.asarray(cam).reshape(-1).astype(np.uint8)[None])
+    if points_cur is None:
+        hyp = hypothesis_list(max_iterations, seed, 4)
+        pose, best_hyp, best_count, mask, _ = ctx.ransac_p3p(_dev(p[None]), _dev(b[None]), n_dev, _dev(hyp.view(np.int32)),
+                                                             float(threshold), cam=cam_dev, rig=rig, n_cams=n_cams)
+    else:
+        pc = np.asarray(points_cur, np.float32)[:, :3]
+        hyp = hypothesis_list(max_iterations, seed)
+        pose, best_hyp, best_count, mask, _ = ctx.ransac_p3d(
+            _dev(p[None]), _dev(pc[None]), n_dev, _dev(hyp.view(np.int32)), ops.SCORE_BEARING, float(threshold),
+            f_cur=_dev(b[None]), cam=cam_dev, rig=rig, n_cams=n_cams)
     T = pose.cpu().numpy()[0].astype(np.float64)
     inliers = np.nonzero(mask.cpu().numpy()[0])[0].astype(np.int64)
     return T, inliers
@@ -74,7 +80,7 @@ def absolute_pose_noncentral_ransac(bearing_vectors, cam_correspondences, points
 
 
 def absolute_pose_ransac(bearing_vectors, points, algo_name, threshold, max_iterations, points_cur=None, seed=_SEED):
-    """Central camera (RGB-D path, pose_est_tools.py:915); `algo_name` ("EPNP", "KNEIP", ...) is accepted and ignored."""
+    """Central camera (RGB-D path, pose_est_tools.py:915); every `algo_name` ("EPNP", "KNEIP", "GAO") runs the same solver."""
     return _ransac(bearing_vectors, points, points_cur, threshold, max_iterations, seed=seed)
 
 

@@ -41,7 +41,7 @@ class Workload:
 
 
 def build(ctx: ops.Context, name: str, batch: int, n_frames: int, seed: int = 0, score_mode: int = ops.SCORE_BEARING,
-          n_hyp: int | None = None) -> Workload:
+          n_hyp: int | None = None, solver: int = ops.SOLVER_ARUN) -> Workload:
     c = CONFIGS[name]
     rig = synth.make_rig(c["width"], c["height"], c["pano_cols"], seed=seed)
     scene = synth.make_scene(int(c["feat"] * 2.0), seed=seed)
@@ -57,13 +57,13 @@ def build(ctx: ops.Context, name: str, batch: int, n_frames: int, seed: int = 0,
         luts.append(ctx.lut_pack(mx, my, (rig.height, rig.width), mask=torch.from_numpy(mask).to(ctx.device)))
     lut = torch.stack(luts).contiguous()
     H = c["n_hyp"] if n_hyp is None else n_hyp
-    hyp_host = np.random.default_rng(seed + 7).integers(0, 2 ** 32, (H, 3), dtype=np.uint64).astype(np.uint32)
+    hyp_host = np.random.default_rng(seed + 7).integers(0, 2 ** 32, (H, 4 if solver == ops.SOLVER_P3P else 3), dtype=np.uint64).astype(np.uint32)
     hyp = torch.from_numpy(hyp_host.view(np.int32)).to(ctx.device)
     thr = 1.0 - math.cos(math.radians(5.0)) if score_mode == ops.SCORE_BEARING else 0.05
     cfg = FrontendConfig(batch=batch, src_h=rig.height, src_w=rig.width, pano_rows=rows, pano_cols=cols,
                          pano_top=rig.pano_vector(), pano_bot=rig.pano_vector(), f_top=rig.f_top, f_bot=rig.f_bot,
                          max_feat_per_view=c["cap"], max_feat_per_bucket=c["max_bucket"], cap=c["cap"], n_hyp=H,
-                         score_mode=score_mode, ransac_threshold=thr)
+                         score_mode=score_mode, ransac_threshold=thr, solver=solver)
     traj = synth.make_trajectory(n_frames, seed=seed)
     return Workload(name, rig, scene, cfg, lut, hyp, hyp_host, masks, maps, traj)
 
