@@ -180,3 +180,38 @@ def test_orb_description_oracle_matches_cv2():
     assert np.array_equal(np.sort(kept), np.flatnonzero(keep))
     assert np.array_equal(got[kept], want)
     assert orb.pattern().shape == (256, 4) and np.abs(orb.pattern()).max() == 13
+
+
+def test_p3p_oracle_solves_the_published_problem():
+    """oracle/p3p.py has no OpenGV output to pin against (parity unpinned): check that every returned depth triple satisfies
+    the three distance constraints, that the planted depths are among them, and that RANSAC on planted data returns the motion
+    — central and with the two-viewpoint rig."""
+    from oracle import p3p
+    from oracle.ransac import cayley_to_rot
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        d = rng.normal(0, 1, (3, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+        s_true = rng.uniform(0.5, 7, 3)
+        X = d * s_true[:, None]
+        R, t = cayley_to_rot(rng.normal(0, 0.3, 3)), rng.normal(0, 1, 3)
+        P = X @ R.T + t
+        sols = p3p.grunert_depths(d, P)
+        assert any(np.allclose(s, s_true, rtol=1e-7) for s in sols)
+        for s in sols:
+            Y = d * np.array(s)[:, None]
+            for i, j in ((0, 1), (0, 2), (1, 2)):
+                assert abs(np.linalg.norm(Y[i] - Y[j]) - np.linalg.norm(P[i] - P[j])) < 1e-7
+    rig = np.stack([np.hstack([np.eye(3), [[0.0], [0.0], [0.06]]]), np.hstack([cayley_to_rot([0.01, 0.02, 0.0]), [[0.01], [0.0], [-0.07]]])])
+    for use_rig in (False, True):
+        n = 200
+        R, t = cayley_to_rot(rng.normal(0, 0.05, 3)), rng.normal(0, 0.1, 3)
+        pb = rng.normal(0, 1, (n, 3)); pb = pb / np.linalg.norm(pb, axis=1, keepdims=True) * rng.uniform(0.5, 7, (n, 1))
+        cam = rng.integers(0, 2, n) if use_rig else None
+        x = np.einsum("nji,nj->ni", rig[cam][:, :, :3], pb - rig[cam][:, :, 3]) if use_rig else pb
+        f = x / np.linalg.norm(x, axis=1, keepdims=True)
+        bad = rng.random(n) < 0.3
+        f[bad] = -f[bad]
+        hyp = rng.integers(0, 2 ** 32, (100, 4), dtype=np.uint64).astype(np.uint32)
+        M, h, c, inl, counts = p3p.ransac_p3p(pb @ R.T + t, f, cam, rig if use_rig else None, hyp, 1 - np.cos(np.radians(1.0)))
+        assert c == (~bad).sum() and np.array_equal(inl, ~bad)
+        assert np.allclose(M, np.hstack([R, t[:, None]]), atol=1e-9)
