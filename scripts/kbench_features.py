@@ -56,6 +56,7 @@ def main():
         nk += len(k)
     t2 = time.perf_counter()
     print(json.dumps({"kernel": "feature_front", "panoramas": n_img, "ms_total": total, "ms_by_entry_point": {k: round(v, 3) for k, v in agg.items()},
+                      "gft_launches_ms": [round(t, 3) for name, t in marks if name.startswith("sos_gft")],
                       "panoramas_per_s": n_img / (total * 1e-3), "corners": int(cnt.sum()), "described": int(keep.sum()),
                       "cv2_one_panorama_ms": {"median+gray": (t1 - t0) * 1e3, "gft+orb x12 masks": (t2 - t1) * 1e3, "keypoints": nk},
                       "cv2_threads": cv2.getNumThreads()}))

@@ -29,67 +29,159 @@ __device__ __forceinline__ int refl(int p, int n) {
   return p;
 }
 
-// covariance terms (dx^2, dx dy, dy^2) per pixel
-__global__ void __launch_bounds__(256) gft_cov_kernel(const uint8_t* __restrict__ gray, int H, int W, float* __restrict__ cov) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= W) return;
-  const uint8_t* img = gray + (size_t)blockIdx.z * H * W;
-  const int xm = refl(x - 1, W), xp = refl(x + 1, W), ym = refl(y - 1, H), yp = refl(y + 1, H);
-  const float s = (float)(1.0 / (4.0 * 3.0 * 255.0)), s2 = 2.0f * s;
-  const float a00 = img[(size_t)ym * W + xm], a01 = img[(size_t)ym * W + x], a02 = img[(size_t)ym * W + xp];
-  const float a10 = img[(size_t)y * W + xm], a11 = img[(size_t)y * W + x], a12 = img[(size_t)y * W + xp];
-  const float a20 = img[(size_t)yp * W + xm], a21 = img[(size_t)yp * W + x], a22 = img[(size_t)yp * W + xp];
-  // d/dx: rows differentiated exactly ([-1 0 1]), columns smoothed with (s, 2s, s)
-  const float ru = a02 - a00, r0 = a12 - a10, rd = a22 - a20;
-  const float dx = __fmaf_rn(s, ru + rd, __fmul_rn(s2, r0));
-  // d/dy: rows smoothed with (s, 2s, s), columns differentiated
-  const float su = __fmaf_rn(s, a00 + a02, __fmul_rn(s2, a01));
-  const float sd = __fmaf_rn(s, a20 + a22, __fmul_rn(s2, a21));
-  const float dy = __fsub_rn(sd, su);
-  float* c = cov + 3 * (((size_t)blockIdx.z * H + y) * W + x);
-  c[0] = __fmul_rn(dx, dx);
-  c[1] = __fmul_rn(dx, dy);
-  c[2] = __fmul_rn(dy, dy);
-  (void)a11;
-}
+// Corner measure + (optionally) the maximum over each mask, fused.  Per pixel: Sobel derivatives (cv2's arithmetic: rows
+// differentiated exactly, columns smoothed with (s, 2s, s), one FMA), covariance terms dx^2, dx dy, dy^2 in float32, their
+// 3 x 3 box sums in double (cv2's RowSum<float,double> / ColumnSum<double,float>), smaller eigenvalue without contraction.
+// Every thread walks down its column with the 3-tap row sums of the last three rows in registers and recomputes the
+// covariance terms of its three columns from the gray image, so nothing but the gray image is read and nothing but the
+// measure is written.  (First version: a covariance image of 12 bytes per pixel written by one kernel and pulled through L2
+// three times by the next - 0.34 + 0.89 ms for 32 C2 panoramas.)
+// `mask_bits` holds one bit per mask and pixel; per warp only the masks present in the warp are reduced (one atomic per mask
+// and warp at most).  Non-negative floats order like their bit patterns, so the maxima are kept as uint32.
+constexpr int GE_ROWS = 16;   // rows per block
 
-// corner measure + (optionally) the maximum over each mask, fused: `mask_bits` holds one bit per mask and pixel; per warp
-// only the masks present in the warp are reduced (one atomic per mask and warp at most).  Non-negative floats order like
-// their bit patterns, so the maxima are kept as uint32.
-__global__ void __launch_bounds__(256)
-gft_eig_kernel(const float* __restrict__ cov, int H, int W, float* __restrict__ eig, const uint32_t* __restrict__ mask_bits,
+__global__ void __launch_bounds__(256, 3)
+gft_eig_kernel(const uint8_t* __restrict__ gray, int H, int W, float* __restrict__ eig, const uint32_t* __restrict__ mask_bits,
                int n_masks, uint32_t* __restrict__ max_bits) {
-  const int xr = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, img = blockIdx.z;
+  const int xr = blockIdx.x * blockDim.x + threadIdx.x, img = blockIdx.z;
+  const int y0 = blockIdx.y * GE_ROWS, y1 = min(H, y0 + GE_ROWS);
   const bool in = xr < W;
   const int x = in ? xr : W - 1;
-  const float* c = cov + 3 * (size_t)img * H * W;
-  double sa = 0.0, sb = 0.0, sc = 0.0;
+  const uint8_t* g = gray + (size_t)img * H * W;
+  // the three columns whose covariance terms enter this pixel's box sums (BORDER_REFLECT_101), each with its own Sobel taps
+  int cx[3][3];
 #pragma unroll
-  for (int j = -1; j <= 1; ++j) {
-    const int yy = refl(y + j, H);
-#pragma unroll
-    for (int i = -1; i <= 1; ++i) {
-      const float* p = c + 3 * ((size_t)yy * W + refl(x + i, W));
-      sa += (double)p[0];
-      sb += (double)p[1];
-      sc += (double)p[2];
-    }
+  for (int j = 0; j < 3; ++j) {
+    const int c0 = refl(x + j - 1, W);
+    cx[j][0] = refl(c0 - 1, W);
+    cx[j][1] = c0;
+    cx[j][2] = refl(c0 + 1, W);
   }
-  const float a = __fmul_rn((float)sa, 0.5f), b = (float)sb, cc = __fmul_rn((float)sc, 0.5f);
-  const float t = __fsub_rn(a, cc);
-  const float r = __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b)));
-  const float v = __fsub_rn(__fadd_rn(a, cc), r);
-  if (in) eig[((size_t)img * H + y) * W + x] = v;
-  if (mask_bits) {
-    const uint32_t mb = (in && v > 0.f) ? mask_bits[(size_t)y * W + x] : 0u;
-    uint32_t present = __reduce_or_sync(0xFFFFFFFFu, mb);
+  const float s = (float)(1.0 / (4.0 * 3.0 * 255.0)), s2 = 2.0f * s;
+  double ha[3], hb[3], hc[3];
+  auto row_sums = [&](int yy, double& a, double& b, double& cc) {
+    const int yc = refl(yy, H);
+    const uint8_t* ru = g + (size_t)refl(yc - 1, H) * W;
+    const uint8_t* r0 = g + (size_t)yc * W;
+    const uint8_t* rd = g + (size_t)refl(yc + 1, H) * W;
+    float pxx[3], pxy[3], pyy[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float a00 = ru[cx[j][0]], a01 = ru[cx[j][1]], a02 = ru[cx[j][2]];
+      const float a10 = r0[cx[j][0]], a12 = r0[cx[j][2]];
+      const float a20 = rd[cx[j][0]], a21 = rd[cx[j][1]], a22 = rd[cx[j][2]];
+      const float du = a02 - a00, d0 = a12 - a10, dd = a22 - a20;
+      const float dx = __fmaf_rn(s, du + dd, __fmul_rn(s2, d0));
+      const float su = __fmaf_rn(s, a00 + a02, __fmul_rn(s2, a01));
+      const float sd = __fmaf_rn(s, a20 + a22, __fmul_rn(s2, a21));
+      const float dy = __fsub_rn(sd, su);
+      pxx[j] = __fmul_rn(dx, dx);
+      pxy[j] = __fmul_rn(dx, dy);
+      pyy[j] = __fmul_rn(dy, dy);
+    }
+    a = ((double)pxx[0] + (double)pxx[1]) + (double)pxx[2];
+    b = ((double)pxy[0] + (double)pxy[1]) + (double)pxy[2];
+    cc = ((double)pyy[0] + (double)pyy[1]) + (double)pyy[2];
+  };
+  // Fast path (warp-uniform): no reflection anywhere in the strip.  Per gray row and column, D = g[x+1] - g[x-1] and
+  // S = fma(s, g[x-1] + g[x+1], 2s g[x]) are computed once and serve the three product rows that touch the row (same
+  // operations, same order as the generic path: bit-identical).
+  const bool fast = __all_sync(0xFFFFFFFFu, in && x >= 2 && x + 2 < W) && y0 >= 2 && y1 <= H - 2;
+  float D[3][3], S[3][3];
+  uint8_t raw[5];                                  // the gray row after next, loaded one iteration ahead of its use
+  auto fetch = [&](int row) {
+    const uint8_t* r = g + (size_t)min(row, H - 1) * W + (x - 2);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) raw[k] = __ldg(r + k);
+  };
+  auto derive = [&](float* Dr, float* Sr) {
+    float v[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) v[k] = raw[k];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      Dr[j] = v[j + 2] - v[j];
+      Sr[j] = __fmaf_rn(s, v[j] + v[j + 2], __fmul_rn(s2, v[j + 1]));
+    }
+  };
+  auto fast_sums = [&](double& a, double& b, double& cc) {
+    float pxx[3], pxy[3], pyy[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float dx = __fmaf_rn(s, D[0][j] + D[2][j], __fmul_rn(s2, D[1][j]));
+      const float dy = __fsub_rn(S[2][j], S[0][j]);
+      pxx[j] = __fmul_rn(dx, dx);
+      pxy[j] = __fmul_rn(dx, dy);
+      pyy[j] = __fmul_rn(dy, dy);
+    }
+    a = ((double)pxx[0] + (double)pxx[1]) + (double)pxx[2];
+    b = ((double)pxy[0] + (double)pxy[1]) + (double)pxy[2];
+    cc = ((double)pyy[0] + (double)pyy[1]) + (double)pyy[2];
+  };
+  auto shift = [&]() {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      D[0][j] = D[1][j]; D[1][j] = D[2][j];
+      S[0][j] = S[1][j]; S[1][j] = S[2][j];
+    }
+  };
+  if (fast) {
+    fetch(y0 - 2); derive(D[0], S[0]);
+    fetch(y0 - 1); derive(D[1], S[1]);
+    fetch(y0);     derive(D[2], S[2]);
+    fast_sums(ha[0], hb[0], hc[0]);
+    shift();
+    fetch(y0 + 1); derive(D[2], S[2]);
+    fast_sums(ha[1], hb[1], hc[1]);
+    fetch(y0 + 2);
+  } else {
+    row_sums(y0 - 1, ha[0], hb[0], hc[0]);
+    row_sums(y0, ha[1], hb[1], hc[1]);
+  }
+  uint32_t tm = 0u, tv = 0u;                      // tracked mask set and the largest measure (as bits) seen under it
+  auto flush = [&]() {
+    uint32_t present = __reduce_or_sync(0xFFFFFFFFu, tm);
     while (present) {
       const int m = __ffs(present) - 1;
       present &= present - 1;
-      const uint32_t best = __reduce_max_sync(0xFFFFFFFFu, ((mb >> m) & 1u) ? __float_as_uint(v) : 0u);
-      if ((threadIdx.x & 31) == 0 && best > max_bits[img * n_masks + m]) atomicMax(&max_bits[img * n_masks + m], best);
+      const uint32_t best = __reduce_max_sync(0xFFFFFFFFu, ((tm >> m) & 1u) ? tv : 0u);
+      if ((threadIdx.x & 31) == 0 && best > 0u) atomicMax(&max_bits[img * n_masks + m], best);
+    }
+    tm = 0u;
+    tv = 0u;
+  };
+  for (int y = y0; y < y1; ++y) {
+    const uint32_t mb_next = (mask_bits && in) ? __ldg(&mask_bits[(size_t)y * W + x]) : 0u;   // early: overlaps the arithmetic
+    if (fast) {
+      shift();
+      derive(D[2], S[2]);                          // gray row y + 2
+      fetch(y + 3);
+      fast_sums(ha[2], hb[2], hc[2]);
+    } else {
+      row_sums(y + 1, ha[2], hb[2], hc[2]);
+    }
+    const double sa = (ha[0] + ha[1]) + ha[2], sb = (hb[0] + hb[1]) + hb[2], sc = (hc[0] + hc[1]) + hc[2];
+    ha[0] = ha[1]; ha[1] = ha[2];
+    hb[0] = hb[1]; hb[1] = hb[2];
+    hc[0] = hc[1]; hc[1] = hc[2];
+    const float a = __fmul_rn((float)sa, 0.5f), b = (float)sb, cc = __fmul_rn((float)sc, 0.5f);
+    const float t = __fsub_rn(a, cc);
+    const float r = __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(b, b)));
+    const float v = __fsub_rn(__fadd_rn(a, cc), r);
+    if (in) eig[((size_t)img * H + y) * W + x] = v;
+    if (mask_bits) {
+      // running maximum per thread while its mask set stays the same down the column (the usual case: masks are column
+      // ranges); the warp flushes to the global maxima when some lane's set changes and at the end of the strip - a
+      // global read-compare-atomic per row would put an L2 round trip into every iteration of the walk
+      const uint32_t mb = (in && v > 0.f) ? mb_next : 0u;
+      if (__any_sync(0xFFFFFFFFu, mb != 0u && tm != 0u && mb != tm)) flush();
+      if (mb) {
+        tm = mb;
+        tv = max(tv, __float_as_uint(v));
+      }
     }
   }
+  if (mask_bits) flush();
 }
 
 // one bit per mask and pixel (masks are shared by all images); flags pixels that belong to more than one mask
@@ -181,25 +273,36 @@ constexpr int GFT_CAP = 16384;      // candidates per (image, mask) kept for the
 constexpr int GFT_THREADS = 1024;
 constexpr int GFT_K = 4;            // stronger neighbours remembered per candidate (more: rescan the rank image)
 
-// one block per (image, mask): sort descending, greedy minimum-distance selection in parallel rounds, strongest first out
+constexpr int GFT_CHUNK = 2048;     // candidates decided per pass of the selection (strongest first)
+
+// Shared memory of the selection for a list sorted as np2 keys: keys, one state byte per candidate, and the neighbour lists of
+// one chunk.
+__host__ __device__ inline size_t gft_select_smem(int np2) {
+  return (size_t)np2 * (sizeof(unsigned long long) + 1) + (size_t)GFT_CHUNK * (GFT_K * sizeof(uint16_t) + 1);
+}
+
+// One block per (image, mask): sort descending, then cv2's strongest-first minimum-distance greedy.  A candidate's fate only
+// depends on STRONGER candidates, so the sorted list is decided chunk by chunk (parallel rounds inside a chunk) and the
+// kernel stops as soon as max_corners corners are accepted - usually inside the first chunk or two.
 __global__ void __launch_bounds__(GFT_THREADS)
 gft_select_kernel(const unsigned long long* __restrict__ keys_in, const int32_t* __restrict__ counts, int cap, int H, int W,
                   int n_masks, int mask_index, int max_corners, int min_dist_sq, int reach, int32_t* __restrict__ rank_img,
-                  uint8_t* __restrict__ state_all, uint16_t* __restrict__ nbr_all, uint8_t* __restrict__ ncnt_all,
                   float* __restrict__ out_xy, int32_t* __restrict__ out_count) {
   extern __shared__ unsigned long long skey[];
-  __shared__ int n_undecided, n_acc_total;
+  __shared__ int n_undecided;
   __shared__ int warp_sums[GFT_THREADS / 32];
   // mask_index >= 0: one launch per mask (masks may overlap, the rank image of an image serves one mask at a time);
   // mask_index < 0: masks are pixel-disjoint, one launch for all lists, rank-image entries are tagged with their mask
   const int img = mask_index >= 0 ? blockIdx.x : blockIdx.x / n_masks;
   const int mk = mask_index >= 0 ? mask_index : blockIdx.x % n_masks;
   const int list = img * n_masks + mk;
-  const int scratch = mask_index >= 0 ? img : list;   // which slice of state / nbr / ncnt this block owns
   const int tag = mk << 16;
   const int n = min(counts[list], cap);
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
+  uint8_t* state = (uint8_t*)(skey + np2);                    // 0 undecided, 1 accepted, 2 rejected
+  uint16_t* nbr = (uint16_t*)(state + np2);                   // [GFT_CHUNK][GFT_K] stronger neighbours of the chunk's candidates
+  uint8_t* ncnt = (uint8_t*)(nbr + (size_t)GFT_CHUNK * GFT_K);
   const unsigned long long* kin = keys_in + (size_t)list * cap;
   for (int i = threadIdx.x; i < np2; i += blockDim.x) skey[i] = i < n ? kin[i] : 0ull;
   __syncthreads();
@@ -217,93 +320,98 @@ gft_select_kernel(const unsigned long long* __restrict__ keys_in, const int32_t*
       __syncthreads();
     }
   int32_t* rimg = rank_img + (size_t)img * H * W;
-  uint8_t* state = state_all + (size_t)scratch * cap;   // 0 undecided, 1 accepted, 2 rejected
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    rimg[(uint32_t)skey[i]] = tag | i;
-    state[i] = 0;
-  }
-  if (threadIdx.x == 0) n_undecided = n;
-  __syncthreads();
+  int processed = 0, accepted = 0;
   if (min_dist_sq > 0) {
-    // phase A (once): the stronger candidates closer than minDistance to candidate i.  All rank-image loads of a candidate
-    // are independent, so they overlap; the rounds below then touch only these few entries.
-    uint16_t* nbr = nbr_all + (size_t)scratch * cap * GFT_K;
-    uint8_t* ncnt = ncnt_all + (size_t)scratch * cap;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const int px = (int)(uint32_t)skey[i];
-      const int y = px / W, x = px - y * W;
-      int cnt = 0;
-      for (int dy = -reach; dy <= reach; ++dy) {
-        const int yy = y + dy;
-        if (yy < 0 || yy >= H) continue;
-        for (int dx = -reach; dx <= reach; ++dx) {
-          const int xx = x + dx;
-          if (xx < 0 || xx >= W || dx * dx + dy * dy >= min_dist_sq) continue;
-          const int e = rimg[(size_t)yy * W + xx];
-          const int j = e & 0xFFFF;
-          if (e >= 0 && (e >> 16) == mk && j < i) {
-            if (cnt < GFT_K) nbr[(size_t)i * GFT_K + cnt] = (uint16_t)j;
-            ++cnt;
-          }
-        }
+    while (processed < n && accepted < max_corners) {
+      const int c0 = processed, c1 = min(n, c0 + GFT_CHUNK);
+      for (int i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+        rimg[(uint32_t)skey[i]] = tag | i;
+        state[i] = 0;
       }
-      ncnt[i] = (uint8_t)min(cnt, 255);
-      if (cnt == 0) state[i] = 1;            // nothing stronger nearby: accepted outright
-    }
-    __syncthreads();
-    // phase B: rounds over the undecided candidates
-    while (true) {
       __syncthreads();
-      if (threadIdx.x == 0) n_undecided = 0;
-      __syncthreads();
-      int still = 0;
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        if (state[i] != 0) continue;
-        bool rejected = false, wait = false;
-        const int cnt = ncnt[i];
-        if (cnt <= GFT_K) {
-          for (int q = 0; q < cnt; ++q) {
-            const uint8_t sj = ((volatile uint8_t*)state)[nbr[(size_t)i * GFT_K + q]];
-            if (sj == 1) { rejected = true; break; }
-            if (sj == 0) wait = true;
-          }
-        } else {                              // more neighbours than the list holds (plateaus): rescan the rank image
-          const int px = (int)(uint32_t)skey[i];
-          const int y = px / W, x = px - y * W;
-          for (int dy = -reach; dy <= reach && !rejected; ++dy) {
-            const int yy = y + dy;
-            if (yy < 0 || yy >= H) continue;
-            for (int dx = -reach; dx <= reach; ++dx) {
-              const int xx = x + dx;
-              if (xx < 0 || xx >= W || dx * dx + dy * dy >= min_dist_sq) continue;
-              const int e = rimg[(size_t)yy * W + xx];
-              const int j = e & 0xFFFF;
-              if (e < 0 || (e >> 16) != mk || j >= i) continue;
-              const uint8_t sj = ((volatile uint8_t*)state)[j];
-              if (sj == 1) { rejected = true; break; }
-              if (sj == 0) wait = true;
+      // phase A: the stronger candidates closer than minDistance to candidate i.  All rank-image loads of a candidate are
+      // independent, so they overlap; the rounds below then touch only these few shared-memory entries.
+      for (int i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+        const int px = (int)(uint32_t)skey[i];
+        const int y = px / W, x = px - y * W;
+        int cnt = 0;
+        for (int dy = -reach; dy <= reach; ++dy) {
+          const int yy = y + dy;
+          if (yy < 0 || yy >= H) continue;
+          for (int dx = -reach; dx <= reach; ++dx) {
+            const int xx = x + dx;
+            if (xx < 0 || xx >= W || dx * dx + dy * dy >= min_dist_sq) continue;
+            const int e = rimg[(size_t)yy * W + xx];
+            const int j = e & 0xFFFF;
+            if (e >= 0 && (e >> 16) == mk && j < i) {
+              if (cnt < GFT_K) nbr[(size_t)(i - c0) * GFT_K + cnt] = (uint16_t)j;
+              ++cnt;
             }
           }
         }
-        // a decision only depends on FINAL states of stronger candidates, so the evaluation order inside a round is free
-        if (rejected) state[i] = 2;
-        else if (!wait) state[i] = 1;
-        else ++still;
+        ncnt[i - c0] = (uint8_t)min(cnt, 255);
+        if (cnt == 0) state[i] = 1;            // nothing stronger nearby: accepted outright
       }
-      if (still) atomicAdd(&n_undecided, still);
-      __syncthreads();
-      if (n_undecided == 0) break;
+      // phase B: rounds over the chunk's undecided candidates
+      while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) n_undecided = 0;
+        __syncthreads();
+        int still = 0;
+        for (int i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+          if (state[i] != 0) continue;
+          bool rejected = false, wait = false;
+          const int cnt = ncnt[i - c0];
+          if (cnt <= GFT_K) {
+            for (int q = 0; q < cnt; ++q) {
+              const uint8_t sj = ((volatile uint8_t*)state)[nbr[(size_t)(i - c0) * GFT_K + q]];
+              if (sj == 1) { rejected = true; break; }
+              if (sj == 0) wait = true;
+            }
+          } else {                              // more neighbours than the list holds (plateaus): rescan the rank image
+            const int px = (int)(uint32_t)skey[i];
+            const int y = px / W, x = px - y * W;
+            for (int dy = -reach; dy <= reach && !rejected; ++dy) {
+              const int yy = y + dy;
+              if (yy < 0 || yy >= H) continue;
+              for (int dx = -reach; dx <= reach; ++dx) {
+                const int xx = x + dx;
+                if (xx < 0 || xx >= W || dx * dx + dy * dy >= min_dist_sq) continue;
+                const int e = rimg[(size_t)yy * W + xx];
+                const int j = e & 0xFFFF;
+                if (e < 0 || (e >> 16) != mk || j >= i) continue;
+                const uint8_t sj = ((volatile uint8_t*)state)[j];
+                if (sj == 1) { rejected = true; break; }
+                if (sj == 0) wait = true;
+              }
+            }
+          }
+          // a decision only depends on FINAL states of stronger candidates, so the evaluation order inside a round is free
+          if (rejected) ((volatile uint8_t*)state)[i] = 2;
+          else if (!wait) ((volatile uint8_t*)state)[i] = 1;
+          else ++still;
+        }
+        if (still) atomicAdd(&n_undecided, still);
+        __syncthreads();
+        if (n_undecided == 0) break;
+      }
+      for (int i0 = c0; i0 < c1; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        accepted += __syncthreads_count(i < c1 && state[i] == 1);
+      }
+      processed = c1;
     }
   } else {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) state[i] = 1;
+    processed = min(n, max_corners);
+    for (int i = threadIdx.x; i < processed; i += blockDim.x) state[i] = 1;
     __syncthreads();
   }
   // ordered compaction of the accepted candidates, at most max_corners
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int base = 0;
-  for (int i0 = 0; i0 < n && base < max_corners; i0 += blockDim.x) {
+  for (int i0 = 0; i0 < processed && base < max_corners; i0 += blockDim.x) {
     const int i = i0 + threadIdx.x;
-    const bool acc = i < n && state[i] == 1;
+    const bool acc = i < processed && state[i] == 1;
     const unsigned vote = __ballot_sync(0xFFFFFFFFu, acc);
     if (lane == 0) warp_sums[warp] = __popc(vote);
     __syncthreads();
@@ -325,12 +433,10 @@ gft_select_kernel(const unsigned long long* __restrict__ keys_in, const int32_t*
     base += total;
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    n_acc_total = min(base, max_corners);
-    out_count[list] = n_acc_total;
-  }
-  // leave the rank image clean for the next mask
-  for (int i = threadIdx.x; i < n; i += blockDim.x) rimg[(uint32_t)skey[i]] = -1;
+  if (threadIdx.x == 0) out_count[list] = min(base, max_corners);
+  // leave the rank image clean for the next mask / call
+  if (min_dist_sq > 0)
+    for (int i = threadIdx.x; i < processed; i += blockDim.x) rimg[(uint32_t)skey[i]] = -1;
 }
 
 }  // namespace
@@ -342,14 +448,8 @@ extern "C" int sos_corner_min_eigenval(sos_ctx* ctx, const uint8_t* gray, int n_
   SOS_CHECK_ARG(gray && eig, "NULL array");
   SOS_CHECK_ARG(n_images <= 65535 && height <= 65535, "too many images / rows");
   SOS_CUDA(cudaSetDevice(ctx->device));
-  void* ws = nullptr;
-  const size_t px = (size_t)n_images * height * width;
-  const int rc = sos_arena_get(ctx, sos_align_up(px * 3 * sizeof(float), 256), &ws);
-  if (rc != SOS_OK) return rc;
-  dim3 grid(sos_div_up(width, 256), height, n_images);
-  gft_cov_kernel<<<grid, 256, 0, ctx->stream>>>(gray, height, width, (float*)ws);
-  SOS_LAUNCHED(ctx);
-  gft_eig_kernel<<<grid, 256, 0, ctx->stream>>>((const float*)ws, height, width, eig, nullptr, 0, nullptr);
+  gft_eig_kernel<<<dim3(sos_div_up(width, 256), sos_div_up(height, GE_ROWS), n_images), 256, 0, ctx->stream>>>(gray, height, width, eig, nullptr, 0,
+                                                                                                                 nullptr);
   SOS_LAUNCHED(ctx);
   return SOS_OK;
 }
@@ -370,28 +470,22 @@ extern "C" int sos_gft_detect(sos_ctx* ctx, const uint8_t* gray, const uint8_t* 
   // scratch layout
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t o = off; off += sos_align_up(bytes, 256); return o; };
-  const size_t o_cov = take(px * 3 * sizeof(float));
   const size_t o_eig = take(px * sizeof(float));
   const size_t o_max = take((size_t)lists * sizeof(uint32_t));
   const size_t o_cnt = take((size_t)lists * sizeof(int32_t));
   const size_t o_keys = take((size_t)lists * GFT_CAP * sizeof(unsigned long long));
   const size_t o_rank = take(px * sizeof(int32_t));
-  const size_t o_state = take((size_t)lists * GFT_CAP);
-  const size_t o_nbr = take((size_t)lists * GFT_CAP * GFT_K * sizeof(uint16_t));
-  const size_t o_ncnt = take((size_t)lists * GFT_CAP);
   const size_t o_flag = take(sizeof(int32_t));
   const size_t o_bits = take((size_t)height * width * sizeof(uint32_t));
   void* ws = nullptr;
   const int rc = sos_arena_get(ctx, off, &ws);
   if (rc != SOS_OK) return rc;
   uint8_t* base = (uint8_t*)ws;
-  float* cov = (float*)(base + o_cov);
   float* eig = (float*)(base + o_eig);
   uint32_t* max_bits = (uint32_t*)(base + o_max);
   int32_t* counts = (int32_t*)(base + o_cnt);
   unsigned long long* keys = (unsigned long long*)(base + o_keys);
   int32_t* rank_img = (int32_t*)(base + o_rank);
-  uint8_t* state = base + o_state;
 
   dim3 grid(sos_div_up(width, 256), height, n_images);
   const size_t per = (size_t)height * width;
@@ -402,16 +496,14 @@ extern "C" int sos_gft_detect(sos_ctx* ctx, const uint8_t* gray, const uint8_t* 
   SOS_CUDA(cudaMemsetAsync(rank_img, 0xFF, px * sizeof(int32_t), ctx->stream));       // -1
   gft_pack_masks_kernel<<<(unsigned)((per + 255) / 256), 256, 0, ctx->stream>>>(masks, per, n_masks, mask_bits, flag);
   SOS_LAUNCHED(ctx);
-  gft_cov_kernel<<<grid, 256, 0, ctx->stream>>>(gray, height, width, cov);
-  SOS_LAUNCHED(ctx);
-  gft_eig_kernel<<<grid, 256, 0, ctx->stream>>>(cov, height, width, eig, mask_bits, n_masks, max_bits);
+  gft_eig_kernel<<<dim3(grid.x, sos_div_up(height, GE_ROWS), grid.z), 256, 0, ctx->stream>>>(gray, height, width, eig, mask_bits, n_masks, max_bits);
   SOS_LAUNCHED(ctx);
   if (eig_out) SOS_CUDA(cudaMemcpyAsync(eig_out, eig, px * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
   gft_candidates_kernel<<<dim3(sos_div_up(width, 256), sos_div_up(height, GC_ROWS), n_images), 256, 0, ctx->stream>>>(
       eig, mask_bits, height, width, n_masks, max_bits, quality_level, GFT_CAP, keys, counts);
   SOS_LAUNCHED(ctx);
   static bool attr_set = false;
-  const size_t smem = (size_t)GFT_CAP * sizeof(unsigned long long);
+  const size_t smem = gft_select_smem(GFT_CAP);
   if (!attr_set) {
     SOS_CUDA(cudaFuncSetAttribute(gft_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
@@ -434,19 +526,17 @@ extern "C" int sos_gft_detect(sos_ctx* ctx, const uint8_t* gray, const uint8_t* 
     for (int v : hc) mx = std::max(mx, std::min(v, GFT_CAP));
     int np2 = 1024;
     while (np2 < mx) np2 <<= 1;
-    sel_smem = (size_t)np2 * sizeof(unsigned long long);
+    sel_smem = gft_select_smem(np2);
   }
   if (!overlap) {
     gft_select_kernel<<<lists, GFT_THREADS, sel_smem, ctx->stream>>>(keys, counts, GFT_CAP, height, width, n_masks, -1, max_corners,
-                                                                 min_dist_sq, reach, rank_img, state, (uint16_t*)(base + o_nbr),
-                                                                 base + o_ncnt, out_xy, out_count);
+                                                                 min_dist_sq, reach, rank_img, out_xy, out_count);
     SOS_LAUNCHED(ctx);
     return SOS_OK;
   }
   for (int m = 0; m < n_masks; ++m) {
     gft_select_kernel<<<n_images, GFT_THREADS, sel_smem, ctx->stream>>>(keys, counts, GFT_CAP, height, width, n_masks, m, max_corners,
-                                                                    min_dist_sq, reach, rank_img, state, (uint16_t*)(base + o_nbr), base + o_ncnt, out_xy,
-                                                                    out_count);
+                                                                    min_dist_sq, reach, rank_img, out_xy, out_count);
     SOS_LAUNCHED(ctx);
   }
   return SOS_OK;

@@ -99,9 +99,52 @@ median11_kernel(const uint8_t* __restrict__ src, int H, int W, int strip_rows, u
 // ---- lane-per-(column, channel) variant ----------------------------------------------------------------------------------
 // ncu on the warp-cooperative kernel above: 219 instructions per two-pixel step with 18 of 32 lanes active on average, issue
 // slots 89 % busy, 5.8 shared-memory wavefronts per atomic.  Here every lane owns one (column, channel) histogram of byte
-// counters (layout word = bin * 8 + lane / 4, byte = lane % 4: 8 KB per warp) and walks down its column by itself: per row 11
-// values leave and 11 enter the window with plain byte read-modify-writes — no atomics, no ballots, no idle lanes.
+// counters and walks down its column by itself: per row 11 values leave and 11 enter the window with plain byte
+// read-modify-writes — no atomics, no ballots, no idle lanes.
+// Layout (8 KB per warp): the counter of bin b of lane l is byte (b & 3) of word (b >> 2) * 32 + l, so a lane only ever touches
+// its own bank.  (First layout: byte b * 32 + l, i.e. four lanes per word - ncu: LSU data-pipe wavefronts at 93 % of peak, 167
+// per step for 68 requests, because lanes of one word group collide whenever their bins differ by a multiple of 4.)
 constexpr int ML_WARPS = 4;
+
+__device__ __forceinline__ int ml_slot(int b) { return ((b & 0xFC) << 5) | (b & 3); }
+
+template <int C, bool INTERIOR>
+__device__ __forceinline__ void median11_lane_column(const uint8_t* __restrict__ img, uint8_t* __restrict__ out, uint8_t* hb,
+                                                     int H, int W, int x, int ch, int y0, int y1) {
+  int xo[2 * MB_R + 1];                                  // byte offsets of the window columns inside a row (replicated border)
+#pragma unroll
+  for (int k = 0; k <= 2 * MB_R; ++k) xo[k] = INTERIOR ? (x + k - MB_R) * C + ch : min(max(x + k - MB_R, 0), W - 1) * C + ch;
+  const size_t pitch = (size_t)W * C;
+  int m = 0, ltm = 0;                                    // median candidate and the number of window values below it
+
+  for (int r = y0 - MB_R; r <= y0 + MB_R; ++r) {
+    const uint8_t* row = img + (size_t)min(max(r, 0), H - 1) * pitch + (INTERIOR ? xo[0] : 0);
+#pragma unroll
+    for (int k = 0; k <= 2 * MB_R; ++k) hb[ml_slot(INTERIOR ? row[k * C] : row[xo[k]])] += 1;
+  }
+  while (ltm + (int)hb[ml_slot(m)] <= MB_HALF) { ltm += hb[ml_slot(m)]; ++m; }
+  out[(size_t)y0 * pitch + (size_t)x * C + ch] = (uint8_t)m;
+
+  for (int y = y0 + 1; y < y1; ++y) {
+    const uint8_t* rold = img + (size_t)min(max(y - MB_R - 1, 0), H - 1) * pitch + (INTERIOR ? xo[0] : 0);
+    const uint8_t* rnew = img + (size_t)min(max(y + MB_R, 0), H - 1) * pitch + (INTERIOR ? xo[0] : 0);
+    int vo[2 * MB_R + 1], vn[2 * MB_R + 1];
+#pragma unroll
+    for (int k = 0; k <= 2 * MB_R; ++k) {                // all 22 loads first: they are independent
+      vo[k] = __ldg(INTERIOR ? rold + k * C : rold + xo[k]);
+      vn[k] = __ldg(INTERIOR ? rnew + k * C : rnew + xo[k]);
+    }
+#pragma unroll
+    for (int k = 0; k <= 2 * MB_R; ++k) {
+      hb[ml_slot(vo[k])] -= 1;
+      hb[ml_slot(vn[k])] += 1;
+      ltm += (vn[k] < m ? 1 : 0) - (vo[k] < m ? 1 : 0);
+    }
+    while (ltm > MB_HALF) { --m; ltm -= hb[ml_slot(m)]; }
+    while (ltm + (int)hb[ml_slot(m)] <= MB_HALF) { ltm += hb[ml_slot(m)]; ++m; }
+    out[(size_t)y * pitch + (size_t)x * C + ch] = (uint8_t)m;
+  }
+}
 
 template <int C>
 __global__ void __launch_bounds__(ML_WARPS * 32)
@@ -120,41 +163,10 @@ median11_lane_kernel(const uint8_t* __restrict__ src, int H, int W, int strip_ro
   const int col = lane / C, ch = lane - col * C;
   const bool active = col < COLS && x0 + col < W;
   if (!active) return;
-  const int x = x0 + col;
-  uint8_t* hb = (uint8_t*)hw + lane;                     // this lane's counter of bin b lives at hb[b * 32]
-  int xo[2 * MB_R + 1];                                  // byte offsets of the window columns inside a row (replicated border)
-#pragma unroll
-  for (int k = 0; k <= 2 * MB_R; ++k) xo[k] = min(max(x + k - MB_R, 0), W - 1) * C + ch;
-  const size_t pitch = (size_t)W * C;
-  int m = 0, ltm = 0;                                    // median candidate and the number of window values below it
-
-  for (int r = y0 - MB_R; r <= y0 + MB_R; ++r) {
-    const uint8_t* row = img + (size_t)min(max(r, 0), H - 1) * pitch;
-#pragma unroll
-    for (int k = 0; k <= 2 * MB_R; ++k) hb[(int)row[xo[k]] * 32] += 1;
-  }
-  while (ltm + (int)hb[m * 32] <= MB_HALF) { ltm += hb[m * 32]; ++m; }
-  out[(size_t)y0 * pitch + (size_t)x * C + ch] = (uint8_t)m;
-
-  for (int y = y0 + 1; y < y1; ++y) {
-    const uint8_t* rold = img + (size_t)min(max(y - MB_R - 1, 0), H - 1) * pitch;
-    const uint8_t* rnew = img + (size_t)min(max(y + MB_R, 0), H - 1) * pitch;
-    int vo[2 * MB_R + 1], vn[2 * MB_R + 1];
-#pragma unroll
-    for (int k = 0; k <= 2 * MB_R; ++k) {                // all 22 loads first: they are independent
-      vo[k] = __ldg(rold + xo[k]);
-      vn[k] = __ldg(rnew + xo[k]);
-    }
-#pragma unroll
-    for (int k = 0; k <= 2 * MB_R; ++k) {
-      hb[vo[k] * 32] -= 1;
-      hb[vn[k] * 32] += 1;
-      ltm += (vn[k] < m ? 1 : 0) - (vo[k] < m ? 1 : 0);
-    }
-    while (ltm > MB_HALF) { --m; ltm -= hb[m * 32]; }
-    while (ltm + (int)hb[m * 32] <= MB_HALF) { ltm += hb[m * 32]; ++m; }
-    out[(size_t)y * pitch + (size_t)x * C + ch] = (uint8_t)m;
-  }
+  uint8_t* hb = (uint8_t*)(hw + lane);                   // this lane's words: hw[(b >> 2) * 32 + lane]
+  // warp-uniform: every window column of every lane lies inside the image -> constant offsets between the 11 loads of a row
+  if (x0 - MB_R >= 0 && x0 + COLS - 1 + MB_R <= W - 1) median11_lane_column<C, true>(img, out, hb, H, W, x0 + col, ch, y0, y1);
+  else median11_lane_column<C, false>(img, out, hb, H, W, x0 + col, ch, y0, y1);
 }
 
 }  // namespace
