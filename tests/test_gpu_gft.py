@@ -69,3 +69,17 @@ def test_gft_no_mask_and_caps(ctx):
     flat = np.full((64, 64), 77, np.uint8)
     xy, cnt = ctx.gft_detect(dev(flat), None, 50)
     assert int(cnt[0, 0]) == 0 and cv_gft(flat, None, 50).shape[0] == 0
+
+
+@pytest.mark.parametrize("N,min_distance", [(300, 5.0), (500, 25.0)])
+def test_gft_long_candidate_lists(ctx, N, min_distance):
+    """~10 k candidates in one list: the selection sorts only a histogram-picked prefix of the strongest candidates
+    (N = 300) and falls back to the whole list when the prefix cannot supply N corners (minDistance = 25)."""
+    rng = np.random.default_rng(3)
+    g = textured(rng, 300, 800, 1.5)
+    xy, cnt = ctx.gft_detect(dev(g), None, N, 0.01, min_distance)
+    want = cv_gft(g, None, N, 0.01, min_distance)
+    got = xy.cpu().numpy()[0, 0, :int(cnt[0, 0])]
+    assert len(want) > 50 and abs(len(got) - len(want)) <= 1
+    k = min(len(got), len(want))
+    assert (got[:k] == want[:k]).all(axis=1).mean() >= 0.99

@@ -14,6 +14,8 @@
 // Selection: candidates of one (image, mask) are sorted by (strength desc, pixel index desc) — cv2's comparator — and the
 // strongest-first greedy of cv2 is evaluated in parallel rounds (a candidate is accepted once every stronger candidate
 // closer than minDistance has been rejected, rejected once one of them has been accepted): same result, no serial walk.
+// Because a decision never depends on weaker candidates, only a histogram-picked prefix of the strongest candidates is sorted
+// and decided, chunk by chunk, until maxCorners corners are accepted (whole list only if the prefix runs dry).
 #include <math_constants.h>
 
 #include <algorithm>
@@ -289,7 +291,8 @@ gft_select_kernel(const unsigned long long* __restrict__ keys_in, const int32_t*
                   int n_masks, int mask_index, int max_corners, int min_dist_sq, int reach, int32_t* __restrict__ rank_img,
                   float* __restrict__ out_xy, int32_t* __restrict__ out_count) {
   extern __shared__ unsigned long long skey[];
-  __shared__ int n_undecided;
+  __shared__ int n_undecided, s_fill, s_bin;
+  __shared__ uint32_t s_maxhi;
   __shared__ int warp_sums[GFT_THREADS / 32];
   // mask_index >= 0: one launch per mask (masks may overlap, the rank image of an image serves one mask at a time);
   // mask_index < 0: masks are pixel-disjoint, one launch for all lists, rank-image entries are tagged with their mask
@@ -304,12 +307,66 @@ gft_select_kernel(const unsigned long long* __restrict__ keys_in, const int32_t*
   uint16_t* nbr = (uint16_t*)(state + np2);                   // [GFT_CHUNK][GFT_K] stronger neighbours of the chunk's candidates
   uint8_t* ncnt = (uint8_t*)(nbr + (size_t)GFT_CHUNK * GFT_K);
   const unsigned long long* kin = keys_in + (size_t)list * cap;
-  for (int i = threadIdx.x; i < np2; i += blockDim.x) skey[i] = i < n ? kin[i] : 0ull;
+  int32_t* rimg = rank_img + (size_t)img * H * W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // Only the strongest few thousand candidates can matter (the walk stops at max_corners accepted), and the sort is the
+  // expensive part (a 16 K bitonic sort is 105 passes), so a histogram of the strength bits first picks a prefix of about
+  // 4 max_corners candidates to sort and decide; if that prefix runs dry the whole list is sorted and the walk starts over.
+  const int target = min(n, max(1024, 4 * max_corners));
+  const bool preselect = min_dist_sq > 0 && n > 2 * target;
+  int ns = n, processed = 0, accepted = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+  if (preselect && attempt == 0) {
+    uint32_t* hist = (uint32_t*)nbr;                          // 1024 bins, free until the first chunk
+    if (threadIdx.x == 0) { s_maxhi = 0u; s_fill = 0; }
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) hist[i] = 0u;
+    __syncthreads();
+    uint32_t mh = 0u;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) mh = max(mh, (uint32_t)(kin[i] >> 32));
+    mh = __reduce_max_sync(0xFFFFFFFFu, mh);
+    if (lane == 0) atomicMax(&s_maxhi, mh);
+    __syncthreads();
+    const uint32_t maxhi = s_maxhi;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[min(1023u, (maxhi - (uint32_t)(kin[i] >> 32)) >> 16)], 1u);
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t loc = 0u;
+      for (int q = 0; q < 32; ++q) loc += hist[lane * 32 + q];
+      uint32_t inc = loc;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, off);
+        if (lane >= off) inc += t;
+      }
+      const unsigned ball = __ballot_sync(0xFFFFFFFFu, inc >= (uint32_t)target);   // never empty: the bins hold all n >= target
+      if (lane == __ffs(ball) - 1) {
+        uint32_t cum = inc - loc;
+        for (int q = 0; q < 32; ++q) {
+          cum += hist[lane * 32 + q];
+          if (cum >= (uint32_t)target) { s_bin = lane * 32 + q; break; }
+        }
+      }
+    }
+    __syncthreads();
+    const uint32_t last_bin = (uint32_t)s_bin;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned long long k = kin[i];
+      if (min(1023u, (maxhi - (uint32_t)(k >> 32)) >> 16) <= last_bin) skey[atomicAdd(&s_fill, 1)] = k;
+    }
+    __syncthreads();
+    ns = s_fill;
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) skey[i] = kin[i];
+    ns = n;
+  }
+  int nps = 1;
+  while (nps < ns) nps <<= 1;
+  for (int i = ns + threadIdx.x; i < nps; i += blockDim.x) skey[i] = 0ull;
   __syncthreads();
   // bitonic sort, descending (key = strength bits << 32 | pixel index: cv2's greaterThanPtr order)
-  for (int k = 2; k <= np2; k <<= 1)
+  for (int k = 2; k <= nps; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+      for (int i = threadIdx.x; i < nps; i += blockDim.x) {
         const int l = i ^ j;
         if (l > i) {
           const unsigned long long a = skey[i], b = skey[l];
@@ -319,11 +376,11 @@ gft_select_kernel(const unsigned long long* __restrict__ keys_in, const int32_t*
       }
       __syncthreads();
     }
-  int32_t* rimg = rank_img + (size_t)img * H * W;
-  int processed = 0, accepted = 0;
+  processed = 0;
+  accepted = 0;
   if (min_dist_sq > 0) {
-    while (processed < n && accepted < max_corners) {
-      const int c0 = processed, c1 = min(n, c0 + GFT_CHUNK);
+    while (processed < ns && accepted < max_corners) {
+      const int c0 = processed, c1 = min(ns, c0 + GFT_CHUNK);
       for (int i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
         rimg[(uint32_t)skey[i]] = tag | i;
         state[i] = 0;
@@ -406,8 +463,12 @@ gft_select_kernel(const unsigned long long* __restrict__ keys_in, const int32_t*
     for (int i = threadIdx.x; i < processed; i += blockDim.x) state[i] = 1;
     __syncthreads();
   }
+  if (!(preselect && attempt == 0 && accepted < max_corners && ns < n)) break;
+  // the prefix ran dry: take the rank image back and decide the whole list
+  for (int i = threadIdx.x; i < processed; i += blockDim.x) rimg[(uint32_t)skey[i]] = -1;
+  __syncthreads();
+  }
   // ordered compaction of the accepted candidates, at most max_corners
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int base = 0;
   for (int i0 = 0; i0 < processed && base < max_corners; i0 += blockDim.x) {
     const int i = i0 + threadIdx.x;
