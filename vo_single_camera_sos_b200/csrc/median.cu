@@ -108,6 +108,39 @@ constexpr int ML_WARPS = 4;
 
 __device__ __forceinline__ int ml_slot(int b) { return ((b & 0xFC) << 5) | (b & 3); }
 
+// Move the median candidate m (with ltm = number of window values below m) to the median: ltm <= MB_HALF < ltm + count(m).
+// The four bins 4k .. 4k+3 of a lane share one word, so long walks (an edge entering the window moves the median by tens of
+// levels, and a warp waits for its slowest lane) take four bins per shared-memory read.
+__device__ __forceinline__ void ml_walk(const uint8_t* hb, int& m, int& ltm) {
+  const uint32_t* hw = (const uint32_t*)hb;                // word k of this lane: hw[k * 32]
+  if (ltm > MB_HALF) {                                     // down; the first step is the usual, single one
+    --m;
+    ltm -= hb[ml_slot(m)];
+    while (ltm > MB_HALF) {
+      if ((m & 3) == 0) {
+        const int sw = (int)__dp4a(hw[((m >> 2) - 1) * 32], 0x01010101u, 0u);
+        if (ltm - sw > MB_HALF) { ltm -= sw; m -= 4; continue; }
+      }
+      --m;
+      ltm -= hb[ml_slot(m)];
+    }
+  }
+  int c = hb[ml_slot(m)];
+  if (ltm + c > MB_HALF) return;                           // up; most steps end here
+  ltm += c;
+  ++m;
+  while (true) {
+    if ((m & 3) == 0) {
+      const int sw = (int)__dp4a(hw[(m >> 2) * 32], 0x01010101u, 0u);
+      if (ltm + sw <= MB_HALF) { ltm += sw; m += 4; continue; }
+    }
+    c = hb[ml_slot(m)];
+    if (ltm + c > MB_HALF) break;
+    ltm += c;
+    ++m;
+  }
+}
+
 template <int C, bool INTERIOR>
 __device__ __forceinline__ void median11_lane_column(const uint8_t* __restrict__ img, uint8_t* __restrict__ out, uint8_t* hb,
                                                      int H, int W, int x, int ch, int y0, int y1) {
@@ -122,7 +155,7 @@ __device__ __forceinline__ void median11_lane_column(const uint8_t* __restrict__
 #pragma unroll
     for (int k = 0; k <= 2 * MB_R; ++k) hb[ml_slot(INTERIOR ? row[k * C] : row[xo[k]])] += 1;
   }
-  while (ltm + (int)hb[ml_slot(m)] <= MB_HALF) { ltm += hb[ml_slot(m)]; ++m; }
+  ml_walk(hb, m, ltm);
   out[(size_t)y0 * pitch + (size_t)x * C + ch] = (uint8_t)m;
 
   for (int y = y0 + 1; y < y1; ++y) {
@@ -140,8 +173,7 @@ __device__ __forceinline__ void median11_lane_column(const uint8_t* __restrict__
       hb[ml_slot(vn[k])] += 1;
       ltm += (vn[k] < m ? 1 : 0) - (vo[k] < m ? 1 : 0);
     }
-    while (ltm > MB_HALF) { --m; ltm -= hb[ml_slot(m)]; }
-    while (ltm + (int)hb[ml_slot(m)] <= MB_HALF) { ltm += hb[ml_slot(m)]; ++m; }
+    ml_walk(hb, m, ltm);
     out[(size_t)y * pitch + (size_t)x * C + ch] = (uint8_t)m;
   }
 }
