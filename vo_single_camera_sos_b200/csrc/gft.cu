@@ -316,157 +316,157 @@ gft_select_kernel(const unsigned long long* __restrict__ keys_in, const int32_t*
   const bool preselect = min_dist_sq > 0 && n > 2 * target;
   int ns = n, processed = 0, accepted = 0;
   for (int attempt = 0; attempt < 2; ++attempt) {
-  if (preselect && attempt == 0) {
-    uint32_t* hist = (uint32_t*)nbr;                          // 1024 bins, free until the first chunk
-    if (threadIdx.x == 0) { s_maxhi = 0u; s_fill = 0; }
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) hist[i] = 0u;
-    __syncthreads();
-    uint32_t mh = 0u;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) mh = max(mh, (uint32_t)(kin[i] >> 32));
-    mh = __reduce_max_sync(0xFFFFFFFFu, mh);
-    if (lane == 0) atomicMax(&s_maxhi, mh);
-    __syncthreads();
-    const uint32_t maxhi = s_maxhi;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[min(1023u, (maxhi - (uint32_t)(kin[i] >> 32)) >> 16)], 1u);
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t loc = 0u;
-      for (int q = 0; q < 32; ++q) loc += hist[lane * 32 + q];
-      uint32_t inc = loc;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, off);
-        if (lane >= off) inc += t;
-      }
-      const unsigned ball = __ballot_sync(0xFFFFFFFFu, inc >= (uint32_t)target);   // never empty: the bins hold all n >= target
-      if (lane == __ffs(ball) - 1) {
-        uint32_t cum = inc - loc;
-        for (int q = 0; q < 32; ++q) {
-          cum += hist[lane * 32 + q];
-          if (cum >= (uint32_t)target) { s_bin = lane * 32 + q; break; }
-        }
-      }
-    }
-    __syncthreads();
-    const uint32_t last_bin = (uint32_t)s_bin;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const unsigned long long k = kin[i];
-      if (min(1023u, (maxhi - (uint32_t)(k >> 32)) >> 16) <= last_bin) skey[atomicAdd(&s_fill, 1)] = k;
-    }
-    __syncthreads();
-    ns = s_fill;
-  } else {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) skey[i] = kin[i];
-    ns = n;
-  }
-  int nps = 1;
-  while (nps < ns) nps <<= 1;
-  for (int i = ns + threadIdx.x; i < nps; i += blockDim.x) skey[i] = 0ull;
-  __syncthreads();
-  // bitonic sort, descending (key = strength bits << 32 | pixel index: cv2's greaterThanPtr order)
-  for (int k = 2; k <= nps; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < nps; i += blockDim.x) {
-        const int l = i ^ j;
-        if (l > i) {
-          const unsigned long long a = skey[i], b = skey[l];
-          const bool desc = (i & k) == 0;
-          if (desc ? (a < b) : (a > b)) { skey[i] = b; skey[l] = a; }
-        }
-      }
+    if (preselect && attempt == 0) {
+      uint32_t* hist = (uint32_t*)nbr;                          // 1024 bins, free until the first chunk
+      if (threadIdx.x == 0) { s_maxhi = 0u; s_fill = 0; }
+      for (int i = threadIdx.x; i < 1024; i += blockDim.x) hist[i] = 0u;
       __syncthreads();
-    }
-  processed = 0;
-  accepted = 0;
-  if (min_dist_sq > 0) {
-    while (processed < ns && accepted < max_corners) {
-      const int c0 = processed, c1 = min(ns, c0 + GFT_CHUNK);
-      for (int i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
-        rimg[(uint32_t)skey[i]] = tag | i;
-        state[i] = 0;
-      }
+      uint32_t mh = 0u;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) mh = max(mh, (uint32_t)(kin[i] >> 32));
+      mh = __reduce_max_sync(0xFFFFFFFFu, mh);
+      if (lane == 0) atomicMax(&s_maxhi, mh);
       __syncthreads();
-      // phase A: the stronger candidates closer than minDistance to candidate i.  All rank-image loads of a candidate are
-      // independent, so they overlap; the rounds below then touch only these few shared-memory entries.
-      for (int i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
-        const int px = (int)(uint32_t)skey[i];
-        const int y = px / W, x = px - y * W;
-        int cnt = 0;
-        for (int dy = -reach; dy <= reach; ++dy) {
-          const int yy = y + dy;
-          if (yy < 0 || yy >= H) continue;
-          for (int dx = -reach; dx <= reach; ++dx) {
-            const int xx = x + dx;
-            if (xx < 0 || xx >= W || dx * dx + dy * dy >= min_dist_sq) continue;
-            const int e = rimg[(size_t)yy * W + xx];
-            const int j = e & 0xFFFF;
-            if (e >= 0 && (e >> 16) == mk && j < i) {
-              if (cnt < GFT_K) nbr[(size_t)(i - c0) * GFT_K + cnt] = (uint16_t)j;
-              ++cnt;
-            }
+      const uint32_t maxhi = s_maxhi;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[min(1023u, (maxhi - (uint32_t)(kin[i] >> 32)) >> 16)], 1u);
+      __syncthreads();
+      if (warp == 0) {
+        uint32_t loc = 0u;
+        for (int q = 0; q < 32; ++q) loc += hist[lane * 32 + q];
+        uint32_t inc = loc;
+  #pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, off);
+          if (lane >= off) inc += t;
+        }
+        const unsigned ball = __ballot_sync(0xFFFFFFFFu, inc >= (uint32_t)target);   // never empty: the bins hold all n >= target
+        if (lane == __ffs(ball) - 1) {
+          uint32_t cum = inc - loc;
+          for (int q = 0; q < 32; ++q) {
+            cum += hist[lane * 32 + q];
+            if (cum >= (uint32_t)target) { s_bin = lane * 32 + q; break; }
           }
         }
-        ncnt[i - c0] = (uint8_t)min(cnt, 255);
-        if (cnt == 0) state[i] = 1;            // nothing stronger nearby: accepted outright
       }
-      // phase B: rounds over the chunk's undecided candidates
-      while (true) {
+      __syncthreads();
+      const uint32_t last_bin = (uint32_t)s_bin;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long k = kin[i];
+        if (min(1023u, (maxhi - (uint32_t)(k >> 32)) >> 16) <= last_bin) skey[atomicAdd(&s_fill, 1)] = k;
+      }
+      __syncthreads();
+      ns = s_fill;
+    } else {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) skey[i] = kin[i];
+      ns = n;
+    }
+    int nps = 1;
+    while (nps < ns) nps <<= 1;
+    for (int i = ns + threadIdx.x; i < nps; i += blockDim.x) skey[i] = 0ull;
+    __syncthreads();
+    // bitonic sort, descending (key = strength bits << 32 | pixel index: cv2's greaterThanPtr order)
+    for (int k = 2; k <= nps; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = threadIdx.x; i < nps; i += blockDim.x) {
+          const int l = i ^ j;
+          if (l > i) {
+            const unsigned long long a = skey[i], b = skey[l];
+            const bool desc = (i & k) == 0;
+            if (desc ? (a < b) : (a > b)) { skey[i] = b; skey[l] = a; }
+          }
+        }
         __syncthreads();
-        if (threadIdx.x == 0) n_undecided = 0;
-        __syncthreads();
-        int still = 0;
+      }
+    processed = 0;
+    accepted = 0;
+    if (min_dist_sq > 0) {
+      while (processed < ns && accepted < max_corners) {
+        const int c0 = processed, c1 = min(ns, c0 + GFT_CHUNK);
         for (int i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
-          if (state[i] != 0) continue;
-          bool rejected = false, wait = false;
-          const int cnt = ncnt[i - c0];
-          if (cnt <= GFT_K) {
-            for (int q = 0; q < cnt; ++q) {
-              const uint8_t sj = ((volatile uint8_t*)state)[nbr[(size_t)(i - c0) * GFT_K + q]];
-              if (sj == 1) { rejected = true; break; }
-              if (sj == 0) wait = true;
-            }
-          } else {                              // more neighbours than the list holds (plateaus): rescan the rank image
-            const int px = (int)(uint32_t)skey[i];
-            const int y = px / W, x = px - y * W;
-            for (int dy = -reach; dy <= reach && !rejected; ++dy) {
-              const int yy = y + dy;
-              if (yy < 0 || yy >= H) continue;
-              for (int dx = -reach; dx <= reach; ++dx) {
-                const int xx = x + dx;
-                if (xx < 0 || xx >= W || dx * dx + dy * dy >= min_dist_sq) continue;
-                const int e = rimg[(size_t)yy * W + xx];
-                const int j = e & 0xFFFF;
-                if (e < 0 || (e >> 16) != mk || j >= i) continue;
-                const uint8_t sj = ((volatile uint8_t*)state)[j];
-                if (sj == 1) { rejected = true; break; }
-                if (sj == 0) wait = true;
+          rimg[(uint32_t)skey[i]] = tag | i;
+          state[i] = 0;
+        }
+        __syncthreads();
+        // phase A: the stronger candidates closer than minDistance to candidate i.  All rank-image loads of a candidate are
+        // independent, so they overlap; the rounds below then touch only these few shared-memory entries.
+        for (int i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+          const int px = (int)(uint32_t)skey[i];
+          const int y = px / W, x = px - y * W;
+          int cnt = 0;
+          for (int dy = -reach; dy <= reach; ++dy) {
+            const int yy = y + dy;
+            if (yy < 0 || yy >= H) continue;
+            for (int dx = -reach; dx <= reach; ++dx) {
+              const int xx = x + dx;
+              if (xx < 0 || xx >= W || dx * dx + dy * dy >= min_dist_sq) continue;
+              const int e = rimg[(size_t)yy * W + xx];
+              const int j = e & 0xFFFF;
+              if (e >= 0 && (e >> 16) == mk && j < i) {
+                if (cnt < GFT_K) nbr[(size_t)(i - c0) * GFT_K + cnt] = (uint16_t)j;
+                ++cnt;
               }
             }
           }
-          // a decision only depends on FINAL states of stronger candidates, so the evaluation order inside a round is free
-          if (rejected) ((volatile uint8_t*)state)[i] = 2;
-          else if (!wait) ((volatile uint8_t*)state)[i] = 1;
-          else ++still;
+          ncnt[i - c0] = (uint8_t)min(cnt, 255);
+          if (cnt == 0) state[i] = 1;            // nothing stronger nearby: accepted outright
         }
-        if (still) atomicAdd(&n_undecided, still);
-        __syncthreads();
-        if (n_undecided == 0) break;
+        // phase B: rounds over the chunk's undecided candidates
+        while (true) {
+          __syncthreads();
+          if (threadIdx.x == 0) n_undecided = 0;
+          __syncthreads();
+          int still = 0;
+          for (int i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+            if (state[i] != 0) continue;
+            bool rejected = false, wait = false;
+            const int cnt = ncnt[i - c0];
+            if (cnt <= GFT_K) {
+              for (int q = 0; q < cnt; ++q) {
+                const uint8_t sj = ((volatile uint8_t*)state)[nbr[(size_t)(i - c0) * GFT_K + q]];
+                if (sj == 1) { rejected = true; break; }
+                if (sj == 0) wait = true;
+              }
+            } else {                              // more neighbours than the list holds (plateaus): rescan the rank image
+              const int px = (int)(uint32_t)skey[i];
+              const int y = px / W, x = px - y * W;
+              for (int dy = -reach; dy <= reach && !rejected; ++dy) {
+                const int yy = y + dy;
+                if (yy < 0 || yy >= H) continue;
+                for (int dx = -reach; dx <= reach; ++dx) {
+                  const int xx = x + dx;
+                  if (xx < 0 || xx >= W || dx * dx + dy * dy >= min_dist_sq) continue;
+                  const int e = rimg[(size_t)yy * W + xx];
+                  const int j = e & 0xFFFF;
+                  if (e < 0 || (e >> 16) != mk || j >= i) continue;
+                  const uint8_t sj = ((volatile uint8_t*)state)[j];
+                  if (sj == 1) { rejected = true; break; }
+                  if (sj == 0) wait = true;
+                }
+              }
+            }
+            // a decision only depends on FINAL states of stronger candidates, so the evaluation order inside a round is free
+            if (rejected) ((volatile uint8_t*)state)[i] = 2;
+            else if (!wait) ((volatile uint8_t*)state)[i] = 1;
+            else ++still;
+          }
+          if (still) atomicAdd(&n_undecided, still);
+          __syncthreads();
+          if (n_undecided == 0) break;
+        }
+        for (int i0 = c0; i0 < c1; i0 += blockDim.x) {
+          const int i = i0 + threadIdx.x;
+          accepted += __syncthreads_count(i < c1 && state[i] == 1);
+        }
+        processed = c1;
       }
-      for (int i0 = c0; i0 < c1; i0 += blockDim.x) {
-        const int i = i0 + threadIdx.x;
-        accepted += __syncthreads_count(i < c1 && state[i] == 1);
-      }
-      processed = c1;
+    } else {
+      processed = min(n, max_corners);
+      for (int i = threadIdx.x; i < processed; i += blockDim.x) state[i] = 1;
+      __syncthreads();
     }
-  } else {
-    processed = min(n, max_corners);
-    for (int i = threadIdx.x; i < processed; i += blockDim.x) state[i] = 1;
+    if (!(preselect && attempt == 0 && accepted < max_corners && ns < n)) break;
+    // the prefix ran dry: take the rank image back and decide the whole list
+    for (int i = threadIdx.x; i < processed; i += blockDim.x) rimg[(uint32_t)skey[i]] = -1;
     __syncthreads();
-  }
-  if (!(preselect && attempt == 0 && accepted < max_corners && ns < n)) break;
-  // the prefix ran dry: take the rank image back and decide the whole list
-  for (int i = threadIdx.x; i < processed; i += blockDim.x) rimg[(uint32_t)skey[i]] = -1;
-  __syncthreads();
   }
   // ordered compaction of the accepted candidates, at most max_corners
   int base = 0;
