@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Kernel micro-benchmarks at C2 sizes (CUDA events, warm-up, inputs rotated): python scripts/kbench.py [hamming|ransac|remap|all]
+"""Kernel micro-benchmarks at C2 sizes (CUDA events, warm-up, inputs rotated): python scripts/kbench.py [hamming|ransac|remap|dense|rgbd|all]
 
 Variants are selected through environment variables read once per process (SOS_HAMMING_VARIANT, SOS_REMAP_BYTE_LOADS),
 so A/B runs are separate processes.  Prints one JSON line per kernel.
@@ -124,6 +124,29 @@ def bench_remap(ctx, hbm_peak, B=16, H=2048, W=2048, rows=849, cols=2400):
                 frac_of_hbm_peak=alg / (ms * 1e-3) / 1e9 / hbm_peak, gbps_src_plus_dst=dram / (ms * 1e-3) / 1e9)
 
 
+def bench_rgbd(ctx, hbm_peak, B=256, h=480, w=640, n=1000):
+    """RGB-D comparison path (BASELINE config 5): radial depth -> Z over whole 640 x 480 maps (4 B in, 4 B out
+    per pixel) and back-projection + range gate at n keypoints per frame (gather: 4 B depth + 8 B index in, 25 B out)."""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    cam = [525.0, 525.0, 319.5, 239.5, 1.0 / 1000.0, 0.0]                # fx, fy, cx, cy, focal_m, depth_is_Z = 0 (radial)
+    depth = [torch.rand((B, h, w), device="cuda", generator=g) * 6.0 + 0.5 for _ in range(2)]
+    u = torch.randint(0, w, (B, n), dtype=torch.int32, device="cuda", generator=g)
+    v = torch.randint(0, h, (B, n), dtype=torch.int32, device="cuda", generator=g)
+    it = [0]
+
+    def run_z():
+        ctx.rgbd_depth_to_z(cam, depth[it[0] & 1])
+        it[0] += 1
+
+    def run_bp():
+        ctx.rgbd_backproject(cam, depth[it[0] & 1], u, v, 0.8, 7.0)
+        it[0] += 1
+    ms_z, ms_bp = timeit(run_z), timeit(run_bp)
+    gbps = B * h * w * 8 / (ms_z * 1e-3) / 1e9
+    return dict(kernel="rgbd", frames=B, ms_depth_to_z=ms_z, gbps_depth_to_z=gbps, frac_of_hbm_peak=gbps / hbm_peak,
+                ms_backproject=ms_bp, keypoints_per_s=B * n / (ms_bp * 1e-3), frames_per_s_both=B / ((ms_z + ms_bp) * 1e-3))
+
+
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     ctx = ops.Context(0)
@@ -141,6 +164,8 @@ def main():
         res.append(bench_remap(ctx, 6451.2))
     if what in ("dense", "all"):
         res.append(bench_dense(ctx, 6451.2))
+    if what in ("rgbd", "all"):
+        res.append(bench_rgbd(ctx, 6451.2))
     for r in res:
         print(json.dumps(r))
 

@@ -412,12 +412,25 @@ __device__ __forceinline__ double rgbd_depth_z(const RgbdP& c, double d, double 
   return f * d / sqrt(xi * xi + yi * yi + f * f);
 }
 
-__global__ void rgbd_depth_to_z_kernel(RgbdP c, const float* __restrict__ depth, int h, int w, float* __restrict__ z) {
+// One thread per pixel position, looping over the frames: the double-precision square root of the radial model depends on
+// (x, y) only, so it is taken once per thread and the per-frame work is one multiply and one divide (first version: sqrt and
+// divide per element, 0.36 ms for 256 VGA frames = 0.27 of the HBM roofline, FP64-pipe bound).
+constexpr int RGBD_Z_SLICES = 8;
+
+__global__ void rgbd_depth_to_z_kernel(RgbdP c, const float* __restrict__ depth, int batch, int h, int w, float* __restrict__ z) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   if (x >= w) return;
-  const size_t o = ((size_t)blockIdx.z * h + y) * w + x;
-  z[o] = (float)rgbd_depth_z(c, (double)depth[o], (double)x, (double)y);
+  const bool is_z = c.v[SOS_RGBD_DEPTH_IS_Z] != 0.0;
+  const double f = c.v[SOS_RGBD_FOCAL_M];
+  const double xi = (f / c.v[SOS_RGBD_FX]) * ((double)x - c.v[SOS_RGBD_CX]);
+  const double yi = (f / c.v[SOS_RGBD_FY]) * ((double)y - c.v[SOS_RGBD_CY]);
+  const double den = sqrt(xi * xi + yi * yi + f * f);
+  const size_t plane = (size_t)h * w, o0 = (size_t)y * w + x;
+  for (int b = blockIdx.z; b < batch; b += gridDim.z) {
+    const float d = depth[b * plane + o0];
+    z[b * plane + o0] = is_z ? d : (float)(f * (double)d / den);     // same operations as rgbd_depth_z
+  }
 }
 
 __global__ void rgbd_backproject_kernel(RgbdP c, const float* __restrict__ depth, int h, int w,
@@ -611,8 +624,8 @@ extern "C" int sos_rgbd_depth_to_z(sos_ctx* ctx, const double* cam, const float*
   SOS_CUDA(cudaSetDevice(ctx->device));
   RgbdP c;
   for (int i = 0; i < SOS_RGBD_NPARAMS; ++i) c.v[i] = cam[i];
-  dim3 grid(sos_div_up(w, 256), h, batch);
-  rgbd_depth_to_z_kernel<<<grid, 256, 0, ctx->stream>>>(c, depth, h, w, z);
+  dim3 grid(sos_div_up(w, 128), h, batch < RGBD_Z_SLICES ? batch : RGBD_Z_SLICES);
+  rgbd_depth_to_z_kernel<<<grid, 128, 0, ctx->stream>>>(c, depth, batch, h, w, z);
   SOS_LAUNCHED(ctx);
   return SOS_OK;
 }
