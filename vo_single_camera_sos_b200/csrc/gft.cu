@@ -301,7 +301,7 @@ gft_select_kernel(const unsigned long long* __restrict__ keys_in, const int32_t*
   const int list = img * n_masks + mk;
   const int tag = mk << 16;
   const int n = min(counts[list], cap);
-  int np2 = 1;
+  int np2 = 8;                                                // >= 8 keeps the byte / uint16 arrays behind the keys aligned
   while (np2 < n) np2 <<= 1;
   uint8_t* state = (uint8_t*)(skey + np2);                    // 0 undecided, 1 accepted, 2 rejected
   uint16_t* nbr = (uint16_t*)(state + np2);                   // [GFT_CHUNK][GFT_K] stronger neighbours of the chunk's candidates
