@@ -262,3 +262,27 @@ def test_frontend_bearing_only_solver_matches_oracle(ctx):
         assert np.allclose(buf["pose"][i][:, :3], T_rel[:3, :3], atol=0.05)
         assert np.allclose(buf["pose"][i][:, 3], T_rel[:3, 3], atol=0.15)
     fe.close()
+
+
+@pytest.mark.parametrize("name", ["c1", "c2"])
+def test_frontend_full_size_stage_by_stage(ctx, name):
+    """The same stage-by-stage comparison at the BASELINE sizes — config 1 (1280 x 960 omni, 1200-wide panoramas, 2000
+    features per view, 210 hypotheses) and config 2 (2048 x 2048, 2400-wide, 8000 features, 4096 hypotheses): every stage of
+    two captured steps against the oracle."""
+    from vo_single_camera_sos_b200 import ops, workload
+    B = 2
+    w = workload.build(ctx, name, batch=B, n_frames=2 * B, seed=5, score_mode=ops.SCORE_BEARING)
+    fe = w.frontend(ctx)
+    prev = None
+    for step in range(2):
+        fr = workload.make_frames(w, step * B, B)
+        fe.step(*workload.to_device(ctx, fr))
+        torch.cuda.synchronize()
+        buf = host(fe.buffers())
+        prev = check_step(w, fr, buf, prev, "bearing")
+    for i in range(B):
+        T_rel = np.linalg.inv(w.trajectory[B + i - 1]) @ w.trajectory[B + i]
+        assert buf["stats"][i, 2] > 500
+        assert np.allclose(buf["pose"][i][:, :3], T_rel[:3, :3], atol=0.02)
+        assert np.allclose(buf["pose"][i][:, 3], T_rel[:3, 3], atol=0.05)
+    fe.close()
