@@ -323,6 +323,12 @@ int sos_refit_inliers(sos_ctx* ctx, const float* p_ref, const float* p_cur, cons
  * channels 1 or 3, not in place.  Bit-exact. */
 int sos_median_blur_11(sos_ctx* ctx, const uint8_t* src, int n_images, int height, int width, int channels, uint8_t* dst);
 
+/* replaces: the pair cv2.medianBlur(pano_img, 11) + cv2.cvtColor(pano_img, cv2.COLOR_BGR2GRAY) (camera_models.py:1708-1711)
+ * in one pass: src uint8 [n_images, height, width, 3] -> gray [n_images, height, width]; dst_bgr (the blurred colour image,
+ * same shape as src) may be NULL when only the gray image is consumed.  Bit-exact with the two OpenCV calls. */
+int sos_median_blur_11_gray(sos_ctx* ctx, const uint8_t* src, int n_images, int height, int width, uint8_t* dst_bgr,
+                            uint8_t* gray);
+
 /* replaces: cv2.cvtColor(pano_img, cv2.COLOR_BGR2GRAY) (camera_models.py:1711).  Bit-exact with OpenCV 4.x (15-bit fixed point). */
 int sos_bgr_to_gray(sos_ctx* ctx, const uint8_t* bgr, size_t n_pixels, uint8_t* gray);
 

@@ -31,3 +31,18 @@ def test_median_blur_panorama_size(ctx):
     pano = cv2.GaussianBlur(rng.integers(0, 256, (849, 2400, 3), dtype=np.uint8), (0, 0), 1.0)
     got = ctx.median_blur_11(dev(pano)).cpu().numpy()
     assert np.array_equal(got, cv2.medianBlur(pano, 11))
+
+
+@pytest.mark.parametrize("shape", [(97, 131, 3), (40, 33, 3), (849, 2400, 3)])
+def test_median_blur_gray_fused(ctx, shape):
+    """medianBlur + cvtColor(BGR2GRAY) in one kernel (camera_models.py:1708-1711): both outputs bit-exact."""
+    rng = np.random.default_rng(sum(shape) + 1)
+    imgs = np.stack([rng.integers(0, 256, shape, dtype=np.uint8),
+                     cv2.GaussianBlur(rng.integers(0, 256, shape, dtype=np.uint8), (0, 0), 1.5)])
+    gray, bgr = ctx.median_blur_11_gray(dev(imgs), want_bgr=True)
+    gray_only = ctx.median_blur_11_gray(dev(imgs))
+    for i in range(2):
+        want = cv2.medianBlur(imgs[i], 11)
+        assert np.array_equal(bgr[i].cpu().numpy(), want)
+        assert np.array_equal(gray[i].cpu().numpy(), cv2.cvtColor(want, cv2.COLOR_BGR2GRAY))
+    assert torch.equal(gray, gray_only)

@@ -57,6 +57,7 @@ PROTOTYPES = {
     "sos_ransac_p3d_eval": (I, [c_ctx, P, P, P, P, P, I, I, P, I, P, I, D, P, P, P]),
     "sos_refit_inliers": (I, [c_ctx, P, P, P, P, I, I, P, P]),
     "sos_median_blur_11": (I, [c_ctx, P, I, I, I, I, P]),
+    "sos_median_blur_11_gray": (I, [c_ctx, P, I, I, I, P, P]),
     "sos_bgr_to_gray": (I, [c_ctx, P, C.c_size_t, P]),
     "sos_orb_blur": (I, [c_ctx, P, I, I, I, P]),
     "sos_orb_describe": (I, [c_ctx, P, I, I, I, P, P, P, I, P, P]),

@@ -563,12 +563,9 @@ extern "C" int sos_gft_detect(sos_ctx* ctx, const uint8_t* gray, const uint8_t* 
   gft_candidates_kernel<<<dim3(sos_div_up(width, 256), sos_div_up(height, GC_ROWS), n_images), 256, 0, ctx->stream>>>(
       eig, mask_bits, height, width, n_masks, max_bits, quality_level, GFT_CAP, keys, counts);
   SOS_LAUNCHED(ctx);
-  static bool attr_set = false;
   const size_t smem = gft_select_smem(GFT_CAP);
-  if (!attr_set) {
-    SOS_CUDA(cudaFuncSetAttribute(gft_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  // per device, so set on every call (a process may hold contexts on several devices)
+  SOS_CUDA(cudaFuncSetAttribute(gft_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const double md2 = min_distance * min_distance;
   const int min_dist_sq = min_distance >= 1.0 ? (int)ceil(md2) : 0;   // integer offsets: dx^2 + dy^2 < minDistance^2
   const int reach = (int)ceil(min_distance);

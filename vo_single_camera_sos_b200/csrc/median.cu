@@ -141,9 +141,23 @@ __device__ __forceinline__ void ml_walk(const uint8_t* hb, int& m, int& ltm) {
   }
 }
 
+// cv::cvtColor(BGR2GRAY) on the three medians of a column (15-bit fixed point, orb.cu): the lanes of one column are
+// neighbours, so the lane of channel 0 collects the other two with shuffles.  `amask` = the warp's lanes that walk columns.
+template <int C>
+__device__ __forceinline__ void ml_store(uint8_t* __restrict__ out, uint8_t* __restrict__ gray, size_t pix, int ch, int m,
+                                         unsigned amask) {
+  if (out) out[pix * C + ch] = (uint8_t)m;
+  if (C == 3 && gray) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t g = __shfl_sync(amask, m, lane - ch + 1), r = __shfl_sync(amask, m, lane - ch + 2);
+    if (ch == 0) gray[pix] = (uint8_t)(((uint32_t)m * 3735u + g * 19235u + r * 9798u + 16384u) >> 15);
+  }
+}
+
 template <int C, bool INTERIOR>
-__device__ __forceinline__ void median11_lane_column(const uint8_t* __restrict__ img, uint8_t* __restrict__ out, uint8_t* hb,
-                                                     int H, int W, int x, int ch, int y0, int y1) {
+__device__ __forceinline__ void median11_lane_column(const uint8_t* __restrict__ img, uint8_t* __restrict__ out,
+                                                     uint8_t* __restrict__ gray, unsigned amask, uint8_t* hb, int H, int W,
+                                                     int x, int ch, int y0, int y1) {
   int xo[2 * MB_R + 1];                                  // byte offsets of the window columns inside a row (replicated border)
 #pragma unroll
   for (int k = 0; k <= 2 * MB_R; ++k) xo[k] = INTERIOR ? (x + k - MB_R) * C + ch : min(max(x + k - MB_R, 0), W - 1) * C + ch;
@@ -156,7 +170,7 @@ __device__ __forceinline__ void median11_lane_column(const uint8_t* __restrict__
     for (int k = 0; k <= 2 * MB_R; ++k) hb[ml_slot(INTERIOR ? row[k * C] : row[xo[k]])] += 1;
   }
   ml_walk(hb, m, ltm);
-  out[(size_t)y0 * pitch + (size_t)x * C + ch] = (uint8_t)m;
+  ml_store<C>(out, gray, (size_t)y0 * W + x, ch, m, amask);
 
   for (int y = y0 + 1; y < y1; ++y) {
     const uint8_t* rold = img + (size_t)min(max(y - MB_R - 1, 0), H - 1) * pitch + (INTERIOR ? xo[0] : 0);
@@ -174,13 +188,14 @@ __device__ __forceinline__ void median11_lane_column(const uint8_t* __restrict__
       ltm += (vn[k] < m ? 1 : 0) - (vo[k] < m ? 1 : 0);
     }
     ml_walk(hb, m, ltm);
-    out[(size_t)y * pitch + (size_t)x * C + ch] = (uint8_t)m;
+    ml_store<C>(out, gray, (size_t)y * W + x, ch, m, amask);
   }
 }
 
 template <int C>
 __global__ void __launch_bounds__(ML_WARPS * 32)
-median11_lane_kernel(const uint8_t* __restrict__ src, int H, int W, int strip_rows, uint8_t* __restrict__ dst) {
+median11_lane_kernel(const uint8_t* __restrict__ src, int H, int W, int strip_rows, uint8_t* __restrict__ dst,
+                     uint8_t* __restrict__ gray_dst) {
   constexpr int COLS = 32 / C;                           // columns per warp: 10 for BGR, 32 for gray
   __shared__ uint32_t hist_all[ML_WARPS][256 * 8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -188,17 +203,19 @@ median11_lane_kernel(const uint8_t* __restrict__ src, int H, int W, int strip_ro
   if (x0 >= W) return;                                   // whole warps leave together; only __syncwarp below
   const int y0 = blockIdx.y * strip_rows, y1 = min(H, y0 + strip_rows);
   const uint8_t* img = src + (size_t)blockIdx.z * H * W * C;
-  uint8_t* out = dst + (size_t)blockIdx.z * H * W * C;
+  uint8_t* out = dst ? dst + (size_t)blockIdx.z * H * W * C : nullptr;
+  uint8_t* gray = gray_dst ? gray_dst + (size_t)blockIdx.z * H * W : nullptr;
   uint32_t* hw = hist_all[warp];
   for (int i = lane; i < 256 * 8; i += 32) hw[i] = 0u;
   __syncwarp();
   const int col = lane / C, ch = lane - col * C;
   const bool active = col < COLS && x0 + col < W;
+  const unsigned amask = __ballot_sync(0xFFFFFFFFu, active);
   if (!active) return;
   uint8_t* hb = (uint8_t*)(hw + lane);                   // this lane's words: hw[(b >> 2) * 32 + lane]
   // warp-uniform: every window column of every lane lies inside the image -> constant offsets between the 11 loads of a row
-  if (x0 - MB_R >= 0 && x0 + COLS - 1 + MB_R <= W - 1) median11_lane_column<C, true>(img, out, hb, H, W, x0 + col, ch, y0, y1);
-  else median11_lane_column<C, false>(img, out, hb, H, W, x0 + col, ch, y0, y1);
+  if (x0 - MB_R >= 0 && x0 + COLS - 1 + MB_R <= W - 1) median11_lane_column<C, true>(img, out, gray, amask, hb, H, W, x0 + col, ch, y0, y1);
+  else median11_lane_column<C, false>(img, out, gray, amask, hb, H, W, x0 + col, ch, y0, y1);
 }
 
 }  // namespace
@@ -221,9 +238,24 @@ extern "C" int sos_median_blur_11(sos_ctx* ctx, const uint8_t* src, int n_images
   } else {
     const int cols_per_block = ML_WARPS * (32 / channels);
     dim3 grid(sos_div_up(width, cols_per_block), sos_div_up(height, strip), n_images);
-    if (channels == 3) median11_lane_kernel<3><<<grid, ML_WARPS * 32, 0, ctx->stream>>>(src, height, width, strip, dst);
-    else median11_lane_kernel<1><<<grid, ML_WARPS * 32, 0, ctx->stream>>>(src, height, width, strip, dst);
+    if (channels == 3) median11_lane_kernel<3><<<grid, ML_WARPS * 32, 0, ctx->stream>>>(src, height, width, strip, dst, nullptr);
+    else median11_lane_kernel<1><<<grid, ML_WARPS * 32, 0, ctx->stream>>>(src, height, width, strip, dst, nullptr);
   }
+  SOS_LAUNCHED(ctx);
+  return SOS_OK;
+}
+
+extern "C" int sos_median_blur_11_gray(sos_ctx* ctx, const uint8_t* src, int n_images, int height, int width, uint8_t* dst_bgr,
+                                       uint8_t* gray) {
+  SOS_CHECK_ARG(ctx, "ctx is NULL");
+  SOS_CHECK_ARG(n_images >= 0 && height >= 0 && width >= 0, "negative size");
+  if (n_images == 0 || height == 0 || width == 0) return SOS_OK;
+  SOS_CHECK_ARG(src && gray && src != dst_bgr, "NULL array or in-place call");
+  SOS_CHECK_ARG(n_images <= 65535, "too many images");
+  SOS_CUDA(cudaSetDevice(ctx->device));
+  const int strip = 128;
+  dim3 grid(sos_div_up(width, ML_WARPS * (32 / 3)), sos_div_up(height, strip), n_images);
+  median11_lane_kernel<3><<<grid, ML_WARPS * 32, 0, ctx->stream>>>(src, height, width, strip, dst_bgr, gray);
   SOS_LAUNCHED(ctx);
   return SOS_OK;
 }

@@ -51,9 +51,7 @@ class FeatureFront:
         B, V, rows, cols, ch = pano.shape
         assert V == 2 and ch == 3
         imgs = pano.reshape(B * 2, rows, cols, 3)
-        if self.median:
-            imgs = ctx.median_blur_11(imgs)
-        gray = ctx.bgr_to_gray(imgs).reshape(B, 2, rows, cols)
+        gray = (ctx.median_blur_11_gray(imgs) if self.median else ctx.bgr_to_gray(imgs)).reshape(B, 2, rows, cols)
         out = []
         for view in range(2):
             g = gray[:, view].contiguous()

@@ -278,6 +278,18 @@ class Context:
         check(self.lib.sos_median_blur_11(self._h, self._t(x, torch.uint8, "img"), n, H, W, ch, out.data_ptr()))
         return out.reshape(img.shape)
 
+    def median_blur_11_gray(self, bgr: torch.Tensor, want_bgr: bool = False):
+        """cv2.cvtColor(cv2.medianBlur(bgr, 11), COLOR_BGR2GRAY) in one kernel: uint8 [n, H, W, 3] -> gray [n, H, W]
+        (and the blurred BGR image when want_bgr)."""
+        self._sync_stream()
+        n, H, W, ch = bgr.shape
+        assert ch == 3
+        gray = self.empty((n, H, W), torch.uint8)
+        out = self.empty((n, H, W, 3), torch.uint8) if want_bgr else None
+        check(self.lib.sos_median_blur_11_gray(self._h, self._t(bgr, torch.uint8, "bgr"), n, H, W,
+                                               out.data_ptr() if want_bgr else None, gray.data_ptr()))
+        return (gray, out) if want_bgr else gray
+
     def bgr_to_gray(self, bgr: torch.Tensor) -> torch.Tensor:
         """uint8 [..., 3] -> uint8 [...]  (cv2.COLOR_BGR2GRAY, bit-exact)."""
         self._sync_stream()
