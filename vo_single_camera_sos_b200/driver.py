@@ -11,6 +11,8 @@ reused.  The sequence of poses and keyframes is the one the sequential loop prod
 from __future__ import annotations
 
 import math
+import os
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass, field
 from typing import Iterable, List, Optional, Sequence
 
@@ -189,22 +191,36 @@ class BatchedVO:
             "boff_bot": ((c.batch, c.n_buckets + 1), torch.int32),
         }
         # pinned staging (one batch) + its device twin; frames are packed into the staging arrays on the host
-        self._pinned = {k: torch.zeros(shape, dtype=dt).pin_memory() for k, (shape, dt) in shapes.items()}
-        self._host = {k: v.numpy() for k, v in self._pinned.items()}
-        self._dev = {k: v.to(ctx.device) for k, v in self._pinned.items()}
+        # two sets, so that the next batch is packed while the current one is copied, tracked and resolved
+        self._pinned = [{k: torch.zeros(shape, dtype=dt).pin_memory() for k, (shape, dt) in shapes.items()} for _ in range(2)]
+        self._host = [{k: v.numpy() for k, v in p.items()} for p in self._pinned]
+        self._dev = [{k: v.to(ctx.device) for k, v in p.items()} for p in self._pinned]
+        self._pool = ThreadPoolExecutor(max_workers=max(1, min(16, len(os.sched_getaffinity(0)))))
+        self._prefetch = ThreadPoolExecutor(max_workers=1)
 
     def close(self):
+        self._prefetch.shutdown(wait=True)
+        self._pool.shutdown(wait=True)
         self.fe.close()
 
-    def _upload(self, frames: Sequence[dict]):
+    def _pack(self, frames: Sequence[dict], s: int):
+        """Frames into the pinned staging set s (host only)."""
         B = self.cfg.batch
-        for k in INPUT_KEYS:
-            h = self._host[k]
-            h[len(frames):] = 0            # unused slots: empty frames (no features -> no work after the remap)
-            for i, f in enumerate(frames):
-                h[i] = f[k]
-            self._dev[k].copy_(self._pinned[k], non_blocking=True)
         assert len(frames) <= B
+        host = self._host[s]
+
+        def pack(i):                        # numpy copies release the GIL
+            for k in INPUT_KEYS:
+                host[k][i] = frames[i][k]
+        # packing a batch of images is the driver's largest host cost (118 MB per 32 C1 frames): spread it over the cores
+        list(self._pool.map(pack, range(len(frames))))
+        if len(frames) < B:
+            for k in INPUT_KEYS:
+                host[k][len(frames):] = 0   # unused slots: empty frames (no features -> no work after the remap)
+
+    def _h2d(self, s: int):
+        for k in INPUT_KEYS:
+            self._dev[s][k].copy_(self._pinned[s][k], non_blocking=True)
 
     def _read(self):
         buf = self.fe.buffers()
@@ -220,14 +236,19 @@ class BatchedVO:
         res = state.result
         self.fe.reset()
         nxt = 0                                   # next frame to resolve
+        cur = 0                                   # staging set of the batch being resolved
+        packed = self._prefetch.submit(self._pack, frames[:B], cur)
         while nxt < len(frames) and res.status == "ok":
             chunk = frames[nxt:nxt + B]
-            self._upload(chunk)
+            packed.result()
+            self._h2d(cur)
+            if nxt + B < len(frames):             # pack the next batch meanwhile
+                packed = self._prefetch.submit(self._pack, frames[nxt + B:nxt + 2 * B], 1 - cur)
             first_batch = nxt == 0
             # slot i+1 holds chunk[i]; everything tracks against the keyframe in slot 0 — except in the very first
             # batch, where frame 0 IS the first keyframe (create_keyframe starts True, pose_est_tools.py:1406)
             self.fe.set_ref_slots([-1] + [1] * (B - 1) if first_batch else [0] * B)
-            self.fe.step(*[self._dev[k] for k in INPUT_KEYS])
+            self.fe.step(*[self._dev[cur][k] for k in INPUT_KEYS])
             res.device_steps += 1
             pose, stats, n_slots = self._read()
             i = 0
@@ -252,6 +273,8 @@ class BatchedVO:
                 elif became_key:
                     self.fe.promote(i)
             nxt += len(chunk)
+            cur = 1 - cur
+        packed.result()                           # a batch packed ahead of a tracking failure is simply dropped
         if est_poses_file is not None:
             for fid, T in zip(res.frame_ids, res.poses_wrt_S):
                 print(tum_line(fid, T), file=est_poses_file)
