@@ -218,6 +218,20 @@ class BatchedVO:
             for k in INPUT_KEYS:
                 host[k][len(frames):] = 0   # unused slots: empty frames (no features -> no work after the remap)
 
+    def _predict(self, i0: int, chain: bool, token: int):
+        """Reference slots for the pairs i0.. of the batch and what each assumes: ("key", token) = the keyframe as of now
+        (slot 0), ("chain", j) = chunk[j - 1] will be the keyframe when frame j is resolved (slot j)."""
+        B = self.cfg.batch
+        refs, assume = [-1] * i0, [None] * i0
+        for j in range(i0, B):
+            if chain and j > i0:
+                refs.append(j)
+                assume.append(("chain", j))
+            else:
+                refs.append(0)
+                assume.append(("key", token))
+        return refs, assume
+
     def _h2d(self, s: int):
         for k in INPUT_KEYS:
             self._dev[s][k].copy_(self._pinned[s][k], non_blocking=True)
@@ -237,6 +251,7 @@ class BatchedVO:
         self.fe.reset()
         nxt = 0                                   # next frame to resolve
         cur = 0                                   # staging set of the batch being resolved
+        chain = False                             # predict "every frame becomes a keyframe" for the next batch
         packed = self._prefetch.submit(self._pack, frames[:B], cur)
         while nxt < len(frames) and res.status == "ok":
             chunk = frames[nxt:nxt + B]
@@ -245,9 +260,17 @@ class BatchedVO:
             if nxt + B < len(frames):             # pack the next batch meanwhile
                 packed = self._prefetch.submit(self._pack, frames[nxt + B:nxt + 2 * B], 1 - cur)
             first_batch = nxt == 0
-            # slot i+1 holds chunk[i]; everything tracks against the keyframe in slot 0 — except in the very first
-            # batch, where frame 0 IS the first keyframe (create_keyframe starts True, pose_est_tools.py:1406)
-            self.fe.set_ref_slots([-1] + [1] * (B - 1) if first_batch else [0] * B)
+            # Slot i+1 holds chunk[i]; slot 0 holds the current keyframe.  Which frame a pair is tracked against is a
+            # PREDICTION of the keyframe decisions still to come: "no new keyframe" (reference = slot 0) or, when keyframes
+            # have been frequent, "the previous frame becomes the keyframe" (reference = slot i, the chain).  A pair whose
+            # prediction turns out wrong is re-tracked (stage B only) once the host knows better.  In the very first batch
+            # frame 0 IS the first keyframe (create_keyframe starts True, pose_est_tools.py:1406).
+            token, last_key = 0, -2                # keyframes created in this batch; chunk index of the newest one
+            if first_batch:
+                refs, assume = [-1] + [1] * (B - 1), [None] + [("key", 0)] * (B - 1)
+            else:
+                refs, assume = self._predict(0, chain, token)
+            self.fe.set_ref_slots(refs)
             self.fe.step(*[self._dev[cur][k] for k in INPUT_KEYS])
             res.device_steps += 1
             pose, stats, n_slots = self._read()
@@ -256,22 +279,23 @@ class BatchedVO:
                 state.first_frame(ids[0], int(n_slots[1]))
                 self.fe.promote(1)
                 i = 1
+            n_keys = 0
             while i < len(chunk):
+                if assume[i] != ("key", token) and assume[i] != ("chain", last_key + 1):
+                    refs, assume = self._predict(i, chain, token)
+                    self.fe.set_ref_slots(refs)
+                    self.fe.retrack()
+                    res.device_retracks += 1
+                    pose, stats, n_slots = self._read()
                 n_corr, inliers, best = int(stats[i, 1]), int(stats[i, 2]), int(stats[i, 3])
                 if n_corr < self.min_correspondences or best < 0:
                     res.status = f"tracking failed at frame {ids[nxt + i]}: {n_corr} point correspondences"
                     break
-                became_key = state.tracked_frame(ids[nxt + i], pose[i], inliers, int(n_slots[i + 1]))
+                if state.tracked_frame(ids[nxt + i], pose[i], inliers, int(n_slots[i + 1])):
+                    self.fe.promote(i + 1)         # chunk[i] is the keyframe now
+                    token, last_key, n_keys = token + 1, i, n_keys + 1
                 i += 1
-                if became_key and i < len(chunk):
-                    # frames after the new keyframe were tracked against the old one: promote it, re-run stage B for them
-                    self.fe.promote(i)
-                    self.fe.set_ref_slots([-1] * i + [0] * (B - i))
-                    self.fe.retrack()
-                    res.device_retracks += 1
-                    pose, stats, n_slots = self._read()
-                elif became_key:
-                    self.fe.promote(i)
+            chain = 2 * n_keys >= len(chunk)       # next batch: chain the pairs when keyframes were the rule
             nxt += len(chunk)
             cur = 1 - cur
         packed.result()                           # a batch packed ahead of a tracking failure is simply dropped
