@@ -27,8 +27,10 @@ def trimmed(fr, i):
                 px_bot=fr["px_bot"][i][:nb], desc_bot=fr["desc_bot"][i][:nb], boff_bot=fr["boff_bot"][i])
 
 
-@pytest.mark.parametrize("refine", ["arun", "lm"])
-def test_batched_vo_matches_sequential_oracle(ctx, refine):
+@pytest.mark.parametrize("refine,pos_min", [("arun", 0.06), ("lm", 0.06), ("arun", 0.004)])
+def test_batched_vo_matches_sequential_oracle(ctx, refine, pos_min):
+    """pos_min = 0.06: a keyframe every 2-3 frames (pairs predicted against the keyframe slot); pos_min = 0.004: every frame
+    becomes a keyframe, so from the second batch on the driver predicts the chain (previous frame = keyframe)."""
     from vo_single_camera_sos_b200 import ops, workload
     from vo_single_camera_sos_b200.driver import BatchedVO, KeyframePolicy, tum_line
     B, n_frames = 4, 15
@@ -37,13 +39,14 @@ def test_batched_vo_matches_sequential_oracle(ctx, refine):
     w.cfg.refit = ops.REFINE_LM if refine == "lm" else ops.REFINE_ARUN
     w.cfg.refine_iters = 60
     fr = workload.make_frames(w, 0, n_frames, render=False)
-    th = dict(odriver.INDOOR, pos_min=0.06)   # the synthetic trajectory moves 1-5 cm per frame: a keyframe every 2-3 frames
+    th = dict(odriver.INDOOR, pos_min=pos_min)   # the synthetic trajectory moves 1-5 cm per frame
     rig = np.zeros((2, 3, 4)); rig[:, :, :3] = np.eye(3); rig[0, :, 3] = w.rig.f_top; rig[1, :, 3] = w.rig.f_bot
     want = odriver.run_vo([trimmed(fr, i) for i in range(n_frames)],
                           (dict(w.rig.pano), w.rig.f_top, w.rig.f_bot, w.cfg.cap),
                           (w.hyp_host, "bearing", w.cfg.ransac_threshold, rig, 0.125 * 0.5 * w.cfg.pano_cols),
                           thresholds=th, refine=refine)
-    assert want["status"] == "ok" and 3 <= len(want["keyframe_ids"]) < n_frames
+    assert want["status"] == "ok" and 3 <= len(want["keyframe_ids"]) <= n_frames
+    assert (len(want["keyframe_ids"]) < n_frames) == (pos_min > 0.01)
     # the decisions the comparison relies on are not within rounding of a threshold
     for dist, ang, *_ in want["decisions"]:
         assert abs(dist - th["pos_min"]) > 1e-3 and abs(dist - th["pos_max"]) > 1e-3 and abs(ang - th["ang_max"]) > 1e-3
@@ -62,6 +65,8 @@ def test_batched_vo_matches_sequential_oracle(ctx, refine):
     assert res.tracked == want["tracked"]
     # every frame was resolved with at most one device step per batch + one stage-B re-run per in-batch keyframe
     assert res.device_steps == -(-n_frames // B) and res.device_retracks <= len(res.keyframe_ids)
+    if pos_min < 0.01:                               # chain prediction: only the first batch needs re-runs
+        assert res.device_retracks <= B
     # files: one TUM line per frame, one id per keyframe (pose_est_tools.py:1557, 1609-1612)
     lines = est.getvalue().strip().split("\n")
     assert len(lines) == n_frames and lines[3] == tum_line(3, res.poses_wrt_S[3])
