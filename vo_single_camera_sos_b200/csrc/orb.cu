@@ -43,37 +43,51 @@ struct Gauss7 {
   double k[7];
 };
 
-constexpr int BL_W = 64, BL_H = 16, BL_R = 3;
+constexpr int BL_ROWS = 32, BL_R = 3;
 
-// out = round_half_even(G * in), exact separable convolution in float64
-__global__ void __launch_bounds__(256) orb_blur_kernel(const uint8_t* __restrict__ in, int H, int W, Gauss7 g,
+// out = round_half_even(G * in), exact separable convolution in float64 (horizontal pass, then vertical, taps in order).
+// One thread per column walks down a strip of BL_ROWS rows with the horizontal sums of the last seven rows in registers; the
+// next row's seven taps are loaded one iteration ahead.  (First version: 64 x 16 tiles with the horizontal sums staged as
+// doubles in shared memory, 0.43 ms for 32 C2 panoramas.)
+__global__ void __launch_bounds__(128) orb_blur_kernel(const uint8_t* __restrict__ in, int H, int W, Gauss7 g,
                                                        uint8_t* __restrict__ out) {
-  __shared__ uint8_t tile[BL_H + 2 * BL_R][BL_W + 2 * BL_R + 2];
-  __shared__ double hrow[BL_H + 2 * BL_R][BL_W];
-  const int x0 = blockIdx.x * BL_W, y0 = blockIdx.y * BL_H;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= W) return;
+  const int y0 = blockIdx.y * BL_ROWS, y1 = min(H, y0 + BL_ROWS);
   const uint8_t* src = in + (size_t)blockIdx.z * H * W;
   uint8_t* dst = out + (size_t)blockIdx.z * H * W;
-  for (int i = threadIdx.x; i < (BL_H + 2 * BL_R) * (BL_W + 2 * BL_R); i += blockDim.x) {
-    const int r = i / (BL_W + 2 * BL_R), c = i % (BL_W + 2 * BL_R);
-    tile[r][c] = src[(size_t)reflect101(y0 + r - BL_R, H) * W + reflect101(x0 + c - BL_R, W)];
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < (BL_H + 2 * BL_R) * BL_W; i += blockDim.x) {
-    const int r = i / BL_W, c = i % BL_W;
+  int cx[7];
+#pragma unroll
+  for (int t = 0; t < 7; ++t) cx[t] = reflect101(x + t - BL_R, W);
+  uint8_t raw[7];
+  auto fetch = [&](int row) {
+    const uint8_t* r = src + (size_t)reflect101(row, H) * W;
+#pragma unroll
+    for (int t = 0; t < 7; ++t) raw[t] = __ldg(r + cx[t]);
+  };
+  auto hsum = [&]() {
     double s = 0.0;
 #pragma unroll
-    for (int t = 0; t < 7; ++t) s += g.k[t] * (double)tile[r][c + t];
-    hrow[r][c] = s;
+    for (int t = 0; t < 7; ++t) s += g.k[t] * (double)raw[t];
+    return s;
+  };
+  double h[7];
+#pragma unroll
+  for (int t = 0; t < 6; ++t) {
+    fetch(y0 - BL_R + t);
+    h[t] = hsum();
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < BL_H * BL_W; i += blockDim.x) {
-    const int r = i / BL_W, c = i % BL_W;
-    if (y0 + r >= H || x0 + c >= W) continue;
+  fetch(y0 + BL_R);
+  for (int y = y0; y < y1; ++y) {
+    h[6] = hsum();                                       // row y + 3
+    fetch(y + BL_R + 1);
     double s = 0.0;
 #pragma unroll
-    for (int t = 0; t < 7; ++t) s += g.k[t] * hrow[r + t][c];
+    for (int t = 0; t < 7; ++t) s += g.k[t] * h[t];
     const int v = __double2int_rn(s);
-    dst[(size_t)(y0 + r) * W + x0 + c] = (uint8_t)min(255, max(0, v));
+    dst[(size_t)y * W + x] = (uint8_t)min(255, max(0, v));
+#pragma unroll
+    for (int t = 0; t < 6; ++t) h[t] = h[t + 1];
   }
 }
 
@@ -171,10 +185,10 @@ extern "C" int sos_orb_blur(sos_ctx* ctx, const uint8_t* gray, int n_images, int
   SOS_CHECK_ARG(n_images >= 0 && height >= 0 && width >= 0, "negative size");
   if (n_images == 0 || height == 0 || width == 0) return SOS_OK;
   SOS_CHECK_ARG(gray && blurred && gray != blurred, "NULL array or in-place call");
-  SOS_CHECK_ARG(n_images <= 65535 && sos_div_up(height, BL_H) <= 65535, "too many images / rows");
+  SOS_CHECK_ARG(n_images <= 65535 && sos_div_up(height, BL_ROWS) <= 65535, "too many images / rows");
   SOS_CUDA(cudaSetDevice(ctx->device));
-  dim3 grid(sos_div_up(width, BL_W), sos_div_up(height, BL_H), n_images);
-  orb_blur_kernel<<<grid, 256, 0, ctx->stream>>>(gray, height, width, gauss_7_sigma2(), blurred);
+  dim3 grid(sos_div_up(width, 128), sos_div_up(height, BL_ROWS), n_images);
+  orb_blur_kernel<<<grid, 128, 0, ctx->stream>>>(gray, height, width, gauss_7_sigma2(), blurred);
   SOS_LAUNCHED(ctx);
   return SOS_OK;
 }
