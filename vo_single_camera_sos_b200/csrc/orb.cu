@@ -26,11 +26,27 @@ __constant__ int8_t c_orb_pattern[256 * 4] = {
 constexpr int ORB_EDGE = 31;
 
 // cv::cvtColor(BGR2GRAY) for 8-bit images in OpenCV 4.x: fixed point with 15 fractional bits (B 3735, G 19235, R 9798)
-__global__ void bgr2gray_kernel(const uint8_t* __restrict__ bgr, size_t n, uint8_t* __restrict__ gray) {
+__device__ __forceinline__ uint32_t gray_of(uint32_t b, uint32_t g, uint32_t r) {
+  return (b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15;
+}
+
+// four pixels per thread: three aligned 32-bit loads, one 32-bit store (the scalar form issued three strided byte loads per
+// pixel: 0.18 ms for 32 C2 panoramas)
+__global__ void bgr2gray_kernel(const uint8_t* __restrict__ bgr, size_t n, uint8_t* __restrict__ gray, int vec_ok) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t b = bgr[3 * i], g = bgr[3 * i + 1], r = bgr[3 * i + 2];
-  gray[i] = (uint8_t)((b * 3735u + g * 19235u + r * 9798u + 16384u) >> 15);
+  const size_t p = 4 * i;
+  if (p >= n) return;
+  if (vec_ok && p + 4 <= n) {
+    const uint32_t* w = (const uint32_t*)(bgr + 3 * p);
+    const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    const uint32_t g0 = gray_of(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u);
+    const uint32_t g1 = gray_of(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u);
+    const uint32_t g2 = gray_of((w1 >> 16) & 255u, w1 >> 24, w2 & 255u);
+    const uint32_t g3 = gray_of((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24);
+    *(uint32_t*)(gray + p) = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+  } else {
+    for (size_t q = p; q < n && q < p + 4; ++q) gray[q] = (uint8_t)gray_of(bgr[3 * q], bgr[3 * q + 1], bgr[3 * q + 2]);
+  }
 }
 
 __device__ __forceinline__ int reflect101(int p, int n) {
@@ -175,7 +191,9 @@ extern "C" int sos_bgr_to_gray(sos_ctx* ctx, const uint8_t* bgr, size_t n_pixels
   SOS_CHECK_ARG(bgr && gray, "NULL array");
   SOS_CHECK_ARG(n_pixels / 256 < (1ull << 31), "image too large");
   SOS_CUDA(cudaSetDevice(ctx->device));
-  bgr2gray_kernel<<<(unsigned)((n_pixels + 255) / 256), 256, 0, ctx->stream>>>(bgr, n_pixels, gray);
+  const int vec_ok = ((uintptr_t)bgr % 4 == 0) && ((uintptr_t)gray % 4 == 0);
+  const size_t n_thr = (n_pixels + 3) / 4;
+  bgr2gray_kernel<<<(unsigned)((n_thr + 255) / 256), 256, 0, ctx->stream>>>(bgr, n_pixels, gray, vec_ok);
   SOS_LAUNCHED(ctx);
   return SOS_OK;
 }

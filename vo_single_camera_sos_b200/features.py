@@ -51,7 +51,9 @@ class FeatureFront:
         B, V, rows, cols, ch = pano.shape
         assert V == 2 and ch == 3
         imgs = pano.reshape(B * 2, rows, cols, 3)
-        gray = (ctx.median_blur_11_gray(imgs) if self.median else ctx.bgr_to_gray(imgs)).reshape(B, 2, rows, cols)
+        if self.median:
+            imgs = ctx.median_blur_11(imgs)   # (median_blur_11_gray fuses the next call; measured 0.05 ms slower than the pair)
+        gray = ctx.bgr_to_gray(imgs).reshape(B, 2, rows, cols)
         out = []
         for view in range(2):
             g = gray[:, view].contiguous()
