@@ -76,21 +76,21 @@ __global__ void temporal_segments_kernel(const int32_t* __restrict__ n, const in
 }
 
 // Stack the temporal matches of both views into one correspondence list per frame pair (pose_est_tools.py:752-778).
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 assemble_kernel(const int32_t* __restrict__ m_q, const int32_t* __restrict__ m_t, const int32_t* __restrict__ m_count,
                 const int32_t* __restrict__ q_start, int B, int cap, const float* __restrict__ xyz,
                 const float* __restrict__ b_top, const float* __restrict__ b_bot, float* __restrict__ p_ref,
                 float* __restrict__ p_cur, float* __restrict__ f_cur, uint8_t* __restrict__ cam,
                 int32_t* __restrict__ n_corr, int32_t* __restrict__ n_corr_top) {
-  const int i = blockIdx.x;  // frame pair
+  const int i = blockIdx.y;  // frame pair; blockIdx.x: 256 rows of its list (one block per pair left 116 of 148 SMs idle)
   const int c_top = m_count[i], c_bot = m_count[B + i];
   const int total = c_top + c_bot;
-  if (threadIdx.x == 0) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     n_corr[i] = total;
     n_corr_top[i] = c_top;
   }
   const int cap2 = 2 * cap;
-  for (int k = threadIdx.x; k < total; k += blockDim.x) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
     const int view = k < c_top ? 0 : 1;
     const int s = view * B + i;
     const int kk = view == 0 ? k : k - c_top;
@@ -299,7 +299,7 @@ int enqueue_stage_b(sos_frontend* fe) {
                         d.tm_t_start, 2 * B, d.uv_c, d.uv_c, c.temporal_max_du, -1.0, d.tm_pair_q, d.tm_pair_t, d.tm_pair_d,
                         d.tm_pair_count);
   if (rc) return rc;
-  assemble_kernel<<<B, 1024, 0, ctx->stream>>>(d.tm_pair_q, d.tm_pair_t, d.tm_pair_count, d.tm_q_start, B, cap, d.xyz, d.b_top,
+  assemble_kernel<<<dim3(sos_div_up(2 * cap, 256), B), 256, 0, ctx->stream>>>(d.tm_pair_q, d.tm_pair_t, d.tm_pair_count, d.tm_q_start, B, cap, d.xyz, d.b_top,
                                               d.b_bot, d.p_ref, d.p_cur, d.f_cur, d.cam, d.n_corr, d.n_corr_top);
   SOS_LAUNCHED(ctx);
   // step 5
