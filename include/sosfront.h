@@ -452,13 +452,17 @@ typedef struct sos_frontend_buffers {
   int32_t* stats;                                  /* [batch, 4]: n_stereo, n_correspondences, n_inliers, best_hyp */
   double* refine_stats;                            /* [batch, 4] of sos_refine_pose (SOS_REFINE_LM only) */
   int32_t* ref_slot;                               /* [batch] reference slot of pair i (keyframe_mode only) */
+  int32_t* overflow;                               /* [batch] feature rows of frame i the capacity clamps dropped in the
+                                                      last step (bucket > max_feat_per_bucket, offsets > max_feat_per_view);
+                                                      0 everywhere unless the configuration is too small for the input */
   int32_t batch, cap, launches_per_step;
 } sos_frontend_buffers;
 
 typedef struct sos_frontend sos_frontend;
 
 /* lut [2, pano_rows, pano_cols] (top, bottom) and hyp [n_hyp, 3] are DEVICE arrays that must outlive the front-end.
- * The front-end binds to the context's CURRENT stream. */
+ * The front-end computes on a private stream; every call (step, submit_host, set_ref_slots, promote, retrack) is fenced
+ * with events against the stream the context holds AT THAT CALL (sos_ctx_set_stream), so callers see plain stream order. */
 int sos_frontend_create(sos_ctx* ctx, const sos_frontend_config* cfg, const sos_lut_entry* lut, const uint32_t* hyp,
                         sos_frontend** out);
 int sos_frontend_destroy(sos_frontend* fe);

@@ -60,6 +60,20 @@ def filter_pixel_correspondences(pts_top, pts_bot, min_rectified_disparity, max_
     return ok
 
 
+def knn2_flat_sorted(q, t):
+    """FeatureMatcher.match with k_best = 2 on binary descriptors (camera_models.py:417-444): knnMatch(k=2) flattened
+    query by query — BOTH neighbours kept, the Lowe test applies to SIFT only — then sorted(key=distance), which is
+    stable: ties keep the (query index, neighbour rank) order.  Returns (query_idx, train_idx, distance)."""
+    i0, d0, i1, d1 = knn2(q, t)
+    qi = np.repeat(np.arange(q.shape[0], dtype=np.int32), 2)
+    ti = np.stack([i0, i1], 1).reshape(-1)
+    dd = np.stack([d0, d1], 1).reshape(-1)
+    have = ti >= 0
+    qi, ti, dd = qi[have], ti[have], dd[have]
+    order = np.argsort(dd, kind="stable")
+    return qi[order], ti[order], dd[order]
+
+
 def match_select(q, t, mode="nn", ratio=0.75, px_q=None, px_t=None, max_du=-1.0, min_dv=-1.0):
     """FeatureMatcher.match (camera_models.py:404-446) + the gate its callers apply (camera_models.py:3086,
     pose_est_tools.py:245-247), for one (query, train) segment.

@@ -157,8 +157,15 @@ def test_frontend_two_steps_stage_by_stage(ctx, mode, graph):
     fe.close()
 
 
-def test_frontend_host_api_matches_device_api(ctx):
+@pytest.mark.parametrize("upload", ["bands", "full"])
+def test_frontend_host_api_matches_device_api(ctx, upload, monkeypatch):
+    """Host-buffer API against the device API.  `bands` uploads only the LUT-reachable row spans of each omni image (the
+    default), `full` the whole images (SOS_FULL_UPLOAD=1, read when the staging buffers are first built)."""
     from vo_single_camera_sos_b200 import workload
+    if upload == "full":
+        monkeypatch.setenv("SOS_FULL_UPLOAD", "1")
+    else:
+        monkeypatch.delenv("SOS_FULL_UPLOAD", raising=False)
     B = 2
     w = workload.build(ctx, "tiny", batch=B, n_frames=3 * B, seed=5)
     fe_dev, fe_host = w.frontend(ctx), w.frontend(ctx)
@@ -180,7 +187,52 @@ def test_frontend_host_api_matches_device_api(ctx):
         assert np.array_equal(p, rp, equal_nan=True)
     with pytest.raises(Exception):
         fe_host.wait_host(t0)  # ticket already consumed
+    h2d, d2h = fe_host.host_bytes()
+    full = B * w.cfg.src_h * w.cfg.src_w * 3
+    assert (h2d > full) if upload == "full" else (h2d < full + B * w.cfg.max_feat_per_view * 2 * 40 + 4096)
     fe_dev.close(); fe_host.close()
+
+
+def test_frontend_oversized_bucket_is_clamped_and_reported(ctx):
+    """A bucket with more features than max_feat_per_bucket: the device path clamps the query side of that segment, counts
+    what it dropped in buffers()["overflow"], and every other stage stays consistent with the clamped segment (no stale
+    scratch is read: pair lists of the other buckets equal the oracle's); the host path refuses the offsets."""
+    from vo_single_camera_sos_b200 import workload
+    B = 2
+    w = workload.build(ctx, "tiny", batch=B, n_frames=B, seed=8)
+    fr = workload.make_frames(w, 0, B, render=False)
+    cfg = w.cfg
+    nb, F, cap_b = cfg.n_buckets, cfg.max_feat_per_view, cfg.max_feat_per_bucket
+    # merge all buckets of frame 0 / bottom view into bucket 0 (and of the top view too, so that matches exist)
+    total_bot, total_top = int(fr["boff_bot"][0, -1]), int(fr["boff_top"][0, -1])
+    assert total_bot > cap_b
+    fr["boff_bot"][0, 1:] = total_bot
+    fr["boff_top"][0, 1:] = total_top
+    fe = w.frontend(ctx)
+    fe.step(*workload.to_device(ctx, fr))
+    torch.cuda.synchronize()
+    buf = host(fe.buffers())
+    assert total_top > cap_b
+    assert buf["overflow"][0] == (total_bot - cap_b) + (total_top - cap_b) and buf["overflow"][1] == 0
+    assert buf["st_q_len"][0] == cap_b and buf["st_t_len"][0] == cap_b
+    qi, ti, dd = hamming.match_select(fr["desc_bot"][0, :cap_b], fr["desc_top"][0, :cap_b], "nn",
+                                      px_q=fr["px_bot"][0, :cap_b], px_t=fr["px_top"][0, :cap_b], max_du=2.5, min_dv=1.0)
+    cnt = int(buf["st_pair_count"][0])
+    assert cnt == len(qi)
+    assert np.array_equal(buf["st_pair_q"][:cnt], qi) and np.array_equal(buf["st_pair_t"][:cnt], ti)
+    assert not buf["st_pair_count"][1:nb].any()
+    # frame 1 is untouched by frame 0's overflow
+    for k in range(nb):
+        q0, q1 = fr["boff_bot"][1, k], fr["boff_bot"][1, k + 1]
+        t0, t1 = fr["boff_top"][1, k], fr["boff_top"][1, k + 1]
+        qi, ti, dd = hamming.match_select(fr["desc_bot"][1, q0:q1], fr["desc_top"][1, t0:t1], "nn",
+                                          px_q=fr["px_bot"][1, q0:q1], px_t=fr["px_top"][1, t0:t1], max_du=2.5, min_dv=1.0)
+        s_ = nb + k
+        assert buf["st_pair_count"][s_] == len(qi)
+    assert buf["n"][1] <= cnt and buf["n"][2] > 0
+    with pytest.raises(ValueError):
+        fe.step_host(*workload.to_pinned(fr))
+    fe.close()
 
 
 def test_frontend_rejects_bad_inputs(ctx):

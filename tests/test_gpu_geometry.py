@@ -131,7 +131,8 @@ def test_lut_build_golden(ctx):
         ru, rv = g[f"map_x64_sub_{name}"], g[f"map_y64_sub_{name}"]
         assert np.array_equal(np.isnan(su), np.isnan(ru))
         ok = ~np.isnan(ru)
-        assert np.max(np.abs(su[ok] - ru[ok])) < 1 / 64 and np.max(np.abs(sv[ok] - rv[ok])) < 1 / 64
+        # bar: 1e-4 px (the kernel works in float64: measured 2e-5 px), far inside the 1/64 px that could move a Q5 LUT entry
+        assert np.max(np.abs(su[ok] - ru[ok])) < 1e-4 and np.max(np.abs(sv[ok] - rv[ok])) < 1e-4
 
 
 def test_rgbd_golden(ctx):

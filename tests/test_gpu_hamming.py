@@ -17,6 +17,15 @@ def dev(a, dtype=None):
     return t.cuda()
 
 
+@pytest.fixture(autouse=True, params=["popc", "mma"])
+def hamming_engine(request, monkeypatch):
+    """Every test of this file runs on both engines of sos_hamming_top2: XOR + POPC on the integer pipe and the int8
+    tensor-core engine (csrc/hamming_mma.cu).  The library reads SOS_HAMMING_ENGINE per call; without it the engine is
+    chosen by problem size."""
+    monkeypatch.setenv("SOS_HAMMING_ENGINE", request.param)
+    return request.param
+
+
 def run_top2(ctx, qs, ts):
     """qs, ts: lists of [n,32] uint8 arrays, one per segment."""
     seg_q = np.concatenate([[0], np.cumsum([len(x) for x in qs])]).astype(np.int32)
@@ -64,6 +73,40 @@ def test_ragged_segments_with_empty_ones(ctx):
         qs.append(q); ts.append(t)
     res, seg_q, _, _, _ = run_top2(ctx, qs, ts)
     check_segments(res, seg_q, qs, ts)
+
+
+def test_nearest_only_path_many_tiles_and_ties(ctx):
+    """want_second=False (the front-end's default 1-NN path) over several 128-row train tiles per segment, with exact
+    duplicates of the best match planted in LATER tiles: the lowest train index must win (cv2.BFMatcher)."""
+    rng = np.random.default_rng(5)
+    qs, ts = [], []
+    for nq, nt in [(700, 900), (130, 513), (257, 128), (5, 1300)]:
+        q, t = make_descriptors(rng, max(nq, nt) + 40, nq, nt, n_ties=6)
+        i0 = hamming.knn2(q, t)[0]
+        for k in range(0, min(nq, 40), 3):                    # copy the winner of query k to a later train row
+            later = int(rng.integers(i0[k] + 1, nt)) if i0[k] + 1 < nt else None
+            if later is not None:
+                t[later] = t[i0[k]]
+        qs.append(q); ts.append(t)
+    seg_q = np.concatenate([[0], np.cumsum([len(x) for x in qs])]).astype(np.int32)
+    seg_t = np.concatenate([[0], np.cumsum([len(x) for x in ts])]).astype(np.int32)
+    i0, d0, i1, d1 = ctx.hamming_top2(dev(np.concatenate(qs)), dev(np.concatenate(ts)), dev(seg_q[:-1]), dev(np.diff(seg_q)),
+                                      dev(seg_t[:-1]), dev(np.diff(seg_t)), 700, 1300, want_second=False)
+    assert i1 is None and d1 is None
+    i0, d0 = i0.cpu().numpy(), d0.cpu().numpy()
+    for s, (q, t) in enumerate(zip(qs, ts)):
+        oi0, od0, _, _ = hamming.knn2(q, t)
+        assert np.array_equal(i0[seg_q[s]:seg_q[s + 1]], oi0) and np.array_equal(d0[seg_q[s]:seg_q[s + 1]], od0)
+
+
+def test_train_rows_beyond_max_nt_are_ignored(ctx):
+    """t_len[s] > max_nt: both engines clamp the train range to max_nt rows (the bound the scratch is sized for)."""
+    rng = np.random.default_rng(6)
+    q, t = make_descriptors(rng, 700, 300, 640, n_ties=3)
+    z = dev(np.zeros(1, np.int32))
+    i0, d0, i1, d1 = ctx.hamming_top2(dev(q), dev(t), z, dev(np.array([300], np.int32)), z, dev(np.array([640], np.int32)), 300, 512)
+    oi0, od0, oi1, od1 = hamming.knn2(q, t[:512])
+    assert np.array_equal(i0.cpu().numpy(), oi0) and np.array_equal(d1.cpu().numpy(), od1)
 
 
 def test_all_equal_descriptors_tie_break(ctx):

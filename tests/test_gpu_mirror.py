@@ -94,7 +94,26 @@ def test_feature_matcher_match(ctx):
     assert np.array_equal(qi[order], g["cross_q"]) and np.array_equal(ti[order], g["cross_t"])
     assert FeatureMatcher("ORB", "BF", 1).match(np.zeros((0, 32), np.uint8), g["t"]) == []
     with pytest.raises(NotImplementedError):
-        FeatureMatcher("SIFT", "BF", 2)
+        FeatureMatcher("ORB", "BF", 3)
+
+
+def test_feature_matcher_k_best_2_on_binary_descriptors(ctx):
+    """camera_models.py:417-444: for ORB the k_best = 2 branch keeps BOTH neighbours of every query (the Lowe ratio test
+    is SIFT-only), flattens query by query and sorts stably by distance.  Golden from the reference's own class."""
+    from omnistereo.camera_models import FeatureMatcher
+    g = load_golden("hamming.npz")
+    m = FeatureMatcher("ORB", "BF", 2).match(query_descriptors=g["q"], train_descriptors=g["t"])
+    assert len(m) == 2 * len(g["q"])
+    assert [x.queryIdx for x in m] == g["k2_q"].tolist() and [x.trainIdx for x in m] == g["k2_t"].tolist()
+    assert [x.distance for x in m] == g["k2_d"].tolist()
+    # a single train row gives one neighbour per query
+    m1 = FeatureMatcher("ORB", "BF", 2).match(query_descriptors=g["q"][:5], train_descriptors=g["t"][:1])
+    assert len(m1) == 5 and all(x.trainIdx == 0 for x in m1)
+    # the explicit (non-reference) ratio kwarg still selects the Lowe test on the device
+    from oracle import hamming
+    qi, ti, dd = FeatureMatcher("ORB", "BF", 2, ratio=0.75).match_arrays(g["q"], g["t"])
+    oq, ot, od = hamming.match_select(g["q"], g["t"], "ratio", ratio=0.75)
+    assert np.array_equal(qi, oq) and np.array_equal(ti, ot) and np.array_equal(dd, od)
 
 
 def test_stereo_and_temporal_matching(gums):

@@ -13,6 +13,17 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
+@pytest.fixture(autouse=True, params=["patch", "tma"])
+def remap_variant(request, monkeypatch):
+    """Every test of this file runs against both 3-channel kernels the library ships: the per-frame patch kernel (default)
+    and the batch-looped kernel with TMA-staged LUT tiles (SOS_REMAP_TMA=1; csrc/remap.cu reads the switch per call)."""
+    if request.param == "tma":
+        monkeypatch.setenv("SOS_REMAP_TMA", "1")
+    else:
+        monkeypatch.delenv("SOS_REMAP_TMA", raising=False)
+    return request.param
+
+
 def test_golden_panoramas(ctx):
     g = load_golden("remap.npz")
     img = dev(g["img"][None])
@@ -81,7 +92,8 @@ def test_full_size_c2_against_cv2(ctx):
     r = np.hypot(xx - p["u_center"], yy - p["v_center"])
     mask = ((r < 0.48 * H) & (r > 0.2 * H)).astype(np.uint8) * 255
     lut = ctx.lut_pack(mx, my, (H, W), mask=dev(mask))
-    out = ctx.remap(dev(img[None]), lut).cpu().numpy()[0, 0]
+    out = ctx.remap(dev(np.stack([img, img[::-1].copy()])), lut).cpu().numpy()
     ref = remap.remap_reference(remap.masked_image(img, mask), mxh, myh)
-    assert np.array_equal(out, ref)
-    assert (out > 0).mean() > 0.2
+    assert np.array_equal(out[0, 0], ref)
+    assert np.array_equal(out[1, 0], remap.remap_reference(remap.masked_image(img[::-1].copy(), mask), mxh, myh))
+    assert (out[0, 0] > 0).mean() > 0.2

@@ -67,6 +67,10 @@ def test_hamming_oracle_matches_bfmatcher():
     order = np.argsort(cq, kind="stable")
     assert np.array_equal(cq[order], g["cross_q"]) and np.array_equal(ct[order], g["cross_t"])
     assert np.array_equal(cd[order], g["cross_d"].astype(np.int32))
+    # k_best = 2 on ORB descriptors: both neighbours, flattened and stably sorted (camera_models.py:417-444)
+    kq, kt, kd = hamming.knn2_flat_sorted(q, t)
+    assert len(kq) == 2 * len(q)
+    assert np.array_equal(kq, g["k2_q"]) and np.array_equal(kt, g["k2_t"]) and np.array_equal(kd, g["k2_d"].astype(np.int32))
     # and against live OpenCV
     rq, rt, rd = hamming.bf_match_reference(q, t)
     assert np.array_equal(i0, rt) and np.array_equal(d0, rd.astype(np.int32))

@@ -29,18 +29,31 @@ struct Buf {
   size_t bytes = 0;
 };
 
+// One thread per frame: the (query = bottom, train = top) segment of every azimuthal bucket.  Offsets are clamped to the
+// frame's feature capacity F and a bucket's rows to max_bucket (the per-segment capacity of the matching scratch and of
+// the candidate-pair arrays); what the clamps drop is counted in overflow[b] so that the caller can see it (the
+// reference has no such cap: size max_feat_per_bucket for the detector's per-bucket budget, pose_est_tools.py:862).
 __global__ void stereo_segments_kernel(const int32_t* __restrict__ boff_top, const int32_t* __restrict__ boff_bot, int B,
-                                       int nb, int F, int32_t* __restrict__ q_start, int32_t* __restrict__ q_len,
-                                       int32_t* __restrict__ t_start, int32_t* __restrict__ t_len) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= B * nb) return;
-  const int b = s / nb, k = s % nb;
+                                       int nb, int F, int max_bucket, int32_t* __restrict__ q_start,
+                                       int32_t* __restrict__ q_len, int32_t* __restrict__ t_start,
+                                       int32_t* __restrict__ t_len, int32_t* __restrict__ overflow) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
   const int32_t* ot = boff_top + (size_t)b * (nb + 1);
   const int32_t* ob = boff_bot + (size_t)b * (nb + 1);
-  q_start[s] = b * F + ob[k];  // bottom view = query (camera_models.py:3042)
-  q_len[s] = max(0, ob[k + 1] - ob[k]);
-  t_start[s] = b * F + ot[k];  // top view = train
-  t_len[s] = max(0, ot[k + 1] - ot[k]);
+  int dropped = 0;
+  for (int k = 0; k < nb; ++k) {
+    const int s = b * nb + k;
+    const int q0 = min(max(ob[k], 0), F), q1 = min(max(ob[k + 1], q0), F);
+    const int t0 = min(max(ot[k], 0), F), t1 = min(max(ot[k + 1], t0), F);
+    const int nq = min(q1 - q0, max_bucket), nt = min(t1 - t0, max_bucket);
+    dropped += max(0, ob[k + 1] - ob[k]) - nq + max(0, ot[k + 1] - ot[k]) - nt;
+    q_start[s] = b * F + q0;  // bottom view = query (camera_models.py:3042)
+    q_len[s] = nq;
+    t_start[s] = b * F + t0;  // top view = train
+    t_len[s] = nt;
+  }
+  overflow[b] = dropped;
 }
 
 // desc_c[(view*(B+1) + slot)*cap + k] = desc_view[src_view[slot*cap + k]] for the B new slots (1..B)
@@ -191,11 +204,6 @@ struct sos_frontend {
   std::vector<Band> bands;
   int64_t omni_bytes_per_frame = 0;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;  // fences against the caller's stream
-  // the remap feeds nothing else in the chain (features are inputs): it runs on a side stream, forked and joined with
-  // events, so that inside the captured graph it is a parallel branch next to the matching / RANSAC chain
-  cudaStream_t side_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  bool overlap_remap = false, remap_forked = false;
   int next_stage = 0;
   // graph cache keyed on the input pointers
   struct GraphKey {
@@ -234,27 +242,16 @@ int enqueue_stage_a(sos_frontend* fe, const uint8_t* omni, const float* px_top, 
   sos_frontend_buffers& d = fe->d;
   const int B = c.batch, nb = c.n_buckets, F = c.max_feat_per_view, cap = c.cap;
   int rc;
-  // step 1
-  if (fe->overlap_remap && !ctx->prof) {
-    cudaStream_t main_stream = ctx->stream;
-    SOS_CUDA(cudaEventRecord(fe->ev_fork, main_stream));
-    SOS_CUDA(cudaStreamWaitEvent(fe->side_stream, fe->ev_fork, 0));
-    ctx->stream = fe->side_stream;
-    rc = sos_remap_u8(ctx, omni, B, c.src_h, c.src_w, c.channels, fe->lut, 2, c.pano_rows, c.pano_cols, c.border,
-                      c.background, d.pano);
-    ctx->stream = main_stream;
-    if (rc) return rc;
-    SOS_CUDA(cudaEventRecord(fe->ev_join, fe->side_stream));
-    fe->remap_forked = true;
-  } else {
-    rc = sos_remap_u8(ctx, omni, B, c.src_h, c.src_w, c.channels, fe->lut, 2, c.pano_rows, c.pano_cols, c.border,
-                      c.background, d.pano);
-    if (rc) return rc;
-  }
+  // step 1 (running the remap as a parallel graph branch next to the matching chain was measured in round 1: no gain,
+  // both branches are issue-bound and fill the GPU — removed)
+  rc = sos_remap_u8(ctx, omni, B, c.src_h, c.src_w, c.channels, fe->lut, 2, c.pano_rows, c.pano_cols, c.border,
+                    c.background, d.pano);
+  if (rc) return rc;
   // step 2a: stereo matching per bucket
   const int S = B * nb;
-  stereo_segments_kernel<<<sos_div_up(S, 128), 128, 0, ctx->stream>>>(boff_top, boff_bot, B, nb, F, d.st_q_start, d.st_q_len,
-                                                                       d.st_t_start, d.st_t_len);
+  stereo_segments_kernel<<<sos_div_up(B, 128), 128, 0, ctx->stream>>>(boff_top, boff_bot, B, nb, F, c.max_feat_per_bucket,
+                                                                       d.st_q_start, d.st_q_len, d.st_t_start, d.st_t_len,
+                                                                       d.overflow);
   SOS_LAUNCHED(ctx);
   rc = sos_hamming_top2(ctx, desc_bot, desc_top, d.st_q_start, d.st_q_len, d.st_t_start, d.st_t_len, S,
                         c.max_feat_per_bucket, c.max_feat_per_bucket, d.st_idx0, d.st_d0, nullptr, nullptr);
@@ -341,10 +338,6 @@ int enqueue_step(sos_frontend* fe, const uint8_t* omni, const float* px_top, con
   int rc = enqueue_stage_a(fe, omni, px_top, desc_top, boff_top, px_bot, desc_bot, boff_bot);
   if (rc == SOS_OK) rc = enqueue_stage_b(fe);
   if (rc == SOS_OK && !fe->cfg.keyframe_mode) rc = enqueue_carry(fe, fe->cfg.batch);
-  if (fe->remap_forked) {   // join the remap branch (also on the error path: an open fork would break a graph capture)
-    fe->remap_forked = false;
-    SOS_CUDA(cudaStreamWaitEvent(fe->ctx->stream, fe->ev_join, 0));
-  }
   return rc;
 }
 
@@ -406,22 +399,26 @@ extern "C" int sos_frontend_create(sos_ctx* ctx, const sos_frontend_config* cfg,
   SOS_CHECK_ARG(cfg->solver != SOS_SOLVER_P3P || cfg->score_mode == SOS_SCORE_BEARING, "the bearing-only solver scores bearings");
   SOS_CUDA(cudaSetDevice(ctx->device));
   sos_frontend* fe = new sos_frontend();
-  // private context: same device and stream, but its own scratch arena — the arena address is baked into the captured
-  // graphs, so no other caller may regrow it
+  // private context: same device, but its own scratch arena — the arena address is baked into the captured graphs, so
+  // no other caller may regrow it
   fe->ctx = new sos_ctx();
   fe->ctx->device = ctx->device;
+  // every failure below goes through sos_frontend_destroy (streams, events, allocations made so far)
+#define FE_CUDA(call)                                                                               \
+  do {                                                                                              \
+    cudaError_t e__ = (call);                                                                       \
+    if (e__ != cudaSuccess) {                                                                       \
+      sos_set_error("sos_frontend_create: %s failed: %s", #call, cudaGetErrorString(e__));          \
+      sos_frontend_destroy(fe);                                                                     \
+      return SOS_ERR_CUDA;                                                                          \
+    }                                                                                               \
+  } while (0)
   // ... and its own compute stream (the caller's may be the legacy default stream, which cannot be captured); every
   // step is fenced against the caller's current stream with events, so the caller sees ordinary stream semantics
-  SOS_CUDA(cudaStreamCreateWithFlags(&fe->ctx->stream, cudaStreamNonBlocking));
+  FE_CUDA(cudaStreamCreateWithFlags(&fe->ctx->stream, cudaStreamNonBlocking));
   fe->ctx->own_stream = true;
-  SOS_CUDA(cudaEventCreateWithFlags(&fe->ev_in, cudaEventDisableTiming));
-  SOS_CUDA(cudaEventCreateWithFlags(&fe->ev_out, cudaEventDisableTiming));
-  SOS_CUDA(cudaStreamCreateWithFlags(&fe->side_stream, cudaStreamNonBlocking));
-  SOS_CUDA(cudaEventCreateWithFlags(&fe->ev_fork, cudaEventDisableTiming));
-  SOS_CUDA(cudaEventCreateWithFlags(&fe->ev_join, cudaEventDisableTiming));
-  // measured at C2: no gain (1.8825 vs 1.8888 ms per step) — both the remap and the Hamming kernel are issue-bound and
-  // fill the GPU, so the branches serialise at block scheduling; kept as an A/B switch, off by default
-  fe->overlap_remap = getenv("SOS_REMAP_OVERLAP") != nullptr;
+  FE_CUDA(cudaEventCreateWithFlags(&fe->ev_in, cudaEventDisableTiming));
+  FE_CUDA(cudaEventCreateWithFlags(&fe->ev_out, cudaEventDisableTiming));
   fe->ctx->sm_count = ctx->sm_count;
   fe->parent = ctx;
   fe->cfg = *cfg;
@@ -452,7 +449,7 @@ extern "C" int sos_frontend_create(sos_ctx* ctx, const sos_frontend_config* cfg,
   FE_ALLOC(p_ref, B * 2 * cap * 3); FE_ALLOC(p_cur, B * 2 * cap * 3); FE_ALLOC(f_cur, B * 2 * cap * 3);
   FE_ALLOC(cam, B * 2 * cap); FE_ALLOC(n_corr, B); FE_ALLOC(n_corr_top, B);
   FE_ALLOC(ransac_pose, B * 12); FE_ALLOC(pose, B * 12); FE_ALLOC(best_hyp, B); FE_ALLOC(best_count, B);
-  FE_ALLOC(n_refit, B); FE_ALLOC(inlier_mask, B * 2 * cap); FE_ALLOC(stats, B * 4); FE_ALLOC(refine_stats, B * 4); FE_ALLOC(ref_slot, B);
+  FE_ALLOC(n_refit, B); FE_ALLOC(inlier_mask, B * 2 * cap); FE_ALLOC(stats, B * 4); FE_ALLOC(refine_stats, B * 4); FE_ALLOC(ref_slot, B); FE_ALLOC(overflow, B);
 #undef FE_ALLOC
   if (rc != SOS_OK) {
     sos_frontend_destroy(fe);
@@ -460,7 +457,10 @@ extern "C" int sos_frontend_create(sos_ctx* ctx, const sos_frontend_config* cfg,
   }
   d.batch = c.batch;
   d.cap = c.cap;
-  SOS_CUDA(cudaStreamSynchronize(ctx->stream));
+  // the zero fills above were queued on the private stream: finish them before anybody can look at the buffers
+  FE_CUDA(cudaStreamSynchronize(fe->ctx->stream));
+  FE_CUDA(cudaStreamSynchronize(ctx->stream));
+#undef FE_CUDA
   *out = fe;
   return SOS_OK;
 }
@@ -468,7 +468,7 @@ extern "C" int sos_frontend_create(sos_ctx* ctx, const sos_frontend_config* cfg,
 extern "C" int sos_frontend_destroy(sos_frontend* fe) {
   if (!fe) return SOS_OK;
   cudaSetDevice(fe->ctx->device);
-  cudaStreamSynchronize(fe->ctx->stream);
+  if (fe->ctx->stream) cudaStreamSynchronize(fe->ctx->stream);
   if (fe->copy_stream) cudaStreamSynchronize(fe->copy_stream);
   for (auto& g : fe->graphs) cudaGraphExecDestroy(g.exec);
   for (void* p : fe->owned) cudaFree(p);
@@ -481,9 +481,6 @@ extern "C" int sos_frontend_destroy(sos_frontend* fe) {
   if (fe->copy_stream) cudaStreamDestroy(fe->copy_stream);
   if (fe->ev_in) cudaEventDestroy(fe->ev_in);
   if (fe->ev_out) cudaEventDestroy(fe->ev_out);
-  if (fe->side_stream) { cudaStreamSynchronize(fe->side_stream); cudaStreamDestroy(fe->side_stream); }
-  if (fe->ev_fork) cudaEventDestroy(fe->ev_fork);
-  if (fe->ev_join) cudaEventDestroy(fe->ev_join);
   if (fe->ctx->own_stream && fe->ctx->stream) cudaStreamDestroy(fe->ctx->stream);
   if (fe->ctx->arena) cudaFree(fe->ctx->arena);
   delete fe->ctx;

@@ -16,6 +16,13 @@
 
 #include "sos_common.cuh"
 
+// tensor-core engine (hamming_mma.cu)
+size_t sos_hamming_mma_scratch_bytes(int n_seg, int max_nq, int max_nt);
+int sos_hamming_mma_launch(sos_ctx* ctx, const uint32_t* q, const uint32_t* t, const int32_t* q_start, const int32_t* q_len,
+                           const int32_t* t_start, const int32_t* t_len, int n_seg, int max_nq, int max_nt, int splits,
+                           const uint32_t* items, const int32_t* n_items, unsigned max_items, bool top2, void* exp,
+                           uint2* partial);
+
 namespace {
 
 constexpr int HB_THREADS = 128;  // threads per block
@@ -34,43 +41,21 @@ __device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t
   asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(carry) : "r"(a), "r"(b), "r"(c));
 }
 
-// Packed key (distance << KEY_IDX_BITS) + tj of one descriptor pair.
-//   VARIANT 0: 8 POPC + adds                      (POPC = XU pipe, 16 lanes/clk/SM: the narrow pipe)
-//   VARIANT 1: three carry-save adders first, 5 POPC: moves work from the XU pipe to the 4x wider ALU pipe; the
-//              weighted sum and the key are formed by IMADs on the FMA pipe
-//   VARIANT 2: full Harley-Seal tree, 4 POPC
-template <int VARIANT>
+// Packed key (distance << KEY_IDX_BITS) + tj of one descriptor pair.  Three carry-save adders first, then 5 POPC instead
+// of 8: moves work from the XU pipe (POPC, 16 lanes/clk/SM: the narrow pipe) to the 4x wider ALU pipe; the weighted sum
+// and the key are formed by IMADs on the FMA pipe.  (Measured against plain 8 x POPC and a full Harley-Seal tree with
+// 4 POPC in round 1: this one is the fastest, profiles/r01/.)
 __device__ __forceinline__ uint32_t hamming_key(const uint4& qa, const uint4& qb, const uint4& ta, const uint4& tb,
                                                 uint32_t tj) {
   const uint32_t x0 = qa.x ^ ta.x, x1 = qa.y ^ ta.y, x2 = qa.z ^ ta.z, x3 = qa.w ^ ta.w;
   const uint32_t x4 = qb.x ^ tb.x, x5 = qb.y ^ tb.y, x6 = qb.z ^ tb.z, x7 = qb.w ^ tb.w;
-  if (VARIANT == 0) {
-    const uint32_t s0 = __popc(x0) + __popc(x1) + __popc(x2);
-    const uint32_t s1 = __popc(x3) + __popc(x4) + __popc(x5);
-    const uint32_t s2 = __popc(x6) + __popc(x7) + s0;
-    return ((s1 + s2) << KEY_IDX_BITS) | tj;
-  } else if (VARIANT == 1) {
-    uint32_t s1, c1, s2, c2, s3, c3;
-    csa(x0, x1, x2, s1, c1);
-    csa(x3, x4, x5, s2, c2);
-    csa(s1, s2, x6, s3, c3);
-    const uint32_t ones = __popc(s3) + __popc(x7);
-    const uint32_t twos = __popc(c1) + __popc(c2) + __popc(c3);
-    return twos * (2u << KEY_IDX_BITS) + (ones * (1u << KEY_IDX_BITS) + tj);
-  } else {
-    uint32_t s1, c1, s2, c2, s3, c3, s5, c5;
-    csa(x0, x1, x2, s1, c1);
-    csa(x3, x4, x5, s2, c2);
-    csa(s1, s2, x6, s3, c3);
-    const uint32_t ones = s3 ^ x7, c4 = s3 & x7;
-    csa(c1, c2, c3, s5, c5);
-    const uint32_t twos = s5 ^ c4, c6 = s5 & c4;
-    const uint32_t fours = c5 ^ c6, eights = c5 & c6;
-    uint32_t key = __popc(ones) * (1u << KEY_IDX_BITS) + tj;
-    key = __popc(twos) * (2u << KEY_IDX_BITS) + key;
-    key = __popc(fours) * (4u << KEY_IDX_BITS) + key;
-    return __popc(eights) * (8u << KEY_IDX_BITS) + key;
-  }
+  uint32_t s1, c1, s2, c2, s3, c3;
+  csa(x0, x1, x2, s1, c1);
+  csa(x3, x4, x5, s2, c2);
+  csa(s1, s2, x6, s3, c3);
+  const uint32_t ones = __popc(s3) + __popc(x7);
+  const uint32_t twos = __popc(c1) + __popc(c2) + __popc(c3);
+  return twos * (2u << KEY_IDX_BITS) + (ones * (1u << KEY_IDX_BITS) + tj);
 }
 
 // Work list: segment lengths live on the device, so the host can only size the grid for the worst case.  Launching
@@ -112,12 +97,12 @@ hamming_plan_kernel(const int32_t* __restrict__ q_len, int n_seg, int max_nq, in
   if (tid == 0) *n_items = carry_sh;
 }
 
-template <int VARIANT, bool TOP2>
+template <bool TOP2>
 __global__ void __launch_bounds__(HB_THREADS)
 hamming_partial_kernel(const uint4* __restrict__ q, const uint4* __restrict__ t, const int32_t* __restrict__ q_start,
                        const int32_t* __restrict__ q_len, const int32_t* __restrict__ t_start,
-                       const int32_t* __restrict__ t_len, int max_nq, int splits, const uint32_t* __restrict__ items,
-                       const int32_t* __restrict__ n_items, uint2* __restrict__ partial) {
+                       const int32_t* __restrict__ t_len, int max_nq, int max_nt, int splits,
+                       const uint32_t* __restrict__ items, const int32_t* __restrict__ n_items, uint2* __restrict__ partial) {
   __shared__ uint4 tile[HB_TILE_T * 2];
 
   if ((int)blockIdx.x >= *n_items) return;
@@ -125,7 +110,7 @@ hamming_partial_kernel(const uint4* __restrict__ q, const uint4* __restrict__ t,
   const int seg = (int)(item >> 16);
   const int q0 = q_start[seg], nq = min(q_len[seg], max_nq);
   const int q_tile = (int)((item >> ITEM_SPLIT_BITS) & ((1u << ITEM_TILE_BITS) - 1u)) * HB_TILE_Q;
-  const int t0 = t_start[seg], nt = t_len[seg];
+  const int t0 = t_start[seg], nt = min(t_len[seg], max_nt);
   const int split = (int)(item & ((1u << ITEM_SPLIT_BITS) - 1u));
   const int chunk = (nt + splits - 1) / splits;
   const int t_begin = min(nt, split * chunk);
@@ -159,7 +144,7 @@ hamming_partial_kernel(const uint4* __restrict__ q, const uint4* __restrict__ t,
         const uint32_t tj = (uint32_t)(tb + j + u);
 #pragma unroll
         for (int r = 0; r < HB_QPT; ++r) {
-          const uint32_t key = hamming_key<VARIANT>(qa[r], qb[r], ta, tbv, tj);
+          const uint32_t key = hamming_key(qa[r], qb[r], ta, tbv, tj);
           if (TOP2) k1[r] = min(k1[r], max(k0[r], key));
           k0[r] = min(k0[r], key);
         }
@@ -170,7 +155,7 @@ hamming_partial_kernel(const uint4* __restrict__ q, const uint4* __restrict__ t,
       const uint32_t tj = (uint32_t)(tb + j);
 #pragma unroll
       for (int r = 0; r < HB_QPT; ++r) {
-        const uint32_t key = hamming_key<VARIANT>(qa[r], qb[r], ta, tbv, tj);
+        const uint32_t key = hamming_key(qa[r], qb[r], ta, tbv, tj);
         if (TOP2) k1[r] = min(k1[r], max(k0[r], key));
         k0[r] = min(k0[r], key);
       }
@@ -336,14 +321,32 @@ extern "C" int sos_hamming_top2(sos_ctx* ctx, const uint32_t* q, const uint32_t*
   SOS_CUDA(cudaSetDevice(ctx->device));
 
   const int q_tiles = sos_div_up(max_nq, HB_TILE_Q);
-  const int t_tiles = sos_div_up(max_nt > 0 ? max_nt : 1, HB_TILE_T);
   SOS_CHECK_ARG(q_tiles <= (1 << ITEM_TILE_BITS), "segment has too many query rows (limit 262144)");
-  // split the train range so that a work item is ~256 x 1024 descriptor pairs and small problems still give every SM
-  // several items; never finer than one shared-memory tile
-  int splits = sos_div_up(max_nt > 0 ? max_nt : 1, 1024);
-  const int fill = sos_div_up(4 * ctx->sm_count, q_tiles * n_seg);
-  if (splits < fill) splits = fill;
-  if (splits > t_tiles) splits = t_tiles;
+  const bool top2 = idx1 != nullptr || d1 != nullptr;
+  // engine: "popc" = XOR + POPC on the integer pipe, "mma" = int8 tensor cores (hamming_mma.cu).  Default: the tensor-core
+  // engine once a segment can fill a few 128 x 128 tiles; below that its fixed cost (expansion, 180 KB of shared memory per
+  // CTA, TMEM allocation) is not repaid.  SOS_HAMMING_ENGINE overrides (read per call; both engines run the same tests).
+  const char* eng = getenv("SOS_HAMMING_ENGINE");
+  bool use_mma = max_nq >= 256 && max_nt >= 512;
+  if (eng && eng[0] == 'p') use_mma = false;
+  if (eng && eng[0] == 'm') use_mma = max_nt > 0;
+
+  int splits;
+  if (use_mma) {
+    // a work item is 256 query rows x (train tiles / splits); keep >= 4 train tiles per item (the two query tiles of an
+    // item are fetched once per item) unless that starves the SMs
+    const int t_tiles = sos_div_up(max_nt, 128);
+    splits = sos_div_up(2 * ctx->sm_count, q_tiles * n_seg);
+    if (splits > t_tiles / 4) splits = t_tiles / 4;
+  } else {
+    // split the train range so that a work item is ~256 x 1024 descriptor pairs and small problems still give every SM
+    // several items; never finer than one shared-memory tile
+    const int t_tiles = sos_div_up(max_nt > 0 ? max_nt : 1, HB_TILE_T);
+    splits = sos_div_up(max_nt > 0 ? max_nt : 1, 1024);
+    const int fill = sos_div_up(4 * ctx->sm_count, q_tiles * n_seg);
+    if (splits < fill) splits = fill;
+    if (splits > t_tiles) splits = t_tiles;
+  }
   if (splits > (1 << ITEM_SPLIT_BITS)) splits = 1 << ITEM_SPLIT_BITS;
   if (splits < 1) splits = 1;
 
@@ -353,7 +356,8 @@ extern "C" int sos_hamming_top2(sos_ctx* ctx, const uint32_t* q, const uint32_t*
   SOS_CHECK_ARG(max_items < ((size_t)1 << 31), "too many work items");
   const size_t partial_bytes = sos_align_up(rows_bound * splits * sizeof(uint2), 256);
   const size_t items_bytes = sos_align_up(max_items * sizeof(uint32_t), 256);
-  int rc = sos_arena_get(ctx, partial_bytes + items_bytes + 256, &ws);
+  const size_t exp_bytes = use_mma ? sos_hamming_mma_scratch_bytes(n_seg, max_nq, max_nt) : 0;
+  int rc = sos_arena_get(ctx, partial_bytes + items_bytes + 256 + exp_bytes, &ws);
   if (rc != SOS_OK) return rc;
   uint32_t* items = (uint32_t*)((char*)ws + partial_bytes);
   int32_t* n_items = (int32_t*)((char*)ws + partial_bytes + items_bytes);
@@ -361,20 +365,19 @@ extern "C" int sos_hamming_top2(sos_ctx* ctx, const uint32_t* q, const uint32_t*
   hamming_plan_kernel<<<1, 256, 0, ctx->stream>>>(q_len, n_seg, max_nq, splits, items, n_items);
   SOS_LAUNCHED(ctx);
   const unsigned grid = (unsigned)max_items;
-  static const int variant = [] {
-    const char* e = getenv("SOS_HAMMING_VARIANT");  // A/B switch for profiling; default = the fastest measured
-    return e ? atoi(e) : 1;
-  }();
-  const bool top2 = idx1 != nullptr || d1 != nullptr;
-#define HB_LAUNCH(V, T2)                                                                                              \
-  hamming_partial_kernel<V, T2><<<grid, HB_THREADS, 0, ctx->stream>>>((const uint4*)q, (const uint4*)t, q_start, q_len, \
-                                                                      t_start, t_len, max_nq, splits, items, n_items,   \
-                                                                      (uint2*)ws)
-  if (variant == 0) { if (top2) HB_LAUNCH(0, true); else HB_LAUNCH(0, false); }
-  else if (variant == 2) { if (top2) HB_LAUNCH(2, true); else HB_LAUNCH(2, false); }
-  else { if (top2) HB_LAUNCH(1, true); else HB_LAUNCH(1, false); }
+  if (use_mma) {
+    rc = sos_hamming_mma_launch(ctx, q, t, q_start, q_len, t_start, t_len, n_seg, max_nq, max_nt, splits, items, n_items,
+                                grid, top2, (char*)ws + partial_bytes + items_bytes + 256, (uint2*)ws);
+    if (rc != SOS_OK) return rc;
+  } else {
+#define HB_LAUNCH(T2)                                                                                                  \
+  hamming_partial_kernel<T2><<<grid, HB_THREADS, 0, ctx->stream>>>((const uint4*)q, (const uint4*)t, q_start, q_len,    \
+                                                                   t_start, t_len, max_nq, max_nt, splits, items,      \
+                                                                   n_items, (uint2*)ws)
+    if (top2) HB_LAUNCH(true); else HB_LAUNCH(false);
 #undef HB_LAUNCH
-  SOS_LAUNCHED(ctx);
+    SOS_LAUNCHED(ctx);
+  }
   dim3 mgrid(sos_div_up(max_nq, 256), n_seg);
   hamming_merge_kernel<<<mgrid, 256, 0, ctx->stream>>>((const uint2*)ws, q_start, q_len, max_nq, splits, idx0, d0, idx1, d1);
   SOS_LAUNCHED(ctx);

@@ -1,0 +1,370 @@
+// Tensor-core engine of the brute-force Hamming matcher (step 2 of the SOS front-end; same contract as the XOR+POPC
+// engine in hamming.cu, which it replaces for large problems: FeatureMatcher.match on cv2.BFMatcher(NORM_HAMMING),
+// reference omnistereo/camera_models.py:402-446).
+//
+// Hamming distance is a contraction: with the 256 descriptor bits mapped to signs s = +-1,
+//     <s_q, s_t> = 256 - 2 d(q, t),
+// so the all-pairs distance matrix of a (query, train) segment is an integer GEMM with K = 256.  Here it runs on the
+// 5th-generation tensor cores (tcgen05.mma kind::i8, int32 accumulators in tensor memory: exact), and the part that bounds
+// the POPC engine — ~26 integer instructions per descriptor pair — shrinks to reading the accumulator back and ONE max:
+//
+//   * operands are +-16 instead of +-1, so the accumulator holds 256 * <s_q, s_t>;
+//   * 32 extra K columns carry bookkeeping through the same MMA: the query side holds the constants (16, 1, 127 x 30),
+//     the train side (-(u >> 4), -(u & 15), pad x 30) with u = row of the train descriptor inside its 128-row tile and
+//     pad = -128 for the padding rows of a ragged last tile, 0 otherwise.  The accumulator therefore is
+//         acc = 256 * <s_q, s_t> - u - 487680 * [padding row]
+//     i.e. ALREADY the packed sort key: max(acc) over a tile = smallest distance, ties to the lowest train row (OpenCV's
+//     order), padding rows lose against everything — no index arithmetic, no masking in the epilogue;
+//   * the epilogue thread that owns query row r (TMEM lane r) reads its 128 accumulators with tcgen05.ld and keeps the
+//     running maximum (3-input integer max: half an instruction per pair); top-2 costs 3 instructions per pair.
+//
+// Data flow per work item (256 query rows x a range of train tiles; one CTA per SM, warp-specialised):
+//   expand kernel : descriptors -> "tile-ready" int8 images in global memory, 128 rows x 288 bytes per tile, stored in the
+//                   canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices), so that a tile is ONE
+//                   contiguous 36 KB block
+//   warp 0        : cp.async.bulk (TMA engine, mbarrier complete_tx) of the two query tiles, then a 3-stage ring of
+//                   train tiles
+//   warp 1        : one lane issues 2 x 9 tcgen05.mma (M128 N128 K32) per train tile into a double-buffered TMEM
+//                   accumulator (2 buffers x 2 query tiles x 128 columns = all 512 columns); tcgen05.commit releases the
+//                   shared-memory stage and publishes the accumulator
+//   warp 2        : tensor-memory allocation
+//   warps 4..11   : epilogue, one thread per (query tile, row)
+// The per-split partial keys use the POPC engine's format and are merged by the same hamming_merge_kernel.
+#include "sos_common.cuh"
+
+namespace sos_hamming_mma {
+
+constexpr int TILE = 128;                        // rows per expanded tile = UMMA M = UMMA N
+constexpr int KB = 288;                          // bytes of K per row: 256 sign bytes + 32 bookkeeping bytes
+constexpr int CHUNKS = KB / 16;                  // 18 core-matrix columns
+constexpr int GROUP_BYTES = CHUNKS * 128;        // one 8-row group: 18 core matrices of 8 x 16 bytes
+constexpr int TILE_BYTES = (TILE / 8) * GROUP_BYTES;  // 36864
+constexpr int STAGES = 3;
+constexpr int THREADS = 384;
+constexpr int SMEM_BYTES = (2 + STAGES) * TILE_BYTES + 256;
+constexpr int PAD_DROP = 30 * 127 * 128;         // what the 30 pad columns subtract from a padding row's accumulator
+constexpr int KEY_IDX_BITS = 22;                 // must match hamming.cu
+constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
+constexpr int ITEM_SPLIT_BITS = 6, ITEM_TILE_BITS = 10;   // item = seg << 16 | tile << 6 | split (hamming.cu)
+
+// ---- expansion ------------------------------------------------------------------------------------------------------
+// four descriptor bits -> four int8 values: bit 0 -> +16, bit 1 -> -16
+__device__ __forceinline__ uint32_t expand4(uint32_t nib) {
+  const uint32_t spread = (nib * 0x00204081u) & 0x01010101u;   // bit i -> LSB of byte i (the shifted copies never overlap)
+  return 0x10101010u ^ (spread * 0xE0u);
+}
+
+// role 0: query rows (A operand), role 1: train rows (B operand).  Tile t of segment s lives at
+// out + (s * tiles_per_seg + t) * TILE_BYTES; byte (row r, k) of a tile at (r / 8) * GROUP_BYTES + (k / 16) * 128 + (r % 8) * 16 + k % 16.
+__global__ void __launch_bounds__(256)
+expand_kernel(const uint32_t* __restrict__ desc, const int32_t* __restrict__ start, const int32_t* __restrict__ len,
+              int max_rows, int tiles_per_seg, int role, uint8_t* __restrict__ out) {
+  const int seg = blockIdx.y, tile = blockIdx.x;
+  const int n = min(len[seg], max_rows);
+  const int row0 = tile * TILE;
+  if (row0 >= n) return;
+  const uint32_t* d = desc + (size_t)start[seg] * 8;
+  uint8_t* tbase = out + ((size_t)seg * tiles_per_seg + tile) * TILE_BYTES;
+  for (int u = threadIdx.x; u < TILE * CHUNKS; u += 256) {
+    const int r8 = u & 7, chunk = (u >> 3) % CHUNKS, rg = u / (8 * CHUNKS);
+    const int r = rg * 8 + r8, row = row0 + r;
+    const bool valid = row < n;
+    uint4 v;
+    if (chunk < 16) {
+      uint32_t bits = 0;
+      if (valid) bits = (__ldg(d + (size_t)row * 8 + (chunk >> 1)) >> ((chunk & 1) * 16)) & 0xFFFFu;
+      v.x = expand4(bits & 15u);
+      v.y = expand4((bits >> 4) & 15u);
+      v.z = expand4((bits >> 8) & 15u);
+      v.w = expand4(bits >> 12);
+      if (!valid) v = make_uint4(0u, 0u, 0u, 0u);          // padding rows: <s_q, s_t> = 0
+    } else if (role == 0) {
+      v = make_uint4(0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x7F7F7F7Fu);
+      if (chunk == 16) v.x = 0x7F7F0110u;                  // bytes (16, 1, 127, 127)
+    } else {
+      const uint32_t pad = valid ? 0u : 0x80808080u;       // -128 in every pad column of a padding row
+      v = make_uint4(pad, pad, pad, pad);
+      if (chunk == 16) {
+        const uint32_t hi = (uint32_t)(-(r >> 4)) & 0xFFu, lo = (uint32_t)(-(r & 15)) & 0xFFu;
+        v.x = (pad & 0xFFFF0000u) | (lo << 8) | hi;
+      }
+    }
+    *(uint4*)(tbase + (size_t)rg * GROUP_BYTES + chunk * 128 + r8 * 16) = v;
+  }
+}
+
+// ---- PTX helpers ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// try_wait suspends the thread in hardware; the spin bound only turns a lost arrival (a bug) into a trap instead of a hang
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (!done && spin > (1u << 20)) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], int8 x int8 -> int32, M128 N128 K32
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// shared-memory matrix descriptor: K-major, no swizzle; core matrices 128 bytes apart along K (LBO) and GROUP_BYTES apart
+// along M/N (SBO); bits [46,48) = 1 (Blackwell descriptor version)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(GROUP_BYTES >> 4) << 32) |
+         ((uint64_t)1 << 46);
+}
+// instruction descriptor: D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), both K-major, N = 128, M = 128
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+
+// 32 consecutive accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+// tcgen05.wait::ld with the destination registers as in/out operands: ties every later use of v[] to the wait, so neither
+// the compiler nor ptxas can schedule a consumer above it (the load itself returns before the registers are written)
+__device__ __forceinline__ void tmem_ld_wait(int (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                 "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                 "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+
+template <bool TOP2>
+__device__ __forceinline__ void reduce32(const int (&v)[32], int& m0, int& m1) {
+  if (TOP2) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      m1 = max(m1, min(m0, v[i]));
+      m0 = max(m0, v[i]);
+    }
+  } else {
+    int a = m0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) a = __vimax3_s32(a, v[i], v[i + 1]);
+    m0 = a;
+  }
+}
+
+// accumulator of (query row, train row u of tile `tile`) -> the POPC engine's key (distance << 22 | train row of the segment)
+__device__ __forceinline__ uint32_t acc_to_key(int acc, int tile) {
+  const int dot = (acc + 255) >> 8;              // acc = 256 * dot - u with 0 <= u < 128
+  if (dot < -256) return KEY_NONE;               // padding row (or no train row at all)
+  const int u = 256 * dot - acc;
+  return ((uint32_t)((256 - dot) >> 1) << KEY_IDX_BITS) | (uint32_t)(tile * TILE + u);
+}
+
+struct Args {
+  const uint8_t *a_exp, *b_exp;
+  const int32_t *q_len, *t_len;
+  int max_nq, max_nt, splits, q_tiles_per_seg, t_tiles_per_seg;
+  const uint32_t* items;
+  const int32_t* n_items;
+  uint2* partial;
+};
+
+template <bool TOP2>
+__global__ void __launch_bounds__(THREADS, 1) mma_kernel(Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((int)blockIdx.x >= *a.n_items) return;
+  const uint32_t item = a.items[blockIdx.x];
+  const int seg = (int)(item >> 16);
+  const int q_tile = (int)((item >> ITEM_SPLIT_BITS) & ((1u << ITEM_TILE_BITS) - 1u));   // 256 query rows
+  const int split = (int)(item & ((1u << ITEM_SPLIT_BITS) - 1u));
+  const int nq = min(a.q_len[seg], a.max_nq), nt = min(a.t_len[seg], a.max_nt);
+  const int t_tiles = (nt + TILE - 1) / TILE;
+  const int chunk_tiles = (t_tiles + a.splits - 1) / a.splits;
+  const int tile_begin = min(t_tiles, split * chunk_tiles);
+  const int n_iter = min(t_tiles, tile_begin + chunk_tiles) - tile_begin;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 2 * TILE_BYTES;
+  uint64_t* bars = (uint64_t*)(smem + (2 + STAGES) * TILE_BYTES);
+  // bars[0..2] full (train stage landed), [3..5] empty (stage consumed), [6..7] accumulator full, [8..9] accumulator drained,
+  // [10] query tiles landed
+  uint32_t* tmem_slot = (uint32_t*)(bars + 12);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+
+  if (n_iter > 0) {   // block-uniform
+    if (tid == 0) {
+      for (int i = 0; i < STAGES; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); }
+      mbar_init(BAR(6), 1); mbar_init(BAR(7), 1);
+      mbar_init(BAR(8), 8); mbar_init(BAR(9), 8);
+      mbar_init(BAR(10), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+      if (lane == 0) {
+        // the item's two query tiles, then the ring of train tiles
+        const uint8_t* ga = a.a_exp + ((size_t)seg * a.q_tiles_per_seg + (size_t)q_tile * 2) * TILE_BYTES;
+        mbar_expect_tx(BAR(10), 2u * TILE_BYTES);
+#pragma unroll
+        for (int p = 0; p < 8; ++p) bulk_g2s(smem_u32(sA) + p * (TILE_BYTES / 4), ga + (size_t)p * (TILE_BYTES / 4), TILE_BYTES / 4, BAR(10));
+        const uint8_t* gb = a.b_exp + ((size_t)seg * a.t_tiles_per_seg + tile_begin) * TILE_BYTES;
+        for (int it = 0; it < n_iter; ++it) {
+          const int s = it % STAGES;
+          mbar_wait(BAR(3 + s), ((it / STAGES) & 1) ^ 1);
+          mbar_expect_tx(BAR(s), TILE_BYTES);
+          const uint32_t dst = smem_u32(sB) + s * TILE_BYTES;
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+            bulk_g2s(dst + p * (TILE_BYTES / 4), gb + (size_t)it * TILE_BYTES + (size_t)p * (TILE_BYTES / 4), TILE_BYTES / 4, BAR(s));
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (lane == 0) {
+        mbar_wait(BAR(10), 0);
+        const uint64_t da0 = smem_desc(smem_u32(sA)), da1 = smem_desc(smem_u32(sA) + TILE_BYTES);
+        for (int it = 0; it < n_iter; ++it) {
+          const int s = it % STAGES, b = it & 1;
+          mbar_wait(BAR(8 + b), ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator buffer
+          mbar_wait(BAR(s), (it / STAGES) & 1);         // the train tile has landed
+          tc_fence_after();
+          const uint64_t db = smem_desc(smem_u32(sB) + s * TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < KB / 32; ++k) tc_mma_i8(tmem + (uint32_t)(b * 2) * TILE, da0 + (uint64_t)(16 * k), db + (uint64_t)(16 * k), IDESC, k > 0);
+#pragma unroll
+          for (int k = 0; k < KB / 32; ++k) tc_mma_i8(tmem + (uint32_t)(b * 2 + 1) * TILE, da1 + (uint64_t)(16 * k), db + (uint64_t)(16 * k), IDESC, k > 0);
+          tc_commit(BAR(3 + s));   // shared-memory stage free once these MMAs have read it
+          tc_commit(BAR(6 + b));   // accumulators complete
+        }
+      }
+      __syncwarp();
+    } else if (warp >= 4) {
+      const int g = (warp - 4) >> 2, quarter = warp & 3;   // a warp may only touch the TMEM lanes of its quarter
+      const int row = q_tile * 256 + g * TILE + quarter * 32 + lane;
+      uint32_t k0 = KEY_NONE, k1 = KEY_NONE;
+      for (int it = 0; it < n_iter; ++it) {
+        const int b = it & 1;
+        mbar_wait(BAR(6 + b), (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 2 + g) * TILE;
+        int m0 = INT_MIN, m1 = INT_MIN;
+        int va[32], vb[32];
+        tmem_ld32(taddr, va);
+        tmem_ld_wait(va);
+        tmem_ld32(taddr + 32, vb);          // in flight while va is reduced
+        reduce32<TOP2>(va, m0, m1);
+        tmem_ld_wait(vb);
+        tmem_ld32(taddr + 64, va);
+        reduce32<TOP2>(vb, m0, m1);
+        tmem_ld_wait(va);
+        tmem_ld32(taddr + 96, vb);
+        reduce32<TOP2>(va, m0, m1);
+        tmem_ld_wait(vb);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(8 + b));          // buffer b may be overwritten
+        reduce32<TOP2>(vb, m0, m1);
+        const int tile = tile_begin + it;
+        const uint32_t key0 = acc_to_key(m0, tile);
+        if (TOP2) {
+          const uint32_t key1 = acc_to_key(m1, tile);
+          k1 = min(k1, max(k0, key0));                    // merge two sorted pairs
+          k0 = min(k0, key0);
+          k1 = min(k1, key1);
+        } else {
+          k0 = min(k0, key0);
+        }
+      }
+      if (row < nq) a.partial[((size_t)seg * a.max_nq + row) * a.splits + split] = make_uint2(k0, k1);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  } else {
+    // no train rows in this split
+    for (int r = tid; r < 256; r += THREADS) {
+      const int row = q_tile * 256 + r;
+      if (row < nq) a.partial[((size_t)seg * a.max_nq + row) * a.splits + split] = make_uint2(KEY_NONE, KEY_NONE);
+    }
+  }
+}
+
+}  // namespace sos_hamming_mma
+
+// Host side, called by sos_hamming_top2 (hamming.cu).  `ws` holds the partial keys + work items (already planned);
+// `exp` is scratch for the expanded tiles.
+size_t sos_hamming_mma_scratch_bytes(int n_seg, int max_nq, int max_nt) {
+  using namespace sos_hamming_mma;
+  const size_t qt = (size_t)((max_nq + 255) / 256) * 2, tt = (size_t)((max_nt + TILE - 1) / TILE);
+  return (size_t)n_seg * (qt + tt) * TILE_BYTES + 256;
+}
+
+int sos_hamming_mma_launch(sos_ctx* ctx, const uint32_t* q, const uint32_t* t, const int32_t* q_start,
+                           const int32_t* q_len, const int32_t* t_start, const int32_t* t_len, int n_seg, int max_nq,
+                           int max_nt, int splits, const uint32_t* items, const int32_t* n_items, unsigned max_items,
+                           bool top2, void* exp, uint2* partial) {
+  using namespace sos_hamming_mma;
+  const int qt = ((max_nq + 255) / 256) * 2, tt = (max_nt + TILE - 1) / TILE;
+  uint8_t* a_exp = (uint8_t*)exp;
+  uint8_t* b_exp = a_exp + (size_t)n_seg * qt * TILE_BYTES;
+  if (qt > 0) {
+    expand_kernel<<<dim3(qt, n_seg), 256, 0, ctx->stream>>>(q, q_start, q_len, max_nq, qt, 0, a_exp);
+    SOS_LAUNCHED(ctx);
+  }
+  if (tt > 0) {
+    expand_kernel<<<dim3(tt, n_seg), 256, 0, ctx->stream>>>(t, t_start, t_len, max_nt, tt, 1, b_exp);
+    SOS_LAUNCHED(ctx);
+  }
+  Args a;
+  a.a_exp = a_exp; a.b_exp = b_exp; a.q_len = q_len; a.t_len = t_len;
+  a.max_nq = max_nq; a.max_nt = max_nt; a.splits = splits; a.q_tiles_per_seg = qt; a.t_tiles_per_seg = tt;
+  a.items = items; a.n_items = n_items; a.partial = partial;
+  static bool attr_set[64][2] = {};     // per device: the opt-in to > 48 KB of dynamic shared memory
+  const int dev = ctx->device & 63, v = top2 ? 1 : 0;
+  if (!attr_set[dev][v]) {
+    if (top2) SOS_CUDA(cudaFuncSetAttribute(mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    else SOS_CUDA(cudaFuncSetAttribute(mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set[dev][v] = true;
+  }
+  if (top2) mma_kernel<true><<<max_items, THREADS, SMEM_BYTES, ctx->stream>>>(a);
+  else mma_kernel<false><<<max_items, THREADS, SMEM_BYTES, ctx->stream>>>(a);
+  SOS_LAUNCHED(ctx);
+  return SOS_OK;
+}

@@ -3,107 +3,19 @@
 // replaces: cv2.medianBlur(pano_img, median_win_size) with median_win_size = 11 (pose_est_tools.py:297;
 //           camera_models.py:1708-1709): exact median of the 121 window values per channel, BORDER_REPLICATE.
 //
-// Sliding-window histograms (Huang), one WARP per pair of image columns walking down a strip of rows: the 11 pixels of
-// the row entering / leaving a window are handled by 11 lanes at once with shared-memory atomics on a 256-word histogram
-// whose bytes hold the three channels' counts (<= 121 each, so no carries), the per-channel "count below the median" is
-// maintained with warp ballots, and the owner lane of each (column, channel) re-centres its median with a few
-// histogram reads per step.  No block-wide barriers; 1 KB of shared memory per column.
+// Sliding-window histograms (Huang).  Every lane owns one (column, channel) histogram of byte counters and walks down its
+// column by itself: per row 11 values leave and 11 enter the window with plain byte read-modify-writes — no atomics, no
+// ballots, no idle lanes.  (The first version — one warp per pair of columns with shared-memory atomics and ballots — took
+// 2.3x longer: 219 instructions per two-pixel step with 18 of 32 lanes active, 5.8 wavefronts per atomic; removed in round 2.)
+// Layout (8 KB per warp): the counter of bin b of lane l is byte (b & 3) of word (b >> 2) * 32 + l, so a lane only ever touches
+// its own bank.  (First layout: byte b * 32 + l, i.e. four lanes per word - ncu: LSU data-pipe wavefronts at 93 % of peak, 167
+// per step for 68 requests, because lanes of one word group collide whenever their bins differ by a multiple of 4.)
 #include "sos_common.cuh"
 
 namespace {
 
-constexpr int MB_WARPS = 8;
-constexpr int MB_COLS = 2;          // columns per warp
 constexpr int MB_R = 5;             // window radius (11 x 11)
 constexpr int MB_HALF = 60;         // 0-based rank of the median among 121 values
-
-template <int C>
-__global__ void __launch_bounds__(MB_WARPS * 32)
-median11_kernel(const uint8_t* __restrict__ src, int H, int W, int strip_rows, uint8_t* __restrict__ dst) {
-  __shared__ uint32_t hist_all[MB_WARPS][MB_COLS][256];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int x0 = (blockIdx.x * MB_WARPS + warp) * MB_COLS;
-  if (x0 >= W) return;                                  // whole warps leave together; only __syncwarp below
-  const int y0 = blockIdx.y * strip_rows, y1 = min(H, y0 + strip_rows);
-  const uint8_t* img = src + (size_t)blockIdx.z * H * W * C;
-  uint8_t* out = dst + (size_t)blockIdx.z * H * W * C;
-  uint32_t(*hist)[256] = hist_all[warp];
-  for (int i = lane; i < MB_COLS * 256; i += 32) (&hist[0][0])[i] = 0u;
-  __syncwarp();
-
-  const int cs = lane / 11, k = lane - cs * 11;         // lanes 0..21: column cs, window offset k - 5
-  const int xcol = x0 + (cs < MB_COLS ? cs : 0);
-  const bool active = cs < MB_COLS && xcol < W;
-  const int xx = min(max(xcol + k - MB_R, 0), W - 1);  // BORDER_REPLICATE
-  const uint32_t colmask = cs < MB_COLS ? (0x7FFu << (11 * cs)) : 0u;
-  // owner lanes 0 .. MB_COLS*C-1: (column oc, channel och) keep the median and the count below it
-  const int oc = lane / C, och = lane - oc * C;
-  const bool owner = lane < MB_COLS * C && x0 + oc < W;
-  const uint32_t ownmask = 0x7FFu << (11 * (owner ? oc : 0));
-  int m = 0, ltm = 0;                                    // owner state
-  int mc[C];                                             // every lane: medians of its own column's channels
-#pragma unroll
-  for (int c = 0; c < C; ++c) mc[c] = 0;
-
-  auto update_row = [&](int r, int sign) {
-    int v[C];
-    if (active) {
-      const uint8_t* p = img + ((size_t)r * W + xx) * C;
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        v[c] = p[c];
-        if (sign > 0) atomicAdd(&hist[cs][v[c]], 1u << (8 * c));
-        else atomicSub(&hist[cs][v[c]], 1u << (8 * c));
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < C; ++c) v[c] = 255;
-    }
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const uint32_t below = __ballot_sync(0xFFFFFFFFu, active && v[c] < mc[c]);
-      if (owner && och == c) ltm += sign * __popc(below & ownmask);
-    }
-  };
-  auto recentre = [&]() {
-    __syncwarp();                                        // the row's atomics are visible to the owner lanes
-    if (owner) {
-      const uint32_t* h = hist[oc];
-      const int sh = 8 * och;
-      while (ltm > MB_HALF) { --m; ltm -= (int)((h[m] >> sh) & 0xFFu); }
-      while (true) {
-        const int cnt = (int)((h[m] >> sh) & 0xFFu);
-        if (ltm + cnt > MB_HALF) break;
-        ltm += cnt;
-        ++m;
-      }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int c = 0; c < C; ++c) mc[c] = __shfl_sync(0xFFFFFFFFu, m, (cs < MB_COLS ? cs : 0) * C + c);
-  };
-
-  for (int r = y0 - MB_R; r <= y0 + MB_R; ++r) update_row(min(max(r, 0), H - 1), +1);
-  recentre();
-  for (int y = y0; y < y1; ++y) {
-    if (y > y0) {
-      update_row(min(max(y - MB_R - 1, 0), H - 1), -1);
-      update_row(min(max(y + MB_R, 0), H - 1), +1);
-      recentre();
-    }
-    if (owner) out[((size_t)y * W + x0 + oc) * C + och] = (uint8_t)m;
-  }
-}
-
-
-// ---- lane-per-(column, channel) variant ----------------------------------------------------------------------------------
-// ncu on the warp-cooperative kernel above: 219 instructions per two-pixel step with 18 of 32 lanes active on average, issue
-// slots 89 % busy, 5.8 shared-memory wavefronts per atomic.  Here every lane owns one (column, channel) histogram of byte
-// counters and walks down its column by itself: per row 11 values leave and 11 enter the window with plain byte
-// read-modify-writes — no atomics, no ballots, no idle lanes.
-// Layout (8 KB per warp): the counter of bin b of lane l is byte (b & 3) of word (b >> 2) * 32 + l, so a lane only ever touches
-// its own bank.  (First layout: byte b * 32 + l, i.e. four lanes per word - ncu: LSU data-pipe wavefronts at 93 % of peak, 167
-// per step for 68 requests, because lanes of one word group collide whenever their bins differ by a multiple of 4.)
 constexpr int ML_WARPS = 4;
 
 __device__ __forceinline__ int ml_slot(int b) { return ((b & 0xFC) << 5) | (b & 3); }
@@ -230,17 +142,10 @@ extern "C" int sos_median_blur_11(sos_ctx* ctx, const uint8_t* src, int n_images
   SOS_CHECK_ARG(n_images <= 65535, "too many images");
   SOS_CUDA(cudaSetDevice(ctx->device));
   const int strip = 128;
-  static const bool coop = getenv("SOS_MEDIAN_V1") != nullptr;   // A/B switch: the warp-cooperative kernel
-  if (coop) {
-    dim3 grid(sos_div_up(width, MB_WARPS * MB_COLS), sos_div_up(height, strip), n_images);
-    if (channels == 3) median11_kernel<3><<<grid, MB_WARPS * 32, 0, ctx->stream>>>(src, height, width, strip, dst);
-    else median11_kernel<1><<<grid, MB_WARPS * 32, 0, ctx->stream>>>(src, height, width, strip, dst);
-  } else {
-    const int cols_per_block = ML_WARPS * (32 / channels);
-    dim3 grid(sos_div_up(width, cols_per_block), sos_div_up(height, strip), n_images);
-    if (channels == 3) median11_lane_kernel<3><<<grid, ML_WARPS * 32, 0, ctx->stream>>>(src, height, width, strip, dst, nullptr);
-    else median11_lane_kernel<1><<<grid, ML_WARPS * 32, 0, ctx->stream>>>(src, height, width, strip, dst, nullptr);
-  }
+  const int cols_per_block = ML_WARPS * (32 / channels);
+  dim3 grid(sos_div_up(width, cols_per_block), sos_div_up(height, strip), n_images);
+  if (channels == 3) median11_lane_kernel<3><<<grid, ML_WARPS * 32, 0, ctx->stream>>>(src, height, width, strip, dst, nullptr);
+  else median11_lane_kernel<1><<<grid, ML_WARPS * 32, 0, ctx->stream>>>(src, height, width, strip, dst, nullptr);
   SOS_LAUNCHED(ctx);
   return SOS_OK;
 }

@@ -220,75 +220,13 @@ __device__ __forceinline__ void load6_32(const uint8_t* __restrict__ p, uint32_t
   hi = __funnelshift_r(B, C, sh);
 }
 
-constexpr int R3_WARPS = 8;
-constexpr int R3_COLS = 128;
-
-__global__ void __launch_bounds__(R3_WARPS * 32)
-remap3_kernel(const uint8_t* __restrict__ src, int wide_ok, int src_h, int src_w, const uint64_t* __restrict__ lut, int views,
-              int rows, int cols, RemapConst k, uint8_t* __restrict__ dst) {
-  __shared__ __align__(16) uint8_t sout[R3_WARPS][R3_COLS * 3];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int col0 = blockIdx.x * R3_COLS;
-  const int row = blockIdx.y * R3_WARPS + warp;
-  if (row >= rows || col0 >= cols) return;  // whole warps leave together; only __syncwarp below
-  const int img = blockIdx.z;
-  const int view = img % views, b = img / views;
-  const uint8_t* s = src + (size_t)b * src_h * src_w * 3;
-  const size_t px0 = (size_t)row * cols + col0;
-  const uint64_t* l = lut + (size_t)view * rows * cols + px0;
-  uint8_t* d = dst + ((size_t)img * rows * cols + px0) * 3;
-  const int npx = min(R3_COLS, cols - col0);
-  const size_t row_bytes = (size_t)src_w * 3;
-  uint8_t* so = sout[warp];
-#pragma unroll
-  for (int pass = 0; pass < R3_COLS / 32; ++pass) {
-    const int c = pass * 32 + lane;
-    if (c < npx) {
-      const uint64_t e = __ldg(l + c);
-      const uint32_t hi = (uint32_t)(e >> 32);
-      uint32_t o[3];
-      if (wide_ok && (hi & (1u << 24))) {
-        const int x0 = (int)(int16_t)(e & 0xFFFF), y0 = (int)(int16_t)((e >> 16) & 0xFFFF);
-        const uint32_t ax = hi & 31u, ay = (hi >> 5) & 31u;
-        const uint8_t* p = s + ((size_t)y0 * src_w + x0) * 3;
-        uint32_t r0l, r0h, r1l, r1h;
-        load6_32(p, r0l, r0h);
-        load6_32(p + row_bytes, r1l, r1h);
-        const uint32_t wx = (32u - ax) | (ax << 8), wy = (32u - ay) | (ay << 8);
-        // channel c: bytes c (left tap) and c + 3 (right tap) of the 6-byte group -> PRMT selectors 0x30, 0x41, 0x52
-        const uint32_t h0 = __dp4a(__byte_perm(r0l, r0h, 0x0030), wx, __dp4a(__byte_perm(r1l, r1h, 0x0030), wx, 0u) << 16);
-        const uint32_t h1 = __dp4a(__byte_perm(r0l, r0h, 0x0041), wx, __dp4a(__byte_perm(r1l, r1h, 0x0041), wx, 0u) << 16);
-        const uint32_t h2 = __dp4a(__byte_perm(r0l, r0h, 0x0052), wx, __dp4a(__byte_perm(r1l, r1h, 0x0052), wx, 0u) << 16);
-        o[0] = __dp2a_lo(h0, wy, 512u) >> 10;
-        o[1] = __dp2a_lo(h1, wy, 512u) >> 10;
-        o[2] = __dp2a_lo(h2, wy, 512u) >> 10;
-      } else {
-        remap_pixel<3>(s, nullptr, src_w, e, k.border, k.bg, o);
-      }
-      so[c * 3 + 0] = (uint8_t)o[0];
-      so[c * 3 + 1] = (uint8_t)o[1];
-      so[c * 3 + 2] = (uint8_t)o[2];
-    }
-  }
-  __syncwarp();
-  const int nbytes = npx * 3;
-  if ((((uintptr_t)d) & 15) == 0) {
-    const int n16 = nbytes >> 4;
-    if (lane < n16) ((uint4*)d)[lane] = ((const uint4*)so)[lane];  // nbytes <= 384 -> at most 24 vectors
-    for (int i = (n16 << 4) + lane; i < nbytes; i += 32) d[i] = so[i];
-  } else {
-    for (int i = lane; i < nbytes; i += 32) d[i] = so[i];
-  }
-}
-
-
 // ---- patch-mapped variant -------------------------------------------------------------------------------------------
 // A warp-wide gather costs one L1 wavefront per distinct 128-byte line it touches.  32 consecutive pixels of ONE panorama
-// row follow an arc in the omni image that crosses ~14 source rows (top mirror at C2) -> ~14 wavefronts per tap load; the
-// kernel above is bound by exactly that (l1tex data-pipe 87 % busy, DRAM 11 %).  Mapping the 32 lanes onto a compact
+// row follow an arc in the omni image that crosses ~14 source rows (top mirror at C2) -> ~14 wavefronts per tap load; a
+// lane-per-pixel-along-the-row kernel is bound by exactly that (l1tex data-pipe 87 % busy, DRAM 11 %).  Mapping the 32 lanes onto a compact
 // 4-row x 8-column panorama patch halves the distinct lines (measured on the C2 LUT: 13.7 -> 6.1 top, 4.5 -> 1.9 bottom).
 // Warp tile = 4 rows x 32 columns in 4 passes; the 4 x 96 output bytes are staged in shared memory and written as
-// 16-byte vectors.  Same arithmetic as remap3_kernel (bit-exact).
+// 16-byte vectors.  Same arithmetic for every lane mapping (bit-exact).
 constexpr int RP_ROWS = 4;                 // rows per warp tile
 constexpr int RP_COLS = 32;                // columns per warp tile
 constexpr int RP_WARPS_X = 4, RP_WARPS_Y = 2;
@@ -370,7 +308,7 @@ constexpr int RB_TILE_COLS = RP_COLS * RP_WARPS_X;   // 128
 __device__ inline uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __global__ void __launch_bounds__(RP_WARPS_X * RP_WARPS_Y * 32)
-remap3b_kernel(const uint8_t* __restrict__ src, int wide_ok, int probe, int batch, int src_h, int src_w, const uint64_t* __restrict__ lut,
+remap3b_kernel(const uint8_t* __restrict__ src, int wide_ok, int batch, int src_h, int src_w, const uint64_t* __restrict__ lut,
                int views, int rows, int cols, RemapConst k, uint8_t* __restrict__ dst) {
   __shared__ __align__(128) uint64_t slut[RB_TILE_ROWS][RB_TILE_COLS];
   __shared__ __align__(16) uint8_t sout[RP_WARPS_X * RP_WARPS_Y][RP_ROWS][RP_COLS * 3];
@@ -436,7 +374,7 @@ remap3b_kernel(const uint8_t* __restrict__ src, int wide_ok, int probe, int batc
     dead |= (dd ? 1u : 0u) << pass;
     slow |= ((live && !w && !dd) ? 1u : 0u) << pass;
     const int x0 = (int)(int16_t)(e & 0xFFFF), y0 = (int)(int16_t)((e >> 16) & 0xFFFF);
-    off[pass] = (w && !(probe & 1)) ? (uint32_t)((y0 * src_w + x0) * 3) : 0u;   // non-fast lanes read (and discard) the first bytes of the image
+    off[pass] = w ? (uint32_t)((y0 * src_w + x0) * 3) : 0u;   // non-fast lanes read (and discard) the first bytes of the image
     const uint32_t ax = hi & 31u, ay = (hi >> 5) & 31u;
     wxy[pass] = (32u - ax) | (ax << 8) | ((32u - ay) << 16) | (ay << 24);
   }
@@ -477,9 +415,7 @@ remap3b_kernel(const uint8_t* __restrict__ src, int wide_ok, int probe, int batc
     }
     __syncwarp();
     uint8_t* d0 = dst + ((((size_t)b * views + view) * rows + row0) * cols + col0) * 3;
-    if (probe & 2) {
-      if (sout[warp][0][lane] == 77 && b == 1000) d0[0] = 1;   // keep the arithmetic alive, never stores
-    } else if (nbytes == RP_COLS * 3 && ((((uintptr_t)d0) | drow) & 15) == 0) {
+    if (nbytes == RP_COLS * 3 && ((((uintptr_t)d0) | drow) & 15) == 0) {
       if (lane < 24 && r2 < nrows) ((uint4*)(d0 + r2 * drow))[ch] = ((const uint4*)sout[warp][r2])[ch];
     } else {
       for (int rr = 0; rr < nrows; ++rr)
@@ -534,34 +470,27 @@ extern "C" int sos_remap_u8(sos_ctx* ctx, const uint8_t* src, int batch, int src
   }
   dim3 grid(sos_div_up(cols, RM_TILE_COLS), sos_div_up(rows, RM_TILE_ROWS), batch * views);
   // the wide (2 x 64-bit) tap loads may touch up to 15 bytes past the taps: allowed only inside [src, wide_end)
-  static const bool wide_off = getenv("SOS_REMAP_BYTE_LOADS") != nullptr;  // A/B switch for profiling
-  const uint8_t* wide_end = (((uintptr_t)src & 7) == 0 && !wide_off) ? src + (size_t)batch * src_h * src_w * channels : nullptr;
-  static const bool old_kernel = getenv("SOS_REMAP_V1") != nullptr;  // A/B switch for profiling
-  static const bool row_kernel = getenv("SOS_REMAP_V2") != nullptr;  // A/B switch for profiling
-  if (channels == 3 && !old_kernel) {
-    const int wide_ok = (((uintptr_t)src & 7) == 0 && !wide_off) ? 1 : 0;
-    // A/B switch: batch-looped blocks with TMA-staged LUT tiles.  Measured equal-to-slightly-slower than the per-frame
-    // patch kernel at C2 (0.32 vs 0.30 ms): the kernel is bound by instruction issue, not by the LUT stream
-    static const bool patch_kernel = getenv("SOS_REMAP_TMA") == nullptr;
-    if (row_kernel) {
-      dim3 g3(sos_div_up(cols, R3_COLS), sos_div_up(rows, R3_WARPS), batch * views);
-      remap3_kernel<<<g3, R3_WARPS * 32, 0, ctx->stream>>>(src, wide_ok, src_h, src_w, lut, views, rows, cols, k, dst);
-    } else if (!patch_kernel && (size_t)src_h * src_w * 3 < (1ull << 32)) {
+  const bool aligned8 = ((uintptr_t)src & 7) == 0;
+  const uint8_t* wide_end = aligned8 ? src + (size_t)batch * src_h * src_w * channels : nullptr;
+  if (channels == 3) {
+    // SOS_REMAP_TMA=1 selects the batch-looped blocks with TMA-staged LUT tiles.  Measured equal-to-slightly-slower than
+    // the per-frame patch kernel at C2 (0.32 vs 0.30 ms): the kernel is bound by instruction issue, not by the LUT stream
+    // (DESIGN.md §5).  Both variants run the same parity tests (tests/test_gpu_remap.py is parametrised over the switch).
+    const char* e = getenv("SOS_REMAP_TMA");
+    const bool tma_kernel = e != nullptr && e[0] != '0' && (size_t)src_h * src_w * 3 < (1ull << 32);
+    if (tma_kernel) {
       dim3 gb(sos_div_up(cols, RB_TILE_COLS), sos_div_up(rows, RB_TILE_ROWS), views);
-      static const int probe = getenv("SOS_REMAP_PROBE") ? atoi(getenv("SOS_REMAP_PROBE")) : 0;  // profiling only: 1 = no gathers, 2 = no stores
-      remap3b_kernel<<<gb, RP_WARPS_X * RP_WARPS_Y * 32, 0, ctx->stream>>>(src, wide_ok, probe, batch, src_h, src_w, lut, views, rows,
-                                                                           cols, k, dst);
+      remap3b_kernel<<<gb, RP_WARPS_X * RP_WARPS_Y * 32, 0, ctx->stream>>>(src, aligned8 ? 1 : 0, batch, src_h, src_w, lut, views,
+                                                                           rows, cols, k, dst);
     } else {
       dim3 gp(sos_div_up(cols, RP_COLS * RP_WARPS_X), sos_div_up(rows, RP_ROWS * RP_WARPS_Y), batch * views);
-      remap3p_kernel<<<gp, RP_WARPS_X * RP_WARPS_Y * 32, 0, ctx->stream>>>(src, wide_ok, src_h, src_w, lut, views, rows, cols,
-                                                                           k, dst);
+      remap3p_kernel<<<gp, RP_WARPS_X * RP_WARPS_Y * 32, 0, ctx->stream>>>(src, aligned8 ? 1 : 0, src_h, src_w, lut, views, rows,
+                                                                           cols, k, dst);
     }
+  } else if (channels == 1) {
+    remap_kernel<1><<<grid, 256, 0, ctx->stream>>>(src, wide_end, src_h, src_w, lut, views, rows, cols, k, dst);
   } else {
-    switch (channels) {
-      case 1: remap_kernel<1><<<grid, 256, 0, ctx->stream>>>(src, wide_end, src_h, src_w, lut, views, rows, cols, k, dst); break;
-      case 3: remap_kernel<3><<<grid, 256, 0, ctx->stream>>>(src, wide_end, src_h, src_w, lut, views, rows, cols, k, dst); break;
-      default: remap_kernel<4><<<grid, 256, 0, ctx->stream>>>(src, wide_end, src_h, src_w, lut, views, rows, cols, k, dst); break;
-    }
+    remap_kernel<4><<<grid, 256, 0, ctx->stream>>>(src, wide_end, src_h, src_w, lut, views, rows, cols, k, dst);
   }
   SOS_LAUNCHED(ctx);
   return SOS_OK;

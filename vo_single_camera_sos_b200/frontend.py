@@ -41,6 +41,7 @@ _BUF_FIELDS = [
     ("tm_pair_count", "i32"), ("p_ref", "f32"), ("p_cur", "f32"), ("f_cur", "f32"), ("cam", "u8"),
     ("n_corr", "i32"), ("n_corr_top", "i32"), ("ransac_pose", "f32"), ("pose", "f32"), ("best_hyp", "i32"),
     ("best_count", "i32"), ("n_refit", "i32"), ("inlier_mask", "u8"), ("stats", "i32"), ("refine_stats", "f64"), ("ref_slot", "i32"),
+    ("overflow", "i32"),
 ]
 
 
@@ -203,16 +204,28 @@ class Frontend:
                     if v.dtype != ndt or not v.flags.c_contiguous:
                         raise TypeError(f"{k}: expected a C-contiguous host array of {ndt}")
                     ptrs[k] = v.ctypes.data
+                if k.startswith("boff"):
+                    # host path: the offsets are at hand, so refuse what the device path can only clamp and count
+                    # (buffers()["overflow"]): non-monotonic offsets, rows beyond max_feat_per_view, oversized buckets
+                    o = np.asarray(v)
+                    w = np.diff(o, axis=1)
+                    if o.min() < 0 or o.max() > c.max_feat_per_view or w.min() < 0:
+                        raise ValueError(f"{k}: bucket offsets must be non-decreasing within [0, max_feat_per_view]")
+                    if w.max() > c.max_feat_per_bucket:
+                        raise ValueError(f"{k}: a bucket holds {int(w.max())} features, max_feat_per_bucket is "
+                                         f"{c.max_feat_per_bucket}")
         return [ptrs[k] for k in ("omni", "px_top", "desc_top", "boff_top", "px_bot", "desc_bot", "boff_bot")]
 
     def step(self, omni, px_top, desc_top, boff_top, px_bot, desc_bot, boff_bot):
         """Asynchronous step on device tensors; results are read through `buffers()`."""
         p = self._check_inputs(omni, px_top, desc_top, boff_top, px_bot, desc_bot, boff_bot, True)
+        self.ctx._sync_stream()   # fence against torch's CURRENT stream (the caller may have switched it since create)
         check(self.ctx.lib.sos_frontend_step(self._h, *p))
 
     def submit_host(self, omni, px_top, desc_top, boff_top, px_bot, desc_bot, boff_bot) -> int:
         p = self._check_inputs(omni, px_top, desc_top, boff_top, px_bot, desc_bot, boff_bot, False)
         t = C.c_int()
+        self.ctx._sync_stream()
         check(self.ctx.lib.sos_frontend_submit_host(self._h, *p, C.byref(t)))
         return t.value
 
@@ -227,12 +240,15 @@ class Frontend:
         arr = np.ascontiguousarray(np.asarray(slots, np.int32))
         if arr.shape != (self.cfg.batch,):
             raise ValueError("one reference slot per pair of the batch")
+        self.ctx._sync_stream()
         check(self.ctx.lib.sos_frontend_set_ref_slots(self._h, arr.ctypes.data))
 
     def promote(self, slot: int):
+        self.ctx._sync_stream()
         check(self.ctx.lib.sos_frontend_promote(self._h, int(slot)))
 
     def retrack(self):
+        self.ctx._sync_stream()
         check(self.ctx.lib.sos_frontend_retrack(self._h))
 
     def host_bytes(self):
@@ -263,6 +279,7 @@ class Frontend:
             "p_ref": (B, 2 * cap, 3), "p_cur": (B, 2 * cap, 3), "f_cur": (B, 2 * cap, 3), "cam": (B, 2 * cap),
             "n_corr": (B,), "n_corr_top": (B,), "ransac_pose": (B, 3, 4), "pose": (B, 3, 4), "best_hyp": (B,),
             "best_count": (B,), "n_refit": (B,), "inlier_mask": (B, 2 * cap), "stats": (B, 4), "refine_stats": (B, 4), "ref_slot": (B,),
+            "overflow": (B,),
         }
         out = {}
         for name, kind in _BUF_FIELDS:

@@ -30,11 +30,15 @@ class FeatureMatcher(object):
         self.num_of_features = kwargs.get("num_of_features", 100)
         self.use_radius_match = kwargs.get("use_radius_match", False)
         self.cross_check = kwargs.get("cross_check", False)   # BFMatcher(crossCheck=True), commented out at :401
-        self.ratio = kwargs.get("ratio", 0.75)                # Lowe ratio of the k_best == 2 branch (:421-436)
+        # Lowe's ratio test exists in the reference only for method == "SIFT" with k_best == 2 (:421-436, ratio 0.75);
+        # a "ratio" kwarg (not in the reference) requests it explicitly for binary descriptors.
+        self.ratio = kwargs.get("ratio", None)
         if matcher_type != "BF":
             raise NotImplementedError("only the brute-force matcher of the reference's default path is mirrored")
         if str(method).upper() in ("SIFT", "SURF"):
             raise NotImplementedError("float descriptors (L2 norm) are not on the SOS hot path; binary descriptors only")
+        if self.k_best > 2:
+            raise NotImplementedError("k_best > 2 is not mirrored (the device kernel keeps the two nearest neighbours)")
 
     def match_arrays(self, query_descriptors, train_descriptors, max_descriptor_distance_radius=-1, px_query=None,
                      px_train=None, max_horizontal_diff=-1.0, min_rectified_disparity=-1.0):
@@ -43,6 +47,8 @@ class FeatureMatcher(object):
         t = np.ascontiguousarray(train_descriptors, np.uint8)
         if q.ndim != 2 or t.ndim != 2 or q.shape[1] != 32 or t.shape[1] != 32:
             raise ValueError("descriptors must be N x 32 uint8 (256-bit)")
+        if self.use_radius_match:
+            raise NotImplementedError("radiusMatch is not used by the SOS / RGB-D trackers (use_radius_match=False)")
         nq, nt = len(q), len(t)
         empty = np.zeros(0, np.int32)
         if nq == 0 or nt == 0:
@@ -53,15 +59,30 @@ class FeatureMatcher(object):
         zero, nq_d, nt_d = i32(0), i32(nq), i32(nt)
         qd, td = to_device(q), to_device(t)
         i0, d0, i1, d1 = ctx.hamming_top2(qd, td, zero, nq_d, zero, nt_d, nq, nt, want_second=True)
-        if self.use_radius_match:
-            raise NotImplementedError("radiusMatch is not used by the SOS / RGB-D trackers (use_radius_match=False)")
+        gate = px_query is not None and px_train is not None
+        if self.k_best == 2 and not self.cross_check and self.ratio is None:
+            # camera_models.py:417-444 for binary descriptors: knnMatch(k=2) flattened query by query (both neighbours
+            # kept, no ratio test), then sorted(key=distance) — stable, so ties keep the (query, neighbour rank) order.
+            i0, d0, i1, d1 = (x.cpu().numpy() for x in (i0, d0, i1, d1))
+            qi = np.repeat(np.arange(nq, dtype=np.int32), 2)
+            ti = np.stack([i0, i1], 1).reshape(-1)
+            dd = np.stack([d0, d1], 1).reshape(-1)
+            have = ti >= 0                                   # a train set of one row yields one neighbour per query
+            qi, ti, dd = qi[have], ti[have], dd[have]
+            order = np.argsort(dd, kind="stable")
+            qi, ti, dd = qi[order], ti[order], dd[order]
+            if gate:
+                from .common_cv import filter_pixel_correspondences
+                ok = filter_pixel_correspondences(np.asarray(px_train)[ti], np.asarray(px_query)[qi],
+                                                  min_rectified_disparity, max_horizontal_diff)
+                qi, ti, dd = qi[ok], ti[ok], dd[ok]
+            return qi, ti.astype(np.int32), dd.astype(np.int32)
         mode, rev = ops.MATCH_NN, None
         if self.cross_check:
             mode = ops.MATCH_CROSS
             rev = ctx.hamming_top2(td, qd, zero, nt_d, zero, nq_d, nt, nq, want_second=False)[0]
         elif self.k_best == 2 and self.ratio is not None and self.ratio > 0:
             mode = ops.MATCH_RATIO
-        gate = px_query is not None and px_train is not None
         oq, ot, od, oc = ctx.match_select(
             mode, i0, d0, d1, zero, nq_d, zero, rev_idx0=rev,
             px_q=to_device(np.asarray(px_query)[:, :2], torch.float32) if gate else None,
