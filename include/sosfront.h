@@ -516,6 +516,9 @@ int sos_frontend_step_host(sos_frontend* fe, const uint8_t* omni, const float* p
 int sos_peak_popc(sos_ctx* ctx, double* tera_popc_per_s);
 int sos_peak_ffma(sos_ctx* ctx, double* tflops);
 int sos_peak_dfma(sos_ctx* ctx, double* tflops); /* float64 FMA pipe (dense triangulation, LM refinement) */
+int sos_peak_ffma2(sos_ctx* ctx, double* tflops); /* packed fma.rn.f32x2 (the form the RANSAC score kernel issues) */
+int sos_peak_tmem_read(sos_ctx* ctx, double* tera_bytes_per_s); /* tcgen05.ld bandwidth: epilogue bound of the tensor-core
+                                                                    Hamming engine */
 
 #ifdef __cplusplus
 }

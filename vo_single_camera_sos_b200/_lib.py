@@ -85,6 +85,8 @@ PROTOTYPES = {
     "sos_peak_popc": (I, [c_ctx, C.POINTER(D)]),
     "sos_peak_ffma": (I, [c_ctx, C.POINTER(D)]),
     "sos_peak_dfma": (I, [c_ctx, C.POINTER(D)]),
+    "sos_peak_ffma2": (I, [c_ctx, C.POINTER(D)]),
+    "sos_peak_tmem_read": (I, [c_ctx, C.POINTER(D)]),
 }
 
 

@@ -252,7 +252,7 @@ int enqueue_stage_a(sos_frontend* fe, const uint8_t* omni, const float* px_top, 
   stereo_segments_kernel<<<sos_div_up(B, 128), 128, 0, ctx->stream>>>(boff_top, boff_bot, B, nb, F, c.max_feat_per_bucket,
                                                                        d.st_q_start, d.st_q_len, d.st_t_start, d.st_t_len,
                                                                        d.overflow);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "stereo_segments_kernel");
   rc = sos_hamming_top2(ctx, desc_bot, desc_top, d.st_q_start, d.st_q_len, d.st_t_start, d.st_t_len, S,
                         c.max_feat_per_bucket, c.max_feat_per_bucket, d.st_idx0, d.st_d0, nullptr, nullptr);
   if (rc) return rc;
@@ -272,7 +272,7 @@ int enqueue_stage_a(sos_frontend* fe, const uint8_t* omni, const float* px_top, 
     dim3 grid(sos_div_up(cap, 128), B, 2);
     gather_desc_kernel<<<grid, 128, 0, ctx->stream>>>((const uint4*)desc_top, (const uint4*)desc_bot, d.src_top, d.src_bot,
                                                       d.n, B, cap, (uint4*)d.desc_c);
-    SOS_LAUNCHED(ctx);
+    SOS_LAUNCHED_AS(ctx, "gather_desc_kernel");
   }
   return SOS_OK;
 }
@@ -287,7 +287,7 @@ int enqueue_stage_b(sos_frontend* fe) {
   // step 2b: temporal matching, 2 views x B pairs
   temporal_segments_kernel<<<sos_div_up(2 * B, 128), 128, 0, ctx->stream>>>(d.n, c.keyframe_mode ? d.ref_slot : nullptr, B, cap,
                                                                             d.tm_q_start, d.tm_q_len, d.tm_t_start, d.tm_t_len);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "temporal_segments_kernel");
   rc = sos_hamming_top2(ctx, d.desc_c, d.desc_c, d.tm_q_start, d.tm_q_len, d.tm_t_start, d.tm_t_len, 2 * B, cap, cap,
                         d.tm_idx0, d.tm_d0, nullptr, nullptr);
   if (rc) return rc;
@@ -298,7 +298,7 @@ int enqueue_stage_b(sos_frontend* fe) {
   if (rc) return rc;
   assemble_kernel<<<dim3(sos_div_up(2 * cap, 256), B), 256, 0, ctx->stream>>>(d.tm_pair_q, d.tm_pair_t, d.tm_pair_count, d.tm_q_start, B, cap, d.xyz, d.b_top,
                                               d.b_bot, d.p_ref, d.p_cur, d.f_cur, d.cam, d.n_corr, d.n_corr_top);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "assemble_kernel");
   // step 5
   rc = c.solver == SOS_SOLVER_P3P
            ? sos_ransac_p3p(ctx, d.p_ref, d.f_cur, d.cam, d.n_corr, B, 2 * cap, c.rig, 2, fe->hyp, c.n_hyp, 0, c.ransac_threshold,
@@ -318,7 +318,7 @@ int enqueue_stage_b(sos_frontend* fe) {
     SOS_CUDA(cudaMemcpyAsync(d.pose, d.ransac_pose, (size_t)B * 12 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
   }
   stats_kernel<<<sos_div_up(B, 128), 128, 0, ctx->stream>>>(d.n, d.n_corr, d.best_count, d.best_hyp, B, d.stats);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "stats_kernel");
   return SOS_OK;
 }
 
@@ -327,7 +327,7 @@ int enqueue_carry(sos_frontend* fe, int from) {
   sos_frontend_buffers& d = fe->d;
   carry_over_kernel<<<sos_div_up(fe->cfg.cap, 256), 256, 0, ctx->stream>>>(fe->cfg.batch, from, fe->cfg.cap, d.uv_top, d.uv_bot,
                                                                             d.b_top, d.b_bot, d.xyz, d.desc_c, d.n);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "carry_over_kernel");
   return SOS_OK;
 }
 

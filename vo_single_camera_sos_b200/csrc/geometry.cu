@@ -485,7 +485,7 @@ static int lift_pano_impl(sos_ctx* ctx, const double* pano, const T* uv, int n, 
   SOS_CHECK_ARG(uv, "uv is NULL");
   SOS_CUDA(cudaSetDevice(ctx->device));
   lift_pano_kernel<T><<<sos_div_up(n, 256), 256, 0, ctx->stream>>>(load_pano(pano), uv, n, az, el, bearing);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "lift_pano_kernel");
   return SOS_OK;
 }
 
@@ -510,7 +510,7 @@ static int triangulate_impl(sos_ctx* ctx, const T* az1, const T* el1, const T* a
   triangulate_kernel<T><<<sos_div_up(n, 256), 256, 0, ctx->stream>>>(az1, el1, az2, el2, n, {f1[0], f1[1], f1[2]},
                                                                     {f2[0], f2[1], f2[2]}, rmin, rmax, homogeneous_norm,
                                                                     xyz, valid);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "triangulate_kernel");
   return SOS_OK;
 }
 
@@ -571,10 +571,10 @@ extern "C" int sos_stereo_lift_triangulate(sos_ctx* ctx, const double* pano_top,
   if (max_pairs_per_seg > 0) {
     dim3 grid(sos_div_up(max_pairs_per_seg, 256), n_segs);
     stereo_geometry_kernel<<<grid, 256, 0, ctx->stream>>>(a);
-    SOS_LAUNCHED(ctx);
+    SOS_LAUNCHED_AS(ctx, "stereo_geometry_kernel");
   }
   stereo_compact_kernel<<<n_segs, ST_THREADS, 0, ctx->stream>>>(a);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "stereo_compact_kernel");
   return SOS_OK;
 }
 
@@ -585,7 +585,7 @@ extern "C" int sos_gum_project(sos_ctx* ctx, const double* gum, const double* pt
   SOS_CHECK_ARG(pts && uv, "NULL array");
   SOS_CUDA(cudaSetDevice(ctx->device));
   gum_project_kernel<<<sos_div_up(n, 256), 256, 0, ctx->stream>>>(load_gum(gum), pts, n, uv);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "gum_project_kernel");
   return SOS_OK;
 }
 
@@ -599,7 +599,7 @@ extern "C" int sos_lut_build(sos_ctx* ctx, const double* gum, int rows, int cols
   dim3 grid(sos_div_up(cols, 256), rows);
   lut_build_kernel<<<grid, 256, 0, ctx->stream>>>(load_gum(gum), rows, cols, cyl_height_max, cyl_height_min, elev_lo,
                                                   elev_hi, map_x, map_y);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "lut_build_kernel");
   return SOS_OK;
 }
 
@@ -611,7 +611,7 @@ extern "C" int sos_lift_gum(sos_ctx* ctx, const double* gum, const double* uv, i
   SOS_CHECK_ARG(uv, "uv is NULL");
   SOS_CUDA(cudaSetDevice(ctx->device));
   lift_gum_kernel<<<sos_div_up(n, 256), 256, 0, ctx->stream>>>(load_gum(gum), uv, n, sphere, az, el);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "lift_gum_kernel");
   return SOS_OK;
 }
 
@@ -626,7 +626,7 @@ extern "C" int sos_rgbd_depth_to_z(sos_ctx* ctx, const double* cam, const float*
   for (int i = 0; i < SOS_RGBD_NPARAMS; ++i) c.v[i] = cam[i];
   dim3 grid(sos_div_up(w, 128), h, batch < RGBD_Z_SLICES ? batch : RGBD_Z_SLICES);
   rgbd_depth_to_z_kernel<<<grid, 128, 0, ctx->stream>>>(c, depth, batch, h, w, z);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "rgbd_depth_to_z_kernel");
   return SOS_OK;
 }
 
@@ -642,7 +642,7 @@ extern "C" int sos_rgbd_backproject(sos_ctx* ctx, const double* cam, const float
   for (int i = 0; i < SOS_RGBD_NPARAMS; ++i) c.v[i] = cam[i];
   dim3 grid(sos_div_up(n, 256), batch);
   rgbd_backproject_kernel<<<grid, 256, 0, ctx->stream>>>(c, depth, h, w, u, v, n, zmin, zmax, xyz, bearing, valid);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "rgbd_backproject_kernel");
   return SOS_OK;
 }
 
@@ -673,7 +673,7 @@ extern "C" int sos_angles_to_sphere_f64(sos_ctx* ctx, const double* az, const do
   SOS_CHECK_ARG(az && el && sphere, "NULL array");
   SOS_CUDA(cudaSetDevice(ctx->device));
   angles_to_sphere_kernel<<<sos_div_up(n, 256), 256, 0, ctx->stream>>>(az, el, n, sphere);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "angles_to_sphere_kernel");
   return SOS_OK;
 }
 
@@ -685,7 +685,7 @@ extern "C" int sos_range_gate_f64(sos_ctx* ctx, const double* xyz, int n, double
   SOS_CHECK_ARG(xyz && valid, "NULL array");
   SOS_CUDA(cudaSetDevice(ctx->device));
   range_gate_kernel<<<sos_div_up(n, 256), 256, 0, ctx->stream>>>(xyz, n, rmin, rmax, homogeneous_norm, valid);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "range_gate_kernel");
   return SOS_OK;
 }
 
@@ -709,17 +709,17 @@ extern "C" int sos_dense_triangulate(sos_ctx* ctx, const double* pano_top, const
   double4* table = (double4*)ws;
   dense_column_table_kernel<<<sos_div_up(cols, 256), 256, 0, ctx->stream>>>(
       load_pano(pano_top), load_pano(pano_bot), {f2[0] - f1[0], f2[1] - f1[1], f2[2] - f1[2]}, cols, table);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "dense_column_table_kernel");
   if (max_disparity == 0.0) {
     dmax = (float*)((uint8_t*)ws + table_bytes);
     disparity_max_kernel<<<n_maps, 1024, 0, ctx->stream>>>(disparity, rows, cols, roi_col0, roi_col1, dmax);
-    SOS_LAUNCHED(ctx);
+    SOS_LAUNCHED_AS(ctx, "disparity_max_kernel");
   }
   SOS_CHECK_ARG(rows <= 65535, "more than 65535 panorama rows");
   dense_triangulate_kernel<<<dim3(sos_div_up(cols, 256), sos_div_up(rows, DT_ROWS), n_maps), 256, 0, ctx->stream>>>(
       load_pano(pano_top), load_pano(pano_bot), table, disparity, rows, cols, n_maps, min_disparity, dmax, max_disparity,
       lowest_reference_row, roi_col0, roi_col1, {f1[0], f1[1], f1[2]}, {f2[0], f2[1], f2[2]},
       1.0 / pano_top[SOS_PANO_RADIUS], 1.0 / pano_bot[SOS_PANO_RADIUS], xyz, valid);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "dense_triangulate_kernel");
   return SOS_OK;
 }

@@ -511,7 +511,7 @@ extern "C" int sos_corner_min_eigenval(sos_ctx* ctx, const uint8_t* gray, int n_
   SOS_CUDA(cudaSetDevice(ctx->device));
   gft_eig_kernel<<<dim3(sos_div_up(width, 256), sos_div_up(height, GE_ROWS), n_images), 256, 0, ctx->stream>>>(gray, height, width, eig, nullptr, 0,
                                                                                                                  nullptr);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "gft_eig_kernel");
   return SOS_OK;
 }
 
@@ -556,13 +556,13 @@ extern "C" int sos_gft_detect(sos_ctx* ctx, const uint8_t* gray, const uint8_t* 
   SOS_CUDA(cudaMemsetAsync(flag, 0, sizeof(int32_t), ctx->stream));
   SOS_CUDA(cudaMemsetAsync(rank_img, 0xFF, px * sizeof(int32_t), ctx->stream));       // -1
   gft_pack_masks_kernel<<<(unsigned)((per + 255) / 256), 256, 0, ctx->stream>>>(masks, per, n_masks, mask_bits, flag);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "gft_pack_masks_kernel");
   gft_eig_kernel<<<dim3(grid.x, sos_div_up(height, GE_ROWS), grid.z), 256, 0, ctx->stream>>>(gray, height, width, eig, mask_bits, n_masks, max_bits);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "gft_eig_kernel");
   if (eig_out) SOS_CUDA(cudaMemcpyAsync(eig_out, eig, px * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
   gft_candidates_kernel<<<dim3(sos_div_up(width, 256), sos_div_up(height, GC_ROWS), n_images), 256, 0, ctx->stream>>>(
       eig, mask_bits, height, width, n_masks, max_bits, quality_level, GFT_CAP, keys, counts);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "gft_candidates_kernel");
   const size_t smem = gft_select_smem(GFT_CAP);
   // per device, so set on every call (a process may hold contexts on several devices)
   SOS_CUDA(cudaFuncSetAttribute(gft_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -589,13 +589,13 @@ extern "C" int sos_gft_detect(sos_ctx* ctx, const uint8_t* gray, const uint8_t* 
   if (!overlap) {
     gft_select_kernel<<<lists, GFT_THREADS, sel_smem, ctx->stream>>>(keys, counts, GFT_CAP, height, width, n_masks, -1, max_corners,
                                                                  min_dist_sq, reach, rank_img, out_xy, out_count);
-    SOS_LAUNCHED(ctx);
+    SOS_LAUNCHED_AS(ctx, "gft_select_kernel");
     return SOS_OK;
   }
   for (int m = 0; m < n_masks; ++m) {
     gft_select_kernel<<<n_images, GFT_THREADS, sel_smem, ctx->stream>>>(keys, counts, GFT_CAP, height, width, n_masks, m, max_corners,
                                                                     min_dist_sq, reach, rank_img, out_xy, out_count);
-    SOS_LAUNCHED(ctx);
+    SOS_LAUNCHED_AS(ctx, "gft_select_kernel");
   }
   return SOS_OK;
 }

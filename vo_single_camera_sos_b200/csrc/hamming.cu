@@ -363,7 +363,7 @@ extern "C" int sos_hamming_top2(sos_ctx* ctx, const uint32_t* q, const uint32_t*
   int32_t* n_items = (int32_t*)((char*)ws + partial_bytes + items_bytes);
 
   hamming_plan_kernel<<<1, 256, 0, ctx->stream>>>(q_len, n_seg, max_nq, splits, items, n_items);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "hamming_plan_kernel");
   const unsigned grid = (unsigned)max_items;
   if (use_mma) {
     rc = sos_hamming_mma_launch(ctx, q, t, q_start, q_len, t_start, t_len, n_seg, max_nq, max_nt, splits, items, n_items,
@@ -376,11 +376,11 @@ extern "C" int sos_hamming_top2(sos_ctx* ctx, const uint32_t* q, const uint32_t*
                                                                    n_items, (uint2*)ws)
     if (top2) HB_LAUNCH(true); else HB_LAUNCH(false);
 #undef HB_LAUNCH
-    SOS_LAUNCHED(ctx);
+    SOS_LAUNCHED_AS(ctx, "hamming_partial_kernel");
   }
   dim3 mgrid(sos_div_up(max_nq, 256), n_seg);
   hamming_merge_kernel<<<mgrid, 256, 0, ctx->stream>>>((const uint2*)ws, q_start, q_len, max_nq, splits, idx0, d0, idx1, d1);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "hamming_merge_kernel");
   return SOS_OK;
 }
 
@@ -406,7 +406,7 @@ extern "C" int sos_match_select(sos_ctx* ctx, int mode, double ratio, const int3
   a.max_du = max_du; a.min_dv = min_dv;
   a.out_q = out_q; a.out_t = out_t; a.out_d = out_d; a.out_count = out_count;
   match_select_kernel<<<n_seg, MS_THREADS, 0, ctx->stream>>>(a);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "match_select_kernel");
   return SOS_OK;
 }
 
@@ -432,6 +432,6 @@ extern "C" int sos_pixel_gate(sos_ctx* ctx, const double* pts_top, const double*
   SOS_CUDA(cudaSetDevice(ctx->device));
   pixel_gate_kernel<<<sos_div_up(n, 256), 256, 0, ctx->stream>>>((const double2*)pts_top, (const double2*)pts_bot, n, max_du,
                                                                   min_dv, valid);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "pixel_gate_kernel");
   return SOS_OK;
 }

@@ -346,11 +346,11 @@ int sos_hamming_mma_launch(sos_ctx* ctx, const uint32_t* q, const uint32_t* t, c
   uint8_t* b_exp = a_exp + (size_t)n_seg * qt * TILE_BYTES;
   if (qt > 0) {
     expand_kernel<<<dim3(qt, n_seg), 256, 0, ctx->stream>>>(q, q_start, q_len, max_nq, qt, 0, a_exp);
-    SOS_LAUNCHED(ctx);
+    SOS_LAUNCHED_AS(ctx, "hamming_expand_kernel");
   }
   if (tt > 0) {
     expand_kernel<<<dim3(tt, n_seg), 256, 0, ctx->stream>>>(t, t_start, t_len, max_nt, tt, 1, b_exp);
-    SOS_LAUNCHED(ctx);
+    SOS_LAUNCHED_AS(ctx, "hamming_expand_kernel");
   }
   Args a;
   a.a_exp = a_exp; a.b_exp = b_exp; a.q_len = q_len; a.t_len = t_len;
@@ -365,6 +365,6 @@ int sos_hamming_mma_launch(sos_ctx* ctx, const uint32_t* q, const uint32_t* t, c
   }
   if (top2) mma_kernel<true><<<max_items, THREADS, SMEM_BYTES, ctx->stream>>>(a);
   else mma_kernel<false><<<max_items, THREADS, SMEM_BYTES, ctx->stream>>>(a);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "hamming_mma_kernel");
   return SOS_OK;
 }

@@ -146,7 +146,7 @@ extern "C" int sos_median_blur_11(sos_ctx* ctx, const uint8_t* src, int n_images
   dim3 grid(sos_div_up(width, cols_per_block), sos_div_up(height, strip), n_images);
   if (channels == 3) median11_lane_kernel<3><<<grid, ML_WARPS * 32, 0, ctx->stream>>>(src, height, width, strip, dst, nullptr);
   else median11_lane_kernel<1><<<grid, ML_WARPS * 32, 0, ctx->stream>>>(src, height, width, strip, dst, nullptr);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "median11_lane_kernel");
   return SOS_OK;
 }
 
@@ -161,6 +161,6 @@ extern "C" int sos_median_blur_11_gray(sos_ctx* ctx, const uint8_t* src, int n_i
   const int strip = 128;
   dim3 grid(sos_div_up(width, ML_WARPS * (32 / 3)), sos_div_up(height, strip), n_images);
   median11_lane_kernel<3><<<grid, ML_WARPS * 32, 0, ctx->stream>>>(src, height, width, strip, dst_bgr, gray);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "median11_lane_kernel");
   return SOS_OK;
 }

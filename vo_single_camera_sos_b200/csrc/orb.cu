@@ -194,7 +194,7 @@ extern "C" int sos_bgr_to_gray(sos_ctx* ctx, const uint8_t* bgr, size_t n_pixels
   const int vec_ok = ((uintptr_t)bgr % 4 == 0) && ((uintptr_t)gray % 4 == 0);
   const size_t n_thr = (n_pixels + 3) / 4;
   bgr2gray_kernel<<<(unsigned)((n_thr + 255) / 256), 256, 0, ctx->stream>>>(bgr, n_pixels, gray, vec_ok);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "bgr2gray_kernel");
   return SOS_OK;
 }
 
@@ -207,7 +207,7 @@ extern "C" int sos_orb_blur(sos_ctx* ctx, const uint8_t* gray, int n_images, int
   SOS_CUDA(cudaSetDevice(ctx->device));
   dim3 grid(sos_div_up(width, 128), sos_div_up(height, BL_ROWS), n_images);
   orb_blur_kernel<<<grid, 128, 0, ctx->stream>>>(gray, height, width, gauss_7_sigma2(), blurred);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "orb_blur_kernel");
   return SOS_OK;
 }
 
@@ -225,6 +225,6 @@ extern "C" int sos_orb_describe(sos_ctx* ctx, const uint8_t* gray, int n_images,
   if (rc != SOS_OK) return rc;
   orb_describe_kernel<<<sos_div_up(n, 8), 256, 0, ctx->stream>>>((const uint8_t*)ws, height, width, (const float2*)kp_xy,
                                                                  kp_angle_deg, kp_image, n, desc, keep);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "orb_describe_kernel");
   return SOS_OK;
 }

@@ -1045,7 +1045,7 @@ template <int MODE>
 int launch_score(sos_ctx* ctx, const Rig& rig, dim3 grid, const float* p_ref, const float* q, const uint8_t* cam,
                  const int32_t* n, int cap, const HypRec* recs, int n_hyp, ScoreConst k, int32_t* counts) {
   score_kernel<MODE><<<grid, RS_THREADS, 0, ctx->stream>>>(p_ref, q, cam, n, cap, recs, n_hyp, k, rig, counts);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "score_kernel");
   return SOS_OK;
 }
 
@@ -1059,7 +1059,7 @@ extern "C" int sos_arun_batch(sos_ctx* ctx, const double* v0, const double* v1, 
   SOS_CHECK_ARG(v0 && v1 && M, "NULL array");
   SOS_CUDA(cudaSetDevice(ctx->device));
   arun_batch_kernel<<<sos_div_up(n_sets, 128), 128, 0, ctx->stream>>>(v0, v1, n_sets, k, with_scale, M, ok);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "arun_batch_kernel");
   return SOS_OK;
 }
 
@@ -1094,7 +1094,7 @@ int ransac_run(sos_ctx* ctx, int solver, const float* p_ref, const float* p_cur,
       hypothesize_p3p_kernel<<<hgrid, 128, 0, ctx->stream>>>(p_ref, f_cur, cam, n, cap, hyp, 0, n_hyp, r, s.recs, s.counts);
     else
       hypothesize_kernel<<<hgrid, 128, 0, ctx->stream>>>(p_ref, p_cur, n, cap, hyp, 0, n_hyp, r, s.recs, s.counts);
-    SOS_LAUNCHED(ctx);
+    SOS_LAUNCHED_AS(ctx, "hypothesize_kernel");
     if (cap > 0) {
       dim3 sgrid(sos_div_up(n_hyp, RS_TILE_H), sos_div_up(cap, RS_CHUNK), n_problems);
       const float* q = score_mode == SOS_SCORE_EUCLID ? p_cur : f_cur;
@@ -1106,7 +1106,7 @@ int ransac_run(sos_ctx* ctx, int solver, const float* p_ref, const float* p_cur,
   }
   argmax_kernel<<<n_problems, 256, 0, ctx->stream>>>(s.counts, s.recs, n_hyp, hyp_offset, best_pose, best_hyp,
                                                      best_count, best_key, s.best_rec);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "argmax_kernel");
   if (all_counts && n_hyp > 0)
     SOS_CUDA(cudaMemcpyAsync(all_counts, s.counts, (size_t)n_problems * n_hyp * sizeof(int32_t), cudaMemcpyDeviceToDevice,
                              ctx->stream));
@@ -1114,7 +1114,7 @@ int ransac_run(sos_ctx* ctx, int solver, const float* p_ref, const float* p_cur,
     dim3 mgrid(sos_div_up(cap, 256), n_problems);
     const float* q = score_mode == SOS_SCORE_EUCLID ? p_cur : f_cur;
     mask_kernel<<<mgrid, 256, 0, ctx->stream>>>(score_mode, p_ref, q, cam, n, cap, s.best_rec, r, threshold, inlier_mask, nullptr);
-    SOS_LAUNCHED(ctx);
+    SOS_LAUNCHED_AS(ctx, "mask_kernel");
   }
   return SOS_OK;
 }
@@ -1160,7 +1160,7 @@ extern "C" int sos_ransac_p3d_eval(sos_ctx* ctx, const float* p_ref, const float
   dim3 hgrid(1, n_problems);
   // one hypothesis per problem, each with its own row of sample numbers (stride 3 per problem)
   hypothesize_kernel<<<hgrid, 128, 0, ctx->stream>>>(p_ref, p_cur, n, cap, hyp_row, 3, 1, r, s.recs, s.counts);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "hypothesize_kernel");
   // counts[b] is 0 for a valid model and hugely negative otherwise: the mask kernel adds the inliers on top
   SOS_CUDA(cudaMemcpyAsync(count, s.counts, (size_t)n_problems * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
   SOS_CUDA(cudaMemcpy2DAsync(pose, 12 * sizeof(float), (const char*)s.recs + offsetof(HypRec, pose), sizeof(HypRec), 12 * sizeof(float), n_problems,
@@ -1169,7 +1169,7 @@ extern "C" int sos_ransac_p3d_eval(sos_ctx* ctx, const float* p_ref, const float
     dim3 mgrid(sos_div_up(cap, 256), n_problems);
     const float* q = score_mode == SOS_SCORE_EUCLID ? p_cur : f_cur;
     mask_kernel<<<mgrid, 256, 0, ctx->stream>>>(score_mode, p_ref, q, cam, n, cap, s.recs, r, threshold, inlier_mask, count);
-    SOS_LAUNCHED(ctx);
+    SOS_LAUNCHED_AS(ctx, "mask_kernel");
   }
   return SOS_OK;
 }
@@ -1182,6 +1182,6 @@ extern "C" int sos_refit_inliers(sos_ctx* ctx, const float* p_ref, const float* 
   SOS_CHECK_ARG(p_ref && p_cur && inlier_mask && n && pose, "NULL array");
   SOS_CUDA(cudaSetDevice(ctx->device));
   refit_kernel<<<n_problems, 1024, 0, ctx->stream>>>(p_ref, p_cur, inlier_mask, n, cap, pose, n_used);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "refit_kernel");
   return SOS_OK;
 }

@@ -439,7 +439,7 @@ static int lut_pack_impl(sos_ctx* ctx, const T* map_x, const T* map_y, int rows,
   SOS_CHECK_ARG(map_x && map_y && lut, "NULL array");
   SOS_CUDA(cudaSetDevice(ctx->device));
   lut_pack_kernel<T><<<sos_div_up((int)n, 256), 256, 0, ctx->stream>>>(map_x, map_y, (int)n, mask, src_h, src_w, lut);
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "lut_pack_kernel");
   return SOS_OK;
 }
 
@@ -492,6 +492,6 @@ extern "C" int sos_remap_u8(sos_ctx* ctx, const uint8_t* src, int batch, int src
   } else {
     remap_kernel<4><<<grid, 256, 0, ctx->stream>>>(src, wide_end, src_h, src_w, lut, views, rows, cols, k, dst);
   }
-  SOS_LAUNCHED(ctx);
+  SOS_LAUNCHED_AS(ctx, "remap_kernel");
   return SOS_OK;
 }

@@ -45,11 +45,13 @@ void sos_prof_mark_launch(sos_ctx* ctx, const char* name);
     }                                                                                      \
   } while (0)
 
-// Call after every kernel launch: counts it and surfaces launch-configuration errors.
-#define SOS_LAUNCHED(ctx)                                                                  \
+// Call after every kernel launch: counts it and surfaces launch-configuration errors.  The profiling mark carries the
+// kernel's name (SOS_LAUNCHED_AS) or, by default, the entry point that launched it.
+#define SOS_LAUNCHED(ctx) SOS_LAUNCHED_AS(ctx, __func__)
+#define SOS_LAUNCHED_AS(ctx, mark_name)                                                    \
   do {                                                                                     \
     (ctx)->launches++;                                                                     \
-    if ((ctx)->prof) sos_prof_mark_launch((ctx), __func__);                                \
+    if ((ctx)->prof) sos_prof_mark_launch((ctx), (mark_name));                             \
     cudaError_t e__ = cudaPeekAtLastError();                                               \
     if (e__ != cudaSuccess) {                                                              \
       (void)cudaGetLastError();                                                            \

@@ -592,6 +592,20 @@ class Context:
         check(self.lib.sos_peak_ffma(self._h, C.byref(v)))
         return v.value
 
+    def peak_ffma2(self) -> float:
+        """TFLOP/s of packed fma.rn.f32x2 (FFMA2)."""
+        self._sync_stream()
+        v = C.c_double()
+        check(self.lib.sos_peak_ffma2(self._h, C.byref(v)))
+        return v.value
+
+    def peak_tmem_read(self) -> float:
+        """TB/s of tcgen05.ld over all SMs (tensor memory -> registers)."""
+        self._sync_stream()
+        v = C.c_double()
+        check(self.lib.sos_peak_tmem_read(self._h, C.byref(v)))
+        return v.value
+
 
 _tls = threading.local()
 

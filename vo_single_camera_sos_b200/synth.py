@@ -162,14 +162,31 @@ def project_to_pano(rig: Rig, which: str, P_c: np.ndarray):
 
 
 def make_frame_features(rig: Rig, scene: Scene, T_c_wrt_w: np.ndarray, n_per_view: int, n_buckets: int, seed: int,
-                        cap: int, flip: float = 0.08, px_sigma: float = 0.15, distractors: float = 0.25, n_ties: int = 8):
+                        cap: int, flip: float = 0.08, px_sigma: float = 0.15, distractors: float = 0.25, n_ties: int = 8,
+                        dynamic: float = 0.0):
     """Features of one frame for both views, bucketed by azimuth (30 deg buckets, pose_est_tools.py:871-878).
+
+    dynamic: fraction of the landmarks that MOVE between frames (a fixed subset, chosen by landmark id): in every frame
+    each of them is displaced by an own random rotation of 8..20 degrees about the camera centre.  They still match by
+    descriptor (stereo and temporal) and triangulate consistently within a frame, but their temporal correspondences
+    violate the rigid motion by more than the 5 degree RANSAC threshold: outliers.  dynamic = 0.65 gives the 35 % inlier
+    rate the reference assumes (outlier fraction 0.65, pose_est_tools.py:675).
 
     Returns per view: px [cap,2] float32, desc [cap,32] uint8, bucket_off [n_buckets+1] int32, landmark id [cap] (-1 for
     distractors); rows beyond bucket_off[-1] are padding."""
     rng = np.random.default_rng(seed)
     Tw2c = np.linalg.inv(T_c_wrt_w)
     P_c = scene.landmarks @ Tw2c[:3, :3].T + Tw2c[:3, 3]
+    if dynamic > 0.0:
+        L = len(P_c)
+        dyn = ((np.arange(L, dtype=np.uint64) * np.uint64(2654435761)) % np.uint64(1000)) < np.uint64(int(round(dynamic * 1000)))
+        rd = np.random.default_rng(seed + 99991)          # own stream: the static features are those of dynamic = 0
+        ax = rd.normal(size=(L, 3))
+        ax /= np.linalg.norm(ax, axis=1, keepdims=True)
+        ang = np.deg2rad(rd.uniform(8.0, 20.0, L))[:, None]
+        # Rodrigues: p cos(a) + (k x p) sin(a) + k (k.p) (1 - cos(a))
+        rot = P_c * np.cos(ang) + np.cross(ax, P_c) * np.sin(ang) + ax * np.sum(ax * P_c, axis=1, keepdims=True) * (1 - np.cos(ang))
+        P_c = np.where(dyn[:, None], rot, P_c)
     out = {}
     # both views favour landmarks visible in both mirrors so that stereo matching has something to find
     vis_both = None

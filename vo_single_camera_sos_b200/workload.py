@@ -35,13 +35,14 @@ class Workload:
     masks: dict
     maps: dict                 # float64 LUT maps on the host (for the CPU baseline / oracle)
     trajectory: np.ndarray
+    moving_fraction: float = 0.0   # share of moving landmarks (synth.make_frame_features `dynamic`): 0.79 -> ~35 % RANSAC inliers
 
     def frontend(self, ctx: ops.Context) -> Frontend:
         return Frontend(ctx, self.cfg, self.lut, self.hyp)
 
 
 def build(ctx: ops.Context, name: str, batch: int, n_frames: int, seed: int = 0, score_mode: int = ops.SCORE_BEARING,
-          n_hyp: int | None = None, solver: int = ops.SOLVER_ARUN) -> Workload:
+          n_hyp: int | None = None, solver: int = ops.SOLVER_ARUN, moving_fraction: float = 0.0) -> Workload:
     c = CONFIGS[name]
     rig = synth.make_rig(c["width"], c["height"], c["pano_cols"], seed=seed)
     scene = synth.make_scene(int(c["feat"] * 2.0), seed=seed)
@@ -65,7 +66,7 @@ def build(ctx: ops.Context, name: str, batch: int, n_frames: int, seed: int = 0,
                          max_feat_per_view=c["cap"], max_feat_per_bucket=c["max_bucket"], cap=c["cap"], n_hyp=H,
                          score_mode=score_mode, ransac_threshold=thr, solver=solver)
     traj = synth.make_trajectory(n_frames, seed=seed)
-    return Workload(name, rig, scene, cfg, lut, hyp, hyp_host, masks, maps, traj)
+    return Workload(name, rig, scene, cfg, lut, hyp, hyp_host, masks, maps, traj, float(moving_fraction))
 
 
 def make_frames(w: Workload, first: int, count: int, render: bool = True, lift=None, renderer: "DeviceRenderer" = None):
@@ -83,7 +84,7 @@ def make_frames(w: Workload, first: int, count: int, render: bool = True, lift=N
     for i in range(n):
         T = w.trajectory[first + i]
         f = synth.make_frame_features(w.rig, w.scene, T, c["feat"], cfg.n_buckets, seed=1000 * (first + i) + 17,
-                                      cap=cfg.max_feat_per_view)
+                                      cap=cfg.max_feat_per_view, dynamic=w.moving_fraction)
         for which in ("top", "bot"):
             out[f"px_{which}"][i] = f[which]["px"]
             out[f"desc_{which}"][i] = f[which]["desc"]
