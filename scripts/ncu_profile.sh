@@ -7,8 +7,8 @@ tag=${1:-r01}
 what=${2:-launches}
 short=${3:-$what}
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu ${SOS_BENCH_ARGS:-}"
-KREGEX='regex:remap|hamming_|match_select|stereo_|score_kernel|hypothesize|argmax_kernel|mask_kernel|refit_kernel|refine_kernel|gather_desc|assemble_kernel|segments_kernel|stats_kernel|carry_over'
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu --no-extras ${SOS_BENCH_ARGS:-}"
+KREGEX='regex:remap|hamming_|mma_kernel|expand_kernel|match_select|stereo_|score_kernel|hypothesize|argmax_kernel|mask_kernel|refit_kernel|refine_kernel|gather_desc|assemble_kernel|segments_kernel|stats_kernel|carry_over'
 $CMD > gpurun_out/${tag}_plain.log 2>&1 || { echo "plain run failed"; tail -20 gpurun_out/${tag}_plain.log; exit 1; }
 tail -c 600 gpurun_out/${tag}_plain.log; echo
 if [ "$what" = launches ]; then

@@ -29,6 +29,9 @@ def test_sharded_sequence_equals_the_undivided_run(ctx):
         assert sequence.trajectory_digest(rel, st) == sequence.trajectory_digest(rel1, st1)
     traj, failed = sequence.chain_trajectory(rel1, st1)
     assert failed == []
-    gt = np.linalg.inv(w.trajectory[0]) @ w.trajectory[n - 1]
-    assert np.linalg.norm(traj[-1][:3, 3] - gt[:3, 3]) < 0.25
+    # sanity against the ground-truth motion, pair by pair (tiny geometry: the bars of tests/test_gpu_frontend.py)
+    for f in range(1, n):
+        gt = np.linalg.inv(w.trajectory[f - 1]) @ w.trajectory[f]
+        assert np.allclose(rel1[f][:, :3], gt[:3, :3], atol=0.05) and np.allclose(rel1[f][:, 3], gt[:3, 3], atol=0.15)
+    assert np.isfinite(traj).all()
     fe.close()

@@ -482,16 +482,17 @@ extern "C" int sos_remap_u8(sos_ctx* ctx, const uint8_t* src, int batch, int src
       dim3 gb(sos_div_up(cols, RB_TILE_COLS), sos_div_up(rows, RB_TILE_ROWS), views);
       remap3b_kernel<<<gb, RP_WARPS_X * RP_WARPS_Y * 32, 0, ctx->stream>>>(src, aligned8 ? 1 : 0, batch, src_h, src_w, lut, views,
                                                                            rows, cols, k, dst);
+      SOS_LAUNCHED_AS(ctx, "remap3b_kernel");
     } else {
       dim3 gp(sos_div_up(cols, RP_COLS * RP_WARPS_X), sos_div_up(rows, RP_ROWS * RP_WARPS_Y), batch * views);
       remap3p_kernel<<<gp, RP_WARPS_X * RP_WARPS_Y * 32, 0, ctx->stream>>>(src, aligned8 ? 1 : 0, src_h, src_w, lut, views, rows,
                                                                            cols, k, dst);
+      SOS_LAUNCHED_AS(ctx, "remap3p_kernel");
     }
-  } else if (channels == 1) {
-    remap_kernel<1><<<grid, 256, 0, ctx->stream>>>(src, wide_end, src_h, src_w, lut, views, rows, cols, k, dst);
   } else {
-    remap_kernel<4><<<grid, 256, 0, ctx->stream>>>(src, wide_end, src_h, src_w, lut, views, rows, cols, k, dst);
+    if (channels == 1) remap_kernel<1><<<grid, 256, 0, ctx->stream>>>(src, wide_end, src_h, src_w, lut, views, rows, cols, k, dst);
+    else remap_kernel<4><<<grid, 256, 0, ctx->stream>>>(src, wide_end, src_h, src_w, lut, views, rows, cols, k, dst);
+    SOS_LAUNCHED_AS(ctx, "remap_kernel");
   }
-  SOS_LAUNCHED_AS(ctx, "remap_kernel");
   return SOS_OK;
 }
