@@ -30,6 +30,8 @@
 //   warp 2        : tensor-memory allocation
 //   warps 4..11   : epilogue, one thread per (query tile, row)
 // The per-split partial keys use the POPC engine's format and are merged by the same hamming_merge_kernel.
+#include <stdlib.h>
+
 #include "sos_common.cuh"
 
 namespace sos_hamming_mma {
@@ -39,9 +41,8 @@ constexpr int KB = 288;                          // bytes of K per row: 256 sign
 constexpr int CHUNKS = KB / 16;                  // 18 core-matrix columns
 constexpr int GROUP_BYTES = CHUNKS * 128;        // one 8-row group: 18 core matrices of 8 x 16 bytes
 constexpr int TILE_BYTES = (TILE / 8) * GROUP_BYTES;  // 36864
-constexpr int STAGES = 3;
 constexpr int THREADS = 384;
-constexpr int SMEM_BYTES = (2 + STAGES) * TILE_BYTES + 256;
+constexpr int smem_bytes(int stages) { return (2 + stages) * TILE_BYTES + 256; }
 constexpr int PAD_DROP = 30 * 127 * 128;         // what the 30 pad columns subtract from a padding row's accumulator
 constexpr int KEY_IDX_BITS = 22;                 // must match hamming.cu
 constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
@@ -196,7 +197,7 @@ struct Args {
   uint2* partial;
 };
 
-template <bool TOP2>
+template <bool TOP2, int STAGES>
 __global__ void __launch_bounds__(THREADS, 1) mma_kernel(Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((int)blockIdx.x >= *a.n_items) return;
@@ -214,18 +215,19 @@ __global__ void __launch_bounds__(THREADS, 1) mma_kernel(Args a) {
   uint8_t* sA = smem;
   uint8_t* sB = smem + 2 * TILE_BYTES;
   uint64_t* bars = (uint64_t*)(smem + (2 + STAGES) * TILE_BYTES);
-  // bars[0..2] full (train stage landed), [3..5] empty (stage consumed), [6..7] accumulator full, [8..9] accumulator drained,
-  // [10] query tiles landed
-  uint32_t* tmem_slot = (uint32_t*)(bars + 12);
+  // bars: FULL + s (train stage landed), EMPTY + s (stage consumed), TFULL + b (accumulator complete), TEMPTY + b
+  // (accumulator drained), AFULL (query tiles landed)
+  constexpr int FULL = 0, EMPTY = STAGES, TFULL = 2 * STAGES, TEMPTY = 2 * STAGES + 2, AFULL = 2 * STAGES + 4;
+  uint32_t* tmem_slot = (uint32_t*)(bars + AFULL + 1);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
   if (n_iter > 0) {   // block-uniform
     if (tid == 0) {
-      for (int i = 0; i < STAGES; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); }
-      mbar_init(BAR(6), 1); mbar_init(BAR(7), 1);
-      mbar_init(BAR(8), 8); mbar_init(BAR(9), 8);
-      mbar_init(BAR(10), 1);
+      for (int i = 0; i < STAGES; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1); }
+      mbar_init(BAR(TFULL), 1); mbar_init(BAR(TFULL + 1), 1);
+      mbar_init(BAR(TEMPTY), 8); mbar_init(BAR(TEMPTY + 1), 8);
+      mbar_init(BAR(AFULL), 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -241,37 +243,37 @@ __global__ void __launch_bounds__(THREADS, 1) mma_kernel(Args a) {
       if (lane == 0) {
         // the item's two query tiles, then the ring of train tiles
         const uint8_t* ga = a.a_exp + ((size_t)seg * a.q_tiles_per_seg + (size_t)q_tile * 2) * TILE_BYTES;
-        mbar_expect_tx(BAR(10), 2u * TILE_BYTES);
+        mbar_expect_tx(BAR(AFULL), 2u * TILE_BYTES);
 #pragma unroll
-        for (int p = 0; p < 8; ++p) bulk_g2s(smem_u32(sA) + p * (TILE_BYTES / 4), ga + (size_t)p * (TILE_BYTES / 4), TILE_BYTES / 4, BAR(10));
+        for (int p = 0; p < 8; ++p) bulk_g2s(smem_u32(sA) + p * (TILE_BYTES / 4), ga + (size_t)p * (TILE_BYTES / 4), TILE_BYTES / 4, BAR(AFULL));
         const uint8_t* gb = a.b_exp + ((size_t)seg * a.t_tiles_per_seg + tile_begin) * TILE_BYTES;
         for (int it = 0; it < n_iter; ++it) {
           const int s = it % STAGES;
-          mbar_wait(BAR(3 + s), ((it / STAGES) & 1) ^ 1);
-          mbar_expect_tx(BAR(s), TILE_BYTES);
+          mbar_wait(BAR(EMPTY + s), ((it / STAGES) & 1) ^ 1);
+          mbar_expect_tx(BAR(FULL + s), TILE_BYTES);
           const uint32_t dst = smem_u32(sB) + s * TILE_BYTES;
 #pragma unroll
           for (int p = 0; p < 4; ++p)
-            bulk_g2s(dst + p * (TILE_BYTES / 4), gb + (size_t)it * TILE_BYTES + (size_t)p * (TILE_BYTES / 4), TILE_BYTES / 4, BAR(s));
+            bulk_g2s(dst + p * (TILE_BYTES / 4), gb + (size_t)it * TILE_BYTES + (size_t)p * (TILE_BYTES / 4), TILE_BYTES / 4, BAR(FULL + s));
         }
       }
       __syncwarp();
     } else if (warp == 1) {
       if (lane == 0) {
-        mbar_wait(BAR(10), 0);
+        mbar_wait(BAR(AFULL), 0);
         const uint64_t da0 = smem_desc(smem_u32(sA)), da1 = smem_desc(smem_u32(sA) + TILE_BYTES);
         for (int it = 0; it < n_iter; ++it) {
           const int s = it % STAGES, b = it & 1;
-          mbar_wait(BAR(8 + b), ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator buffer
-          mbar_wait(BAR(s), (it / STAGES) & 1);         // the train tile has landed
+          mbar_wait(BAR(TEMPTY + b), ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator buffer
+          mbar_wait(BAR(FULL + s), (it / STAGES) & 1);       // the train tile has landed
           tc_fence_after();
           const uint64_t db = smem_desc(smem_u32(sB) + s * TILE_BYTES);
 #pragma unroll
           for (int k = 0; k < KB / 32; ++k) tc_mma_i8(tmem + (uint32_t)(b * 2) * TILE, da0 + (uint64_t)(16 * k), db + (uint64_t)(16 * k), IDESC, k > 0);
 #pragma unroll
           for (int k = 0; k < KB / 32; ++k) tc_mma_i8(tmem + (uint32_t)(b * 2 + 1) * TILE, da1 + (uint64_t)(16 * k), db + (uint64_t)(16 * k), IDESC, k > 0);
-          tc_commit(BAR(3 + s));   // shared-memory stage free once these MMAs have read it
-          tc_commit(BAR(6 + b));   // accumulators complete
+          tc_commit(BAR(EMPTY + s));   // shared-memory stage free once these MMAs have read it
+          tc_commit(BAR(TFULL + b));   // accumulators complete
         }
       }
       __syncwarp();
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(THREADS, 1) mma_kernel(Args a) {
       uint32_t k0 = KEY_NONE, k1 = KEY_NONE;
       for (int it = 0; it < n_iter; ++it) {
         const int b = it & 1;
-        mbar_wait(BAR(6 + b), (it >> 1) & 1);
+        mbar_wait(BAR(TFULL + b), (it >> 1) & 1);
         tc_fence_after();
         const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 2 + g) * TILE;
         int m0 = INT_MIN, m1 = INT_MIN;
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(THREADS, 1) mma_kernel(Args a) {
         tmem_ld_wait(vb);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(8 + b));          // buffer b may be overwritten
+        if (lane == 0) mbar_arrive(BAR(TEMPTY + b));     // buffer b may be overwritten
         reduce32<TOP2>(vb, m0, m1);
         const int tile = tile_begin + it;
         const uint32_t key0 = acc_to_key(m0, tile);
@@ -356,15 +358,24 @@ int sos_hamming_mma_launch(sos_ctx* ctx, const uint32_t* q, const uint32_t* t, c
   a.a_exp = a_exp; a.b_exp = b_exp; a.q_len = q_len; a.t_len = t_len;
   a.max_nq = max_nq; a.max_nt = max_nt; a.splits = splits; a.q_tiles_per_seg = qt; a.t_tiles_per_seg = tt;
   a.items = items; a.n_items = n_items; a.partial = partial;
-  static bool attr_set[64][2] = {};     // per device: the opt-in to > 48 KB of dynamic shared memory
-  const int dev = ctx->device & 63, v = top2 ? 1 : 0;
-  if (!attr_set[dev][v]) {
-    if (top2) SOS_CUDA(cudaFuncSetAttribute(mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    else SOS_CUDA(cudaFuncSetAttribute(mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set[dev][v] = true;
-  }
-  if (top2) mma_kernel<true><<<max_items, THREADS, SMEM_BYTES, ctx->stream>>>(a);
-  else mma_kernel<false><<<max_items, THREADS, SMEM_BYTES, ctx->stream>>>(a);
+  // EXPERIMENT (round 2): depth of the train-tile ring (3 stages = 184 KB, 4 stages = 221 KB of shared memory)
+  const char* e = getenv("SOS_HAMMING_STAGES");
+  const int stages = (e && atoi(e) == 3) ? 3 : 4;
+  static bool attr_set[64][4] = {};     // per device: the opt-in to > 48 KB of dynamic shared memory
+  const int dev = ctx->device & 63, v = (top2 ? 1 : 0) + (stages == 4 ? 2 : 0);
+#define MMA_CASE(T2, ST)                                                                                               \
+  do {                                                                                                                 \
+    if (!attr_set[dev][v]) {                                                                                           \
+      SOS_CUDA(cudaFuncSetAttribute(mma_kernel<T2, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(ST))); \
+      attr_set[dev][v] = true;                                                                                         \
+    }                                                                                                                  \
+    mma_kernel<T2, ST><<<max_items, THREADS, smem_bytes(ST), ctx->stream>>>(a);                                         \
+  } while (0)
+  if (top2 && stages == 4) MMA_CASE(true, 4);
+  else if (top2) MMA_CASE(true, 3);
+  else if (stages == 4) MMA_CASE(false, 4);
+  else MMA_CASE(false, 3);
+#undef MMA_CASE
   SOS_LAUNCHED_AS(ctx, "hamming_mma_kernel");
   return SOS_OK;
 }

@@ -18,6 +18,7 @@
 //   mask         re-evaluates the winner with the very same float32 instruction sequence -> inlier mask.
 #include <math_constants.h>
 #include <stddef.h>
+#include <stdlib.h>
 
 #include "sos_common.cuh"
 
@@ -690,21 +691,21 @@ __device__ __forceinline__ void decision2(const float2* __restrict__ A, const Po
 // pair of the batch was inside the guard band.  Otherwise the (batch, hypothesis) is queued and re-decided after the
 // loop, uncertain pairs in float64 — keeping that path out of the loop keeps the warps converged (measured: the
 // in-loop version ran with 24 of 32 lanes active).
-template <int MODE>
-__global__ void __launch_bounds__(RS_THREADS)
+template <int MODE, int HPT, int CHUNK, int MINB>
+__global__ void __launch_bounds__(RS_THREADS, MINB)
 score_kernel(const float* __restrict__ p_ref, const float* __restrict__ q_arr, const uint8_t* __restrict__ cam,
              const int32_t* __restrict__ n_arr, int cap, const HypRec* __restrict__ recs, int n_hyp, ScoreConst k,
              const __grid_constant__ Rig rig, int32_t* __restrict__ counts) {
-  __shared__ PointRec pts[RS_CHUNK];
-  __shared__ unsigned char pcam[RS_CHUNK];
-  __shared__ float pguard[RS_CHUNK];
+  __shared__ PointRec pts[CHUNK];
+  __shared__ unsigned char pcam[CHUNK];
+  __shared__ float pguard[CHUNK];
   __shared__ uint32_t queue[RS_QCAP];
   __shared__ int queue_n, switch_count, switch_at;
   const int b = blockIdx.z;
   const int n = n_arr[b];
-  const int j0 = blockIdx.y * RS_CHUNK;
+  const int j0 = blockIdx.y * CHUNK;
   if (j0 >= n) return;
-  const int nj = min(RS_CHUNK, n - j0);
+  const int nj = min(CHUNK, n - j0);
   const bool multi_cam = rig.n_cams > 1 && cam != nullptr;
   if (threadIdx.x == 0) {
     queue_n = 0;
@@ -734,13 +735,13 @@ score_kernel(const float* __restrict__ p_ref, const float* __restrict__ q_arr, c
     pcam[j] = (unsigned char)c;
     pguard[j] = g;
   }
-  constexpr int NP = RS_HPT / 2;
+  constexpr int NP = HPT / 2;
   float2 A[NP][12];
-  int cnt[RS_HPT];
-  const HypRec* rec[RS_HPT];
+  int cnt[HPT];
+  const HypRec* rec[HPT];
 #pragma unroll
-  for (int r = 0; r < RS_HPT; ++r) {
-    int h = blockIdx.x * RS_TILE_H + r * RS_THREADS + threadIdx.x;
+  for (int r = 0; r < HPT; ++r) {
+    int h = blockIdx.x * (RS_THREADS * HPT) + r * RS_THREADS + threadIdx.x;
     if (h >= n_hyp) h = n_hyp - 1;  // duplicate work, never stored
     rec[r] = recs + (size_t)b * n_hyp + h;
     cnt[r] = 0;
@@ -769,10 +770,10 @@ score_kernel(const float* __restrict__ p_ref, const float* __restrict__ q_arr, c
         A[pr][i] = make_float2(__ldg(&rec[2 * pr]->xf[c][i]), __ldg(&rec[2 * pr + 1]->xf[c][i]));
     for (int jb = j_begin; jb < j_end; jb += RS_BATCH) {
       const int je = min(j_end, jb + RS_BATCH);
-      int nlo[RS_HPT], nhi[RS_HPT];
+      int nlo[HPT], nhi[HPT];
 #pragma unroll
-      for (int r = 0; r < RS_HPT; ++r) nlo[r] = nhi[r] = 0;
-#pragma unroll 2
+      for (int r = 0; r < HPT; ++r) nlo[r] = nhi[r] = 0;
+#pragma unroll(HPT == 2 ? 4 : 2)
       for (int j = jb; j < je; ++j) {
         const PointRec pt = pts[j];
 #pragma unroll
@@ -786,7 +787,7 @@ score_kernel(const float* __restrict__ p_ref, const float* __restrict__ q_arr, c
         }
       }
 #pragma unroll
-      for (int r = 0; r < RS_HPT; ++r) {
+      for (int r = 0; r < HPT; ++r) {
         if (nlo[r] == nhi[r]) {
           cnt[r] += (je - jb) - nlo[r];  // all decided: inliers = pairs whose D - g is not negative
         } else {  // rare; two instructions long so that the warp stays converged
@@ -802,7 +803,7 @@ score_kernel(const float* __restrict__ p_ref, const float* __restrict__ q_arr, c
   if (nq > RS_QCAP) {  // block-uniform; queue overflow has never been observed: redo the whole chunk in float64
     nq = 0;
 #pragma unroll 1
-    for (int r = 0; r < RS_HPT; ++r) {
+    for (int r = 0; r < HPT; ++r) {
       cnt[r] = 0;
 #pragma unroll 1
       for (int j = 0; j < nj; ++j) {
@@ -814,8 +815,8 @@ score_kernel(const float* __restrict__ p_ref, const float* __restrict__ q_arr, c
     }
   }
 #pragma unroll
-  for (int r = 0; r < RS_HPT; ++r) {
-    const int h = blockIdx.x * RS_TILE_H + r * RS_THREADS + threadIdx.x;
+  for (int r = 0; r < HPT; ++r) {
+    const int h = blockIdx.x * (RS_THREADS * HPT) + r * RS_THREADS + threadIdx.x;
     if (h < n_hyp && cnt[r] != 0) atomicAdd(&counts[(size_t)b * n_hyp + h], cnt[r]);
   }
   // deferred pass: queue entry = (first point, length <= RS_BATCH, hypothesis slot r, owning thread); every pair of the
@@ -823,7 +824,7 @@ score_kernel(const float* __restrict__ p_ref, const float* __restrict__ q_arr, c
   for (int e = threadIdx.x; e < nq; e += RS_THREADS) {
     const uint32_t v = queue[e];
     const int jb = (int)(v >> 16), len = (int)((v >> 10) & 0x3F), r = (int)((v >> 8) & 0x3), t = (int)(v & 0xFF);
-    const int h = blockIdx.x * RS_TILE_H + r * RS_THREADS + t;
+    const int h = blockIdx.x * (RS_THREADS * HPT) + r * RS_THREADS + t;
     if (h >= n_hyp) continue;
     const HypRec* hr = recs + (size_t)b * n_hyp + h;
     int add = 0;
@@ -1044,7 +1045,19 @@ int ransac_scratch(sos_ctx* ctx, int n_problems, int n_hyp, RansacScratch& s) {
 template <int MODE>
 int launch_score(sos_ctx* ctx, const Rig& rig, dim3 grid, const float* p_ref, const float* q, const uint8_t* cam,
                  const int32_t* n, int cap, const HypRec* recs, int n_hyp, ScoreConst k, int32_t* counts) {
-  score_kernel<MODE><<<grid, RS_THREADS, 0, ctx->stream>>>(p_ref, q, cam, n, cap, recs, n_hyp, k, rig, counts);
+  // EXPERIMENT (round 2): occupancy / ILP variants of the scoring kernel, selected per call
+  const char* e = getenv("SOS_SCORE_VARIANT");
+  const int v = e ? atoi(e) : 0;
+  const int n_problems = grid.z;
+#define SCORE_LAUNCH(HPT, CHUNK, MINB)                                                                                  \
+  score_kernel<MODE, HPT, CHUNK, MINB><<<dim3(sos_div_up(n_hyp, RS_THREADS * HPT), sos_div_up(cap, CHUNK), n_problems), \
+                                         RS_THREADS, 0, ctx->stream>>>(p_ref, q, cam, n, cap, recs, n_hyp, k, rig, counts)
+  if (v == 1) SCORE_LAUNCH(2, 256, 8);
+  else if (v == 2) SCORE_LAUNCH(2, 512, 6);
+  else if (v == 3) SCORE_LAUNCH(4, 256, 5);
+  else if (v == 4) SCORE_LAUNCH(2, 256, 6);
+  else SCORE_LAUNCH(4, 512, 4);
+#undef SCORE_LAUNCH
   SOS_LAUNCHED_AS(ctx, "score_kernel");
   return SOS_OK;
 }
