@@ -306,6 +306,7 @@ def run_gpu(args, rank, local_rank, world):
     pin_sets = [workload.to_pinned(fr) for fr in sets]
     in_bytes = sum(int(t.numel() * t.element_size()) for t in dev_sets[0])
     fe = w.frontend(ctx)
+    ctx_sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
 
     def barrier():
         if world > 1:
@@ -380,7 +381,10 @@ def run_gpu(args, rank, local_rank, world):
     n_corr = buf["n_corr"].cpu().numpy().astype(np.int64)
     rows, cols = w.cfg.pano_rows, w.cfg.pano_cols
     remap_bytes = B * (2 * rows * cols * (8 + 3) + c["height"] * c["width"] * 3)
-    flop_pair = 30.0 if args.score == "euclid" else 45.0
+    flop_pair = 30.0 if args.score == "euclid" else 45.0          # SURVEY 8d's model
+    # executed per pair, counted in the SASS of score_kernel's inner loop (8 pairs per trip): bearing 68 FFMA2 + 8 FMUL2 =
+    # 17 FFMA + 2 FMUL = 36 FLOP; euclid 52 FFMA2 + 12 FADD2 + 4 FMUL2 = 13 FFMA + 3 FADD + 1 FMUL = 30 FLOP
+    flop_exec = 30.0 if args.score == "euclid" else 36.0
     popc_peak = ctx.peak_popc()   # T POPC/s, measured on this GPU just now
     ffma_peak = ctx.peak_ffma()   # TFLOP/s, measured
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
@@ -408,19 +412,26 @@ def run_gpu(args, rank, local_rank, world):
     for tag, idx, pairs in (("stereo", 0, st_pairs), ("temporal", 1, tm_pairs)):
         if mma_engine and f"hamming_mma_kernel#{idx}" in kernels:
             t = k_ms(f"hamming_mma_kernel#{idx}")
-            tb = pairs * 4.0 / (t * 1e-3) / 1e12
+            # int8 tensor peak: 8192 MAC/clk/SM (M128 N128 K32 per 64 clk: the rate ncu's sm__pipe_tensor_cycles_active counts
+            # against) at the SM clock seen during the run; no measured int8 figure exists in MEASURED_PEAKS.json, so the bf16
+            # figures are shown beside it (int8 = 2 x bf16 nominal)
+            sm_clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
+            tensor_peak = ctx_sm_count * 8192 * 2 * sm_clk / 1e12
+            tops = pairs * 288.0 * 2.0 / (t * 1e-3) / 1e12
             roof[f"hamming_{tag}"] = {
-                "kernel": "hamming_mma_kernel (tcgen05.mma kind::i8 + tcgen05.ld epilogue)", "bound": "tmem-read", "achieved": tb,
-                "peak": tmem_peak, "unit": "TB/s", "frac": tb / tmem_peak, "ms": t,
-                "peak_source": "tcgen05.ld microbenchmark run in this process (sos_peak_tmem_read)", "descriptor_pairs": pairs,
-                "matches_per_s": pairs / (t * 1e-3), "traffic": None,
-                "tensor_int8_tops": pairs * 288.0 * 2.0 / (t * 1e-3) / 1e12,
+                "kernel": "hamming_mma_kernel (tcgen05.mma kind::i8 + tcgen05.ld epilogue)", "bound": "tensor", "achieved": tops,
+                "peak": tensor_peak, "unit": "TOP/s (int8)", "frac": tops / tensor_peak, "ms": t,
+                "peak_source": "148 SMs x 8192 int8 MAC/clk x SM clock (the tensor-pipe rate; ncu sm__pipe_tensor_cycles_active "
+                               "of the same kernel: profiles/r02/hamming_mma_*_metrics.txt); MEASURED_PEAKS bf16 "
+                               f"{peaks.get('bf16_tflops')} TFLOP/s burst for scale",
+                "descriptor_pairs": pairs, "matches_per_s": pairs / (t * 1e-3), "traffic": None,
+                "algorithmic_ops_per_pair": "288 int8 MACs (256 sign products + 32 bookkeeping columns)",
+                "tmem_read_tb_per_s": pairs * 4.0 / (t * 1e-3) / 1e12, "tmem_read_peak_tb_per_s": tmem_peak,
                 "popc_equivalent": {"achieved_tpopc": 8.0 * pairs / (t * 1e-3) / 1e12, "peak": popc_peak,
                                     "frac": 8.0 * pairs / (t * 1e-3) / 1e12 / popc_peak},
                 "expand_ms": k_ms(f"hamming_expand_kernel#{2 * idx}") + k_ms(f"hamming_expand_kernel#{2 * idx + 1}"),
-                "note": "one int32 accumulator (4 B) is read from tensor memory per descriptor pair; the MMA (288 int8 MACs per pair) "
-                        "runs below the tensor-core rate because tcgen05.ld bounds the epilogue; popc_equivalent = SURVEY 8d's "
-                        "8-POPC-per-pair count over the POPC-pipe peak, for comparison with the integer-pipe engine"}
+                "note": "achieved counts the MACs of the REAL descriptor pairs (padding of ragged tiles excluded); popc_equivalent = "
+                        "SURVEY 8d's 8-POPC-per-pair count over the POPC-pipe peak, for comparison with the integer-pipe engine"}
         else:
             t = k_ms(f"hamming_partial_kernel#{idx}")
             ops_t = 8.0 * pairs
@@ -434,10 +445,15 @@ def run_gpu(args, rank, local_rank, world):
                         "adders); algorithmic_frac counts SURVEY 8d's 8 POPC32 per pair and can exceed 1"}
     t = k_ms("score_kernel#0")
     fl = float(w.cfg.n_hyp) * float(n_corr.sum()) * flop_pair
-    roof["ransac_score"] = {"kernel": "score_kernel", "bound": "fp32-fma", "achieved": fl / (t * 1e-3) / 1e12, "peak": ffma_peak,
-                            "unit": "TFLOP/s", "frac": fl / (t * 1e-3) / 1e12 / ffma_peak, "ms": t,
-                            "peak_source": "scalar FFMA microbenchmark run in this process", "ffma2_peak_tflops": ffma2_peak,
-                            "flop_per_pair_model": flop_pair,
+    fl_exec = float(w.cfg.n_hyp) * float(n_corr.sum()) * flop_exec
+    roof["ransac_score"] = {"kernel": "score_kernel", "bound": "fp32-fma", "achieved": fl_exec / (t * 1e-3) / 1e12, "peak": ffma2_peak,
+                            "unit": "TFLOP/s", "frac": fl_exec / (t * 1e-3) / 1e12 / ffma2_peak, "ms": t,
+                            "peak_source": "packed fma.rn.f32x2 microbenchmark run in this process (the instruction the kernel issues); "
+                                           "scalar FFMA peak beside it", "ffma_scalar_peak_tflops": ffma_peak,
+                            "flop_per_pair_executed": flop_exec, "flop_per_pair_model": flop_pair,
+                            "model_frac": fl / (t * 1e-3) / 1e12 / ffma_peak,
+                            "note": "achieved = FLOPs the kernel executes (SASS count of the inner loop x pairs); ncu "
+                                    "sm__pipe_fma_cycles_active of the same kernel: profiles/r02/score_*_metrics.txt",
                             "hypothesis_point_pairs": float(w.cfg.n_hyp) * float(n_corr.sum()), "traffic": None}
     t = k_ms("stereo_geometry_kernel#0") + k_ms("stereo_compact_kernel#0")
     lt_bytes = 53.0 * float(buf["st_pair_count"].sum())
@@ -710,7 +726,7 @@ def run_c4(args, ctx, rank, world, steps=20, warm=3):
         verified = bool(int(fh[0]) == int(winner[0]) and int(fc[0]) == int(count[0]) and torch.equal(fm, mask)
                         and torch.equal(fp, pose))
         pairs = float(n) * H
-        ffma = ctx.peak_ffma()
+        ffma = ctx.peak_ffma2()
         tfl = pairs * 30 / (float(tt[0]) * 1e-3) / 1e12
         out = {
             "metric": "ransac_hypothesis_point_pairs_per_s", "value": pairs / (float(tt[0]) * 1e-3), "unit": "pairs/s",
@@ -723,7 +739,7 @@ def run_c4(args, ctx, rank, world, steps=20, warm=3):
             "winner": int(winner[0]), "inliers": int(count[0]), "matches_single_gpu_full_list": verified,
             "gpu_launches": int(ll[0]),
             "roofline": {"bound": "fp32-fma", "achieved": tfl, "peak": ffma * world, "unit": "TFLOP/s", "frac": tfl / (ffma * world),
-                         "note": "30 FLOP per (hypothesis, correspondence) (SURVEY 8d) over all ranks; peak = FFMA microbenchmark x ranks"},
+                         "note": "30 FLOP per (hypothesis, correspondence) executed (SASS count; equals SURVEY 8d's model) over all ranks; peak = packed-FMA microbenchmark x ranks"},
         }
     return out
 

@@ -22,7 +22,7 @@
 //   expand kernel : descriptors -> "tile-ready" int8 images in global memory, 128 rows x 288 bytes per tile, stored in the
 //                   canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices), so that a tile is ONE
 //                   contiguous 36 KB block
-//   warp 0        : cp.async.bulk (TMA engine, mbarrier complete_tx) of the two query tiles, then a 3-stage ring of
+//   warp 0        : cp.async.bulk (TMA engine, mbarrier complete_tx) of the two query tiles, then a 4-stage ring of
 //                   train tiles
 //   warp 1        : one lane issues 2 x 9 tcgen05.mma (M128 N128 K32) per train tile into a double-buffered TMEM
 //                   accumulator (2 buffers x 2 query tiles x 128 columns = all 512 columns); tcgen05.commit releases the
@@ -30,8 +30,6 @@
 //   warp 2        : tensor-memory allocation
 //   warps 4..11   : epilogue, one thread per (query tile, row)
 // The per-split partial keys use the POPC engine's format and are merged by the same hamming_merge_kernel.
-#include <stdlib.h>
-
 #include "sos_common.cuh"
 
 namespace sos_hamming_mma {
@@ -358,24 +356,17 @@ int sos_hamming_mma_launch(sos_ctx* ctx, const uint32_t* q, const uint32_t* t, c
   a.a_exp = a_exp; a.b_exp = b_exp; a.q_len = q_len; a.t_len = t_len;
   a.max_nq = max_nq; a.max_nt = max_nt; a.splits = splits; a.q_tiles_per_seg = qt; a.t_tiles_per_seg = tt;
   a.items = items; a.n_items = n_items; a.partial = partial;
-  // EXPERIMENT (round 2): depth of the train-tile ring (3 stages = 184 KB, 4 stages = 221 KB of shared memory)
-  const char* e = getenv("SOS_HAMMING_STAGES");
-  const int stages = (e && atoi(e) == 3) ? 3 : 4;
-  static bool attr_set[64][4] = {};     // per device: the opt-in to > 48 KB of dynamic shared memory
-  const int dev = ctx->device & 63, v = (top2 ? 1 : 0) + (stages == 4 ? 2 : 0);
-#define MMA_CASE(T2, ST)                                                                                               \
-  do {                                                                                                                 \
-    if (!attr_set[dev][v]) {                                                                                           \
-      SOS_CUDA(cudaFuncSetAttribute(mma_kernel<T2, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(ST))); \
-      attr_set[dev][v] = true;                                                                                         \
-    }                                                                                                                  \
-    mma_kernel<T2, ST><<<max_items, THREADS, smem_bytes(ST), ctx->stream>>>(a);                                         \
-  } while (0)
-  if (top2 && stages == 4) MMA_CASE(true, 4);
-  else if (top2) MMA_CASE(true, 3);
-  else if (stages == 4) MMA_CASE(false, 4);
-  else MMA_CASE(false, 3);
-#undef MMA_CASE
+  // ring depth 4 (221 KB of shared memory); 3 stages measured the same (profiles/r02/score_variants_and_ring_depth_ab.log)
+  constexpr int ST = 4;
+  static bool attr_set[64][2] = {};     // per device: the opt-in to > 48 KB of dynamic shared memory
+  const int dev = ctx->device & 63, v = top2 ? 1 : 0;
+  if (!attr_set[dev][v]) {
+    if (top2) SOS_CUDA(cudaFuncSetAttribute(mma_kernel<true, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(ST)));
+    else SOS_CUDA(cudaFuncSetAttribute(mma_kernel<false, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(ST)));
+    attr_set[dev][v] = true;
+  }
+  if (top2) mma_kernel<true, ST><<<max_items, THREADS, smem_bytes(ST), ctx->stream>>>(a);
+  else mma_kernel<false, ST><<<max_items, THREADS, smem_bytes(ST), ctx->stream>>>(a);
   SOS_LAUNCHED_AS(ctx, "hamming_mma_kernel");
   return SOS_OK;
 }

@@ -18,7 +18,6 @@
 //   mask         re-evaluates the winner with the very same float32 instruction sequence -> inlier mask.
 #include <math_constants.h>
 #include <stddef.h>
-#include <stdlib.h>
 
 #include "sos_common.cuh"
 
@@ -1045,19 +1044,11 @@ int ransac_scratch(sos_ctx* ctx, int n_problems, int n_hyp, RansacScratch& s) {
 template <int MODE>
 int launch_score(sos_ctx* ctx, const Rig& rig, dim3 grid, const float* p_ref, const float* q, const uint8_t* cam,
                  const int32_t* n, int cap, const HypRec* recs, int n_hyp, ScoreConst k, int32_t* counts) {
-  // EXPERIMENT (round 2): occupancy / ILP variants of the scoring kernel, selected per call
-  const char* e = getenv("SOS_SCORE_VARIANT");
-  const int v = e ? atoi(e) : 0;
-  const int n_problems = grid.z;
-#define SCORE_LAUNCH(HPT, CHUNK, MINB)                                                                                  \
-  score_kernel<MODE, HPT, CHUNK, MINB><<<dim3(sos_div_up(n_hyp, RS_THREADS * HPT), sos_div_up(cap, CHUNK), n_problems), \
-                                         RS_THREADS, 0, ctx->stream>>>(p_ref, q, cam, n, cap, recs, n_hyp, k, rig, counts)
-  if (v == 1) SCORE_LAUNCH(2, 256, 8);
-  else if (v == 2) SCORE_LAUNCH(2, 512, 6);
-  else if (v == 3) SCORE_LAUNCH(4, 256, 5);
-  else if (v == 4) SCORE_LAUNCH(2, 256, 6);
-  else SCORE_LAUNCH(4, 512, 4);
-#undef SCORE_LAUNCH
+  // 4 hypotheses per thread, 512 correspondences per block, 4 blocks per SM.  Measured against higher-occupancy shapes in
+  // round 2 (profiles/r02/score_variants_and_ring_depth_ab.log: 2 hypotheses per thread with 6-8 blocks per SM, 256-point
+  // chunks): all slower (0.74 - 0.81 ms against 0.72 ms) — fewer hypotheses per shared-memory read and more block prologues
+  // cost more than the extra warps hide.
+  score_kernel<MODE, RS_HPT, RS_CHUNK, 4><<<grid, RS_THREADS, 0, ctx->stream>>>(p_ref, q, cam, n, cap, recs, n_hyp, k, rig, counts);
   SOS_LAUNCHED_AS(ctx, "score_kernel");
   return SOS_OK;
 }
