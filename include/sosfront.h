@@ -356,7 +356,8 @@ int sos_corner_min_eigenval(sos_ctx* ctx, const uint8_t* gray, int n_images, int
  *   out_xy    float32 [n_images, n_masks, max_corners, 2] corner (x, y), strongest first
  *   out_count int32 [n_images, n_masks]
  *   eig_out   float32 [n_images, height, width] (nullable) receives the corner measure
- * At most 16384 local maxima above the quality threshold are considered per (image, mask). */
+ * More than 16384 local maxima above the quality threshold in one (image, mask) cannot be ranked reproducibly: with
+ * several masks the call fails with SOS_ERR_INVALID, with one mask out_count of that list is set to -(candidates). */
 int sos_gft_detect(sos_ctx* ctx, const uint8_t* gray, const uint8_t* masks, int n_images, int height, int width,
                    int n_masks, int max_corners, double quality_level, double min_distance, float* out_xy,
                    int32_t* out_count, float* eig_out);

@@ -4,7 +4,7 @@ import importlib
 import sys
 
 _MIRROR = "vo_single_camera_sos_b200.omnistereo"
-for _name in ("common_tools", "common_cv", "transformations", "panorama", "camera_models", "gum", "pose_est_tools"):
+for _name in ("common_tools", "common_cv", "common_plot", "transformations", "panorama", "camera_models", "gum", "pose_est_tools"):
     _mod = importlib.import_module(f"{_MIRROR}.{_name}")
     sys.modules[f"{__name__}.{_name}"] = _mod
     globals()[_name] = _mod

@@ -300,7 +300,13 @@ gft_select_kernel(const unsigned long long* __restrict__ keys_in, const int32_t*
   const int mk = mask_index >= 0 ? mask_index : blockIdx.x % n_masks;
   const int list = img * n_masks + mk;
   const int tag = mk << 16;
-  const int n = min(counts[list], cap);
+  if (counts[list] > cap) {
+    // more local maxima than the candidate buffer holds: the atomics that filled it kept a schedule-dependent subset, so
+    // refuse instead of returning a corner set that can change from run to run (out_count < 0 = -candidates)
+    if (threadIdx.x == 0) out_count[list] = -counts[list];
+    return;
+  }
+  const int n = counts[list];
   int np2 = 8;                                                // >= 8 keeps the byte / uint16 arrays behind the keys aligned
   while (np2 < n) np2 <<= 1;
   uint8_t* state = (uint8_t*)(skey + np2);                    // 0 undecided, 1 accepted, 2 rejected
@@ -581,7 +587,13 @@ extern "C" int sos_gft_detect(sos_ctx* ctx, const uint8_t* gray, const uint8_t* 
     SOS_CUDA(cudaMemcpyAsync(hc.data(), counts, sizeof(int32_t) * lists, cudaMemcpyDeviceToHost, ctx->stream));
     SOS_CUDA(cudaStreamSynchronize(ctx->stream));
     int mx = 1;
-    for (int v : hc) mx = std::max(mx, std::min(v, GFT_CAP));
+    for (int v : hc) {
+      if (v > GFT_CAP) {
+        sos_set_error("sos_gft_detect: %d corner candidates in one mask, the selection holds %d: raise quality_level", v, GFT_CAP);
+        return SOS_ERR_INVALID;
+      }
+      mx = std::max(mx, v);
+    }
     int np2 = 1024;
     while (np2 < mx) np2 <<= 1;
     sel_smem = gft_select_smem(np2);
