@@ -18,7 +18,8 @@
 //   * the epilogue thread that owns query row r (TMEM lane r) reads its 128 accumulators with tcgen05.ld and keeps the
 //     running maximum (3-input integer max: half an instruction per pair); top-2 costs 3 instructions per pair.
 //
-// Data flow per work item (256 query rows x a range of train tiles; one CTA per SM, warp-specialised):
+// Data flow per work item (256 query rows x a range of train tiles; ONE PERSISTENT CTA per SM walks the work list,
+// warp-specialised):
 //   expand kernel : descriptors -> "tile-ready" int8 images in global memory, 128 rows x 288 bytes per tile, stored in the
 //                   canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices), so that a tile is ONE
 //                   contiguous 36 KB block
@@ -195,95 +196,131 @@ struct Args {
   uint2* partial;
 };
 
+// Work item -> (segment, first query row, split, train tiles [tile_begin, tile_begin + n_iter))
+struct Item {
+  int seg, q_tile, split, nq, tile_begin, n_iter;
+};
+__device__ __forceinline__ Item decode_item(const Args& a, uint32_t item) {
+  Item it;
+  it.seg = (int)(item >> 16);
+  it.q_tile = (int)((item >> ITEM_SPLIT_BITS) & ((1u << ITEM_TILE_BITS) - 1u));   // 256 query rows
+  it.split = (int)(item & ((1u << ITEM_SPLIT_BITS) - 1u));
+  it.nq = min(a.q_len[it.seg], a.max_nq);
+  const int nt = min(a.t_len[it.seg], a.max_nt);
+  const int t_tiles = (nt + TILE - 1) / TILE;
+  const int chunk_tiles = (t_tiles + a.splits - 1) / a.splits;
+  it.tile_begin = min(t_tiles, it.split * chunk_tiles);
+  it.n_iter = min(t_tiles, it.tile_begin + chunk_tiles) - it.tile_begin;
+  return it;
+}
+
+// PERSISTENT: one CTA per SM walks the work list with stride gridDim.x; barriers, the tensor-memory allocation and the three
+// pipelines (train-tile ring, accumulator double buffer, query tiles) live across items, so the tensor pipe only idles while
+// the next item's query tiles land (the train tiles of the next item are already streaming into the ring by then).  The
+// roles agree on every counter because they walk the same items in the same order:
+//   t  = train tiles consumed so far by this CTA -> ring stage t % STAGES, accumulator buffer t & 1
+//   ic = items with work so far                  -> phase of the query-tile barriers
 template <bool TOP2, int STAGES>
 __global__ void __launch_bounds__(THREADS, 1) mma_kernel(Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  if ((int)blockIdx.x >= *a.n_items) return;
-  const uint32_t item = a.items[blockIdx.x];
-  const int seg = (int)(item >> 16);
-  const int q_tile = (int)((item >> ITEM_SPLIT_BITS) & ((1u << ITEM_TILE_BITS) - 1u));   // 256 query rows
-  const int split = (int)(item & ((1u << ITEM_SPLIT_BITS) - 1u));
-  const int nq = min(a.q_len[seg], a.max_nq), nt = min(a.t_len[seg], a.max_nt);
-  const int t_tiles = (nt + TILE - 1) / TILE;
-  const int chunk_tiles = (t_tiles + a.splits - 1) / a.splits;
-  const int tile_begin = min(t_tiles, split * chunk_tiles);
-  const int n_iter = min(t_tiles, tile_begin + chunk_tiles) - tile_begin;
-
+  const int n_items = *a.n_items;
+  if ((int)blockIdx.x >= n_items) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* sA = smem;
   uint8_t* sB = smem + 2 * TILE_BYTES;
   uint64_t* bars = (uint64_t*)(smem + (2 + STAGES) * TILE_BYTES);
   // bars: FULL + s (train stage landed), EMPTY + s (stage consumed), TFULL + b (accumulator complete), TEMPTY + b
-  // (accumulator drained), AFULL (query tiles landed)
-  constexpr int FULL = 0, EMPTY = STAGES, TFULL = 2 * STAGES, TEMPTY = 2 * STAGES + 2, AFULL = 2 * STAGES + 4;
-  uint32_t* tmem_slot = (uint32_t*)(bars + AFULL + 1);
+  // (accumulator drained), AFULL (query tiles landed), AEMPTY (query tiles no longer read by the tensor core)
+  constexpr int FULL = 0, EMPTY = STAGES, TFULL = 2 * STAGES, TEMPTY = 2 * STAGES + 2, AFULL = 2 * STAGES + 4, AEMPTY = 2 * STAGES + 5;
+  uint32_t* tmem_slot = (uint32_t*)(bars + AEMPTY + 1);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
-  if (n_iter > 0) {   // block-uniform
-    if (tid == 0) {
-      for (int i = 0; i < STAGES; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1); }
-      mbar_init(BAR(TFULL), 1); mbar_init(BAR(TFULL + 1), 1);
-      mbar_init(BAR(TEMPTY), 8); mbar_init(BAR(TEMPTY + 1), 8);
-      mbar_init(BAR(AFULL), 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 2) {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1); }
+    mbar_init(BAR(TFULL), 1); mbar_init(BAR(TFULL + 1), 1);
+    mbar_init(BAR(TEMPTY), 8); mbar_init(BAR(TEMPTY + 1), 8);
+    mbar_init(BAR(AFULL), 1); mbar_init(BAR(AEMPTY), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
 
-    if (warp == 0) {
-      if (lane == 0) {
-        // the item's two query tiles, then the ring of train tiles
-        const uint8_t* ga = a.a_exp + ((size_t)seg * a.q_tiles_per_seg + (size_t)q_tile * 2) * TILE_BYTES;
-        mbar_expect_tx(BAR(AFULL), 2u * TILE_BYTES);
-#pragma unroll
-        for (int p = 0; p < 8; ++p) bulk_g2s(smem_u32(sA) + p * (TILE_BYTES / 4), ga + (size_t)p * (TILE_BYTES / 4), TILE_BYTES / 4, BAR(AFULL));
-        const uint8_t* gb = a.b_exp + ((size_t)seg * a.t_tiles_per_seg + tile_begin) * TILE_BYTES;
-        for (int it = 0; it < n_iter; ++it) {
-          const int s = it % STAGES;
-          mbar_wait(BAR(EMPTY + s), ((it / STAGES) & 1) ^ 1);
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t t = 0, ic = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const Item it = decode_item(a, a.items[w]);
+        if (it.n_iter <= 0) continue;
+        const uint8_t* gb = a.b_exp + ((size_t)it.seg * a.t_tiles_per_seg + it.tile_begin) * TILE_BYTES;
+        auto load_b = [&](int k) {
+          const uint32_t s = t % STAGES;
+          mbar_wait(BAR(EMPTY + s), ((t / STAGES) & 1) ^ 1);
           mbar_expect_tx(BAR(FULL + s), TILE_BYTES);
           const uint32_t dst = smem_u32(sB) + s * TILE_BYTES;
 #pragma unroll
           for (int p = 0; p < 4; ++p)
-            bulk_g2s(dst + p * (TILE_BYTES / 4), gb + (size_t)it * TILE_BYTES + (size_t)p * (TILE_BYTES / 4), TILE_BYTES / 4, BAR(FULL + s));
-        }
+            bulk_g2s(dst + p * (TILE_BYTES / 4), gb + (size_t)k * TILE_BYTES + (size_t)p * (TILE_BYTES / 4), TILE_BYTES / 4, BAR(FULL + s));
+          ++t;
+        };
+        // the first train tiles of this item go into the ring as soon as stages free up, i.e. while the previous item is still
+        // being multiplied; only then wait for the tensor core to be done with the previous item's query tiles and fetch ours
+        const int pre = min(it.n_iter, STAGES);
+        for (int k = 0; k < pre; ++k) load_b(k);
+        mbar_wait(BAR(AEMPTY), (ic & 1) ^ 1);
+        const uint8_t* ga = a.a_exp + ((size_t)it.seg * a.q_tiles_per_seg + (size_t)it.q_tile * 2) * TILE_BYTES;
+        mbar_expect_tx(BAR(AFULL), 2u * TILE_BYTES);
+#pragma unroll
+        for (int p = 0; p < 8; ++p) bulk_g2s(smem_u32(sA) + p * (TILE_BYTES / 4), ga + (size_t)p * (TILE_BYTES / 4), TILE_BYTES / 4, BAR(AFULL));
+        ++ic;
+        for (int k = pre; k < it.n_iter; ++k) load_b(k);
       }
-      __syncwarp();
-    } else if (warp == 1) {
-      if (lane == 0) {
-        mbar_wait(BAR(AFULL), 0);
-        const uint64_t da0 = smem_desc(smem_u32(sA)), da1 = smem_desc(smem_u32(sA) + TILE_BYTES);
-        for (int it = 0; it < n_iter; ++it) {
-          const int s = it % STAGES, b = it & 1;
-          mbar_wait(BAR(TEMPTY + b), ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator buffer
-          mbar_wait(BAR(FULL + s), (it / STAGES) & 1);       // the train tile has landed
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint64_t da0 = smem_desc(smem_u32(sA)), da1 = smem_desc(smem_u32(sA) + TILE_BYTES);
+      uint32_t t = 0, ic = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const Item it = decode_item(a, a.items[w]);
+        if (it.n_iter <= 0) continue;
+        mbar_wait(BAR(AFULL), ic & 1);
+        ++ic;
+        for (int k = 0; k < it.n_iter; ++k, ++t) {
+          const uint32_t s = t % STAGES, b = t & 1;
+          mbar_wait(BAR(TEMPTY + b), ((t >> 1) & 1) ^ 1);    // the epilogue has drained this accumulator buffer
+          mbar_wait(BAR(FULL + s), (t / STAGES) & 1);        // the train tile has landed
           tc_fence_after();
           const uint64_t db = smem_desc(smem_u32(sB) + s * TILE_BYTES);
 #pragma unroll
-          for (int k = 0; k < KB / 32; ++k) tc_mma_i8(tmem + (uint32_t)(b * 2) * TILE, da0 + (uint64_t)(16 * k), db + (uint64_t)(16 * k), IDESC, k > 0);
+          for (int kk = 0; kk < KB / 32; ++kk) tc_mma_i8(tmem + (b * 2) * TILE, da0 + (uint64_t)(16 * kk), db + (uint64_t)(16 * kk), IDESC, kk > 0);
 #pragma unroll
-          for (int k = 0; k < KB / 32; ++k) tc_mma_i8(tmem + (uint32_t)(b * 2 + 1) * TILE, da1 + (uint64_t)(16 * k), db + (uint64_t)(16 * k), IDESC, k > 0);
-          tc_commit(BAR(EMPTY + s));   // shared-memory stage free once these MMAs have read it
-          tc_commit(BAR(TFULL + b));   // accumulators complete
+          for (int kk = 0; kk < KB / 32; ++kk) tc_mma_i8(tmem + (b * 2 + 1) * TILE, da1 + (uint64_t)(16 * kk), db + (uint64_t)(16 * kk), IDESC, kk > 0);
+          tc_commit(BAR(EMPTY + s));    // shared-memory stage free once these MMAs have read it
+          tc_commit(BAR(TFULL + b));    // accumulators complete
         }
+        tc_commit(BAR(AEMPTY));         // every MMA of this item has read the query tiles
       }
-      __syncwarp();
-    } else if (warp >= 4) {
-      const int g = (warp - 4) >> 2, quarter = warp & 3;   // a warp may only touch the TMEM lanes of its quarter
-      const int row = q_tile * 256 + g * TILE + quarter * 32 + lane;
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int g = (warp - 4) >> 2, quarter = warp & 3;   // a warp may only touch the TMEM lanes of its quarter
+    uint32_t t = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const Item it = decode_item(a, a.items[w]);
+      const int row = it.q_tile * 256 + g * TILE + quarter * 32 + lane;
       uint32_t k0 = KEY_NONE, k1 = KEY_NONE;
-      for (int it = 0; it < n_iter; ++it) {
-        const int b = it & 1;
-        mbar_wait(BAR(TFULL + b), (it >> 1) & 1);
+      for (int k = 0; k < it.n_iter; ++k, ++t) {
+        const uint32_t b = t & 1;
+        mbar_wait(BAR(TFULL + b), (t >> 1) & 1);
         tc_fence_after();
-        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 2 + g) * TILE;
+        const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (b * 2 + g) * TILE;
         int m0 = INT_MIN, m1 = INT_MIN;
         int va[32], vb[32];
         tmem_ld32(taddr, va);
@@ -301,7 +338,7 @@ __global__ void __launch_bounds__(THREADS, 1) mma_kernel(Args a) {
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(TEMPTY + b));     // buffer b may be overwritten
         reduce32<TOP2>(vb, m0, m1);
-        const int tile = tile_begin + it;
+        const int tile = it.tile_begin + k;
         const uint32_t key0 = acc_to_key(m0, tile);
         if (TOP2) {
           const uint32_t key1 = acc_to_key(m1, tile);
@@ -312,18 +349,13 @@ __global__ void __launch_bounds__(THREADS, 1) mma_kernel(Args a) {
           k0 = min(k0, key0);
         }
       }
-      if (row < nq) a.partial[((size_t)seg * a.max_nq + row) * a.splits + split] = make_uint2(k0, k1);
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
-  } else {
-    // no train rows in this split
-    for (int r = tid; r < 256; r += THREADS) {
-      const int row = q_tile * 256 + r;
-      if (row < nq) a.partial[((size_t)seg * a.max_nq + row) * a.splits + split] = make_uint2(KEY_NONE, KEY_NONE);
+      // (no train rows in this split: both keys stay KEY_NONE)
+      if (row < it.nq) a.partial[((size_t)it.seg * a.max_nq + row) * a.splits + it.split] = make_uint2(k0, k1);
     }
   }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
 }  // namespace sos_hamming_mma
@@ -365,8 +397,9 @@ int sos_hamming_mma_launch(sos_ctx* ctx, const uint32_t* q, const uint32_t* t, c
     else SOS_CUDA(cudaFuncSetAttribute(mma_kernel<false, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(ST)));
     attr_set[dev][v] = true;
   }
-  if (top2) mma_kernel<true, ST><<<max_items, THREADS, smem_bytes(ST), ctx->stream>>>(a);
-  else mma_kernel<false, ST><<<max_items, THREADS, smem_bytes(ST), ctx->stream>>>(a);
+  const unsigned grid = max_items < (unsigned)ctx->sm_count ? max_items : (unsigned)ctx->sm_count;   // one CTA per SM
+  if (top2) mma_kernel<true, ST><<<grid, THREADS, smem_bytes(ST), ctx->stream>>>(a);
+  else mma_kernel<false, ST><<<grid, THREADS, smem_bytes(ST), ctx->stream>>>(a);
   SOS_LAUNCHED_AS(ctx, "hamming_mma_kernel");
   return SOS_OK;
 }
