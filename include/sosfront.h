@@ -148,6 +148,14 @@ int sos_hamming_top2(sos_ctx* ctx, const uint32_t* q, const uint32_t* t, const i
                      const int32_t* q_len, const int32_t* t_start, const int32_t* t_len, int n_seg, int max_nq,
                      int max_nt, int32_t* idx0, int32_t* d0, int32_t* idx1, int32_t* d1);
 
+/* replaces: cv2.BFMatcher(NORM_HAMMING).radiusMatch(queryDescriptors, trainDescriptors, maxDistance), the
+ * use_radius_match branch of FeatureMatcher.match (camera_models.py:409-412): every train row t with
+ * hamming(q, t) <= max_distance, per query in train-index order.  Two passes over the same arguments:
+ *   pass 1: count int32 [nq] receives the number of rows per query (offset, out_t, out_d NULL);
+ *   pass 2: offset int64 [nq] (exclusive prefix sum of count) says where query r writes its out_t / out_d entries. */
+int sos_hamming_radius(sos_ctx* ctx, const uint32_t* q, int nq, const uint32_t* t, int nt, int max_distance,
+                       int32_t* count, const int64_t* offset, int32_t* out_t, int32_t* out_d);
+
 #define SOS_MATCH_NN 0    /* 1-NN, the reference default (k_best = 1, pose_est_tools.py:686) */
 #define SOS_MATCH_RATIO 1 /* keep m0 iff d0 < ratio * d1 (camera_models.py:421-436) */
 #define SOS_MATCH_CROSS 2 /* mutual nearest neighbours (BFMatcher crossCheck, camera_models.py:401) */

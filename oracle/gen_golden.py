@@ -142,6 +142,15 @@ def gen_hamming():
     out["k2_q"] = np.array([x.queryIdx for x in m2], np.int32)
     out["k2_t"] = np.array([x.trainIdx for x in m2], np.int32)
     out["k2_d"] = np.array([x.distance for x in m2], np.float64)
+    # use_radius_match branch (camera_models.py:409-412): radiusMatch at a descriptor distance, flattened, sorted
+    fmr = FeatureMatcher("ORB", "BF", 1, use_radius_match=True)
+    for radius in (40, 70.5):
+        mr = fmr.match(query_descriptors=q, train_descriptors=t, max_descriptor_distance_radius=radius)
+        tag = f"r{int(radius)}"
+        out[f"{tag}_radius"] = np.float64(radius)
+        out[f"{tag}_q"] = np.array([x.queryIdx for x in mr], np.int32)
+        out[f"{tag}_t"] = np.array([x.trainIdx for x in mr], np.int32)
+        out[f"{tag}_d"] = np.array([x.distance for x in mr], np.float64)
     np.savez_compressed(os.path.join(OUT, "hamming.npz"), **out)
 
 

@@ -74,6 +74,19 @@ def knn2_flat_sorted(q, t):
     return qi[order], ti[order], dd[order]
 
 
+def radius_match_flat_sorted(q, t, max_distance):
+    """FeatureMatcher.match with use_radius_match (camera_models.py:409-412): BFMatcher.radiusMatch keeps every train row with
+    distance <= maxDistance per query, each query's list sorted by distance (ties in train-index order); the lists are
+    flattened query by query and sorted(key=distance) — stable.  Returns (query_idx, train_idx, distance)."""
+    d = hamming_matrix(q, t).astype(np.int32)
+    qi, ti = np.nonzero(d <= max_distance)
+    dd = d[qi, ti]
+    within = np.lexsort((ti, dd, qi))
+    qi, ti, dd = qi[within], ti[within], dd[within]
+    order = np.argsort(dd, kind="stable")
+    return qi[order].astype(np.int32), ti[order].astype(np.int32), dd[order]
+
+
 def match_select(q, t, mode="nn", ratio=0.75, px_q=None, px_t=None, max_du=-1.0, min_dv=-1.0):
     """FeatureMatcher.match (camera_models.py:404-446) + the gate its callers apply (camera_models.py:3086,
     pose_est_tools.py:245-247), for one (query, train) segment.

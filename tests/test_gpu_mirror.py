@@ -116,6 +116,26 @@ def test_feature_matcher_k_best_2_on_binary_descriptors(ctx):
     assert np.array_equal(qi, oq) and np.array_equal(ti, ot) and np.array_equal(dd, od)
 
 
+def test_feature_matcher_radius_match(ctx):
+    """use_radius_match=True (camera_models.py:409-412): goldens from the reference's own class at an integer and a fractional
+    descriptor radius, plus a dense case against the oracle (many rows per query, ties within a query)."""
+    from omnistereo.camera_models import FeatureMatcher
+    from oracle import hamming
+    g = load_golden("hamming.npz")
+    fm = FeatureMatcher("ORB", "BF", 1, use_radius_match=True)
+    for tag in ("r40", "r70"):
+        m = fm.match(query_descriptors=g["q"], train_descriptors=g["t"], max_descriptor_distance_radius=float(g[f"{tag}_radius"]))
+        assert [x.queryIdx for x in m] == g[f"{tag}_q"].tolist() and [x.trainIdx for x in m] == g[f"{tag}_t"].tolist()
+        assert [x.distance for x in m] == g[f"{tag}_d"].tolist()
+    rng = np.random.default_rng(4)
+    q = rng.integers(0, 256, (333, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (517, 32), dtype=np.uint8)
+    qi, ti, dd = fm.match_arrays(q, t, max_descriptor_distance_radius=118)
+    oq, ot, od = hamming.radius_match_flat_sorted(q, t, 118)
+    assert len(oq) > 5000 and np.array_equal(qi, oq) and np.array_equal(ti, ot) and np.array_equal(dd, od)
+    assert fm.match(q, t, max_descriptor_distance_radius=20) == []
+
+
 def test_stereo_and_temporal_matching(gums):
     from omnistereo import pose_est_tools
     from omnistereo.camera_models import FeatureMatcher

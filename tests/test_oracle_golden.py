@@ -71,6 +71,11 @@ def test_hamming_oracle_matches_bfmatcher():
     kq, kt, kd = hamming.knn2_flat_sorted(q, t)
     assert len(kq) == 2 * len(q)
     assert np.array_equal(kq, g["k2_q"]) and np.array_equal(kt, g["k2_t"]) and np.array_equal(kd, g["k2_d"].astype(np.int32))
+    # use_radius_match: radiusMatch flattened and sorted (camera_models.py:409-412), integer and fractional radius
+    for tag in ("r40", "r70"):
+        rq_, rt_, rd_ = hamming.radius_match_flat_sorted(q, t, float(g[f"{tag}_radius"]))
+        assert len(rq_) > 50
+        assert np.array_equal(rq_, g[f"{tag}_q"]) and np.array_equal(rt_, g[f"{tag}_t"]) and np.array_equal(rd_, g[f"{tag}_d"].astype(np.int32))
     # and against live OpenCV
     rq, rt, rd = hamming.bf_match_reference(q, t)
     assert np.array_equal(i0, rt) and np.array_equal(d0, rd.astype(np.int32))

@@ -384,6 +384,61 @@ extern "C" int sos_hamming_top2(sos_ctx* ctx, const uint32_t* q, const uint32_t*
   return SOS_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// radiusMatch: every train row within a descriptor distance of a query row.  One thread per query walks the train rows in
+// index order (shared-memory tiles as above); pass 1 counts, pass 2 fills at the caller's offsets.  A non-default branch
+// of FeatureMatcher.match (use_radius_match, camera_models.py:409-412): correctness first, no work splitting.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+hamming_radius_kernel(const uint4* __restrict__ q, int nq, const uint4* __restrict__ t, int nt, int max_dist,
+                      int32_t* __restrict__ count, const int64_t* __restrict__ offset, int32_t* __restrict__ out_t,
+                      int32_t* __restrict__ out_d) {
+  __shared__ uint4 tile[HB_TILE_T * 2];
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = row < nq;
+  uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
+  if (live) { qa = __ldg(q + (size_t)row * 2); qb = __ldg(q + (size_t)row * 2 + 1); }
+  int n = 0;
+  int64_t base = FILL && live ? offset[row] : 0;
+  for (int tb = 0; tb < nt; tb += HB_TILE_T) {
+    const int n_tile = min(HB_TILE_T, nt - tb);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_tile * 2; i += blockDim.x) tile[i] = __ldg(t + (size_t)tb * 2 + i);
+    __syncthreads();
+    if (!live) continue;
+    for (int j = 0; j < n_tile; ++j) {
+      const uint4 ta = tile[j * 2], tbv = tile[j * 2 + 1];
+      const int d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
+                    __popc(qb.x ^ tbv.x) + __popc(qb.y ^ tbv.y) + __popc(qb.z ^ tbv.z) + __popc(qb.w ^ tbv.w);
+      if (d <= max_dist) {
+        if (FILL) { out_t[base + n] = tb + j; out_d[base + n] = d; }
+        ++n;
+      }
+    }
+  }
+  if (!FILL && live) count[row] = n;
+}
+}  // namespace
+
+extern "C" int sos_hamming_radius(sos_ctx* ctx, const uint32_t* q, int nq, const uint32_t* t, int nt, int max_distance,
+                                  int32_t* count, const int64_t* offset, int32_t* out_t, int32_t* out_d) {
+  SOS_CHECK_ARG(ctx, "ctx is NULL");
+  SOS_CHECK_ARG(nq >= 0 && nt >= 0, "negative size");
+  if (nq == 0) return SOS_OK;
+  SOS_CHECK_ARG(q && (t || nt == 0), "NULL array");
+  SOS_CHECK_ARG(((uintptr_t)q & 15) == 0 && ((uintptr_t)t & 15) == 0, "descriptor arrays must be 16-byte aligned");
+  SOS_CHECK_ARG((count != nullptr) != (offset != nullptr), "pass either count (pass 1) or offset + out_t + out_d (pass 2)");
+  SOS_CHECK_ARG(count || (out_t && out_d), "pass 2 needs out_t and out_d");
+  SOS_CUDA(cudaSetDevice(ctx->device));
+  const int grid = sos_div_up(nq, 128);
+  if (count) hamming_radius_kernel<false><<<grid, 128, 0, ctx->stream>>>((const uint4*)q, nq, (const uint4*)t, nt, max_distance, count, nullptr, nullptr, nullptr);
+  else hamming_radius_kernel<true><<<grid, 128, 0, ctx->stream>>>((const uint4*)q, nq, (const uint4*)t, nt, max_distance, nullptr, offset, out_t, out_d);
+  SOS_LAUNCHED_AS(ctx, "hamming_radius_kernel");
+  return SOS_OK;
+}
+
 extern "C" int sos_match_select(sos_ctx* ctx, int mode, double ratio, const int32_t* idx0, const int32_t* d0,
                                 const int32_t* d1, const int32_t* rev_idx0, const int32_t* q_start,
                                 const int32_t* q_len, const int32_t* t_start, int n_seg, const float* px_q,

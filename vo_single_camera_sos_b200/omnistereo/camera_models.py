@@ -47,13 +47,26 @@ class FeatureMatcher(object):
         t = np.ascontiguousarray(train_descriptors, np.uint8)
         if q.ndim != 2 or t.ndim != 2 or q.shape[1] != 32 or t.shape[1] != 32:
             raise ValueError("descriptors must be N x 32 uint8 (256-bit)")
-        if self.use_radius_match:
-            raise NotImplementedError("radiusMatch is not used by the SOS / RGB-D trackers (use_radius_match=False)")
         nq, nt = len(q), len(t)
         empty = np.zeros(0, np.int32)
         if nq == 0 or nt == 0:
             return empty, empty, empty
         ctx = device_context()
+        if self.use_radius_match:
+            # camera_models.py:409-412: radiusMatch (every train row within the descriptor distance), flattened query by
+            # query, then sorted(key=distance) — stable.  cv2 compares float distances: d <= maxDistance.
+            qi, ti, dd = ctx.hamming_radius(to_device(q), to_device(t), int(np.floor(max_descriptor_distance_radius)))
+            qi, ti, dd = qi.cpu().numpy().astype(np.int32), ti.cpu().numpy(), dd.cpu().numpy()
+            within = np.lexsort((ti, dd, qi))            # per query by (distance, train index): cv2 sorts each query's list
+            qi, ti, dd = qi[within], ti[within], dd[within]
+            order = np.argsort(dd, kind="stable")
+            qi, ti, dd = qi[order], ti[order], dd[order]
+            if px_query is not None and px_train is not None:
+                from .common_cv import filter_pixel_correspondences
+                ok = filter_pixel_correspondences(np.asarray(px_train)[ti], np.asarray(px_query)[qi],
+                                                  min_rectified_disparity, max_horizontal_diff)
+                qi, ti, dd = qi[ok], ti[ok], dd[ok]
+            return qi, ti, dd
         dev = ctx.device
         i32 = lambda v: torch.tensor([v], dtype=torch.int32, device=dev)
         zero, nq_d, nt_d = i32(0), i32(nq), i32(nt)

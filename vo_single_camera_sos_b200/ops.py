@@ -179,6 +179,25 @@ class Context:
                                         d1.data_ptr() if d1 is not None else None))
         return idx0, d0, idx1, d1
 
+    def hamming_radius(self, q: torch.Tensor, t: torch.Tensor, max_distance: int):
+        """Every (query, train, distance) with distance <= max_distance, query-major, train index ascending within a query
+        (cv2.BFMatcher.radiusMatch).  -> (query int64 [M], train int32 [M], distance int32 [M]) device tensors."""
+        self._sync_stream()
+        nq, nt = q.shape[0], t.shape[0]
+        qp, tp = self._desc(q, "q"), self._desc(t, "t")
+        count = torch.zeros((nq,), dtype=torch.int32, device=self.device)
+        check(self.lib.sos_hamming_radius(self._h, qp, nq, tp, nt, int(max_distance), count.data_ptr(), None, None, None))
+        incl = torch.cumsum(count.to(torch.int64), 0)
+        offset = (incl - count).contiguous()
+        m = int(incl[-1]) if nq else 0
+        out_t = torch.empty((max(m, 1),), dtype=torch.int32, device=self.device)
+        out_d = torch.empty((max(m, 1),), dtype=torch.int32, device=self.device)
+        if m:
+            check(self.lib.sos_hamming_radius(self._h, qp, nq, tp, nt, int(max_distance), None, offset.data_ptr(),
+                                              out_t.data_ptr(), out_d.data_ptr()))
+        qi = torch.repeat_interleave(torch.arange(nq, device=self.device), count.to(torch.int64))
+        return qi, out_t[:m], out_d[:m]
+
     def _desc(self, d: torch.Tensor, what: str):
         if d.dtype == torch.uint8:
             if d.dim() != 2 or d.shape[1] != 32:
