@@ -156,6 +156,20 @@ int sos_hamming_top2(sos_ctx* ctx, const uint32_t* q, const uint32_t* t, const i
 int sos_hamming_radius(sos_ctx* ctx, const uint32_t* q, int nq, const uint32_t* t, int nt, int max_distance,
                        int32_t* count, const int64_t* offset, int32_t* out_t, int32_t* out_d);
 
+/* replaces: cv2.BFMatcher() (NORM_L2) .match / .knnMatch(k = 2) on float descriptors — the SIFT / SURF branch of
+ * FeatureMatcher (camera_models.py:397-399, 417-442).  The optional float-descriptor variant of the matcher, a real GEMM:
+ * |q - t|^2 = |q|^2 + |t|^2 - 2 <q, t> on the tensor cores (tcgen05.mma kind::f16, bfloat16 operands, float32
+ * accumulators in tensor memory).  EXACT for descriptors whose values are integers in [0, 255] — what cv2's SIFT
+ * returns — because those are exact in bfloat16 and every partial sum stays below 2^24: distances equal cv2's
+ * sqrt(float32 sum of squared differences) bit for bit, ties go to the lowest train row.  Other values are refused:
+ * not_integer_flag[0] (DEVICE int32) is set non-zero and the outputs are meaningless.
+ *   q, t [*, dim] float32 rows, dim <= 128; segments as in sos_hamming_top2
+ *   idx0, idx1 int32 (train row relative to t_start[s], -1: none); d0, d1 float32 L2 distances (-1: none);
+ *   idx1 / d1 may be NULL. */
+int sos_l2_top2(sos_ctx* ctx, const float* q, const float* t, int dim, const int32_t* q_start, const int32_t* q_len,
+                const int32_t* t_start, const int32_t* t_len, int n_seg, int max_nq, int max_nt, int32_t* idx0,
+                float* d0, int32_t* idx1, float* d1, int32_t* not_integer_flag);
+
 #define SOS_MATCH_NN 0    /* 1-NN, the reference default (k_best = 1, pose_est_tools.py:686) */
 #define SOS_MATCH_RATIO 1 /* keep m0 iff d0 < ratio * d1 (camera_models.py:421-436) */
 #define SOS_MATCH_CROSS 2 /* mutual nearest neighbours (BFMatcher crossCheck, camera_models.py:401) */

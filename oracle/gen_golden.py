@@ -154,6 +154,46 @@ def gen_hamming():
     np.savez_compressed(os.path.join(OUT, "hamming.npz"), **out)
 
 
+def make_sift_like(rng, n_land, n_q, n_t, dim=128, n_ties=6):
+    """Integer-valued float32 descriptors with SIFT's look: sparse-ish gradient histograms in [0, 255] (cv2's SIFT scales
+    the unit vector by 512, clips at 255 and rounds), each view a noisy copy of a landmark subset, plus unrelated rows and
+    exact duplicates (ties)."""
+    land = np.clip(rng.gamma(0.7, 28.0, (n_land, dim)), 0, 255).round()
+
+    def view(n):
+        ids = rng.permutation(n_land)[:n]
+        d = np.clip(land[ids] + rng.normal(0, 6.0, (n, dim)).round(), 0, 255)
+        return d.astype(np.float32)
+
+    q, t = view(n_q), view(n_t)
+    q[: n_q // 4] = np.clip(rng.gamma(0.7, 28.0, (n_q // 4, dim)), 0, 255).round()
+    for _ in range(n_ties):
+        a, b = rng.integers(0, n_t, 2)
+        t[b] = t[a]
+    return q, t
+
+
+def gen_l2():
+    """The SIFT branch of FeatureMatcher (camera_models.py:397-399, 417-442): cv2.BFMatcher() = NORM_L2."""
+    from omnistereo.camera_models import FeatureMatcher
+    rng = np.random.default_rng(12)
+    out = {}
+    q, t = make_sift_like(rng, 500, 380, 450)
+    out["q"], out["t"] = q, t
+    for name, method, k in (("sift1", "SIFT", 1), ("sift2", "SIFT", 2), ("surf2", "SURF", 2)):
+        m = FeatureMatcher(method, "BF", k).match(query_descriptors=q, train_descriptors=t)
+        out[f"{name}_q"] = np.array([x.queryIdx for x in m], np.int32)
+        out[f"{name}_t"] = np.array([x.trainIdx for x in m], np.int32)
+        out[f"{name}_d"] = np.array([x.distance for x in m], np.float32)
+    q64, t64 = make_sift_like(rng, 300, 200, 190, dim=64)
+    out["q64"], out["t64"] = q64, t64
+    m = FeatureMatcher("SURF", "BF", 1).match(query_descriptors=q64, train_descriptors=t64)
+    out["surf1_64_q"] = np.array([x.queryIdx for x in m], np.int32)
+    out["surf1_64_t"] = np.array([x.trainIdx for x in m], np.int32)
+    out["surf1_64_d"] = np.array([x.distance for x in m], np.float32)
+    np.savez_compressed(os.path.join(OUT, "l2.npz"), **out)
+
+
 def gen_matching_frames():
     """match_features_panoramic_top_bottom (camera_models.py:3027-3101) and match_features_frame_to_frame
     (pose_est_tools.py:211-269) on synthetic bucketed keypoints."""
@@ -413,6 +453,7 @@ def main():
     with contextlib.redirect_stdout(buf):  # the reference prints progress
         gen_remap()
         gen_hamming()
+        gen_l2()
         gen_matching_frames()
         gen_lifting()
         gen_rgbd()

@@ -113,3 +113,45 @@ def match_select(q, t, mode="nn", ratio=0.75, px_q=None, px_t=None, max_du=-1.0,
         ok = filter_pixel_correspondences(px_t[ti], px_q[qi], min_dv, max_du)
         qi, ti, dd = qi[ok], ti[ok], dd[ok]
     return qi, ti, dd
+
+
+# ---- float descriptors, L2 norm (the SIFT / SURF branch of FeatureMatcher, camera_models.py:397-399, 417-442) -----------
+def l2_matrix_sq(q: np.ndarray, t: np.ndarray) -> np.ndarray:
+    """Squared L2 distances of integer-valued float descriptors as exact int64 (cv2 sums the squared float32 differences;
+    for integer values in [0, 255] and <= 128 dimensions that sum is an exact integer below 2^24)."""
+    qi, ti = np.asarray(q, np.float64).astype(np.int64), np.asarray(t, np.float64).astype(np.int64)
+    return (qi * qi).sum(1)[:, None] + (ti * ti).sum(1)[None, :] - 2 * (qi @ ti.T)
+
+
+def l2_knn2(q: np.ndarray, t: np.ndarray):
+    """Two nearest train rows per query by (distance, train index); distances float32 = sqrt(float32(sum)) like cv2."""
+    nq, nt = len(q), len(t)
+    idx = np.full((nq, 2), -1, np.int32)
+    dist = np.full((nq, 2), -1.0, np.float32)
+    if nq == 0 or nt == 0:
+        return idx[:, 0], dist[:, 0], idx[:, 1], dist[:, 1]
+    d2 = l2_matrix_sq(q, t)
+    key = d2 * (1 << 22) + np.arange(nt, dtype=np.int64)[None, :]
+    k = min(2, nt)
+    part = np.sort(key, axis=1)[:, :k]
+    idx[:, :k] = part & ((1 << 22) - 1)
+    dist[:, :k] = np.sqrt((part >> 22).astype(np.float32))
+    return idx[:, 0], dist[:, 0], idx[:, 1], dist[:, 1]
+
+
+def l2_match(q, t, method="SIFT", k_best=1):
+    """FeatureMatcher(method, "BF", k_best).match for float descriptors -> (query_idx, train_idx, distance float32)."""
+    i0, d0, i1, d1 = l2_knn2(q, t)
+    qi = np.arange(len(q), dtype=np.int32)
+    if k_best == 2 and method.upper() == "SIFT":
+        keep = (i1 >= 0) & (d0.astype(np.float64) < d1.astype(np.float64) * 0.75)
+        qi, ti, dd = qi[keep], i0[keep], d0[keep]
+    elif k_best == 2:
+        qi = np.repeat(qi, 2)
+        ti, dd = np.stack([i0, i1], 1).reshape(-1), np.stack([d0, d1], 1).reshape(-1)
+        have = ti >= 0
+        qi, ti, dd = qi[have], ti[have], dd[have]
+    else:
+        ti, dd = i0, d0
+    order = np.argsort(dd, kind="stable")
+    return qi[order], ti[order], dd[order]

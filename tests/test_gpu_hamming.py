@@ -99,6 +99,21 @@ def test_nearest_only_path_many_tiles_and_ties(ctx):
         assert np.array_equal(i0[seg_q[s]:seg_q[s + 1]], oi0) and np.array_equal(d0[seg_q[s]:seg_q[s + 1]], od0)
 
 
+def test_many_small_segments_walk_the_persistent_work_list(ctx):
+    """More work items than SMs with short train ranges: the tensor-core engine runs persistent (one CTA per SM takes several
+    items in turn, pipelines and tensor memory carried across items); ragged lengths, some empty segments."""
+    rng = np.random.default_rng(8)
+    n_seg = 420
+    qs, ts = [], []
+    for s_ in range(n_seg):
+        nq = int(rng.integers(0, 300)) if s_ % 37 else 0
+        nt = int(rng.integers(1, 400)) if s_ % 41 else 0
+        q, t = make_descriptors(rng, max(nq, nt, 1) + 10, nq, nt, n_ties=1 if min(nq, nt) > 20 else 0)
+        qs.append(q); ts.append(t)
+    res, seg_q, _, _, _ = run_top2(ctx, qs, ts)
+    check_segments(res, seg_q, qs, ts)
+
+
 def test_train_rows_beyond_max_nt_are_ignored(ctx):
     """t_len[s] > max_nt: both engines clamp the train range to max_nt rows (the bound the scratch is sized for)."""
     rng = np.random.default_rng(6)

@@ -81,6 +81,22 @@ def test_hamming_oracle_matches_bfmatcher():
     assert np.array_equal(i0, rt) and np.array_equal(d0, rd.astype(np.int32))
 
 
+def test_l2_oracle_matches_bfmatcher_on_float_descriptors():
+    """The SIFT / SURF branch of FeatureMatcher (cv2.BFMatcher() = NORM_L2, camera_models.py:397-399, 417-442): the exact-integer
+    restatement against goldens from the reference's class and against live OpenCV (distances bit-equal as float32)."""
+    import cv2
+    g = load_golden("l2.npz")
+    for name, method, k, qk, tk in (("sift1", "SIFT", 1, "q", "t"), ("sift2", "SIFT", 2, "q", "t"), ("surf2", "SURF", 2, "q", "t"),
+                                    ("surf1_64", "SURF", 1, "q64", "t64")):
+        qi, ti, dd = hamming.l2_match(g[qk], g[tk], method, k)
+        assert np.array_equal(qi, g[f"{name}_q"]) and np.array_equal(ti, g[f"{name}_t"]) and np.array_equal(dd, g[f"{name}_d"]), name
+    assert 0 < len(g["sift2_q"]) < len(g["q"])          # the ratio test rejected some queries and kept others
+    knn = cv2.BFMatcher().knnMatch(queryDescriptors=g["q"], trainDescriptors=g["t"], k=2)
+    i0, d0, i1, d1 = hamming.l2_knn2(g["q"], g["t"])
+    assert np.array_equal(np.array([[m.trainIdx for m in r] for r in knn]), np.stack([i0, i1], 1))
+    assert np.array_equal(np.array([[m.distance for m in r] for r in knn], np.float32), np.stack([d0, d1], 1))
+
+
 def test_stereo_and_temporal_matching_oracle():
     g = load_golden("matching_frames.npz")
     m_top, m_bot = [], []

@@ -23,6 +23,12 @@ int sos_hamming_mma_launch(sos_ctx* ctx, const uint32_t* q, const uint32_t* t, c
                            const uint32_t* items, const int32_t* n_items, unsigned max_items, bool top2, void* exp,
                            uint2* partial);
 
+size_t sos_l2_mma_scratch_bytes(int n_seg, int max_nq, int max_nt);
+int sos_l2_mma_launch(sos_ctx* ctx, const float* q, const float* t, int dim, const int32_t* q_start, const int32_t* q_len,
+                      const int32_t* t_start, const int32_t* t_len, int n_seg, int max_nq, int max_nt, int splits,
+                      const uint32_t* items, const int32_t* n_items, unsigned max_items, bool top2, void* exp,
+                      ulonglong2* partial, int32_t* flag);
+
 namespace {
 
 constexpr int HB_THREADS = 128;  // threads per block
@@ -436,6 +442,74 @@ extern "C" int sos_hamming_radius(sos_ctx* ctx, const uint32_t* q, int nq, const
   if (count) hamming_radius_kernel<false><<<grid, 128, 0, ctx->stream>>>((const uint4*)q, nq, (const uint4*)t, nt, max_distance, count, nullptr, nullptr, nullptr);
   else hamming_radius_kernel<true><<<grid, 128, 0, ctx->stream>>>((const uint4*)q, nq, (const uint4*)t, nt, max_distance, nullptr, offset, out_t, out_d);
   SOS_LAUNCHED_AS(ctx, "hamming_radius_kernel");
+  return SOS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Float descriptors, L2 norm (cv2.BFMatcher() of the SIFT / SURF branch, camera_models.py:397-399): tensor-core engine only.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+l2_merge_kernel(const ulonglong2* __restrict__ partial, const int32_t* __restrict__ q_start, const int32_t* __restrict__ q_len,
+                int max_nq, int splits, int32_t* __restrict__ idx0, float* __restrict__ d0, int32_t* __restrict__ idx1,
+                float* __restrict__ d1) {
+  const int seg = blockIdx.y;
+  const int q0 = q_start[seg], nq = min(q_len[seg], max_nq);
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nq) return;
+  const ulonglong2* p = partial + ((size_t)seg * max_nq + row) * splits;
+  unsigned long long k0 = ~0ull, k1 = ~0ull;
+  for (int s = 0; s < splits; ++s) {
+    const ulonglong2 v = p[s];
+    k1 = min(k1, max(k0, v.x));
+    k0 = min(k0, v.x);
+    k1 = min(k1, v.y);
+  }
+  // cv2 reports sqrt of the float32 sum of squared differences; the sum is an exact integer < 2^24 here
+  idx0[q0 + row] = (k0 == ~0ull) ? -1 : (int32_t)(k0 & 0xFFFFFFFFull);
+  d0[q0 + row] = (k0 == ~0ull) ? -1.f : sqrtf((float)(uint32_t)(k0 >> 32));
+  if (idx1) idx1[q0 + row] = (k1 == ~0ull) ? -1 : (int32_t)(k1 & 0xFFFFFFFFull);
+  if (d1) d1[q0 + row] = (k1 == ~0ull) ? -1.f : sqrtf((float)(uint32_t)(k1 >> 32));
+}
+}  // namespace
+
+extern "C" int sos_l2_top2(sos_ctx* ctx, const float* q, const float* t, int dim, const int32_t* q_start,
+                           const int32_t* q_len, const int32_t* t_start, const int32_t* t_len, int n_seg, int max_nq,
+                           int max_nt, int32_t* idx0, float* d0, int32_t* idx1, float* d1, int32_t* not_integer_flag) {
+  SOS_CHECK_ARG(ctx, "ctx is NULL");
+  SOS_CHECK_ARG(n_seg >= 0 && max_nq >= 0 && max_nt >= 0, "negative size");
+  SOS_CHECK_ARG(dim >= 1 && dim <= 128, "descriptor length must be 1..128 (SIFT: 128, SURF: 64)");
+  SOS_CHECK_ARG(n_seg <= 65535, "at most 65535 segments per call");
+  if (n_seg == 0 || max_nq == 0) return SOS_OK;
+  SOS_CHECK_ARG(q && t && q_start && q_len && t_start && t_len && idx0 && d0 && not_integer_flag, "NULL array");
+  SOS_CUDA(cudaSetDevice(ctx->device));
+  const int q_tiles = sos_div_up(max_nq, HB_TILE_Q);
+  SOS_CHECK_ARG(q_tiles <= (1 << ITEM_TILE_BITS), "segment has too many query rows (limit 262144)");
+  const bool top2 = idx1 != nullptr || d1 != nullptr;
+  const int t_tiles = sos_div_up(max_nt > 0 ? max_nt : 1, 128);
+  int splits = sos_div_up(2 * ctx->sm_count, q_tiles * n_seg);
+  if (splits > t_tiles / 4) splits = t_tiles / 4;
+  if (splits > (1 << ITEM_SPLIT_BITS)) splits = 1 << ITEM_SPLIT_BITS;
+  if (splits < 1) splits = 1;
+  void* ws = nullptr;
+  const size_t max_items = (size_t)q_tiles * splits * n_seg;
+  SOS_CHECK_ARG(max_items < ((size_t)1 << 31), "too many work items");
+  const size_t partial_bytes = sos_align_up((size_t)max_nq * n_seg * splits * sizeof(ulonglong2), 256);
+  const size_t items_bytes = sos_align_up(max_items * sizeof(uint32_t), 256);
+  int rc = sos_arena_get(ctx, partial_bytes + items_bytes + 256 + sos_l2_mma_scratch_bytes(n_seg, max_nq, max_nt), &ws);
+  if (rc != SOS_OK) return rc;
+  uint32_t* items = (uint32_t*)((char*)ws + partial_bytes);
+  int32_t* n_items = (int32_t*)((char*)ws + partial_bytes + items_bytes);
+  SOS_CUDA(cudaMemsetAsync(not_integer_flag, 0, sizeof(int32_t), ctx->stream));
+  hamming_plan_kernel<<<1, 256, 0, ctx->stream>>>(q_len, n_seg, max_nq, splits, items, n_items);
+  SOS_LAUNCHED_AS(ctx, "hamming_plan_kernel");
+  rc = sos_l2_mma_launch(ctx, q, t, dim, q_start, q_len, t_start, t_len, n_seg, max_nq, max_nt, splits, items, n_items,
+                         (unsigned)max_items, top2, (char*)ws + partial_bytes + items_bytes + 256, (ulonglong2*)ws,
+                         not_integer_flag);
+  if (rc != SOS_OK) return rc;
+  dim3 mgrid(sos_div_up(max_nq, 256), n_seg);
+  l2_merge_kernel<<<mgrid, 256, 0, ctx->stream>>>((const ulonglong2*)ws, q_start, q_len, max_nq, splits, idx0, d0, idx1, d1);
+  SOS_LAUNCHED_AS(ctx, "l2_merge_kernel");
   return SOS_OK;
 }
 

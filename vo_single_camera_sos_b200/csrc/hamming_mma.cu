@@ -18,8 +18,7 @@
 //   * the epilogue thread that owns query row r (TMEM lane r) reads its 128 accumulators with tcgen05.ld and keeps the
 //     running maximum (3-input integer max: half an instruction per pair); top-2 costs 3 instructions per pair.
 //
-// Data flow per work item (256 query rows x a range of train tiles; ONE PERSISTENT CTA per SM walks the work list,
-// warp-specialised):
+// Data flow per work item (256 query rows x a range of train tiles; one CTA per SM at a time, warp-specialised):
 //   expand kernel : descriptors -> "tile-ready" int8 images in global memory, 128 rows x 288 bytes per tile, stored in the
 //                   canonical K-major no-swizzle UMMA layout (8-row x 16-byte core matrices), so that a tile is ONE
 //                   contiguous 36 KB block
@@ -31,6 +30,8 @@
 //   warp 2        : tensor-memory allocation
 //   warps 4..11   : epilogue, one thread per (query tile, row)
 // The per-split partial keys use the POPC engine's format and are merged by the same hamming_merge_kernel.
+#include <cuda_bf16.h>
+
 #include "sos_common.cuh"
 
 namespace sos_hamming_mma {
@@ -123,11 +124,19 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], int8 x int8 -> int32, M128 N128 K32
-__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-               "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-               ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+// D[tmem] (+)= A[smem] * B[smem], M128 N128, 32 bytes of K per instruction:
+//   KIND_HAMMING: int8 x int8 -> int32 (K32);   KIND_L2: bf16 x bf16 -> float32 (K16)
+constexpr int KIND_HAMMING = 0, KIND_L2 = 1;
+template <int KIND>
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if (KIND == KIND_HAMMING)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // shared-memory matrix descriptor: K-major, no swizzle; core matrices 128 bytes apart along K (LBO) and GROUP_BYTES apart
 // along M/N (SBO); bits [46,48) = 1 (Blackwell descriptor version)
@@ -137,6 +146,8 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
 }
 // instruction descriptor: D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), both K-major, N = 128, M = 128
 constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+// the float-descriptor L2 engine: D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10), both K-major, N = 128, M = 128
+constexpr uint32_t IDESC_L2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
 
 // 32 consecutive accumulator columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
@@ -187,13 +198,36 @@ __device__ __forceinline__ uint32_t acc_to_key(int acc, int tile) {
   return ((uint32_t)((256 - dot) >> 1) << KEY_IDX_BITS) | (uint32_t)(tile * TILE + u);
 }
 
+// ---- float-descriptor L2 engine: epilogue pieces ------------------------------------------------------------------------
+// accumulator (float32, an exact integer) = 2 <q, t> - |t|^2 of (query row, train row u); the largest one is the nearest
+// neighbour.  key = acc * 128 + (127 - u): max(key) = largest accumulator, ties to the lowest train row.
+constexpr int L2_PAD_BELOW = -12000000;   // valid accumulators are >= -128 * 255^2 = -8323200; padding rows sit at -16.7 M
+template <bool TOP2>
+__device__ __forceinline__ void reduce32_l2(const int (&v)[32], int col0, int& m0, int& m1) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int k = __float2int_rn(__int_as_float(v[i])) * 128 + (127 - (col0 + i));
+    if (TOP2) m1 = max(m1, min(m0, k));
+    m0 = max(m0, k);
+  }
+}
+constexpr unsigned long long KEY64_NONE = ~0ull;
+// key of the tile -> (squared distance << 32 | train row of the segment); nq = |q|^2 of this thread's query row
+__device__ __forceinline__ unsigned long long l2_key(int key, int tile, int nq) {
+  const int acc = key >> 7;                          // floor: key = acc * 128 + low, 0 <= low < 128
+  if (acc < L2_PAD_BELOW) return KEY64_NONE;
+  const int u = 127 - (key & 127);
+  return ((unsigned long long)(uint32_t)(nq - acc) << 32) | (unsigned long long)(uint32_t)(tile * TILE + u);
+}
+
 struct Args {
+  const int32_t* a_norm;   // KIND_L2: |q|^2 per expanded query row [n_seg, q_tiles_per_seg * 128]
   const uint8_t *a_exp, *b_exp;
   const int32_t *q_len, *t_len;
   int max_nq, max_nt, splits, q_tiles_per_seg, t_tiles_per_seg;
   const uint32_t* items;
   const int32_t* n_items;
-  uint2* partial;
+  void* partial;           // uint2 (Hamming keys) or ulonglong2 (L2 keys) per (segment, query row, split)
 };
 
 // Work item -> (segment, first query row, split, train tiles [tile_begin, tile_begin + n_iter))
@@ -214,13 +248,14 @@ __device__ __forceinline__ Item decode_item(const Args& a, uint32_t item) {
   return it;
 }
 
-// PERSISTENT: one CTA per SM walks the work list with stride gridDim.x; barriers, the tensor-memory allocation and the three
-// pipelines (train-tile ring, accumulator double buffer, query tiles) live across items, so the tensor pipe only idles while
-// the next item's query tiles land (the train tiles of the next item are already streaming into the ring by then).  The
-// roles agree on every counter because they walk the same items in the same order:
+// A CTA walks the work list with stride gridDim.x (launched either with one CTA per item, or PERSISTENT with one CTA per SM:
+// see the host side).  Barriers, the tensor-memory allocation and the three pipelines (train-tile ring, accumulator double
+// buffer, query tiles) live across items, so in the persistent shape the tensor pipe only idles while the next item's query
+// tiles land (the train tiles of the next item are already streaming into the ring by then).  The roles agree on every
+// counter because they walk the same items in the same order:
 //   t  = train tiles consumed so far by this CTA -> ring stage t % STAGES, accumulator buffer t & 1
 //   ic = items with work so far                  -> phase of the query-tile barriers
-template <bool TOP2, int STAGES>
+template <bool TOP2, int STAGES, int KIND>
 __global__ void __launch_bounds__(THREADS, 1) mma_kernel(Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int n_items = *a.n_items;
@@ -299,9 +334,11 @@ __global__ void __launch_bounds__(THREADS, 1) mma_kernel(Args a) {
           tc_fence_after();
           const uint64_t db = smem_desc(smem_u32(sB) + s * TILE_BYTES);
 #pragma unroll
-          for (int kk = 0; kk < KB / 32; ++kk) tc_mma_i8(tmem + (b * 2) * TILE, da0 + (uint64_t)(16 * kk), db + (uint64_t)(16 * kk), IDESC, kk > 0);
+          for (int kk = 0; kk < KB / 32; ++kk)
+            tc_mma<KIND>(tmem + (b * 2) * TILE, da0 + (uint64_t)(16 * kk), db + (uint64_t)(16 * kk), KIND == KIND_L2 ? IDESC_L2 : IDESC, kk > 0);
 #pragma unroll
-          for (int kk = 0; kk < KB / 32; ++kk) tc_mma_i8(tmem + (b * 2 + 1) * TILE, da1 + (uint64_t)(16 * kk), db + (uint64_t)(16 * kk), IDESC, kk > 0);
+          for (int kk = 0; kk < KB / 32; ++kk)
+            tc_mma<KIND>(tmem + (b * 2 + 1) * TILE, da1 + (uint64_t)(16 * kk), db + (uint64_t)(16 * kk), KIND == KIND_L2 ? IDESC_L2 : IDESC, kk > 0);
           tc_commit(BAR(EMPTY + s));    // shared-memory stage free once these MMAs have read it
           tc_commit(BAR(TFULL + b));    // accumulators complete
         }
@@ -316,6 +353,9 @@ __global__ void __launch_bounds__(THREADS, 1) mma_kernel(Args a) {
       const Item it = decode_item(a, a.items[w]);
       const int row = it.q_tile * 256 + g * TILE + quarter * 32 + lane;
       uint32_t k0 = KEY_NONE, k1 = KEY_NONE;
+      unsigned long long w0 = KEY64_NONE, w1 = KEY64_NONE;
+      int nq_norm = 0;
+      if (KIND == KIND_L2 && it.n_iter > 0) nq_norm = a.a_norm[(size_t)it.seg * a.q_tiles_per_seg * TILE + row];
       for (int k = 0; k < it.n_iter; ++k, ++t) {
         const uint32_t b = t & 1;
         mbar_wait(BAR(TFULL + b), (t >> 1) & 1);
@@ -323,39 +363,125 @@ __global__ void __launch_bounds__(THREADS, 1) mma_kernel(Args a) {
         const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (b * 2 + g) * TILE;
         int m0 = INT_MIN, m1 = INT_MIN;
         int va[32], vb[32];
+        auto reduce = [&](const int (&v)[32], int col0) {
+          if (KIND == KIND_L2) reduce32_l2<TOP2>(v, col0, m0, m1);
+          else reduce32<TOP2>(v, m0, m1);
+        };
         tmem_ld32(taddr, va);
         tmem_ld_wait(va);
         tmem_ld32(taddr + 32, vb);          // in flight while va is reduced
-        reduce32<TOP2>(va, m0, m1);
+        reduce(va, 0);
         tmem_ld_wait(vb);
         tmem_ld32(taddr + 64, va);
-        reduce32<TOP2>(vb, m0, m1);
+        reduce(vb, 32);
         tmem_ld_wait(va);
         tmem_ld32(taddr + 96, vb);
-        reduce32<TOP2>(va, m0, m1);
+        reduce(va, 64);
         tmem_ld_wait(vb);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(BAR(TEMPTY + b));     // buffer b may be overwritten
-        reduce32<TOP2>(vb, m0, m1);
+        reduce(vb, 96);
         const int tile = it.tile_begin + k;
-        const uint32_t key0 = acc_to_key(m0, tile);
-        if (TOP2) {
-          const uint32_t key1 = acc_to_key(m1, tile);
-          k1 = min(k1, max(k0, key0));                    // merge two sorted pairs
-          k0 = min(k0, key0);
-          k1 = min(k1, key1);
+        if (KIND == KIND_L2) {
+          const unsigned long long key0 = l2_key(m0, tile, nq_norm);
+          if (TOP2) {
+            const unsigned long long key1 = m1 == INT_MIN ? KEY64_NONE : l2_key(m1, tile, nq_norm);
+            w1 = min(w1, max(w0, key0));
+            w0 = min(w0, key0);
+            w1 = min(w1, key1);
+          } else {
+            w0 = min(w0, key0);
+          }
         } else {
-          k0 = min(k0, key0);
+          const uint32_t key0 = acc_to_key(m0, tile);
+          if (TOP2) {
+            const uint32_t key1 = acc_to_key(m1, tile);
+            k1 = min(k1, max(k0, key0));                    // merge two sorted pairs
+            k0 = min(k0, key0);
+            k1 = min(k1, key1);
+          } else {
+            k0 = min(k0, key0);
+          }
         }
       }
-      // (no train rows in this split: both keys stay KEY_NONE)
-      if (row < it.nq) a.partial[((size_t)it.seg * a.max_nq + row) * a.splits + it.split] = make_uint2(k0, k1);
+      // (no train rows in this split: the keys stay "none")
+      if (row < it.nq) {
+        const size_t o = ((size_t)it.seg * a.max_nq + row) * a.splits + it.split;
+        if (KIND == KIND_L2) ((ulonglong2*)a.partial)[o] = make_ulonglong2(w0, w1);
+        else ((uint2*)a.partial)[o] = make_uint2(k0, k1);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// ---- float-descriptor L2 engine: expansion ---------------------------------------------------------------------------
+// Float descriptors whose values are integers in [0, 255] (what cv2's SIFT returns) are exactly representable in bfloat16,
+// their dot products (< 2^24) exactly in the float32 accumulator: |q - t|^2 = |q|^2 + |t|^2 - 2 <q, t> comes out of the
+// tensor core as an exact integer.  A tile has the Hamming engine's geometry: 144 bf16 = 288 bytes per row; elements 0..127
+// hold 2 q (query role) or t (train role), elements 128..130 carry the norm: (1, 256, 65536) against minus the base-256
+// digits of |t|^2, so that the accumulator is 2 <q, t> - |t|^2; padding rows get the digits (255, 255, 255).
+// One block per tile; every warp first sums the squares of 16 rows.  flag[0] is set when a value is not an integer in [0, 255].
+__global__ void __launch_bounds__(256)
+expand_l2_kernel(const float* __restrict__ desc, int dim, const int32_t* __restrict__ start, const int32_t* __restrict__ len,
+                 int max_rows, int tiles_per_seg, int role, uint8_t* __restrict__ out, int32_t* __restrict__ norms,
+                 int32_t* __restrict__ flag) {
+  __shared__ int snorm[TILE];
+  const int seg = blockIdx.y, tile = blockIdx.x;
+  const int n = min(len[seg], max_rows);
+  const int row0 = tile * TILE;
+  if (row0 >= n) return;
+  const float* d = desc + (size_t)start[seg] * dim;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  bool bad = false;
+  for (int r = warp; r < TILE; r += 8) {
+    const int row = row0 + r;
+    int acc = 0;
+    if (row < n)
+      for (int k = lane; k < dim; k += 32) {
+        const float v = __ldg(d + (size_t)row * dim + k);
+        const int iv = (int)v;
+        bad |= !(v >= 0.f && v <= 255.f && (float)iv == v);
+        acc += iv * iv;
+      }
+    acc = __reduce_add_sync(0xFFFFFFFFu, acc);
+    if (lane == 0) snorm[r] = row < n ? acc : -1;
+  }
+  if (bad) atomicOr(flag, 1);
+  __syncthreads();
+  uint8_t* tbase = out + ((size_t)seg * tiles_per_seg + tile) * TILE_BYTES;
+  if (role == 0 && norms)
+    for (int r = threadIdx.x; r < TILE; r += 256) norms[((size_t)seg * tiles_per_seg + tile) * TILE + r] = max(snorm[r], 0);
+  const float scale = role == 0 ? 2.f : 1.f;
+  for (int u = threadIdx.x; u < TILE * CHUNKS; u += 256) {
+    const int r8 = u & 7, chunk = (u >> 3) % CHUNKS, rg = u / (8 * CHUNKS);
+    const int r = rg * 8 + r8, row = row0 + r;
+    const bool valid = row < n;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (chunk < 16) {                       // elements 8 chunk .. 8 chunk + 7
+      if (valid) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int k = chunk * 8 + e;
+          const float v = k < dim ? scale * __ldg(d + (size_t)row * dim + k) : 0.f;
+          w[e >> 1] |= (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v)) << (16 * (e & 1));
+        }
+      }
+    } else if (chunk == 16) {               // elements 128 .. 135: the norm digits
+      float e0, e1, e2;
+      if (role == 0) { e0 = 1.f; e1 = 256.f; e2 = 65536.f; }
+      else {
+        const int nt = valid ? snorm[r] : 0xFFFFFF;
+        e0 = -(float)(nt & 255); e1 = -(float)((nt >> 8) & 255); e2 = -(float)((nt >> 16) & 255);
+      }
+      w[0] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(e0)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(e1)) << 16);
+      w[1] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(e2));
+    }
+    *(uint4*)(tbase + (size_t)rg * GROUP_BYTES + chunk * 128 + r8 * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
 }
 
 }  // namespace sos_hamming_mma
@@ -388,18 +514,70 @@ int sos_hamming_mma_launch(sos_ctx* ctx, const uint32_t* q, const uint32_t* t, c
   a.a_exp = a_exp; a.b_exp = b_exp; a.q_len = q_len; a.t_len = t_len;
   a.max_nq = max_nq; a.max_nt = max_nt; a.splits = splits; a.q_tiles_per_seg = qt; a.t_tiles_per_seg = tt;
   a.items = items; a.n_items = n_items; a.partial = partial;
+  a.a_norm = nullptr;
   // ring depth 4 (221 KB of shared memory); 3 stages measured the same (profiles/r02/score_variants_and_ring_depth_ab.log)
   constexpr int ST = 4;
   static bool attr_set[64][2] = {};     // per device: the opt-in to > 48 KB of dynamic shared memory
   const int dev = ctx->device & 63, v = top2 ? 1 : 0;
   if (!attr_set[dev][v]) {
-    if (top2) SOS_CUDA(cudaFuncSetAttribute(mma_kernel<true, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(ST)));
-    else SOS_CUDA(cudaFuncSetAttribute(mma_kernel<false, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(ST)));
+    if (top2) SOS_CUDA(cudaFuncSetAttribute(mma_kernel<true, ST, KIND_HAMMING>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(ST)));
+    else SOS_CUDA(cudaFuncSetAttribute(mma_kernel<false, ST, KIND_HAMMING>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(ST)));
     attr_set[dev][v] = true;
   }
-  const unsigned grid = max_items < (unsigned)ctx->sm_count ? max_items : (unsigned)ctx->sm_count;   // one CTA per SM
-  if (top2) mma_kernel<true, ST><<<grid, THREADS, smem_bytes(ST), ctx->stream>>>(a);
-  else mma_kernel<false, ST><<<grid, THREADS, smem_bytes(ST), ctx->stream>>>(a);
+  // One kernel, two launch shapes.  Short items (stereo buckets: a handful of train tiles each) run PERSISTENT — one CTA per
+  // SM walks the work list, so barriers, tensor memory and the pipelines survive from item to item (measured: 0.083 ->
+  // 0.076 ms on the 384 C2 buckets).  Long items (temporal matching: ~36 train tiles each) get one CTA per item and leave
+  // the balancing to the hardware scheduler: the fixed striding of the persistent shape loses more to unequal SMs than the
+  // per-item set-up costs (0.285 vs 0.300 ms; profiles/r02/hamming_ab_persistent.log).
+  const bool persistent = max_nt <= 2048;
+  const unsigned grid = (persistent && max_items > (unsigned)ctx->sm_count) ? (unsigned)ctx->sm_count : max_items;
+  if (top2) mma_kernel<true, ST, KIND_HAMMING><<<grid, THREADS, smem_bytes(ST), ctx->stream>>>(a);
+  else mma_kernel<false, ST, KIND_HAMMING><<<grid, THREADS, smem_bytes(ST), ctx->stream>>>(a);
   SOS_LAUNCHED_AS(ctx, "hamming_mma_kernel");
+  return SOS_OK;
+}
+
+// The float-descriptor L2 engine (sos_l2_top2 in hamming.cu).  `exp` = expanded tiles followed by the query norms.
+size_t sos_l2_mma_scratch_bytes(int n_seg, int max_nq, int max_nt) {
+  using namespace sos_hamming_mma;
+  const size_t qt = (size_t)((max_nq + 255) / 256) * 2;
+  return sos_hamming_mma_scratch_bytes(n_seg, max_nq, max_nt) + (size_t)n_seg * qt * TILE * sizeof(int32_t) + 256;
+}
+
+int sos_l2_mma_launch(sos_ctx* ctx, const float* q, const float* t, int dim, const int32_t* q_start, const int32_t* q_len,
+                      const int32_t* t_start, const int32_t* t_len, int n_seg, int max_nq, int max_nt, int splits,
+                      const uint32_t* items, const int32_t* n_items, unsigned max_items, bool top2, void* exp,
+                      ulonglong2* partial, int32_t* flag) {
+  using namespace sos_hamming_mma;
+  const int qt = ((max_nq + 255) / 256) * 2, tt = (max_nt + TILE - 1) / TILE;
+  uint8_t* a_exp = (uint8_t*)exp;
+  uint8_t* b_exp = a_exp + (size_t)n_seg * qt * TILE_BYTES;
+  int32_t* norms = (int32_t*)(b_exp + sos_align_up((size_t)n_seg * tt * TILE_BYTES, 256));
+  if (qt > 0) {
+    expand_l2_kernel<<<dim3(qt, n_seg), 256, 0, ctx->stream>>>(q, dim, q_start, q_len, max_nq, qt, 0, a_exp, norms, flag);
+    SOS_LAUNCHED_AS(ctx, "l2_expand_kernel");
+  }
+  if (tt > 0) {
+    expand_l2_kernel<<<dim3(tt, n_seg), 256, 0, ctx->stream>>>(t, dim, t_start, t_len, max_nt, tt, 1, b_exp, nullptr, flag);
+    SOS_LAUNCHED_AS(ctx, "l2_expand_kernel");
+  }
+  Args a;
+  a.a_norm = norms;
+  a.a_exp = a_exp; a.b_exp = b_exp; a.q_len = q_len; a.t_len = t_len;
+  a.max_nq = max_nq; a.max_nt = max_nt; a.splits = splits; a.q_tiles_per_seg = qt; a.t_tiles_per_seg = tt;
+  a.items = items; a.n_items = n_items; a.partial = partial;
+  constexpr int ST = 4;
+  static bool attr_set[64][2] = {};
+  const int dev = ctx->device & 63, v = top2 ? 1 : 0;
+  if (!attr_set[dev][v]) {
+    if (top2) SOS_CUDA(cudaFuncSetAttribute(mma_kernel<true, ST, KIND_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(ST)));
+    else SOS_CUDA(cudaFuncSetAttribute(mma_kernel<false, ST, KIND_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(ST)));
+    attr_set[dev][v] = true;
+  }
+  const bool persistent = max_nt <= 2048;
+  const unsigned grid = (persistent && max_items > (unsigned)ctx->sm_count) ? (unsigned)ctx->sm_count : max_items;
+  if (top2) mma_kernel<true, ST, KIND_L2><<<grid, THREADS, smem_bytes(ST), ctx->stream>>>(a);
+  else mma_kernel<false, ST, KIND_L2><<<grid, THREADS, smem_bytes(ST), ctx->stream>>>(a);
+  SOS_LAUNCHED_AS(ctx, "l2_mma_kernel");
   return SOS_OK;
 }

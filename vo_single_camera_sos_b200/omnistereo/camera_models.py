@@ -19,7 +19,9 @@ def get_normalized_points(points_wrt_M):
 class FeatureMatcher(object):
     """Brute-force descriptor matcher with the reference's interface.  For binary descriptors ("ORB", ...) the distances
     are Hamming distances computed by sos_hamming_top2; results are ordered like sorted(matches, key=distance), i.e.
-    stably by (distance, queryIdx), with ties between train rows going to the lowest trainIdx (cv2.BFMatcher)."""
+    stably by (distance, queryIdx), with ties between train rows going to the lowest trainIdx (cv2.BFMatcher).
+    method "SIFT" / "SURF" selects the L2 norm on float descriptors like the reference (camera_models.py:397-399): the
+    tensor-core matcher sos_l2_top2, exact for integer-valued descriptors (cv2's SIFT output)."""
 
     def __init__(self, method, matcher_type, k_best, *args, **kwargs):
         self.feature_detection_method = method
@@ -35,14 +37,18 @@ class FeatureMatcher(object):
         self.ratio = kwargs.get("ratio", None)
         if matcher_type != "BF":
             raise NotImplementedError("only the brute-force matcher of the reference's default path is mirrored")
-        if str(method).upper() in ("SIFT", "SURF"):
-            raise NotImplementedError("float descriptors (L2 norm) are not on the SOS hot path; binary descriptors only")
+        self.float_descriptors = str(method).upper() in ("SIFT", "SURF")
+        if self.float_descriptors and (self.use_radius_match or self.cross_check):
+            raise NotImplementedError("radius match / cross check are mirrored for binary descriptors only")
         if self.k_best > 2:
             raise NotImplementedError("k_best > 2 is not mirrored (the device kernel keeps the two nearest neighbours)")
 
     def match_arrays(self, query_descriptors, train_descriptors, max_descriptor_distance_radius=-1, px_query=None,
                      px_train=None, max_horizontal_diff=-1.0, min_rectified_disparity=-1.0):
         """(queryIdx, trainIdx, distance) int32 arrays in the reference's output order; optional fused pixel gate."""
+        if self.float_descriptors:
+            return self._match_arrays_l2(query_descriptors, train_descriptors, px_query, px_train, max_horizontal_diff,
+                                         min_rectified_disparity)
         q = np.ascontiguousarray(query_descriptors, np.uint8)
         t = np.ascontiguousarray(train_descriptors, np.uint8)
         if q.ndim != 2 or t.ndim != 2 or q.shape[1] != 32 or t.shape[1] != 32:
@@ -103,6 +109,41 @@ class FeatureMatcher(object):
             max_du=float(max_horizontal_diff), min_dv=float(min_rectified_disparity), ratio=float(self.ratio or 0.75))
         n = int(oc.cpu().numpy()[0])
         return oq[:n].cpu().numpy(), ot[:n].cpu().numpy(), od[:n].cpu().numpy()
+
+    def _match_arrays_l2(self, query_descriptors, train_descriptors, px_query, px_train, max_du, min_dv):
+        """The SIFT / SURF branch (camera_models.py:397-399, 417-442): cv2.BFMatcher() = NORM_L2.  k_best = 1: the nearest
+        train row per query; k_best = 2: knnMatch(k = 2), for "SIFT" filtered by Lowe's ratio test m0.distance <
+        0.75 * m1.distance (len(m) == 2 required, :423), otherwise both neighbours flattened; then sorted(key=distance).
+        Distances are float32 like cv2's."""
+        q = np.ascontiguousarray(query_descriptors, np.float32)
+        t = np.ascontiguousarray(train_descriptors, np.float32)
+        if q.ndim != 2 or t.ndim != 2 or q.shape[1] != t.shape[1] or q.shape[1] > 128:
+            raise ValueError("float descriptors must be N x dim float32 with dim <= 128")
+        nq, nt = len(q), len(t)
+        if nq == 0 or nt == 0:
+            return np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0, np.float32)
+        ctx = device_context()
+        i32 = lambda v: torch.tensor([v], dtype=torch.int32, device=ctx.device)
+        zero = i32(0)
+        i0, d0, i1, d1 = (x.cpu().numpy() for x in ctx.l2_top2(to_device(q), to_device(t), zero, i32(nq), zero, i32(nt), nq, nt))
+        qi = np.arange(nq, dtype=np.int32)
+        if self.k_best == 2 and str(self.feature_detection_method).upper() == "SIFT":
+            keep = (i1 >= 0) & (d0.astype(np.float64) < d1.astype(np.float64) * 0.75)      # Python floats in the reference
+            qi, ti, dd = qi[keep], i0[keep], d0[keep]
+        elif self.k_best == 2:
+            qi = np.repeat(qi, 2)
+            ti, dd = np.stack([i0, i1], 1).reshape(-1), np.stack([d0, d1], 1).reshape(-1)
+            have = ti >= 0
+            qi, ti, dd = qi[have], ti[have], dd[have]
+        else:
+            ti, dd = i0, d0
+        order = np.argsort(dd, kind="stable")
+        qi, ti, dd = qi[order], ti[order], dd[order]
+        if px_query is not None and px_train is not None:
+            from .common_cv import filter_pixel_correspondences
+            ok = filter_pixel_correspondences(np.asarray(px_train)[ti], np.asarray(px_query)[qi], min_dv, max_du)
+            qi, ti, dd = qi[ok], ti[ok], dd[ok]
+        return qi, ti.astype(np.int32), dd
 
     def match(self, query_descriptors, train_descriptors, max_descriptor_distance_radius=-1):
         """List of cv2.DMatch sorted by distance — the reference's return type (camera_models.py:404-446)."""

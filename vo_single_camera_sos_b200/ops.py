@@ -179,6 +179,32 @@ class Context:
                                         d1.data_ptr() if d1 is not None else None))
         return idx0, d0, idx1, d1
 
+    def l2_top2(self, q: torch.Tensor, t: torch.Tensor, q_start, q_len, t_start, t_len, max_nq: int, max_nt: int,
+                want_second: bool = True):
+        """Float descriptors (integer-valued in [0, 255], e.g. cv2 SIFT): q [Nq, dim], t [Nt, dim] float32, dim <= 128.
+        -> (idx0 int32, d0 float32, idx1, d1) like hamming_top2, distances = cv2's NORM_L2.  Raises ValueError when a
+        descriptor value is not an integer in [0, 255] (the tensor-core path is exact only for those)."""
+        self._sync_stream()
+        nq, dim = q.shape
+        if t.dim() != 2 or t.shape[1] != dim or dim > 128:
+            raise ValueError("q / t must be [N, dim] with the same dim <= 128")
+        n_seg = q_start.numel()
+        idx0 = torch.full((nq,), -1, dtype=torch.int32, device=self.device)
+        d0 = torch.full((nq,), -1.0, dtype=torch.float32, device=self.device)
+        idx1 = torch.full((nq,), -1, dtype=torch.int32, device=self.device) if want_second else None
+        d1 = torch.full((nq,), -1.0, dtype=torch.float32, device=self.device) if want_second else None
+        flag = torch.zeros((1,), dtype=torch.int32, device=self.device)
+        check(self.lib.sos_l2_top2(self._h, self._t(q, torch.float32, "q"), self._t(t, torch.float32, "t"), int(dim),
+                                   self._t(q_start, torch.int32, "q_start"), self._t(q_len, torch.int32, "q_len"),
+                                   self._t(t_start, torch.int32, "t_start"), self._t(t_len, torch.int32, "t_len"), n_seg,
+                                   int(max_nq), int(max_nt), idx0.data_ptr(), d0.data_ptr(),
+                                   idx1.data_ptr() if idx1 is not None else None, d1.data_ptr() if d1 is not None else None,
+                                   flag.data_ptr()))
+        if int(flag.item()):
+            raise ValueError("float descriptors must hold integers in [0, 255] (cv2 SIFT); other values are not supported "
+                             "by the exact tensor-core L2 matcher")
+        return idx0, d0, idx1, d1
+
     def hamming_radius(self, q: torch.Tensor, t: torch.Tensor, max_distance: int):
         """Every (query, train, distance) with distance <= max_distance, query-major, train index ascending within a query
         (cv2.BFMatcher.radiusMatch).  -> (query int64 [M], train int32 [M], distance int32 [M]) device tensors."""
