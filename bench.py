@@ -396,7 +396,7 @@ def run_gpu(args, rank, local_rank, world):
 
     tmem_peak = ctx.peak_tmem_read()     # TB/s, measured: tcgen05.ld over all SMs
     ffma2_peak = ctx.peak_ffma2()        # TFLOP/s, measured: packed fma.rn.f32x2
-    remap_name = "remap3b_kernel" if os.environ.get("SOS_REMAP_TMA", "0") not in ("", "0") else "remap3p_kernel"
+    remap_name = "remap3b_kernel" if f"remap3b_kernel#0" in kernels else "remap3p_kernel"
     mma_engine = f"hamming_mma_kernel#1" in kernels
     roof = {}
     t = k_ms(f"{remap_name}#0")

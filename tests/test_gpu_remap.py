@@ -13,12 +13,13 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-@pytest.fixture(autouse=True, params=["patch", "tma"])
+@pytest.fixture(autouse=True, params=["tma", "patch"])
 def remap_variant(request, monkeypatch):
-    """Every test of this file runs against both 3-channel kernels the library ships: the per-frame patch kernel (default)
-    and the batch-looped kernel with TMA-staged LUT tiles (SOS_REMAP_TMA=1; csrc/remap.cu reads the switch per call)."""
-    if request.param == "tma":
-        monkeypatch.setenv("SOS_REMAP_TMA", "1")
+    """Every test of this file runs against both 3-channel kernels the library ships: the batch-looped kernel with TMA-staged
+    LUT tiles (default whenever the source rows are a multiple of 8 bytes) and the per-frame patch kernel (SOS_REMAP_TMA=0,
+    and every other shape; csrc/remap.cu reads the switch per call)."""
+    if request.param == "patch":
+        monkeypatch.setenv("SOS_REMAP_TMA", "0")
     else:
         monkeypatch.delenv("SOS_REMAP_TMA", raising=False)
     return request.param

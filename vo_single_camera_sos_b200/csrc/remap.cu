@@ -294,27 +294,38 @@ remap3p_kernel(const uint8_t* __restrict__ src, int wide_ok, int src_h, int src_
 }
 
 
-// ---- batch-looped variant with TMA-staged LUT tiles -------------------------------------------------------------------
-// The LUT depends on (view, row, col) only, so a block that owns one 8 x 128 LUT tile can serve that tile for EVERY frame
-// of the batch: the tile is fetched once (8 KB, one cp.async.bulk row copy per panorama row, completion on an mbarrier),
-// each thread decodes its four entries into registers once (source offset, packed weights), and the per-frame loop is
-// only tap loads + dp4a arithmetic + stores.  That removes the LUT stream from the L1 fill path (521 MB -> 33 MB per C2
-// step of 16 frames) and, more importantly, the LUT-load -> tap-load dependency from the per-pixel critical path: all tap
-// addresses of a frame are known before the loop body starts.  Lane mapping, arithmetic and output staging are those of
-// remap3p_kernel (bit-exact).
+// ---- batch-looped kernel with TMA-staged LUT tiles (the default 3-channel path) --------------------------------------------
+// The LUT depends on (view, row, col) only, so a block that owns one 8 x 128 LUT tile serves that tile for EVERY frame of
+// its share of the batch: the tile is fetched once (8 KB, one cp.async.bulk row copy per panorama row, completion on an
+// mbarrier), each lane decodes its four entries ONCE into registers (32-bit source offset, alignment shift, weights), and
+// the per-frame loop is nothing but 16 tap loads, the alignment funnel, dp4a arithmetic and the staged store:
+//   * ~45 instructions per pixel and frame instead of ~100 (ncu, round 1: the per-frame patch kernel is issue bound and
+//     spends more than half of its instructions on LUT decode, 64-bit address arithmetic, per-warp prologue and branches);
+//   * all 16 loads of a lane are in flight before the first use: no LUT-load -> tap-load dependency in the loop;
+//   * rows outside the mirror's field of view (38 % of the C2 panorama: whole rows of the LUT are "dead") never touch the
+//     source image: the warp stages the border colour once and only stores;
+//   * lanes that are neither fast nor dead (image edge, mirror-mask edge: ~1 % of the 4 x 8 patches) are fixed up by the
+//     generic per-tap path inside a warp-uniform branch.
+// Vertical interpolation first: one PRMT gathers (row 0, row 1) bytes of the left and right tap of a channel, dp4a with the
+// weights (32 - ay, ay, 0, 0) / (0, 0, 32 - ay, ay) gives vL and vR, then (wl * vL + ax * vR + 512) >> 10 — the same integer
+// as cv::remap's (sum_i w_i p_i + 16384) >> 15 because the Q15 weights are 32 * (6-bit x 6-bit products).
+// Requires an 8-byte aligned source whose rows are a multiple of 8 bytes (src_w % 8 == 0), so that the alignment of a tap
+// address is the same for every frame and both rows; other shapes take remap3p_kernel.
 constexpr int RB_TILE_ROWS = RP_ROWS * RP_WARPS_Y;   // 8
 constexpr int RB_TILE_COLS = RP_COLS * RP_WARPS_X;   // 128
+constexpr int RB_NP = RP_COLS / 8;                   // passes per lane
 
 __device__ inline uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(RP_WARPS_X * RP_WARPS_Y * 32)
-remap3b_kernel(const uint8_t* __restrict__ src, int wide_ok, int batch, int src_h, int src_w, const uint64_t* __restrict__ lut,
-               int views, int rows, int cols, RemapConst k, uint8_t* __restrict__ dst) {
+__global__ void __launch_bounds__(RP_WARPS_X * RP_WARPS_Y * 32, 3)
+remap3b_kernel(const uint8_t* __restrict__ src, int batch, int frames_per_block, int src_h, int src_w,
+               const uint64_t* __restrict__ lut, int views, int rows, int cols, RemapConst k, uint8_t* __restrict__ dst) {
   __shared__ __align__(128) uint64_t slut[RB_TILE_ROWS][RB_TILE_COLS];
   __shared__ __align__(16) uint8_t sout[RP_WARPS_X * RP_WARPS_Y][RP_ROWS][RP_COLS * 3];
   __shared__ __align__(8) uint64_t mbar;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int view = blockIdx.z;
+  const int view = blockIdx.z % views;
+  const int b_begin = (blockIdx.z / views) * frames_per_block, b_end = min(batch, b_begin + frames_per_block);
   const int row_t0 = blockIdx.y * RB_TILE_ROWS, col_t0 = blockIdx.x * RB_TILE_COLS;
   const uint64_t* ltile = lut + ((size_t)view * rows + row_t0) * cols + col_t0;
   // bulk copies need 16-byte aligned addresses and sizes: full tiles of an even-width, 16-byte aligned LUT
@@ -354,68 +365,106 @@ remap3b_kernel(const uint8_t* __restrict__ src, int wide_ok, int batch, int src_
   if (row0 >= rows || col0 >= cols) return;   // whole warps leave together; only __syncwarp below
   const int npx = min(RP_COLS, cols - col0), nrows = min(RP_ROWS, rows - row0);
   const int r = lane >> 3, cc = lane & 7;
-  const size_t row_bytes = (size_t)src_w * 3;
+  const uint32_t row_bytes = (uint32_t)src_w * 3u;
   const size_t img_bytes = (size_t)src_h * row_bytes;
-  // decode once: source offset + packed weights per pass; bit p of `fast` / `dead` / `slow` classifies pass p
+  // decode once.  Bit p of fastm / deadm / slowm classifies this lane's pixel of pass p:
   //   fast: all four taps usable, wide loads stay inside the image    dead: no tap inside the image -> border colour
-  //   slow: everything else (image edge, mirror-mask edge)            -> generic per-tap path, rare
-  constexpr int NP = RP_COLS / 8;
-  uint32_t off[NP], wxy[NP];
-  uint32_t fast = 0, dead = 0, slow = 0;
+  //   slow: everything else (image edge, mirror-mask edge)            -> generic per-tap path, per frame
+  uint32_t off[RB_NP], sh[RB_NP], wl[RB_NP], ax[RB_NP], wya[RB_NP];
+  bool hiw[RB_NP];
+  uint32_t fastm = 0, deadm = 0, slowm = 0;
 #pragma unroll
-  for (int pass = 0; pass < NP; ++pass) {
+  for (int pass = 0; pass < RB_NP; ++pass) {
     const int c = pass * 8 + cc;
     const uint64_t e = slut[wy * RP_ROWS + r][wx * RP_COLS + c];
-    const uint32_t hi = (uint32_t)(e >> 32);
+    const uint32_t lo = (uint32_t)e, hi = (uint32_t)(e >> 32);
     const bool live = r < nrows && c < npx;
-    const bool w = live && wide_ok && (hi & (1u << 24));
+    const bool w = live && (hi & (1u << 24));
     const bool dd = live && !w && ((hi >> 16) & 0xFu) == 0;
-    fast |= (w ? 1u : 0u) << pass;
-    dead |= (dd ? 1u : 0u) << pass;
-    slow |= ((live && !w && !dd) ? 1u : 0u) << pass;
-    const int x0 = (int)(int16_t)(e & 0xFFFF), y0 = (int)(int16_t)((e >> 16) & 0xFFFF);
-    off[pass] = w ? (uint32_t)((y0 * src_w + x0) * 3) : 0u;   // non-fast lanes read (and discard) the first bytes of the image
-    const uint32_t ax = hi & 31u, ay = (hi >> 5) & 31u;
-    wxy[pass] = (32u - ax) | (ax << 8) | ((32u - ay) << 16) | (ay << 24);
+    fastm |= (w ? 1u : 0u) << pass;
+    deadm |= (dd ? 1u : 0u) << pass;
+    slowm |= ((live && !w && !dd) ? 1u : 0u) << pass;
+    // fast entries have 0 <= x0, y0 (all taps inside the image): plain unsigned arithmetic
+    const uint32_t o = w ? ((lo >> 16) * (uint32_t)src_w + (lo & 0xFFFFu)) * 3u : 0u;   // other lanes read (and discard) the first bytes of the frame
+    off[pass] = o & ~7u;
+    sh[pass] = (o & 3u) * 8u;
+    hiw[pass] = (o & 4u) != 0u;
+    ax[pass] = hi & 31u;
+    wl[pass] = 32u - ax[pass];
+    const uint32_t ay = (hi >> 5) & 31u;
+    wya[pass] = (32u - ay) | (ay << 8);
   }
-  const uint32_t border3 = (uint32_t)k.border[0] | ((uint32_t)k.border[1] << 8) | ((uint32_t)k.border[2] << 16);
+  const bool any_fast = __any_sync(0xFFFFFFFFu, fastm != 0u);
+  const bool any_slow = __any_sync(0xFFFFFFFFu, slowm != 0u);
   uint8_t* so = sout[warp][r];
+  // dead pixels are the same in every frame (the fast path below never stores to them)
+#pragma unroll
+  for (int pass = 0; pass < RB_NP; ++pass)
+    if ((deadm >> pass) & 1u) {
+      const int c = pass * 8 + cc;
+      so[c * 3 + 0] = (uint8_t)k.border[0];
+      so[c * 3 + 1] = (uint8_t)k.border[1];
+      so[c * 3 + 2] = (uint8_t)k.border[2];
+    }
+  __syncwarp();
   const int nbytes = npx * 3;
   const size_t drow = (size_t)cols * 3;
   const int r2 = lane / 6, ch = lane - r2 * 6;
-  for (int b = 0; b < batch; ++b) {
-    const uint8_t* s = src + (size_t)b * img_bytes;
-    // all tap loads of the frame first (unconditional: 16 independent 64-bit loads per lane in flight), then arithmetic
-    uint32_t t0l[NP], t0h[NP], t1l[NP], t1h[NP];
+  const uint8_t* s = src + (size_t)b_begin * img_bytes;
+  uint8_t* d0 = dst + ((((size_t)b_begin * views + view) * rows + row0) * cols + col0) * 3;
+  const size_t dframe = (size_t)views * rows * cols * 3;
+  const bool vec_out = nbytes == RP_COLS * 3 && ((((uintptr_t)d0) | drow | dframe) & 15) == 0;
+  for (int b = b_begin; b < b_end; ++b, s += img_bytes, d0 += dframe) {
+    if (any_fast) {
+      // all tap loads of the frame first (unconditional: 16 independent 64-bit loads per lane in flight), then arithmetic
+      uint2 t0a[RB_NP], t0b[RB_NP], t1a[RB_NP], t1b[RB_NP];
 #pragma unroll
-    for (int pass = 0; pass < NP; ++pass) {
-      const uint8_t* p = s + off[pass];
-      load6_32(p, t0l[pass], t0h[pass]);
-      load6_32(p + row_bytes, t1l[pass], t1h[pass]);
+      for (int pass = 0; pass < RB_NP; ++pass) {
+        const uint2* p0 = (const uint2*)(s + off[pass]);
+        const uint2* p1 = (const uint2*)(s + off[pass] + row_bytes);
+        t0a[pass] = __ldg(p0);
+        t0b[pass] = __ldg(p0 + 1);
+        t1a[pass] = __ldg(p1);
+        t1b[pass] = __ldg(p1 + 1);
+      }
+#pragma unroll
+      for (int pass = 0; pass < RB_NP; ++pass) {
+        const int c = pass * 8 + cc;
+        const bool h = hiw[pass];
+        const uint32_t A0 = h ? t0a[pass].y : t0a[pass].x, B0 = h ? t0b[pass].x : t0a[pass].y, C0 = h ? t0b[pass].y : t0b[pass].x;
+        const uint32_t A1 = h ? t1a[pass].y : t1a[pass].x, B1 = h ? t1b[pass].x : t1a[pass].y, C1 = h ? t1b[pass].y : t1b[pass].x;
+        const uint32_t lo0 = __funnelshift_r(A0, B0, sh[pass]), hi0 = __funnelshift_r(B0, C0, sh[pass]);
+        const uint32_t lo1 = __funnelshift_r(A1, B1, sh[pass]), hi1 = __funnelshift_r(B1, C1, sh[pass]);
+        // (row 0, row 1) byte pairs: q0 = channel 0 left | right, q1 = channel 1 left | channel 2 left, q2 = channel 1 right | channel 2 right
+        const uint32_t q0 = __byte_perm(lo0, lo1, 0x7340), q1 = __byte_perm(lo0, lo1, 0x6251), q2 = __byte_perm(hi0, hi1, 0x5140);
+        const uint32_t wa = wya[pass], wb = wya[pass] << 16;
+        const uint32_t v0l = __dp4a(q0, wa, 0u), v0r = __dp4a(q0, wb, 0u);
+        const uint32_t v1l = __dp4a(q1, wa, 0u), v2l = __dp4a(q1, wb, 0u);
+        const uint32_t v1r = __dp4a(q2, wa, 0u), v2r = __dp4a(q2, wb, 0u);
+        const uint32_t o0 = (wl[pass] * v0l + (ax[pass] * v0r + 512u)) >> 10;
+        const uint32_t o1 = (wl[pass] * v1l + (ax[pass] * v1r + 512u)) >> 10;
+        const uint32_t o2 = (wl[pass] * v2l + (ax[pass] * v2r + 512u)) >> 10;
+        if ((fastm >> pass) & 1u) {
+          so[c * 3 + 0] = (uint8_t)o0;
+          so[c * 3 + 1] = (uint8_t)o1;
+          so[c * 3 + 2] = (uint8_t)o2;
+        }
+      }
     }
-#pragma unroll
-    for (int pass = 0; pass < NP; ++pass) {
-      const int c = pass * 8 + cc;
-      const uint32_t wxp = wxy[pass] & 0xFFFFu, wyp = wxy[pass] >> 16;
-      const uint32_t h0 = __dp4a(__byte_perm(t0l[pass], t0h[pass], 0x0030), wxp, __dp4a(__byte_perm(t1l[pass], t1h[pass], 0x0030), wxp, 0u) << 16);
-      const uint32_t h1 = __dp4a(__byte_perm(t0l[pass], t0h[pass], 0x0041), wxp, __dp4a(__byte_perm(t1l[pass], t1h[pass], 0x0041), wxp, 0u) << 16);
-      const uint32_t h2 = __dp4a(__byte_perm(t0l[pass], t0h[pass], 0x0052), wxp, __dp4a(__byte_perm(t1l[pass], t1h[pass], 0x0052), wxp, 0u) << 16);
-      uint32_t o0 = __dp2a_lo(h0, wyp, 512u) >> 10, o1 = __dp2a_lo(h1, wyp, 512u) >> 10, o2 = __dp2a_lo(h2, wyp, 512u) >> 10;
-      if ((dead >> pass) & 1u) { o0 = border3 & 0xFFu; o1 = (border3 >> 8) & 0xFFu; o2 = border3 >> 16; }
-      if ((slow >> pass) & 1u) {
-        uint32_t o[3];
-        remap_pixel<3>(s, nullptr, src_w, slut[wy * RP_ROWS + r][wx * RP_COLS + c], k.border, k.bg, o);
-        o0 = o[0]; o1 = o[1]; o2 = o[2];
-      }
-      if (((fast | dead | slow) >> pass) & 1u) {
-        so[c * 3 + 0] = (uint8_t)o0;
-        so[c * 3 + 1] = (uint8_t)o1;
-        so[c * 3 + 2] = (uint8_t)o2;
-      }
+    if (any_slow) {
+#pragma unroll 1
+      for (int pass = 0; pass < RB_NP; ++pass)
+        if ((slowm >> pass) & 1u) {
+          const int c = pass * 8 + cc;
+          uint32_t o[3];
+          remap_pixel<3>(s, nullptr, src_w, slut[wy * RP_ROWS + r][wx * RP_COLS + c], k.border, k.bg, o);
+          so[c * 3 + 0] = (uint8_t)o[0];
+          so[c * 3 + 1] = (uint8_t)o[1];
+          so[c * 3 + 2] = (uint8_t)o[2];
+        }
     }
     __syncwarp();
-    uint8_t* d0 = dst + ((((size_t)b * views + view) * rows + row0) * cols + col0) * 3;
-    if (nbytes == RP_COLS * 3 && ((((uintptr_t)d0) | drow) & 15) == 0) {
+    if (vec_out) {
       if (lane < 24 && r2 < nrows) ((uint4*)(d0 + r2 * drow))[ch] = ((const uint4*)sout[warp][r2])[ch];
     } else {
       for (int rr = 0; rr < nrows; ++rr)
@@ -473,15 +522,24 @@ extern "C" int sos_remap_u8(sos_ctx* ctx, const uint8_t* src, int batch, int src
   const bool aligned8 = ((uintptr_t)src & 7) == 0;
   const uint8_t* wide_end = aligned8 ? src + (size_t)batch * src_h * src_w * channels : nullptr;
   if (channels == 3) {
-    // SOS_REMAP_TMA=1 selects the batch-looped blocks with TMA-staged LUT tiles.  Measured equal-to-slightly-slower than
-    // the per-frame patch kernel at C2 (0.32 vs 0.30 ms): the kernel is bound by instruction issue, not by the LUT stream
-    // (DESIGN.md §5).  Both variants run the same parity tests (tests/test_gpu_remap.py is parametrised over the switch).
+    // Default: batch-looped blocks with TMA-staged LUT tiles (remap3b_kernel).  It needs tap addresses whose alignment is
+    // the same in every frame and row (8-byte aligned source, src_w % 8 == 0) and 32-bit offsets inside a frame; anything
+    // else, or SOS_REMAP_TMA=0, takes the per-frame patch kernel.  tests/test_gpu_remap.py runs every case on both.
     const char* e = getenv("SOS_REMAP_TMA");
-    const bool tma_kernel = e != nullptr && e[0] != '0' && (size_t)src_h * src_w * 3 < (1ull << 32);
+    const bool want_tma = e == nullptr || e[0] != '0';
+    const bool tma_kernel = want_tma && aligned8 && (src_w % 8) == 0 && (size_t)src_h * src_w * 3 < (1ull << 32);
     if (tma_kernel) {
-      dim3 gb(sos_div_up(cols, RB_TILE_COLS), sos_div_up(rows, RB_TILE_ROWS), views);
-      remap3b_kernel<<<gb, RP_WARPS_X * RP_WARPS_Y * 32, 0, ctx->stream>>>(src, aligned8 ? 1 : 0, batch, src_h, src_w, lut, views,
-                                                                           rows, cols, k, dst);
+      const int tiles = sos_div_up(cols, RB_TILE_COLS) * sos_div_up(rows, RB_TILE_ROWS) * views;
+      // enough blocks for ~5 waves of 3 blocks per SM; every block decodes its LUT tile once for its share of the batch
+      const int want_blocks = ctx->sm_count * 3 * 5;
+      int splits = (want_blocks + tiles - 1) / tiles;
+      splits = splits < 1 ? 1 : (splits > batch ? batch : splits);
+      const int fpb = sos_div_up(batch, splits);
+      splits = sos_div_up(batch, fpb);
+      SOS_CHECK_ARG((long long)views * splits <= 65535, "views * batch splits exceeds 65535");
+      dim3 gb(sos_div_up(cols, RB_TILE_COLS), sos_div_up(rows, RB_TILE_ROWS), views * splits);
+      remap3b_kernel<<<gb, RP_WARPS_X * RP_WARPS_Y * 32, 0, ctx->stream>>>(src, batch, fpb, src_h, src_w, lut, views, rows, cols, k,
+                                                                           dst);
       SOS_LAUNCHED_AS(ctx, "remap3b_kernel");
     } else {
       dim3 gp(sos_div_up(cols, RP_COLS * RP_WARPS_X), sos_div_up(rows, RP_ROWS * RP_WARPS_Y), batch * views);
