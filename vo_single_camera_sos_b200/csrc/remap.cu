@@ -309,7 +309,7 @@ remap3p_kernel(const uint8_t* __restrict__ src, int wide_ok, int src_h, int src_
 // Vertical interpolation first: one PRMT gathers (row 0, row 1) bytes of the left and right tap of a channel, dp4a with the
 // weights (32 - ay, ay, 0, 0) / (0, 0, 32 - ay, ay) gives vL and vR, then (wl * vL + ax * vR + 512) >> 10 — the same integer
 // as cv::remap's (sum_i w_i p_i + 16384) >> 15 because the Q15 weights are 32 * (6-bit x 6-bit products).
-// Requires an 8-byte aligned source whose rows are a multiple of 8 bytes (src_w % 8 == 0), so that the alignment of a tap
+// Requires a 4-byte aligned source whose rows are a multiple of 4 bytes (src_w % 4 == 0), so that the alignment of a tap
 // address is the same for every frame and both rows; other shapes take remap3p_kernel.
 constexpr int RB_TILE_ROWS = RP_ROWS * RP_WARPS_Y;   // 8
 constexpr int RB_TILE_COLS = RP_COLS * RP_WARPS_X;   // 128
@@ -371,7 +371,6 @@ remap3b_kernel(const uint8_t* __restrict__ src, int batch, int frames_per_block,
   //   fast: all four taps usable, wide loads stay inside the image    dead: no tap inside the image -> border colour
   //   slow: everything else (image edge, mirror-mask edge)            -> generic per-tap path, per frame
   uint32_t off[RB_NP], sh[RB_NP], wl[RB_NP], ax[RB_NP], wya[RB_NP];
-  bool hiw[RB_NP];
   uint32_t fastm = 0, deadm = 0, slowm = 0;
 #pragma unroll
   for (int pass = 0; pass < RB_NP; ++pass) {
@@ -386,9 +385,8 @@ remap3b_kernel(const uint8_t* __restrict__ src, int batch, int frames_per_block,
     slowm |= ((live && !w && !dd) ? 1u : 0u) << pass;
     // fast entries have 0 <= x0, y0 (all taps inside the image): plain unsigned arithmetic
     const uint32_t o = w ? ((lo >> 16) * (uint32_t)src_w + (lo & 0xFFFFu)) * 3u : 0u;   // other lanes read (and discard) the first bytes of the frame
-    off[pass] = o & ~7u;
+    off[pass] = o & ~3u;
     sh[pass] = (o & 3u) * 8u;
-    hiw[pass] = (o & 4u) != 0u;
     ax[pass] = hi & 31u;
     wl[pass] = 32u - ax[pass];
     const uint32_t ay = (hi >> 5) & 31u;
@@ -416,25 +414,26 @@ remap3b_kernel(const uint8_t* __restrict__ src, int batch, int frames_per_block,
   const bool vec_out = nbytes == RP_COLS * 3 && ((((uintptr_t)d0) | drow | dframe) & 15) == 0;
   for (int b = b_begin; b < b_end; ++b, s += img_bytes, d0 += dframe) {
     if (any_fast) {
-      // all tap loads of the frame first (unconditional: 16 independent 64-bit loads per lane in flight), then arithmetic
-      uint2 t0a[RB_NP], t0b[RB_NP], t1a[RB_NP], t1b[RB_NP];
+      // all tap loads of the frame first (unconditional: 24 independent loads per lane), then arithmetic.  The six bytes of a
+      // tap pair sit in the 12-byte window at the 4-byte aligned address below them: three 32-bit loads per row.  (Two 64-bit
+      // loads + selects were measured slower, 0.460 vs 0.403 ms: the kernel is bound by the L1 data pipe, which spends one
+      // wavefront per distinct 128-byte line of a request and two for 64-bit accesses — ncu l1tex__data_pipe_lsu_wavefronts 83 %.)
+      uint32_t ta[RB_NP][2][3];
 #pragma unroll
       for (int pass = 0; pass < RB_NP; ++pass) {
-        const uint2* p0 = (const uint2*)(s + off[pass]);
-        const uint2* p1 = (const uint2*)(s + off[pass] + row_bytes);
-        t0a[pass] = __ldg(p0);
-        t0b[pass] = __ldg(p0 + 1);
-        t1a[pass] = __ldg(p1);
-        t1b[pass] = __ldg(p1 + 1);
+#pragma unroll
+        for (int row = 0; row < 2; ++row) {
+          const uint32_t* p = (const uint32_t*)(s + off[pass] + (row ? row_bytes : 0u));
+          ta[pass][row][0] = __ldg(p);
+          ta[pass][row][1] = __ldg(p + 1);
+          ta[pass][row][2] = __ldg(p + 2);
+        }
       }
 #pragma unroll
       for (int pass = 0; pass < RB_NP; ++pass) {
         const int c = pass * 8 + cc;
-        const bool h = hiw[pass];
-        const uint32_t A0 = h ? t0a[pass].y : t0a[pass].x, B0 = h ? t0b[pass].x : t0a[pass].y, C0 = h ? t0b[pass].y : t0b[pass].x;
-        const uint32_t A1 = h ? t1a[pass].y : t1a[pass].x, B1 = h ? t1b[pass].x : t1a[pass].y, C1 = h ? t1b[pass].y : t1b[pass].x;
-        const uint32_t lo0 = __funnelshift_r(A0, B0, sh[pass]), hi0 = __funnelshift_r(B0, C0, sh[pass]);
-        const uint32_t lo1 = __funnelshift_r(A1, B1, sh[pass]), hi1 = __funnelshift_r(B1, C1, sh[pass]);
+        const uint32_t lo0 = __funnelshift_r(ta[pass][0][0], ta[pass][0][1], sh[pass]), hi0 = __funnelshift_r(ta[pass][0][1], ta[pass][0][2], sh[pass]);
+        const uint32_t lo1 = __funnelshift_r(ta[pass][1][0], ta[pass][1][1], sh[pass]), hi1 = __funnelshift_r(ta[pass][1][1], ta[pass][1][2], sh[pass]);
         // (row 0, row 1) byte pairs: q0 = channel 0 left | right, q1 = channel 1 left | channel 2 left, q2 = channel 1 right | channel 2 right
         const uint32_t q0 = __byte_perm(lo0, lo1, 0x7340), q1 = __byte_perm(lo0, lo1, 0x6251), q2 = __byte_perm(hi0, hi1, 0x5140);
         const uint32_t wa = wya[pass], wb = wya[pass] << 16;
@@ -523,11 +522,11 @@ extern "C" int sos_remap_u8(sos_ctx* ctx, const uint8_t* src, int batch, int src
   const uint8_t* wide_end = aligned8 ? src + (size_t)batch * src_h * src_w * channels : nullptr;
   if (channels == 3) {
     // Default: batch-looped blocks with TMA-staged LUT tiles (remap3b_kernel).  It needs tap addresses whose alignment is
-    // the same in every frame and row (8-byte aligned source, src_w % 8 == 0) and 32-bit offsets inside a frame; anything
+    // the same in every frame and row (4-byte aligned source, src_w % 4 == 0) and 32-bit offsets inside a frame; anything
     // else, or SOS_REMAP_TMA=0, takes the per-frame patch kernel.  tests/test_gpu_remap.py runs every case on both.
     const char* e = getenv("SOS_REMAP_TMA");
     const bool want_tma = e == nullptr || e[0] != '0';
-    const bool tma_kernel = want_tma && aligned8 && (src_w % 8) == 0 && (size_t)src_h * src_w * 3 < (1ull << 32);
+    const bool tma_kernel = want_tma && ((uintptr_t)src & 3) == 0 && (src_w % 4) == 0 && (size_t)src_h * src_w * 3 < (1ull << 32);
     if (tma_kernel) {
       const int tiles = sos_div_up(cols, RB_TILE_COLS) * sos_div_up(rows, RB_TILE_ROWS) * views;
       // enough blocks for ~5 waves of 3 blocks per SM; every block decodes its LUT tile once for its share of the batch
@@ -538,8 +537,7 @@ extern "C" int sos_remap_u8(sos_ctx* ctx, const uint8_t* src, int batch, int src
       splits = sos_div_up(batch, fpb);
       SOS_CHECK_ARG((long long)views * splits <= 65535, "views * batch splits exceeds 65535");
       dim3 gb(sos_div_up(cols, RB_TILE_COLS), sos_div_up(rows, RB_TILE_ROWS), views * splits);
-      remap3b_kernel<<<gb, RP_WARPS_X * RP_WARPS_Y * 32, 0, ctx->stream>>>(src, batch, fpb, src_h, src_w, lut, views, rows, cols, k,
-                                                                           dst);
+      remap3b_kernel<<<gb, RP_WARPS_X * RP_WARPS_Y * 32, 0, ctx->stream>>>(src, batch, fpb, src_h, src_w, lut, views, rows, cols, k, dst);
       SOS_LAUNCHED_AS(ctx, "remap3b_kernel");
     } else {
       dim3 gp(sos_div_up(cols, RP_COLS * RP_WARPS_X), sos_div_up(rows, RP_ROWS * RP_WARPS_Y), batch * views);
