@@ -11,6 +11,18 @@ from oracle import ransac
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["tensor", "fma"])
+def score_engine(request, monkeypatch):
+    """Every test of this file runs with both engines of the bearing score: the bfloat16-split GEMMs on the tensor cores
+    (csrc/score_mma.cuh, default) and the FP32-pipe kernel (SOS_SCORE_ENGINE=fma; the library reads the switch per call).
+    The Euclidean score only has the FP32-pipe kernel."""
+    if request.param == "fma":
+        monkeypatch.setenv("SOS_SCORE_ENGINE", "fma")
+    else:
+        monkeypatch.delenv("SOS_SCORE_ENGINE", raising=False)
+    return request.param
+
+
 def dev(a, dtype=None):
     t = torch.from_numpy(np.ascontiguousarray(a))
     if dtype is not None:

@@ -19,7 +19,10 @@
 #include <math_constants.h>
 #include <stddef.h>
 
+#include <cuda_bf16.h>
+
 #include "sos_common.cuh"
+#include "tc_common.cuh"
 
 namespace {
 
@@ -157,7 +160,89 @@ struct HypRec {
   float xf[RS_MAX_CAMS][12];      // per camera: A (9, row-major) then b (3):  x = A p_ref + b
 };
 
-__device__ void make_scoring_transforms(const double* M, const Rig& rig, HypRec& rec) {
+// ------------------------------------------------------------------------------------------------------------
+// The inlier test.
+//
+// Fast path: float32 FMAs on the per-hypothesis transform.  It also produces a rigorous bound `guard` on its own
+// rounding error; when the decision variable D lies inside the guard band the pair is re-evaluated by
+// inlier_exact() in float64 with the reference's own formula.  The decision therefore equals the float64 decision
+// (up to ~1e-15 relative), which is what makes inlier SETS bit-exact against the NumPy oracle, while >99.9 % of the
+// pairs never leave the FP32 pipe.
+//
+// Error model (p, q are exact float32 inputs, A and b are float32 roundings of float64 values, u = 2^-24):
+//   each component of x = A p + b:   |err| <= E = 4u (|p|_1 + |b|_inf),  and  |b|_inf <= |x|_2 + |p|_2
+//   EUCLID : D = |x - q|^2 - thr^2;  within the band |x|_2 <= |q|_2 + 2 thr, |x - q|_1 <= 2 sqrt(3) thr, hence
+//            |err D| <= u (28 thr (2|p|_1 + |q|_1 + 2 thr) + 18 thr^2) =: guard_j   (per correspondence, staged in .w)
+//   BEARING: D = s^2 - c^2 |x|^2, s = f.x, c = 1 - thr;  |err D| <= u (80 |x|^2 + 32 |p|_1^2) = k |x|^2 + guard_j
+// ------------------------------------------------------------------------------------------------------------
+struct ScoreConst {
+  float thr_sq;       // EUCLID: thr^2
+  float cos_min_sq;   // BEARING: (1 - thr)^2
+  float guard_rel;    // BEARING: 80 u
+  double thr;         // the threshold itself, for the exact path
+};
+
+__device__ __noinline__ bool inlier_exact(int mode, const double* __restrict__ M, const Rig& rig, int cam, float4 p,
+                                          float4 q, double thr) {
+  const double px = p.x, py = p.y, pz = p.z;
+  if (mode == SOS_SCORE_EUCLID) {
+    // |p_ref - (R p_cur + t)| < thr
+    const double cx = q.x, cy = q.y, cz = q.z;
+    const double dx = px - (M[0] * cx + M[1] * cy + M[2] * cz + M[3]);
+    const double dy = py - (M[4] * cx + M[5] * cy + M[6] * cz + M[7]);
+    const double dz = pz - (M[8] * cx + M[9] * cy + M[10] * cz + M[11]);
+    return sqrt(dx * dx + dy * dy + dz * dz) < thr;
+  }
+  // 1 - f . normalize(Rc^T (R^T (p - t) - tc)) < thr   (pose_est_tools.py:150-203, 181-185)
+  const double ex = px - M[3], ey = py - M[7], ez = pz - M[11];
+  double bx = M[0] * ex + M[4] * ey + M[8] * ez;
+  double by = M[1] * ex + M[5] * ey + M[9] * ez;
+  double bz = M[2] * ex + M[6] * ey + M[10] * ez;
+  const double* C = rig.Rt[cam];
+  bx -= C[3]; by -= C[7]; bz -= C[11];
+  const double x = C[0] * bx + C[4] * by + C[8] * bz;
+  const double y = C[1] * bx + C[5] * by + C[9] * bz;
+  const double z = C[2] * bx + C[6] * by + C[10] * bz;
+  const double nrm = sqrt(x * x + y * y + z * z);
+  return 1.0 - ((double)q.x * (x / nrm) + (double)q.y * (y / nrm) + (double)q.z * (z / nrm)) < thr;
+}
+
+// Returns the fast decision in `in` and whether it is uncertain.
+// Decision variable D (inlier <=> D > 0) and the bound g of its float32 rounding error (uncertain <=> |D| < g).
+template <int MODE>
+__device__ __forceinline__ void decision(const float* __restrict__ A, const float4& p, const float4& q, float guard_j,
+                                         const ScoreConst& k, float& D, float& g) {
+  const float x = __fmaf_rn(A[2], p.z, __fmaf_rn(A[1], p.y, __fmaf_rn(A[0], p.x, A[9])));
+  const float y = __fmaf_rn(A[5], p.z, __fmaf_rn(A[4], p.y, __fmaf_rn(A[3], p.x, A[10])));
+  const float z = __fmaf_rn(A[8], p.z, __fmaf_rn(A[7], p.y, __fmaf_rn(A[6], p.x, A[11])));
+  if (MODE == SOS_SCORE_EUCLID) {
+    const float dx = __fsub_rn(x, q.x), dy = __fsub_rn(y, q.y), dz = __fsub_rn(z, q.z);
+    const float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    D = __fsub_rn(k.thr_sq, r2);
+    g = guard_j;
+  } else {
+    const float s = __fmaf_rn(q.z, z, __fmaf_rn(q.y, y, __fmul_rn(q.x, x)));
+    const float n2 = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
+    D = __fmaf_rn(s, fabsf(s), -__fmul_rn(k.cos_min_sq, n2));  // s|s| folds the s > 0 test into D
+    g = __fmaf_rn(k.guard_rel, n2, guard_j);
+  }
+}
+
+__device__ __forceinline__ float guard_of(int mode, float px, float py, float pz, float qx, float qy, float qz, double thr) {
+  const double u = 5.9604644775390625e-08;  // 2^-24
+  const double p1 = fabs((double)px) + fabs((double)py) + fabs((double)pz);
+  if (mode == SOS_SCORE_EUCLID) {
+    const double q1 = fabs((double)qx) + fabs((double)qy) + fabs((double)qz);
+    return (float)(u * (28.0 * thr * (2.0 * p1 + q1 + 2.0 * thr) + 18.0 * thr * thr) * 1.0001);
+  }
+  return (float)(u * 32.0 * p1 * p1 * 1.0001);
+}
+
+#include "score_mma.cuh"
+
+// `tc_tile` (may be NULL): the two per-camera hypothesis tiles of the tensor-core score engine this hypothesis belongs to
+// (score_mma.cuh); row `tc_row` of each gets the float64-derived features of that camera's transform.
+__device__ void make_scoring_transforms(const double* M, const Rig& rig, HypRec& rec, uint8_t* tc_tile, int tc_row) {
 #pragma unroll
   for (int i = 0; i < 12; ++i) {
     rec.pose64[i] = M[i];
@@ -178,25 +263,45 @@ __device__ void make_scoring_transforms(const double* M, const Rig& rig, HypRec&
       continue;
     }
     const double* C = rig.Rt[c];  // x = Rc^T (y - tc)
+    double Ad[9], bd[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
 #pragma unroll
-      for (int j = 0; j < 3; ++j)
-        rec.xf[c][i * 3 + j] = (float)(C[0 * 4 + i] * Rt_[0 * 3 + j] + C[1 * 4 + i] * Rt_[1 * 3 + j] + C[2 * 4 + i] * Rt_[2 * 3 + j]);
-      rec.xf[c][9 + i] = (float)(C[0 * 4 + i] * (bt[0] - C[3]) + C[1 * 4 + i] * (bt[1] - C[7]) + C[2 * 4 + i] * (bt[2] - C[11]));
+      for (int j = 0; j < 3; ++j) Ad[i * 3 + j] = C[0 * 4 + i] * Rt_[0 * 3 + j] + C[1 * 4 + i] * Rt_[1 * 3 + j] + C[2 * 4 + i] * Rt_[2 * 3 + j];
+      bd[i] = C[0 * 4 + i] * (bt[0] - C[3]) + C[1 * 4 + i] * (bt[1] - C[7]) + C[2 * 4 + i] * (bt[2] - C[11]);
     }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) rec.xf[c][i] = (float)Ad[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) rec.xf[c][9 + i] = (float)bd[i];
+    if (tc_tile) score_tc::emit_hyp_row(tc_tile + (size_t)c * score_tc::TILE_BYTES, tc_row, Ad, bd, true);
+  }
+}
+
+// a failed model: NaN never passes the inlier test
+__device__ void make_failed_model(const Rig& rig, HypRec& rec, uint8_t* tc_tile, int tc_row) {
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    rec.pose[i] = CUDART_NAN_F;
+    rec.pose64[i] = CUDART_NAN;
+  }
+  for (int c = 0; c < RS_MAX_CAMS; ++c) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) rec.xf[c][i] = CUDART_NAN_F;
+    if (tc_tile && c < rig.n_cams) score_tc::emit_hyp_row(tc_tile + (size_t)c * score_tc::TILE_BYTES, tc_row, nullptr, nullptr, false);
   }
 }
 
 __global__ void __launch_bounds__(128)
 hypothesize_kernel(const float* __restrict__ p_ref, const float* __restrict__ p_cur, const int32_t* __restrict__ n_arr,
                    int cap, const uint32_t* __restrict__ hyp, int hyp_stride_problem, int n_hyp, Rig rig,
-                   HypRec* __restrict__ recs, int32_t* __restrict__ counts) {
+                   HypRec* __restrict__ recs, int32_t* __restrict__ counts, uint8_t* __restrict__ tc_a) {
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (h >= n_hyp) return;
   const int n = n_arr[b];
   const uint32_t* hr = hyp + (size_t)b * hyp_stride_problem + (size_t)h * 3;
+  uint8_t* tc_tile = tc_a ? tc_a + ((size_t)b * gridDim.x + blockIdx.x) * 2 * score_tc::TILE_BYTES : nullptr;  // 128 threads = one tile
   bool ok = n >= 3;
   int rows[3] = {0, 0, 0};
   if (ok) {
@@ -219,18 +324,8 @@ hypothesize_kernel(const float* __restrict__ p_ref, const float* __restrict__ p_
   }
   if (ok) ok = arun_fit(v0, v1, 3, M);
   HypRec rec;
-  if (ok) {
-    make_scoring_transforms(M, rig, rec);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 12; ++i) {
-      rec.pose[i] = CUDART_NAN_F;
-      rec.pose64[i] = CUDART_NAN;
-    }
-    for (int c = 0; c < RS_MAX_CAMS; ++c)
-#pragma unroll
-      for (int i = 0; i < 12; ++i) rec.xf[c][i] = CUDART_NAN_F;  // NaN never passes the inlier test
-  }
+  if (ok) make_scoring_transforms(M, rig, rec, tc_tile, (int)threadIdx.x);
+  else make_failed_model(rig, rec, tc_tile, (int)threadIdx.x);
   recs[(size_t)b * n_hyp + h] = rec;
   counts[(size_t)b * n_hyp + h] = ok ? 0 : -(1 << 30);  // failed model: stays negative whatever is added
 }
@@ -350,12 +445,13 @@ __device__ __forceinline__ void triangle_frame(const double* T, double* F) {
 __global__ void __launch_bounds__(128)
 hypothesize_p3p_kernel(const float* __restrict__ p_ref, const float* __restrict__ f_cur, const uint8_t* __restrict__ cam,
                        const int32_t* __restrict__ n_arr, int cap, const uint32_t* __restrict__ hyp, int hyp_stride_problem,
-                       int n_hyp, Rig rig, HypRec* __restrict__ recs, int32_t* __restrict__ counts) {
+                       int n_hyp, Rig rig, HypRec* __restrict__ recs, int32_t* __restrict__ counts, uint8_t* __restrict__ tc_a) {
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (h >= n_hyp) return;
   const int n = n_arr[b];
   const uint32_t* hr = hyp + (size_t)b * hyp_stride_problem + (size_t)h * 4;
+  uint8_t* tc_tile = tc_a ? tc_a + ((size_t)b * gridDim.x + blockIdx.x) * 2 * score_tc::TILE_BYTES : nullptr;
   bool ok = n >= 4;
   int rows[4] = {0, 0, 0, 0};
   if (ok) {
@@ -517,98 +613,10 @@ hypothesize_p3p_kernel(const float* __restrict__ p_ref, const float* __restrict_
     ok = best_res < CUDART_INF;
   }
   HypRec rec;
-  if (ok) {
-    make_scoring_transforms(best_M, rig, rec);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 12; ++i) {
-      rec.pose[i] = CUDART_NAN_F;
-      rec.pose64[i] = CUDART_NAN;
-    }
-    for (int c = 0; c < RS_MAX_CAMS; ++c)
-#pragma unroll
-      for (int i = 0; i < 12; ++i) rec.xf[c][i] = CUDART_NAN_F;
-  }
+  if (ok) make_scoring_transforms(best_M, rig, rec, tc_tile, (int)threadIdx.x);
+  else make_failed_model(rig, rec, tc_tile, (int)threadIdx.x);
   recs[(size_t)b * n_hyp + h] = rec;
   counts[(size_t)b * n_hyp + h] = ok ? 0 : -(1 << 30);
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// The inlier test.
-//
-// Fast path: float32 FMAs on the per-hypothesis transform.  It also produces a rigorous bound `guard` on its own
-// rounding error; when the decision variable D lies inside the guard band the pair is re-evaluated by
-// inlier_exact() in float64 with the reference's own formula.  The decision therefore equals the float64 decision
-// (up to ~1e-15 relative), which is what makes inlier SETS bit-exact against the NumPy oracle, while >99.9 % of the
-// pairs never leave the FP32 pipe.
-//
-// Error model (p, q are exact float32 inputs, A and b are float32 roundings of float64 values, u = 2^-24):
-//   each component of x = A p + b:   |err| <= E = 4u (|p|_1 + |b|_inf),  and  |b|_inf <= |x|_2 + |p|_2
-//   EUCLID : D = |x - q|^2 - thr^2;  within the band |x|_2 <= |q|_2 + 2 thr, |x - q|_1 <= 2 sqrt(3) thr, hence
-//            |err D| <= u (28 thr (2|p|_1 + |q|_1 + 2 thr) + 18 thr^2) =: guard_j   (per correspondence, staged in .w)
-//   BEARING: D = s^2 - c^2 |x|^2, s = f.x, c = 1 - thr;  |err D| <= u (80 |x|^2 + 32 |p|_1^2) = k |x|^2 + guard_j
-// ------------------------------------------------------------------------------------------------------------
-struct ScoreConst {
-  float thr_sq;       // EUCLID: thr^2
-  float cos_min_sq;   // BEARING: (1 - thr)^2
-  float guard_rel;    // BEARING: 80 u
-  double thr;         // the threshold itself, for the exact path
-};
-
-__device__ __noinline__ bool inlier_exact(int mode, const double* __restrict__ M, const Rig& rig, int cam, float4 p,
-                                          float4 q, double thr) {
-  const double px = p.x, py = p.y, pz = p.z;
-  if (mode == SOS_SCORE_EUCLID) {
-    // |p_ref - (R p_cur + t)| < thr
-    const double cx = q.x, cy = q.y, cz = q.z;
-    const double dx = px - (M[0] * cx + M[1] * cy + M[2] * cz + M[3]);
-    const double dy = py - (M[4] * cx + M[5] * cy + M[6] * cz + M[7]);
-    const double dz = pz - (M[8] * cx + M[9] * cy + M[10] * cz + M[11]);
-    return sqrt(dx * dx + dy * dy + dz * dz) < thr;
-  }
-  // 1 - f . normalize(Rc^T (R^T (p - t) - tc)) < thr   (pose_est_tools.py:150-203, 181-185)
-  const double ex = px - M[3], ey = py - M[7], ez = pz - M[11];
-  double bx = M[0] * ex + M[4] * ey + M[8] * ez;
-  double by = M[1] * ex + M[5] * ey + M[9] * ez;
-  double bz = M[2] * ex + M[6] * ey + M[10] * ez;
-  const double* C = rig.Rt[cam];
-  bx -= C[3]; by -= C[7]; bz -= C[11];
-  const double x = C[0] * bx + C[4] * by + C[8] * bz;
-  const double y = C[1] * bx + C[5] * by + C[9] * bz;
-  const double z = C[2] * bx + C[6] * by + C[10] * bz;
-  const double nrm = sqrt(x * x + y * y + z * z);
-  return 1.0 - ((double)q.x * (x / nrm) + (double)q.y * (y / nrm) + (double)q.z * (z / nrm)) < thr;
-}
-
-// Returns the fast decision in `in` and whether it is uncertain.
-// Decision variable D (inlier <=> D > 0) and the bound g of its float32 rounding error (uncertain <=> |D| < g).
-template <int MODE>
-__device__ __forceinline__ void decision(const float* __restrict__ A, const float4& p, const float4& q, float guard_j,
-                                         const ScoreConst& k, float& D, float& g) {
-  const float x = __fmaf_rn(A[2], p.z, __fmaf_rn(A[1], p.y, __fmaf_rn(A[0], p.x, A[9])));
-  const float y = __fmaf_rn(A[5], p.z, __fmaf_rn(A[4], p.y, __fmaf_rn(A[3], p.x, A[10])));
-  const float z = __fmaf_rn(A[8], p.z, __fmaf_rn(A[7], p.y, __fmaf_rn(A[6], p.x, A[11])));
-  if (MODE == SOS_SCORE_EUCLID) {
-    const float dx = __fsub_rn(x, q.x), dy = __fsub_rn(y, q.y), dz = __fsub_rn(z, q.z);
-    const float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-    D = __fsub_rn(k.thr_sq, r2);
-    g = guard_j;
-  } else {
-    const float s = __fmaf_rn(q.z, z, __fmaf_rn(q.y, y, __fmul_rn(q.x, x)));
-    const float n2 = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
-    D = __fmaf_rn(s, fabsf(s), -__fmul_rn(k.cos_min_sq, n2));  // s|s| folds the s > 0 test into D
-    g = __fmaf_rn(k.guard_rel, n2, guard_j);
-  }
-}
-
-__device__ __forceinline__ float guard_of(int mode, float px, float py, float pz, float qx, float qy, float qz, double thr) {
-  const double u = 5.9604644775390625e-08;  // 2^-24
-  const double p1 = fabs((double)px) + fabs((double)py) + fabs((double)pz);
-  if (mode == SOS_SCORE_EUCLID) {
-    const double q1 = fabs((double)qx) + fabs((double)qy) + fabs((double)qz);
-    return (float)(u * (28.0 * thr * (2.0 * p1 + q1 + 2.0 * thr) + 18.0 * thr * thr) * 1.0001);
-  }
-  return (float)(u * 32.0 * p1 * p1 * 1.0001);
 }
 
 constexpr int RS_THREADS = 128;
@@ -1026,18 +1034,65 @@ struct RansacScratch {
   HypRec* recs;
   int32_t* counts;
   HypRec* best_rec;
+  uint8_t *tc_a, *tc_b;          // tensor-core score engine: hypothesis tiles, correspondence tiles (score_mma.cuh)
+  score_tc::TileMeta* tc_meta;
 };
 
-int ransac_scratch(sos_ctx* ctx, int n_problems, int n_hyp, RansacScratch& s) {
+int ransac_scratch(sos_ctx* ctx, int n_problems, int n_hyp, int tc_cap, RansacScratch& s) {
   const size_t rec_bytes = sos_align_up((size_t)n_problems * n_hyp * sizeof(HypRec), 256);
   const size_t cnt_bytes = sos_align_up((size_t)n_problems * n_hyp * sizeof(int32_t), 256);
   const size_t best_bytes = sos_align_up((size_t)n_problems * sizeof(HypRec), 256);
+  const size_t ht = (size_t)sos_div_up(n_hyp, score_tc::TILE), ct = (size_t)sos_div_up(tc_cap > 0 ? tc_cap : 1, score_tc::TILE);
+  const size_t a_bytes = tc_cap > 0 ? (size_t)n_problems * ht * 2 * score_tc::TILE_BYTES : 0;
+  const size_t b_bytes = tc_cap > 0 ? (size_t)n_problems * ct * 2 * score_tc::TILE_BYTES : 0;
+  const size_t m_bytes = tc_cap > 0 ? sos_align_up((size_t)n_problems * ct * sizeof(score_tc::TileMeta), 256) : 0;
   void* base = nullptr;
-  const int rc = sos_arena_get(ctx, rec_bytes + cnt_bytes + best_bytes, &base);
+  const int rc = sos_arena_get(ctx, rec_bytes + cnt_bytes + best_bytes + a_bytes + b_bytes + m_bytes + 1024, &base);
   if (rc != SOS_OK) return rc;
-  s.recs = (HypRec*)base;
-  s.counts = (int32_t*)((char*)base + rec_bytes);
-  s.best_rec = (HypRec*)((char*)base + rec_bytes + cnt_bytes);
+  char* p = (char*)base;
+  s.recs = (HypRec*)p; p += rec_bytes;
+  s.counts = (int32_t*)p; p += cnt_bytes;
+  s.best_rec = (HypRec*)p; p += best_bytes;
+  p = (char*)sos_align_up((size_t)(uintptr_t)p, 1024);
+  s.tc_a = tc_cap > 0 ? (uint8_t*)p : nullptr; p += a_bytes;
+  s.tc_b = tc_cap > 0 ? (uint8_t*)p : nullptr; p += b_bytes;
+  s.tc_meta = tc_cap > 0 ? (score_tc::TileMeta*)p : nullptr;
+  return SOS_OK;
+}
+
+// The bearing score on the tensor cores (score_mma.cuh).  SOS_SCORE_ENGINE=fma keeps the FP32-pipe kernel (the only
+// engine of the Euclidean score); tests/test_gpu_ransac.py runs the bearing cases on both.
+bool use_tensor_score(int score_mode, int n_hyp, int cap) {
+  if (score_mode != SOS_SCORE_BEARING || n_hyp < 32 || cap < 1) return false;
+  const char* e = getenv("SOS_SCORE_ENGINE");
+  return !(e && e[0] == 'f');
+}
+
+int launch_score_tc(sos_ctx* ctx, const Rig& rig, const RansacScratch& s, const float* p_ref, const float* f_cur, const uint8_t* cam,
+                    const int32_t* n, int n_problems, int cap, int n_hyp, ScoreConst k, float* probe) {
+  using namespace score_tc;
+  const int ht = sos_div_up(n_hyp, TILE), ct = sos_div_up(cap, TILE);
+  corr_expand_kernel<<<dim3(ct, n_problems), TILE, 0, ctx->stream>>>(p_ref, f_cur, cam, n, cap, rig.n_cams, ct, s.tc_b, s.tc_meta);
+  SOS_LAUNCHED_AS(ctx, "score_expand_kernel");
+  Args a;
+  a.a_exp = s.tc_a; a.b_exp = s.tc_b; a.meta = s.tc_meta; a.n_arr = n;
+  a.cap = cap; a.n_hyp = n_hyp; a.ht = ht; a.ct = ct;
+  // enough work items for two CTAs' worth per SM; a few tiles per item at least
+  int splits = sos_div_up(2 * ctx->sm_count, n_problems * ht);
+  splits = splits < 1 ? 1 : (splits > sos_div_up(ct, 4) ? sos_div_up(ct, 4) : splits);
+  a.splits = splits;
+  a.recs = s.recs; a.counts = s.counts; a.p_ref = p_ref; a.f_cur = f_cur; a.cam = cam; a.k = k; a.probe = probe;
+  static bool attr_set[64][2] = {};     // per device: the opt-in to > 48 KB of dynamic shared memory
+  const int dev = ctx->device & 63, v = probe ? 1 : 0;
+  if (!attr_set[dev][v]) {
+    if (probe) SOS_CUDA(cudaFuncSetAttribute(score_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    else SOS_CUDA(cudaFuncSetAttribute(score_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set[dev][v] = true;
+  }
+  const unsigned grid = (unsigned)n_problems * ht * splits;
+  if (probe) score_mma_kernel<true><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(a, rig);
+  else score_mma_kernel<false><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(a, rig);
+  SOS_LAUNCHED_AS(ctx, "score_mma_kernel");
   return SOS_OK;
 }
 
@@ -1073,7 +1128,7 @@ int ransac_run(sos_ctx* ctx, int solver, const float* p_ref, const float* p_cur,
                               const uint8_t* cam, const int32_t* n, int n_problems, int cap, const double* rig,
                               int n_cams, const uint32_t* hyp, int n_hyp, int hyp_offset, int score_mode,
                               double threshold, float* best_pose, int32_t* best_hyp, int32_t* best_count,
-                              uint8_t* inlier_mask, uint64_t* best_key, int32_t* all_counts) {
+                              uint8_t* inlier_mask, uint64_t* best_key, int32_t* all_counts, float* tc_probe = nullptr) {
   SOS_CHECK_ARG(ctx, "ctx is NULL");
   SOS_CHECK_ARG(n_problems >= 0 && cap >= 0 && n_hyp >= 0, "negative size");
   SOS_CHECK_ARG(score_mode == SOS_SCORE_EUCLID || score_mode == SOS_SCORE_BEARING, "unknown score mode");
@@ -1090,16 +1145,20 @@ int ransac_run(sos_ctx* ctx, int solver, const float* p_ref, const float* p_cur,
   const ScoreConst k = make_const(score_mode, threshold);
   RansacScratch s;
   const int n_hyp_alloc = n_hyp > 0 ? n_hyp : 1;
-  int rc = ransac_scratch(ctx, n_problems, n_hyp_alloc, s);
+  const bool tc = tc_probe != nullptr || use_tensor_score(score_mode, n_hyp, cap);
+  int rc = ransac_scratch(ctx, n_problems, n_hyp_alloc, tc ? cap : 0, s);
   if (rc != SOS_OK) return rc;
   if (n_hyp > 0) {
     dim3 hgrid(sos_div_up(n_hyp, 128), n_problems);
     if (solver == 1)
-      hypothesize_p3p_kernel<<<hgrid, 128, 0, ctx->stream>>>(p_ref, f_cur, cam, n, cap, hyp, 0, n_hyp, r, s.recs, s.counts);
+      hypothesize_p3p_kernel<<<hgrid, 128, 0, ctx->stream>>>(p_ref, f_cur, cam, n, cap, hyp, 0, n_hyp, r, s.recs, s.counts, s.tc_a);
     else
-      hypothesize_kernel<<<hgrid, 128, 0, ctx->stream>>>(p_ref, p_cur, n, cap, hyp, 0, n_hyp, r, s.recs, s.counts);
+      hypothesize_kernel<<<hgrid, 128, 0, ctx->stream>>>(p_ref, p_cur, n, cap, hyp, 0, n_hyp, r, s.recs, s.counts, s.tc_a);
     SOS_LAUNCHED_AS(ctx, "hypothesize_kernel");
-    if (cap > 0) {
+    if (cap > 0 && tc) {
+      rc = launch_score_tc(ctx, r, s, p_ref, f_cur, cam, n, n_problems, cap, n_hyp, k, tc_probe);
+      if (rc != SOS_OK) return rc;
+    } else if (cap > 0) {
       dim3 sgrid(sos_div_up(n_hyp, RS_TILE_H), sos_div_up(cap, RS_CHUNK), n_problems);
       const float* q = score_mode == SOS_SCORE_EUCLID ? p_cur : f_cur;
       rc = score_mode == SOS_SCORE_EUCLID
@@ -1133,6 +1192,15 @@ extern "C" int sos_ransac_p3d(sos_ctx* ctx, const float* p_ref, const float* p_c
                     threshold, best_pose, best_hyp, best_count, inlier_mask, best_key, all_counts);
 }
 
+extern "C" int sos_ransac_score_probe(sos_ctx* ctx, const float* p_ref, const float* p_cur, const float* f_cur,
+                                      const uint8_t* cam, const int32_t* n, int n_problems, int cap, const double* rig,
+                                      int n_cams, const uint32_t* hyp, int n_hyp, double threshold, float* best_pose,
+                                      int32_t* best_hyp, int32_t* best_count, int32_t* all_counts, float* sn) {
+  SOS_CHECK_ARG(sn, "sn is NULL");
+  return ransac_run(ctx, 0, p_ref, p_cur, f_cur, cam, n, n_problems, cap, rig, n_cams, hyp, n_hyp, 0, SOS_SCORE_BEARING,
+                    threshold, best_pose, best_hyp, best_count, nullptr, nullptr, all_counts, sn);
+}
+
 extern "C" int sos_ransac_p3p(sos_ctx* ctx, const float* p_ref, const float* f_cur, const uint8_t* cam, const int32_t* n,
                               int n_problems, int cap, const double* rig, int n_cams, const uint32_t* hyp, int n_hyp,
                               int hyp_offset, double threshold, float* best_pose, int32_t* best_hyp, int32_t* best_count,
@@ -1159,11 +1227,11 @@ extern "C" int sos_ransac_p3d_eval(sos_ctx* ctx, const float* p_ref, const float
   fill_rig(score_mode == SOS_SCORE_BEARING ? rig : nullptr, score_mode == SOS_SCORE_BEARING ? n_cams : 1, r);
   const ScoreConst k = make_const(score_mode, threshold);
   RansacScratch s;
-  int rc = ransac_scratch(ctx, n_problems, 1, s);
+  int rc = ransac_scratch(ctx, n_problems, 1, 0, s);
   if (rc != SOS_OK) return rc;
   dim3 hgrid(1, n_problems);
   // one hypothesis per problem, each with its own row of sample numbers (stride 3 per problem)
-  hypothesize_kernel<<<hgrid, 128, 0, ctx->stream>>>(p_ref, p_cur, n, cap, hyp_row, 3, 1, r, s.recs, s.counts);
+  hypothesize_kernel<<<hgrid, 128, 0, ctx->stream>>>(p_ref, p_cur, n, cap, hyp_row, 3, 1, r, s.recs, s.counts, nullptr);
   SOS_LAUNCHED_AS(ctx, "hypothesize_kernel");
   // counts[b] is 0 for a valid model and hugely negative otherwise: the mask kernel adds the inliers on top
   SOS_CUDA(cudaMemcpyAsync(count, s.counts, (size_t)n_problems * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));

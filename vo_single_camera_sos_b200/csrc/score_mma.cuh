@@ -1,0 +1,401 @@
+// Tensor-core engine of the bearing-angle RANSAC score (step 5 of the SOS front-end).  Included by ransac.cu inside its
+// anonymous namespace, after HypRec / Rig / ScoreConst / decision / guard_of / inlier_exact.
+//
+// The score of (hypothesis h, correspondence j) is  1 - f_j . x / |x| < thr  with  x = A_h p_j + b_h  (per camera; reference
+// omnistereo/pose_est_tools.py:150-203 with the non-central correction of its comment at :181-185).  Both quantities the
+// decision needs are BILINEAR in (hypothesis, correspondence) features:
+//     s  = f . x  = sum_ik A_ik (f_i p_k) + sum_i b_i f_i                                        12 terms
+//     n2 = |x|^2  = sum_kl (A^T A)_kl p_k p_l + 2 sum_k (A^T b)_k p_k + |b|^2                     10 terms
+// i.e. two small-K GEMMs over (hypotheses x correspondences), and the decision is  D = s |s| - (1 - thr)^2 n2 > 0.
+// The FP32 kernel (score_kernel) spends 19 FMA-pipe lanes per pair on them; here they come out of the 5th-generation
+// tensor cores and the SM's ALUs only see 4 instructions per pair:
+//   * every float32 feature is split exactly into three bfloat16 pieces (8 + 8 + 8 mantissa bits), and the six partial
+//     products hi*hi, hi*mid, mid*hi, hi*lo, lo*hi, mid*mid are laid out as six K columns per feature (what is dropped is
+//     below 2^-25 of the term), so a tcgen05.mma kind::f16 with float32 accumulators in tensor memory reproduces the
+//     float32 product to ~1e-7 relative; K = 12*6 -> 80 columns for s, 10*6 -> 64 columns for n2: 288 bytes per row, the same
+//     tile geometry as the Hamming engine (128 rows x 288 bytes, canonical K-major no-swizzle UMMA layout);
+//   * hypothesis features depend on the camera of the correspondence (A = Rc^T R^T, b = -Rc^T (R^T t + tc)), so each
+//     hypothesis tile exists once per camera, and each correspondence tile too (rows of the other camera are zero); a tile
+//     that mixes cameras simply runs both MMAs into the same accumulator;
+//   * an epilogue thread owns one hypothesis (= TMEM lane), reads 32 pairs of (s, n2) with tcgen05.ld and per pair does
+//     FMUL (s|s|), FFMA (D), FSETP.OR (|D| < band), SHF (collect the sign bit); 32 signs are counted with one POPC.
+// Exactness: a band bounds the error of D from the split, the accumulation and the two float32 operations:
+// |err D| <= BAND_REL (|p|^2 + |b|^2) (measured on every pair of the test problems by tests/test_gpu_score_tc.py through the
+// PROBE instantiation: 1.4e-6, BAND_REL is 9 x that), and since x = A p + b with A orthogonal, |p|^2 <= 2 n2 + 2 |b|^2, so
+// the band is  2 BAND_REL n2 + 3 BAND_REL |b|^2  — relative to the pair's own n2, one more FFMA per pair.  A 32-pair chunk
+// with a pair inside the band is queued and
+// re-decided after the item by the scalar float32 path with ITS rigorous guard and, inside that, by inlier_exact() in
+// float64 — the same deferred path score_kernel uses — so every count equals the float64 oracle's.
+// (ransac.cu includes <cuda_bf16.h> and "tc_common.cuh" at file scope before this.)
+#pragma once
+
+namespace score_tc {
+using namespace sos_tc;
+
+constexpr int TILE = 128;
+constexpr int KS = 12, KN = 10;                 // features of s and n2
+constexpr int ES = 80, EN = 64;                 // bf16 elements per row: 6 per feature, zero padded to a multiple of 16
+constexpr int KB = (ES + EN) * 2;               // 288 bytes per row
+constexpr int CHUNKS = KB / 16;                 // 18 core-matrix columns
+constexpr int GROUP_BYTES = CHUNKS * 128;       // one 8-row group
+constexpr int TILE_BYTES = (TILE / 8) * GROUP_BYTES;   // 36864
+constexpr int STAGES = 4;
+constexpr int THREADS = 384;
+constexpr int QCAP = 1536;                      // deferred 32-pair chunks per work item held in shared memory
+constexpr int SMEM_BYTES = (2 + STAGES) * TILE_BYTES + 256 + QCAP * 4;
+constexpr float PAD_N2 = 1e30f;                 // n2 feature of a padding correspondence: D = -c^2 1e30, a certain outlier
+// |err D| <= BAND_REL (|p|^2 + max_cam |b|^2): 13 eps + 5e-7 with eps = 2^-20 for the relative error of an accumulated term
+// sum (tests/test_gpu_score_tc.py measures 1.4e-6 for the whole expression and asserts a 4x margin)
+constexpr float BAND_REL = 13.0f * 9.5367431640625e-07f + 5e-7f;
+constexpr float BAND_N2 = 2.02f * BAND_REL, BAND_B2 = 3.03f * BAND_REL;   // band = BAND_N2 n2 + BAND_B2 |b|^2
+
+struct TileMeta {
+  uint32_t cam_mask;   // bit c: the tile holds correspondences of camera c
+};
+
+// float32 -> three bfloat16 pieces with x == hi + mid + lo exactly
+__device__ __forceinline__ void split3(float x, uint32_t& h, uint32_t& m, uint32_t& l) {
+  const __nv_bfloat16 bh = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(bh);
+  const __nv_bfloat16 bm = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(bm);
+  const __nv_bfloat16 bl = __float2bfloat16_rn(r2);
+  h = __bfloat16_as_ushort(bh);
+  m = __bfloat16_as_ushort(bm);
+  l = __bfloat16_as_ushort(bl);
+}
+
+// One 288-byte row of a tile.  ROLE 0 (hypothesis, A operand): the six columns of a feature hold (h, h, m, h, l, m);
+// ROLE 1 (correspondence, B operand): (h, m, h, l, h, m) — their products are hh + hm + mh + hl + lh + mm.
+// Byte (row r, k) of a tile sits at (r / 8) * GROUP_BYTES + (k / 16) * 128 + (r % 8) * 16 + k % 16.
+template <int ROLE>
+__device__ __forceinline__ void write_row(uint8_t* __restrict__ tile, int r, const float* fs, const float* fn) {
+  uint32_t e[(ES + EN) / 2];   // packed pairs of bf16
+#pragma unroll
+  for (int i = 0; i < (ES + EN) / 2; ++i) e[i] = 0u;
+  auto put = [&](int base, int k, float x) {
+    uint32_t h, m, l;
+    split3(x, h, m, l);
+    const uint32_t c0 = h, c1 = ROLE ? m : h, c2 = ROLE ? h : m, c3 = ROLE ? l : h, c4 = ROLE ? h : l, c5 = m;
+    const int el = base + 6 * k;   // even
+    e[el / 2 + 0] = c0 | (c1 << 16);
+    e[el / 2 + 1] = c2 | (c3 << 16);
+    e[el / 2 + 2] = c4 | (c5 << 16);
+  };
+#pragma unroll
+  for (int k = 0; k < KS; ++k) put(0, k, fs[k]);
+#pragma unroll
+  for (int k = 0; k < KN; ++k) put(ES, k, fn[k]);
+  uint8_t* row = tile + (size_t)(r >> 3) * GROUP_BYTES + (r & 7) * 16;
+#pragma unroll
+  for (int c = 0; c < CHUNKS; ++c)
+    *(uint4*)(row + c * 128) = make_uint4(e[4 * c], e[4 * c + 1], e[4 * c + 2], e[4 * c + 3]);
+}
+
+// Hypothesis side, called by the hypothesize kernels: Ad (3x3 row-major) and bd of camera c in float64.
+__device__ __forceinline__ void emit_hyp_row(uint8_t* __restrict__ tile, int r, const double* Ad, const double* bd, bool ok) {
+  float fs[KS], fn[KN];
+  if (ok) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) fs[i] = (float)Ad[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) fs[9 + i] = (float)bd[i];
+    auto G = [&](int k, int l) { return Ad[k] * Ad[l] + Ad[3 + k] * Ad[3 + l] + Ad[6 + k] * Ad[6 + l]; };
+    fn[0] = (float)G(0, 0); fn[1] = (float)G(1, 1); fn[2] = (float)G(2, 2);
+    fn[3] = (float)G(0, 1); fn[4] = (float)G(0, 2); fn[5] = (float)G(1, 2);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) fn[6 + k] = (float)(Ad[k] * bd[0] + Ad[3 + k] * bd[1] + Ad[6 + k] * bd[2]);
+    fn[9] = (float)(bd[0] * bd[0] + bd[1] * bd[1] + bd[2] * bd[2]);
+  } else {
+    // failed model: NaN accumulators never land inside the band (no deferred work) and its count stays hugely negative
+#pragma unroll
+    for (int i = 0; i < KS; ++i) fs[i] = CUDART_NAN_F;
+#pragma unroll
+    for (int i = 0; i < KN; ++i) fn[i] = CUDART_NAN_F;
+  }
+  write_row<0>(tile, r, fs, fn);
+}
+
+// Correspondence side: one block per 128-row tile of one problem; both camera tiles are written (the other camera's row
+// is zero), plus the tile's camera mask and max |p|^2.
+__global__ void __launch_bounds__(TILE)
+corr_expand_kernel(const float* __restrict__ p_ref, const float* __restrict__ f_cur, const uint8_t* __restrict__ cam,
+                   const int32_t* __restrict__ n_arr, int cap, int n_cams, int ct, uint8_t* __restrict__ b_exp,
+                   TileMeta* __restrict__ meta) {
+  __shared__ uint32_t wmask[TILE / 32];
+  const int b = blockIdx.y, tile = blockIdx.x, r = threadIdx.x;
+  const int n = min(n_arr[b], cap);
+  if (tile * TILE >= n) return;
+  const int j = tile * TILE + r;
+  float fs[KS], fn[KN];
+#pragma unroll
+  for (int i = 0; i < KS; ++i) fs[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < KN; ++i) fn[i] = 0.f;
+  int c = 0;
+  bool real = false;
+  if (j < n) {
+    const size_t o = ((size_t)b * cap + j) * 3;
+    const float p[3] = {p_ref[o], p_ref[o + 1], p_ref[o + 2]}, f[3] = {f_cur[o], f_cur[o + 1], f_cur[o + 2]};
+    c = (n_cams > 1 && cam) ? (cam[(size_t)b * cap + j] ? 1 : 0) : 0;
+    real = isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]) && isfinite(f[0]) && isfinite(f[1]) && isfinite(f[2]);
+    if (real) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) fs[i * 3 + k] = (float)((double)f[i] * (double)p[k]);
+        fs[9 + i] = f[i];
+      }
+      const double px = p[0], py = p[1], pz = p[2];
+      fn[0] = (float)(px * px); fn[1] = (float)(py * py); fn[2] = (float)(pz * pz);
+      fn[3] = (float)(2.0 * px * py); fn[4] = (float)(2.0 * px * pz); fn[5] = (float)(2.0 * py * pz);
+      fn[6] = 2.f * p[0]; fn[7] = 2.f * p[1]; fn[8] = 2.f * p[2];
+      fn[9] = 1.f;
+    }
+  }
+  uint8_t* t0 = b_exp + ((size_t)((size_t)b * ct + tile) * 2) * TILE_BYTES;
+  float zs[KS], zn[KN];
+#pragma unroll
+  for (int i = 0; i < KS; ++i) zs[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < KN; ++i) zn[i] = 0.f;
+  if (!real) {
+    // padding row, or a correspondence with a non-finite coordinate (NaN never passes the reference's test): n2 = 1e30 in
+    // whichever camera tiles are multiplied
+    fn[0] = PAD_N2;
+    zn[0] = PAD_N2;
+  }
+  write_row<1>(t0 + (size_t)c * TILE_BYTES, r, fs, fn);
+  write_row<1>(t0 + (size_t)(c ^ 1) * TILE_BYTES, r, zs, zn);
+  // tile meta
+  uint32_t mask = (j < n) ? (1u << c) : 0u;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mask |= __shfl_xor_sync(0xFFFFFFFFu, mask, off);
+  if ((r & 31) == 0) wmask[r >> 5] = mask;
+  __syncthreads();
+  if (r == 0) {
+    TileMeta m;
+    m.cam_mask = wmask[0] | wmask[1] | wmask[2] | wmask[3];
+    meta[(size_t)b * ct + tile] = m;
+  }
+}
+
+// instruction descriptor: D = F32 (1 << 4), A = B = BF16 (1 << 7, 1 << 10), both K-major, N = 128, M = 128
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TILE >> 3) << 17) | ((uint32_t)(TILE >> 4) << 24);
+
+struct Args {
+  const uint8_t *a_exp, *b_exp;
+  const TileMeta* meta;
+  const int32_t* n_arr;
+  int cap, n_hyp, ht, ct, splits;
+  const HypRec* recs;
+  int32_t* counts;
+  const float *p_ref, *f_cur;
+  const uint8_t* cam;
+  ScoreConst k;
+  float* probe;          // PROBE: (s, n2) of every pair, [problem][hypothesis][ct * 128][2]
+};
+
+// one deferred pair, decided exactly like score_kernel's deferred pass
+__device__ __forceinline__ int exact_pair(const Args& a, const Rig& rig, int b, int h, int j, int n) {
+  if (j >= n) return 0;
+  const HypRec* hr = a.recs + (size_t)b * a.n_hyp + h;
+  const size_t o = ((size_t)b * a.cap + j) * 3;
+  const int c = (rig.n_cams > 1 && a.cam) ? (a.cam[(size_t)b * a.cap + j] ? 1 : 0) : 0;
+  const float4 p = make_float4(a.p_ref[o], a.p_ref[o + 1], a.p_ref[o + 2], 0.f);
+  const float4 q = make_float4(a.f_cur[o], a.f_cur[o + 1], a.f_cur[o + 2], 0.f);
+  float Ax[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) Ax[i] = __ldg(&hr->xf[c][i]);
+  float D, g;
+  decision<SOS_SCORE_BEARING>(Ax, p, q, guard_of(SOS_SCORE_BEARING, p.x, p.y, p.z, q.x, q.y, q.z, a.k.thr), a.k, D, g);
+  if (fabsf(D) < g) return inlier_exact(SOS_SCORE_BEARING, hr->pose64, rig, c, p, q, a.k.thr) ? 1 : 0;
+  return D > 0.f ? 1 : 0;
+}
+
+// Work item = (problem, 128 hypotheses, a range of correspondence tiles); one CTA per item, warp-specialised like the
+// Hamming engine: warp 0 streams the two hypothesis tiles (one per camera) and a ring of correspondence tiles with
+// cp.async.bulk, one lane of warp 1 issues 5 + 4 tcgen05.mma (M128 N128 K16) per (tile, camera) into a double-buffered
+// accumulator pair (s: 128 columns, n2: 128 columns; 2 buffers = all 512 TMEM columns), warps 4..11 are the epilogue:
+// warp group g takes correspondences [64 g, 64 g + 64) of every tile.
+template <bool PROBE>
+__global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, const __grid_constant__ Rig rig) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int item = blockIdx.x;
+  const int b = item / (a.ht * a.splits), ht = (item / a.splits) % a.ht, split = item % a.splits;
+  const int n = min(a.n_arr[b], a.cap);
+  const int nt = (n + TILE - 1) / TILE;
+  const int per = (nt + a.splits - 1) / a.splits;
+  const int k_begin = min(nt, split * per), k_end = min(nt, k_begin + per);
+  if (k_begin >= k_end) return;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 2 * TILE_BYTES;
+  uint64_t* bars = (uint64_t*)(smem + (2 + STAGES) * TILE_BYTES);
+  constexpr int FULL = 0, EMPTY = STAGES, TFULL = 2 * STAGES, TEMPTY = 2 * STAGES + 2, AFULL = 2 * STAGES + 4;
+  uint32_t* tmem_slot = (uint32_t*)(bars + AFULL + 1);
+  int* q_n = (int*)(tmem_slot + 1);
+  uint32_t* queue = (uint32_t*)(smem + (2 + STAGES) * TILE_BYTES + 256);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const TileMeta* meta = a.meta + (size_t)b * a.ct;
+
+  if (tid == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1); }
+    mbar_init(BAR(TFULL), 1); mbar_init(BAR(TFULL + 1), 1);
+    mbar_init(BAR(TEMPTY), 8); mbar_init(BAR(TEMPTY + 1), 8);
+    mbar_init(BAR(AFULL), 1);
+    *q_n = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint8_t* ga = a.a_exp + ((size_t)((size_t)b * a.ht + ht) * 2) * TILE_BYTES;
+      mbar_expect_tx(BAR(AFULL), 2u * TILE_BYTES);
+#pragma unroll
+      for (int p = 0; p < 8; ++p) bulk_g2s(smem_u32(sA) + p * (TILE_BYTES / 4), ga + (size_t)p * (TILE_BYTES / 4), TILE_BYTES / 4, BAR(AFULL));
+      uint32_t t = 0;
+      for (int k = k_begin; k < k_end; ++k) {
+        const uint32_t mask = meta[k].cam_mask;
+        for (int c = 0; c < 2; ++c) {
+          if (!((mask >> c) & 1u)) continue;
+          const uint32_t s = t % STAGES;
+          mbar_wait(BAR(EMPTY + s), ((t / STAGES) & 1) ^ 1);
+          mbar_expect_tx(BAR(FULL + s), TILE_BYTES);
+          const uint8_t* gb = a.b_exp + ((size_t)(((size_t)b * a.ct + k) * 2 + c)) * TILE_BYTES;
+          const uint32_t dst = smem_u32(sB) + s * TILE_BYTES;
+#pragma unroll
+          for (int p = 0; p < 4; ++p) bulk_g2s(dst + p * (TILE_BYTES / 4), gb + (size_t)p * (TILE_BYTES / 4), TILE_BYTES / 4, BAR(FULL + s));
+          ++t;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(BAR(AFULL), 0);
+      uint32_t t = 0, it = 0;
+      for (int k = k_begin; k < k_end; ++k, ++it) {
+        const uint32_t mask = meta[k].cam_mask;
+        const uint32_t buf = it & 1;
+        mbar_wait(BAR(TEMPTY + buf), ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator pair
+        uint32_t acc = 0;
+        for (int c = 0; c < 2; ++c) {
+          if (!((mask >> c) & 1u)) continue;
+          const uint32_t s = t % STAGES;
+          mbar_wait(BAR(FULL + s), (t / STAGES) & 1);
+          tc_fence_after();
+          const uint64_t da = smem_desc(smem_u32(sA) + c * TILE_BYTES, GROUP_BYTES);
+          const uint64_t db = smem_desc(smem_u32(sB) + s * TILE_BYTES, GROUP_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < ES / 16; ++kk)
+            tc_mma<KIND_L2>(tmem + buf * 256, da + (uint64_t)(16 * kk), db + (uint64_t)(16 * kk), IDESC, acc | (kk > 0));
+#pragma unroll
+          for (int kk = ES / 16; kk < (ES + EN) / 16; ++kk)
+            tc_mma<KIND_L2>(tmem + buf * 256 + TILE, da + (uint64_t)(16 * kk), db + (uint64_t)(16 * kk), IDESC, acc | (kk > ES / 16));
+          tc_commit(BAR(EMPTY + s));
+          acc = 1;
+          ++t;
+        }
+        tc_commit(BAR(TFULL + buf));
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    const int g = (warp - 4) >> 2, quarter = warp & 3;   // a warp may only touch the TMEM lanes of its quarter
+    const int row = quarter * 32 + lane;
+    const int h = ht * TILE + row;
+    const bool valid_h = h < a.n_hyp;
+    float bmax2 = 0.f;
+    if (valid_h) {
+      const HypRec* hr = a.recs + (size_t)b * a.n_hyp + h;
+      for (int c = 0; c < rig.n_cams; ++c) {
+        const float bx = __ldg(&hr->xf[c][9]), by = __ldg(&hr->xf[c][10]), bz = __ldg(&hr->xf[c][11]);
+        bmax2 = fmaxf(bmax2, bx * bx + by * by + bz * bz);
+      }
+      bmax2 *= 1.000001f;
+    }
+    const float nc2 = -a.k.cos_min_sq;
+    const float Gh = BAND_B2 * bmax2;
+    int cnt = 0;
+    uint32_t it = 0;
+    for (int k = k_begin; k < k_end; ++k, ++it) {
+      const uint32_t buf = it & 1;
+      mbar_wait(BAR(TFULL + buf), (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * 256 + g * 64;
+      int sv[32], nv[32], sw[32], nw[32];
+      tmem_ld32(taddr, sv);
+      tmem_ld32(taddr + TILE, nv);
+      tmem_ld_wait(sv);
+      tmem_ld_wait(nv);
+      tmem_ld32(taddr + 32, sw);            // in flight while the first chunk is classified
+      tmem_ld32(taddr + TILE + 32, nw);
+      auto classify = [&](const int (&S)[32], const int (&N)[32], int chunk) {
+        uint32_t signs = 0;
+        float slack = CUDART_INF_F;    // min over the chunk of |D| - BAND_N2 n2 (NaN pairs of a failed model drop out of fminf)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float s = __int_as_float(S[i]), n2 = __int_as_float(N[i]);
+          const float D = __fmaf_rn(n2, nc2, __fmul_rn(s, fabsf(s)));   // s|s| folds the s > 0 test into D
+          slack = fminf(slack, __fmaf_rn(n2, -BAND_N2, fabsf(D)));
+          signs = __funnelshift_l(__float_as_uint(D), signs, 1);
+          if (PROBE && valid_h) {
+            float* o = a.probe + (((size_t)b * a.n_hyp + h) * ((size_t)a.ct * TILE) + (size_t)k * TILE + chunk * 32 + i) * 2;
+            o[0] = s;
+            o[1] = n2;
+          }
+        }
+        if (!valid_h) return;
+        if (!(slack <= Gh)) {
+          cnt += 32 - __popc(signs);
+        } else {
+          const int slot = atomicAdd(q_n, 1);
+          if (slot < QCAP) {
+            queue[slot] = ((uint32_t)k << 9) | ((uint32_t)chunk << 7) | (uint32_t)row;
+          } else {   // queue full (never observed): this thread decides its 32 pairs on its own
+            for (int i = 0; i < 32; ++i) cnt += exact_pair(a, rig, b, h, k * TILE + chunk * 32 + i, n);
+          }
+        }
+      };
+      classify(sv, nv, 2 * g);
+      tmem_ld_wait(sw);
+      tmem_ld_wait(nw);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(TEMPTY + buf));     // the accumulator pair may be overwritten
+      classify(sw, nw, 2 * g + 1);
+    }
+    if (valid_h && cnt != 0) atomicAdd(&a.counts[(size_t)b * a.n_hyp + h], cnt);
+    // deferred chunks: one warp per entry, one lane per pair
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const int nq = min(*q_n, QCAP);
+    for (int e = warp - 4; e < nq; e += 8) {
+      const uint32_t v = queue[e];
+      const int k = (int)(v >> 9), chunk = (int)((v >> 7) & 3u), r = (int)(v & 127u);
+      const int hh = ht * TILE + r;
+      const int in = exact_pair(a, rig, b, hh, k * TILE + chunk * 32 + lane, n);
+      const unsigned vote = __ballot_sync(0xFFFFFFFFu, in != 0);
+      if (lane == 0 && vote) atomicAdd(&a.counts[(size_t)b * a.n_hyp + hh], __popc(vote));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+inline size_t scratch_bytes(int n_problems, int n_hyp, int cap) {
+  const size_t ht = (size_t)(n_hyp + TILE - 1) / TILE, ct = (size_t)(cap + TILE - 1) / TILE;
+  return (size_t)n_problems * (ht + ct) * 2 * TILE_BYTES + sos_align_up((size_t)n_problems * ct * sizeof(TileMeta), 256) + 512;
+}
+
+}  // namespace score_tc
