@@ -18,14 +18,16 @@
 //     hypothesis tile exists once per camera, and each correspondence tile too (rows of the other camera are zero); a tile
 //     that mixes cameras simply runs both MMAs into the same accumulator;
 //   * an epilogue thread owns one hypothesis (= TMEM lane), reads 32 pairs of (s, n2) with tcgen05.ld and per pair does
-//     FMUL (s|s|), FFMA (D), FSETP.OR (|D| < band), SHF (collect the sign bit); 32 signs are counted with one POPC.
+//     two FFMA (s|s| -+ the absolute part of the band), one packed FFMA2 per two pairs for each of t = D - band and
+//     u = D + band, and two SHF that collect their sign bits; 32 pairs are counted with one POPC.
 // Exactness: a band bounds the error of D from the split, the accumulation and the two float32 operations:
 // |err D| <= BAND_REL (|p|^2 + |b|^2) (measured on every pair of the test problems by tests/test_gpu_score_tc.py through the
-// PROBE instantiation: 1.4e-6, BAND_REL is 9 x that), and since x = A p + b with A orthogonal, |p|^2 <= 2 n2 + 2 |b|^2, so
-// the band is  2 BAND_REL n2 + 3 BAND_REL |b|^2  — relative to the pair's own n2, one more FFMA per pair.  A 32-pair chunk
-// with a pair inside the band is queued and
-// re-decided after the item by the scalar float32 path with ITS rigorous guard and, inside that, by inlier_exact() in
-// float64 — the same deferred path score_kernel uses — so every count equals the float64 oracle's.
+// PROBE instantiation: 1.4e-6, BAND_REL is 9 x that).  Since x = A p + b with A orthogonal, |p|^2 <= 2 n2 + 2 |b|^2, so the
+// band is at most BETA n2 + G_h with BETA = 2 BAND_REL and G_h = 3 BAND_REL |b_h|^2 — relative to the pair's own n2 plus a
+// constant of the hypothesis, which fold into the FFMA constants: t = (s|s| - G_h) - (c^2 + BETA) n2 >= 0 is a certain
+// inlier, u = (s|s| + G_h) - (c^2 - BETA) n2 < 0 a certain outlier.  The uncertain pairs of a chunk
+// (bit mask) are queued and re-decided after the item by the scalar float32 path with ITS rigorous guard and, inside that,
+// by inlier_exact() in float64 — the same deferred path score_kernel uses — so every count equals the float64 oracle's.
 // (ransac.cu includes <cuda_bf16.h> and "tc_common.cuh" at file scope before this.)
 #pragma once
 
@@ -39,15 +41,16 @@ constexpr int KB = (ES + EN) * 2;               // 288 bytes per row
 constexpr int CHUNKS = KB / 16;                 // 18 core-matrix columns
 constexpr int GROUP_BYTES = CHUNKS * 128;       // one 8-row group
 constexpr int TILE_BYTES = (TILE / 8) * GROUP_BYTES;   // 36864
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr int THREADS = 384;
-constexpr int QCAP = 1536;                      // deferred 32-pair chunks per work item held in shared memory
-constexpr int SMEM_BYTES = (2 + STAGES) * TILE_BYTES + 256 + QCAP * 4;
+constexpr int ECAP = 1536;                      // chunks with uncertain pairs per work item held in shared memory (entry + bit mask)
+constexpr int PCAP = 2048;                      // uncertain pairs expanded per round of the deferred pass
+constexpr int SMEM_BYTES = (2 + STAGES) * TILE_BYTES + 256 + ECAP * 8 + PCAP * 4 + TILE * 4;
 constexpr float PAD_N2 = 1e30f;                 // n2 feature of a padding correspondence: D = -c^2 1e30, a certain outlier
 // |err D| <= BAND_REL (|p|^2 + max_cam |b|^2): 13 eps + 5e-7 with eps = 2^-20 for the relative error of an accumulated term
 // sum (tests/test_gpu_score_tc.py measures 1.4e-6 for the whole expression and asserts a 4x margin)
 constexpr float BAND_REL = 13.0f * 9.5367431640625e-07f + 5e-7f;
-constexpr float BAND_N2 = 2.02f * BAND_REL, BAND_B2 = 3.03f * BAND_REL;   // band = BAND_N2 n2 + BAND_B2 |b|^2
+constexpr float BETA = 2.02f * BAND_REL, BAND_B2 = 3.03f * BAND_REL;   // band <= BETA n2 + BAND_B2 |b|^2
 
 struct TileMeta {
   uint32_t cam_mask;   // bit c: the tile holds correspondences of camera c
@@ -213,6 +216,14 @@ __device__ __forceinline__ int exact_pair(const Args& a, const Rig& rig, int b, 
   return D > 0.f ? 1 : 0;
 }
 
+__device__ __forceinline__ float2 pk_ffma2(float2 x, float2 y, float2 z) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<uint64_t&>(d))
+      : "l"(reinterpret_cast<uint64_t&>(x)), "l"(reinterpret_cast<uint64_t&>(y)), "l"(reinterpret_cast<uint64_t&>(z)));
+  return d;
+}
+
 // Work item = (problem, 128 hypotheses, a range of correspondence tiles); one CTA per item, warp-specialised like the
 // Hamming engine: warp 0 streams the two hypothesis tiles (one per camera) and a ring of correspondence tiles with
 // cp.async.bulk, one lane of warp 1 issues 5 + 4 tcgen05.mma (M128 N128 K16) per (tile, camera) into a double-buffered
@@ -234,8 +245,12 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
   uint64_t* bars = (uint64_t*)(smem + (2 + STAGES) * TILE_BYTES);
   constexpr int FULL = 0, EMPTY = STAGES, TFULL = 2 * STAGES, TEMPTY = 2 * STAGES + 2, AFULL = 2 * STAGES + 4;
   uint32_t* tmem_slot = (uint32_t*)(bars + AFULL + 1);
-  int* q_n = (int*)(tmem_slot + 1);
-  uint32_t* queue = (uint32_t*)(smem + (2 + STAGES) * TILE_BYTES + 256);
+  int* q_n = (int*)(tmem_slot + 1);       // chunks queued
+  int* p_n = q_n + 1;                     // pairs expanded in this round
+  uint32_t* qent = (uint32_t*)(smem + (2 + STAGES) * TILE_BYTES + 256);   // tile << 9 | chunk << 7 | row
+  uint32_t* qmask = qent + ECAP;                                           // uncertain pairs of the chunk (bit 31 - i = pair i)
+  uint32_t* pairs = qmask + ECAP;                                          // entry << 5 | pair
+  int* fixcnt = (int*)(pairs + PCAP);                                      // inliers found by the deferred pass, per hypothesis row
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   const TileMeta* meta = a.meta + (size_t)b * a.ct;
@@ -248,6 +263,7 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
     *q_n = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (tid < TILE) fixcnt[tid] = 0;
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -322,10 +338,10 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
         const float bx = __ldg(&hr->xf[c][9]), by = __ldg(&hr->xf[c][10]), bz = __ldg(&hr->xf[c][11]);
         bmax2 = fmaxf(bmax2, bx * bx + by * by + bz * bz);
       }
-      bmax2 *= 1.000001f;
     }
-    const float nc2 = -a.k.cos_min_sq;
     const float Gh = BAND_B2 * bmax2;
+    const float2 ka = make_float2(-(a.k.cos_min_sq + BETA), -(a.k.cos_min_sq + BETA));
+    const float2 kb = make_float2(-(a.k.cos_min_sq - BETA), -(a.k.cos_min_sq - BETA));
     int cnt = 0;
     uint32_t it = 0;
     for (int k = k_begin; k < k_end; ++k, ++it) {
@@ -341,29 +357,35 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
       tmem_ld32(taddr + 32, sw);            // in flight while the first chunk is classified
       tmem_ld32(taddr + TILE + 32, nw);
       auto classify = [&](const int (&S)[32], const int (&N)[32], int chunk) {
-        uint32_t signs = 0;
-        float slack = CUDART_INF_F;    // min over the chunk of |D| - BAND_N2 n2 (NaN pairs of a failed model drop out of fminf)
+        uint32_t mt = 0, mu = 0;       // sign bits of t and u: pair i ends up in bit 31 - i
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = __int_as_float(S[i]), n2 = __int_as_float(N[i]);
-          const float D = __fmaf_rn(n2, nc2, __fmul_rn(s, fabsf(s)));   // s|s| folds the s > 0 test into D
-          slack = fminf(slack, __fmaf_rn(n2, -BAND_N2, fabsf(D)));
-          signs = __funnelshift_l(__float_as_uint(D), signs, 1);
+        for (int i = 0; i < 32; i += 2) {
+          const float s0 = __int_as_float(S[i]), s1 = __int_as_float(S[i + 1]);
+          const float2 n2 = make_float2(__int_as_float(N[i]), __int_as_float(N[i + 1]));
+          // s|s| folds the s > 0 test into D
+          const float2 wt = make_float2(__fmaf_rn(s0, fabsf(s0), -Gh), __fmaf_rn(s1, fabsf(s1), -Gh));
+          const float2 wu = make_float2(__fmaf_rn(s0, fabsf(s0), Gh), __fmaf_rn(s1, fabsf(s1), Gh));
+          const float2 t = pk_ffma2(n2, ka, wt), u = pk_ffma2(n2, kb, wu);
+          mt = __funnelshift_l(__float_as_uint(t.x), mt, 1);
+          mt = __funnelshift_l(__float_as_uint(t.y), mt, 1);
+          mu = __funnelshift_l(__float_as_uint(u.x), mu, 1);
+          mu = __funnelshift_l(__float_as_uint(u.y), mu, 1);
           if (PROBE && valid_h) {
             float* o = a.probe + (((size_t)b * a.n_hyp + h) * ((size_t)a.ct * TILE) + (size_t)k * TILE + chunk * 32 + i) * 2;
-            o[0] = s;
-            o[1] = n2;
+            o[0] = s0; o[1] = n2.x; o[2] = s1; o[3] = n2.y;
           }
         }
         if (!valid_h) return;
-        if (!(slack <= Gh)) {
-          cnt += 32 - __popc(signs);
-        } else {
+        const uint32_t unsure = mt & ~mu;          // t < 0 <= u
+        cnt += 32 - __popc(mt);                    // certain inliers; uncertain pairs are added by the deferred pass
+        if (unsure) {
           const int slot = atomicAdd(q_n, 1);
-          if (slot < QCAP) {
-            queue[slot] = ((uint32_t)k << 9) | ((uint32_t)chunk << 7) | (uint32_t)row;
-          } else {   // queue full (never observed): this thread decides its 32 pairs on its own
-            for (int i = 0; i < 32; ++i) cnt += exact_pair(a, rig, b, h, k * TILE + chunk * 32 + i, n);
+          if (slot < ECAP) {
+            qent[slot] = ((uint32_t)k << 9) | ((uint32_t)chunk << 7) | (uint32_t)row;
+            qmask[slot] = unsure;
+          } else {   // queue full (never observed): this thread decides its uncertain pairs on its own
+            for (int i = 0; i < 32; ++i)
+              if ((unsure >> (31 - i)) & 1u) cnt += exact_pair(a, rig, b, h, k * TILE + chunk * 32 + i, n);
           }
         }
       };
@@ -375,18 +397,37 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
       if (lane == 0) mbar_arrive(BAR(TEMPTY + buf));     // the accumulator pair may be overwritten
       classify(sw, nw, 2 * g + 1);
     }
-    if (valid_h && cnt != 0) atomicAdd(&a.counts[(size_t)b * a.n_hyp + h], cnt);
-    // deferred chunks: one warp per entry, one lane per pair
+    // deferred pass over the uncertain pairs, all 256 epilogue threads: expand the chunk masks into a pair list (in rounds
+    // of PCAP pairs), one thread per pair
+    const int te = tid - 4 * 32;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    const int nq = min(*q_n, QCAP);
-    for (int e = warp - 4; e < nq; e += 8) {
-      const uint32_t v = queue[e];
-      const int k = (int)(v >> 9), chunk = (int)((v >> 7) & 3u), r = (int)(v & 127u);
-      const int hh = ht * TILE + r;
-      const int in = exact_pair(a, rig, b, hh, k * TILE + chunk * 32 + lane, n);
-      const unsigned vote = __ballot_sync(0xFFFFFFFFu, in != 0);
-      if (lane == 0 && vote) atomicAdd(&a.counts[(size_t)b * a.n_hyp + hh], __popc(vote));
+    const int nq = min(*q_n, ECAP);
+    for (bool more = nq > 0; more;) {
+      if (te == 0) *p_n = 0;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int e = te; e < nq; e += 256) {
+        uint32_t m = qmask[e];
+        while (m) {
+          const int slot = atomicAdd(p_n, 1);
+          if (slot >= PCAP) break;
+          const int bit = 31 - __clz(m);
+          pairs[slot] = ((uint32_t)e << 5) | (uint32_t)(31 - bit);
+          m &= ~(1u << bit);
+        }
+        qmask[e] = m;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int np = *p_n;
+      for (int x = te; x < min(np, PCAP); x += 256) {
+        const uint32_t v = pairs[x], ent = qent[v >> 5];
+        const int k = (int)(ent >> 9), chunk = (int)((ent >> 7) & 3u), r = (int)(ent & 127u);
+        if (exact_pair(a, rig, b, ht * TILE + r, k * TILE + chunk * 32 + (int)(v & 31u), n)) atomicAdd(&fixcnt[r], 1);
+      }
+      more = np > PCAP;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
+    if (g == 0) cnt += fixcnt[row];
+    if (valid_h && cnt != 0) atomicAdd(&a.counts[(size_t)b * a.n_hyp + h], cnt);
   }
   tc_fence_before();
   __syncthreads();
