@@ -443,18 +443,39 @@ def run_gpu(args, rank, local_rank, world):
                 "algorithmic_frac": ops_t / (t * 1e-3) / 1e12 / popc_peak,
                 "note": "frac = share of the POPC pipe actually used (the kernel executes 5 POPC per pair after three carry-save "
                         "adders); algorithmic_frac counts SURVEY 8d's 8 POPC32 per pair and can exceed 1"}
-    t = k_ms("score_kernel#0")
-    fl = float(w.cfg.n_hyp) * float(n_corr.sum()) * flop_pair
-    fl_exec = float(w.cfg.n_hyp) * float(n_corr.sum()) * flop_exec
-    roof["ransac_score"] = {"kernel": "score_kernel", "bound": "fp32-fma", "achieved": fl_exec / (t * 1e-3) / 1e12, "peak": ffma2_peak,
-                            "unit": "TFLOP/s", "frac": fl_exec / (t * 1e-3) / 1e12 / ffma2_peak, "ms": t,
-                            "peak_source": "packed fma.rn.f32x2 microbenchmark run in this process (the instruction the kernel issues); "
-                                           "scalar FFMA peak beside it", "ffma_scalar_peak_tflops": ffma_peak,
-                            "flop_per_pair_executed": flop_exec, "flop_per_pair_model": flop_pair,
-                            "model_frac": fl / (t * 1e-3) / 1e12 / ffma_peak,
-                            "note": "achieved = FLOPs the kernel executes (SASS count of the inner loop x pairs); ncu "
-                                    "sm__pipe_fma_cycles_active of the same kernel: profiles/r02/score_*_metrics.txt",
-                            "hypothesis_point_pairs": float(w.cfg.n_hyp) * float(n_corr.sum()), "traffic": None}
+    pairs_hc = float(w.cfg.n_hyp) * float(n_corr.sum())
+    fl = pairs_hc * flop_pair
+    if "score_mma_kernel#0" in kernels:
+        # bearing score on the tensor cores (csrc/score_mma.cuh): 144 bf16 MACs per (hypothesis, correspondence) pair — 12 + 10
+        # features x 6 partial products of the three-way bfloat16 split, zero padded to 80 + 64 K columns
+        t = k_ms("score_mma_kernel#0")
+        bf16_peak = float(peaks.get("bf16_tflops", 1694.3))
+        mac_flop = pairs_hc * 144.0 * 2.0
+        roof["ransac_score"] = {
+            "kernel": "score_mma_kernel (tcgen05.mma kind::f16, bf16 x 3 split, fp32 accumulators in TMEM)", "bound": "tensor",
+            "achieved": mac_flop / (t * 1e-3) / 1e12, "peak": bf16_peak, "unit": "TFLOP/s", "frac": mac_flop / (t * 1e-3) / 1e12 / bf16_peak,
+            "ms": t, "peak_source": "MEASURED_PEAKS.json bf16_tflops (cuBLAS burst)" if peaks else "fallback 1694.3 TFLOP/s",
+            "hypothesis_point_pairs": pairs_hc, "traffic": None, "expand_ms": k_ms("score_expand_kernel#0"),
+            "algorithmic_flop_per_pair": "288 (144 bf16 MACs: the float32 products of SURVEY 8d's 45-FLOP model, each split into six bf16 products)",
+            "fp32_equivalent": {"flop_per_pair_model": flop_pair, "tflops": fl / (t * 1e-3) / 1e12, "ffma_peak_tflops": ffma_peak,
+                                "frac_of_fp32_peak": fl / (t * 1e-3) / 1e12 / ffma_peak,
+                                "note": "SURVEY 8d's FP32-pipe count of the same work over the measured FFMA peak; above the FP32-pipe "
+                                        "kernel's 0.82 because the products left that pipe"},
+            "note": "the tensor pipe is NOT what limits this kernel (ncu sm__pipe_tensor_cycles_active 26 %): the epilogue is — "
+                    "4 KB of accumulators per warp and tile through tcgen05.ld plus 5 ALU/FMA instructions per pair on 8 warps "
+                    "(profiles/r02/score_mma_*_metrics.txt, DESIGN.md section 5)"}
+    else:
+        t = k_ms("score_kernel#0")
+        fl_exec = pairs_hc * flop_exec
+        roof["ransac_score"] = {"kernel": "score_kernel", "bound": "fp32-fma", "achieved": fl_exec / (t * 1e-3) / 1e12, "peak": ffma2_peak,
+                                "unit": "TFLOP/s", "frac": fl_exec / (t * 1e-3) / 1e12 / ffma2_peak, "ms": t,
+                                "peak_source": "packed fma.rn.f32x2 microbenchmark run in this process (the instruction the kernel issues); "
+                                               "scalar FFMA peak beside it", "ffma_scalar_peak_tflops": ffma_peak,
+                                "flop_per_pair_executed": flop_exec, "flop_per_pair_model": flop_pair,
+                                "model_frac": fl / (t * 1e-3) / 1e12 / ffma_peak,
+                                "note": "achieved = FLOPs the kernel executes (SASS count of the inner loop x pairs); ncu "
+                                        "sm__pipe_fma_cycles_active of the same kernel: profiles/r02/score_*_metrics.txt",
+                                "hypothesis_point_pairs": pairs_hc, "traffic": None}
     t = k_ms("stereo_geometry_kernel#0") + k_ms("stereo_compact_kernel#0")
     lt_bytes = 53.0 * float(buf["st_pair_count"].sum())
     roof["lift_triangulate"] = {"kernel": "stereo_geometry_kernel + stereo_compact_kernel", "bound": "hbm", "achieved": lt_bytes / (t * 1e-3) / 1e9,

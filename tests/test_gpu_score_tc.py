@@ -15,6 +15,7 @@ pytestmark = pytest.mark.gpu
 
 THR = 1.0 - np.cos(np.deg2rad(5.0))
 BAND_REL = 13.0 * 2.0 ** -20 + 5e-7      # csrc/score_mma.cuh
+B2_SHIFT = 1.52
 
 
 def rig_pair(rng):
@@ -62,7 +63,10 @@ def test_accumulators_within_a_quarter_of_the_band(ctx, with_rig):
             s, n2 = np.sum(f64 * x, axis=1), np.sum(x * x, axis=1)
             bvec = np.einsum("nji,nj->ni", r[ci, :, :3], (-t @ R)[None, :] - r[ci, :, 3])
             scale = np.sum(a64 * a64, axis=1) + np.sum(bvec * bvec, axis=1)
-            got_s, got_n = sn[b, h, :len(a), 0], sn[b, h, :len(a), 1]
+            # the n2 accumulator carries the hypothesis' band constant: N' = n2 + B2_SHIFT max_cam |b|^2 (score_mma.cuh)
+            ball = np.einsum("cji,j->ci", r[:, :, :3], -t @ R) - np.einsum("cji,cj->ci", r[:, :, :3], r[:, :, 3])
+            shift = B2_SHIFT * float(np.max(np.sum(ball * ball, axis=1)))
+            got_s, got_n = sn[b, h, :len(a), 0], sn[b, h, :len(a), 1] - shift
             D_true = s * np.abs(s) - c2 * n2
             D_got = got_s * np.abs(got_s) - c2 * got_n
             worst = max(worst, float(np.max(np.abs(D_got - D_true) / scale)))

@@ -256,6 +256,7 @@ __device__ void make_scoring_transforms(const double* M, const Rig& rig, HypRec&
     for (int j = 0; j < 3; ++j) Rt_[i * 3 + j] = M[j * 4 + i];
 #pragma unroll
   for (int i = 0; i < 3; ++i) bt[i] = -(Rt_[i * 3] * M[3] + Rt_[i * 3 + 1] * M[7] + Rt_[i * 3 + 2] * M[11]);
+  double Ad[RS_MAX_CAMS][9], bd[RS_MAX_CAMS][3], bmax2 = 0.0;
   for (int c = 0; c < RS_MAX_CAMS; ++c) {
     if (c >= rig.n_cams) {
 #pragma unroll
@@ -263,19 +264,20 @@ __device__ void make_scoring_transforms(const double* M, const Rig& rig, HypRec&
       continue;
     }
     const double* C = rig.Rt[c];  // x = Rc^T (y - tc)
-    double Ad[9], bd[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
 #pragma unroll
-      for (int j = 0; j < 3; ++j) Ad[i * 3 + j] = C[0 * 4 + i] * Rt_[0 * 3 + j] + C[1 * 4 + i] * Rt_[1 * 3 + j] + C[2 * 4 + i] * Rt_[2 * 3 + j];
-      bd[i] = C[0 * 4 + i] * (bt[0] - C[3]) + C[1 * 4 + i] * (bt[1] - C[7]) + C[2 * 4 + i] * (bt[2] - C[11]);
+      for (int j = 0; j < 3; ++j) Ad[c][i * 3 + j] = C[0 * 4 + i] * Rt_[0 * 3 + j] + C[1 * 4 + i] * Rt_[1 * 3 + j] + C[2 * 4 + i] * Rt_[2 * 3 + j];
+      bd[c][i] = C[0 * 4 + i] * (bt[0] - C[3]) + C[1 * 4 + i] * (bt[1] - C[7]) + C[2 * 4 + i] * (bt[2] - C[11]);
     }
 #pragma unroll
-    for (int i = 0; i < 9; ++i) rec.xf[c][i] = (float)Ad[i];
+    for (int i = 0; i < 9; ++i) rec.xf[c][i] = (float)Ad[c][i];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) rec.xf[c][9 + i] = (float)bd[i];
-    if (tc_tile) score_tc::emit_hyp_row(tc_tile + (size_t)c * score_tc::TILE_BYTES, tc_row, Ad, bd, true);
+    for (int i = 0; i < 3; ++i) rec.xf[c][9 + i] = (float)bd[c][i];
+    bmax2 = fmax(bmax2, bd[c][0] * bd[c][0] + bd[c][1] * bd[c][1] + bd[c][2] * bd[c][2]);
   }
+  if (tc_tile)
+    for (int c = 0; c < rig.n_cams; ++c) score_tc::emit_hyp_row(tc_tile + (size_t)c * score_tc::TILE_BYTES, tc_row, Ad[c], bd[c], bmax2, true);
 }
 
 // a failed model: NaN never passes the inlier test
@@ -288,7 +290,7 @@ __device__ void make_failed_model(const Rig& rig, HypRec& rec, uint8_t* tc_tile,
   for (int c = 0; c < RS_MAX_CAMS; ++c) {
 #pragma unroll
     for (int i = 0; i < 12; ++i) rec.xf[c][i] = CUDART_NAN_F;
-    if (tc_tile && c < rig.n_cams) score_tc::emit_hyp_row(tc_tile + (size_t)c * score_tc::TILE_BYTES, tc_row, nullptr, nullptr, false);
+    if (tc_tile && c < rig.n_cams) score_tc::emit_hyp_row(tc_tile + (size_t)c * score_tc::TILE_BYTES, tc_row, nullptr, nullptr, 0.0, false);
   }
 }
 

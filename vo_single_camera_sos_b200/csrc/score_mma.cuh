@@ -18,14 +18,16 @@
 //     hypothesis tile exists once per camera, and each correspondence tile too (rows of the other camera are zero); a tile
 //     that mixes cameras simply runs both MMAs into the same accumulator;
 //   * an epilogue thread owns one hypothesis (= TMEM lane), reads 32 pairs of (s, n2) with tcgen05.ld and per pair does
-//     two FFMA (s|s| -+ the absolute part of the band), one packed FFMA2 per two pairs for each of t = D - band and
+//     one FFMA (s|s| + a constant of the hypothesis), one packed FFMA2 per two pairs for each of t = D - band and
 //     u = D + band, and two SHF that collect their sign bits; 32 pairs are counted with one POPC.
 // Exactness: a band bounds the error of D from the split, the accumulation and the two float32 operations:
 // |err D| <= BAND_REL (|p|^2 + |b|^2) (measured on every pair of the test problems by tests/test_gpu_score_tc.py through the
 // PROBE instantiation: 1.4e-6, BAND_REL is 9 x that).  Since x = A p + b with A orthogonal, |p|^2 <= 2 n2 + 2 |b|^2, so the
-// band is at most BETA n2 + G_h with BETA = 2 BAND_REL and G_h = 3 BAND_REL |b_h|^2 — relative to the pair's own n2 plus a
-// constant of the hypothesis, which fold into the FFMA constants: t = (s|s| - G_h) - (c^2 + BETA) n2 >= 0 is a certain
-// inlier, u = (s|s| + G_h) - (c^2 - BETA) n2 < 0 a certain outlier.  The uncertain pairs of a chunk
+// band is at most BETA n2 + G_h with BETA = 2 BAND_REL and G_h = 3 BAND_REL |b_h|^2 = BETA * 1.5 |b_h|^2.  The constant of
+// the hypothesis rides through the MMA: the n2 GEMM delivers N' = n2 + 1.5 |b_h|^2 (added to the hypothesis feature that
+// multiplies the correspondence's constant 1), so the band is BETA N' and D = (s|s| + c^2 1.5 |b_h|^2) - c^2 N':
+// t = w - (c^2 + BETA) N' >= 0 is a certain inlier, u = w - (c^2 - BETA) N' < 0 a certain outlier, with
+// w = s|s| + K_h one FFMA.  The uncertain pairs of a chunk
 // (bit mask) are queued and re-decided after the item by the scalar float32 path with ITS rigorous guard and, inside that,
 // by inlier_exact() in float64 — the same deferred path score_kernel uses — so every count equals the float64 oracle's.
 // (ransac.cu includes <cuda_bf16.h> and "tc_common.cuh" at file scope before this.)
@@ -50,7 +52,8 @@ constexpr float PAD_N2 = 1e30f;                 // n2 feature of a padding corre
 // |err D| <= BAND_REL (|p|^2 + max_cam |b|^2): 13 eps + 5e-7 with eps = 2^-20 for the relative error of an accumulated term
 // sum (tests/test_gpu_score_tc.py measures 1.4e-6 for the whole expression and asserts a 4x margin)
 constexpr float BAND_REL = 13.0f * 9.5367431640625e-07f + 5e-7f;
-constexpr float BETA = 2.02f * BAND_REL, BAND_B2 = 3.03f * BAND_REL;   // band <= BETA n2 + BAND_B2 |b|^2
+constexpr float BETA = 2.02f * BAND_REL;        // band <= BETA (n2 + B2_SHIFT |b|^2)
+constexpr double B2_SHIFT = 1.52;               // (3 / 2 of the derivation, padded for the float32 rounding of |b|^2 in the epilogue)
 
 struct TileMeta {
   uint32_t cam_mask;   // bit c: the tile holds correspondences of camera c
@@ -95,8 +98,10 @@ __device__ __forceinline__ void write_row(uint8_t* __restrict__ tile, int r, con
     *(uint4*)(row + c * 128) = make_uint4(e[4 * c], e[4 * c + 1], e[4 * c + 2], e[4 * c + 3]);
 }
 
-// Hypothesis side, called by the hypothesize kernels: Ad (3x3 row-major) and bd of camera c in float64.
-__device__ __forceinline__ void emit_hyp_row(uint8_t* __restrict__ tile, int r, const double* Ad, const double* bd, bool ok) {
+// Hypothesis side, called by the hypothesize kernels: Ad (3x3 row-major) and bd of camera c in float64; bmax2 = the largest
+// |b|^2 over the cameras of the rig (the band constant must not depend on the camera of the correspondence).
+__device__ __forceinline__ void emit_hyp_row(uint8_t* __restrict__ tile, int r, const double* Ad, const double* bd, double bmax2,
+                                             bool ok) {
   float fs[KS], fn[KN];
   if (ok) {
 #pragma unroll
@@ -108,7 +113,7 @@ __device__ __forceinline__ void emit_hyp_row(uint8_t* __restrict__ tile, int r, 
     fn[3] = (float)G(0, 1); fn[4] = (float)G(0, 2); fn[5] = (float)G(1, 2);
 #pragma unroll
     for (int k = 0; k < 3; ++k) fn[6 + k] = (float)(Ad[k] * bd[0] + Ad[3 + k] * bd[1] + Ad[6 + k] * bd[2]);
-    fn[9] = (float)(bd[0] * bd[0] + bd[1] * bd[1] + bd[2] * bd[2]);
+    fn[9] = (float)(bd[0] * bd[0] + bd[1] * bd[1] + bd[2] * bd[2] + B2_SHIFT * bmax2);   // N' = n2 + B2_SHIFT max |b|^2
   } else {
     // failed model: NaN accumulators never land inside the band (no deferred work) and its count stays hugely negative
 #pragma unroll
@@ -196,7 +201,7 @@ struct Args {
   const float *p_ref, *f_cur;
   const uint8_t* cam;
   ScoreConst k;
-  float* probe;          // PROBE: (s, n2) of every pair, [problem][hypothesis][ct * 128][2]
+  float* probe;          // PROBE: (s, N') of every pair, [problem][hypothesis][ct * 128][2]
 };
 
 // one deferred pair, decided exactly like score_kernel's deferred pass
@@ -274,44 +279,52 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint8_t* ga = a.a_exp + ((size_t)((size_t)b * a.ht + ht) * 2) * TILE_BYTES;
+    // producer: the whole warp walks the tiles (camera masks prefetched one tile ahead: a dependent global load per tile in
+    // this loop held the ring back), the elected lane issues the copies
+    const uint8_t* ga = a.a_exp + ((size_t)((size_t)b * a.ht + ht) * 2) * TILE_BYTES;
+    if (elect_one()) {
       mbar_expect_tx(BAR(AFULL), 2u * TILE_BYTES);
 #pragma unroll
       for (int p = 0; p < 8; ++p) bulk_g2s(smem_u32(sA) + p * (TILE_BYTES / 4), ga + (size_t)p * (TILE_BYTES / 4), TILE_BYTES / 4, BAR(AFULL));
-      uint32_t t = 0;
-      for (int k = k_begin; k < k_end; ++k) {
-        const uint32_t mask = meta[k].cam_mask;
-        for (int c = 0; c < 2; ++c) {
-          if (!((mask >> c) & 1u)) continue;
-          const uint32_t s = t % STAGES;
-          mbar_wait(BAR(EMPTY + s), ((t / STAGES) & 1) ^ 1);
+    }
+    uint32_t t = 0;
+    uint32_t mask = meta[k_begin].cam_mask;
+    for (int k = k_begin; k < k_end; ++k) {
+      const uint32_t mask_next = meta[min(k + 1, k_end - 1)].cam_mask;
+      for (int c = 0; c < 2; ++c) {
+        if (!((mask >> c) & 1u)) continue;
+        const uint32_t s = t % STAGES;
+        mbar_wait(BAR(EMPTY + s), ((t / STAGES) & 1) ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(BAR(FULL + s), TILE_BYTES);
           const uint8_t* gb = a.b_exp + ((size_t)(((size_t)b * a.ct + k) * 2 + c)) * TILE_BYTES;
           const uint32_t dst = smem_u32(sB) + s * TILE_BYTES;
 #pragma unroll
           for (int p = 0; p < 4; ++p) bulk_g2s(dst + p * (TILE_BYTES / 4), gb + (size_t)p * (TILE_BYTES / 4), TILE_BYTES / 4, BAR(FULL + s));
-          ++t;
         }
+        __syncwarp();
+        ++t;
       }
+      mask = mask_next;
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(BAR(AFULL), 0);
-      uint32_t t = 0, it = 0;
-      for (int k = k_begin; k < k_end; ++k, ++it) {
-        const uint32_t mask = meta[k].cam_mask;
-        const uint32_t buf = it & 1;
-        mbar_wait(BAR(TEMPTY + buf), ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator pair
-        uint32_t acc = 0;
-        for (int c = 0; c < 2; ++c) {
-          if (!((mask >> c) & 1u)) continue;
-          const uint32_t s = t % STAGES;
-          mbar_wait(BAR(FULL + s), (t / STAGES) & 1);
-          tc_fence_after();
-          const uint64_t da = smem_desc(smem_u32(sA) + c * TILE_BYTES, GROUP_BYTES);
-          const uint64_t db = smem_desc(smem_u32(sB) + s * TILE_BYTES, GROUP_BYTES);
+    // MMA issuer: converged warp, elected lane (see elect_one)
+    mbar_wait(BAR(AFULL), 0);
+    uint32_t t = 0, it = 0;
+    uint32_t mask = meta[k_begin].cam_mask;
+    for (int k = k_begin; k < k_end; ++k, ++it) {
+      const uint32_t mask_next = meta[min(k + 1, k_end - 1)].cam_mask;
+      const uint32_t buf = it & 1;
+      mbar_wait(BAR(TEMPTY + buf), ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator pair
+      uint32_t acc = 0;
+      for (int c = 0; c < 2; ++c) {
+        if (!((mask >> c) & 1u)) continue;
+        const uint32_t s = t % STAGES;
+        mbar_wait(BAR(FULL + s), (t / STAGES) & 1);
+        tc_fence_after();
+        const uint64_t da = smem_desc(smem_u32(sA) + c * TILE_BYTES, GROUP_BYTES);
+        const uint64_t db = smem_desc(smem_u32(sB) + s * TILE_BYTES, GROUP_BYTES);
+        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < ES / 16; ++kk)
             tc_mma<KIND_L2>(tmem + buf * 256, da + (uint64_t)(16 * kk), db + (uint64_t)(16 * kk), IDESC, acc | (kk > 0));
@@ -319,13 +332,15 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
           for (int kk = ES / 16; kk < (ES + EN) / 16; ++kk)
             tc_mma<KIND_L2>(tmem + buf * 256 + TILE, da + (uint64_t)(16 * kk), db + (uint64_t)(16 * kk), IDESC, acc | (kk > ES / 16));
           tc_commit(BAR(EMPTY + s));
-          acc = 1;
-          ++t;
         }
-        tc_commit(BAR(TFULL + buf));
+        __syncwarp();
+        acc = 1;
+        ++t;
       }
+      if (elect_one()) tc_commit(BAR(TFULL + buf));
+      __syncwarp();
+      mask = mask_next;
     }
-    __syncwarp();
   } else if (warp >= 4) {
     const int g = (warp - 4) >> 2, quarter = warp & 3;   // a warp may only touch the TMEM lanes of its quarter
     const int row = quarter * 32 + lane;
@@ -339,7 +354,7 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
         bmax2 = fmaxf(bmax2, bx * bx + by * by + bz * bz);
       }
     }
-    const float Gh = BAND_B2 * bmax2;
+    const float Kh = a.k.cos_min_sq * (float)B2_SHIFT * bmax2;   // D = (s|s| + Kh) - c^2 N'
     const float2 ka = make_float2(-(a.k.cos_min_sq + BETA), -(a.k.cos_min_sq + BETA));
     const float2 kb = make_float2(-(a.k.cos_min_sq - BETA), -(a.k.cos_min_sq - BETA));
     int cnt = 0;
@@ -363,9 +378,8 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
           const float s0 = __int_as_float(S[i]), s1 = __int_as_float(S[i + 1]);
           const float2 n2 = make_float2(__int_as_float(N[i]), __int_as_float(N[i + 1]));
           // s|s| folds the s > 0 test into D
-          const float2 wt = make_float2(__fmaf_rn(s0, fabsf(s0), -Gh), __fmaf_rn(s1, fabsf(s1), -Gh));
-          const float2 wu = make_float2(__fmaf_rn(s0, fabsf(s0), Gh), __fmaf_rn(s1, fabsf(s1), Gh));
-          const float2 t = pk_ffma2(n2, ka, wt), u = pk_ffma2(n2, kb, wu);
+          const float2 w = make_float2(__fmaf_rn(s0, fabsf(s0), Kh), __fmaf_rn(s1, fabsf(s1), Kh));
+          const float2 t = pk_ffma2(n2, ka, w), u = pk_ffma2(n2, kb, w);
           mt = __funnelshift_l(__float_as_uint(t.x), mt, 1);
           mt = __funnelshift_l(__float_as_uint(t.y), mt, 1);
           mu = __funnelshift_l(__float_as_uint(u.x), mu, 1);

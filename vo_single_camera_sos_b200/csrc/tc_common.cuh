@@ -30,6 +30,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// One lane of a CONVERGED warp (elect.sync).  Code that issues tcgen05.mma / cp.async.bulk from `if (lane == 0)` is compiled
+// as divergent code: every instruction with uniform-register operands (UTCHMMA, UBLKCP, UTCBAR) gets wrapped in an
+// elect + broadcast loop of ~13 instructions, which made the issuing thread — not the tensor pipe — the bound (83 cycles per
+// 64-cycle MMA, measured with clock64 stamps).  With the whole warp running the loop and only the instruction itself
+// predicated on the elected lane the operands are warp-uniform by construction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t p;
+  asm volatile("{ .reg .pred p; elect.sync _|p, 0xFFFFFFFF; selp.u32 %0, 1, 0, p; }" : "=r"(p));
+  return p != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
