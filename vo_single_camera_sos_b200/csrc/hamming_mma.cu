@@ -216,51 +216,57 @@ __global__ void __launch_bounds__(THREADS, 1) mma_kernel(Args a) {
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t t = 0, ic = 0;
-      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-        const Item it = decode_item(a, a.items[w]);
-        if (it.n_iter <= 0) continue;
-        const uint8_t* gb = a.b_exp + ((size_t)it.seg * a.t_tiles_per_seg + it.tile_begin) * TILE_BYTES;
-        auto load_b = [&](int k) {
-          const uint32_t s = t % STAGES;
-          mbar_wait(BAR(EMPTY + s), ((t / STAGES) & 1) ^ 1);
+    // producer: the whole (converged) warp walks the items, the elected lane issues the copies (tc_common.cuh: elect_one)
+    uint32_t t = 0, ic = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const Item it = decode_item(a, a.items[w]);
+      if (it.n_iter <= 0) continue;
+      const uint8_t* gb = a.b_exp + ((size_t)it.seg * a.t_tiles_per_seg + it.tile_begin) * TILE_BYTES;
+      auto load_b = [&](int k) {
+        const uint32_t s = t % STAGES;
+        mbar_wait(BAR(EMPTY + s), ((t / STAGES) & 1) ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(BAR(FULL + s), TILE_BYTES);
           const uint32_t dst = smem_u32(sB) + s * TILE_BYTES;
 #pragma unroll
           for (int p = 0; p < 4; ++p)
             bulk_g2s(dst + p * (TILE_BYTES / 4), gb + (size_t)k * TILE_BYTES + (size_t)p * (TILE_BYTES / 4), TILE_BYTES / 4, BAR(FULL + s));
-          ++t;
-        };
-        // the first train tiles of this item go into the ring as soon as stages free up, i.e. while the previous item is still
-        // being multiplied; only then wait for the tensor core to be done with the previous item's query tiles and fetch ours
-        const int pre = min(it.n_iter, STAGES);
-        for (int k = 0; k < pre; ++k) load_b(k);
-        mbar_wait(BAR(AEMPTY), (ic & 1) ^ 1);
-        const uint8_t* ga = a.a_exp + ((size_t)it.seg * a.q_tiles_per_seg + (size_t)it.q_tile * 2) * TILE_BYTES;
+        }
+        __syncwarp();
+        ++t;
+      };
+      // the first train tiles of this item go into the ring as soon as stages free up, i.e. while the previous item is still
+      // being multiplied; only then wait for the tensor core to be done with the previous item's query tiles and fetch ours
+      const int pre = min(it.n_iter, STAGES);
+      for (int k = 0; k < pre; ++k) load_b(k);
+      mbar_wait(BAR(AEMPTY), (ic & 1) ^ 1);
+      const uint8_t* ga = a.a_exp + ((size_t)it.seg * a.q_tiles_per_seg + (size_t)it.q_tile * 2) * TILE_BYTES;
+      if (elect_one()) {
         mbar_expect_tx(BAR(AFULL), 2u * TILE_BYTES);
 #pragma unroll
         for (int p = 0; p < 8; ++p) bulk_g2s(smem_u32(sA) + p * (TILE_BYTES / 4), ga + (size_t)p * (TILE_BYTES / 4), TILE_BYTES / 4, BAR(AFULL));
-        ++ic;
-        for (int k = pre; k < it.n_iter; ++k) load_b(k);
       }
+      __syncwarp();
+      ++ic;
+      for (int k = pre; k < it.n_iter; ++k) load_b(k);
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint64_t da0 = smem_desc(smem_u32(sA)), da1 = smem_desc(smem_u32(sA) + TILE_BYTES);
-      uint32_t t = 0, ic = 0;
-      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-        const Item it = decode_item(a, a.items[w]);
-        if (it.n_iter <= 0) continue;
-        mbar_wait(BAR(AFULL), ic & 1);
-        ++ic;
-        for (int k = 0; k < it.n_iter; ++k, ++t) {
-          const uint32_t s = t % STAGES, b = t & 1;
-          mbar_wait(BAR(TEMPTY + b), ((t >> 1) & 1) ^ 1);    // the epilogue has drained this accumulator buffer
-          mbar_wait(BAR(FULL + s), (t / STAGES) & 1);        // the train tile has landed
-          tc_fence_after();
-          const uint64_t db = smem_desc(smem_u32(sB) + s * TILE_BYTES);
+    // MMA issuer: converged warp, elected lane — issued from `if (lane == 0)` every tcgen05.mma was wrapped in an
+    // elect / broadcast loop of ~13 instructions and the issuing thread, not the tensor pipe, set the pace
+    const uint64_t da0 = smem_desc(smem_u32(sA)), da1 = smem_desc(smem_u32(sA) + TILE_BYTES);
+    uint32_t t = 0, ic = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const Item it = decode_item(a, a.items[w]);
+      if (it.n_iter <= 0) continue;
+      mbar_wait(BAR(AFULL), ic & 1);
+      ++ic;
+      for (int k = 0; k < it.n_iter; ++k, ++t) {
+        const uint32_t s = t % STAGES, b = t & 1;
+        mbar_wait(BAR(TEMPTY + b), ((t >> 1) & 1) ^ 1);    // the epilogue has drained this accumulator buffer
+        mbar_wait(BAR(FULL + s), (t / STAGES) & 1);        // the train tile has landed
+        tc_fence_after();
+        const uint64_t db = smem_desc(smem_u32(sB) + s * TILE_BYTES);
+        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < KB / 32; ++kk)
             tc_mma<KIND>(tmem + (b * 2) * TILE, da0 + (uint64_t)(16 * kk), db + (uint64_t)(16 * kk), KIND == KIND_L2 ? IDESC_L2 : IDESC, kk > 0);
@@ -270,10 +276,11 @@ __global__ void __launch_bounds__(THREADS, 1) mma_kernel(Args a) {
           tc_commit(BAR(EMPTY + s));    // shared-memory stage free once these MMAs have read it
           tc_commit(BAR(TFULL + b));    // accumulators complete
         }
-        tc_commit(BAR(AEMPTY));         // every MMA of this item has read the query tiles
+        __syncwarp();
       }
+      if (elect_one()) tc_commit(BAR(AEMPTY));         // every MMA of this item has read the query tiles
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp >= 4) {
     const int g = (warp - 4) >> 2, quarter = warp & 3;   // a warp may only touch the TMEM lanes of its quarter
     uint32_t t = 0;

@@ -44,7 +44,12 @@ constexpr int CHUNKS = KB / 16;                 // 18 core-matrix columns
 constexpr int GROUP_BYTES = CHUNKS * 128;       // one 8-row group
 constexpr int TILE_BYTES = (TILE / 8) * GROUP_BYTES;   // 36864
 constexpr int STAGES = 3;
-constexpr int THREADS = 384;
+constexpr int EPI_WARPS = 16;                   // warps 0..15: epilogue, 4 per SM sub-partition
+// The warp schedulers prefer the HIGHEST warp id, so the latency-critical single-issue roles sit above the epilogue warps:
+// as warps 0 and 1 below 16 busy epilogue warps they were starved (clock64 stamps: 780 cycles to issue four bulk copies,
+// 890 cycles for a try_wait on an already completed barrier).
+constexpr int W_PRODUCER = EPI_WARPS, W_MMA = EPI_WARPS + 1, W_ALLOC = EPI_WARPS + 2;
+constexpr int THREADS = (EPI_WARPS + 3) * 32;
 constexpr int ECAP = 1536;                      // chunks with uncertain pairs per work item held in shared memory (entry + bit mask)
 constexpr int PCAP = 2048;                      // uncertain pairs expanded per round of the deferred pass
 constexpr int SMEM_BYTES = (2 + STAGES) * TILE_BYTES + 256 + ECAP * 8 + PCAP * 4 + TILE * 4;
@@ -230,10 +235,10 @@ __device__ __forceinline__ float2 pk_ffma2(float2 x, float2 y, float2 z) {
 }
 
 // Work item = (problem, 128 hypotheses, a range of correspondence tiles); one CTA per item, warp-specialised like the
-// Hamming engine: warp 0 streams the two hypothesis tiles (one per camera) and a ring of correspondence tiles with
-// cp.async.bulk, one lane of warp 1 issues 5 + 4 tcgen05.mma (M128 N128 K16) per (tile, camera) into a double-buffered
-// accumulator pair (s: 128 columns, n2: 128 columns; 2 buffers = all 512 TMEM columns), warps 4..11 are the epilogue:
-// warp group g takes correspondences [64 g, 64 g + 64) of every tile.
+// Hamming engine: the producer warp streams the two hypothesis tiles (one per camera) and a ring of correspondence tiles
+// with cp.async.bulk, one lane of the MMA warp issues 5 + 4 tcgen05.mma (M128 N128 K16) per (tile, camera) into a double-buffered
+// accumulator pair (s: 128 columns, n2: 128 columns; 2 buffers = all 512 TMEM columns), warps 0..15 are the epilogue:
+// warp group g takes the 32-pair chunk g of every tile.
 template <bool PROBE>
 __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, const __grid_constant__ Rig rig) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -263,13 +268,13 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
   if (tid == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1); }
     mbar_init(BAR(TFULL), 1); mbar_init(BAR(TFULL + 1), 1);
-    mbar_init(BAR(TEMPTY), 8); mbar_init(BAR(TEMPTY + 1), 8);
+    mbar_init(BAR(TEMPTY), EPI_WARPS); mbar_init(BAR(TEMPTY + 1), EPI_WARPS);
     mbar_init(BAR(AFULL), 1);
     *q_n = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < TILE) fixcnt[tid] = 0;
-  if (warp == 2) {
+  if (warp == W_ALLOC) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -278,7 +283,7 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == W_PRODUCER) {
     // producer: the whole warp walks the tiles (camera masks prefetched one tile ahead: a dependent global load per tile in
     // this loop held the ring back), the elected lane issues the copies
     const uint8_t* ga = a.a_exp + ((size_t)((size_t)b * a.ht + ht) * 2) * TILE_BYTES;
@@ -307,7 +312,7 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
       }
       mask = mask_next;
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     // MMA issuer: converged warp, elected lane (see elect_one)
     mbar_wait(BAR(AFULL), 0);
     uint32_t t = 0, it = 0;
@@ -341,8 +346,8 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
       __syncwarp();
       mask = mask_next;
     }
-  } else if (warp >= 4) {
-    const int g = (warp - 4) >> 2, quarter = warp & 3;   // a warp may only touch the TMEM lanes of its quarter
+  } else if (warp < EPI_WARPS) {
+    const int g = warp >> 2, quarter = warp & 3;   // a warp may only touch the TMEM lanes of its quarter
     const int row = quarter * 32 + lane;
     const int h = ht * TILE + row;
     const bool valid_h = h < a.n_hyp;
@@ -363,14 +368,15 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
       const uint32_t buf = it & 1;
       mbar_wait(BAR(TFULL + buf), (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * 256 + g * 64;
-      int sv[32], nv[32], sw[32], nw[32];
+      const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + buf * 256 + g * 32;
+      int sv[32], nv[32];
       tmem_ld32(taddr, sv);
       tmem_ld32(taddr + TILE, nv);
       tmem_ld_wait(sv);
       tmem_ld_wait(nv);
-      tmem_ld32(taddr + 32, sw);            // in flight while the first chunk is classified
-      tmem_ld32(taddr + TILE + 32, nw);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(TEMPTY + buf));     // this warp's share of the accumulator pair is in registers
       auto classify = [&](const int (&S)[32], const int (&N)[32], int chunk) {
         uint32_t mt = 0, mu = 0;       // sign bits of t and u: pair i ends up in bit 31 - i
 #pragma unroll
@@ -403,23 +409,17 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
           }
         }
       };
-      classify(sv, nv, 2 * g);
-      tmem_ld_wait(sw);
-      tmem_ld_wait(nw);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(TEMPTY + buf));     // the accumulator pair may be overwritten
-      classify(sw, nw, 2 * g + 1);
+      classify(sv, nv, g);
     }
     // deferred pass over the uncertain pairs, all 256 epilogue threads: expand the chunk masks into a pair list (in rounds
     // of PCAP pairs), one thread per pair
-    const int te = tid - 4 * 32;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const int te = tid;
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
     const int nq = min(*q_n, ECAP);
     for (bool more = nq > 0; more;) {
       if (te == 0) *p_n = 0;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int e = te; e < nq; e += 256) {
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      for (int e = te; e < nq; e += EPI_WARPS * 32) {
         uint32_t m = qmask[e];
         while (m) {
           const int slot = atomicAdd(p_n, 1);
@@ -430,22 +430,22 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
         }
         qmask[e] = m;
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
       const int np = *p_n;
-      for (int x = te; x < min(np, PCAP); x += 256) {
+      for (int x = te; x < min(np, PCAP); x += EPI_WARPS * 32) {
         const uint32_t v = pairs[x], ent = qent[v >> 5];
         const int k = (int)(ent >> 9), chunk = (int)((ent >> 7) & 3u), r = (int)(ent & 127u);
         if (exact_pair(a, rig, b, ht * TILE + r, k * TILE + chunk * 32 + (int)(v & 31u), n)) atomicAdd(&fixcnt[r], 1);
       }
       more = np > PCAP;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
     }
     if (g == 0) cnt += fixcnt[row];
     if (valid_h && cnt != 0) atomicAdd(&a.counts[(size_t)b * a.n_hyp + h], cnt);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  if (warp == W_ALLOC) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
 inline size_t scratch_bytes(int n_problems, int n_hyp, int cap) {
