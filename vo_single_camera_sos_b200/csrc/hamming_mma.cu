@@ -58,27 +58,45 @@ __device__ __forceinline__ uint32_t expand4(uint32_t nib) {
 
 // role 0: query rows (A operand), role 1: train rows (B operand).  Tile t of segment s lives at
 // out + (s * tiles_per_seg + t) * TILE_BYTES; byte (row r, k) of a tile at (r / 8) * GROUP_BYTES + (k / 16) * 128 + (r % 8) * 16 + k % 16.
+// One launch expands both roles (blockIdx.z); the nine 16-byte units of a thread are independent, so the loop is unrolled
+// and all descriptor loads are in flight before the first store (the rolled loop was latency bound: 4 x 27 us per step).
+struct ExpandArgs {
+  const uint32_t* desc[2];
+  const int32_t *start[2], *len[2];
+  int max_rows[2], tiles_per_seg[2];
+  uint8_t* out[2];
+};
+
 __global__ void __launch_bounds__(256)
-expand_kernel(const uint32_t* __restrict__ desc, const int32_t* __restrict__ start, const int32_t* __restrict__ len,
-              int max_rows, int tiles_per_seg, int role, uint8_t* __restrict__ out) {
-  const int seg = blockIdx.y, tile = blockIdx.x;
-  const int n = min(len[seg], max_rows);
+expand_kernel(const ExpandArgs a) {
+  const int role = blockIdx.z, seg = blockIdx.y, tile = blockIdx.x;
+  if (tile >= a.tiles_per_seg[role]) return;
+  const int n = min(a.len[role][seg], a.max_rows[role]);
   const int row0 = tile * TILE;
   if (row0 >= n) return;
-  const uint32_t* d = desc + (size_t)start[seg] * 8;
-  uint8_t* tbase = out + ((size_t)seg * tiles_per_seg + tile) * TILE_BYTES;
-  for (int u = threadIdx.x; u < TILE * CHUNKS; u += 256) {
+  const uint32_t* d = a.desc[role] + (size_t)a.start[role][seg] * 8;
+  uint8_t* tbase = a.out[role] + ((size_t)seg * a.tiles_per_seg[role] + tile) * TILE_BYTES;
+  constexpr int UNITS = TILE * CHUNKS / 256;   // 9
+  uint32_t bits[UNITS];
+#pragma unroll
+  for (int it = 0; it < UNITS; ++it) {
+    const int u = threadIdx.x + it * 256;
+    const int r8 = u & 7, chunk = (u >> 3) % CHUNKS, rg = u / (8 * CHUNKS);
+    const int row = row0 + rg * 8 + r8;
+    bits[it] = (chunk < 16 && row < n) ? (__ldg(d + (size_t)row * 8 + (chunk >> 1)) >> ((chunk & 1) * 16)) & 0xFFFFu : 0u;
+  }
+#pragma unroll
+  for (int it = 0; it < UNITS; ++it) {
+    const int u = threadIdx.x + it * 256;
     const int r8 = u & 7, chunk = (u >> 3) % CHUNKS, rg = u / (8 * CHUNKS);
     const int r = rg * 8 + r8, row = row0 + r;
     const bool valid = row < n;
     uint4 v;
     if (chunk < 16) {
-      uint32_t bits = 0;
-      if (valid) bits = (__ldg(d + (size_t)row * 8 + (chunk >> 1)) >> ((chunk & 1) * 16)) & 0xFFFFu;
-      v.x = expand4(bits & 15u);
-      v.y = expand4((bits >> 4) & 15u);
-      v.z = expand4((bits >> 8) & 15u);
-      v.w = expand4(bits >> 12);
+      v.x = expand4(bits[it] & 15u);
+      v.y = expand4((bits[it] >> 4) & 15u);
+      v.z = expand4((bits[it] >> 8) & 15u);
+      v.w = expand4(bits[it] >> 12);
       if (!valid) v = make_uint4(0u, 0u, 0u, 0u);          // padding rows: <s_q, s_t> = 0
     } else if (role == 0) {
       v = make_uint4(0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x7F7F7F7Fu);
@@ -437,12 +455,12 @@ int sos_hamming_mma_launch(sos_ctx* ctx, const uint32_t* q, const uint32_t* t, c
   const int qt = ((max_nq + 255) / 256) * 2, tt = (max_nt + TILE - 1) / TILE;
   uint8_t* a_exp = (uint8_t*)exp;
   uint8_t* b_exp = a_exp + (size_t)n_seg * qt * TILE_BYTES;
-  if (qt > 0) {
-    expand_kernel<<<dim3(qt, n_seg), 256, 0, ctx->stream>>>(q, q_start, q_len, max_nq, qt, 0, a_exp);
-    SOS_LAUNCHED_AS(ctx, "hamming_expand_kernel");
-  }
-  if (tt > 0) {
-    expand_kernel<<<dim3(tt, n_seg), 256, 0, ctx->stream>>>(t, t_start, t_len, max_nt, tt, 1, b_exp);
+  if (qt > 0 || tt > 0) {
+    ExpandArgs e;
+    e.desc[0] = q; e.desc[1] = t; e.start[0] = q_start; e.start[1] = t_start; e.len[0] = q_len; e.len[1] = t_len;
+    e.max_rows[0] = max_nq; e.max_rows[1] = max_nt; e.tiles_per_seg[0] = qt; e.tiles_per_seg[1] = tt;
+    e.out[0] = a_exp; e.out[1] = b_exp;
+    expand_kernel<<<dim3(qt > tt ? qt : tt, n_seg, 2), 256, 0, ctx->stream>>>(e);
     SOS_LAUNCHED_AS(ctx, "hamming_expand_kernel");
   }
   Args a;

@@ -135,7 +135,6 @@ __global__ void __launch_bounds__(TILE)
 corr_expand_kernel(const float* __restrict__ p_ref, const float* __restrict__ f_cur, const uint8_t* __restrict__ cam,
                    const int32_t* __restrict__ n_arr, int cap, int n_cams, int ct, uint8_t* __restrict__ b_exp,
                    TileMeta* __restrict__ meta) {
-  __shared__ uint32_t wmask[TILE / 32];
   const int b = blockIdx.y, tile = blockIdx.x, r = threadIdx.x;
   const int n = min(n_arr[b], cap);
   if (tile * TILE >= n) return;
@@ -166,6 +165,8 @@ corr_expand_kernel(const float* __restrict__ p_ref, const float* __restrict__ f_
       fn[9] = 1.f;
     }
   }
+  // which cameras the tile holds (the MMA kernel never reads the tile of an absent camera, so it is not written either)
+  const uint32_t mask = (uint32_t)__syncthreads_or((j < n && c == 0) ? 1 : 0) | ((uint32_t)__syncthreads_or((j < n && c == 1) ? 1 : 0) << 1);
   uint8_t* t0 = b_exp + ((size_t)((size_t)b * ct + tile) * 2) * TILE_BYTES;
   float zs[KS], zn[KN];
 #pragma unroll
@@ -179,16 +180,10 @@ corr_expand_kernel(const float* __restrict__ p_ref, const float* __restrict__ f_
     zn[0] = PAD_N2;
   }
   write_row<1>(t0 + (size_t)c * TILE_BYTES, r, fs, fn);
-  write_row<1>(t0 + (size_t)(c ^ 1) * TILE_BYTES, r, zs, zn);
-  // tile meta
-  uint32_t mask = (j < n) ? (1u << c) : 0u;
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) mask |= __shfl_xor_sync(0xFFFFFFFFu, mask, off);
-  if ((r & 31) == 0) wmask[r >> 5] = mask;
-  __syncthreads();
+  if ((mask >> (c ^ 1)) & 1u) write_row<1>(t0 + (size_t)(c ^ 1) * TILE_BYTES, r, zs, zn);
   if (r == 0) {
     TileMeta m;
-    m.cam_mask = wmask[0] | wmask[1] | wmask[2] | wmask[3];
+    m.cam_mask = mask;
     meta[(size_t)b * ct + tile] = m;
   }
 }
