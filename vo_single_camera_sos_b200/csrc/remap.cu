@@ -426,7 +426,9 @@ remap3b_kernel(const uint8_t* __restrict__ src, int batch, int frames_per_block,
           const uint32_t* p = (const uint32_t*)(s + off[pass] + (row ? row_bytes : 0u));
           ta[pass][row][0] = __ldg(p);
           ta[pass][row][1] = __ldg(p + 1);
-          ta[pass][row][2] = __ldg(p + 2);
+          // the six bytes reach into the third word only when they start at byte 3 of the window (a quarter of the taps): the
+          // predicated load touches fewer distinct lines per request, and wavefronts per line are what the L1 pipe counts
+          ta[pass][row][2] = sh[pass] == 24u ? __ldg(p + 2) : 0u;
         }
       }
 #pragma unroll
