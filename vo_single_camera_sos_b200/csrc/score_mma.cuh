@@ -48,8 +48,11 @@ constexpr int EPI_WARPS = 16;                   // warps 0..15: epilogue, 4 per 
 // The warp schedulers prefer the HIGHEST warp id, so the latency-critical single-issue roles sit above the epilogue warps:
 // as warps 0 and 1 below 16 busy epilogue warps they were starved (clock64 stamps: 780 cycles to issue four bulk copies,
 // 890 cycles for a try_wait on an already completed barrier).
-constexpr int W_PRODUCER = EPI_WARPS, W_MMA = EPI_WARPS + 1, W_ALLOC = EPI_WARPS + 2;
-constexpr int THREADS = (EPI_WARPS + 3) * 32;
+// Two MMA-issuing warps (on different sub-partitions): one owns the s accumulator (5 instructions per tile and camera), the
+// other the n2 accumulator (4) — the issue loop of a single warp, competing with four busy epilogue warps for issue slots,
+// took ~1800 cycles per tile for 576 cycles of tensor work (ncu: stall_not_selected / dispatch on every instruction of it).
+constexpr int W_PRODUCER = EPI_WARPS, W_MMA = EPI_WARPS + 1, W_MMA2 = EPI_WARPS + 2, W_ALLOC = EPI_WARPS + 3;
+constexpr int THREADS = (EPI_WARPS + 4) * 32;
 constexpr int ECAP = 1536;                      // chunks with uncertain pairs per work item held in shared memory (entry + bit mask)
 constexpr int PCAP = 2048;                      // uncertain pairs expanded per round of the deferred pass
 constexpr int SMEM_BYTES = (2 + STAGES) * TILE_BYTES + 256 + ECAP * 8 + PCAP * 4 + TILE * 4;
@@ -261,8 +264,8 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
   const TileMeta* meta = a.meta + (size_t)b * a.ct;
 
   if (tid == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1); }
-    mbar_init(BAR(TFULL), 1); mbar_init(BAR(TFULL + 1), 1);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 2); }   // EMPTY, TFULL: one commit per MMA warp
+    mbar_init(BAR(TFULL), 2); mbar_init(BAR(TFULL + 1), 2);
     mbar_init(BAR(TEMPTY), EPI_WARPS); mbar_init(BAR(TEMPTY + 1), EPI_WARPS);
     mbar_init(BAR(AFULL), 1);
     *q_n = 0;
@@ -307,8 +310,9 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
       }
       mask = mask_next;
     }
-  } else if (warp == W_MMA) {
-    // MMA issuer: converged warp, elected lane (see elect_one)
+  } else if (warp == W_MMA || warp == W_MMA2) {
+    // MMA issuers: converged warps, elected lane (see elect_one); W_MMA owns the s accumulator, W_MMA2 the n2 accumulator
+    const bool part_n = warp == W_MMA2;
     mbar_wait(BAR(AFULL), 0);
     uint32_t t = 0, it = 0;
     uint32_t mask = meta[k_begin].cam_mask;
@@ -325,12 +329,15 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
         const uint64_t da = smem_desc(smem_u32(sA) + c * TILE_BYTES, GROUP_BYTES);
         const uint64_t db = smem_desc(smem_u32(sB) + s * TILE_BYTES, GROUP_BYTES);
         if (elect_one()) {
+          if (!part_n) {
 #pragma unroll
-          for (int kk = 0; kk < ES / 16; ++kk)
-            tc_mma<KIND_L2>(tmem + buf * 256, da + (uint64_t)(16 * kk), db + (uint64_t)(16 * kk), IDESC, acc | (kk > 0));
+            for (int kk = 0; kk < ES / 16; ++kk)
+              tc_mma<KIND_L2>(tmem + buf * 256, da + (uint64_t)(16 * kk), db + (uint64_t)(16 * kk), IDESC, acc | (kk > 0));
+          } else {
 #pragma unroll
-          for (int kk = ES / 16; kk < (ES + EN) / 16; ++kk)
-            tc_mma<KIND_L2>(tmem + buf * 256 + TILE, da + (uint64_t)(16 * kk), db + (uint64_t)(16 * kk), IDESC, acc | (kk > ES / 16));
+            for (int kk = ES / 16; kk < (ES + EN) / 16; ++kk)
+              tc_mma<KIND_L2>(tmem + buf * 256 + TILE, da + (uint64_t)(16 * kk), db + (uint64_t)(16 * kk), IDESC, acc | (kk > ES / 16));
+          }
           tc_commit(BAR(EMPTY + s));
         }
         __syncwarp();
