@@ -24,7 +24,7 @@
 //                   contiguous 36 KB block
 //   warp 0        : cp.async.bulk (TMA engine, mbarrier complete_tx) of the two query tiles, then a 4-stage ring of
 //                   train tiles
-//   warp 1        : one lane issues 2 x 9 tcgen05.mma (M128 N128 K32) per train tile into a double-buffered TMEM
+//   warps 1, 3    : one lane of each issues 9 tcgen05.mma (M128 N128 K32) per train tile, one warp per query tile, into a double-buffered TMEM
 //                   accumulator (2 buffers x 2 query tiles x 128 columns = all 512 columns); tcgen05.commit releases the
 //                   shared-memory stage and publishes the accumulator
 //   warp 2        : tensor-memory allocation
@@ -218,10 +218,10 @@ __global__ void __launch_bounds__(THREADS, 1) mma_kernel(Args a) {
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
 
   if (tid == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 1); }
-    mbar_init(BAR(TFULL), 1); mbar_init(BAR(TFULL + 1), 1);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(BAR(FULL + i), 1); mbar_init(BAR(EMPTY + i), 2); }   // EMPTY, TFULL, AEMPTY: one commit per MMA warp
+    mbar_init(BAR(TFULL), 2); mbar_init(BAR(TFULL + 1), 2);
     mbar_init(BAR(TEMPTY), 8); mbar_init(BAR(TEMPTY + 1), 8);
-    mbar_init(BAR(AFULL), 1); mbar_init(BAR(AEMPTY), 1);
+    mbar_init(BAR(AFULL), 1); mbar_init(BAR(AEMPTY), 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -268,10 +268,13 @@ __global__ void __launch_bounds__(THREADS, 1) mma_kernel(Args a) {
       ++ic;
       for (int k = pre; k < it.n_iter; ++k) load_b(k);
     }
-  } else if (warp == 1) {
-    // MMA issuer: converged warp, elected lane — issued from `if (lane == 0)` every tcgen05.mma was wrapped in an
-    // elect / broadcast loop of ~13 instructions and the issuing thread, not the tensor pipe, set the pace
-    const uint64_t da0 = smem_desc(smem_u32(sA)), da1 = smem_desc(smem_u32(sA) + TILE_BYTES);
+  } else if (warp == 1 || warp == 3) {
+    // MMA issuers: converged warps, elected lane — issued from `if (lane == 0)` every tcgen05.mma was wrapped in an
+    // elect / broadcast loop of ~13 instructions and the issuing thread, not the tensor pipe, set the pace.  Two of them (on
+    // different sub-partitions), one per query tile = accumulator: the issue loop of a single warp sharing its scheduler
+    // with busy epilogue warps was still slower than the tensor pipe (found on the score engine, score_mma.cuh).
+    const int qt = warp == 1 ? 0 : 1;
+    const uint64_t da = smem_desc(smem_u32(sA) + qt * TILE_BYTES);
     uint32_t t = 0, ic = 0;
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
       const Item it = decode_item(a, a.items[w]);
@@ -287,12 +290,9 @@ __global__ void __launch_bounds__(THREADS, 1) mma_kernel(Args a) {
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < KB / 32; ++kk)
-            tc_mma<KIND>(tmem + (b * 2) * TILE, da0 + (uint64_t)(16 * kk), db + (uint64_t)(16 * kk), KIND == KIND_L2 ? IDESC_L2 : IDESC, kk > 0);
-#pragma unroll
-          for (int kk = 0; kk < KB / 32; ++kk)
-            tc_mma<KIND>(tmem + (b * 2 + 1) * TILE, da1 + (uint64_t)(16 * kk), db + (uint64_t)(16 * kk), KIND == KIND_L2 ? IDESC_L2 : IDESC, kk > 0);
-          tc_commit(BAR(EMPTY + s));    // shared-memory stage free once these MMAs have read it
-          tc_commit(BAR(TFULL + b));    // accumulators complete
+            tc_mma<KIND>(tmem + (b * 2 + qt) * TILE, da + (uint64_t)(16 * kk), db + (uint64_t)(16 * kk), KIND == KIND_L2 ? IDESC_L2 : IDESC, kk > 0);
+          tc_commit(BAR(EMPTY + s));    // shared-memory stage free once both warps' MMAs have read it
+          tc_commit(BAR(TFULL + b));    // this query tile's accumulator complete
         }
         __syncwarp();
       }
