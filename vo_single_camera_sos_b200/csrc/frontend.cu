@@ -204,6 +204,11 @@ struct sos_frontend {
   std::vector<Band> bands;
   int64_t omni_bytes_per_frame = 0;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;  // fences against the caller's stream
+  // the remap is a branch of its own in the step (nothing later in the step reads the panoramas): it fills the SMs while the
+  // many small, latency-bound kernels of the matching / RANSAC chain run
+  cudaStream_t remap_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool remap_forked = false;
   int next_stage = 0;
   // graph cache keyed on the input pointers
   struct GraphKey {
@@ -242,11 +247,25 @@ int enqueue_stage_a(sos_frontend* fe, const uint8_t* omni, const float* px_top, 
   sos_frontend_buffers& d = fe->d;
   const int B = c.batch, nb = c.n_buckets, F = c.max_feat_per_view, cap = c.cap;
   int rc;
-  // step 1 (running the remap as a parallel graph branch next to the matching chain was measured in round 1: no gain,
-  // both branches are issue-bound and fill the GPU — removed)
-  rc = sos_remap_u8(ctx, omni, B, c.src_h, c.src_w, c.channels, fe->lut, 2, c.pano_rows, c.pano_cols, c.border,
-                    c.background, d.pano);
-  if (rc) return rc;
+  // step 1, as a parallel branch (fork here, join at the end of the step).  Round 1 measured no gain from this — then the
+  // chain was three long kernels that filled the GPU; now a fifth of the step is small launches that leave most SMs idle.
+  // Per-kernel profiling runs keep it in line so that every kernel is timed alone.
+  fe->remap_forked = fe->remap_stream != nullptr && !ctx->prof;
+  if (fe->remap_forked) {
+    SOS_CUDA(cudaEventRecord(fe->ev_fork, ctx->stream));
+    SOS_CUDA(cudaStreamWaitEvent(fe->remap_stream, fe->ev_fork, 0));
+    cudaStream_t main_stream = ctx->stream;
+    ctx->stream = fe->remap_stream;
+    rc = sos_remap_u8(ctx, omni, B, c.src_h, c.src_w, c.channels, fe->lut, 2, c.pano_rows, c.pano_cols, c.border,
+                      c.background, d.pano);
+    ctx->stream = main_stream;
+    if (rc) return rc;
+    SOS_CUDA(cudaEventRecord(fe->ev_join, fe->remap_stream));
+  } else {
+    rc = sos_remap_u8(ctx, omni, B, c.src_h, c.src_w, c.channels, fe->lut, 2, c.pano_rows, c.pano_cols, c.border,
+                      c.background, d.pano);
+    if (rc) return rc;
+  }
   // step 2a: stereo matching per bucket
   const int S = B * nb;
   stereo_segments_kernel<<<sos_div_up(B, 128), 128, 0, ctx->stream>>>(boff_top, boff_bot, B, nb, F, c.max_feat_per_bucket,
@@ -338,6 +357,10 @@ int enqueue_step(sos_frontend* fe, const uint8_t* omni, const float* px_top, con
   int rc = enqueue_stage_a(fe, omni, px_top, desc_top, boff_top, px_bot, desc_bot, boff_bot);
   if (rc == SOS_OK) rc = enqueue_stage_b(fe);
   if (rc == SOS_OK && !fe->cfg.keyframe_mode) rc = enqueue_carry(fe, fe->cfg.batch);
+  if (fe->remap_forked) {   // join the remap branch (also on an error path: a capture must not end with an open fork)
+    fe->remap_forked = false;
+    SOS_CUDA(cudaStreamWaitEvent(fe->ctx->stream, fe->ev_join, 0));
+  }
   return rc;
 }
 
@@ -415,10 +438,17 @@ extern "C" int sos_frontend_create(sos_ctx* ctx, const sos_frontend_config* cfg,
   } while (0)
   // ... and its own compute stream (the caller's may be the legacy default stream, which cannot be captured); every
   // step is fenced against the caller's current stream with events, so the caller sees ordinary stream semantics
-  FE_CUDA(cudaStreamCreateWithFlags(&fe->ctx->stream, cudaStreamNonBlocking));
+  int prio_lo = 0, prio_hi = 0;   // (numerically lower = higher priority)
+  FE_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  FE_CUDA(cudaStreamCreateWithPriority(&fe->ctx->stream, cudaStreamNonBlocking, prio_hi));
   fe->ctx->own_stream = true;
   FE_CUDA(cudaEventCreateWithFlags(&fe->ev_in, cudaEventDisableTiming));
   FE_CUDA(cudaEventCreateWithFlags(&fe->ev_out, cudaEventDisableTiming));
+  // lowest priority for the remap branch: the chain's kernels take the SMs they can use first, the remap's blocks fill
+  // what is left (measured: 1.321 -> 1.303 ms per C2 step; shorter remap blocks to free SMs sooner were slower)
+  FE_CUDA(cudaStreamCreateWithPriority(&fe->remap_stream, cudaStreamNonBlocking, prio_lo));
+  FE_CUDA(cudaEventCreateWithFlags(&fe->ev_fork, cudaEventDisableTiming));
+  FE_CUDA(cudaEventCreateWithFlags(&fe->ev_join, cudaEventDisableTiming));
   fe->ctx->sm_count = ctx->sm_count;
   fe->parent = ctx;
   fe->cfg = *cfg;
@@ -470,6 +500,7 @@ extern "C" int sos_frontend_destroy(sos_frontend* fe) {
   cudaSetDevice(fe->ctx->device);
   if (fe->ctx->stream) cudaStreamSynchronize(fe->ctx->stream);
   if (fe->copy_stream) cudaStreamSynchronize(fe->copy_stream);
+  if (fe->remap_stream) cudaStreamSynchronize(fe->remap_stream);
   for (auto& g : fe->graphs) cudaGraphExecDestroy(g.exec);
   for (void* p : fe->owned) cudaFree(p);
   for (auto& s : fe->stage) {
@@ -481,6 +512,9 @@ extern "C" int sos_frontend_destroy(sos_frontend* fe) {
   if (fe->copy_stream) cudaStreamDestroy(fe->copy_stream);
   if (fe->ev_in) cudaEventDestroy(fe->ev_in);
   if (fe->ev_out) cudaEventDestroy(fe->ev_out);
+  if (fe->ev_fork) cudaEventDestroy(fe->ev_fork);
+  if (fe->ev_join) cudaEventDestroy(fe->ev_join);
+  if (fe->remap_stream) cudaStreamDestroy(fe->remap_stream);
   if (fe->ctx->own_stream && fe->ctx->stream) cudaStreamDestroy(fe->ctx->stream);
   if (fe->ctx->arena) cudaFree(fe->ctx->arena);
   delete fe->ctx;
