@@ -841,7 +841,7 @@ def main():
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
     args.steps_given = args.steps is not None
     if args.steps is None:
-        args.steps = 200 if args.impl == "ours" else 5  # ~0.5 s timed region: enough nvidia-smi clock samples
+        args.steps = 500 if args.impl == "ours" else 5  # ~0.65 s timed region: enough nvidia-smi clock samples
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args, rank, world)
