@@ -759,9 +759,20 @@ def run_c4(args, ctx, rank, world, steps=20, warm=3):
             "allreduce_ms": float(tt[1]), "allreduce_share": float(tt[1]) / float(tt[0]) if world > 1 else 0.0,
             "winner": int(winner[0]), "inliers": int(count[0]), "matches_single_gpu_full_list": verified,
             "gpu_launches": int(ll[0]),
-            "roofline": {"bound": "fp32-fma", "achieved": tfl, "peak": ffma * world, "unit": "TFLOP/s", "frac": tfl / (ffma * world),
-                         "note": "30 FLOP per (hypothesis, correspondence) executed (SASS count; equals SURVEY 8d's model) over all ranks; peak = packed-FMA microbenchmark x ranks"},
         }
+        if os.environ.get("SOS_SCORE_ENGINE", "")[:1] == "f":
+            out["roofline"] = {"bound": "fp32-fma", "achieved": tfl, "peak": ffma * world, "unit": "TFLOP/s", "frac": tfl / (ffma * world),
+                               "note": "score_kernel: 30 FLOP per (hypothesis, correspondence) executed (SASS count; equals SURVEY 8d's "
+                                       "model) over all ranks; peak = packed-FMA microbenchmark x ranks"}
+        else:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+            bf16 = float(peaks.get("bf16_tflops", 1694.3))
+            mac = pairs * 144.0 * 2.0 / (float(tt[0]) * 1e-3) / 1e12
+            out["roofline"] = {"bound": "tensor", "achieved": mac, "peak": bf16 * world, "unit": "TFLOP/s", "frac": mac / (bf16 * world),
+                               "note": "score_mma_kernel (Euclidean score as two bfloat16-split GEMMs, csrc/score_mma.cuh): 144 bf16 MACs per "
+                                       "(hypothesis, correspondence) over the WHOLE step (hypothesis generation, expansion, deferred "
+                                       "re-decisions and the winner's re-derivation included); peak = MEASURED_PEAKS bf16 x ranks",
+                               "fp32_equivalent_tflops": tfl, "ffma_peak_tflops": ffma * world}
     return out
 
 

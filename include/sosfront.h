@@ -301,8 +301,8 @@ int sos_arun_batch(sos_ctx* ctx, const double* v0, const double* v1, int n_sets,
  * best_key [n_problems] uint64 = (count+1) << 32 | (0xFFFFFFFF - (hyp_offset + h)) for cross-GPU max-reduce
  * (may be NULL), all_counts [n_problems, n_hyp] int32 (may be NULL): every hypothesis' inlier count, negative for a
  * rejected sample.
- * Scoring runs in float32 (EUCLID: FP32 pipe; BEARING: bfloat16-split GEMMs on the tensor cores, SOS_SCORE_ENGINE=fma
- * selects the FP32-pipe kernel) with a rounding-error guard band; pairs inside the band are re-decided in float64 with
+ * Scoring runs in float32 (bfloat16-split GEMMs on the tensor cores; SOS_SCORE_ENGINE=fma selects the FP32-pipe kernel)
+ * with a rounding-error guard band; pairs inside the band are re-decided in float64 with
  * the reference's formula, so counts and inlier sets equal the float64 result. */
 int sos_ransac_p3d(sos_ctx* ctx, const float* p_ref, const float* p_cur, const float* f_cur, const uint8_t* cam,
                    const int32_t* n, int n_problems, int cap, const double* rig, int n_cams, const uint32_t* hyp,
@@ -310,15 +310,16 @@ int sos_ransac_p3d(sos_ctx* ctx, const float* p_ref, const float* p_cur, const f
                    int32_t* best_hyp, int32_t* best_count, uint8_t* inlier_mask, uint64_t* best_key,
                    int32_t* all_counts);
 
-/* Diagnostics of the tensor-core engine of the bearing score (csrc/score_mma.cuh): sos_ransac_p3d with SOS_SCORE_BEARING
- * forced onto that engine, which additionally stores what the tensor cores accumulated for every (hypothesis,
- * correspondence) pair: sn [n_problems, n_hyp, ceil(cap/128)*128, 2] float32 = (s, n2) with s = f . x and n2 = |x|^2,
- * x = Rc^T (R^T (p - t) - tc) (pose_est_tools.py:150-203, 181-185).  The parity tests bound their error against float64
- * with it; the guard band of the engine is 4 x that bound. */
+/* Diagnostics of the tensor-core engine of the scores (csrc/score_mma.cuh): sos_ransac_p3d forced onto that engine, which
+ * additionally stores what the tensor cores accumulated for every (hypothesis, correspondence) pair:
+ * sn [n_problems, n_hyp, ceil(cap/128)*128, 2] float32.  SOS_SCORE_BEARING: (s, N') with s = f . x and N' = |x|^2 + 1.52 max_cam
+ * |b|^2, x = Rc^T (R^T (p - t) - tc) (pose_est_tools.py:150-203, 181-185); SOS_SCORE_EUCLID: (s', n2) with s' = |q|^2 - 2 q . x
+ * and n2 = |x|^2, q = p_cur, so that s' + n2 = |x - q|^2.  The parity tests bound their error against float64 with it; the
+ * guard band of the engine is 4 x that bound. */
 int sos_ransac_score_probe(sos_ctx* ctx, const float* p_ref, const float* p_cur, const float* f_cur, const uint8_t* cam,
                            const int32_t* n, int n_problems, int cap, const double* rig, int n_cams, const uint32_t* hyp,
-                           int n_hyp, double threshold, float* best_pose, int32_t* best_hyp, int32_t* best_count,
-                           int32_t* all_counts, float* sn);
+                           int n_hyp, int score_mode, double threshold, float* best_pose, int32_t* best_hyp,
+                           int32_t* best_count, int32_t* all_counts, float* sn);
 
 /* replaces: pyopengv.absolute_pose_noncentral_ransac(bearings, cam_idx, points, cam_offsets, cam_rotations, thr, iters)
  * (pose_est_tools.py:785) and pyopengv.absolute_pose_ransac(bearings, points, algo, thr, iters) (pose_est_tools.py:915)

@@ -16,6 +16,7 @@ pytestmark = pytest.mark.gpu
 THR = 1.0 - np.cos(np.deg2rad(5.0))
 BAND_REL = 13.0 * 2.0 ** -20 + 5e-7      # csrc/score_mma.cuh
 B2_SHIFT = 1.52
+BAND_EUCLID = 5e-6                       # csrc/score_mma.cuh
 
 
 def rig_pair(rng):
@@ -75,6 +76,36 @@ def test_accumulators_within_a_quarter_of_the_band(ctx, with_rig):
         assert np.all(pad[:, 1] > 1e29) and np.all(pad[:, 0] == 0.0)
     print(f"worst |err D| / (|p|^2 + |b|^2) = {worst:.3e}  (band {BAND_REL:.3e})")
     assert worst < BAND_REL / 4.0, worst
+
+
+def test_euclid_accumulators_within_a_quarter_of_the_band(ctx):
+    """Euclidean score: r^2 = s' + n2 from the two accumulators against float64, scaled by |p|^2 + |q|^2 + |b|^2."""
+    rng = np.random.default_rng(77)
+    n, H, B = 700, 300, 2
+    thr = 0.05
+    probs = [make_problem(rng, n - 33 * b) for b in range(B)]
+    p_ref, p_cur, f_cur, cam, ns = pack(probs, n)
+    hyp = hyp_list(rng, H)
+    counts, sn = ctx.ransac_score_probe(dev(p_ref), dev(p_cur), None, dev(ns), as_i32(hyp), thr, score_mode=0)
+    counts, sn = counts.cpu().numpy(), sn.cpu().numpy().astype(np.float64)
+    worst = 0.0
+    for b, (a, c, f, cm) in enumerate(probs):
+        a64, c64 = a.astype(np.float64), c.astype(np.float64)
+        o = ransac.ransac_p3d(a, c, hyp, "euclid", thr)
+        assert np.array_equal(np.where(counts[b] < 0, -1, counts[b]), o["counts"])
+        rows = ransac.sample_rows(hyp, len(a))
+        good = np.nonzero(o["counts"] >= 0)[0]
+        poses = ransac.arun_batch(c64[rows[good]], a64[rows[good]])
+        for h, M in zip(good, poses):
+            R, t = M[:, :3], M[:, 3]
+            x = (a64 - t) @ R                      # R^T (p_ref - t): the reference point in the current frame
+            r2 = np.sum((x - c64) ** 2, axis=1)
+            bvec = -t @ R
+            scale = np.sum(a64 * a64, axis=1) + np.sum(c64 * c64, axis=1) + float(bvec @ bvec)
+            got = sn[b, h, :len(a), 0] + sn[b, h, :len(a), 1]
+            worst = max(worst, float(np.max(np.abs(got - r2) / scale)))
+    print(f"euclid: worst |err r^2| / (|p|^2 + |q|^2 + |b|^2) = {worst:.3e}  (band {BAND_EUCLID:.3e})")
+    assert worst < BAND_EUCLID / 4.0, worst
 
 
 def counts_equal_oracle(ctx, probs, cap, hyp, rig, cams):

@@ -242,7 +242,7 @@ __device__ __forceinline__ float guard_of(int mode, float px, float py, float pz
 
 // `tc_tile` (may be NULL): the two per-camera hypothesis tiles of the tensor-core score engine this hypothesis belongs to
 // (score_mma.cuh); row `tc_row` of each gets the float64-derived features of that camera's transform.
-__device__ void make_scoring_transforms(const double* M, const Rig& rig, HypRec& rec, uint8_t* tc_tile, int tc_row) {
+__device__ void make_scoring_transforms(const double* M, const Rig& rig, HypRec& rec, uint8_t* tc_tile, int tc_row, int tc_mode) {
 #pragma unroll
   for (int i = 0; i < 12; ++i) {
     rec.pose64[i] = M[i];
@@ -277,11 +277,11 @@ __device__ void make_scoring_transforms(const double* M, const Rig& rig, HypRec&
     bmax2 = fmax(bmax2, bd[c][0] * bd[c][0] + bd[c][1] * bd[c][1] + bd[c][2] * bd[c][2]);
   }
   if (tc_tile)
-    for (int c = 0; c < rig.n_cams; ++c) score_tc::emit_hyp_row(tc_tile + (size_t)c * score_tc::TILE_BYTES, tc_row, Ad[c], bd[c], bmax2, true);
+    for (int c = 0; c < rig.n_cams; ++c) score_tc::emit_hyp_row(tc_tile + (size_t)c * score_tc::TILE_BYTES, tc_row, Ad[c], bd[c], bmax2, true, tc_mode);
 }
 
 // a failed model: NaN never passes the inlier test
-__device__ void make_failed_model(const Rig& rig, HypRec& rec, uint8_t* tc_tile, int tc_row) {
+__device__ void make_failed_model(const Rig& rig, HypRec& rec, uint8_t* tc_tile, int tc_row, int tc_mode) {
 #pragma unroll
   for (int i = 0; i < 12; ++i) {
     rec.pose[i] = CUDART_NAN_F;
@@ -290,14 +290,14 @@ __device__ void make_failed_model(const Rig& rig, HypRec& rec, uint8_t* tc_tile,
   for (int c = 0; c < RS_MAX_CAMS; ++c) {
 #pragma unroll
     for (int i = 0; i < 12; ++i) rec.xf[c][i] = CUDART_NAN_F;
-    if (tc_tile && c < rig.n_cams) score_tc::emit_hyp_row(tc_tile + (size_t)c * score_tc::TILE_BYTES, tc_row, nullptr, nullptr, 0.0, false);
+    if (tc_tile && c < rig.n_cams) score_tc::emit_hyp_row(tc_tile + (size_t)c * score_tc::TILE_BYTES, tc_row, nullptr, nullptr, 0.0, false, tc_mode);
   }
 }
 
 __global__ void __launch_bounds__(128)
 hypothesize_kernel(const float* __restrict__ p_ref, const float* __restrict__ p_cur, const int32_t* __restrict__ n_arr,
                    int cap, const uint32_t* __restrict__ hyp, int hyp_stride_problem, int n_hyp, Rig rig,
-                   HypRec* __restrict__ recs, int32_t* __restrict__ counts, uint8_t* __restrict__ tc_a) {
+                   HypRec* __restrict__ recs, int32_t* __restrict__ counts, uint8_t* __restrict__ tc_a, int tc_mode) {
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (h >= n_hyp) return;
@@ -326,8 +326,8 @@ hypothesize_kernel(const float* __restrict__ p_ref, const float* __restrict__ p_
   }
   if (ok) ok = arun_fit(v0, v1, 3, M);
   HypRec rec;
-  if (ok) make_scoring_transforms(M, rig, rec, tc_tile, (int)threadIdx.x);
-  else make_failed_model(rig, rec, tc_tile, (int)threadIdx.x);
+  if (ok) make_scoring_transforms(M, rig, rec, tc_tile, (int)threadIdx.x, tc_mode);
+  else make_failed_model(rig, rec, tc_tile, (int)threadIdx.x, tc_mode);
   recs[(size_t)b * n_hyp + h] = rec;
   counts[(size_t)b * n_hyp + h] = ok ? 0 : -(1 << 30);  // failed model: stays negative whatever is added
 }
@@ -447,7 +447,7 @@ __device__ __forceinline__ void triangle_frame(const double* T, double* F) {
 __global__ void __launch_bounds__(128)
 hypothesize_p3p_kernel(const float* __restrict__ p_ref, const float* __restrict__ f_cur, const uint8_t* __restrict__ cam,
                        const int32_t* __restrict__ n_arr, int cap, const uint32_t* __restrict__ hyp, int hyp_stride_problem,
-                       int n_hyp, Rig rig, HypRec* __restrict__ recs, int32_t* __restrict__ counts, uint8_t* __restrict__ tc_a) {
+                       int n_hyp, Rig rig, HypRec* __restrict__ recs, int32_t* __restrict__ counts, uint8_t* __restrict__ tc_a, int tc_mode) {
   const int h = blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (h >= n_hyp) return;
@@ -615,8 +615,8 @@ hypothesize_p3p_kernel(const float* __restrict__ p_ref, const float* __restrict_
     ok = best_res < CUDART_INF;
   }
   HypRec rec;
-  if (ok) make_scoring_transforms(best_M, rig, rec, tc_tile, (int)threadIdx.x);
-  else make_failed_model(rig, rec, tc_tile, (int)threadIdx.x);
+  if (ok) make_scoring_transforms(best_M, rig, rec, tc_tile, (int)threadIdx.x, tc_mode);
+  else make_failed_model(rig, rec, tc_tile, (int)threadIdx.x, tc_mode);
   recs[(size_t)b * n_hyp + h] = rec;
   counts[(size_t)b * n_hyp + h] = ok ? 0 : -(1 << 30);
 }
@@ -1062,19 +1062,20 @@ int ransac_scratch(sos_ctx* ctx, int n_problems, int n_hyp, int tc_cap, RansacSc
   return SOS_OK;
 }
 
-// The bearing score on the tensor cores (score_mma.cuh).  SOS_SCORE_ENGINE=fma keeps the FP32-pipe kernel (the only
-// engine of the Euclidean score); tests/test_gpu_ransac.py runs the bearing cases on both.
+// Both scores on the tensor cores (score_mma.cuh).  SOS_SCORE_ENGINE=fma keeps the FP32-pipe kernel; tests/test_gpu_ransac.py
+// runs every case on both.
 bool use_tensor_score(int score_mode, int n_hyp, int cap) {
-  if (score_mode != SOS_SCORE_BEARING || n_hyp < 32 || cap < 1) return false;
+  (void)score_mode;   // both scores have a tensor-core engine
+  if (n_hyp < 32 || cap < 1) return false;
   const char* e = getenv("SOS_SCORE_ENGINE");
   return !(e && e[0] == 'f');
 }
 
-int launch_score_tc(sos_ctx* ctx, const Rig& rig, const RansacScratch& s, const float* p_ref, const float* f_cur, const uint8_t* cam,
+int launch_score_tc(sos_ctx* ctx, int mode, const Rig& rig, const RansacScratch& s, const float* p_ref, const float* f_cur, const uint8_t* cam,
                     const int32_t* n, int n_problems, int cap, int n_hyp, ScoreConst k, float* probe) {
   using namespace score_tc;
   const int ht = sos_div_up(n_hyp, TILE), ct = sos_div_up(cap, TILE);
-  corr_expand_kernel<<<dim3(ct, n_problems), TILE, 0, ctx->stream>>>(p_ref, f_cur, cam, n, cap, rig.n_cams, ct, s.tc_b, s.tc_meta);
+  corr_expand_kernel<<<dim3(ct, n_problems), TILE, 0, ctx->stream>>>(mode, p_ref, f_cur, cam, n, cap, rig.n_cams, ct, s.tc_b, s.tc_meta);
   SOS_LAUNCHED_AS(ctx, "score_expand_kernel");
   Args a;
   a.a_exp = s.tc_a; a.b_exp = s.tc_b; a.meta = s.tc_meta; a.n_arr = n;
@@ -1084,16 +1085,17 @@ int launch_score_tc(sos_ctx* ctx, const Rig& rig, const RansacScratch& s, const 
   splits = splits < 1 ? 1 : (splits > sos_div_up(ct, 4) ? sos_div_up(ct, 4) : splits);
   a.splits = splits;
   a.recs = s.recs; a.counts = s.counts; a.p_ref = p_ref; a.f_cur = f_cur; a.cam = cam; a.k = k; a.probe = probe;
-  static bool attr_set[64][2] = {};     // per device: the opt-in to > 48 KB of dynamic shared memory
-  const int dev = ctx->device & 63, v = probe ? 1 : 0;
+  static bool attr_set[64][4] = {};     // per device: the opt-in to > 48 KB of dynamic shared memory
+  const bool euclid = mode == SOS_SCORE_EUCLID;
+  const int dev = ctx->device & 63, v = (probe ? 1 : 0) + (euclid ? 2 : 0);
+  auto kern = probe ? (euclid ? score_mma_kernel<true, SOS_SCORE_EUCLID> : score_mma_kernel<true, SOS_SCORE_BEARING>)
+                    : (euclid ? score_mma_kernel<false, SOS_SCORE_EUCLID> : score_mma_kernel<false, SOS_SCORE_BEARING>);
   if (!attr_set[dev][v]) {
-    if (probe) SOS_CUDA(cudaFuncSetAttribute(score_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    else SOS_CUDA(cudaFuncSetAttribute(score_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    SOS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set[dev][v] = true;
   }
   const unsigned grid = (unsigned)n_problems * ht * splits;
-  if (probe) score_mma_kernel<true><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(a, rig);
-  else score_mma_kernel<false><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(a, rig);
+  kern<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(a, rig);
   SOS_LAUNCHED_AS(ctx, "score_mma_kernel");
   return SOS_OK;
 }
@@ -1153,12 +1155,13 @@ int ransac_run(sos_ctx* ctx, int solver, const float* p_ref, const float* p_cur,
   if (n_hyp > 0) {
     dim3 hgrid(sos_div_up(n_hyp, 128), n_problems);
     if (solver == 1)
-      hypothesize_p3p_kernel<<<hgrid, 128, 0, ctx->stream>>>(p_ref, f_cur, cam, n, cap, hyp, 0, n_hyp, r, s.recs, s.counts, s.tc_a);
+      hypothesize_p3p_kernel<<<hgrid, 128, 0, ctx->stream>>>(p_ref, f_cur, cam, n, cap, hyp, 0, n_hyp, r, s.recs, s.counts, s.tc_a, score_mode);
     else
-      hypothesize_kernel<<<hgrid, 128, 0, ctx->stream>>>(p_ref, p_cur, n, cap, hyp, 0, n_hyp, r, s.recs, s.counts, s.tc_a);
+      hypothesize_kernel<<<hgrid, 128, 0, ctx->stream>>>(p_ref, p_cur, n, cap, hyp, 0, n_hyp, r, s.recs, s.counts, s.tc_a, score_mode);
     SOS_LAUNCHED_AS(ctx, "hypothesize_kernel");
     if (cap > 0 && tc) {
-      rc = launch_score_tc(ctx, r, s, p_ref, f_cur, cam, n, n_problems, cap, n_hyp, k, tc_probe);
+      rc = launch_score_tc(ctx, score_mode, r, s, p_ref, score_mode == SOS_SCORE_EUCLID ? p_cur : f_cur, cam, n, n_problems, cap, n_hyp, k,
+                           tc_probe);
       if (rc != SOS_OK) return rc;
     } else if (cap > 0) {
       dim3 sgrid(sos_div_up(n_hyp, RS_TILE_H), sos_div_up(cap, RS_CHUNK), n_problems);
@@ -1196,10 +1199,11 @@ extern "C" int sos_ransac_p3d(sos_ctx* ctx, const float* p_ref, const float* p_c
 
 extern "C" int sos_ransac_score_probe(sos_ctx* ctx, const float* p_ref, const float* p_cur, const float* f_cur,
                                       const uint8_t* cam, const int32_t* n, int n_problems, int cap, const double* rig,
-                                      int n_cams, const uint32_t* hyp, int n_hyp, double threshold, float* best_pose,
-                                      int32_t* best_hyp, int32_t* best_count, int32_t* all_counts, float* sn) {
+                                      int n_cams, const uint32_t* hyp, int n_hyp, int score_mode, double threshold,
+                                      float* best_pose, int32_t* best_hyp, int32_t* best_count, int32_t* all_counts,
+                                      float* sn) {
   SOS_CHECK_ARG(sn, "sn is NULL");
-  return ransac_run(ctx, 0, p_ref, p_cur, f_cur, cam, n, n_problems, cap, rig, n_cams, hyp, n_hyp, 0, SOS_SCORE_BEARING,
+  return ransac_run(ctx, 0, p_ref, p_cur, f_cur, cam, n, n_problems, cap, rig, n_cams, hyp, n_hyp, 0, score_mode,
                     threshold, best_pose, best_hyp, best_count, nullptr, nullptr, all_counts, sn);
 }
 
@@ -1233,7 +1237,7 @@ extern "C" int sos_ransac_p3d_eval(sos_ctx* ctx, const float* p_ref, const float
   if (rc != SOS_OK) return rc;
   dim3 hgrid(1, n_problems);
   // one hypothesis per problem, each with its own row of sample numbers (stride 3 per problem)
-  hypothesize_kernel<<<hgrid, 128, 0, ctx->stream>>>(p_ref, p_cur, n, cap, hyp_row, 3, 1, r, s.recs, s.counts, nullptr);
+  hypothesize_kernel<<<hgrid, 128, 0, ctx->stream>>>(p_ref, p_cur, n, cap, hyp_row, 3, 1, r, s.recs, s.counts, nullptr, score_mode);
   SOS_LAUNCHED_AS(ctx, "hypothesize_kernel");
   // counts[b] is 0 for a valid model and hugely negative otherwise: the mask kernel adds the inliers on top
   SOS_CUDA(cudaMemcpyAsync(count, s.counts, (size_t)n_problems * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));

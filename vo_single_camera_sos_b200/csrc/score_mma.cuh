@@ -30,6 +30,13 @@
 // w = s|s| + K_h one FFMA.  The uncertain pairs of a chunk
 // (bit mask) are queued and re-decided after the item by the scalar float32 path with ITS rigorous guard and, inside that,
 // by inlier_exact() in float64 — the same deferred path score_kernel uses — so every count equals the float64 oracle's.
+// Euclidean score (|A p + b - q| < thr, q = the current frame's 3D point): r^2 = s' + n2 with s' = |q|^2 - 2 q.(A p + b) — the
+// same 13 hypothesis features against (-2 q_i p_k, -2 q_i, |q|^2) — and the same n2 GEMM, so both scores share tiles, MMA
+// issue and pipeline; only the correspondence features and the epilogue arithmetic differ.  r^2 is a difference of large
+// terms, so its band scales with |p|^2 + |q|^2 + |b|^2, not with r^2 — but both accumulators bound those: |p|^2 <= 2 n2 +
+// 2 |b|^2 and, because r^2 = |q - x|^2 >= (|q| - |x|)^2, |q|^2 <= 2 n2 + 2 r^2.  So band <= B (4 n2 + 2 r^2 + 3 |b_h|^2) per
+// pair: t = (thr^2 - 3B|b|^2) - (1 + 2B) r^2 - 4B n2 >= 0 is a certain inlier, u = (thr^2 + 3B|b|^2) - (1 - 2B) r^2 + 4B n2 < 0
+// a certain outlier.
 // (ransac.cu includes <cuda_bf16.h> and "tc_common.cuh" at file scope before this.)
 #pragma once
 
@@ -37,7 +44,7 @@ namespace score_tc {
 using namespace sos_tc;
 
 constexpr int TILE = 128;
-constexpr int KS = 12, KN = 10;                 // features of s and n2
+constexpr int KS = 13, KN = 10;                 // features of the first accumulator (s / s') and of n2
 constexpr int ES = 80, EN = 64;                 // bf16 elements per row: 6 per feature, zero padded to a multiple of 16
 constexpr int KB = (ES + EN) * 2;               // 288 bytes per row
 constexpr int CHUNKS = KB / 16;                 // 18 core-matrix columns
@@ -61,10 +68,14 @@ constexpr float PAD_N2 = 1e30f;                 // n2 feature of a padding corre
 // sum (tests/test_gpu_score_tc.py measures 1.4e-6 for the whole expression and asserts a 4x margin)
 constexpr float BAND_REL = 13.0f * 9.5367431640625e-07f + 5e-7f;
 constexpr float BETA = 2.02f * BAND_REL;        // band <= BETA (n2 + B2_SHIFT |b|^2)
+// Euclidean score: |err r^2| <= BAND_EUCLID (|p|^2 + |q|^2 + |b|^2); tests/test_gpu_score_tc.py measures 5.8e-7 (the sum has
+// fewer and better conditioned terms than the bearing score's D) and asserts the 4x margin
+constexpr float BAND_EUCLID = 5e-6f;
 constexpr double B2_SHIFT = 1.52;               // (3 / 2 of the derivation, padded for the float32 rounding of |b|^2 in the epilogue)
 
 struct TileMeta {
   uint32_t cam_mask;   // bit c: the tile holds correspondences of camera c
+  float pq2;           // Euclidean score: max over the tile of |p|^2 + |q|^2 (the absolute part of its band)
 };
 
 // float32 -> three bfloat16 pieces with x == hi + mid + lo exactly
@@ -109,19 +120,21 @@ __device__ __forceinline__ void write_row(uint8_t* __restrict__ tile, int r, con
 // Hypothesis side, called by the hypothesize kernels: Ad (3x3 row-major) and bd of camera c in float64; bmax2 = the largest
 // |b|^2 over the cameras of the rig (the band constant must not depend on the camera of the correspondence).
 __device__ __forceinline__ void emit_hyp_row(uint8_t* __restrict__ tile, int r, const double* Ad, const double* bd, double bmax2,
-                                             bool ok) {
+                                             bool ok, int mode) {
   float fs[KS], fn[KN];
   if (ok) {
 #pragma unroll
     for (int i = 0; i < 9; ++i) fs[i] = (float)Ad[i];
 #pragma unroll
     for (int i = 0; i < 3; ++i) fs[9 + i] = (float)bd[i];
+    fs[12] = 1.f;   // against |q|^2 (Euclidean score; the bearing score's correspondence side holds 0 there)
     auto G = [&](int k, int l) { return Ad[k] * Ad[l] + Ad[3 + k] * Ad[3 + l] + Ad[6 + k] * Ad[6 + l]; };
     fn[0] = (float)G(0, 0); fn[1] = (float)G(1, 1); fn[2] = (float)G(2, 2);
     fn[3] = (float)G(0, 1); fn[4] = (float)G(0, 2); fn[5] = (float)G(1, 2);
 #pragma unroll
     for (int k = 0; k < 3; ++k) fn[6 + k] = (float)(Ad[k] * bd[0] + Ad[3 + k] * bd[1] + Ad[6 + k] * bd[2]);
-    fn[9] = (float)(bd[0] * bd[0] + bd[1] * bd[1] + bd[2] * bd[2] + B2_SHIFT * bmax2);   // N' = n2 + B2_SHIFT max |b|^2
+    // bearing score: N' = n2 + B2_SHIFT max |b|^2; Euclidean score: plain n2
+    fn[9] = (float)(bd[0] * bd[0] + bd[1] * bd[1] + bd[2] * bd[2] + (mode == SOS_SCORE_BEARING ? B2_SHIFT * bmax2 : 0.0));
   } else {
     // failed model: NaN accumulators never land inside the band (no deferred work) and its count stays hugely negative
 #pragma unroll
@@ -135,9 +148,10 @@ __device__ __forceinline__ void emit_hyp_row(uint8_t* __restrict__ tile, int r, 
 // Correspondence side: one block per 128-row tile of one problem; both camera tiles are written (the other camera's row
 // is zero), plus the tile's camera mask and max |p|^2.
 __global__ void __launch_bounds__(TILE)
-corr_expand_kernel(const float* __restrict__ p_ref, const float* __restrict__ f_cur, const uint8_t* __restrict__ cam,
+corr_expand_kernel(int mode, const float* __restrict__ p_ref, const float* __restrict__ f_cur, const uint8_t* __restrict__ cam,
                    const int32_t* __restrict__ n_arr, int cap, int n_cams, int ct, uint8_t* __restrict__ b_exp,
-                   TileMeta* __restrict__ meta) {
+                   TileMeta* __restrict__ meta) {   // f_cur: bearings (bearing score) or the current frame's points (Euclidean)
+  __shared__ float wmax[TILE / 32];
   const int b = blockIdx.y, tile = blockIdx.x, r = threadIdx.x;
   const int n = min(n_arr[b], cap);
   if (tile * TILE >= n) return;
@@ -149,6 +163,7 @@ corr_expand_kernel(const float* __restrict__ p_ref, const float* __restrict__ f_
   for (int i = 0; i < KN; ++i) fn[i] = 0.f;
   int c = 0;
   bool real = false;
+  float pq2 = 0.f;
   if (j < n) {
     const size_t o = ((size_t)b * cap + j) * 3;
     const float p[3] = {p_ref[o], p_ref[o + 1], p_ref[o + 2]}, f[3] = {f_cur[o], f_cur[o + 1], f_cur[o + 2]};
@@ -156,12 +171,19 @@ corr_expand_kernel(const float* __restrict__ p_ref, const float* __restrict__ f_
     real = isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]) && isfinite(f[0]) && isfinite(f[1]) && isfinite(f[2]);
     if (real) {
 #pragma unroll
+      const double sc = mode == SOS_SCORE_BEARING ? 1.0 : -2.0;   // bearing: f_i p_k, f_i; Euclidean: -2 q_i p_k, -2 q_i, |q|^2
+#pragma unroll
       for (int i = 0; i < 3; ++i) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) fs[i * 3 + k] = (float)((double)f[i] * (double)p[k]);
-        fs[9 + i] = f[i];
+        for (int k = 0; k < 3; ++k) fs[i * 3 + k] = (float)(sc * (double)f[i] * (double)p[k]);
+        fs[9 + i] = (float)(sc * (double)f[i]);
       }
       const double px = p[0], py = p[1], pz = p[2];
+      if (mode != SOS_SCORE_BEARING) {
+        const double q2 = (double)f[0] * f[0] + (double)f[1] * f[1] + (double)f[2] * f[2];
+        fs[12] = (float)q2;
+        pq2 = (float)(px * px + py * py + pz * pz + q2) * 1.000001f;
+      }
       fn[0] = (float)(px * px); fn[1] = (float)(py * py); fn[2] = (float)(pz * pz);
       fn[3] = (float)(2.0 * px * py); fn[4] = (float)(2.0 * px * pz); fn[5] = (float)(2.0 * py * pz);
       fn[6] = 2.f * p[0]; fn[7] = 2.f * p[1]; fn[8] = 2.f * p[2];
@@ -184,9 +206,14 @@ corr_expand_kernel(const float* __restrict__ p_ref, const float* __restrict__ f_
   }
   write_row<1>(t0 + (size_t)c * TILE_BYTES, r, fs, fn);
   if ((mask >> (c ^ 1)) & 1u) write_row<1>(t0 + (size_t)(c ^ 1) * TILE_BYTES, r, zs, zn);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) pq2 = fmaxf(pq2, __shfl_xor_sync(0xFFFFFFFFu, pq2, off));
+  if ((r & 31) == 0) wmax[r >> 5] = pq2;
+  __syncthreads();
   if (r == 0) {
     TileMeta m;
     m.cam_mask = mask;
+    m.pq2 = fmaxf(fmaxf(wmax[0], wmax[1]), fmaxf(wmax[2], wmax[3]));
     meta[(size_t)b * ct + tile] = m;
   }
 }
@@ -201,13 +228,14 @@ struct Args {
   int cap, n_hyp, ht, ct, splits;
   const HypRec* recs;
   int32_t* counts;
-  const float *p_ref, *f_cur;
+  const float *p_ref, *f_cur;   // f_cur: bearings, or the current frame's points (Euclidean score)
   const uint8_t* cam;
   ScoreConst k;
   float* probe;          // PROBE: (s, N') of every pair, [problem][hypothesis][ct * 128][2]
 };
 
 // one deferred pair, decided exactly like score_kernel's deferred pass
+template <int MODE>
 __device__ __forceinline__ int exact_pair(const Args& a, const Rig& rig, int b, int h, int j, int n) {
   if (j >= n) return 0;
   const HypRec* hr = a.recs + (size_t)b * a.n_hyp + h;
@@ -219,8 +247,8 @@ __device__ __forceinline__ int exact_pair(const Args& a, const Rig& rig, int b, 
 #pragma unroll
   for (int i = 0; i < 12; ++i) Ax[i] = __ldg(&hr->xf[c][i]);
   float D, g;
-  decision<SOS_SCORE_BEARING>(Ax, p, q, guard_of(SOS_SCORE_BEARING, p.x, p.y, p.z, q.x, q.y, q.z, a.k.thr), a.k, D, g);
-  if (fabsf(D) < g) return inlier_exact(SOS_SCORE_BEARING, hr->pose64, rig, c, p, q, a.k.thr) ? 1 : 0;
+  decision<MODE>(Ax, p, q, guard_of(MODE, p.x, p.y, p.z, q.x, q.y, q.z, a.k.thr), a.k, D, g);
+  if (fabsf(D) < g) return inlier_exact(MODE, hr->pose64, rig, c, p, q, a.k.thr) ? 1 : 0;
   return D > 0.f ? 1 : 0;
 }
 
@@ -237,7 +265,7 @@ __device__ __forceinline__ float2 pk_ffma2(float2 x, float2 y, float2 z) {
 // with cp.async.bulk, one lane of the MMA warp issues 5 + 4 tcgen05.mma (M128 N128 K16) per (tile, camera) into a double-buffered
 // accumulator pair (s: 128 columns, n2: 128 columns; 2 buffers = all 512 TMEM columns), warps 0..15 are the epilogue:
 // warp group g takes the 32-pair chunk g of every tile.
-template <bool PROBE>
+template <bool PROBE, int MODE>
 __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, const __grid_constant__ Rig rig) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -361,6 +389,12 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
         bmax2 = fmaxf(bmax2, bx * bx + by * by + bz * bz);
       }
     }
+    // Euclidean score: t = t_lo - e_lo r^2 - e_n n2,  u = t_hi - e_hi r^2 + e_n n2  (band = B (4 n2 + 2 r^2 + 3 |b|^2), padded 1 %)
+    constexpr float EB = 1.01f * BAND_EUCLID;
+    const float2 t_lo = make_float2(a.k.thr_sq - 3.f * EB * bmax2, a.k.thr_sq - 3.f * EB * bmax2);
+    const float2 t_hi = make_float2(a.k.thr_sq + 3.f * EB * bmax2, a.k.thr_sq + 3.f * EB * bmax2);
+    const float2 e_lo = make_float2(-(1.f + 2.f * EB), -(1.f + 2.f * EB)), e_hi = make_float2(-(1.f - 2.f * EB), -(1.f - 2.f * EB));
+    const float2 e_np = make_float2(4.f * EB, 4.f * EB), e_nm = make_float2(-4.f * EB, -4.f * EB);
     const float Kh = a.k.cos_min_sq * (float)B2_SHIFT * bmax2;   // D = (s|s| + Kh) - c^2 N'
     const float2 ka = make_float2(-(a.k.cos_min_sq + BETA), -(a.k.cos_min_sq + BETA));
     const float2 kb = make_float2(-(a.k.cos_min_sq - BETA), -(a.k.cos_min_sq - BETA));
@@ -385,9 +419,18 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
         for (int i = 0; i < 32; i += 2) {
           const float s0 = __int_as_float(S[i]), s1 = __int_as_float(S[i + 1]);
           const float2 n2 = make_float2(__int_as_float(N[i]), __int_as_float(N[i + 1]));
-          // s|s| folds the s > 0 test into D
-          const float2 w = make_float2(__fmaf_rn(s0, fabsf(s0), Kh), __fmaf_rn(s1, fabsf(s1), Kh));
-          const float2 t = pk_ffma2(n2, ka, w), u = pk_ffma2(n2, kb, w);
+          float2 t, u;
+          if (MODE == SOS_SCORE_BEARING) {
+            // s|s| folds the s > 0 test into D
+            const float2 w = make_float2(__fmaf_rn(s0, fabsf(s0), Kh), __fmaf_rn(s1, fabsf(s1), Kh));
+            t = pk_ffma2(n2, ka, w);
+            u = pk_ffma2(n2, kb, w);
+          } else {
+            // r^2 = s' + n2;  t >= 0: certain inlier,  u < 0: certain outlier (constants above)
+            const float2 r2 = make_float2(__fadd_rn(s0, n2.x), __fadd_rn(s1, n2.y));
+            t = pk_ffma2(n2, e_nm, pk_ffma2(r2, e_lo, t_lo));
+            u = pk_ffma2(n2, e_np, pk_ffma2(r2, e_hi, t_hi));
+          }
           mt = __funnelshift_l(__float_as_uint(t.x), mt, 1);
           mt = __funnelshift_l(__float_as_uint(t.y), mt, 1);
           mu = __funnelshift_l(__float_as_uint(u.x), mu, 1);
@@ -407,7 +450,7 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
             qmask[slot] = unsure;
           } else {   // queue full (never observed): this thread decides its uncertain pairs on its own
             for (int i = 0; i < 32; ++i)
-              if ((unsure >> (31 - i)) & 1u) cnt += exact_pair(a, rig, b, h, k * TILE + chunk * 32 + i, n);
+              if ((unsure >> (31 - i)) & 1u) cnt += exact_pair<MODE>(a, rig, b, h, k * TILE + chunk * 32 + i, n);
           }
         }
       };
@@ -437,7 +480,7 @@ __global__ void __launch_bounds__(THREADS, 1) score_mma_kernel(const Args a, con
       for (int x = te; x < min(np, PCAP); x += EPI_WARPS * 32) {
         const uint32_t v = pairs[x], ent = qent[v >> 5];
         const int k = (int)(ent >> 9), chunk = (int)((ent >> 7) & 3u), r = (int)(ent & 127u);
-        if (exact_pair(a, rig, b, ht * TILE + r, k * TILE + chunk * 32 + (int)(v & 31u), n)) atomicAdd(&fixcnt[r], 1);
+        if (exact_pair<MODE>(a, rig, b, ht * TILE + r, k * TILE + chunk * 32 + (int)(v & 31u), n)) atomicAdd(&fixcnt[r], 1);
       }
       more = np > PCAP;
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");

@@ -540,8 +540,9 @@ class Context:
             self._t(all_counts, torch.int32, "all_counts", optional=True)))
         return pose, best_hyp, best_count, mask, key
 
-    def ransac_score_probe(self, p_ref, p_cur, f_cur, n, hyp, threshold: float, cam=None, rig=None, n_cams: int = 0):
-        """Bearing score on the tensor-core engine, dumping its (s, n2) accumulators (sos_ransac_score_probe).
+    def ransac_score_probe(self, p_ref, p_cur, f_cur, n, hyp, threshold: float, cam=None, rig=None, n_cams: int = 0,
+                           score_mode: int = 1):
+        """A score on the tensor-core engine, dumping its two accumulators per pair (sos_ransac_score_probe).
         Returns (all_counts [B, H] int32, sn [B, H, ceil(cap / 128) * 128, 2] float32)."""
         self._sync_stream()
         B, cap, _ = p_ref.shape
@@ -554,9 +555,9 @@ class Context:
         sn = torch.zeros((B, H, (cap + 127) // 128 * 128, 2), dtype=torch.float32, device=self.device)
         check(self.lib.sos_ransac_score_probe(
             self._h, self._t(p_ref, torch.float32, "p_ref"), self._t(p_cur, torch.float32, "p_cur"),
-            self._t(f_cur, torch.float32, "f_cur"), self._t(cam, torch.uint8, "cam", optional=True),
-            self._t(n, torch.int32, "n"), B, cap, _ptr(r), n_cams, self._t(hyp, torch.int32, "hyp"), H, float(threshold),
-            pose.data_ptr(), best_hyp.data_ptr(), best_count.data_ptr(), counts.data_ptr(), sn.data_ptr()))
+            self._t(f_cur, torch.float32, "f_cur", optional=True), self._t(cam, torch.uint8, "cam", optional=True),
+            self._t(n, torch.int32, "n"), B, cap, _ptr(r), n_cams, self._t(hyp, torch.int32, "hyp"), H, int(score_mode),
+            float(threshold), pose.data_ptr(), best_hyp.data_ptr(), best_count.data_ptr(), counts.data_ptr(), sn.data_ptr()))
         return counts, sn
 
     def ransac_p3p(self, p_ref, f_cur, n, hyp, threshold: float, cam=None, rig=None, n_cams: int = 0, hyp_offset: int = 0,
