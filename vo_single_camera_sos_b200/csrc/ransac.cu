@@ -854,11 +854,11 @@ score_kernel(const float* __restrict__ p_ref, const float* __restrict__ q_arr, c
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 argmax_kernel(const int32_t* __restrict__ counts, const HypRec* __restrict__ recs, int n_hyp, int hyp_offset,
               float* __restrict__ best_pose, int32_t* __restrict__ best_hyp, int32_t* __restrict__ best_count,
               uint64_t* __restrict__ best_key, HypRec* __restrict__ best_rec) {
-  __shared__ unsigned long long warp_best[8];
+  __shared__ unsigned long long warp_best[32];
   const int b = blockIdx.x;
   unsigned long long best = 0ull;
   for (int h = threadIdx.x; h < n_hyp; h += blockDim.x) {
@@ -873,7 +873,7 @@ argmax_kernel(const int32_t* __restrict__ counts, const HypRec* __restrict__ rec
   if ((threadIdx.x & 31) == 0) warp_best[threadIdx.x >> 5] = best;
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w) best = max(best, warp_best[w]);
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = max(best, warp_best[w]);
     if (best_key) best_key[b] = best;
     const bool any = best != 0ull;
     const int h = any ? (int)((0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull)) - (uint32_t)hyp_offset) : -1;
@@ -1080,9 +1080,23 @@ int launch_score_tc(sos_ctx* ctx, int mode, const Rig& rig, const RansacScratch&
   Args a;
   a.a_exp = s.tc_a; a.b_exp = s.tc_b; a.meta = s.tc_meta; a.n_arr = n;
   a.cap = cap; a.n_hyp = n_hyp; a.ht = ht; a.ct = ct;
-  // enough work items for two CTAs' worth per SM; a few tiles per item at least
+  // work items = problems x hypothesis tiles x splits of the correspondence range: at least two per SM, a few tiles per item
+  // at least, and among the candidates the split with the smallest loss to the last, partly filled wave of CTAs (one CTA
+  // per SM at a time: 512 items on 148 SMs would idle 13 % of the machine, 1024 items 1 %)
+  const int max_splits = sos_div_up(ct, 4);
   int splits = sos_div_up(2 * ctx->sm_count, n_problems * ht);
-  splits = splits < 1 ? 1 : (splits > sos_div_up(ct, 4) ? sos_div_up(ct, 4) : splits);
+  splits = splits < 1 ? 1 : (splits > max_splits ? max_splits : splits);
+  {
+    double best_loss = 1e30;
+    int best = splits;
+    for (int sp = splits; sp <= max_splits && sp < splits + 8; ++sp) {
+      const long long items = (long long)n_problems * ht * sp;
+      const long long waves = (items + ctx->sm_count - 1) / ctx->sm_count;
+      const double loss = (double)(waves * ctx->sm_count) / (double)items * (1.0 + 0.01 * (sp - splits));   // (a split costs a prologue)
+      if (loss < best_loss - 1e-9) { best_loss = loss; best = sp; }
+    }
+    splits = best;
+  }
   a.splits = splits;
   a.recs = s.recs; a.counts = s.counts; a.p_ref = p_ref; a.f_cur = f_cur; a.cam = cam; a.k = k; a.probe = probe;
   static bool attr_set[64][4] = {};     // per device: the opt-in to > 48 KB of dynamic shared memory
@@ -1172,7 +1186,7 @@ int ransac_run(sos_ctx* ctx, int solver, const float* p_ref, const float* p_cur,
       if (rc != SOS_OK) return rc;
     }
   }
-  argmax_kernel<<<n_problems, 256, 0, ctx->stream>>>(s.counts, s.recs, n_hyp, hyp_offset, best_pose, best_hyp,
+  argmax_kernel<<<n_problems, n_hyp > 8192 ? 1024 : 256, 0, ctx->stream>>>(s.counts, s.recs, n_hyp, hyp_offset, best_pose, best_hyp,
                                                      best_count, best_key, s.best_rec);
   SOS_LAUNCHED_AS(ctx, "argmax_kernel");
   if (all_counts && n_hyp > 0)
