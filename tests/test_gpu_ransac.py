@@ -230,3 +230,23 @@ def test_parallel_ransac_split_single_rank(ctx):
         lo, hi = parallel.shard_hypotheses(len(hyp), 3, r)
         keys.append(int(ctx.ransac_p3d(*args, as_i32(hyp[lo:hi]), 0, 0.05, hyp_offset=lo, want_mask=False)[4][0]))
     assert parallel.unpack_key(max(keys)) == (int(full[2][0]), int(full[1][0]))
+
+
+@pytest.mark.parametrize("mode", ["euclid", "bearing"])
+def test_long_hypothesis_list(ctx, mode):
+    """More than 8192 hypotheses: the wide argmax block and several hypothesis tiles per problem; ties go to the lowest index."""
+    rng = np.random.default_rng(5 + len(mode))
+    n, H = 400, 9000
+    a, c, f, cm = make_problem(rng, n)
+    hyp = hyp_list(rng, H)
+    hyp[8500] = hyp[17]            # the same triple twice: equal counts, the lower index must win if it is the best
+    thr = 0.05 if mode == "euclid" else 1.0 - np.cos(np.deg2rad(5.0))
+    all_counts = torch.empty((1, H), dtype=torch.int32, device="cuda")
+    pose, best_hyp, best_count, mask, key = ctx.ransac_p3d(dev(a[None]), dev(c[None]), dev(np.array([n], np.int32)), as_i32(hyp),
+                                                           0 if mode == "euclid" else 1, thr, f_cur=dev(f[None]), all_counts=all_counts)
+    o = ransac.ransac_p3d(a, c, hyp, mode, thr, f_cur=f)
+    got = all_counts.cpu().numpy()[0]
+    assert np.array_equal(np.where(got < 0, -1, got), o["counts"])
+    assert int(best_hyp[0]) == o["best_hyp"] and int(best_count[0]) == o["best_count"]
+    assert np.array_equal(mask.cpu().numpy()[0].astype(bool), o["mask"])
+    assert int(key[0]) == ((o["best_count"] + 1) << 32) | (0xFFFFFFFF - o["best_hyp"])
