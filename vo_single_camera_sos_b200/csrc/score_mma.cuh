@@ -1,5 +1,5 @@
-// Tensor-core engine of the bearing-angle RANSAC score (step 5 of the SOS front-end).  Included by ransac.cu inside its
-// anonymous namespace, after HypRec / Rig / ScoreConst / decision / guard_of / inlier_exact.
+// Tensor-core engine of the RANSAC scores (step 5 of the SOS front-end): the reference's bearing-angle score, and the
+// Euclidean score of the 3D-3D stress configuration (end of this comment).  Included by ransac.cu inside its anonymous namespace, after HypRec / Rig / ScoreConst / decision / guard_of / inlier_exact.
 //
 // The score of (hypothesis h, correspondence j) is  1 - f_j . x / |x| < thr  with  x = A_h p_j + b_h  (per camera; reference
 // omnistereo/pose_est_tools.py:150-203 with the non-central correction of its comment at :181-185).  Both quantities the
@@ -12,7 +12,8 @@
 //   * every float32 feature is split exactly into three bfloat16 pieces (8 + 8 + 8 mantissa bits), and the six partial
 //     products hi*hi, hi*mid, mid*hi, hi*lo, lo*hi, mid*mid are laid out as six K columns per feature (what is dropped is
 //     below 2^-25 of the term), so a tcgen05.mma kind::f16 with float32 accumulators in tensor memory reproduces the
-//     float32 product to ~1e-7 relative; K = 12*6 -> 80 columns for s, 10*6 -> 64 columns for n2: 288 bytes per row, the same
+//     float32 product to ~1e-7 relative; K = 13*6 -> 80 columns for s (the thirteenth feature serves the Euclidean score),
+//     10*6 -> 64 columns for n2: 288 bytes per row, the same
 //     tile geometry as the Hamming engine (128 rows x 288 bytes, canonical K-major no-swizzle UMMA layout);
 //   * hypothesis features depend on the camera of the correspondence (A = Rc^T R^T, b = -Rc^T (R^T t + tc)), so each
 //     hypothesis tile exists once per camera, and each correspondence tile too (rows of the other camera are zero); a tile
@@ -52,9 +53,9 @@ constexpr int GROUP_BYTES = CHUNKS * 128;       // one 8-row group
 constexpr int TILE_BYTES = (TILE / 8) * GROUP_BYTES;   // 36864
 constexpr int STAGES = 3;
 constexpr int EPI_WARPS = 16;                   // warps 0..15: epilogue, 4 per SM sub-partition
-// The warp schedulers prefer the HIGHEST warp id, so the latency-critical single-issue roles sit above the epilogue warps:
-// as warps 0 and 1 below 16 busy epilogue warps they were starved (clock64 stamps: 780 cycles to issue four bulk copies,
-// 890 cycles for a try_wait on an already completed barrier).
+// The single-issue roles sit above the epilogue warps (measured equal to sitting below them: what slows them is sharing a
+// scheduler with four busy epilogue warps at all — clock64 stamps: 780 cycles to issue four bulk copies, 890 cycles for a
+// try_wait on an already completed barrier while the epilogue classifies).
 // Two MMA-issuing warps (on different sub-partitions): one owns the s accumulator (5 instructions per tile and camera), the
 // other the n2 accumulator (4) — the issue loop of a single warp, competing with four busy epilogue warps for issue slots,
 // took ~1800 cycles per tile for 576 cycles of tensor work (ncu: stall_not_selected / dispatch on every instruction of it).
